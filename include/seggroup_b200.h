@@ -1,0 +1,227 @@
+/* seggroup_b200 — C-ABI of the B200-native SegGroup hot path (libseggroup_b200.so).
+ *
+ * Every entry point takes plain DEVICE pointers (unless the name ends in `_host`), sizes and the
+ * CUDA stream to launch on (`void* stream` = cudaStream_t; NULL = legacy default stream).  No entry
+ * point allocates device memory: callers pass workspaces sized by the matching `*_ws_bytes`.
+ * Return value: 0 = ok, negative = `sgb_status`.  Nothing here synchronises the stream unless the
+ * comment says so; the work is complete when the stream reaches the point after the call.
+ *
+ * Index type is int32 everywhere on the device (the reference uses int64 torch tensors in
+ * seggroup/model.py and int32 in the kpconv C++ cores; the Python layer converts at the boundary).
+ * Each declaration cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef SEGGROUP_B200_H
+#define SEGGROUP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SGB_OK = 0,
+    SGB_ERR_INVALID = -1,        /* bad argument (null pointer, negative size, unsupported width) */
+    SGB_ERR_WORKSPACE = -2,      /* workspace too small */
+    SGB_ERR_CUDA = -3,           /* a CUDA runtime call failed: see sgb_last_cuda_error() */
+    SGB_ERR_UNSUPPORTED = -4,    /* shape outside what the kernels are built for */
+    SGB_ERR_NO_DEVICE = -5
+} sgb_status;
+
+int sgb_version(void);                       /* 100*major + minor */
+const char* sgb_status_string(int status);
+int sgb_last_cuda_error(void);               /* cudaError_t of the last SGB_ERR_CUDA on this thread */
+const char* sgb_last_cuda_error_string(void);
+int sgb_device_arch(int* major, int* minor); /* compute capability of the current device */
+
+/* ---------------------------------------------------------------------------------------------
+ * Primitives (used by the ops below; exported for the parity tests)
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_scan_ws_bytes(int n);
+/* out[i] = sum(in[0..i-1]); out has n+1 entries (out[n] = total).  in/out may not alias. */
+int sgb_exclusive_scan_i32(const int* in, int* out, int n, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10  segment pooling: point features -> segment features
+ * replaces seggroup/model.py:278-288 `aggregate_cluster_feature` (use_avg=False at every call
+ * site: 770, 793, 815, 834, 856, 470, 507) and the per-instance max of model.py:912-919.
+ *
+ * Segment s owns rows members[offsets[s] .. offsets[s+1]) of feat (members == NULL: identity, i.e.
+ * feat rows are already in segment-major order).  out[s,c] = max over the rows, argmax[s,c] = the
+ * FIRST maximal row in member-list order (what `torch.max(dim=0)` over the gathered rows returns,
+ * SURVEY.md 9.2 #14) as a row id of feat.  NaN propagates like torch.max.  Empty segments are
+ * invalid input.  ws: sgb_segment_pool_ws_bytes(S, C).
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_segment_pool_ws_bytes(int S, int C);
+int sgb_segment_pool_max_fwd(const float* feat, int n_rows, int C, const int* members, int n_members,
+                             const int* offsets, int S, float* out, int* argmax,
+                             void* ws, size_t ws_bytes, void* stream);
+/* grad_feat[argmax[s,c], c] += grad_out[s,c]; grad_feat must be zero-filled (or hold a running sum).
+ * Deterministic when the segments are disjoint (every row has at most one owner), as in the model. */
+int sgb_segment_pool_max_bwd(const float* grad_out, const int* argmax, int S, int C,
+                             float* grad_feat, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5/a7  kNN inside clusters
+ * replaces seggroup/model.py:30-36 `knn` and 512-522 `get_knn` (k = 20).
+ *
+ * order[cl_off[c] .. cl_off[c+1]) are the point ids of cluster c in member order.  For a cluster
+ * with n > k members: knn[p, :] = the k members with the largest score
+ *   score(i,j) = (-|x_j|^2 - (-2 * <x_i,x_j>)) - |x_i|^2
+ * evaluated exactly as torch-CPU does in fp32 (<.,.> = fma(z,z,fma(y,y,x*x)), |x|^2 = (x*x+y*y)+z*z),
+ * ranked (score desc, member position asc).  For n <= k: the first n columns are all members in
+ * member order, the remaining columns are 0 (the reference leaves them pointing at global point 0).
+ * xyz rows have `stride` floats.  knn is [N,k] int32, every row is written.
+ * ------------------------------------------------------------------------------------------- */
+int sgb_cluster_knn(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
+                    int k, int* knn, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  per-cluster fixed-size clouds
+ * replaces seggroup/model.py:398-426 `get_cluster_pointcloud`, 329-395 `farthest_point_sampling`.
+ *
+ * cloud_idx[c, 0..P) = point ids: the members tiled floor(P/n) times followed by P mod n farthest
+ * point picks (start member 0, skip_initial, fp32 squared distances without FMA contraction,
+ * argmax ties -> lowest member position, trailing picks equal to member 0 replaced by the leading
+ * picks, model.py:407-412).  status[0] |= 1 if a cluster with P mod n > 0 has all members
+ * coincident (the reference raises there).
+ * sgb_cluster_cloud_transform writes clouds[c,p,0..6): xyz minus the mean over the P rows, divided
+ * by max |xyz| of the centred cloud (model.py:421-423); rgb copied.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_cluster_cloud_ws_bytes(int N);
+int sgb_cluster_cloud_indices(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
+                              int P, int* cloud_idx, int* status, void* ws, size_t ws_bytes, void* stream);
+int sgb_cluster_cloud_transform(const float* data6, const int* cloud_idx, int S, int P, float* clouds,
+                                void* stream);
+
+/* a8  replaces seggroup/model.py:429-436 `combine_centralized_pointcloud`:
+ * x9[p] = (data6[p], xyz[p] - mean xyz of p's cluster). */
+int sgb_centralize(const float* data6, int N, const int* order, const int* cl_off, int S, float* x9,
+                   float* mean_ws /* [S,3] scratch, holds the cluster means on return */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5/a6  structural-layer MLP on the 64-point segment clouds
+ * replaces seggroup/model.py:39-80 (`get_graph_feature1`, `MLP1.forward`, BatchNorm2d in training
+ * mode = statistics of this scene over S*64*10 edge activations).
+ * clouds [S,64,6] -> feat [S,128] = cat(max over points, mean over points) of max_k lrelu(BN(W e)).
+ * W [64,6]; knn_idx [S,64,10] local neighbour ids (score desc, index asc); arg_pt [S,64] (may be NULL).
+ * stats [4][64] = (batch mean, 1/sqrt(var+eps), gamma/sqrt(var+eps), beta); var [64] biased batch
+ * variance (for the running-stat update); mom [27] fp64 input moments (kept for the backward).
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_mlp1_ws_bytes(int S);
+int sgb_mlp1_fwd(const float* clouds, int S, const float* W, const float* gamma, const float* beta,
+                 float* feat, int* knn_idx, int* arg_pt, float* stats, float* var, double* mom,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* Parameter gradients of sgb_mlp1_fwd (the clouds carry no gradient): g [S,128] -> gW [64,6], ggamma, gbeta [64].
+ * Analytic training-mode BatchNorm backward from the stored input moments (see csrc/edgeconv_bwd.cu). */
+size_t sgb_mlp1_bwd_ws_bytes(int S);
+int sgb_mlp1_bwd(const float* g, const float* clouds, const int* knn_idx, const int* arg_pt, int S, const float* W,
+                 const float* stats, const double* mom, float* gW, float* gg, float* gb,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a9  EdgeConv point MLPs over the kNN graph
+ * replaces seggroup/model.py:83-138 (`get_graph_feature2`, `MLP2.forward`, `MLP3.forward`).
+ * x9 [N,9], knn [N,20] -> out [N,64] = max_k lrelu(BN1(W1 e)) (two_layer = 0, MLP2) or
+ * max_k lrelu(BN2(W2 lrelu(BN1(W1 e)))) (two_layer = 1, MLP3), e = (x_j - x_i, x_i).
+ * argk [N,64] uint8 (may be NULL): arg-max edge per point and channel, needed by the backward.
+ * W1 [64,18], W2 [64,64]; stats1, stats2, var1, var2 as in sgb_mlp1_fwd; mom1 [189] / mom2 [4160] fp64 moments of the
+ * layer inputs (NULL allowed for mom1 when no backward follows); ctr_out [18] = centre e0 the first
+ * moments were taken about (NULL allowed).
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_edgeconv_ws_bytes(int N, int two_layer);
+int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_layer,
+                     const float* W1, const float* gamma1, const float* beta1,
+                     const float* W2, const float* gamma2, const float* beta2,
+                     float* out, unsigned char* argk, float* stats1, float* var1, double* mom1,
+                     float* stats2, float* var2, double* mom2, float* ctr_out,
+                     void* ws, size_t ws_bytes, void* stream);
+/* Parameter gradients of sgb_edgeconv_fwd followed by the point -> segment max pooling (model.py:793, 834):
+ * g [S,64] = gradient of the pooled features, arg [S,64] = arg-max point ids from sgb_segment_pool_max_fwd,
+ * argk [N,64] = arg-max edge per point and channel from the forward.  x9 carries no gradient. */
+size_t sgb_edgeconv_bwd_ws_bytes(int N, int S, int two_layer);
+int sgb_edgeconv_bwd(const float* g, const int* arg, const unsigned char* argk, int S, const float* x9, const int* knn, int N,
+                     int two_layer, const float* W1, const float* stats1, const double* mom1, const float* e0,
+                     const float* W2, const float* stats2, const double* mom2,
+                     float* gW1, float* gg1, float* gb1, float* gW2, float* gg2, float* gb2,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2  union-find state of the segment graph
+ * replaces seggroup/model.py:169-214 `DisjointSet` and the graph initialisation of 712-721.
+ * The state is SEGMENT level (a cluster is always a concatenation of whole level-1 segments,
+ * model.py:191): uf = int[6][S1] = parent, next, tail, pnum, ins, sem; member lists are linked lists of
+ * level-1 segments in the reference's list order (root = head).
+ * seg_off [S1+1] / seg_members [N]: CSR of the input over-segmentation (seg.json), segments in ascending
+ * root-point order; weak_label [N,2] int32 (sem, ins), -1 = unlabeled.
+ * Outputs: seg_of_point [N], seg_of_pos [N] (segment of the q-th entry of seg_members), uf.
+ * ------------------------------------------------------------------------------------------- */
+int sgb_scene_init(const int* seg_off, const int* seg_members, const int* weak_label, int N, int S1,
+                   int* seg_of_point, int* seg_of_pos, int* uf, void* stream);
+
+/* Level construction: replaces `get_cluster_list` (model.py:209-214) and the cluster/cluster_map/
+ * cluster_unmap dict loops (727-732, 759-768, 804-813, 845-854).  Clusters are enumerated by ascending
+ * root point id.  All outputs are sized for S1 (offset arrays S1+1); counts[0] <- number of clusters.
+ *   roots [S]: root level-1 segment of every cluster;  seg2cl [S1]: cluster of every level-1 segment;
+ *   cl_seg_off/cl_seg_list: level-1 segments of every cluster in member-list order;
+ *   cl_pt_off/order [N]: point ids of every cluster in member-list order;
+ *   cl_ins, cl_sem, cl_rootpt [S]: weak labels and root point id of every cluster. */
+size_t sgb_level_ws_bytes(int S1);
+int sgb_level_build(const int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
+                    int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
+                    int* cl_ins, int* cl_sem, int* cl_rootpt, int* counts, void* ws, size_t ws_bytes, void* stream);
+/* cluster_new_to_old (model.py:760-768): old2new [n_old]; child_off [n_new+1] / child_list [n_old] = old dense
+ * cluster ids of every new cluster, ascending. */
+size_t sgb_children_ws_bytes(int n_new);
+int sgb_level_children(const int* roots_old, int n_old, const int* seg2cl_new, int n_new, int* old2new,
+                       int* child_off, int* child_list, void* ws, size_t ws_bytes, void* stream);
+
+/* a3  replaces seggroup/model.py:291-302 `update_adj`: map both endpoints (map[old id] = new dense id
+ * < S_new), drop self edges, order each pair, unique rows in lexicographic order.  counts[1] <- rows. */
+size_t sgb_update_adj_ws_bytes(int S_new);
+int sgb_update_adj(const int* edges, int E, const int* map, int S_new, int* adj_out, int* counts,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* symmetric CSR of a unique (u<v) edge list: row i = (neighbour, edge id) sorted by neighbour.
+ * row_off [S+1], nbr/eid [2A].  Gives every gather-reduce below a fixed summation order. */
+size_t sgb_sym_csr_ws_bytes(int S);
+int sgb_sym_csr(const int* adj, int A, int S, int* row_off, int* nbr, int* eid, void* ws, size_t ws_bytes, void* stream);
+
+/* a11  replaces seggroup/model.py:269-274 `calculate_distance` (F.pairwise_distance: ||a - b + 1e-6||_2). */
+int sgb_edge_dist_fwd(const float* feat, int C, const int* adj, int A, float* dist, void* stream);
+int sgb_edge_dist_bwd(const float* feat, int S, int C, const int* adj, int A, const float* dist, const float* gdist,
+                      const int* row_off, const int* eid, float* gfeat /* += */, void* stream);
+
+/* a12  replaces seggroup/model.py:305-309 `build_similarity_matrix` + the normalise/aggregate half of
+ * `GCN.forward` (146-149): AX = ((I + sym(sims)) / rowsum) X as a CSR gather-reduce; the dense
+ * fc + relu that follows is a plain library GEMM on the caller's side. */
+int sgb_gcn_agg_fwd(const float* X, int S, int C, const float* sims, const int* row_off, const int* nbr, const int* eid,
+                    float* AX, float* rowsum, void* stream);
+int sgb_gcn_agg_bwd(const float* dAX, const float* X, const float* AX, int S, int C, const float* sims, const float* rowsum,
+                    const int* adj, int A, const int* row_off, const int* nbr, const int* eid,
+                    float* dX, float* dsims, void* stream);
+
+/* a13  replaces seggroup/model.py:218-258 `group_nearby_clusters`: edge-order replay of the unions
+ * (skip iff dist > th), then the small-cluster (< 5 points) sweeps.  adj holds dense ids of the current
+ * level, roots_cur maps them to level-1 root segments.  status |= 2 if the sweep cap was hit (the
+ * reference loops forever in that case). */
+int sgb_group_nearby(const int* adj, int A, const int* roots_cur, const float* dist, float th, int* uf, int S1,
+                     int sweep_cap, int* status, void* stream);
+
+/* a14  one iteration of phase A of seggroup/model.py:439-470 `group_unlabeled_clusters`: row arg-min of
+ * the dense distance matrix (fill 1000, first minimum), then union of every unlabeled cluster into it. */
+int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
+                             const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream);
+
+/* a16  replaces seggroup/model.py:525-605 `export_{segment,instance,semantic}_label` up to the text
+ * formatting: per raw vertex r (p = unmap[r], int64 as stored in unmap.pth; NULL = identity):
+ * seg = root point id of p's cluster, ins/sem = weak label + 1 or -1. */
+int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
+                      const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,104 @@
+"""ctypes binding of libseggroup_b200.so — the only way the Python layer reaches the CUDA kernels.
+
+Prototypes are parsed from `include/seggroup_b200.h` (single source of truth for the C-ABI), so a
+symbol declared there but missing from the library fails at load time, loudly.  There is NO fallback:
+if the library is absent or a kernel call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "seggroup_b200.h")
+LIB_PATH = os.path.join(_HERE, "lib", "libseggroup_b200.so")
+
+_SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t,
+            "long long": ctypes.c_longlong}
+
+
+class SgbError(RuntimeError):
+    pass
+
+
+def parse_header(path: str = HEADER) -> dict:
+    """{name: (restype, [(ctype, argname), ...])} for every `sgb_*` function declared in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = {}
+    for m in re.finditer(r"\b(int|size_t|const char\s*\*)\s+(sgb_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = {"int": ctypes.c_int, "size_t": ctypes.c_size_t}.get(ret, ctypes.c_char_p)
+        argl = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    argl.append((ctypes.c_void_p, a.split("*")[-1].strip()))
+                else:
+                    ty, nm = a.rsplit(" ", 1)
+                    ty = ty.replace("const ", "").strip()
+                    argl.append((_SCALARS[ty], nm))
+        protos[name] = (restype, argl)
+    return protos
+
+
+_lib = None
+_protos = None
+
+
+def load():
+    """Load the library (building it with nvcc first if the sources are newer and nvcc exists)."""
+    global _lib, _protos
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH) or os.environ.get("SGB_REBUILD"):
+        from . import build as _build
+        _build.build()
+    if not os.path.isfile(LIB_PATH):
+        raise SgbError("libseggroup_b200.so not found at %s (run `python -m seggroup_b200.build`)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    _protos = parse_header()
+    for name, (restype, argl) in _protos.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise SgbError("symbol %s declared in %s is missing from %s" % (name, HEADER, LIB_PATH)) from e
+        fn.restype = restype
+        fn.argtypes = [t for t, _ in argl]
+    _lib = lib
+    return lib
+
+
+def prototypes() -> dict:
+    load()
+    return _protos
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return ctypes.c_void_p(x)
+    return ctypes.c_void_p(x.data_ptr())          # torch tensor
+
+
+def call(name: str, *args):
+    """Call `name`; tensors / None / ints are passed as pointers where the prototype has a pointer.
+    Raises SgbError on a negative status.  Returns the int / size_t result."""
+    lib = load()
+    restype, argl = _protos[name]
+    if len(args) != len(argl):
+        raise TypeError("%s expects %d arguments (%s), got %d" % (name, len(argl), ", ".join(n for _, n in argl), len(args)))
+    conv = []
+    for (t, _), a in zip(argl, args):
+        conv.append(_ptr(a) if t is ctypes.c_void_p else a)
+    rc = getattr(lib, name)(*conv)
+    if restype is ctypes.c_int and name not in ("sgb_version", "sgb_last_cuda_error") and rc < 0:
+        msg = lib.sgb_status_string(rc).decode()
+        if rc == -3:
+            msg += ": " + lib.sgb_last_cuda_error_string().decode()
+        raise SgbError("%s failed: %s (%d)" % (name, msg, rc))
+    return rc

@@ -1,0 +1,220 @@
+// a4/a8: per-cluster fixed-size clouds (tile + farthest point sampling), their normalisation, and the
+// centred-coordinate append.  seggroup/model.py:329-395, 398-426, 429-436.
+//
+// FPS: one CTA per cluster.  (x, y, z, running min d^2) live as float4 in shared memory when the
+// cluster has <= FPS_SMEM_PTS members, else in a caller-provided global scratch indexed by member
+// position (same code path through a generic pointer).  Each pick is a block-wide arg-max with the
+// numpy tie rule (first maximum).  Squared distances use __fmul_rn/__fadd_rn in numpy's order
+// ((dx^2 + dy^2) + dz^2) so the picks are bit-identical to the reference.
+#include "common.cuh"
+
+namespace {
+constexpr int FPS_THREADS = 256;
+constexpr int FPS_SMEM_PTS = 2048;
+
+__device__ __forceinline__ float sq_dist_np(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// block-wide argmax, ties -> lowest index.  Result broadcast to all threads.
+__device__ __forceinline__ int block_argmax(float v, int i, float* s_val, int* s_idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(SGB_FULL_MASK, v, o);
+        const int oi = __shfl_xor_sync(SGB_FULL_MASK, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { s_val[w] = v; s_idx[w] = i; }
+    __syncthreads();
+    if (w == 0) {
+        v = lane < (FPS_THREADS / 32) ? s_val[lane] : -INFINITY;
+        i = lane < (FPS_THREADS / 32) ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(SGB_FULL_MASK, v, o);
+            const int oi = __shfl_xor_sync(SGB_FULL_MASK, i, o);
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+        if (lane == 0) s_idx[0] = i;
+    }
+    __syncthreads();
+    return s_idx[0];
+}
+
+__global__ void __launch_bounds__(FPS_THREADS)
+cluster_cloud_indices_kernel(const float* __restrict__ xyz, int stride, const int* __restrict__ order,
+                             const int* __restrict__ cl_off, int P, int* __restrict__ cloud_idx,
+                             float4* __restrict__ scratch, int* __restrict__ status) {
+    __shared__ float4 s_pts[FPS_SMEM_PTS];
+    __shared__ float s_val[FPS_THREADS / 32];
+    __shared__ int s_idx[FPS_THREADS / 32];
+    extern __shared__ int s_choice[];          // [rem]
+    const int c = blockIdx.x;
+    const int lo = cl_off[c], n = cl_off[c + 1] - lo;
+    int* out = cloud_idx + (size_t)c * P;
+    if (n <= 0) return;
+    const int rep = P / n, rem = P % n;
+    for (int i = threadIdx.x; i < rep * n; i += FPS_THREADS) out[i] = __ldg(order + lo + (i % n));
+    if (rem == 0) return;
+
+    float4* pts = (n <= FPS_SMEM_PTS) ? s_pts : (scratch + lo);
+    // distances to member 0
+    const float* p0 = xyz + (size_t)__ldg(order + lo) * stride;
+    float sx = __ldg(p0), sy = __ldg(p0 + 1), sz = __ldg(p0 + 2);
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += FPS_THREADS) {
+        const float* p = xyz + (size_t)__ldg(order + lo + i) * stride;
+        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+        const float d = sq_dist_np(sx, sy, sz, x, y, z);
+        pts[i] = make_float4(x, y, z, d);
+        if (d > bv) { bv = d; bi = i; }
+    }
+    int sel = block_argmax(bv, bi, s_val, s_idx);      // also orders the pts[] writes before the reads below
+    if (threadIdx.x == 0) s_choice[0] = sel;
+    // skip_initial: restart the running minimum from the first pick
+    {
+        const float4 q = pts[sel];
+        __syncthreads();
+        sx = q.x; sy = q.y; sz = q.z;
+        bv = -INFINITY; bi = 0x7fffffff;
+        for (int i = threadIdx.x; i < n; i += FPS_THREADS) {
+            float4 t = pts[i];
+            t.w = sq_dist_np(sx, sy, sz, t.x, t.y, t.z);
+            pts[i] = t;
+            if (t.w > bv) { bv = t.w; bi = i; }
+        }
+    }
+    for (int k = 1; k < rem; ++k) {
+        sel = block_argmax(bv, bi, s_val, s_idx);
+        if (threadIdx.x == 0) s_choice[k] = sel;
+        const float4 q = pts[sel];
+        __syncthreads();
+        sx = q.x; sy = q.y; sz = q.z;
+        bv = -INFINITY; bi = 0x7fffffff;
+        for (int i = threadIdx.x; i < n; i += FPS_THREADS) {
+            float4 t = pts[i];
+            const float d = sq_dist_np(sx, sy, sz, t.x, t.y, t.z);
+            if (d < t.w) { t.w = d; pts[i] = t; }
+            if (t.w > bv) { bv = t.w; bi = i; }
+        }
+    }
+    __syncthreads();
+    // trailing picks equal to member 0 are replaced by the leading picks (model.py:407-412)
+    if (threadIdx.x == 0 && s_choice[rem - 1] == 0) {
+        int j = 1;
+        for (; j <= rem; ++j) if (s_choice[rem - j] != 0) break;
+        if (j > rem) j = rem;                              // python leaves j at its last value
+        const int invalid = j - 1;
+        if (invalid == 0) atomicOr(status, 1);             // the reference raises here
+        for (int t = 0; t < invalid; ++t) s_choice[rem - invalid + t] = s_choice[t];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < rem; i += FPS_THREADS) out[rep * n + i] = __ldg(order + lo + s_choice[i]);
+}
+
+// one warp per cluster: mean over the P rows, centre, scale by max |xyz|.
+__global__ void cluster_cloud_transform_kernel(const float* __restrict__ data6, const int* __restrict__ cloud_idx,
+                                               int S, int P, float* __restrict__ clouds) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= S) return;
+    const int* idx = cloud_idx + (size_t)c * P;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int i = lane; i < P; i += 32) {
+        const float* p = data6 + (size_t)__ldg(idx + i) * 6;
+        sx += __ldg(p); sy += __ldg(p + 1); sz += __ldg(p + 2);
+    }
+    sx = sgb_warp_sum(sx); sy = sgb_warp_sum(sy); sz = sgb_warp_sum(sz);
+    const float mx = sx / (float)P, my = sy / (float)P, mz = sz / (float)P;
+    float amax = 0.f;
+    for (int i = lane; i < P; i += 32) {
+        const float* p = data6 + (size_t)__ldg(idx + i) * 6;
+        amax = fmaxf(amax, fmaxf(fabsf(__ldg(p) - mx), fmaxf(fabsf(__ldg(p + 1) - my), fabsf(__ldg(p + 2) - mz))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(SGB_FULL_MASK, amax, o));
+    for (int i = lane; i < P; i += 32) {
+        const float* p = data6 + (size_t)__ldg(idx + i) * 6;
+        float* o = clouds + ((size_t)c * P + i) * 6;
+        o[0] = (__ldg(p) - mx) / amax; o[1] = (__ldg(p + 1) - my) / amax; o[2] = (__ldg(p + 2) - mz) / amax;
+        o[3] = __ldg(p + 3); o[4] = __ldg(p + 4); o[5] = __ldg(p + 5);
+    }
+}
+
+// one warp per R positions, running sums flushed at cluster boundaries would need atomics; clusters can be
+// huge, so: pass 1 = per-cluster mean by one CTA per cluster (fp64 accumulate), pass 2 = per point write.
+__global__ void __launch_bounds__(256)
+cluster_mean_kernel(const float* __restrict__ data6, const int* __restrict__ order, const int* __restrict__ cl_off,
+                    float* __restrict__ mean /*[S,3]*/) {
+    __shared__ double s_acc[8][3];
+    const int c = blockIdx.x;
+    const int lo = cl_off[c], hi = cl_off[c + 1];
+    double ax = 0, ay = 0, az = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float* p = data6 + (size_t)__ldg(order + i) * 6;
+        ax += (double)__ldg(p); ay += (double)__ldg(p + 1); az += (double)__ldg(p + 2);
+    }
+    ax = sgb_warp_sum(ax); ay = sgb_warp_sum(ay); az = sgb_warp_sum(az);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_acc[w][0] = ax; s_acc[w][1] = ay; s_acc[w][2] = az; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int i = 0; i < 8; ++i) t += s_acc[i][threadIdx.x];
+        mean[(size_t)c * 3 + threadIdx.x] = (float)(t / (double)(hi - lo));
+    }
+}
+
+__global__ void centralize_kernel(const float* __restrict__ data6, int N, const int* __restrict__ order,
+                                  const int* __restrict__ cl_off, int S, const float* __restrict__ mean,
+                                  float* __restrict__ x9) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    const int c = sgb_upper_segment(cl_off, S, q);
+    const int pid = __ldg(order + q);
+    const float* p = data6 + (size_t)pid * 6;
+    float* o = x9 + (size_t)pid * 9;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    o[0] = x; o[1] = y; o[2] = z; o[3] = __ldg(p + 3); o[4] = __ldg(p + 4); o[5] = __ldg(p + 5);
+    o[6] = x - __ldg(mean + c * 3); o[7] = y - __ldg(mean + c * 3 + 1); o[8] = z - __ldg(mean + c * 3 + 2);
+}
+}  // namespace
+
+extern "C" size_t sgb_cluster_cloud_ws_bytes(int N) { return (size_t)(N > 0 ? N : 0) * sizeof(float4); }
+
+extern "C" int sgb_cluster_cloud_indices(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
+                                         int P, int* cloud_idx, int* status, void* ws, size_t ws_bytes, void* stream) {
+    if (S < 0 || P <= 0 || stride < 3 || N < 0) return SGB_ERR_INVALID;
+    if (S == 0) return SGB_OK;
+    if (!xyz || !order || !cl_off || !cloud_idx || !status || !ws) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_cluster_cloud_ws_bytes(N)) return SGB_ERR_WORKSPACE;
+    if ((size_t)P * sizeof(int) > 40 * 1024) return SGB_ERR_UNSUPPORTED;
+    cluster_cloud_indices_kernel<<<S, FPS_THREADS, (size_t)P * sizeof(int), (cudaStream_t)stream>>>(
+        xyz, stride, order, cl_off, P, cloud_idx, (float4*)ws, status);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_cluster_cloud_transform(const float* data6, const int* cloud_idx, int S, int P, float* clouds, void* stream) {
+    if (S < 0 || P <= 0) return SGB_ERR_INVALID;
+    if (S == 0) return SGB_OK;
+    if (!data6 || !cloud_idx || !clouds) return SGB_ERR_INVALID;
+    cluster_cloud_transform_kernel<<<sgb_div_up(S, 4), 128, 0, (cudaStream_t)stream>>>(data6, cloud_idx, S, P, clouds);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_centralize(const float* data6, int N, const int* order, const int* cl_off, int S, float* x9,
+                              float* mean_ws /*[S,3]*/, void* stream) {
+    if (N < 0 || S < 0) return SGB_ERR_INVALID;
+    if (N == 0 || S == 0) return SGB_OK;
+    if (!data6 || !order || !cl_off || !x9 || !mean_ws) return SGB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    cluster_mean_kernel<<<S, 256, 0, st>>>(data6, order, cl_off, mean_ws);
+    centralize_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, mean_ws, x9);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}

@@ -1,0 +1,381 @@
+// a9: EdgeConv point-feature blocks MLP2 / MLP3 (seggroup/model.py:83-138), forward.
+//
+//   e_ij = (x_j - x_i, x_i)  in R^18, j in knn(i) (k = 20)
+//   MLP2: out_i = max_j lrelu(BN1(W1 e_ij))
+//   MLP3: out_i = max_j lrelu(BN2(W2 lrelu(BN1(W1 e_ij))))
+// BatchNorm always uses the statistics of the current scene (the reference never calls .eval()).
+//
+// The reference materialises [1,18,N,20] and [1,64,N,20] (5 KB/point).  Here nothing edge-sized ever
+// reaches HBM: batch statistics come from second moments accumulated on the fly,
+//   pass A : G  = sum_e e' e'^T, s = sum_e e'   (e' = e centred on the scene mean, 18x18)  -> BN1 mean/var
+//   pass A2: H  = sum_e h h^T,   t = sum_e h    (h = lrelu(BN1(W1 e)), 64x64, MLP3 only)   -> BN2 mean/var
+//            because mean(W h) = W t / M and E[(W h)^2] = W H W^T / M;
+//   pass B : recompute the edge MLP from the gathered rows, max over k              -> out [N,64]
+// (the same moments are exactly what the analytic backward needs, see edgeconv_bwd.cu).
+// One warp per point, lanes own 2 of the 64 output channels; the 20 gathered edge vectors of a point are
+// staged in shared memory by lanes 0..19 (one 36 B row each) and read back as broadcast float4.
+// Partial sums are fp32 per point / per warp, fp64 across points, reduced in a fixed order (deterministic).
+// Algorithmic HBM bytes per point: 36 (x9) + 80 (knn) + 256 (out) per pass B; passes A/A2 read 116 B/point.
+#include "common.cuh"
+#include "bn_moments.cuh"
+#include "edgeconv_common.cuh"
+
+namespace sgb_ec {
+// ------------------------------------------------------------------------------------------------
+// scene mean of x9 (centre for the moment accumulation): partial sums per block, fixed-order finish
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) x9_mean_partial(const float* __restrict__ x9, int N, double* __restrict__ part) {
+    __shared__ double sm[8][9];
+    double acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] += (double)__ldg(x9 + (size_t)p * 9 + t);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = sgb_warp_sum(acc[t]);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) sm[threadIdx.x >> 5][t] = acc[t];
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += sm[w][threadIdx.x];
+        part[(size_t)blockIdx.x * 9 + threadIdx.x] = s;
+    }
+}
+__global__ void x9_mean_finish(const double* __restrict__ part, int nb, int N, float* __restrict__ ctr) {
+    if (threadIdx.x < 9) {
+        double s = 0;
+        for (int b = 0; b < nb; ++b) s += part[(size_t)b * 9 + threadIdx.x];
+        ctr[threadIdx.x] = 0.f;
+        ctr[9 + threadIdx.x] = (float)(s / (double)N);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass A: first and second moments of the (centred) edge features
+// entry n < CIN: sum e_n ; entry CIN + pair(t,u), t <= u : sum e_t e_u
+// ------------------------------------------------------------------------------------------------
+constexpr int NE1_PER_LANE = (NE1 + 31) / 32;   // 6
+
+__global__ void __launch_bounds__(WARPS * 32)
+gram1_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ ctr,
+             double* __restrict__ part /*[grid][NE1]*/) {
+    __shared__ __align__(16) float s_e[WARPS][KNN][CINP];
+    __shared__ double s_red[WARPS][NE1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float (*se)[CINP] = s_e[warp];
+    int et[NE1_PER_LANE], eu[NE1_PER_LANE];
+#pragma unroll
+    for (int m = 0; m < NE1_PER_LANE; ++m) {
+        const int n = lane + 32 * m;
+        et[m] = -1; eu[m] = 0;
+        if (n < CIN) { et[m] = n; eu[m] = -1; }
+        else if (n < NE1) {
+            int q = n - CIN, t = 0;
+            while (q >= CIN - t) { q -= CIN - t; ++t; }
+            et[m] = t; eu[m] = t + q;
+        }
+    }
+    float c9[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) c9[t] = __ldg(ctr + 9 + t);
+    double acc[NE1_PER_LANE];
+#pragma unroll
+    for (int m = 0; m < NE1_PER_LANE; ++m) acc[m] = 0.0;
+
+    for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
+        float xi[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) xi[t] = __ldg(x9 + (size_t)p * 9 + t);
+        __syncwarp();
+        stage_edges(x9, knn, p, lane, se, xi, c9);
+#pragma unroll
+        for (int m = 0; m < NE1_PER_LANE; ++m) {
+            if (et[m] >= 0) {
+                float a = 0.f;
+                if (eu[m] < 0) { for (int k = 0; k < KNN; ++k) a += se[k][et[m]]; }
+                else { for (int k = 0; k < KNN; ++k) a = fmaf(se[k][et[m]], se[k][eu[m]], a); }
+                acc[m] += (double)a;
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NE1_PER_LANE; ++m) { const int n = lane + 32 * m; if (n < NE1) s_red[warp][n] = acc[m]; }
+    __syncthreads();
+    for (int n = threadIdx.x; n < NE1; n += blockDim.x) {
+        double s = 0;
+        for (int w = 0; w < WARPS; ++w) s += s_red[w][n];
+        part[(size_t)blockIdx.x * NE1 + n] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass A2 (MLP3): moments of the hidden activations h = lrelu(BN1(W1 e)):  H = sum h h^T, t = sum h
+// lane owns rows c0, c0+1 of H (128 fp32 accumulators) + its two entries of t.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS * 32, 1)
+gram2_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ W1,
+             const float* __restrict__ stats1, double* __restrict__ part /*[grid][NE2]*/) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float (*s_e)[KNN][CINP] = reinterpret_cast<float (*)[KNN][CINP]>(smem_raw);
+    float (*s_h)[KNN][COUT] = reinterpret_cast<float (*)[KNN][COUT]>(smem_raw + sizeof(float) * WARPS * KNN * CINP);
+    double* s_acc = reinterpret_cast<double*>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT));   // [NE2]
+    float (*s_w1t)[COUT] = reinterpret_cast<float (*)[COUT]>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT) + sizeof(double) * NE2);  // [t][c]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = lane * 2;
+    for (int i = threadIdx.x; i < COUT * CIN; i += blockDim.x) s_w1t[i % CIN][i / CIN] = __ldg(W1 + i);
+    const float mean0 = stats1[c0], mean1 = stats1[c0 + 1];
+    const float sc0 = stats1[128 + c0], sc1 = stats1[128 + c0 + 1];
+    const float be0 = stats1[192 + c0], be1 = stats1[192 + c0 + 1];
+    float acc[2][COUT];
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = threadIdx.x; i < NE2; i += blockDim.x) s_acc[i] = 0.0;
+    __syncthreads();
+
+    for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
+        float xi[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) xi[t] = __ldg(x9 + (size_t)p * 9 + t);
+        __syncwarp();
+        stage_edges(x9, knn, p, lane, s_e[warp], xi, nullptr);
+#pragma unroll 2
+        for (int k = 0; k < KNN; ++k) {
+            float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < CIN; ++t) {
+                const float2 wv = *reinterpret_cast<const float2*>(&s_w1t[t][c0]);
+                const float ev = s_e[warp][k][t];
+                y0 = fmaf(wv.x, ev, y0); y1 = fmaf(wv.y, ev, y1);
+            }
+            const float h0 = lrelu(fmaf(y0 - mean0, sc0, be0));
+            const float h1 = lrelu(fmaf(y1 - mean1, sc1, be1));
+            *reinterpret_cast<float2*>(&s_h[warp][k][c0]) = make_float2(h0, h1);
+            t0 += h0; t1 += h1;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < KNN; ++k) {
+            const float2 hh = *reinterpret_cast<const float2*>(&s_h[warp][k][c0]);
+#pragma unroll
+            for (int j4 = 0; j4 < COUT / 4; ++j4) {
+                const float4 v = *reinterpret_cast<const float4*>(&s_h[warp][k][j4 * 4]);
+                acc[0][j4 * 4 + 0] = fmaf(hh.x, v.x, acc[0][j4 * 4 + 0]);
+                acc[0][j4 * 4 + 1] = fmaf(hh.x, v.y, acc[0][j4 * 4 + 1]);
+                acc[0][j4 * 4 + 2] = fmaf(hh.x, v.z, acc[0][j4 * 4 + 2]);
+                acc[0][j4 * 4 + 3] = fmaf(hh.x, v.w, acc[0][j4 * 4 + 3]);
+                acc[1][j4 * 4 + 0] = fmaf(hh.y, v.x, acc[1][j4 * 4 + 0]);
+                acc[1][j4 * 4 + 1] = fmaf(hh.y, v.y, acc[1][j4 * 4 + 1]);
+                acc[1][j4 * 4 + 2] = fmaf(hh.y, v.z, acc[1][j4 * 4 + 2]);
+                acc[1][j4 * 4 + 3] = fmaf(hh.y, v.w, acc[1][j4 * 4 + 3]);
+                if ((j4 & 3) == 3) asm volatile("" ::: "memory");   // keep at most 4 float4 loads in flight (register budget)
+            }
+        }
+    }
+    // fixed-order (warp 0, 1, ...) accumulation into the fp64 block sums
+#pragma unroll 1
+    for (int wv = 0; wv < WARPS; ++wv) {
+        __syncthreads();
+        if (warp == wv) {
+#pragma unroll
+            for (int j = 0; j < COUT; ++j) {
+                s_acc[c0 * COUT + j] += (double)acc[0][j];
+                s_acc[(c0 + 1) * COUT + j] += (double)acc[1][j];
+            }
+            s_acc[COUT * COUT + c0] += (double)t0;
+            s_acc[COUT * COUT + c0 + 1] += (double)t1;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NE2; i += blockDim.x) part[(size_t)blockIdx.x * NE2 + i] = s_acc[i];
+}
+
+__global__ void __launch_bounds__(256)
+gram2_reduce_kernel(const double* __restrict__ part, int nb, double* __restrict__ moments /*[NE2]*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NE2) return;
+    double s = 0;
+    for (int b = 0; b < nb; ++b) s += part[(size_t)b * NE2 + i];
+    moments[i] = s;
+}
+
+__global__ void __launch_bounds__(64)
+bn2_finalize_kernel(const double* __restrict__ moments, double M, const float* __restrict__ W2, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ stats, float* __restrict__ var_out) {
+    const int c = threadIdx.x;
+    if (c >= COUT) return;
+    double mean = 0, ez2 = 0;
+    for (int j = 0; j < COUT; ++j) {
+        const double wj = (double)W2[c * COUT + j];
+        mean += wj * moments[COUT * COUT + j];
+        double r = 0;
+        // H is accumulated as full 64x64 (rows by owner lane); symmetrise to cancel the fp32 asymmetry
+        for (int i = 0; i < COUT; ++i) r += 0.5 * (moments[j * COUT + i] + moments[i * COUT + j]) * (double)W2[c * COUT + i];
+        ez2 += wj * r;
+    }
+    mean /= M; ez2 /= M;
+    double var = ez2 - mean * mean;
+    if (var < 0) var = 0;
+    const double invstd = 1.0 / sqrt(var + (double)BN_EPS);
+    stats[c] = (float)mean;
+    stats[64 + c] = (float)invstd;
+    stats[128 + c] = (float)((double)gamma[c] * invstd);
+    stats[192 + c] = beta[c];
+    if (var_out) var_out[c] = (float)var;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B: out[p, c] = max_k of the edge MLP
+// ------------------------------------------------------------------------------------------------
+template <bool TWO>
+__global__ void __launch_bounds__(WARPS * 32)
+forward_max_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ W1,
+                   const float* __restrict__ stats1, const float* __restrict__ W2, const float* __restrict__ stats2,
+                   float* __restrict__ out, unsigned char* __restrict__ argk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float (*s_e)[KNN][CINP] = reinterpret_cast<float (*)[KNN][CINP]>(smem_raw);
+    float (*s_h)[KNN][COUT] = reinterpret_cast<float (*)[KNN][COUT]>(smem_raw + sizeof(float) * WARPS * KNN * CINP);
+    float (*s_w2t)[COUT] = reinterpret_cast<float (*)[COUT]>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT));  // [j][c]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = lane * 2;
+    float w[2][CIN];
+#pragma unroll
+    for (int t = 0; t < CIN; ++t) { w[0][t] = __ldg(W1 + c0 * CIN + t); w[1][t] = __ldg(W1 + (c0 + 1) * CIN + t); }
+    const float mean0 = stats1[c0], mean1 = stats1[c0 + 1];
+    const float sc0 = stats1[128 + c0], sc1 = stats1[128 + c0 + 1];
+    const float be0 = stats1[192 + c0], be1 = stats1[192 + c0 + 1];
+    float m2_0 = 0.f, m2_1 = 0.f, s2_0 = 0.f, s2_1 = 0.f, b2_0 = 0.f, b2_1 = 0.f;
+    if (TWO) {
+        for (int i = threadIdx.x; i < COUT * COUT; i += blockDim.x) {
+            const int c = i / COUT, j = i % COUT;
+            s_w2t[j][c] = __ldg(W2 + i);
+        }
+        m2_0 = stats2[c0]; m2_1 = stats2[c0 + 1];
+        s2_0 = stats2[128 + c0]; s2_1 = stats2[128 + c0 + 1];
+        b2_0 = stats2[192 + c0]; b2_1 = stats2[192 + c0 + 1];
+        __syncthreads();
+    }
+    for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
+        float xi[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) xi[t] = __ldg(x9 + (size_t)p * 9 + t);
+        __syncwarp();
+        stage_edges(x9, knn, p, lane, s_e[warp], xi, nullptr);
+        float best0 = -INFINITY, best1 = -INFINITY;
+        int bk0 = 0, bk1 = 0;
+        if (!TWO) {
+#pragma unroll
+            for (int k = 0; k < KNN; ++k) {
+                float y0, y1;
+                conv1(s_e[warp], k, w, y0, y1);
+                const float a0 = lrelu(fmaf(y0 - mean0, sc0, be0)), a1 = lrelu(fmaf(y1 - mean1, sc1, be1));
+                if (a0 > best0) { best0 = a0; bk0 = k; }
+                if (a1 > best1) { best1 = a1; bk1 = k; }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KNN; ++k) {
+                float y0, y1;
+                conv1(s_e[warp], k, w, y0, y1);
+                *reinterpret_cast<float2*>(&s_h[warp][k][c0]) =
+                    make_float2(lrelu(fmaf(y0 - mean0, sc0, be0)), lrelu(fmaf(y1 - mean1, sc1, be1)));
+            }
+            __syncwarp();
+            float z0[KNN], z1[KNN];
+#pragma unroll
+            for (int k = 0; k < KNN; ++k) { z0[k] = 0.f; z1[k] = 0.f; }
+#pragma unroll 2
+            for (int j4 = 0; j4 < COUT / 4; ++j4) {
+                const float2 wa = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 0][c0]);
+                const float2 wb = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 1][c0]);
+                const float2 wc = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 2][c0]);
+                const float2 wd = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 3][c0]);
+#pragma unroll
+                for (int k = 0; k < KNN; ++k) {
+                    const float4 v = *reinterpret_cast<const float4*>(&s_h[warp][k][j4 * 4]);
+                    z0[k] = fmaf(wa.x, v.x, z0[k]); z1[k] = fmaf(wa.y, v.x, z1[k]);
+                    z0[k] = fmaf(wb.x, v.y, z0[k]); z1[k] = fmaf(wb.y, v.y, z1[k]);
+                    z0[k] = fmaf(wc.x, v.z, z0[k]); z1[k] = fmaf(wc.y, v.z, z1[k]);
+                    z0[k] = fmaf(wd.x, v.w, z0[k]); z1[k] = fmaf(wd.y, v.w, z1[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KNN; ++k) {
+                const float a0 = lrelu(fmaf(z0[k] - m2_0, s2_0, b2_0)), a1 = lrelu(fmaf(z1[k] - m2_1, s2_1, b2_1));
+                if (a0 > best0) { best0 = a0; bk0 = k; }
+                if (a1 > best1) { best1 = a1; bk1 = k; }
+            }
+        }
+        *reinterpret_cast<float2*>(out + (size_t)p * COUT + c0) = make_float2(best0, best1);
+        if (argk) *reinterpret_cast<uchar2*>(argk + (size_t)p * COUT + c0) = make_uchar2((unsigned char)bk0, (unsigned char)bk1);
+    }
+}
+
+inline int persistent_grid(int N) {
+    int g = sgb_div_up(N, WARPS);
+    const int cap = 148 * 4;
+    return g < cap ? (g < 1 ? 1 : g) : cap;
+}
+constexpr size_t SMEM_STAGE = sizeof(float) * WARPS * KNN * (CINP + COUT);
+}  // namespace sgb_ec
+
+using namespace sgb_ec;
+
+// workspace layout (bytes): [ctr 16 floats][mean partials 256*9 dbl][gram1 partials grid*NE1 dbl][gram2 partials grid*NE2 dbl]
+extern "C" size_t sgb_edgeconv_ws_bytes(int N, int two_layer) {
+    const size_t g = (size_t)persistent_grid(N);
+    size_t b = 128 + 256 * 9 * 8 + g * NE1 * 8;
+    if (two_layer) b += (size_t)(148 * 2) * NE2 * 8;
+    return b;
+}
+
+// stats1/stats2: [4][64] float (mean, invstd, gamma*invstd, beta); var1/var2: [64] biased batch variance;
+// mom1: [189] double, mom2: [4160] double — moments kept for the backward pass (may be NULL for inference).
+extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_layer,
+                                const float* W1, const float* gamma1, const float* beta1,
+                                const float* W2, const float* gamma2, const float* beta2,
+                                float* out, unsigned char* argk, float* stats1, float* var1, double* mom1,
+                                float* stats2, float* var2, double* mom2, float* ctr_out /*[18] = e0*/,
+                                void* ws, size_t ws_bytes, void* stream) {
+    if (N <= 0) return N == 0 ? SGB_OK : SGB_ERR_INVALID;
+    if (!x9 || !knn || !W1 || !gamma1 || !beta1 || !out || !stats1 || !ws) return SGB_ERR_INVALID;
+    if (two_layer && (!W2 || !gamma2 || !beta2 || !stats2 || !mom2)) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_edgeconv_ws_bytes(N, two_layer)) return SGB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* w8 = (unsigned char*)ws;
+    float* ctr = (float*)w8;
+    double* mpart = (double*)(w8 + 128);
+    double* g1part = mpart + 256 * 9;
+    const int grid = persistent_grid(N);
+    double* g2part = g1part + (size_t)grid * NE1;
+    const double M = (double)N * KNN;
+
+    const int mb = N < 256 * 256 ? sgb_div_up(N, 256) : 256;
+    x9_mean_partial<<<mb, 256, 0, st>>>(x9, N, mpart);
+    x9_mean_finish<<<1, 32, 0, st>>>(mpart, mb, N, ctr);
+    gram1_kernel<<<grid, WARPS * 32, 0, st>>>(x9, knn, N, ctr, g1part);
+    bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(g1part, grid, M, W1, ctr, gamma1, beta1, stats1, var1, mom1);
+    if (ctr_out) SGB_CUDA(cudaMemcpyAsync(ctr_out, ctr, 18 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (two_layer) {
+        const int g2 = grid < 148 * 2 ? grid : 148 * 2;
+        const size_t sm2 = SMEM_STAGE + NE2 * sizeof(double) + sizeof(float) * CIN * COUT;
+        SGB_CUDA(cudaFuncSetAttribute(gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        gram2_kernel<<<g2, WARPS * 32, sm2, st>>>(x9, knn, N, W1, stats1, g2part);
+        gram2_reduce_kernel<<<sgb_div_up(NE2, 256), 256, 0, st>>>(g2part, g2, mom2);
+        bn2_finalize_kernel<<<1, 64, 0, st>>>(mom2, M, W2, gamma2, beta2, stats2, var2);
+        const size_t smB = SMEM_STAGE + sizeof(float) * COUT * COUT;
+        SGB_CUDA(cudaFuncSetAttribute(forward_max_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+        forward_max_kernel<true><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, W2, stats2, out, argk);
+    } else {
+        const size_t smB = sizeof(float) * WARPS * KNN * CINP;
+        SGB_CUDA(cudaFuncSetAttribute(forward_max_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+        forward_max_kernel<false><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, nullptr, nullptr, out, argk);
+    }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}

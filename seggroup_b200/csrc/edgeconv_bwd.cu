@@ -1,0 +1,356 @@
+// a9 backward: parameter gradients of MLP2 / MLP3 fused with the point -> segment max pooling.
+// (The reference gets these from autograd over materialised [1,64,N,20] tensors; inputs have no grad.)
+//
+// Upstream gradient g[s,c] reaches exactly one edge activation per (segment, channel): point
+// p* = argmax point of the pooling, edge k* = argmax edge of that point (argk, kept by the forward).
+// Training-mode BatchNorm couples every edge through the batch statistics:
+//     dy = gamma*invstd * (dv - mean(dv) - zhat * mean(dv*zhat))
+// so dW = sum_e dy_e x_e^T has a SPARSE part (the S*64 winning edges) and a DENSE part that is a linear
+// function of the layer-input moments the forward already accumulated:
+//     dW[c,:] = gamma_c invstd_c [ sum_sparse dv (x - xbar)  -  dgamma_c invstd_c (Cov_x W_c) ]
+// For MLP3 the gradient also flows into the hidden layer,
+//     dh_e = sparse_e - q0/M - Bm (h_e - hbar),   Bm = W2^T diag(gamma2 invstd2^2 dgamma2) W2 / M
+// whose dense part needs one pass over all edges (recompute h, 64x64 mat-vec, LeakyReLU mask, accumulate
+// sum dv1, sum dv1*zhat1, sum dv1 (e - ebar)^T).  Order of kernels:
+//     sparse -> [mid finalize -> dense] -> last finalize.
+// All cross-warp / cross-block sums run in a fixed order (deterministic).
+#include "edgeconv_common.cuh"
+
+namespace sgb_ec {
+constexpr int NACC = CIN + 2;          // per hidden channel: dbeta, dgamma, T[18]
+constexpr int SEG_CHUNK = 32;          // segments per sparse-kernel block
+
+// ebar[t] = mean edge feature = s'/M + e0
+__device__ __forceinline__ void load_ebar(const double* __restrict__ mom1, const float* __restrict__ e0, double M, float* s_ebar) {
+    if (threadIdx.x < CIN) s_ebar[threadIdx.x] = (float)(mom1[threadIdx.x] / M + (double)e0[threadIdx.x]);
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(WARPS * 32)
+bwd_sparse_kernel(const float* __restrict__ g /*[S,64]*/, const int* __restrict__ arg /*[S,64] point ids*/,
+                  const unsigned char* __restrict__ argk /*[N,64]*/, int S,
+                  const float* __restrict__ x9, const int* __restrict__ knn, const float* __restrict__ W1,
+                  const float* __restrict__ stats1, const double* __restrict__ mom1, const float* __restrict__ e0, double M,
+                  const float* __restrict__ W2, const float* __restrict__ stats2, const double* __restrict__ mom2,
+                  float* __restrict__ part1 /*[gridDim.y*gridDim.x][64*NACC]*/, float* __restrict__ part2 /*[gridDim.x][64][66]*/) {
+    __shared__ float s_w1t[CIN][COUT];
+    __shared__ float s_ebar[CINP];
+    __shared__ float s_red[WARPS][COUT * NACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.y * WARPS + warp;          // pooled-output channel of this warp
+    const int c0 = lane * 2;                          // hidden / layer-1 channels of this lane
+    for (int i = threadIdx.x; i < COUT * CIN; i += blockDim.x) s_w1t[i % CIN][i / CIN] = __ldg(W1 + i);
+    load_ebar(mom1, e0, M, s_ebar);
+    __syncthreads();
+    const float mu0 = stats1[c0], mu1 = stats1[c0 + 1], is0 = stats1[64 + c0], is1 = stats1[64 + c0 + 1];
+    const float ga0 = stats1[128 + c0], ga1 = stats1[128 + c0 + 1], be0 = stats1[192 + c0], be1 = stats1[192 + c0 + 1];
+    float w2a = 0.f, w2b = 0.f, mu2 = 0.f, is2 = 0.f, ga2 = 0.f, be2 = 0.f, hb0 = 0.f, hb1 = 0.f;
+    if (TWO) {
+        w2a = __ldg(W2 + c * COUT + c0); w2b = __ldg(W2 + c * COUT + c0 + 1);
+        mu2 = stats2[c]; is2 = stats2[64 + c]; ga2 = stats2[128 + c]; be2 = stats2[192 + c];
+        hb0 = (float)(mom2[COUT * COUT + c0] / M); hb1 = (float)(mom2[COUT * COUT + c0 + 1] / M);
+    }
+    float acc[2][NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+    float db2 = 0.f, dg2 = 0.f, t2a = 0.f, t2b = 0.f;
+
+    const int s_begin = blockIdx.x * SEG_CHUNK, s_end = min(S, s_begin + SEG_CHUNK);
+    for (int s = s_begin; s < s_end; ++s) {
+        const float gv = __ldg(g + (size_t)s * COUT + c);
+        const int p = __ldg(arg + (size_t)s * COUT + c);
+        const int k = argk[(size_t)p * COUT + c];
+        const int j = __ldg(knn + (size_t)p * KNN + k);
+        float e[CIN];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float xi = __ldg(x9 + (size_t)p * 9 + t);
+            e[t] = __ldg(x9 + (size_t)j * 9 + t) - xi;
+            e[9 + t] = xi;
+        }
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < CIN; ++t) {
+            const float2 w = *reinterpret_cast<const float2*>(&s_w1t[t][c0]);
+            y0 = fmaf(w.x, e[t], y0); y1 = fmaf(w.y, e[t], y1);
+        }
+        const float z0 = (y0 - mu0) * is0, z1 = (y1 - mu1) * is1;          // zhat1
+        const float v0 = fmaf(y0 - mu0, ga0, be0), v1 = fmaf(y1 - mu1, ga1, be1);
+        float dv0, dv1;
+        if (TWO) {
+            const float h0 = lrelu(v0), h1 = lrelu(v1);
+            const float y2 = sgb_warp_sum(fmaf(w2a, h0, w2b * h1));
+            const float zz = (y2 - mu2) * is2;
+            const float v2 = fmaf(y2 - mu2, ga2, be2);
+            const float dv2 = gv * (v2 > 0.f ? 1.f : SLOPE);
+            db2 += dv2; dg2 = fmaf(dv2, zz, dg2);
+            t2a = fmaf(dv2, h0 - hb0, t2a); t2b = fmaf(dv2, h1 - hb1, t2b);
+            const float dy2 = ga2 * dv2;                                    // gamma2*invstd2*dv2 (stats2[128+c] = gamma*invstd)
+            dv0 = w2a * dy2 * (v0 > 0.f ? 1.f : SLOPE);
+            dv1 = w2b * dy2 * (v1 > 0.f ? 1.f : SLOPE);
+        } else {
+            dv0 = (c0 == c) ? gv * (v0 > 0.f ? 1.f : SLOPE) : 0.f;
+            dv1 = (c0 + 1 == c) ? gv * (v1 > 0.f ? 1.f : SLOPE) : 0.f;
+        }
+        acc[0][0] += dv0; acc[1][0] += dv1;
+        acc[0][1] = fmaf(dv0, z0, acc[0][1]); acc[1][1] = fmaf(dv1, z1, acc[1][1]);
+#pragma unroll
+        for (int t = 0; t < CIN; ++t) {
+            const float d = e[t] - s_ebar[t];
+            acc[0][2 + t] = fmaf(dv0, d, acc[0][2 + t]);
+            acc[1][2 + t] = fmaf(dv1, d, acc[1][2 + t]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { s_red[warp][c0 * NACC + i] = acc[0][i]; s_red[warp][(c0 + 1) * NACC + i] = acc[1][i]; }
+    __syncthreads();
+    float* dst = part1 + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (COUT * NACC);
+    for (int i = threadIdx.x; i < COUT * NACC; i += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) sum += s_red[w][i];
+        dst[i] = sum;
+    }
+    if (TWO) {
+        float* d2 = part2 + ((size_t)blockIdx.x * COUT + c) * 66;
+        d2[c0] = t2a; d2[c0 + 1] = t2b;
+        if (lane == 0) { d2[64] = db2; d2[65] = dg2; }
+    }
+}
+
+// MLP3: reduce the layer-2 partials, emit dW2 / dgamma2 / dbeta2 and the dense-pass coefficients Bm [64][64], r [64].
+__global__ void __launch_bounds__(256)
+bwd_mid_kernel(const float* __restrict__ part2, int nchunk, double M, const float* __restrict__ W2, const float* __restrict__ stats2,
+               const double* __restrict__ mom2, float* __restrict__ gW2, float* __restrict__ gg2, float* __restrict__ gb2,
+               float* __restrict__ coef /*[64*64 + 64]*/) {
+    __shared__ double s_t2[COUT][COUT + 2];     // [c][j], [c][64] = dbeta2, [c][65] = dgamma2
+    __shared__ double s_hbar[COUT];
+    __shared__ double s_d[COUT];                // D_c = gamma2 invstd2^2 dgamma2
+    __shared__ double s_q[COUT];                // gamma2 invstd2 dbeta2
+    for (int i = threadIdx.x; i < COUT * 66; i += blockDim.x) {
+        double s = 0;
+        for (int b = 0; b < nchunk; ++b) s += (double)part2[(size_t)b * COUT * 66 + i];
+        s_t2[i / 66][i % 66] = s;
+    }
+    if (threadIdx.x < COUT) s_hbar[threadIdx.x] = mom2[COUT * COUT + threadIdx.x] / M;
+    __syncthreads();
+    if (threadIdx.x < COUT) {
+        const int c = threadIdx.x;
+        const double gi = (double)stats2[128 + c];                // gamma*invstd
+        s_d[c] = gi * (double)stats2[64 + c] * s_t2[c][65];
+        s_q[c] = gi * s_t2[c][64];
+        gb2[c] = (float)s_t2[c][64];
+        gg2[c] = (float)s_t2[c][65];
+    }
+    __syncthreads();
+    // Bm[i][j] = (1/M) sum_c W2[c][i] D_c W2[c][j]
+    for (int ij = threadIdx.x; ij < COUT * COUT; ij += blockDim.x) {
+        const int i = ij / COUT, j = ij % COUT;
+        double s = 0;
+        for (int c = 0; c < COUT; ++c) s += (double)W2[c * COUT + i] * s_d[c] * (double)W2[c * COUT + j];
+        coef[ij] = (float)(s / M);
+    }
+    // dW2[c][j] = gamma2 invstd2 [ T2[c][j] - dgamma2 invstd2 sum_i CovH[j][i] W2[c][i] ]
+    for (int cj = threadIdx.x; cj < COUT * COUT; cj += blockDim.x) {
+        const int c = cj / COUT, j = cj % COUT;
+        double r = 0;
+        for (int i = 0; i < COUT; ++i) {
+            const double cov = 0.5 * (mom2[j * COUT + i] + mom2[i * COUT + j]) / M - s_hbar[j] * s_hbar[i];
+            r += cov * (double)W2[c * COUT + i];
+        }
+        gW2[cj] = (float)((double)stats2[128 + c] * (s_t2[c][j] - s_t2[c][65] * (double)stats2[64 + c] * r));
+    }
+    __syncthreads();
+    // r[j] = -q0'[j]/M + (Bm hbar)[j],  q0'[j] = sum_c W2[c][j] gamma2 invstd2 dbeta2   (Bm read back from coef)
+    if (threadIdx.x < COUT) {
+        const int j = threadIdx.x;
+        double q0 = 0, bh = 0;
+        for (int c = 0; c < COUT; ++c) q0 += (double)W2[c * COUT + j] * s_q[c];
+        for (int i = 0; i < COUT; ++i) bh += (double)coef[j * COUT + i] * s_hbar[i];
+        coef[COUT * COUT + j] = (float)(-q0 / M + bh);
+    }
+}
+
+// MLP3 dense pass over all edges: dv1 = (r - Bm h) * lrelu'(v1); accumulate sum dv1, sum dv1 zhat1, sum dv1 (e - ebar)
+__global__ void __launch_bounds__(WARPS * 32)
+bwd_dense_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ W1,
+                 const float* __restrict__ stats1, const double* __restrict__ mom1, const float* __restrict__ e0, double M,
+                 const float* __restrict__ coef, float* __restrict__ partD /*[grid][64*NACC]*/) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float (*s_e)[KNN][CINP] = reinterpret_cast<float (*)[KNN][CINP]>(smem_raw);
+    float (*s_h)[KNN][COUT] = reinterpret_cast<float (*)[KNN][COUT]>(smem_raw + sizeof(float) * WARPS * KNN * CINP);
+    float (*s_bm)[COUT] = reinterpret_cast<float (*)[COUT]>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT));   // symmetric
+    float* s_ebar = reinterpret_cast<float*>(smem_raw + sizeof(float) * (WARPS * KNN * (CINP + COUT) + COUT * COUT));  // [CINP]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = lane * 2;
+    float w[2][CIN];
+#pragma unroll
+    for (int t = 0; t < CIN; ++t) { w[0][t] = __ldg(W1 + c0 * CIN + t); w[1][t] = __ldg(W1 + (c0 + 1) * CIN + t); }
+    const float mu0 = stats1[c0], mu1 = stats1[c0 + 1], is0 = stats1[64 + c0], is1 = stats1[64 + c0 + 1];
+    const float ga0 = stats1[128 + c0], ga1 = stats1[128 + c0 + 1], be0 = stats1[192 + c0], be1 = stats1[192 + c0 + 1];
+    for (int i = threadIdx.x; i < COUT * COUT; i += blockDim.x) (&s_bm[0][0])[i] = __ldg(coef + i);
+    load_ebar(mom1, e0, M, s_ebar);
+    const float r0 = __ldg(coef + COUT * COUT + c0), r1 = __ldg(coef + COUT * COUT + c0 + 1);
+    __syncthreads();
+    float acc[2][NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+
+    for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
+        float xi[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) xi[t] = __ldg(x9 + (size_t)p * 9 + t);
+        __syncwarp();
+        stage_edges(x9, knn, p, lane, s_e[warp], xi, nullptr);
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) {
+            float y0, y1;
+            conv1(s_e[warp], k, w, y0, y1);
+            *reinterpret_cast<float2*>(&s_h[warp][k][c0]) =
+                make_float2(lrelu(fmaf(y0 - mu0, ga0, be0)), lrelu(fmaf(y1 - mu1, ga1, be1)));
+        }
+        __syncwarp();
+        float a0[KNN], a1[KNN];
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+#pragma unroll 2
+        for (int j4 = 0; j4 < COUT / 4; ++j4) {
+            const float2 ba = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 0][c0]);
+            const float2 bb = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 1][c0]);
+            const float2 bc = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 2][c0]);
+            const float2 bd = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 3][c0]);
+#pragma unroll
+            for (int k = 0; k < KNN; ++k) {
+                const float4 h = *reinterpret_cast<const float4*>(&s_h[warp][k][j4 * 4]);
+                a0[k] = fmaf(ba.x, h.x, a0[k]); a1[k] = fmaf(ba.y, h.x, a1[k]);
+                a0[k] = fmaf(bb.x, h.y, a0[k]); a1[k] = fmaf(bb.y, h.y, a1[k]);
+                a0[k] = fmaf(bc.x, h.z, a0[k]); a1[k] = fmaf(bc.y, h.z, a1[k]);
+                a0[k] = fmaf(bd.x, h.w, a0[k]); a1[k] = fmaf(bd.y, h.w, a1[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) {
+            float y0, y1;
+            conv1(s_e[warp], k, w, y0, y1);        // recomputed: cheaper than keeping 80 more registers live
+            const float z0 = (y0 - mu0) * is0, z1 = (y1 - mu1) * is1;
+            const float v0 = fmaf(y0 - mu0, ga0, be0), v1 = fmaf(y1 - mu1, ga1, be1);
+            const float dv0 = (r0 - a0[k]) * (v0 > 0.f ? 1.f : SLOPE), dv1 = (r1 - a1[k]) * (v1 > 0.f ? 1.f : SLOPE);
+            acc[0][0] += dv0; acc[1][0] += dv1;
+            acc[0][1] = fmaf(dv0, z0, acc[0][1]); acc[1][1] = fmaf(dv1, z1, acc[1][1]);
+#pragma unroll
+            for (int t4 = 0; t4 < CINP / 4; ++t4) {
+                const float4 ev = *reinterpret_cast<const float4*>(&s_e[warp][k][t4 * 4]);
+                const float e4[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = t4 * 4 + q;
+                    if (t < CIN) {
+                        const float d = e4[q] - s_ebar[t];
+                        acc[0][2 + t] = fmaf(dv0, d, acc[0][2 + t]);
+                        acc[1][2 + t] = fmaf(dv1, d, acc[1][2 + t]);
+                    }
+                }
+            }
+        }
+    }
+    // block reduction in fixed warp order (reuse the s_h staging area: WARPS*KNN*COUT >= WARPS*COUT*NACC)
+    __syncthreads();
+    float* s_red = &s_h[0][0][0];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        s_red[warp * (COUT * NACC) + c0 * NACC + i] = acc[0][i];
+        s_red[warp * (COUT * NACC) + (c0 + 1) * NACC + i] = acc[1][i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * NACC; i += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < WARPS; ++wv) sum += s_red[wv * (COUT * NACC) + i];
+        partD[(size_t)blockIdx.x * (COUT * NACC) + i] = sum;
+    }
+}
+
+// dW1 / dgamma1 / dbeta1 from the accumulated (sparse + dense) sums
+__global__ void __launch_bounds__(64)
+bwd_last_kernel(const float* __restrict__ part1, int n1, const float* __restrict__ partD, int nD, double M,
+                const float* __restrict__ W1, const float* __restrict__ stats1, const double* __restrict__ mom1,
+                float* __restrict__ gW1, float* __restrict__ gg1, float* __restrict__ gb1) {
+    __shared__ double s_cov[CIN][CIN];
+    for (int n = threadIdx.x; n < CIN * (CIN + 1) / 2; n += blockDim.x) {
+        int q = n, t = 0;
+        while (q >= CIN - t) { q -= CIN - t; ++t; }
+        const int u = t + q;
+        const double cv = mom1[CIN + n] / M - (mom1[t] / M) * (mom1[u] / M);
+        s_cov[t][u] = cv; s_cov[u][t] = cv;
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (c >= COUT) return;
+    double a[NACC];
+    for (int i = 0; i < NACC; ++i) {
+        double s = 0;
+        for (int b = 0; b < n1; ++b) s += (double)part1[(size_t)b * (COUT * NACC) + c * NACC + i];
+        for (int b = 0; b < nD; ++b) s += (double)partD[(size_t)b * (COUT * NACC) + c * NACC + i];
+        a[i] = s;
+    }
+    gb1[c] = (float)a[0];
+    gg1[c] = (float)a[1];
+    const double gi = (double)stats1[128 + c], is = (double)stats1[64 + c];
+    for (int t = 0; t < CIN; ++t) {
+        double r = 0;
+        for (int u = 0; u < CIN; ++u) r += s_cov[t][u] * (double)W1[c * CIN + u];
+        gW1[c * CIN + t] = (float)(gi * (a[2 + t] - a[1] * is * r));
+    }
+}
+
+inline int bwd_dense_grid(int N) {
+    int g = sgb_div_up(N, WARPS);
+    return g < 148 * 2 ? (g < 1 ? 1 : g) : 148 * 2;
+}
+}  // namespace sgb_ec
+
+using namespace sgb_ec;
+
+extern "C" size_t sgb_edgeconv_bwd_ws_bytes(int N, int S, int two_layer) {
+    const size_t nchunk = (size_t)sgb_div_up(S, SEG_CHUNK);
+    size_t b = nchunk * 8 * COUT * NACC * sizeof(float);
+    if (two_layer) b += nchunk * COUT * 66 * sizeof(float) + (COUT * COUT + COUT) * sizeof(float) + (size_t)bwd_dense_grid(N) * COUT * NACC * sizeof(float);
+    return b + 256;
+}
+
+// g [S,64] gradient of the pooled features; arg [S,64] argmax point ids (sgb_segment_pool_max_fwd);
+// argk [N,64] argmax edge per point/channel (sgb_edgeconv_fwd); stats/mom/e0 as returned by the forward.
+// Outputs: gW1 [64,18], gg1/gb1 [64] (+ gW2 [64,64], gg2/gb2 [64] when two_layer).
+extern "C" int sgb_edgeconv_bwd(const float* g, const int* arg, const unsigned char* argk, int S, const float* x9, const int* knn, int N,
+                                int two_layer, const float* W1, const float* stats1, const double* mom1, const float* e0,
+                                const float* W2, const float* stats2, const double* mom2,
+                                float* gW1, float* gg1, float* gb1, float* gW2, float* gg2, float* gb2,
+                                void* ws, size_t ws_bytes, void* stream) {
+    if (S <= 0 || N <= 0) return SGB_ERR_INVALID;
+    if (!g || !arg || !argk || !x9 || !knn || !W1 || !stats1 || !mom1 || !e0 || !gW1 || !gg1 || !gb1 || !ws) return SGB_ERR_INVALID;
+    if (two_layer && (!W2 || !stats2 || !mom2 || !gW2 || !gg2 || !gb2)) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_edgeconv_bwd_ws_bytes(N, S, two_layer)) return SGB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nchunk = sgb_div_up(S, SEG_CHUNK);
+    const double M = (double)N * KNN;
+    float* part1 = (float*)ws;
+    float* part2 = part1 + (size_t)nchunk * 8 * COUT * NACC;
+    dim3 grid(nchunk, COUT / WARPS);
+    if (!two_layer) {
+        bwd_sparse_kernel<false><<<grid, WARPS * 32, 0, st>>>(g, arg, argk, S, x9, knn, W1, stats1, mom1, e0, M, nullptr, nullptr, nullptr,
+                                                             part1, nullptr);
+        bwd_last_kernel<<<1, 64, 0, st>>>(part1, nchunk * 8, nullptr, 0, M, W1, stats1, mom1, gW1, gg1, gb1);
+    } else {
+        float* coef = part2 + (size_t)nchunk * COUT * 66;
+        float* partD = coef + COUT * COUT + COUT;
+        const int gd = bwd_dense_grid(N);
+        bwd_sparse_kernel<true><<<grid, WARPS * 32, 0, st>>>(g, arg, argk, S, x9, knn, W1, stats1, mom1, e0, M, W2, stats2, mom2, part1, part2);
+        bwd_mid_kernel<<<1, 256, 0, st>>>(part2, nchunk, M, W2, stats2, mom2, gW2, gg2, gb2, coef);
+        const size_t sm = sizeof(float) * (WARPS * KNN * (CINP + COUT) + COUT * COUT + CINP);
+        SGB_CUDA(cudaFuncSetAttribute(bwd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        bwd_dense_kernel<<<gd, WARPS * 32, sm, st>>>(x9, knn, N, W1, stats1, mom1, e0, M, coef, partD);
+        bwd_last_kernel<<<1, 64, 0, st>>>(part1, nchunk * 8, partD, gd, M, W1, stats1, mom1, gW1, gg1, gb1);
+    }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}

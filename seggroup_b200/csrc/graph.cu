@@ -1,0 +1,592 @@
+// a2/a3/a11/a12/a13/a14/a16: the segment graph — union-find state, level construction, adjacency
+// update, edge distances, CSR GCN aggregation, order-exact grouping, label export.
+// seggroup/model.py:169-258, 262-316, 439-509, 525-605.
+//
+// The reference keeps a POINT-level DisjointSet with explicit member lists; a cluster is always a
+// concatenation of whole level-1 segments (model.py:191), so the device state is SEGMENT-level:
+//   uf = int[6][S1]: parent, next, tail (member lists as linked lists of level-1 segments, the root is
+//   the head of its list), pnum (point count), ins, sem (weak labels of the root).
+// `union(a, b)` (model.py:181-192): veto if both labelled and different; root = b; b's list += a's list.
+// Grouping is inherently sequential in edge order: it runs on ONE thread of one CTA
+// with the state in L1/L2, after a parallel filter has discarded the edges that cannot matter.
+#include "common.cuh"
+
+namespace {
+struct UF {
+    int* parent; int* next; int* tail; int* pnum; int* ins; int* sem;
+    __host__ __device__ UF(int* base, int S) : parent(base), next(base + S), tail(base + 2 * S), pnum(base + 3 * S),
+                                               ins(base + 4 * S), sem(base + 5 * S) {}
+};
+
+__device__ __forceinline__ int uf_find(const UF& u, int s) {            // path halving (single writer)
+    while (u.parent[s] != s) { u.parent[s] = u.parent[u.parent[s]]; s = u.parent[s]; }
+    return s;
+}
+__device__ __forceinline__ int uf_find_ro(const int* __restrict__ parent, int s) {   // read-only, any thread
+    int p = parent[s];
+    while (p != s) { s = p; p = parent[s]; }
+    return s;
+}
+__device__ __forceinline__ bool uf_union(const UF& u, int a, int b) {   // model.py:181-192
+    if (a == b) return false;
+    const int ia = u.ins[a], ib = u.ins[b];
+    if (ia != -1 && ib != -1 && ia != ib) return false;
+    u.parent[a] = b;
+    u.pnum[b] += u.pnum[a];
+    if (ia != ib) { u.ins[b] = -ia * ib; u.sem[b] = -u.sem[a] * u.sem[b]; }
+    u.next[u.tail[b]] = a;
+    u.tail[b] = u.tail[a];
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene init (model.py:712-721)
+// ---------------------------------------------------------------------------------------------
+__global__ void scene_init_points(const int* __restrict__ seg_off, const int* __restrict__ seg_members, int N, int S,
+                                  int* __restrict__ seg_of_point, int* __restrict__ seg_of_pos) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    const int s = sgb_upper_segment(seg_off, S, q);
+    seg_of_pos[q] = s;
+    seg_of_point[__ldg(seg_members + q)] = s;
+}
+__global__ void scene_init_uf(const int* __restrict__ seg_off, const int* __restrict__ seg_members, const int* __restrict__ weak,
+                              int S, int* __restrict__ ufb) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    UF u(ufb, S);
+    const int root_pt = __ldg(seg_members + __ldg(seg_off + s));
+    u.parent[s] = s; u.next[s] = -1; u.tail[s] = s;
+    u.pnum[s] = __ldg(seg_off + s + 1) - __ldg(seg_off + s);
+    u.sem[s] = __ldg(weak + (size_t)root_pt * 2);
+    u.ins[s] = __ldg(weak + (size_t)root_pt * 2 + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// level construction (model.py:209-214 get_cluster_list + the cluster_map dict loops 759-768)
+// ---------------------------------------------------------------------------------------------
+__global__ void level_flag_roots(const int* __restrict__ parent, int S, int* __restrict__ flag) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) flag[s] = parent[s] == s ? 1 : 0;
+}
+__global__ void level_assign(const int* __restrict__ ufb, int S, const int* __restrict__ dense /*scan of flags, [S+1]*/,
+                             const int* __restrict__ seg_off, const int* __restrict__ seg_members,
+                             int* __restrict__ roots, int* __restrict__ seg2cl, int* __restrict__ cl_ins, int* __restrict__ cl_sem,
+                             int* __restrict__ cl_rootpt, int* __restrict__ counts) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) counts[0] = dense[S];
+    if (s >= S) return;
+    const int* parent = ufb;
+    const int r = uf_find_ro(parent, s);
+    const int c = dense[r];
+    seg2cl[s] = c;
+    if (r == s) {
+        roots[c] = s;
+        cl_ins[c] = ufb[4 * S + s];
+        cl_sem[c] = ufb[5 * S + s];
+        cl_rootpt[c] = __ldg(seg_members + __ldg(seg_off + s));
+    }
+}
+// one thread per cluster walks its member list: segment order, per-segment start inside the cluster
+__global__ void level_walk_lists(const int* __restrict__ ufb, int S, const int* __restrict__ counts, const int* __restrict__ roots,
+                                 const int* __restrict__ seg_off, int* __restrict__ cl_nseg, int* __restrict__ cl_npt,
+                                 int* __restrict__ seg_rank /*[S] index inside the list*/, int* __restrict__ seg_start /*[S] point offset inside the cluster*/) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = counts[0];
+    if (c >= S) return;
+    if (c >= nc) { cl_nseg[c] = 0; cl_npt[c] = 0; return; }
+    const int* next = ufb + S;
+    int s = roots[c], i = 0, pts = 0;
+    while (s >= 0) {
+        seg_rank[s] = i; seg_start[s] = pts;
+        pts += __ldg(seg_off + s + 1) - __ldg(seg_off + s);
+        ++i;
+        s = next[s];
+    }
+    cl_nseg[c] = i; cl_npt[c] = pts;
+}
+__global__ void level_fill_seglist(int S, const int* __restrict__ seg2cl, const int* __restrict__ seg_rank,
+                                   const int* __restrict__ cl_seg_off, int* __restrict__ cl_seg_list) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) cl_seg_list[cl_seg_off[seg2cl[s]] + seg_rank[s]] = s;
+}
+__global__ void level_fill_order(int N, const int* __restrict__ seg_of_pos, const int* __restrict__ seg_off,
+                                 const int* __restrict__ seg_members, const int* __restrict__ seg2cl, const int* __restrict__ seg_start,
+                                 const int* __restrict__ cl_pt_off, int* __restrict__ order) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    const int s = seg_of_pos[q];
+    order[cl_pt_off[seg2cl[s]] + seg_start[s] + (q - __ldg(seg_off + s))] = __ldg(seg_members + q);
+}
+
+// children of every new cluster among the old clusters, ascending old index (model.py:760-768):
+// one warp per new cluster scans the old->new map with ballots (ordered compaction, no atomics).
+__global__ void children_count(const int* __restrict__ old2new, int n_old, int* __restrict__ cnt, int n_new_cap) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_old) atomicAdd(cnt + old2new[j], 1);
+}
+__global__ void children_fill(const int* __restrict__ old2new, int n_old, const int* __restrict__ child_off, int n_new,
+                              int* __restrict__ child_list) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n_new) return;
+    int w = child_off[c];
+    const int end = child_off[c + 1];
+    for (int j0 = 0; j0 < n_old && w < end; j0 += 32) {
+        const int j = j0 + lane;
+        const bool hit = j < n_old && old2new[j] == c;
+        const unsigned m = __ballot_sync(SGB_FULL_MASK, hit);
+        if (hit) child_list[w + __popc(m & ((1u << lane) - 1))] = j;
+        w += __popc(m);
+    }
+}
+__global__ void gather_old2new(const int* __restrict__ roots_old, int n_old, const int* __restrict__ seg2cl_new, int* __restrict__ old2new) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_old) old2new[j] = seg2cl_new[roots_old[j]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// update_adj (model.py:291-302): map, drop self edges, order each pair, unique-lexicographic.
+// Dedupe through an S x S bitmap (S <= ~3k clusters -> <= 1.1 MB): set bits, then per-row ordered
+// compaction.  Output is sorted by construction.
+// ---------------------------------------------------------------------------------------------
+__global__ void adj_set_bits(const int* __restrict__ edges, int E, const int* __restrict__ map, int S, int words_per_row,
+                             unsigned* __restrict__ bitmap) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int a = map[__ldg(edges + 2 * (size_t)e)], b = map[__ldg(edges + 2 * (size_t)e + 1)];
+    if (a == b) return;
+    if (a > b) { const int t = a; a = b; b = t; }
+    atomicOr(bitmap + (size_t)a * words_per_row + (b >> 5), 1u << (b & 31));
+}
+__global__ void adj_row_count(const unsigned* __restrict__ bitmap, int S, int words_per_row, int* __restrict__ row_cnt) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= S) return;
+    int c = 0;
+    for (int w = lane; w < words_per_row; w += 32) c += __popc(bitmap[(size_t)r * words_per_row + w]);
+    c = sgb_warp_sum(c);
+    if (lane == 0) row_cnt[r] = c;
+}
+__global__ void adj_row_write(const unsigned* __restrict__ bitmap, int S, int words_per_row, const int* __restrict__ row_off,
+                              int* __restrict__ adj_out, int* __restrict__ counts) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r == 0 && threadIdx.x == 0 && blockIdx.x == 0) counts[1] = row_off[S];
+    if (r >= S) return;
+    int w0 = row_off[r];
+    for (int wb = 0; wb < words_per_row; wb += 32) {
+        const int w = wb + lane;
+        const unsigned bits = w < words_per_row ? bitmap[(size_t)r * words_per_row + w] : 0u;
+        int c = __popc(bits);
+        // exclusive prefix over lanes
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(SGB_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+        int pos = w0 + inc - c;
+        unsigned b = bits;
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            adj_out[2 * (size_t)pos] = r;
+            adj_out[2 * (size_t)pos + 1] = w * 32 + bit;
+            ++pos;
+        }
+        w0 += __shfl_sync(SGB_FULL_MASK, inc, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// symmetric CSR of an edge list (for gather-style reductions): row i lists (neighbour, edge id) sorted
+// by neighbour.  Atomic fill, then a per-row insertion sort -> deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void csr_degree(const int* __restrict__ adj, int A, int* __restrict__ deg) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A) return;
+    atomicAdd(deg + adj[2 * e], 1);
+    atomicAdd(deg + adj[2 * e + 1], 1);
+}
+__global__ void csr_fill(const int* __restrict__ adj, int A, const int* __restrict__ row_off, int* __restrict__ cursor,
+                         int* __restrict__ nbr, int* __restrict__ eid) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A) return;
+    const int u = adj[2 * e], v = adj[2 * e + 1];
+    int p = row_off[u] + atomicAdd(cursor + u, 1);
+    nbr[p] = v; eid[p] = e;
+    p = row_off[v] + atomicAdd(cursor + v, 1);
+    nbr[p] = u; eid[p] = e;
+}
+__global__ void csr_sort_rows(const int* __restrict__ row_off, int S, int* __restrict__ nbr, int* __restrict__ eid) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= S) return;
+    const int a = row_off[r], b = row_off[r + 1];
+    for (int i = a + 1; i < b; ++i) {
+        const int kn = nbr[i], ke = eid[i];
+        int j = i - 1;
+        while (j >= a && nbr[j] > kn) { nbr[j + 1] = nbr[j]; eid[j + 1] = eid[j]; --j; }
+        nbr[j + 1] = kn; eid[j + 1] = ke;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge distances (model.py:269-274; F.pairwise_distance = ||a - b + 1e-6||_2): one warp per edge
+// ---------------------------------------------------------------------------------------------
+__global__ void edge_dist_fwd_kernel(const float* __restrict__ feat, int C, const int* __restrict__ adj, int A, float* __restrict__ dist) {
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= A) return;
+    const float* a = feat + (size_t)adj[2 * e] * C;
+    const float* b = feat + (size_t)adj[2 * e + 1] * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = (__ldg(a + c) - __ldg(b + c)) + 1e-6f; s = fmaf(d, d, s); }
+    s = sgb_warp_sum(s);
+    if (lane == 0) dist[e] = sqrtf(s);
+}
+// grad_feat[i] += sum over incident edges of +-g[e] * (F[u]-F[v]+eps)/d[e]   (gather over the symmetric CSR)
+__global__ void edge_dist_bwd_kernel(const float* __restrict__ feat, int C, const int* __restrict__ adj, const float* __restrict__ dist,
+                                     const float* __restrict__ gdist, const int* __restrict__ row_off, const int* __restrict__ eid,
+                                     int S, float* __restrict__ gfeat) {
+    const int i = blockIdx.x;
+    if (i >= S) return;
+    const int a = row_off[i], b = row_off[i + 1];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int t = a; t < b; ++t) {
+            const int e = eid[t];
+            const int u = adj[2 * e], v = adj[2 * e + 1];
+            const float d = dist[e];
+            const float g = gdist[e];
+            const float diff = (__ldg(feat + (size_t)u * C + c) - __ldg(feat + (size_t)v * C + c)) + 1e-6f;
+            const float val = d > 0.f ? g * diff / d : 0.f;
+            acc += (u == i) ? val : -val;
+        }
+        gfeat[(size_t)i * C + c] += acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GCN aggregation (model.py:305-309, 146-151): A = I + sym(sims); AX = (A / rowsum) X   as a CSR gather
+// ---------------------------------------------------------------------------------------------
+__global__ void gcn_agg_fwd_kernel(const float* __restrict__ X, int C, const float* __restrict__ sims, const int* __restrict__ row_off,
+                                   const int* __restrict__ nbr, const int* __restrict__ eid, int S, float* __restrict__ AX,
+                                   float* __restrict__ rowsum) {
+    const int i = blockIdx.x;
+    if (i >= S) return;
+    const int a = row_off[i], b = row_off[i + 1];
+    float rs = 1.f;                                   // diagonal
+    for (int t = a; t < b; ++t) rs += sims[eid[t]];
+    if (threadIdx.x == 0) rowsum[i] = rs;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        bool diag_done = false;
+        for (int t = a; t < b; ++t) {                 // ascending column order incl. the diagonal
+            const int j = nbr[t];
+            if (!diag_done && j > i) { acc = fmaf(1.f / rs, __ldg(X + (size_t)i * C + c), acc); diag_done = true; }
+            acc = fmaf(sims[eid[t]] / rs, __ldg(X + (size_t)j * C + c), acc);
+        }
+        if (!diag_done) acc = fmaf(1.f / rs, __ldg(X + (size_t)i * C + c), acc);
+        AX[(size_t)i * C + c] = acc;
+    }
+}
+// dX[j] = sum_i A[i,j]/rs_i * dAX[i]  (structure symmetric: gather over row j, using the neighbour's rowsum)
+__global__ void gcn_agg_bwd_x_kernel(const float* __restrict__ dAX, int C, const float* __restrict__ sims, const float* __restrict__ rowsum,
+                                     const int* __restrict__ row_off, const int* __restrict__ nbr, const int* __restrict__ eid, int S,
+                                     float* __restrict__ dX) {
+    const int j = blockIdx.x;
+    if (j >= S) return;
+    const int a = row_off[j], b = row_off[j + 1];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = __ldg(dAX + (size_t)j * C + c) / rowsum[j];
+        for (int t = a; t < b; ++t) {
+            const int i = nbr[t];
+            acc = fmaf(sims[eid[t]] / rowsum[i], __ldg(dAX + (size_t)i * C + c), acc);
+        }
+        dX[(size_t)j * C + c] = acc;
+    }
+}
+// dsims[e=(u,v)] = (dAX[u].X[v] - dAX[u].AX[u]) / rs_u + (dAX[v].X[u] - dAX[v].AX[v]) / rs_v : one warp per edge
+__global__ void gcn_agg_bwd_s_kernel(const float* __restrict__ dAX, const float* __restrict__ X, const float* __restrict__ AX, int C,
+                                     const float* __restrict__ rowsum, const int* __restrict__ adj, int A, float* __restrict__ dsims) {
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= A) return;
+    const int u = adj[2 * e], v = adj[2 * e + 1];
+    float s_uv = 0.f, s_uu = 0.f, s_vu = 0.f, s_vv = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float gu = __ldg(dAX + (size_t)u * C + c), gv = __ldg(dAX + (size_t)v * C + c);
+        s_uv = fmaf(gu, __ldg(X + (size_t)v * C + c), s_uv);
+        s_uu = fmaf(gu, __ldg(AX + (size_t)u * C + c), s_uu);
+        s_vu = fmaf(gv, __ldg(X + (size_t)u * C + c), s_vu);
+        s_vv = fmaf(gv, __ldg(AX + (size_t)v * C + c), s_vv);
+    }
+    s_uv = sgb_warp_sum(s_uv); s_uu = sgb_warp_sum(s_uu); s_vu = sgb_warp_sum(s_vu); s_vv = sgb_warp_sum(s_vv);
+    if (lane == 0) dsims[e] = (s_uv - s_uu) / rowsum[u] + (s_vu - s_vv) / rowsum[v];
+}
+
+// ---------------------------------------------------------------------------------------------
+// group_nearby_clusters (model.py:218-258) — sequential replay on one thread.
+// status bit 1 (value 2): the small-cluster sweep hit the cap (the reference would spin forever).
+// ---------------------------------------------------------------------------------------------
+__global__ void group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ roots_cur,
+                                    const float* __restrict__ dist, float th, int* __restrict__ ufb, int S1,
+                                    int sweep_cap, int* __restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    UF u(ufb, S1);
+    for (int i = 0; i < A; ++i) {
+        if (dist[i] > th) continue;                   // NaN distance -> comparison false -> merge attempt, as in Python
+        const int c1 = uf_find(u, roots_cur[adj[2 * i]]);
+        const int c2 = uf_find(u, roots_cur[adj[2 * i + 1]]);
+        uf_union(u, c1, c2);
+    }
+    int sweeps = 0;
+    while (true) {
+        bool attempted = false;
+        for (int i = 0; i < A; ++i) {
+            const int c1 = uf_find(u, roots_cur[adj[2 * i]]);
+            const int c2 = uf_find(u, roots_cur[adj[2 * i + 1]]);
+            if (u.pnum[c1] < 5 || u.pnum[c2] < 5) { uf_union(u, c1, c2); attempted = true; }
+        }
+        if (!attempted) break;
+        if (++sweeps > sweep_cap) { atomicOr(status, 2); break; }
+    }
+}
+
+// group_unlabeled_clusters phase A, one iteration (model.py:441-470):
+// row argmin of the dense distance matrix (fill 1000, first minimum) from the symmetric CSR, then the
+// sequential unions of unlabeled clusters in ascending order.
+__global__ void unlabeled_argmin_kernel(const float* __restrict__ dist, const int* __restrict__ row_off, const int* __restrict__ nbr,
+                                        const int* __restrict__ eid, int S, int* __restrict__ amin) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const int a = row_off[i], b = row_off[i + 1];
+    // dense row: dm[i][j] = dist(e) for neighbours, 1000 elsewhere (diagonal included)
+    float best = INFINITY; int bj = -1;
+    int expect = 0;                                   // smallest column not yet known to be a neighbour
+    int first_fill = -1;
+    for (int t = a; t < b; ++t) {
+        const int j = nbr[t];
+        if (first_fill < 0 && j > expect) first_fill = expect;
+        if (j == expect) ++expect;
+        else if (j > expect) expect = j + 1;
+        const float d = dist[eid[t]];
+        if (d < best) { best = d; bj = j; }
+    }
+    if (first_fill < 0 && expect < S) first_fill = expect;
+    // candidates: (best, bj) among edges, (1000, first_fill) among the filled entries; first minimum wins
+    if (first_fill >= 0 && (bj < 0 || 1000.f < best || (1000.f == best && first_fill < bj))) bj = first_fill;
+    amin[i] = bj < 0 ? 0 : bj;
+}
+__global__ void unlabeled_union_kernel(const int* __restrict__ amin, int S, const int* __restrict__ roots_cur, int* __restrict__ ufb, int S1) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    UF u(ufb, S1);
+    for (int i = 0; i < S; ++i) {
+        const int c1 = uf_find(u, roots_cur[i]);
+        if (u.ins[c1] != -1) continue;
+        uf_union(u, c1, uf_find(u, roots_cur[amin[i]]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// label export (model.py:525-605): per raw vertex r, p = unmap[r]: segment = root point id of p's cluster,
+// instance / semantic = weak label + 1 (or -1 when the cluster is unlabeled)
+// ---------------------------------------------------------------------------------------------
+__global__ void export_labels_kernel(const long long* __restrict__ unmap, int n_raw, const int* __restrict__ seg_of_point,
+                                     const int* __restrict__ seg2cl, const int* __restrict__ cl_rootpt, const int* __restrict__ cl_ins,
+                                     const int* __restrict__ cl_sem, int* __restrict__ out_seg, int* __restrict__ out_ins, int* __restrict__ out_sem) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_raw) return;
+    const int p = unmap ? (int)unmap[r] : r;
+    const int c = seg2cl[seg_of_point[p]];
+    if (out_seg) out_seg[r] = cl_rootpt[c];
+    const int ins = cl_ins[c], sem = cl_sem[c];
+    if (out_ins) out_ins[r] = ins != -1 ? ins + 1 : -1;
+    if (out_sem) out_sem[r] = sem != -1 ? sem + 1 : -1;
+}
+}  // namespace
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" int sgb_scene_init(const int* seg_off, const int* seg_members, const int* weak_label, int N, int S,
+                              int* seg_of_point, int* seg_of_pos, int* uf, void* stream) {
+    if (N <= 0 || S <= 0 || !seg_off || !seg_members || !weak_label || !seg_of_point || !seg_of_pos || !uf) return SGB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    scene_init_points<<<sgb_div_up(N, 256), 256, 0, st>>>(seg_off, seg_members, N, S, seg_of_point, seg_of_pos);
+    scene_init_uf<<<sgb_div_up(S, 256), 256, 0, st>>>(seg_off, seg_members, weak_label, S, uf);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" size_t sgb_level_ws_bytes(int S1) { return (size_t)(6 * (S1 + 1)) * sizeof(int) + sgb_scan_ws_bytes(S1 + 1); }
+
+// counts[0] <- number of clusters.  All outputs are sized for the level-1 segment count S1 (cl_*_off: S1+1).
+extern "C" int sgb_level_build(const int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
+                               int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
+                               int* cl_ins, int* cl_sem, int* cl_rootpt, int* counts, void* ws, size_t ws_bytes, void* stream) {
+    if (S1 <= 0 || N <= 0 || !uf || !seg_off || !seg_members || !seg_of_pos || !roots || !seg2cl || !cl_seg_off || !cl_seg_list ||
+        !cl_pt_off || !order || !cl_ins || !cl_sem || !cl_rootpt || !counts || !ws) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_level_ws_bytes(S1)) return SGB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* flag = (int*)ws;                 // [S1+1]
+    int* dense = flag + (S1 + 1);         // [S1+1]
+    int* cl_nseg = dense + (S1 + 1);      // [S1+1]
+    int* cl_npt = cl_nseg + (S1 + 1);     // [S1+1]
+    int* seg_rank = cl_npt + (S1 + 1);    // [S1+1]
+    int* seg_start = seg_rank + (S1 + 1); // [S1+1]
+    void* scan_ws = seg_start + (S1 + 1);
+    const size_t scan_bytes = sgb_scan_ws_bytes(S1 + 1);
+    const int g = sgb_div_up(S1, 256);
+    int rc;
+    level_flag_roots<<<g, 256, 0, st>>>(uf, S1, flag);
+    if ((rc = sgb_exclusive_scan_i32(flag, dense, S1, scan_ws, scan_bytes, st))) return rc;
+    level_assign<<<g, 256, 0, st>>>(uf, S1, dense, seg_off, seg_members, roots, seg2cl, cl_ins, cl_sem, cl_rootpt, counts);
+    level_walk_lists<<<g, 256, 0, st>>>(uf, S1, counts, roots, seg_off, cl_nseg, cl_npt, seg_rank, seg_start);
+    if ((rc = sgb_exclusive_scan_i32(cl_nseg, cl_seg_off, S1, scan_ws, scan_bytes, st))) return rc;
+    if ((rc = sgb_exclusive_scan_i32(cl_npt, cl_pt_off, S1, scan_ws, scan_bytes, st))) return rc;
+    level_fill_seglist<<<g, 256, 0, st>>>(S1, seg2cl, seg_rank, cl_seg_off, cl_seg_list);
+    level_fill_order<<<sgb_div_up(N, 256), 256, 0, st>>>(N, seg_of_pos, seg_off, seg_members, seg2cl, seg_start, cl_pt_off, order);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+// children CSR: child_off [n_new+1], child_list [n_old] (old dense cluster ids, ascending inside each new cluster),
+// old2new [n_old].  ws: (n_new + 1) ints + scan workspace.
+extern "C" size_t sgb_children_ws_bytes(int n_new) { return (size_t)(n_new + 1) * sizeof(int) + sgb_scan_ws_bytes(n_new + 1); }
+extern "C" int sgb_level_children(const int* roots_old, int n_old, const int* seg2cl_new, int n_new, int* old2new,
+                                  int* child_off, int* child_list, void* ws, size_t ws_bytes, void* stream) {
+    if (n_old <= 0 || n_new <= 0 || !roots_old || !seg2cl_new || !old2new || !child_off || !child_list || !ws) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_children_ws_bytes(n_new)) return SGB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* cnt = (int*)ws;
+    void* scan_ws = cnt + (n_new + 1);
+    SGB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n_new + 1) * sizeof(int), st));
+    gather_old2new<<<sgb_div_up(n_old, 256), 256, 0, st>>>(roots_old, n_old, seg2cl_new, old2new);
+    children_count<<<sgb_div_up(n_old, 256), 256, 0, st>>>(old2new, n_old, cnt, n_new);
+    int rc;
+    if ((rc = sgb_exclusive_scan_i32(cnt, child_off, n_new, scan_ws, sgb_scan_ws_bytes(n_new + 1), st))) return rc;
+    children_fill<<<sgb_div_up(n_new, 8), 256, 0, st>>>(old2new, n_old, child_off, n_new, child_list);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" size_t sgb_update_adj_ws_bytes(int S_new) {
+    const size_t wpr = (size_t)(S_new + 31) / 32;
+    return (size_t)S_new * wpr * 4 + (size_t)(2 * (S_new + 1)) * sizeof(int) + sgb_scan_ws_bytes(S_new + 1);
+}
+// edges [E,2] (ids of the old level), map [n_old] -> new dense ids (< S_new).  adj_out capacity must be >= min(E, S_new*(S_new-1)/2)
+// rows; counts[1] <- number of rows written.
+extern "C" int sgb_update_adj(const int* edges, int E, const int* map, int S_new, int* adj_out, int* counts,
+                              void* ws, size_t ws_bytes, void* stream) {
+    if (E < 0 || S_new <= 0 || !map || !adj_out || !counts || !ws) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_update_adj_ws_bytes(S_new)) return SGB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = (S_new + 31) / 32;
+    unsigned* bitmap = (unsigned*)ws;
+    int* row_cnt = (int*)(bitmap + (size_t)S_new * wpr);
+    int* row_off = row_cnt + (S_new + 1);
+    void* scan_ws = row_off + (S_new + 1);
+    SGB_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)S_new * wpr * 4, st));
+    if (E > 0) {
+        if (!edges) return SGB_ERR_INVALID;
+        adj_set_bits<<<sgb_div_up(E, 256), 256, 0, st>>>(edges, E, map, S_new, wpr, bitmap);
+    }
+    adj_row_count<<<sgb_div_up(S_new, 8), 256, 0, st>>>(bitmap, S_new, wpr, row_cnt);
+    int rc;
+    if ((rc = sgb_exclusive_scan_i32(row_cnt, row_off, S_new, scan_ws, sgb_scan_ws_bytes(S_new + 1), st))) return rc;
+    adj_row_write<<<sgb_div_up(S_new, 8), 256, 0, st>>>(bitmap, S_new, wpr, row_off, adj_out, counts);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" size_t sgb_sym_csr_ws_bytes(int S) { return (size_t)(2 * (S + 1)) * sizeof(int) + sgb_scan_ws_bytes(S + 1); }
+extern "C" int sgb_sym_csr(const int* adj, int A, int S, int* row_off, int* nbr, int* eid, void* ws, size_t ws_bytes, void* stream) {
+    if (A < 0 || S <= 0 || !row_off || !ws) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_sym_csr_ws_bytes(S)) return SGB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* deg = (int*)ws;
+    int* cursor = deg + (S + 1);
+    void* scan_ws = cursor + (S + 1);
+    SGB_CUDA(cudaMemsetAsync(deg, 0, (size_t)(2 * (S + 1)) * sizeof(int), st));
+    if (A > 0) {
+        if (!adj || !nbr || !eid) return SGB_ERR_INVALID;
+        csr_degree<<<sgb_div_up(A, 256), 256, 0, st>>>(adj, A, deg);
+    }
+    int rc;
+    if ((rc = sgb_exclusive_scan_i32(deg, row_off, S, scan_ws, sgb_scan_ws_bytes(S + 1), st))) return rc;
+    if (A > 0) {
+        csr_fill<<<sgb_div_up(A, 256), 256, 0, st>>>(adj, A, row_off, cursor, nbr, eid);
+        csr_sort_rows<<<sgb_div_up(S, 128), 128, 0, st>>>(row_off, S, nbr, eid);
+    }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_edge_dist_fwd(const float* feat, int C, const int* adj, int A, float* dist, void* stream) {
+    if (A < 0 || C <= 0) return SGB_ERR_INVALID;
+    if (A == 0) return SGB_OK;
+    if (!feat || !adj || !dist) return SGB_ERR_INVALID;
+    edge_dist_fwd_kernel<<<sgb_div_up(A, 8), 256, 0, (cudaStream_t)stream>>>(feat, C, adj, A, dist);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+// gfeat [S,C] += d(dist)/d(feat) * gdist  (gfeat must be initialised by the caller)
+extern "C" int sgb_edge_dist_bwd(const float* feat, int S, int C, const int* adj, int A, const float* dist, const float* gdist,
+                                 const int* row_off, const int* eid, float* gfeat, void* stream) {
+    if (A < 0 || C <= 0 || S <= 0) return SGB_ERR_INVALID;
+    if (A == 0) return SGB_OK;
+    if (!feat || !adj || !dist || !gdist || !row_off || !eid || !gfeat) return SGB_ERR_INVALID;
+    edge_dist_bwd_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(feat, C, adj, dist, gdist, row_off, eid, S, gfeat);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_gcn_agg_fwd(const float* X, int S, int C, const float* sims, const int* row_off, const int* nbr, const int* eid,
+                               float* AX, float* rowsum, void* stream) {
+    if (S <= 0 || C <= 0 || !X || !row_off || !AX || !rowsum) return SGB_ERR_INVALID;
+    gcn_agg_fwd_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(X, C, sims, row_off, nbr, eid, S, AX, rowsum);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+extern "C" int sgb_gcn_agg_bwd(const float* dAX, const float* X, const float* AX, int S, int C, const float* sims, const float* rowsum,
+                               const int* adj, int A, const int* row_off, const int* nbr, const int* eid,
+                               float* dX, float* dsims, void* stream) {
+    if (S <= 0 || C <= 0 || A < 0 || !dAX || !X || !AX || !rowsum || !row_off || !dX) return SGB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    gcn_agg_bwd_x_kernel<<<S, 128, 0, st>>>(dAX, C, sims, rowsum, row_off, nbr, eid, S, dX);
+    if (A > 0) {
+        if (!adj || !dsims || !sims) return SGB_ERR_INVALID;
+        gcn_agg_bwd_s_kernel<<<sgb_div_up(A, 8), 256, 0, st>>>(dAX, X, AX, C, rowsum, adj, A, dsims);
+    }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_group_nearby(const int* adj, int A, const int* roots_cur, const float* dist, float th, int* uf, int S1,
+                                int sweep_cap, int* status, void* stream) {
+    if (A < 0 || S1 <= 0 || !uf || !status) return SGB_ERR_INVALID;
+    if (A == 0) return SGB_OK;
+    if (!adj || !roots_cur || !dist) return SGB_ERR_INVALID;
+    group_nearby_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(adj, A, roots_cur, dist, th, uf, S1, sweep_cap, status);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+// one iteration of phase A of group_unlabeled_clusters; amin_ws [S] ints
+extern "C" int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
+                                        const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream) {
+    if (S <= 0 || S1 <= 0 || !row_off || !roots_cur || !uf || !amin_ws) return SGB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    unlabeled_argmin_kernel<<<sgb_div_up(S, 128), 128, 0, st>>>(dist, row_off, nbr, eid, S, amin_ws);
+    unlabeled_union_kernel<<<1, 32, 0, st>>>(amin_ws, S, roots_cur, uf, S1);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
+                                 const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem, void* stream) {
+    if (n_raw <= 0 || !seg_of_point || !seg2cl || !cl_rootpt || !cl_ins || !cl_sem) return SGB_ERR_INVALID;
+    export_labels_kernel<<<sgb_div_up(n_raw, 256), 256, 0, (cudaStream_t)stream>>>(unmap, n_raw, seg_of_point, seg2cl, cl_rootpt,
+                                                                                   cl_ins, cl_sem, out_seg, out_ins, out_sem);
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}

@@ -1,0 +1,313 @@
+"""Tensor-level wrappers over the C-ABI (`include/seggroup_b200.h`).
+
+PyTorch is used here for device memory and streams only: every function allocates its outputs and
+workspaces as CUDA tensors, hands raw pointers + the current stream to libseggroup_b200.so, and returns
+the tensors.  No function has a CPU or eager-PyTorch fallback: inputs must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+I32 = torch.int32
+F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.SgbError("%s must be a CUDA tensor (seggroup_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+def exclusive_scan(x):
+    _chk(x, I32, "x")
+    n = x.numel()
+    out = torch.empty(n + 1, dtype=I32, device=x.device)
+    ws = _ws(_lib.call("sgb_scan_ws_bytes", n), x.device)
+    _lib.call("sgb_exclusive_scan_i32", x, out, n, ws, ws.numel(), _stream())
+    return out
+
+
+def segment_pool_max(feat, offsets, members=None, want_argmax=True):
+    """feat [R,C] f32; offsets [S+1] i32; members [M] i32 row ids (None = rows already segment-major).
+    Returns (out [S,C], argmax [S,C] i32 row ids)."""
+    _chk(feat, F32, "feat"); _chk(offsets, I32, "offsets")
+    R, C = feat.shape
+    S = offsets.numel() - 1
+    M = R if members is None else members.numel()
+    if members is not None:
+        _chk(members, I32, "members")
+    out = torch.empty(S, C, dtype=F32, device=feat.device)
+    arg = torch.empty(S, C, dtype=I32, device=feat.device) if want_argmax else None
+    ws = _ws(_lib.call("sgb_segment_pool_ws_bytes", S, C), feat.device)
+    _lib.call("sgb_segment_pool_max_fwd", feat, R, C, members, M, offsets, S, out, arg, ws, ws.numel(), _stream())
+    return out, arg
+
+
+def segment_pool_max_bwd(grad_out, argmax, n_rows):
+    _chk(grad_out, F32, "grad_out"); _chk(argmax, I32, "argmax")
+    S, C = grad_out.shape
+    g = torch.zeros(n_rows, C, dtype=F32, device=grad_out.device)
+    _lib.call("sgb_segment_pool_max_bwd", grad_out, argmax, S, C, g, _stream())
+    return g
+
+
+def cluster_knn(xyz, order, cl_off, k=20):
+    """xyz [N,>=3] f32 (row stride = xyz.stride(0)); order [N] i32; cl_off [S+1] i32 -> knn [N,k] i32."""
+    _chk(order, I32, "order"); _chk(cl_off, I32, "cl_off")
+    if not xyz.is_cuda or xyz.dtype != F32 or xyz.stride(1) != 1:
+        raise ValueError("xyz must be a CUDA float32 tensor with unit inner stride")
+    N = order.numel()
+    knn = torch.empty(N, k, dtype=I32, device=xyz.device)
+    _lib.call("sgb_cluster_knn", xyz, xyz.stride(0), N, order, cl_off, cl_off.numel() - 1, k, knn, _stream())
+    return knn
+
+
+def cluster_cloud_indices(xyz, order, cl_off, P):
+    """-> (cloud_idx [S,P] i32 point ids, status [1] i32)."""
+    _chk(order, I32, "order"); _chk(cl_off, I32, "cl_off")
+    if not xyz.is_cuda or xyz.dtype != F32 or xyz.stride(1) != 1:
+        raise ValueError("xyz must be a CUDA float32 tensor with unit inner stride")
+    S = cl_off.numel() - 1
+    N = order.numel()
+    idx = torch.empty(S, P, dtype=I32, device=xyz.device)
+    status = torch.zeros(1, dtype=I32, device=xyz.device)
+    ws = _ws(_lib.call("sgb_cluster_cloud_ws_bytes", N), xyz.device)
+    _lib.call("sgb_cluster_cloud_indices", xyz, xyz.stride(0), N, order, cl_off, S, P, idx, status, ws, ws.numel(), _stream())
+    return idx, status
+
+
+def cluster_cloud_transform(data6, cloud_idx):
+    _chk(data6, F32, "data6"); _chk(cloud_idx, I32, "cloud_idx")
+    S, P = cloud_idx.shape
+    clouds = torch.empty(S, P, 6, dtype=F32, device=data6.device)
+    _lib.call("sgb_cluster_cloud_transform", data6, cloud_idx, S, P, clouds, _stream())
+    return clouds
+
+
+def centralize(data6, order, cl_off):
+    _chk(data6, F32, "data6"); _chk(order, I32, "order"); _chk(cl_off, I32, "cl_off")
+    N = data6.shape[0]
+    S = cl_off.numel() - 1
+    x9 = torch.empty(N, 9, dtype=F32, device=data6.device)
+    mean = torch.empty(S, 3, dtype=F32, device=data6.device)
+    _lib.call("sgb_centralize", data6, N, order, cl_off, S, x9, mean, _stream())
+    return x9
+
+
+def mlp1_fwd(clouds, W, gamma, beta):
+    """clouds [S,64,6] -> dict(feat [S,128], knn [S,64,10], arg_pt [S,64], stats [4,64], var [64], mom [27] f64)."""
+    _chk(clouds, F32, "clouds")
+    S = clouds.shape[0]
+    dev = clouds.device
+    W = _chk(W.reshape(64, 6), F32, "W")
+    out = dict(feat=torch.empty(S, 128, dtype=F32, device=dev), knn=torch.empty(S, 64, 10, dtype=I32, device=dev),
+               arg_pt=torch.empty(S, 64, dtype=I32, device=dev), stats=torch.empty(4, 64, dtype=F32, device=dev),
+               var=torch.empty(64, dtype=F32, device=dev), mom=torch.empty(27, dtype=torch.float64, device=dev))
+    ws = _ws(_lib.call("sgb_mlp1_ws_bytes", S), dev)
+    _lib.call("sgb_mlp1_fwd", clouds, S, W, gamma, beta, out["feat"], out["knn"], out["arg_pt"], out["stats"], out["var"],
+              out["mom"], ws, ws.numel(), _stream())
+    return out
+
+
+def mlp1_bwd(g, clouds, knn, arg_pt, W, stats, mom):
+    """-> (gW [64,6], ggamma [64], gbeta [64])"""
+    S = clouds.shape[0]
+    dev = clouds.device
+    W = _chk(W.reshape(64, 6).contiguous(), F32, "W")
+    gW = torch.empty(64, 6, dtype=F32, device=dev)
+    gg = torch.empty(64, dtype=F32, device=dev)
+    gb = torch.empty(64, dtype=F32, device=dev)
+    ws = _ws(_lib.call("sgb_mlp1_bwd_ws_bytes", S), dev)
+    _lib.call("sgb_mlp1_bwd", _chk(g, F32, "g"), clouds, knn, arg_pt, S, W, stats, mom, gW, gg, gb, ws, ws.numel(), _stream())
+    return gW, gg, gb
+
+
+def edgeconv_bwd(g, arg, argk, x9, knn, W1, stats1, mom1, e0, W2=None, stats2=None, mom2=None):
+    """g [S,64] -> dict(gW1, gg1, gb1 [, gW2, gg2, gb2])."""
+    S = g.shape[0]
+    N = x9.shape[0]
+    dev = g.device
+    two = W2 is not None
+    W1 = _chk(W1.reshape(64, 18).contiguous(), F32, "W1")
+    r = dict(gW1=torch.empty(64, 18, dtype=F32, device=dev), gg1=torch.empty(64, dtype=F32, device=dev),
+             gb1=torch.empty(64, dtype=F32, device=dev))
+    if two:
+        W2 = _chk(W2.reshape(64, 64).contiguous(), F32, "W2")
+        r.update(gW2=torch.empty(64, 64, dtype=F32, device=dev), gg2=torch.empty(64, dtype=F32, device=dev),
+                 gb2=torch.empty(64, dtype=F32, device=dev))
+    ws = _ws(_lib.call("sgb_edgeconv_bwd_ws_bytes", N, S, int(two)), dev)
+    _lib.call("sgb_edgeconv_bwd", _chk(g, F32, "g"), arg, argk, S, x9, knn, N, int(two), W1, stats1, mom1, e0, W2, stats2, mom2,
+              r["gW1"], r["gg1"], r["gb1"], r.get("gW2"), r.get("gg2"), r.get("gb2"), ws, ws.numel(), _stream())
+    return r
+
+
+def edgeconv_fwd(x9, knn, W1, gamma1, beta1, W2=None, gamma2=None, beta2=None, want_argk=True):
+    """x9 [N,9], knn [N,20] -> dict(out [N,64], argk [N,64] u8, stats1, var1, mom1, ctr [, stats2, var2, mom2])."""
+    _chk(x9, F32, "x9"); _chk(knn, I32, "knn")
+    N = x9.shape[0]
+    dev = x9.device
+    two = W2 is not None
+    W1 = _chk(W1.reshape(64, 18), F32, "W1")
+    if two:
+        W2 = _chk(W2.reshape(64, 64), F32, "W2")
+    o = dict(out=torch.empty(N, 64, dtype=F32, device=dev), stats1=torch.empty(4, 64, dtype=F32, device=dev),
+             var1=torch.empty(64, dtype=F32, device=dev), mom1=torch.empty(189, dtype=torch.float64, device=dev),
+             ctr=torch.empty(18, dtype=F32, device=dev),
+             argk=torch.empty(N, 64, dtype=torch.uint8, device=dev) if want_argk else None)
+    if two:
+        o.update(stats2=torch.empty(4, 64, dtype=F32, device=dev), var2=torch.empty(64, dtype=F32, device=dev),
+                 mom2=torch.empty(4160, dtype=torch.float64, device=dev))
+    ws = _ws(_lib.call("sgb_edgeconv_ws_bytes", N, int(two)), dev)
+    _lib.call("sgb_edgeconv_fwd", x9, knn, N, int(two), W1, gamma1, beta1, W2, gamma2, beta2, o["out"], o["argk"], o["stats1"], o["var1"],
+              o["mom1"], o.get("stats2"), o.get("var2"), o.get("mom2"), o["ctr"], ws, ws.numel(), _stream())
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
+# segment graph
+# ------------------------------------------------------------------------------------------------
+def scene_init(seg_off, seg_members, weak_label):
+    """-> (seg_of_point [N], seg_of_pos [N], uf [6,S1])."""
+    _chk(seg_off, I32, "seg_off"); _chk(seg_members, I32, "seg_members"); _chk(weak_label, I32, "weak_label")
+    N = seg_members.numel()
+    S = seg_off.numel() - 1
+    dev = seg_off.device
+    sop = torch.empty(N, dtype=I32, device=dev)
+    sos = torch.empty(N, dtype=I32, device=dev)
+    uf = torch.empty(6, S, dtype=I32, device=dev)
+    _lib.call("sgb_scene_init", seg_off, seg_members, weak_label, N, S, sop, sos, uf, _stream())
+    return sop, sos, uf
+
+
+class Level:
+    """Device arrays of one clustering level (all sized for S1; `S` is read back once, after build)."""
+    __slots__ = ("S", "roots", "seg2cl", "cl_seg_off", "cl_seg_list", "cl_pt_off", "order", "cl_ins", "cl_sem", "cl_rootpt",
+                 "counts")
+
+
+def level_build(uf, seg_off, seg_members, seg_of_pos):
+    S1 = uf.shape[1]
+    N = seg_members.numel()
+    dev = uf.device
+    L = Level()
+    e = lambda n: torch.empty(n, dtype=I32, device=dev)
+    L.roots, L.seg2cl, L.cl_seg_off, L.cl_seg_list = e(S1), e(S1), e(S1 + 1), e(S1)
+    L.cl_pt_off, L.order, L.cl_ins, L.cl_sem, L.cl_rootpt = e(S1 + 1), e(N), e(S1), e(S1), e(S1)
+    L.counts = torch.zeros(4, dtype=I32, device=dev)
+    ws = _ws(_lib.call("sgb_level_ws_bytes", S1), dev)
+    _lib.call("sgb_level_build", uf, S1, N, seg_off, seg_members, seg_of_pos, L.roots, L.seg2cl, L.cl_seg_off, L.cl_seg_list,
+              L.cl_pt_off, L.order, L.cl_ins, L.cl_sem, L.cl_rootpt, L.counts, ws, ws.numel(), _stream())
+    L.S = int(L.counts[0].item())          # the one host sync per level (shapes of everything downstream)
+    # trim views to the live cluster count
+    S = L.S
+    L.roots, L.cl_seg_off, L.cl_pt_off = L.roots[:S], L.cl_seg_off[:S + 1], L.cl_pt_off[:S + 1]
+    L.cl_ins, L.cl_sem, L.cl_rootpt = L.cl_ins[:S], L.cl_sem[:S], L.cl_rootpt[:S]
+    return L
+
+
+def level_children(old: Level, new: Level):
+    """-> (old2new [S_old], child_off [S_new+1], child_list [S_old])."""
+    dev = old.roots.device
+    o2n = torch.empty(old.S, dtype=I32, device=dev)
+    off = torch.empty(new.S + 1, dtype=I32, device=dev)
+    lst = torch.empty(old.S, dtype=I32, device=dev)
+    ws = _ws(_lib.call("sgb_children_ws_bytes", new.S), dev)
+    _lib.call("sgb_level_children", old.roots, old.S, new.seg2cl, new.S, o2n, off, lst, ws, ws.numel(), _stream())
+    return o2n, off, lst
+
+
+def update_adj(edges, mapping, S_new):
+    """edges [E,2] i32, mapping [n_old] i32 -> adj [A,2] i32 (unique, row-sorted, lexicographic)."""
+    _chk(edges, I32, "edges"); _chk(mapping, I32, "mapping")
+    E = edges.shape[0]
+    dev = mapping.device
+    cap = max(1, min(E, S_new * (S_new - 1) // 2))
+    out = torch.empty(cap, 2, dtype=I32, device=dev)
+    counts = torch.zeros(4, dtype=I32, device=dev)
+    ws = _ws(_lib.call("sgb_update_adj_ws_bytes", S_new), dev)
+    _lib.call("sgb_update_adj", edges, E, mapping, S_new, out, counts, ws, ws.numel(), _stream())
+    A = int(counts[1].item())
+    return out[:A]
+
+
+def sym_csr(adj, S):
+    _chk(adj, I32, "adj")
+    A = adj.shape[0]
+    dev = adj.device
+    row_off = torch.empty(S + 1, dtype=I32, device=dev)
+    nbr = torch.empty(max(2 * A, 1), dtype=I32, device=dev)
+    eid = torch.empty(max(2 * A, 1), dtype=I32, device=dev)
+    ws = _ws(_lib.call("sgb_sym_csr_ws_bytes", S), dev)
+    _lib.call("sgb_sym_csr", adj, A, S, row_off, nbr, eid, ws, ws.numel(), _stream())
+    return row_off, nbr, eid
+
+
+def edge_dist(feat, adj):
+    _chk(feat, F32, "feat"); _chk(adj, I32, "adj")
+    A = adj.shape[0]
+    d = torch.empty(A, dtype=F32, device=feat.device)
+    _lib.call("sgb_edge_dist_fwd", feat, feat.shape[1], adj, A, d, _stream())
+    return d
+
+
+def edge_dist_bwd(feat, adj, dist, gdist, csr, gfeat):
+    row_off, nbr, eid = csr
+    _lib.call("sgb_edge_dist_bwd", feat, feat.shape[0], feat.shape[1], adj, adj.shape[0], dist, gdist, row_off, eid, gfeat, _stream())
+    return gfeat
+
+
+def gcn_agg(X, sims, csr):
+    row_off, nbr, eid = csr
+    S, C = X.shape
+    AX = torch.empty(S, C, dtype=F32, device=X.device)
+    rs = torch.empty(S, dtype=F32, device=X.device)
+    _lib.call("sgb_gcn_agg_fwd", X, S, C, sims, row_off, nbr, eid, AX, rs, _stream())
+    return AX, rs
+
+
+def gcn_agg_bwd(dAX, X, AX, sims, rs, adj, csr):
+    row_off, nbr, eid = csr
+    S, C = X.shape
+    A = adj.shape[0]
+    dX = torch.empty(S, C, dtype=F32, device=X.device)
+    dsims = torch.zeros(max(A, 1), dtype=F32, device=X.device)[:A]
+    _lib.call("sgb_gcn_agg_bwd", dAX, X, AX, S, C, sims, rs, adj, A, row_off, nbr, eid, dX, dsims, _stream())
+    return dX, dsims
+
+
+def group_nearby(adj, roots_cur, dist, th, uf, status, sweep_cap=64):
+    _lib.call("sgb_group_nearby", adj, adj.shape[0], roots_cur, dist, float(th), uf, uf.shape[1], sweep_cap, status, _stream())
+
+
+def group_unlabeled_step(dist, csr, S, roots_cur, uf):
+    row_off, nbr, eid = csr
+    amin = torch.empty(S, dtype=I32, device=uf.device)
+    _lib.call("sgb_group_unlabeled_step", dist, row_off, nbr, eid, S, roots_cur, uf, uf.shape[1], amin, _stream())
+    return amin
+
+
+def export_labels(unmap, seg_of_point, level: Level, want_seg=True):
+    """unmap [N_raw] i64 (or None) -> (seg, ins, sem) int32 [N_raw]."""
+    dev = seg_of_point.device
+    n_raw = unmap.numel() if unmap is not None else seg_of_point.numel()
+    seg = torch.empty(n_raw, dtype=I32, device=dev) if want_seg else None
+    ins = torch.empty(n_raw, dtype=I32, device=dev)
+    sem = torch.empty(n_raw, dtype=I32, device=dev)
+    _lib.call("sgb_export_labels", unmap, n_raw, seg_of_point, level.seg2cl, level.cl_rootpt, level.cl_ins, level.cl_sem,
+              seg, ins, sem, _stream())
+    return seg, ins, sem
