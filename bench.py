@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py — points/sec of the SegGroup hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scenes 8] [--points 150000]
+
+A "step" is one training step of BASELINE.json configs[1]: forward + backward + SGD update over a batch of
+`--scenes` synthetic ScanNet-v2-shaped scenes of `--points` points each (per-scene BatchNorm statistics,
+gradient = mean over scenes of loss_sum/loss_num, reference semantics of train.py:165-170 at 8 ranks).
+With N > 1 (torchrun, one rank per GPU) every rank runs its own batch (weak scaling) and the flat fp32
+gradient buffer is all-reduced once per step over NCCL.
+
+One JSON line is printed by rank 0:
+  value        whole-job points/sec, scene inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e          same metric through the host-facing call: every step copies the scenes' inputs from pinned host
+               memory and reads the loss back
+  roofline     dominant kernel (EdgeConv forward of MLP3): algorithmic HBM bytes / measured launch time
+  cpu_baseline the oracle port of the reference CPU path, timed on a bounded sample on this box's host cores
+`--impl reference` times that CPU port alone, as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "points/sec SegGroup fwd+bwd and inference at 1/2/4/8 B200; % HBM roofline"
+UNIT = "points/s"
+GSCALE = 4.0          # calibrated weight set of SURVEY.md 8d: every grouping stage does non-trivial work
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_port_points_per_sec(n_points, steps=1, warmup=0):
+    """The oracle (CPU restatement of the reference's torch/numpy path) fwd+bwd on one scene: points/sec."""
+    from oracle import seggroup_oracle as O
+    from seggroup_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    scene = synth.make_scene(101, n_points)
+    params = O.init_params(1, GSCALE)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.forward(scene, params, mode="train", tie="torch", want_grads=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_points / float(np.mean(times)), float(np.mean(times)), torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_points
+    pps, sec, cores = cpu_port_points_per_sec(n, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    sample = "1 scene x %d points fwd+bwd per step (bounded sample of the %d x %d batch)" % (n, args.scenes, args.points)
+    line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SegGroup training step fwd+bwd, %d scenes x %d points per GPU (configs[1])" % (args.scenes, args.points),
+                       "reference_arm": "oracle port of seggroup/model.py on host cores (the Python reference does not travel to the GPU box)"},
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=8)
+    ap.add_argument("--points", type=int, default=150000)
+    ap.add_argument("--ref-points", type=int, default=30000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    from seggroup_b200 import _lib, pipeline, synth
+    from seggroup_b200.params import TRAINABLE, init_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the seggroup_b200 product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    # ---- synthetic batch (seeded per rank), pinned on the host and resident on the device
+    scenes_host = [synth.make_scene(1000 * rank + i, args.points) for i in range(args.scenes)]
+    pinned = []
+    for s in scenes_host:
+        pinned.append({k: torch.as_tensor(np.ascontiguousarray(v)).pin_memory() for k, v in
+                       dict(data=s.data, weak=s.weak_label.astype(np.int32), seg_off=s.seg_offsets.astype(np.int32),
+                            seg_members=s.seg_members.astype(np.int32), adj=s.adj.astype(np.int32), unmap=s.unmap, real=s.real_label).items()})
+    h2d_bytes = sum(sum(t.numel() * t.element_size() for t in d.values()) for d in pinned)
+
+    def upload(d):
+        t = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
+        return pipeline.SceneDevice(data=t["data"], weak_label=t["weak"], seg_off=t["seg_off"], seg_members=t["seg_members"], adj0=t["adj"],
+                                    unmap=t["unmap"], real_label=t["real"])
+
+    resident = [upload(d) for d in pinned]
+    torch.manual_seed(1)
+    p = {k: v.to(dev) for k, v in init_params(1, GSCALE).items()}
+    train_keys = list(TRAINABLE)
+    for k in train_keys:
+        p[k].requires_grad_(True)
+    opt = torch.optim.SGD([p[k] for k in train_keys], lr=0.1, momentum=0.9, weight_decay=1e-4)      # train.py:96-97
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                                 # > 126 MB L2
+
+    def allreduce_grads():
+        if dist is None:
+            return
+        flat = torch.cat([p[k].grad.reshape(-1) for k in train_keys])
+        dist.all_reduce(flat)
+        flat /= world
+        o = 0
+        for k in train_keys:
+            n = p[k].numel()
+            p[k].grad.copy_(flat[o:o + n].view_as(p[k]))
+            o += n
+
+    def step(scenes, from_host):
+        flush_buf.fill_(0)                                  # evict L2 between steps (inside the timed region, ~40 us)
+        opt.zero_grad(set_to_none=False)
+        total = torch.zeros((), device=dev)
+        for s in scenes:
+            sc = upload(s) if from_host else s
+            r = pipeline.forward_scene(sc, p, mode="train")
+            loss = r.loss_raw[:, 0].sum() / r.loss_raw[:, 1].sum() / len(scenes)
+            loss.backward()
+            total += loss.detach()
+        allreduce_grads()
+        opt.step()
+        return total
+
+    def timed(scenes, from_host, n_steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(n_steps):
+            last = step(scenes, from_host)
+            if from_host:
+                last = float(last.item())                   # device -> host read of the step's loss
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), last
+
+    for _ in range(args.warmup):
+        step(resident, False)
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.launch_count = 0
+    _lib.time_entry = "sgb_edgeconv_fwd"
+    _lib.timed_events = []
+    ms, _ = timed(resident, False, args.steps)
+    launches = _lib.launch_count
+    kernel_events = _lib.timed_events
+    _lib.time_entry = None
+    clocks = sampler.stop() if rank == 0 else None
+    pts_per_step = args.scenes * args.points * world
+    value = pts_per_step * args.steps / (ms * 1e-3)
+    # ---- timed region 2: end to end from pinned host buffers
+    step(pinned, True)
+    ms_e2e, _ = timed(pinned, True, args.steps)
+    e2e = pts_per_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        # dominant kernel: EdgeConv forward of MLP3 (two_layer launches are every second call).  Algorithmic bytes
+        # (SURVEY.md 8d): 36 (x9) + 4*20 (knn) + 256 (out) + 64 (arg-max edge kept for backward) per point.
+        ev = [e0.elapsed_time(e1) for (tag, e0, e1) in kernel_events if tag == 1]
+        k_ms = float(np.mean(ev)) if ev else None
+        alg_bytes = args.points * (36 + 80 + 256 + 64)
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
+        roofline = {"bound": "hbm", "kernel": "sgb_edgeconv_fwd (MLP3: moments + moments2 + max pass)", "achieved": achieved,
+                    "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"] if achieved else None,
+                    "traffic": None, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": len(ev)}
+        cpu = None
+        if not args.no_cpu_baseline:
+            pps, sec, cores = cpu_port_points_per_sec(args.ref_points)
+            cpu = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "1 scene x %d points fwd+bwd (%.1f s) of the %d x %d batch" % (args.ref_points, sec, args.scenes, args.points)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "SegGroup training step fwd+bwd+SGD, %d scenes x %d points per GPU (BASELINE configs[1])" % (args.scenes, args.points),
+                           "weights": "torch.manual_seed(1) default init, mlp_1.bn1.weight x %g" % GSCALE, "l2": "256 MiB flush buffer written every step",
+                           "parallelism": "dp%d" % world if world > 1 else "single"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

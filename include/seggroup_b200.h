@@ -221,6 +221,10 @@ int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* n
 int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
                       const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem, void* stream);
 
+/* HOST function: writes n lines '%d\n' to `path` — the text format of seggroup/model.py:536-546 that the stage-2
+ * consumers read (kpconv/datasets/Scannet2.py:148-156).  `values` is a host pointer. */
+int sgb_write_labels_host(const char* path, const int* values, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,10 +82,67 @@ def _ptr(x):
         return None
     if isinstance(x, int):
         return ctypes.c_void_p(x)
+    if isinstance(x, bytes):
+        return ctypes.cast(ctypes.c_char_p(x), ctypes.c_void_p)
+    if hasattr(x, "ctypes"):                       # host numpy array (only for *_host entry points)
+        return ctypes.c_void_p(x.ctypes.data)
     return ctypes.c_void_p(x.data_ptr())          # torch tensor
 
 
+# optional per-entry-point device timing (tools/profile_scene.py): name -> [calls, ms]
+profile = None
+
+# bench.py bookkeeping: kernels launched per entry point (counted from csrc/*.cu), and CUDA-event pairs around
+# one chosen entry point (recorded on the launching stream, resolved by the caller after its final synchronize).
+launch_count = 0
+time_entry = None
+timed_events = []
+KERNELS_PER_CALL = {"sgb_exclusive_scan_i32": 3, "sgb_segment_pool_max_fwd": 2, "sgb_segment_pool_max_bwd": 1, "sgb_cluster_knn": 1,
+                    "sgb_cluster_cloud_indices": 1, "sgb_cluster_cloud_transform": 1, "sgb_centralize": 2, "sgb_mlp1_fwd": 3,
+                    "sgb_mlp1_bwd": 3, "sgb_scene_init": 2, "sgb_level_build": 14, "sgb_level_children": 6, "sgb_update_adj": 6,
+                    "sgb_sym_csr": 6, "sgb_edge_dist_fwd": 1, "sgb_edge_dist_bwd": 1, "sgb_gcn_agg_fwd": 1, "sgb_gcn_agg_bwd": 2,
+                    "sgb_group_nearby": 1, "sgb_group_unlabeled_step": 2, "sgb_export_labels": 1}
+
+
+def _kernels(name, args):
+    if name == "sgb_edgeconv_fwd":
+        return 8 if args[3] else 5
+    if name == "sgb_edgeconv_bwd":
+        return 5 if args[7] else 2
+    return KERNELS_PER_CALL.get(name, 0)
+
+
+def enable_profile():
+    global profile
+    profile = {}
+
+
 def call(name: str, *args):
+    global launch_count
+    launch_count += _kernels(name, args)
+    if time_entry is not None and name == time_entry:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _call(name, *args)
+        e1.record()
+        timed_events.append((args[3] if name == "sgb_edgeconv_fwd" else 0, e0, e1))
+        return rc
+    if profile is not None and not name.endswith("_bytes"):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _call(name, *args)
+        e1.record()
+        e1.synchronize()
+        rec = profile.setdefault(name, [0, 0.0])
+        rec[0] += 1
+        rec[1] += e0.elapsed_time(e1)
+        return rc
+    return _call(name, *args)
+
+
+def _call(name: str, *args):
     """Call `name`; tensors / None / ints are passed as pointers where the prototype has a pointer.
     Raises SgbError on a negative status.  Returns the int / size_t result."""
     lib = load()

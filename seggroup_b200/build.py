@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu") or f.endswith(".cpp"))
 
 
 def _digest():
@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
 
     def compile_one(src):
-        obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(OUT_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

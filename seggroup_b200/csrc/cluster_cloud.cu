@@ -116,30 +116,44 @@ cluster_cloud_indices_kernel(const float* __restrict__ xyz, int stride, const in
 }
 
 // one warp per cluster: mean over the P rows, centre, scale by max |xyz|.
+// The mean reproduces torch-CPU's fp32 summation order for a [P<=64, 3] reduction over dim 0 (probed: four
+// interleaved row accumulators, row i -> acc[i % 4], combined ((a0+a1)+a2)+a3), so the transformed clouds —
+// and the kNN ranking computed on them — are bit-identical to the reference.
 __global__ void cluster_cloud_transform_kernel(const float* __restrict__ data6, const int* __restrict__ cloud_idx,
                                                int S, int P, float* __restrict__ clouds) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= S) return;
     const int* idx = cloud_idx + (size_t)c * P;
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (int i = lane; i < P; i += 32) {
-        const float* p = data6 + (size_t)__ldg(idx + i) * 6;
-        sx += __ldg(p); sy += __ldg(p + 1); sz += __ldg(p + 2);
+    float m = 0.f;
+    if (lane < 3) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int i = 0;
+        for (; i + 3 < P; i += 4) {
+            a0 = __fadd_rn(a0, __ldg(data6 + (size_t)__ldg(idx + i) * 6 + lane));
+            a1 = __fadd_rn(a1, __ldg(data6 + (size_t)__ldg(idx + i + 1) * 6 + lane));
+            a2 = __fadd_rn(a2, __ldg(data6 + (size_t)__ldg(idx + i + 2) * 6 + lane));
+            a3 = __fadd_rn(a3, __ldg(data6 + (size_t)__ldg(idx + i + 3) * 6 + lane));
+        }
+        if (i < P) a0 = __fadd_rn(a0, __ldg(data6 + (size_t)__ldg(idx + i) * 6 + lane));
+        if (i + 1 < P) a1 = __fadd_rn(a1, __ldg(data6 + (size_t)__ldg(idx + i + 1) * 6 + lane));
+        if (i + 2 < P) a2 = __fadd_rn(a2, __ldg(data6 + (size_t)__ldg(idx + i + 2) * 6 + lane));
+        m = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3), (float)P);
     }
-    sx = sgb_warp_sum(sx); sy = sgb_warp_sum(sy); sz = sgb_warp_sum(sz);
-    const float mx = sx / (float)P, my = sy / (float)P, mz = sz / (float)P;
+    const float mx = __shfl_sync(SGB_FULL_MASK, m, 0), my = __shfl_sync(SGB_FULL_MASK, m, 1), mz = __shfl_sync(SGB_FULL_MASK, m, 2);
     float amax = 0.f;
     for (int i = lane; i < P; i += 32) {
         const float* p = data6 + (size_t)__ldg(idx + i) * 6;
-        amax = fmaxf(amax, fmaxf(fabsf(__ldg(p) - mx), fmaxf(fabsf(__ldg(p + 1) - my), fabsf(__ldg(p + 2) - mz))));
+        amax = fmaxf(amax, fmaxf(fabsf(__fsub_rn(__ldg(p), mx)), fmaxf(fabsf(__fsub_rn(__ldg(p + 1), my)), fabsf(__fsub_rn(__ldg(p + 2), mz)))));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(SGB_FULL_MASK, amax, o));
     for (int i = lane; i < P; i += 32) {
         const float* p = data6 + (size_t)__ldg(idx + i) * 6;
         float* o = clouds + ((size_t)c * P + i) * 6;
-        o[0] = (__ldg(p) - mx) / amax; o[1] = (__ldg(p + 1) - my) / amax; o[2] = (__ldg(p + 2) - mz) / amax;
+        o[0] = __fdiv_rn(__fsub_rn(__ldg(p), mx), amax);
+        o[1] = __fdiv_rn(__fsub_rn(__ldg(p + 1), my), amax);
+        o[2] = __fdiv_rn(__fsub_rn(__ldg(p + 2), mz), amax);
         o[3] = __ldg(p + 3); o[4] = __ldg(p + 4); o[5] = __ldg(p + 5);
     }
 }

@@ -1,0 +1,45 @@
+"""CUDA path against the golden vectors minted from the unmodified reference (tests/golden/): pseudo-label ids
+bit-exact, loss / metrics / gradients within 1e-4 (gradients 1e-3) relative."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_oracle_golden import CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode,g", CASES)
+def test_cuda_matches_reference_golden(scene8k, mode, g):
+    from seggroup_b200 import pipeline
+    from seggroup_b200.params import TRAINABLE, init_params
+    gold = load_golden(mode, g)
+    p = {k: v.cuda() for k, v in init_params(1, g).items()}
+    mask = None
+    if mode == "train":
+        for k in TRAINABLE:
+            p[k].requires_grad_(True)
+        n_inst = int(gold["out/0"][0, 1])
+        torch.manual_seed(1001)
+        mask = (F.dropout(torch.ones(n_inst, 128), 0.5, True) != 0).cuda()
+    sc = pipeline.SceneDevice.from_host(scene8k)
+    with torch.set_grad_enabled(mode == "train"):
+        res = pipeline.forward_scene(sc, p, mode=mode, dropout_mask=mask)
+    assert res.status == 0
+    for k in gold.files:
+        if k.startswith("label/"):
+            got = res.labels[k[6:]].cpu().numpy()
+            assert np.array_equal(got, gold[k]), "%s: %d vertices differ" % (k, (got != gold[k]).sum())
+    metrics = [gold["out/%d" % i] for i in range(4 if mode == "train" else 3)]
+    if mode == "train":
+        assert np.allclose(res.loss_raw.detach().cpu().numpy(), metrics[0], rtol=1e-4)
+        metrics = metrics[1:]
+        (res.loss_raw[:, 0].sum() / res.loss_raw[:, 1].sum()).backward()
+        for k in TRAINABLE:
+            if "grad/" + k in gold.files:
+                gr = gold["grad/" + k]
+                err = np.abs(p[k].grad.cpu().numpy() - gr).max() / (np.abs(gr).max() + 1e-30)
+                assert err < 1e-3, (k, err)
+    for a, b in zip(res.metrics, metrics):
+        assert np.allclose(a.cpu().numpy(), b, atol=1e-6)

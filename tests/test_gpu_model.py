@@ -1,0 +1,101 @@
+"""Boundary B1: the nn.Module drop-in (`seggroup_b200.model.SegModel`) driven the way seggroup/train.py and
+infer.py drive the reference: tensors shaped [1,N,6] / [1,N,2] / [1,1], side files read by relative path, the
+14 label files written, loss tuple returned, gradients in .grad after backward, BN buffers updated."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def tree(tmp_path, scene8k):
+    from seggroup_b200 import synth
+    synth.write_scene_tree(str(tmp_path), [scene8k])
+    old = os.getcwd()
+    os.chdir(tmp_path)
+    yield tmp_path
+    os.chdir(old)
+
+
+def _inputs(scene):
+    data = torch.from_numpy(scene.data.copy()).unsqueeze(0).cuda()
+    weak = torch.from_numpy(scene.weak_label.copy()).unsqueeze(0).cuda()
+    info = torch.tensor([[0]]).cuda()       # DDP moves `info` to the GPU as well
+    return data, weak, info
+
+
+def test_train_step_matches_oracle(tree, scene8k):
+    from oracle import seggroup_oracle as O
+    from seggroup_b200.model import SegModel
+    torch.manual_seed(1)
+    model = SegModel(exp_name="t").to("cuda")
+    with torch.no_grad():
+        model.mlp_1.bn1.weight.mul_(4.0)
+    model.classifier.dp1.p = 0.0            # identity dropout so the oracle can follow (mask 0.5 * 2 = 1)
+    model.train()
+    model.epoch = "1"
+    params = O.from_reference_state({k: v.detach().cpu() for k, v in model.state_dict().items()})
+    out = model(*_inputs(scene8k))
+    assert len(out) == 4 and out[0].shape == (1, 2) and out[1].shape == (1, 2, 40) and out[3].shape == (4,)
+    loss = torch.sum(out[0][:, 0]) / torch.sum(out[0][:, 1])       # train.py:165-167
+    loss.backward()
+    model.flush_exports()
+    probe = O.forward(scene8k, params, mode="ins_infer", tie="canonical")
+    n_inst = len(np.unique(probe["levels"][-1].ins))
+    ref = O.forward(scene8k, params, mode="train", tie="canonical", dropout_mask=torch.full((n_inst, 128), 0.5), want_grads=True)
+    assert abs(float(out[0][0, 0]) - ref["loss_raw"][0, 0]) < 1e-4 * abs(ref["loss_raw"][0, 0])
+    root = os.path.join("results", "t", scene8k.name, "epoch_1")
+    files = sorted(os.listdir(root))
+    assert len(files) == 14
+    for k, v in ref["labels"].items():
+        got = np.loadtxt(os.path.join(root, k + ".txt"), dtype=np.int64)
+        assert np.array_equal(got, v), k
+    named = dict(model.named_parameters())
+    for k in O.TRAINABLE:
+        gr = ref["grads"][k]
+        if gr is None:
+            continue
+        g = named[k].grad.cpu()
+        assert float((g - gr).abs().max()) <= 1e-3 * float(gr.abs().max()) + 1e-7, k
+    for a, b in zip(out[1:], ref["metrics"]):
+        assert np.allclose(a.cpu().numpy(), b, atol=1e-6)
+    assert int(model.mlp_2.bn1.num_batches_tracked) == 1 and float(model.mlp_2.bn1.running_mean.abs().sum()) > 0
+
+
+def test_infer_modes_and_optimizer(tree, scene8k):
+    from seggroup_b200.model import SegModel
+    torch.manual_seed(1)
+    for flags, tag, n_files in ((dict(sem_infer=True), "sem_infer", 6), (dict(ins_infer=True), "ins_infer", 14)):
+        model = SegModel(exp_name="i", **flags).to("cuda")
+        model.epoch = tag
+        with torch.no_grad():
+            out = model(*_inputs(scene8k))
+        model.flush_exports()
+        assert len(out) == 3
+        assert len(os.listdir(os.path.join("results", "i", scene8k.name, tag))) == n_files
+    # two SGD steps as train.py runs them (lr 0.1, momentum 0.9, wd 1e-4): the loss must stay finite and parameters move
+    model = SegModel(exp_name="o").to("cuda")
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    model.epoch = "1"
+    w0 = model.mlp_3.conv2[0].weight.detach().clone()
+    for _ in range(2):
+        loss_raw = model(*_inputs(scene8k))[0]
+        loss = torch.sum(loss_raw[:, 0]) / torch.sum(loss_raw[:, 1])
+        opt.zero_grad(); loss.backward(); opt.step()
+        assert torch.isfinite(loss)
+    assert float((model.mlp_3.conv2[0].weight - w0).abs().max()) > 0
+    sd = model.state_dict()
+    model2 = SegModel(exp_name="o2")
+    model2.load_state_dict(sd)
+
+
+def test_cpu_input_is_refused(tree, scene8k):
+    from seggroup_b200._lib import SgbError
+    from seggroup_b200.model import SegModel
+    model = SegModel(exp_name="c")
+    d, w, i = _inputs(scene8k)
+    with pytest.raises(SgbError):
+        model(d.cpu(), w.cpu(), i.cpu())
