@@ -221,6 +221,62 @@ int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* n
 int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
                       const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * a18  grid subsampling (boundaries B2 / B3)
+ * replaces kpconv/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106 (what
+ * `grid_subsampling.compute`, wrapper.cpp:58-286, runs) and kpconv/tf_custom_ops/tf_subsampling/
+ * grid_subsampling/grid_subsampling.cpp:5-150 (`GridSubsampling` / `BatchGridSubsampling` ops).
+ * points [N,3]; feat [N,fdim] / cls [N,ldim] optional (NULL, dim 0); batches [B] device lengths (NULL = one cloud,
+ * B = 1).  Voxel key, origin and NX/NY use the reference's fp32 expressions; barycentre = fp32 sum in input order
+ * times (float)(1.0/count), feature mean = fp32 sum / (float)count (bit-identical to the reference).  Voxels are
+ * listed per batch element in order of FIRST OCCURRENCE (the reference: hash-map iteration order); label ties ->
+ * smallest label.  Outputs are sized for M = N; counts[0] <- M; out_first [N] = input index of each voxel's first
+ * point (may be NULL); out_batches [B] (may be NULL).  status |= 4 bad batch lengths, |= 8 grid finer than 2^44 cells.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_grid_subsample_ws_bytes(int N, int B);
+int sgb_grid_subsample(const float* xyz, const float* feat, const int* cls, int N, int fdim, int ldim,
+                       const int* batches, int B, float dl, float* out_xyz, float* out_feat, int* out_cls,
+                       int* out_first, int* out_batches, int* counts, int* status,
+                       void* ws, size_t ws_bytes, void* stream);
+/* per batch element min / max corner: minmax [B][6], boff_out [B+1] */
+int sgb_batch_bounds(const float* xyz, int N, const int* batches, int B, float* minmax, int* boff_out, int* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a19  batched radius neighbours (boundary B3)
+ * replaces kpconv/tf_custom_ops/tf_neighbors/neighbors/neighbors.cpp:211-332 `batch_nanoflann_neighbors` (the
+ * function the `BatchOrderedNeighbors` op calls, tf_batch_neighbors.cpp:93) and the brute-force variants :58-208.
+ * Strict d2 < r*r with d2 = dx*dx + dy*dy + dz*dz in fp32 left to right; rows sorted by (d2, index), padded with Ns,
+ * indices global (batch offset added).  The row width is the global maximum count -> two phases sharing `ws`:
+ * _count builds the hashed support grid and writes the maximum count to max_count_out (device int), the caller
+ * reads it back, allocates neighbors [Nq, W] and calls _fill.  status |= 16 grid too large, |= 32 > 1024 hits.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_radius_neighbors_ws_bytes(int Nq, int Ns, int B);
+int sgb_radius_neighbors_count(const float* queries, int Nq, const float* supports, int Ns, const int* q_batches,
+                               const int* s_batches, int B, float radius, int* max_count_out, int* status,
+                               void* ws, size_t ws_bytes, void* stream);
+int sgb_radius_neighbors_fill(const float* queries, int Nq, const float* supports, int Ns, int B, float radius, int W,
+                              int* neighbors, int* status, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a20  rigid KPConv (boundary B4)
+ * replaces kpconv/kernels/convolution_ops.py:161-249 `KPConv_ops` (argument order kept): query_points [n,3],
+ * support_points [n0,3], neighbors [n,W] int32 (index >= n0 = shadow neighbour), features [n0,Cin], K_points [K,3],
+ * K_values [K,Cin,Cout], KP_extent; influence 0 'linear' / 1 'constant' / 2 'gaussian' (sigma = 0.3 extent);
+ * closest 0 'sum' / 1 'closest' aggregation.  out [n,Cout].  fp32 throughout (1e-4 relative vs an fp64 evaluation).
+ * Limits: K <= 17, Cout multiple of 4 and <= 1024.
+ * ------------------------------------------------------------------------------------------- */
+int sgb_kpconv_fwd(const float* query_points, const float* support_points, const int* neighbors, const float* features,
+                   const float* K_points, const float* K_values, int n, int n0, int W, int Cin, int Cout, int K,
+                   float KP_extent, int influence, int closest, float* out, void* stream);
+
+/* gradients of sgb_kpconv_fwd w.r.t. features (gfeat [n0,Cin], accumulated: caller zero-fills) and K_values
+ * (gK [K,Cin,Cout], overwritten; deterministic).  g [n,Cout] = upstream gradient. */
+size_t sgb_kpconv_bwd_ws_bytes(int n, int Cin, int Cout, int K);
+int sgb_kpconv_bwd(const float* g, const float* query_points, const float* support_points, const int* neighbors,
+                   const float* features, const float* K_points, const float* K_values, int n, int n0, int W, int Cin, int Cout,
+                   int K, float KP_extent, int influence, int closest, float* gfeat, float* gK,
+                   void* ws, size_t ws_bytes, void* stream);
+
 /* HOST function: writes n lines '%d\n' to `path` — the text format of seggroup/model.py:536-546 that the stage-2
  * consumers read (kpconv/datasets/Scannet2.py:148-156).  `values` is a host pointer. */
 int sgb_write_labels_host(const char* path, const int* values, int n);

@@ -1,0 +1,183 @@
+"""TEST INFRASTRUCTURE — CPU restatement (oracle) of the KPConv operator set: grid subsampling, batch radius
+neighbours and the rigid KPConv operator.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import it.
+
+Pinning: grid subsampling and neighbours are checked against the compiled, unmodified reference cores
+(oracle/_ref, tests/test_kpconv_oracle.py) through the canonical forms defined here — the reference's output
+ORDER is libstdc++ hash-map iteration order / std::sort tie order, which no other implementation can follow
+(SURVEY.md 7.3 #4, #5).  `kpconv_ops` restates kpconv/kernels/convolution_ops.py:161-249 (TensorFlow is not
+installable here, so it is pinned only by derivation: PARITY UNPINNED for that function, fp64 evaluation is the
+golden).
+
+Canonical forms:
+  * subsampled voxels are listed per batch element in order of FIRST OCCURRENCE (the point with the smallest
+    input index of every voxel, ascending) — i.e. the order in which the reference inserts them into its map;
+  * majority label ties -> smallest label;
+  * neighbour rows are sorted by (squared distance, index).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# grid subsampling  (kpconv/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106,
+#                    kpconv/tf_custom_ops/tf_subsampling/grid_subsampling/grid_subsampling.cpp:5-150)
+# ------------------------------------------------------------------------------------------------
+def voxel_keys(points, dl):
+    """fp32 arithmetic of grid_subsampling.cpp:24-56 -> (uint64 keys, origin, NX, NY)."""
+    p = np.ascontiguousarray(points, np.float32)
+    dl = np.float32(dl)
+    mn, mx = p.min(0), p.max(0)
+    inv = np.float32(1) / dl                                 # `1/sampleDl` (int / float -> float)
+    origin = (np.floor(mn * inv) * dl).astype(np.float32)
+    nx = np.uint64(np.floor((mx[0] - origin[0]) / dl)) + np.uint64(1)
+    ny = np.uint64(np.floor((mx[1] - origin[1]) / dl)) + np.uint64(1)
+    idx = np.floor((p - origin[None, :]) / dl).astype(np.uint64)
+    return idx[:, 0] + nx * idx[:, 1] + nx * ny * idx[:, 2], origin, nx, ny
+
+
+def grid_subsampling(points, features=None, classes=None, dl=0.1):
+    """Single cloud.  Returns (sub_points [M,3], sub_features or None, sub_classes [M,ld] or None, first_index [M])
+    in canonical (first occurrence) order.  Sums run in input order in fp32, barycentre = sum * (float)(1.0/count),
+    feature mean = sum / (float)count (grid_subsampling.cpp:85-95)."""
+    p = np.ascontiguousarray(points, np.float32)
+    keys, _, _, _ = voxel_keys(p, dl)
+    _, first, inv, cnt = np.unique(keys, return_index=True, return_inverse=True, return_counts=True)
+    order = np.argsort(first, kind="stable")                  # voxels by first occurrence
+    rank = np.empty_like(order); rank[order] = np.arange(len(order))
+    vox = rank[inv]                                           # voxel id of every point
+    M = len(order)
+    sums = np.zeros((M, 3), np.float32)
+    for i in range(len(p)):                                   # input order, fp32 (np.add.at is not order-safe for floats)
+        sums[vox[i]] += p[i]
+    counts = cnt[order]
+    scale = (1.0 / counts.astype(np.float64)).astype(np.float32)
+    sub = sums * scale[:, None]
+    subf = None
+    if features is not None:
+        f = np.ascontiguousarray(features, np.float32)
+        fs = np.zeros((M, f.shape[1]), np.float32)
+        for i in range(len(p)):
+            fs[vox[i]] += f[i]
+        subf = fs / counts.astype(np.float32)[:, None]
+    subc = None
+    if classes is not None:
+        c = np.ascontiguousarray(classes, np.int32)
+        if c.ndim == 1:
+            c = c[:, None]
+        subc = np.empty((M, c.shape[1]), np.int32)
+        by_vox = np.argsort(vox, kind="stable")
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        for v in range(M):
+            rows = c[by_vox[starts[v]:starts[v + 1]]]
+            for d in range(c.shape[1]):
+                vals, n = np.unique(rows[:, d], return_counts=True)
+                subc[v, d] = vals[np.argmax(n)]               # ties -> smallest label
+    return sub, subf, subc, first[order]
+
+
+def batch_grid_subsampling(points, batches, dl):
+    """tf variant (points only): per batch element its own origin; -> (sub_points, sub_batches)."""
+    out, lens, s = [], [], 0
+    for b in batches:
+        sub, _, _, _ = grid_subsampling(points[s:s + b], dl=dl)
+        out.append(sub); lens.append(len(sub)); s += b
+    return np.concatenate(out, 0), np.array(lens, np.int32)
+
+
+def reference_to_canonical(ref_points, points, dl):
+    """Permutation that brings the reference's output (libstdc++ hash-map iteration order) into canonical order:
+    every barycentre is assigned to its voxel with the ORIGINAL cloud's origin / NX / NY, then voxels are ordered
+    by first occurrence.  Returns perm with ref_points[perm] canonical."""
+    p = np.ascontiguousarray(points, np.float32)
+    keys, origin, nx, ny = voxel_keys(p, dl)
+    uk, first = np.unique(keys, return_index=True)
+    idx = np.floor((np.asarray(ref_points, np.float32) - origin[None, :]) / np.float32(dl)).astype(np.uint64)
+    rk = idx[:, 0] + nx * idx[:, 1] + nx * ny * idx[:, 2]
+    pos = np.searchsorted(uk, rk)
+    if len(np.unique(rk)) != len(rk) or not np.array_equal(uk[np.clip(pos, 0, len(uk) - 1)], rk):
+        raise ValueError("a reference barycentre does not fall inside its own voxel (fp32 edge case): pick another seed")
+    return np.argsort(first[pos], kind="stable")
+
+
+# ------------------------------------------------------------------------------------------------
+# radius neighbours  (kpconv/tf_custom_ops/tf_neighbors/neighbors/neighbors.cpp:125-332)
+# ------------------------------------------------------------------------------------------------
+def canonical_rows(nb, queries, supports):
+    """Sort every row of a reference neighbour matrix by (d2, index); padding (index == Ns) stays at the end."""
+    q = np.asarray(queries, np.float32); s = np.asarray(supports, np.float32)
+    Ns = len(s)
+    out = nb.copy()
+    for i in range(len(nb)):
+        row = nb[i]
+        v = row[row < Ns]
+        d = q[i][None, :] - s[v]
+        d2 = ((d[:, 0] * d[:, 0]).astype(np.float32) + (d[:, 1] * d[:, 1]).astype(np.float32)).astype(np.float32) + (d[:, 2] * d[:, 2]).astype(np.float32)
+        o = np.lexsort((v, d2.astype(np.float32)))
+        out[i, :len(v)] = v[o]
+    return out
+
+
+def batch_neighbors(queries, supports, q_batches, s_batches, radius, chunk=2048):
+    """Brute force, fp32 d2 = dx*dx + dy*dy + dz*dz (left to right), strict d2 < r*r, rows sorted by (d2, index),
+    padded with Ns to the global maximum count."""
+    q = np.asarray(queries, np.float32); s = np.asarray(supports, np.float32)
+    r2 = np.float32(radius) * np.float32(radius)
+    rows = []
+    qs = ss = 0
+    for qb, sb in zip(q_batches, s_batches):
+        S = s[ss:ss + sb]
+        for c0 in range(qs, qs + qb, chunk):
+            Q = q[c0:min(c0 + chunk, qs + qb)]
+            d = Q[:, None, :] - S[None, :, :]
+            d2 = ((d[..., 0] * d[..., 0]) + (d[..., 1] * d[..., 1])).astype(np.float32) + (d[..., 2] * d[..., 2])
+            d2 = d2.astype(np.float32)
+            for i in range(len(Q)):
+                v = np.nonzero(d2[i] < r2)[0]
+                o = np.lexsort((v, d2[i][v]))
+                rows.append(v[o] + ss)
+        qs += qb; ss += sb
+    W = max((len(r) for r in rows), default=0)
+    out = np.full((len(q), W), len(s), np.int32)
+    for i, r in enumerate(rows):
+        out[i, :len(r)] = r
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# KPConv  (kpconv/kernels/convolution_ops.py:161-249)
+# ------------------------------------------------------------------------------------------------
+def kpconv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
+               KP_influence="linear", aggregation_mode="sum", dtype=None):
+    """torch restatement; tensors in, tensor out (differentiable w.r.t. features and K_values)."""
+    import torch
+    dt = dtype or features.dtype
+    q = query_points.to(dt); s = support_points.to(dt); f = features.to(dt); Kp = K_points.to(dt); Kv = K_values.to(dt)
+    idx = neighbors_indices.long()
+    n_kp = Kp.shape[0]
+    shadow = torch.ones_like(s[:1, :]) * 1e6                                   # :190
+    s = torch.cat([s, shadow], dim=0)                                          # :191
+    nb = s[idx]                                                                # :194  [n, W, 3]
+    nb = nb - q.unsqueeze(1)                                                   # :197
+    diff = nb.unsqueeze(2) - Kp.view(1, 1, n_kp, 3)                            # :200-203  [n, W, K, 3]
+    sq = (diff ** 2).sum(dim=3)                                                # :205
+    if KP_influence == "constant":                                             # :208-212
+        w = torch.ones_like(sq).transpose(1, 2)
+    elif KP_influence == "linear":                                             # :214-217
+        w = torch.clamp(1 - torch.sqrt(sq) / KP_extent, min=0.0).transpose(1, 2)
+    elif KP_influence == "gaussian":                                           # :219-222, radius_gaussian :48-55
+        sigma = KP_extent * 0.3
+        w = torch.exp(-sq / (2 * sigma ** 2 + 1e-9)).transpose(1, 2)
+    else:
+        raise ValueError("Unknown influence function type (config.KP_influence)")
+    if aggregation_mode == "closest":                                          # :227-229
+        nn_idx = torch.argmin(sq, dim=2)
+        w = w * torch.nn.functional.one_hot(nn_idx, n_kp).to(dt).transpose(1, 2)
+    elif aggregation_mode != "sum":
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    f = torch.cat([f, torch.zeros_like(f[:1, :])], dim=0)                      # :234
+    nf = f[idx]                                                                # :237  [n, W, Cin]
+    wf = torch.matmul(w, nf)                                                   # :240  [n, K, Cin]
+    wf = wf.permute(1, 0, 2)                                                   # :243
+    out = torch.matmul(wf, Kv)                                                 # :244  [K, n, Cout]
+    return out.sum(dim=0)                                                      # :247

@@ -324,30 +324,82 @@ __global__ void gcn_agg_bwd_s_kernel(const float* __restrict__ dAX, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
-// group_nearby_clusters (model.py:218-258) — sequential replay on one thread.
-// status bit 1 (value 2): the small-cluster sweep hit the cap (the reference would spin forever).
+// group_nearby_clusters (model.py:218-258) — sequential replay by ONE thread, everything else parallel:
+// the union-find state is staged in shared memory (24 B per level-1 segment), edges stream through shared
+// memory in chunks with their endpoints already resolved to level-1 roots and the `dist > th` test already
+// applied by the whole CTA, and the small-cluster sweep only runs after a CTA-wide check found a cluster
+// with < 5 points (a cluster never shrinks, so "no small endpoint now" == "the sweep would attempt nothing").
+// status bit 1 (value 2): the sweep cap was hit (the reference would spin forever).
 // ---------------------------------------------------------------------------------------------
-__global__ void group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ roots_cur,
-                                    const float* __restrict__ dist, float th, int* __restrict__ ufb, int S1,
-                                    int sweep_cap, int* __restrict__ status) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    UF u(ufb, S1);
-    for (int i = 0; i < A; ++i) {
-        if (dist[i] > th) continue;                   // NaN distance -> comparison false -> merge attempt, as in Python
-        const int c1 = uf_find(u, roots_cur[adj[2 * i]]);
-        const int c2 = uf_find(u, roots_cur[adj[2 * i + 1]]);
-        uf_union(u, c1, c2);
+constexpr int GN_THREADS = 256;
+constexpr int GN_CHUNK = 2048;
+
+__global__ void __launch_bounds__(GN_THREADS)
+group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ roots_cur,
+                    const float* __restrict__ dist, float th, int* __restrict__ ufb, int S1,
+                    int sweep_cap, int* __restrict__ status, int state_in_smem) {
+    extern __shared__ int gn_smem[];
+    __shared__ int s_ru[GN_CHUNK], s_rv[GN_CHUNK];
+    __shared__ int s_flag;
+    int* base = state_in_smem ? gn_smem : ufb;
+    if (state_in_smem) {
+        for (int i = threadIdx.x; i < 6 * S1; i += GN_THREADS) gn_smem[i] = ufb[i];
     }
+    __syncthreads();
+    UF u(base, S1);
+    // pass 1: edges in order, skip iff dist > th (NaN compares false -> merge attempt, as in Python)
+    for (int c0 = 0; c0 < A; c0 += GN_CHUNK) {
+        const int n = min(GN_CHUNK, A - c0);
+        for (int i = threadIdx.x; i < n; i += GN_THREADS) {
+            const int e = c0 + i;
+            const bool skip = dist[e] > th;
+            s_ru[i] = skip ? -1 : roots_cur[adj[2 * e]];
+            s_rv[i] = skip ? -1 : roots_cur[adj[2 * e + 1]];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < n; ++i) {
+                if (s_ru[i] < 0) continue;
+                uf_union(u, uf_find(u, s_ru[i]), uf_find(u, s_rv[i]));
+            }
+        }
+        __syncthreads();
+    }
+    // pass 2: sweeps over ALL edges while some endpoint cluster has < 5 points
     int sweeps = 0;
     while (true) {
-        bool attempted = false;
-        for (int i = 0; i < A; ++i) {
-            const int c1 = uf_find(u, roots_cur[adj[2 * i]]);
-            const int c2 = uf_find(u, roots_cur[adj[2 * i + 1]]);
-            if (u.pnum[c1] < 5 || u.pnum[c2] < 5) { uf_union(u, c1, c2); attempted = true; }
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+        int any = 0;
+        for (int e = threadIdx.x; e < A; e += GN_THREADS) {
+            const int c1 = uf_find_ro(u.parent, roots_cur[adj[2 * e]]);
+            const int c2 = uf_find_ro(u.parent, roots_cur[adj[2 * e + 1]]);
+            any |= (u.pnum[c1] < 5 || u.pnum[c2] < 5);
         }
-        if (!attempted) break;
-        if (++sweeps > sweep_cap) { atomicOr(status, 2); break; }
+        if (any) s_flag = 1;
+        __syncthreads();
+        if (!s_flag) break;
+        if (sweeps >= sweep_cap) { if (threadIdx.x == 0) atomicOr(status, 2); break; }
+        ++sweeps;
+        for (int c0 = 0; c0 < A; c0 += GN_CHUNK) {
+            const int n = min(GN_CHUNK, A - c0);
+            for (int i = threadIdx.x; i < n; i += GN_THREADS) {
+                s_ru[i] = roots_cur[adj[2 * (c0 + i)]];
+                s_rv[i] = roots_cur[adj[2 * (c0 + i) + 1]];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < n; ++i) {
+                    const int c1 = uf_find(u, s_ru[i]), c2 = uf_find(u, s_rv[i]);
+                    if (u.pnum[c1] < 5 || u.pnum[c2] < 5) uf_union(u, c1, c2);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (state_in_smem) {
+        for (int i = threadIdx.x; i < 6 * S1; i += GN_THREADS) ufb[i] = gn_smem[i];
     }
 }
 
@@ -566,7 +618,12 @@ extern "C" int sgb_group_nearby(const int* adj, int A, const int* roots_cur, con
     if (A < 0 || S1 <= 0 || !uf || !status) return SGB_ERR_INVALID;
     if (A == 0) return SGB_OK;
     if (!adj || !roots_cur || !dist) return SGB_ERR_INVALID;
-    group_nearby_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(adj, A, roots_cur, dist, th, uf, S1, sweep_cap, status);
+    const size_t state_bytes = (size_t)6 * S1 * sizeof(int);
+    const int in_smem = state_bytes <= 160 * 1024;
+    if (in_smem && state_bytes > 16 * 1024)
+        SGB_CUDA(cudaFuncSetAttribute(group_nearby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)state_bytes));
+    group_nearby_kernel<<<1, GN_THREADS, in_smem ? state_bytes : 0, (cudaStream_t)stream>>>(adj, A, roots_cur, dist, th, uf, S1, sweep_cap,
+                                                                                           status, in_smem);
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

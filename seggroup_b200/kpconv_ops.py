@@ -1,0 +1,196 @@
+"""KPConv operator set on the CUDA kernels, behind the reference's call signatures (boundaries B2-B4).
+
+  B2  grid_subsampling.compute(points, features=None, classes=None, sampleDl=0.1, method='barycenters', verbose=0)
+      numpy in / numpy out, same RuntimeError messages as kpconv/cpp_wrappers/cpp_subsampling/wrapper.cpp:58-286
+  B3  batch_grid_subsampling(points, batches, dl), grid_subsampling_op(points, dl),
+      batch_ordered_neighbors(queries, supports, q_batches, s_batches, radius), ordered_neighbors(queries, supports, radius)
+      CUDA tensors in / out, positional order and dtypes of kpconv/tf_custom_ops/tf_*/tf_*.cpp
+  B4  KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
+                 KP_influence, aggregation_mode)    kpconv/kernels/convolution_ops.py:161-169
+
+Output ORDER of the subsampling is canonical (voxels in order of first occurrence per batch element, label ties ->
+smallest label) and neighbour rows are sorted by (distance, index): the reference's orders are libstdc++ hash-map
+iteration order and std::sort tie order.  No CPU fallback anywhere.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import F32, I32, _chk, _stream, _ws
+
+_INFLUENCE = {"linear": 0, "constant": 1, "gaussian": 2}
+
+
+def _status_check(status, what):
+    s = int(status.item())
+    if s & 4:
+        raise RuntimeError("%s: batch lengths do not sum to the number of points" % what)
+    if s & 8:
+        raise RuntimeError("%s: voxel grid exceeds 2^44 cells (sampleDl too small for this extent)" % what)
+    if s & 16:
+        raise RuntimeError("%s: more than 2^17 grid cells along an axis (radius too small for this extent)" % what)
+    if s & 32:
+        raise RuntimeError("%s: a query has more than 1024 neighbours" % what)
+
+
+def _grid_subsample(points, features, classes, batches, dl):
+    dev = points.device
+    N = points.shape[0]
+    B = 1 if batches is None else batches.numel()
+    fdim = 0 if features is None else features.shape[1]
+    ldim = 0 if classes is None else classes.shape[1]
+    out_xyz = torch.empty(N, 3, dtype=F32, device=dev)
+    out_f = torch.empty(N, fdim, dtype=F32, device=dev) if fdim else None
+    out_c = torch.empty(N, ldim, dtype=I32, device=dev) if ldim else None
+    out_b = torch.empty(B, dtype=I32, device=dev)
+    counts = torch.zeros(4, dtype=I32, device=dev)
+    status = torch.zeros(1, dtype=I32, device=dev)
+    ws = _ws(_lib.call("sgb_grid_subsample_ws_bytes", N, B), dev)
+    _lib.call("sgb_grid_subsample", points, features, classes, N, fdim, ldim, batches, B, float(dl), out_xyz, out_f, out_c, None, out_b,
+              counts, status, ws, ws.numel(), _stream())
+    M = int(counts[0].item())
+    _status_check(status, "grid_subsampling")
+    return out_xyz[:M], (out_f[:M] if fdim else None), (out_c[:M] if ldim else None), out_b
+
+
+# ------------------------------------------------------------------------------------------------ B3
+def batch_grid_subsampling(points, batches, dl):
+    """tf_batch_subsampling.cpp:8-20: points f32 [N,3], batches i32 [B], dl -> (sub_points f32 [M,3], sub_batches i32 [B])."""
+    _chk(points, F32, "points"); _chk(batches, I32, "batches")
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise ValueError("BatchGridSubsampling expects points with shape [None, 3]")
+    sub, _, _, sb = _grid_subsample(points, None, None, batches, dl)
+    return sub, sb
+
+
+def grid_subsampling_op(points, dl):
+    """tf_subsampling.cpp:8-17: points f32 [N,3], dl -> sub_points f32 [M,3]."""
+    _chk(points, F32, "points")
+    return _grid_subsample(points, None, None, None, dl)[0]
+
+
+def batch_ordered_neighbors(queries, supports, q_batches, s_batches, radius):
+    """tf_batch_neighbors.cpp:8-30: -> neighbors i32 [Nq, W]; padding / shadow index = supports.shape[0]."""
+    _chk(queries, F32, "queries"); _chk(supports, F32, "supports")
+    if q_batches is not None:
+        _chk(q_batches, I32, "q_batches"); _chk(s_batches, I32, "s_batches")
+    dev = queries.device
+    Nq, Ns = queries.shape[0], supports.shape[0]
+    B = 1 if q_batches is None else q_batches.numel()
+    status = torch.zeros(1, dtype=I32, device=dev)
+    maxc = torch.zeros(1, dtype=I32, device=dev)
+    ws = _ws(_lib.call("sgb_radius_neighbors_ws_bytes", Nq, Ns, B), dev)
+    _lib.call("sgb_radius_neighbors_count", queries, Nq, supports, Ns, q_batches, s_batches, B, float(radius), maxc, status, ws, ws.numel(), _stream())
+    W = int(maxc.item())                          # the output width is data dependent (neighbors.cpp:296-304)
+    _status_check(status, "batch_ordered_neighbors")
+    nb = torch.empty(Nq, W, dtype=I32, device=dev)
+    _lib.call("sgb_radius_neighbors_fill", queries, Nq, supports, Ns, B, float(radius), W, nb, status, ws, ws.numel(), _stream())
+    _status_check(status, "batch_ordered_neighbors")
+    return nb
+
+
+def ordered_neighbors(queries, supports, radius):
+    """tf_neighbors.cpp:8-17 (single cloud)."""
+    return batch_ordered_neighbors(queries, supports, None, None, radius)
+
+
+# ------------------------------------------------------------------------------------------------ B4
+class _KPConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, s, idx, feats, kpts, kvals, extent, influence, closest):
+        n, n0 = q.shape[0], s.shape[0]
+        W = idx.shape[1]
+        K, Cin, Cout = kvals.shape
+        out = torch.empty(n, Cout, dtype=F32, device=q.device)
+        _lib.call("sgb_kpconv_fwd", q, s, idx, feats, kpts, kvals, n, n0, W, Cin, Cout, K, float(extent), influence, closest, out, _stream())
+        ctx.save_for_backward(q, s, idx, feats, kpts, kvals)
+        ctx.cfg = (float(extent), influence, closest)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, s, idx, feats, kpts, kvals = ctx.saved_tensors
+        extent, influence, closest = ctx.cfg
+        n, n0 = q.shape[0], s.shape[0]
+        K, Cin, Cout = kvals.shape
+        gf = torch.zeros(n0, Cin, dtype=F32, device=q.device)
+        gk = torch.zeros(K, Cin, Cout, dtype=F32, device=q.device)
+        ws = _ws(_lib.call("sgb_kpconv_bwd_ws_bytes", n, Cin, Cout, K), q.device)
+        _lib.call("sgb_kpconv_bwd", g.contiguous(), q, s, idx, feats, kpts, kvals, n, n0, idx.shape[1], Cin, Cout, K, extent, influence, closest,
+                  gf, gk, ws, ws.numel(), _stream())
+        return None, None, None, gf, None, gk, None, None, None
+
+
+def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent, KP_influence, aggregation_mode):
+    """kpconv/kernels/convolution_ops.py:161-249, same argument order; differentiable w.r.t. features and K_values."""
+    if KP_influence not in _INFLUENCE:
+        raise ValueError('Unknown influence function type (config.KP_influence)')
+    if aggregation_mode not in ("sum", "closest"):
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    q = _chk(query_points.contiguous(), F32, "query_points"); s = _chk(support_points.contiguous(), F32, "support_points")
+    idx = neighbors_indices
+    if idx.dtype != I32:
+        idx = idx.to(I32)
+    idx = _chk(idx.contiguous(), I32, "neighbors_indices")
+    return _KPConvFn.apply(q, s, idx, features.contiguous(), _chk(K_points.contiguous(), F32, "K_points"), K_values.contiguous(),
+                           KP_extent, _INFLUENCE[KP_influence], int(aggregation_mode == "closest"))
+
+
+def KPConv(query_points, support_points, neighbors_indices, features, K_values, fixed='center', KP_extent=1.0,
+           KP_influence='linear', aggregation_mode='sum', K_points=None):
+    """kpconv/kernels/convolution_ops.py:102-158.  The reference regenerates the kernel-point disposition inside this
+    call (random optimisation + rotation, kernel_points.py:182-278, unseeded); here the disposition is an explicit
+    input (`K_points`, [K,3], already scaled by the caller's K_radius) — SURVEY.md 8c."""
+    if K_points is None:
+        raise ValueError("K_points must be given: kernel-point dispositions are an input of the op (SURVEY.md 8c)")
+    return KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent, KP_influence, aggregation_mode)
+
+
+# ------------------------------------------------------------------------------------------------ B2
+class _GridSubsamplingModule:
+    """Stands in for the numpy C-extension `grid_subsampling` (wrapper.cpp): `compute(...)`."""
+
+    @staticmethod
+    def compute(points, *, features=None, classes=None, sampleDl=0.1, method="barycenters", verbose=0):
+        if method not in ("barycenters", "voxelcenters"):
+            raise RuntimeError('Error parsing method. Valid method names are "barycenters" and "voxelcenters" ')
+        try:
+            p = np.ascontiguousarray(points, dtype=np.float32)
+        except Exception:
+            raise RuntimeError("Error converting input points to numpy arrays of type float32")
+        f = c = None
+        if features is not None:
+            try:
+                f = np.ascontiguousarray(features, dtype=np.float32)
+            except Exception:
+                raise RuntimeError("Error converting input features to numpy arrays of type float32")
+        if classes is not None:
+            try:
+                c = np.ascontiguousarray(classes, dtype=np.int32)
+            except Exception:
+                raise RuntimeError("Error converting input classes to numpy arrays of type int32")
+        if p.ndim != 2 or p.shape[1] != 3:
+            raise RuntimeError("Wrong dimensions : points.shape is not (N, 3)")
+        if f is not None and (f.ndim != 2 or f.shape[0] != p.shape[0]):
+            raise RuntimeError("Wrong dimensions : features.shape is not (N, d)")
+        if c is not None:
+            if c.ndim > 2 or c.shape[0] != p.shape[0]:
+                raise RuntimeError("Wrong dimensions : classes.shape is not (N,) or (N, d)")
+            if c.ndim == 1:
+                c = c[:, None]
+        if not torch.cuda.is_available():
+            raise _lib.SgbError("grid_subsampling.compute needs a CUDA device (seggroup_b200 has no CPU path)")
+        dev = torch.device("cuda")
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        sub, sf, sc, _ = _grid_subsample(t(p), t(f), t(c), None, float(sampleDl))
+        res = [sub.cpu().numpy()]
+        if f is not None:
+            res.append(sf.cpu().numpy())
+        if c is not None:
+            res.append(sc.cpu().numpy())
+        return res[0] if len(res) == 1 else tuple(res)
+
+
+grid_subsampling = _GridSubsamplingModule()

@@ -1,0 +1,139 @@
+"""Parity of the KPConv operator set (grid subsampling, radius neighbours, KPConv) on the GPU against the oracle
+(oracle/kpconv_oracle.py, itself pinned against the compiled reference cores in tests/test_kpconv_oracle.py) and,
+when oracle/_ref is present, against those cores directly."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def cloud(seed, n, batches=1):
+    from seggroup_b200 import synth
+    return synth.make_cloud(seed, n, batches=batches)
+
+
+def cu(a, dt=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    return (t if dt is None else t.to(dt)).cuda()
+
+
+@pytest.mark.parametrize("dl", [0.04, 0.1, 0.5])
+def test_grid_subsampling_compute(dl):
+    """B2: numpy in / out, barycentres + feature means bit-exact, labels with the canonical tie rule."""
+    from oracle import kpconv_oracle as K
+    from seggroup_b200.kpconv_ops import grid_subsampling
+    pts, _ = cloud(1, 20000)
+    rng = np.random.default_rng(0)
+    feats = rng.standard_normal((len(pts), 4)).astype(np.float32)
+    cls = rng.integers(0, 5, (len(pts), 2)).astype(np.int32)
+    sub, subf, subc = grid_subsampling.compute(pts, features=feats, classes=cls, sampleDl=dl)
+    rs, rf, rc, _ = K.grid_subsampling(pts, feats, cls, dl)
+    assert sub.dtype == np.float32 and subc.dtype == np.int32 and subc.shape[1] == 2
+    assert np.array_equal(sub, rs) and np.array_equal(subf, rf) and np.array_equal(subc, rc)
+    only = grid_subsampling.compute(pts, sampleDl=dl)
+    assert isinstance(only, np.ndarray) and np.array_equal(only, rs)
+    p2, c2 = grid_subsampling.compute(pts, classes=cls[:, 0], sampleDl=dl)
+    assert c2.shape == (len(rs), 1) and np.array_equal(c2[:, 0], rc[:, 0])
+
+
+def test_grid_subsampling_errors():
+    from seggroup_b200.kpconv_ops import grid_subsampling
+    pts, _ = cloud(1, 8000)
+    with pytest.raises(RuntimeError, match="points.shape is not"):
+        grid_subsampling.compute(pts[:, :2])
+    with pytest.raises(RuntimeError, match="features.shape is not"):
+        grid_subsampling.compute(pts, features=np.zeros((5, 2), np.float32))
+    with pytest.raises(RuntimeError, match="classes.shape is not"):
+        grid_subsampling.compute(pts, classes=np.zeros((5,), np.int32))
+    with pytest.raises(RuntimeError, match="Error parsing method"):
+        grid_subsampling.compute(pts, method="median")
+
+
+def test_grid_subsampling_vs_compiled_reference():
+    from oracle import kpconv_oracle as K
+    from oracle import kpconv_ref
+    if not kpconv_ref.available():
+        pytest.skip("oracle/_ref not built")
+    from seggroup_b200.kpconv_ops import batch_grid_subsampling
+    pts, lens = cloud(2, 12000, batches=3)
+    sub, sb = batch_grid_subsampling(cu(pts), cu(lens, torch.int32), 0.05)
+    rp, rb = kpconv_ref.batch_grid_subsampling(pts, lens, 0.05)
+    assert np.array_equal(sb.cpu().numpy(), rb)
+    sub = sub.cpu().numpy()
+    s = so = 0
+    for b, m in zip(lens, rb):
+        perm = K.reference_to_canonical(rp[so:so + m], pts[s:s + b], 0.05)
+        assert np.array_equal(sub[so:so + m], rp[so:so + m][perm])
+        s += b; so += m
+
+
+def test_big_voxels_keep_input_order():
+    """a voxel holding thousands of points exercises the big-bucket sort; the fp32 sum must still run in input order"""
+    from oracle import kpconv_oracle as K
+    from seggroup_b200.kpconv_ops import grid_subsampling_op
+    rng = np.random.default_rng(3)
+    pts = (rng.random((6000, 3)) * np.array([2.0, 2.0, 0.5])).astype(np.float32)
+    sub = grid_subsampling_op(cu(pts), 1.0).cpu().numpy()
+    ref, _, _, _ = K.grid_subsampling(pts, dl=1.0)
+    assert len(ref) <= 8 and np.array_equal(sub, ref)
+
+
+@pytest.mark.parametrize("radius", [0.08, 0.2])
+def test_batch_neighbors(radius):
+    from oracle import kpconv_oracle as K
+    from seggroup_b200.kpconv_ops import batch_grid_subsampling, batch_ordered_neighbors, ordered_neighbors
+    pts, lens = cloud(3, 15000, batches=2)
+    P, Lb = cu(pts), cu(lens, torch.int32)
+    sub, sb = batch_grid_subsampling(P, Lb, 0.04)
+    q, qb = batch_grid_subsampling(P, Lb, 0.08)
+    nb = batch_ordered_neighbors(q, sub, qb, sb, radius).cpu().numpy()
+    ref = K.batch_neighbors(q.cpu().numpy(), sub.cpu().numpy(), qb.cpu().numpy(), sb.cpu().numpy(), radius)
+    assert nb.shape == ref.shape and nb.dtype == np.int32
+    assert np.array_equal(nb, ref)
+    # single cloud signature; queries == supports puts every point first in its own row
+    one = sub[: int(sb[0])].contiguous()
+    nb1 = ordered_neighbors(one, one, radius).cpu().numpy()
+    assert np.array_equal(nb1[:, 0], np.arange(len(one)))
+
+
+def test_batch_neighbors_vs_compiled_reference():
+    from oracle import kpconv_oracle as K
+    from oracle import kpconv_ref
+    if not kpconv_ref.available():
+        pytest.skip("oracle/_ref not built")
+    from seggroup_b200.kpconv_ops import batch_ordered_neighbors
+    pts, lens = cloud(4, 6000, batches=2)
+    sub, sb = K.batch_grid_subsampling(pts, lens, 0.05)
+    nb = batch_ordered_neighbors(cu(sub), cu(sub), cu(sb, torch.int32), cu(sb, torch.int32), 0.12).cpu().numpy()
+    ref = kpconv_ref.batch_neighbors(sub, sub, sb, sb, 0.12, nanoflann=True)
+    assert np.array_equal(nb, K.canonical_rows(ref, sub, sub))
+
+
+@pytest.mark.parametrize("cin,cout", [(5, 64), (64, 64), (128, 128), (64, 32)])
+@pytest.mark.parametrize("influence,mode", [("linear", "sum"), ("gaussian", "sum"), ("linear", "closest"), ("constant", "sum")])
+def test_kpconv_forward_backward(cin, cout, influence, mode):
+    from oracle import kpconv_oracle as K
+    from seggroup_b200.kpconv_ops import KPConv_ops, batch_ordered_neighbors
+    pts, lens = cloud(5, 6000)
+    sub, _ = K.batch_grid_subsampling(pts, lens, 0.06)
+    qs, _ = K.batch_grid_subsampling(pts, lens, 0.12)
+    S, Q = cu(sub), cu(qs)
+    radius, extent = 0.15, 0.06
+    nb = batch_ordered_neighbors(Q, S, None, None, radius)
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    kp = (torch.rand(15, 3, generator=g) * 2 - 1) * 0.09
+    kp[0] = 0
+    feats = torch.randn(len(sub), cin, generator=g)
+    kv = torch.randn(15, cin, cout, generator=g) * (1.0 / np.sqrt(cin * 15))
+    fd = feats.cuda().requires_grad_(True); kd = kv.cuda().requires_grad_(True)
+    out = KPConv_ops(Q, S, nb, fd, kp.cuda(), kd, extent, influence, mode)
+    f64 = feats.double().requires_grad_(True); k64 = kv.double().requires_grad_(True)
+    ref = K.kpconv_ops(Q.cpu(), S.cpu(), nb.cpu(), f64, kp, k64, extent, influence, mode, dtype=torch.float64)
+    scale = float(ref.abs().max())
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) < 1e-4 * scale       # fp32 SIMT path: 1e-4 relative
+    go = torch.randn(out.shape, generator=g)
+    (out * go.cuda()).sum().backward()
+    (ref * go.double()).sum().backward()
+    assert float((fd.grad.cpu().double() - f64.grad).abs().max()) < 1e-4 * float(f64.grad.abs().max())
+    assert float((kd.grad.cpu().double() - k64.grad).abs().max()) < 1e-4 * float(k64.grad.abs().max())
