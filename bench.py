@@ -125,11 +125,12 @@ def main():
     ap.add_argument("--points", type=int, default=150000)
     ap.add_argument("--ref-points", type=int, default=30000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="scenes in flight per GPU (CUDA streams / host threads)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    from seggroup_b200 import _lib, pipeline, synth
+    from seggroup_b200 import _lib, engine, pipeline, synth
     from seggroup_b200.params import TRAINABLE, init_params
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -180,16 +181,12 @@ def main():
             p[k].grad.copy_(flat[o:o + n].view_as(p[k]))
             o += n
 
+    ex = engine.SceneExecutor(dev, n_streams=args.streams)
+
     def step(scenes, from_host):
         flush_buf.fill_(0)                                  # evict L2 between steps (inside the timed region, ~40 us)
         opt.zero_grad(set_to_none=False)
-        total = torch.zeros((), device=dev)
-        for s in scenes:
-            sc = upload(s) if from_host else s
-            r = pipeline.forward_scene(sc, p, mode="train")
-            loss = r.loss_raw[:, 0].sum() / r.loss_raw[:, 1].sum() / len(scenes)
-            loss.backward()
-            total += loss.detach()
+        total = ex.train_batch(scenes, p, train_keys, upload=upload if from_host else None)
         allreduce_grads()
         opt.step()
         return total
@@ -220,11 +217,11 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    _lib.launch_count = 0
+    launches0 = _lib.launch_count()
     _lib.time_entry = "sgb_edgeconv_fwd"
     _lib.timed_events = []
     ms, _ = timed(resident, False, args.steps)
-    launches = _lib.launch_count
+    launches = _lib.launch_count() - launches0
     kernel_events = _lib.timed_events
     _lib.time_entry = None
     clocks = sampler.stop() if rank == 0 else None
@@ -256,7 +253,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "SegGroup training step fwd+bwd+SGD, %d scenes x %d points per GPU (BASELINE configs[1])" % (args.scenes, args.points),
                            "weights": "torch.manual_seed(1) default init, mlp_1.bn1.weight x %g" % GSCALE, "l2": "256 MiB flush buffer written every step",
-                           "parallelism": "dp%d" % world if world > 1 else "single"},
+                           "parallelism": "dp%d" % world if world > 1 else "single", "scenes_in_flight": args.streams},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

@@ -34,6 +34,7 @@ const char* sgb_status_string(int status);
 int sgb_last_cuda_error(void);               /* cudaError_t of the last SGB_ERR_CUDA on this thread */
 const char* sgb_last_cuda_error_string(void);
 int sgb_device_arch(int* major, int* minor); /* compute capability of the current device */
+long long sgb_launch_count(void);            /* kernels of this library launched by this process so far (all threads) */
 
 /* ---------------------------------------------------------------------------------------------
  * Primitives (used by the ops below; exported for the parity tests)

@@ -28,9 +28,9 @@ def parse_header(path: str = HEADER) -> dict:
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     text = re.sub(r"//[^\n]*", " ", text)
     protos = {}
-    for m in re.finditer(r"\b(int|size_t|const char\s*\*)\s+(sgb_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"\b(long long|int|size_t|const char\s*\*)\s+(sgb_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
-        restype = {"int": ctypes.c_int, "size_t": ctypes.c_size_t}.get(ret, ctypes.c_char_p)
+        restype = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "long long": ctypes.c_longlong}.get(ret, ctypes.c_char_p)
         argl = []
         if args and args != "void":
             for a in args.split(","):
@@ -92,24 +92,14 @@ def _ptr(x):
 # optional per-entry-point device timing (tools/profile_scene.py): name -> [calls, ms]
 profile = None
 
-# bench.py bookkeeping: kernels launched per entry point (counted from csrc/*.cu), and CUDA-event pairs around
-# one chosen entry point (recorded on the launching stream, resolved by the caller after its final synchronize).
-launch_count = 0
+# bench.py bookkeeping: CUDA-event pairs around one chosen entry point (recorded on the launching stream, resolved by the
+# caller after its final synchronize).  Kernel launches are counted inside the library (sgb_launch_count).
 time_entry = None
 timed_events = []
-KERNELS_PER_CALL = {"sgb_exclusive_scan_i32": 3, "sgb_segment_pool_max_fwd": 2, "sgb_segment_pool_max_bwd": 1, "sgb_cluster_knn": 1,
-                    "sgb_cluster_cloud_indices": 1, "sgb_cluster_cloud_transform": 1, "sgb_centralize": 2, "sgb_mlp1_fwd": 3,
-                    "sgb_mlp1_bwd": 3, "sgb_scene_init": 2, "sgb_level_build": 14, "sgb_level_children": 6, "sgb_update_adj": 6,
-                    "sgb_sym_csr": 6, "sgb_edge_dist_fwd": 1, "sgb_edge_dist_bwd": 1, "sgb_gcn_agg_fwd": 1, "sgb_gcn_agg_bwd": 2,
-                    "sgb_group_nearby": 1, "sgb_group_unlabeled_step": 2, "sgb_export_labels": 1}
 
 
-def _kernels(name, args):
-    if name == "sgb_edgeconv_fwd":
-        return 8 if args[3] else 5
-    if name == "sgb_edgeconv_bwd":
-        return 5 if args[7] else 2
-    return KERNELS_PER_CALL.get(name, 0)
+def launch_count() -> int:
+    return int(load().sgb_launch_count())
 
 
 def enable_profile():
@@ -118,8 +108,6 @@ def enable_profile():
 
 
 def call(name: str, *args):
-    global launch_count
-    launch_count += _kernels(name, args)
     if time_entry is not None and name == time_entry:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

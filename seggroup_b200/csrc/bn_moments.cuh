@@ -9,6 +9,30 @@ constexpr int COUT = 64;
 
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * SLOPE; }
 
+// out[i] = sum_b part[b*n + i] in a fixed order (row groups b = y, y+8, ... summed per thread, then groups 0..7):
+// the per-CTA partial sums of the moment / gradient kernels are reduced by n/32 CTAs instead of one thread per entry.
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const T* __restrict__ part, int nb, int n, double* __restrict__ out) {
+    __shared__ double s_p[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
+    double s = 0;
+    if (i < n) for (int b = y; b < nb; b += 8) s += (double)part[(size_t)b * n + i];
+    s_p[y][x] = s;
+    __syncthreads();
+    if (y == 0 && i < n) {
+        double t = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += s_p[g][x];
+        out[i] = t;
+    }
+}
+template <typename T>
+inline void reduce_partials(const T* part, int nb, int n, double* out, cudaStream_t st) {
+    { reduce_partials_kernel<T><<<(n + 31) / 32, 256, 0, st>>>(part, nb, n, out); SGB_COUNT_LAUNCH(); }
+}
+
 // BN1 statistics from the moments: y = W e = W e' + W e0 (e0 = centre the moments were taken about).
 // stats layout [4][64]: mean, invstd, scale = gamma*invstd, beta ; var_out[64] = biased variance.
 // moments_out[NE1] = reduced (s', G') in fp64 for the backward pass.

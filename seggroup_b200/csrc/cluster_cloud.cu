@@ -206,8 +206,8 @@ extern "C" int sgb_cluster_cloud_indices(const float* xyz, int stride, int N, co
     if (!xyz || !order || !cl_off || !cloud_idx || !status || !ws) return SGB_ERR_INVALID;
     if (ws_bytes < sgb_cluster_cloud_ws_bytes(N)) return SGB_ERR_WORKSPACE;
     if ((size_t)P * sizeof(int) > 40 * 1024) return SGB_ERR_UNSUPPORTED;
-    cluster_cloud_indices_kernel<<<S, FPS_THREADS, (size_t)P * sizeof(int), (cudaStream_t)stream>>>(
-        xyz, stride, order, cl_off, P, cloud_idx, (float4*)ws, status);
+    { cluster_cloud_indices_kernel<<<S, FPS_THREADS, (size_t)P * sizeof(int), (cudaStream_t)stream>>>(
+        xyz, stride, order, cl_off, P, cloud_idx, (float4*)ws, status); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -216,7 +216,7 @@ extern "C" int sgb_cluster_cloud_transform(const float* data6, const int* cloud_
     if (S < 0 || P <= 0) return SGB_ERR_INVALID;
     if (S == 0) return SGB_OK;
     if (!data6 || !cloud_idx || !clouds) return SGB_ERR_INVALID;
-    cluster_cloud_transform_kernel<<<sgb_div_up(S, 4), 128, 0, (cudaStream_t)stream>>>(data6, cloud_idx, S, P, clouds);
+    { cluster_cloud_transform_kernel<<<sgb_div_up(S, 4), 128, 0, (cudaStream_t)stream>>>(data6, cloud_idx, S, P, clouds); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -227,8 +227,8 @@ extern "C" int sgb_centralize(const float* data6, int N, const int* order, const
     if (N == 0 || S == 0) return SGB_OK;
     if (!data6 || !order || !cl_off || !x9 || !mean_ws) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    cluster_mean_kernel<<<S, 256, 0, st>>>(data6, order, cl_off, mean_ws);
-    centralize_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, mean_ws, x9);
+    { cluster_mean_kernel<<<S, 256, 0, st>>>(data6, order, cl_off, mean_ws); SGB_COUNT_LAUNCH(); }
+    { centralize_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, mean_ws, x9); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

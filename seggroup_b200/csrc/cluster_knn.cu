@@ -103,9 +103,9 @@ extern "C" int sgb_cluster_knn(const float* xyz, int stride, int N, const int* o
     if (!xyz || !order || !cl_off || !knn || S == 0) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = sgb_div_up(N, KNN_THREADS);
-    if (k == 20) cluster_knn_kernel<20><<<grid, KNN_THREADS, 0, st>>>(xyz, stride, N, order, cl_off, S, knn);
-    else if (k == 10) cluster_knn_kernel<10><<<grid, KNN_THREADS, 0, st>>>(xyz, stride, N, order, cl_off, S, knn);
-    else if (k == 16) cluster_knn_kernel<16><<<grid, KNN_THREADS, 0, st>>>(xyz, stride, N, order, cl_off, S, knn);
+    if (k == 20) { cluster_knn_kernel<20><<<grid, KNN_THREADS, 0, st>>>(xyz, stride, N, order, cl_off, S, knn); SGB_COUNT_LAUNCH(); }
+    else if (k == 10) { cluster_knn_kernel<10><<<grid, KNN_THREADS, 0, st>>>(xyz, stride, N, order, cl_off, S, knn); SGB_COUNT_LAUNCH(); }
+    else if (k == 16) { cluster_knn_kernel<16><<<grid, KNN_THREADS, 0, st>>>(xyz, stride, N, order, cl_off, S, knn); SGB_COUNT_LAUNCH(); }
     else return SGB_ERR_UNSUPPORTED;
     SGB_CHECK_LAUNCH();
     return SGB_OK;

@@ -17,6 +17,8 @@
     } while (0)
 
 int sgb_cuda_error(int cuda_code);   // records the code, returns SGB_ERR_CUDA
+void sgb_count_launch();             // one kernel of this library was launched (sgb_launch_count)
+#define SGB_COUNT_LAUNCH() sgb_count_launch()
 
 static inline int sgb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -1,7 +1,12 @@
 // Status plumbing and the int32 exclusive scan used by the CSR builders.
 #include "common.cuh"
+#include <atomic>
 
 static thread_local int g_last_cuda_error = 0;
+static std::atomic<long long> g_launches{0};
+
+void sgb_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long sgb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int sgb_cuda_error(int code) { g_last_cuda_error = code; return SGB_ERR_CUDA; }
 
@@ -106,6 +111,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles(const int* __restrict
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *grand;
 }
 __global__ void scan_empty(int* out) { out[0] = 0; }
+
+// whole scan in ONE CTA (n <= SCAN_SINGLE_MAX): the CSR builders of the segment graph scan a few thousand entries, where
+// three dependent launches cost more than the work.
+constexpr int SCAN_SINGLE_MAX = 8 * SCAN_TILE;
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single(const int* __restrict__ in, int n, int* __restrict__ out) {
+    __shared__ int sm[33];
+    int carry = 0;
+    for (int t0 = 0; t0 < n; t0 += SCAN_TILE) {
+        const int base = t0 + threadIdx.x * SCAN_ITEMS;
+        int v[SCAN_ITEMS];
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+        int tot;
+        int ex = block_exclusive_scan(s, &tot, sm) + carry;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+        carry += tot;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
 }  // namespace
 
 extern "C" size_t sgb_scan_ws_bytes(int n) {
@@ -116,15 +142,20 @@ extern "C" size_t sgb_scan_ws_bytes(int n) {
 extern "C" int sgb_exclusive_scan_i32(const int* in, int* out, int n, void* ws, size_t ws_bytes, void* stream) {
     if (n < 0 || !out) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { scan_empty<<<1, 1, 0, st>>>(out); SGB_CHECK_LAUNCH(); return SGB_OK; }
+    if (n == 0) { { scan_empty<<<1, 1, 0, st>>>(out); SGB_COUNT_LAUNCH(); } SGB_CHECK_LAUNCH(); return SGB_OK; }
     if (!in || !ws) return SGB_ERR_INVALID;
     if (ws_bytes < sgb_scan_ws_bytes(n)) return SGB_ERR_WORKSPACE;
+    if (n <= SCAN_SINGLE_MAX) {
+        { scan_single<<<1, SCAN_THREADS, 0, st>>>(in, n, out); SGB_COUNT_LAUNCH(); }
+        SGB_CHECK_LAUNCH();
+        return SGB_OK;
+    }
     int nb = sgb_div_up(n, SCAN_TILE);
     int* sums = (int*)ws;
     int* grand = sums + nb;
-    scan_tile_sums<<<nb, SCAN_THREADS, 0, st>>>(in, n, sums);
-    scan_block_sums<<<1, SCAN_THREADS, 0, st>>>(sums, nb, grand);
-    scan_tiles<<<nb, SCAN_THREADS, 0, st>>>(in, n, sums, grand, out);
+    { scan_tile_sums<<<nb, SCAN_THREADS, 0, st>>>(in, n, sums); SGB_COUNT_LAUNCH(); }
+    { scan_block_sums<<<1, SCAN_THREADS, 0, st>>>(sums, nb, grand); SGB_COUNT_LAUNCH(); }
+    { scan_tiles<<<nb, SCAN_THREADS, 0, st>>>(in, n, sums, grand, out); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

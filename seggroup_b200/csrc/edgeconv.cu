@@ -204,29 +204,35 @@ gram2_reduce_kernel(const double* __restrict__ part, int nb, double* __restrict_
     moments[i] = s;
 }
 
+// one CTA per output channel c, thread j owns row j of the (symmetrised) H:  E[z_c^2] = w^T H w / M
 __global__ void __launch_bounds__(64)
 bn2_finalize_kernel(const double* __restrict__ moments, double M, const float* __restrict__ W2, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float* __restrict__ stats, float* __restrict__ var_out) {
-    const int c = threadIdx.x;
-    if (c >= COUT) return;
-    double mean = 0, ez2 = 0;
-    for (int j = 0; j < COUT; ++j) {
-        const double wj = (double)W2[c * COUT + j];
-        mean += wj * moments[COUT * COUT + j];
-        double r = 0;
-        // H is accumulated as full 64x64 (rows by owner lane); symmetrise to cancel the fp32 asymmetry
-        for (int i = 0; i < COUT; ++i) r += 0.5 * (moments[j * COUT + i] + moments[i * COUT + j]) * (double)W2[c * COUT + i];
-        ez2 += wj * r;
+    __shared__ double s_w[COUT];
+    __shared__ double s_q[COUT];
+    __shared__ double s_m[COUT];
+    const int c = blockIdx.x, j = threadIdx.x;
+    s_w[j] = (double)W2[c * COUT + j];
+    __syncthreads();
+    double r = 0;
+    // H is accumulated as full 64x64 (rows by owner lane); symmetrise to cancel the fp32 asymmetry
+    for (int i = 0; i < COUT; ++i) r += 0.5 * (moments[j * COUT + i] + moments[i * COUT + j]) * s_w[i];
+    s_q[j] = s_w[j] * r;
+    s_m[j] = s_w[j] * moments[COUT * COUT + j];
+    __syncthreads();
+    if (j == 0) {
+        double mean = 0, ez2 = 0;
+        for (int i = 0; i < COUT; ++i) { mean += s_m[i]; ez2 += s_q[i]; }      // fixed order
+        mean /= M; ez2 /= M;
+        double var = ez2 - mean * mean;
+        if (var < 0) var = 0;
+        const double invstd = 1.0 / sqrt(var + (double)BN_EPS);
+        stats[c] = (float)mean;
+        stats[64 + c] = (float)invstd;
+        stats[128 + c] = (float)((double)gamma[c] * invstd);
+        stats[192 + c] = beta[c];
+        if (var_out) var_out[c] = (float)var;
     }
-    mean /= M; ez2 /= M;
-    double var = ez2 - mean * mean;
-    if (var < 0) var = 0;
-    const double invstd = 1.0 / sqrt(var + (double)BN_EPS);
-    stats[c] = (float)mean;
-    stats[64 + c] = (float)invstd;
-    stats[128 + c] = (float)((double)gamma[c] * invstd);
-    stats[192 + c] = beta[c];
-    if (var_out) var_out[c] = (float)var;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,10 +332,10 @@ constexpr size_t SMEM_STAGE = sizeof(float) * WARPS * KNN * (CINP + COUT);
 
 using namespace sgb_ec;
 
-// workspace layout (bytes): [ctr 16 floats][mean partials 256*9 dbl][gram1 partials grid*NE1 dbl][gram2 partials grid*NE2 dbl]
+// workspace layout (bytes): [ctr 16 floats][mean partials 256*9 dbl][reduced gram1 192 dbl][gram1 partials grid*NE1 dbl][gram2 partials grid*NE2 dbl]
 extern "C" size_t sgb_edgeconv_ws_bytes(int N, int two_layer) {
     const size_t g = (size_t)persistent_grid(N);
-    size_t b = 128 + 256 * 9 * 8 + g * NE1 * 8;
+    size_t b = 128 + 256 * 9 * 8 + 192 * 8 + g * NE1 * 8;
     if (two_layer) b += (size_t)(148 * 2) * NE2 * 8;
     return b;
 }
@@ -350,31 +356,34 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     unsigned char* w8 = (unsigned char*)ws;
     float* ctr = (float*)w8;
     double* mpart = (double*)(w8 + 128);
-    double* g1part = mpart + 256 * 9;
+    double* g1red = mpart + 256 * 9;      // [NE1 -> 192] reduced first-layer moments when the caller keeps none
+    double* g1part = g1red + 192;
     const int grid = persistent_grid(N);
     double* g2part = g1part + (size_t)grid * NE1;
     const double M = (double)N * KNN;
 
     const int mb = N < 256 * 256 ? sgb_div_up(N, 256) : 256;
-    x9_mean_partial<<<mb, 256, 0, st>>>(x9, N, mpart);
-    x9_mean_finish<<<1, 32, 0, st>>>(mpart, mb, N, ctr);
-    gram1_kernel<<<grid, WARPS * 32, 0, st>>>(x9, knn, N, ctr, g1part);
-    bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(g1part, grid, M, W1, ctr, gamma1, beta1, stats1, var1, mom1);
+    { x9_mean_partial<<<mb, 256, 0, st>>>(x9, N, mpart); SGB_COUNT_LAUNCH(); }
+    { x9_mean_finish<<<1, 32, 0, st>>>(mpart, mb, N, ctr); SGB_COUNT_LAUNCH(); }
+    { gram1_kernel<<<grid, WARPS * 32, 0, st>>>(x9, knn, N, ctr, g1part); SGB_COUNT_LAUNCH(); }
+    double* m1red = mom1 ? mom1 : g1red;
+    sgb_bn::reduce_partials(g1part, grid, NE1, m1red, st);
+    { bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(m1red, 1, M, W1, ctr, gamma1, beta1, stats1, var1, nullptr); SGB_COUNT_LAUNCH(); }
     if (ctr_out) SGB_CUDA(cudaMemcpyAsync(ctr_out, ctr, 18 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (two_layer) {
         const int g2 = grid < 148 * 2 ? grid : 148 * 2;
         const size_t sm2 = SMEM_STAGE + NE2 * sizeof(double) + sizeof(float) * CIN * COUT;
         SGB_CUDA(cudaFuncSetAttribute(gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-        gram2_kernel<<<g2, WARPS * 32, sm2, st>>>(x9, knn, N, W1, stats1, g2part);
-        gram2_reduce_kernel<<<sgb_div_up(NE2, 256), 256, 0, st>>>(g2part, g2, mom2);
-        bn2_finalize_kernel<<<1, 64, 0, st>>>(mom2, M, W2, gamma2, beta2, stats2, var2);
+        { gram2_kernel<<<g2, WARPS * 32, sm2, st>>>(x9, knn, N, W1, stats1, g2part); SGB_COUNT_LAUNCH(); }
+        sgb_bn::reduce_partials(g2part, g2, NE2, mom2, st);
+        { bn2_finalize_kernel<<<COUT, 64, 0, st>>>(mom2, M, W2, gamma2, beta2, stats2, var2); SGB_COUNT_LAUNCH(); }
         const size_t smB = SMEM_STAGE + sizeof(float) * COUT * COUT;
         SGB_CUDA(cudaFuncSetAttribute(forward_max_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
-        forward_max_kernel<true><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, W2, stats2, out, argk);
+        { forward_max_kernel<true><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, W2, stats2, out, argk); SGB_COUNT_LAUNCH(); }
     } else {
         const size_t smB = sizeof(float) * WARPS * KNN * CINP;
         SGB_CUDA(cudaFuncSetAttribute(forward_max_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
-        forward_max_kernel<false><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, nullptr, nullptr, out, argk);
+        { forward_max_kernel<false><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, nullptr, nullptr, out, argk); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();
     return SGB_OK;

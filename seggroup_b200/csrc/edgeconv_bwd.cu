@@ -118,56 +118,50 @@ bwd_sparse_kernel(const float* __restrict__ g /*[S,64]*/, const int* __restrict_
     }
 }
 
-// MLP3: reduce the layer-2 partials, emit dW2 / dgamma2 / dbeta2 and the dense-pass coefficients Bm [64][64], r [64].
-__global__ void __launch_bounds__(256)
-bwd_mid_kernel(const float* __restrict__ part2, int nchunk, double M, const float* __restrict__ W2, const float* __restrict__ stats2,
+// MLP3: from the reduced layer-2 sums t2 [64][66] ([c][j] = sum dv2 (h_j - hbar_j), [c][64] = dbeta2, [c][65] = dgamma2)
+// emit dW2 / dgamma2 / dbeta2 and the dense-pass coefficients Bm [64][64], r [64].  One CTA per row (64 CTAs x 64 threads).
+__global__ void __launch_bounds__(64)
+bwd_mid_kernel(const double* __restrict__ t2, double M, const float* __restrict__ W2, const float* __restrict__ stats2,
                const double* __restrict__ mom2, float* __restrict__ gW2, float* __restrict__ gg2, float* __restrict__ gb2,
                float* __restrict__ coef /*[64*64 + 64]*/) {
-    __shared__ double s_t2[COUT][COUT + 2];     // [c][j], [c][64] = dbeta2, [c][65] = dgamma2
+    __shared__ float s_w2[COUT][COUT + 1];
     __shared__ double s_hbar[COUT];
     __shared__ double s_d[COUT];                // D_c = gamma2 invstd2^2 dgamma2
     __shared__ double s_q[COUT];                // gamma2 invstd2 dbeta2
-    for (int i = threadIdx.x; i < COUT * 66; i += blockDim.x) {
-        double s = 0;
-        for (int b = 0; b < nchunk; ++b) s += (double)part2[(size_t)b * COUT * 66 + i];
-        s_t2[i / 66][i % 66] = s;
-    }
-    if (threadIdx.x < COUT) s_hbar[threadIdx.x] = mom2[COUT * COUT + threadIdx.x] / M;
-    __syncthreads();
-    if (threadIdx.x < COUT) {
-        const int c = threadIdx.x;
-        const double gi = (double)stats2[128 + c];                // gamma*invstd
-        s_d[c] = gi * (double)stats2[64 + c] * s_t2[c][65];
-        s_q[c] = gi * s_t2[c][64];
-        gb2[c] = (float)s_t2[c][64];
-        gg2[c] = (float)s_t2[c][65];
+    __shared__ double s_red[COUT];
+    const int b = blockIdx.x, j = threadIdx.x;
+    for (int i = j; i < COUT * COUT; i += COUT) s_w2[i / COUT][i % COUT] = __ldg(W2 + i);
+    s_hbar[j] = mom2[COUT * COUT + j] / M;
+    {
+        const double gi = (double)stats2[128 + j];                // gamma*invstd
+        s_d[j] = gi * (double)stats2[64 + j] * t2[j * 66 + 65];
+        s_q[j] = gi * t2[j * 66 + 64];
+        if (b == 0) { gb2[j] = (float)t2[j * 66 + 64]; gg2[j] = (float)t2[j * 66 + 65]; }
     }
     __syncthreads();
-    // Bm[i][j] = (1/M) sum_c W2[c][i] D_c W2[c][j]
-    for (int ij = threadIdx.x; ij < COUT * COUT; ij += blockDim.x) {
-        const int i = ij / COUT, j = ij % COUT;
-        double s = 0;
-        for (int c = 0; c < COUT; ++c) s += (double)W2[c * COUT + i] * s_d[c] * (double)W2[c * COUT + j];
-        coef[ij] = (float)(s / M);
-    }
-    // dW2[c][j] = gamma2 invstd2 [ T2[c][j] - dgamma2 invstd2 sum_i CovH[j][i] W2[c][i] ]
-    for (int cj = threadIdx.x; cj < COUT * COUT; cj += blockDim.x) {
-        const int c = cj / COUT, j = cj % COUT;
+    // Bm[b][j] = (1/M) sum_c W2[c][b] D_c W2[c][j]
+    double bm = 0;
+    for (int c = 0; c < COUT; ++c) bm += (double)s_w2[c][b] * s_d[c] * (double)s_w2[c][j];
+    const float bmf = (float)(bm / M);
+    coef[b * COUT + j] = bmf;
+    // dW2[c=b][j] = gamma2 invstd2 [ T2[c][j] - dgamma2 invstd2 sum_i CovH[j][i] W2[c][i] ]
+    {
+        const int c = b;
         double r = 0;
         for (int i = 0; i < COUT; ++i) {
             const double cov = 0.5 * (mom2[j * COUT + i] + mom2[i * COUT + j]) / M - s_hbar[j] * s_hbar[i];
-            r += cov * (double)W2[c * COUT + i];
+            r += cov * (double)s_w2[c][i];
         }
-        gW2[cj] = (float)((double)stats2[128 + c] * (s_t2[c][j] - s_t2[c][65] * (double)stats2[64 + c] * r));
+        gW2[c * COUT + j] = (float)((double)stats2[128 + c] * (t2[c * 66 + j] - t2[c * 66 + 65] * (double)stats2[64 + c] * r));
     }
+    // r[b] = -q0'[b]/M + (Bm hbar)[b],  q0'[b] = sum_c W2[c][b] gamma2 invstd2 dbeta2   (Bm as rounded to fp32 for the dense pass)
+    s_red[j] = (double)bmf * s_hbar[j];
     __syncthreads();
-    // r[j] = -q0'[j]/M + (Bm hbar)[j],  q0'[j] = sum_c W2[c][j] gamma2 invstd2 dbeta2   (Bm read back from coef)
-    if (threadIdx.x < COUT) {
-        const int j = threadIdx.x;
+    if (j == 0) {
         double q0 = 0, bh = 0;
-        for (int c = 0; c < COUT; ++c) q0 += (double)W2[c * COUT + j] * s_q[c];
-        for (int i = 0; i < COUT; ++i) bh += (double)coef[j * COUT + i] * s_hbar[i];
-        coef[COUT * COUT + j] = (float)(-q0 / M + bh);
+        for (int c = 0; c < COUT; ++c) q0 += (double)s_w2[c][b] * s_q[c];
+        for (int i = 0; i < COUT; ++i) bh += s_red[i];
+        coef[COUT * COUT + b] = (float)(-q0 / M + bh);
     }
 }
 
@@ -270,9 +264,9 @@ bwd_dense_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int 
     }
 }
 
-// dW1 / dgamma1 / dbeta1 from the accumulated (sparse + dense) sums
+// dW1 / dgamma1 / dbeta1 from the reduced (sparse [+ dense]) sums red [nred][64*NACC]
 __global__ void __launch_bounds__(64)
-bwd_last_kernel(const float* __restrict__ part1, int n1, const float* __restrict__ partD, int nD, double M,
+bwd_last_kernel(const double* __restrict__ red, int nred, double M,
                 const float* __restrict__ W1, const float* __restrict__ stats1, const double* __restrict__ mom1,
                 float* __restrict__ gW1, float* __restrict__ gg1, float* __restrict__ gb1) {
     __shared__ double s_cov[CIN][CIN];
@@ -289,8 +283,7 @@ bwd_last_kernel(const float* __restrict__ part1, int n1, const float* __restrict
     double a[NACC];
     for (int i = 0; i < NACC; ++i) {
         double s = 0;
-        for (int b = 0; b < n1; ++b) s += (double)part1[(size_t)b * (COUT * NACC) + c * NACC + i];
-        for (int b = 0; b < nD; ++b) s += (double)partD[(size_t)b * (COUT * NACC) + c * NACC + i];
+        for (int b = 0; b < nred; ++b) s += red[(size_t)b * (COUT * NACC) + c * NACC + i];
         a[i] = s;
     }
     gb1[c] = (float)a[0];
@@ -315,6 +308,7 @@ extern "C" size_t sgb_edgeconv_bwd_ws_bytes(int N, int S, int two_layer) {
     const size_t nchunk = (size_t)sgb_div_up(S, SEG_CHUNK);
     size_t b = nchunk * 8 * COUT * NACC * sizeof(float);
     if (two_layer) b += nchunk * COUT * 66 * sizeof(float) + (COUT * COUT + COUT) * sizeof(float) + (size_t)bwd_dense_grid(N) * COUT * NACC * sizeof(float);
+    b += (size_t)(2 * COUT * NACC + COUT * 66) * sizeof(double);       // reduced sums
     return b + 256;
 }
 
@@ -333,23 +327,29 @@ extern "C" int sgb_edgeconv_bwd(const float* g, const int* arg, const unsigned c
     cudaStream_t st = (cudaStream_t)stream;
     const int nchunk = sgb_div_up(S, SEG_CHUNK);
     const double M = (double)N * KNN;
-    float* part1 = (float*)ws;
+    double* red = (double*)ws;                               // [2][64*NACC] sparse / dense sums, then t2 [64*66]
+    double* t2 = red + 2 * COUT * NACC;
+    float* part1 = (float*)(t2 + COUT * 66);
     float* part2 = part1 + (size_t)nchunk * 8 * COUT * NACC;
     dim3 grid(nchunk, COUT / WARPS);
     if (!two_layer) {
-        bwd_sparse_kernel<false><<<grid, WARPS * 32, 0, st>>>(g, arg, argk, S, x9, knn, W1, stats1, mom1, e0, M, nullptr, nullptr, nullptr,
-                                                             part1, nullptr);
-        bwd_last_kernel<<<1, 64, 0, st>>>(part1, nchunk * 8, nullptr, 0, M, W1, stats1, mom1, gW1, gg1, gb1);
+        { bwd_sparse_kernel<false><<<grid, WARPS * 32, 0, st>>>(g, arg, argk, S, x9, knn, W1, stats1, mom1, e0, M, nullptr, nullptr, nullptr,
+                                                             part1, nullptr); SGB_COUNT_LAUNCH(); }
+        sgb_bn::reduce_partials(part1, nchunk * 8, COUT * NACC, red, st);
+        { bwd_last_kernel<<<1, 64, 0, st>>>(red, 1, M, W1, stats1, mom1, gW1, gg1, gb1); SGB_COUNT_LAUNCH(); }
     } else {
         float* coef = part2 + (size_t)nchunk * COUT * 66;
         float* partD = coef + COUT * COUT + COUT;
         const int gd = bwd_dense_grid(N);
-        bwd_sparse_kernel<true><<<grid, WARPS * 32, 0, st>>>(g, arg, argk, S, x9, knn, W1, stats1, mom1, e0, M, W2, stats2, mom2, part1, part2);
-        bwd_mid_kernel<<<1, 256, 0, st>>>(part2, nchunk, M, W2, stats2, mom2, gW2, gg2, gb2, coef);
+        { bwd_sparse_kernel<true><<<grid, WARPS * 32, 0, st>>>(g, arg, argk, S, x9, knn, W1, stats1, mom1, e0, M, W2, stats2, mom2, part1, part2); SGB_COUNT_LAUNCH(); }
+        sgb_bn::reduce_partials(part1, nchunk * 8, COUT * NACC, red, st);
+        sgb_bn::reduce_partials(part2, nchunk, COUT * 66, t2, st);
+        { bwd_mid_kernel<<<COUT, 64, 0, st>>>(t2, M, W2, stats2, mom2, gW2, gg2, gb2, coef); SGB_COUNT_LAUNCH(); }
         const size_t sm = sizeof(float) * (WARPS * KNN * (CINP + COUT) + COUT * COUT + CINP);
         SGB_CUDA(cudaFuncSetAttribute(bwd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        bwd_dense_kernel<<<gd, WARPS * 32, sm, st>>>(x9, knn, N, W1, stats1, mom1, e0, M, coef, partD);
-        bwd_last_kernel<<<1, 64, 0, st>>>(part1, nchunk * 8, partD, gd, M, W1, stats1, mom1, gW1, gg1, gb1);
+        { bwd_dense_kernel<<<gd, WARPS * 32, sm, st>>>(x9, knn, N, W1, stats1, mom1, e0, M, coef, partD); SGB_COUNT_LAUNCH(); }
+        sgb_bn::reduce_partials(partD, gd, COUT * NACC, red + COUT * NACC, st);
+        { bwd_last_kernel<<<1, 64, 0, st>>>(red, 2, M, W1, stats1, mom1, gW1, gg1, gb1); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();
     return SGB_OK;

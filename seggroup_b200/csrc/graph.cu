@@ -197,34 +197,77 @@ __global__ void adj_row_write(const unsigned* __restrict__ bitmap, int S, int wo
 }
 
 // ---------------------------------------------------------------------------------------------
-// symmetric CSR of an edge list (for gather-style reductions): row i lists (neighbour, edge id) sorted
-// by neighbour.  Atomic fill, then a per-row insertion sort -> deterministic.
+// symmetric CSR of a unique, lexicographically sorted (u < v) edge list, for gather-style reductions with a fixed
+// summation order: row i lists (neighbour, edge id) by ascending neighbour.  No sort: a symmetric S x S bitmap
+// (<= 1.1 MB at S = 3k, L2 resident) is filled from the edges and compacted in order, one warp per row; the edge id
+// of (min, max) is first[min] + rank of max among the bits above the diagonal of row min, because adj is sorted.
 // ---------------------------------------------------------------------------------------------
-__global__ void csr_degree(const int* __restrict__ adj, int A, int* __restrict__ deg) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= A) return;
-    atomicAdd(deg + adj[2 * e], 1);
-    atomicAdd(deg + adj[2 * e + 1], 1);
-}
-__global__ void csr_fill(const int* __restrict__ adj, int A, const int* __restrict__ row_off, int* __restrict__ cursor,
-                         int* __restrict__ nbr, int* __restrict__ eid) {
+__global__ void csr_set_bits(const int* __restrict__ adj, int A, int wpr, unsigned* __restrict__ bitmap) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= A) return;
     const int u = adj[2 * e], v = adj[2 * e + 1];
-    int p = row_off[u] + atomicAdd(cursor + u, 1);
-    nbr[p] = v; eid[p] = e;
-    p = row_off[v] + atomicAdd(cursor + v, 1);
-    nbr[p] = u; eid[p] = e;
+    atomicOr(bitmap + (size_t)u * wpr + (v >> 5), 1u << (v & 31));
+    atomicOr(bitmap + (size_t)v * wpr + (u >> 5), 1u << (u & 31));
 }
-__global__ void csr_sort_rows(const int* __restrict__ row_off, int S, int* __restrict__ nbr, int* __restrict__ eid) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// bits of word w of row i strictly above column c
+__device__ __forceinline__ unsigned bits_above(unsigned bits, int w, int c) {
+    const int lo = c + 1 - w * 32;                     // first column of this word that counts
+    if (lo <= 0) return bits;
+    if (lo >= 32) return 0u;
+    return bits & (0xffffffffu << lo);
+}
+__global__ void csr_row_degrees(const unsigned* __restrict__ bitmap, int S, int wpr, int* __restrict__ deg, int* __restrict__ outdeg) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (r >= S) return;
-    const int a = row_off[r], b = row_off[r + 1];
-    for (int i = a + 1; i < b; ++i) {
-        const int kn = nbr[i], ke = eid[i];
-        int j = i - 1;
-        while (j >= a && nbr[j] > kn) { nbr[j + 1] = nbr[j]; eid[j + 1] = eid[j]; --j; }
-        nbr[j + 1] = kn; eid[j + 1] = ke;
+    int d = 0, o = 0;
+    for (int w = lane; w < wpr; w += 32) {
+        const unsigned bits = bitmap[(size_t)r * wpr + w];
+        d += __popc(bits);
+        o += __popc(bits_above(bits, w, r));
+    }
+    d = sgb_warp_sum(d); o = sgb_warp_sum(o);
+    if (lane == 0) { deg[r] = d; outdeg[r] = o; }
+}
+__global__ void csr_row_write(const unsigned* __restrict__ bitmap, int S, int wpr, const int* __restrict__ row_off,
+                              const int* __restrict__ first, int* __restrict__ nbr, int* __restrict__ eid) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= S) return;
+    const int base = row_off[r];
+    const int indeg = (row_off[r + 1] - base) - (first[r + 1] - first[r]);
+    const int first_r = first[r];
+    int w0 = base;
+    for (int wb = 0; wb < wpr; wb += 32) {
+        const int w = wb + lane;
+        const unsigned bits = w < wpr ? bitmap[(size_t)r * wpr + w] : 0u;
+        const int c = __popc(bits);
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(SGB_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+        int pos = w0 + inc - c;
+        unsigned b = bits;
+        while (b) {
+            const int j = w * 32 + __ffs(b) - 1;
+            b &= b - 1;
+            int e;
+            if (j > r) {
+                e = first_r + (pos - base - indeg);
+            } else {                                   // edge (j, r): rank of r among the bits above the diagonal of row j
+                const unsigned* rowj = bitmap + (size_t)j * wpr;
+                int rank = 0;
+                for (int ww = j >> 5; ww <= (r >> 5); ++ww) {
+                    unsigned bb = bits_above(rowj[ww], ww, j);
+                    const int hi = r - ww * 32;        // keep columns < r
+                    if (hi < 32) bb &= (hi <= 0 ? 0u : (0xffffffffu >> (32 - hi)));
+                    rank += __popc(bb);
+                }
+                e = first[j] + rank;
+            }
+            nbr[pos] = j; eid[pos] = e;
+            ++pos;
+        }
+        w0 += __shfl_sync(SGB_FULL_MASK, inc, 31);
     }
 }
 
@@ -463,8 +506,8 @@ extern "C" int sgb_scene_init(const int* seg_off, const int* seg_members, const 
                               int* seg_of_point, int* seg_of_pos, int* uf, void* stream) {
     if (N <= 0 || S <= 0 || !seg_off || !seg_members || !weak_label || !seg_of_point || !seg_of_pos || !uf) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    scene_init_points<<<sgb_div_up(N, 256), 256, 0, st>>>(seg_off, seg_members, N, S, seg_of_point, seg_of_pos);
-    scene_init_uf<<<sgb_div_up(S, 256), 256, 0, st>>>(seg_off, seg_members, weak_label, S, uf);
+    { scene_init_points<<<sgb_div_up(N, 256), 256, 0, st>>>(seg_off, seg_members, N, S, seg_of_point, seg_of_pos); SGB_COUNT_LAUNCH(); }
+    { scene_init_uf<<<sgb_div_up(S, 256), 256, 0, st>>>(seg_off, seg_members, weak_label, S, uf); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -489,14 +532,14 @@ extern "C" int sgb_level_build(const int* uf, int S1, int N, const int* seg_off,
     const size_t scan_bytes = sgb_scan_ws_bytes(S1 + 1);
     const int g = sgb_div_up(S1, 256);
     int rc;
-    level_flag_roots<<<g, 256, 0, st>>>(uf, S1, flag);
+    { level_flag_roots<<<g, 256, 0, st>>>(uf, S1, flag); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(flag, dense, S1, scan_ws, scan_bytes, st))) return rc;
-    level_assign<<<g, 256, 0, st>>>(uf, S1, dense, seg_off, seg_members, roots, seg2cl, cl_ins, cl_sem, cl_rootpt, counts);
-    level_walk_lists<<<g, 256, 0, st>>>(uf, S1, counts, roots, seg_off, cl_nseg, cl_npt, seg_rank, seg_start);
+    { level_assign<<<g, 256, 0, st>>>(uf, S1, dense, seg_off, seg_members, roots, seg2cl, cl_ins, cl_sem, cl_rootpt, counts); SGB_COUNT_LAUNCH(); }
+    { level_walk_lists<<<g, 256, 0, st>>>(uf, S1, counts, roots, seg_off, cl_nseg, cl_npt, seg_rank, seg_start); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(cl_nseg, cl_seg_off, S1, scan_ws, scan_bytes, st))) return rc;
     if ((rc = sgb_exclusive_scan_i32(cl_npt, cl_pt_off, S1, scan_ws, scan_bytes, st))) return rc;
-    level_fill_seglist<<<g, 256, 0, st>>>(S1, seg2cl, seg_rank, cl_seg_off, cl_seg_list);
-    level_fill_order<<<sgb_div_up(N, 256), 256, 0, st>>>(N, seg_of_pos, seg_off, seg_members, seg2cl, seg_start, cl_pt_off, order);
+    { level_fill_seglist<<<g, 256, 0, st>>>(S1, seg2cl, seg_rank, cl_seg_off, cl_seg_list); SGB_COUNT_LAUNCH(); }
+    { level_fill_order<<<sgb_div_up(N, 256), 256, 0, st>>>(N, seg_of_pos, seg_off, seg_members, seg2cl, seg_start, cl_pt_off, order); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -512,11 +555,11 @@ extern "C" int sgb_level_children(const int* roots_old, int n_old, const int* se
     int* cnt = (int*)ws;
     void* scan_ws = cnt + (n_new + 1);
     SGB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n_new + 1) * sizeof(int), st));
-    gather_old2new<<<sgb_div_up(n_old, 256), 256, 0, st>>>(roots_old, n_old, seg2cl_new, old2new);
-    children_count<<<sgb_div_up(n_old, 256), 256, 0, st>>>(old2new, n_old, cnt, n_new);
+    { gather_old2new<<<sgb_div_up(n_old, 256), 256, 0, st>>>(roots_old, n_old, seg2cl_new, old2new); SGB_COUNT_LAUNCH(); }
+    { children_count<<<sgb_div_up(n_old, 256), 256, 0, st>>>(old2new, n_old, cnt, n_new); SGB_COUNT_LAUNCH(); }
     int rc;
     if ((rc = sgb_exclusive_scan_i32(cnt, child_off, n_new, scan_ws, sgb_scan_ws_bytes(n_new + 1), st))) return rc;
-    children_fill<<<sgb_div_up(n_new, 8), 256, 0, st>>>(old2new, n_old, child_off, n_new, child_list);
+    { children_fill<<<sgb_div_up(n_new, 8), 256, 0, st>>>(old2new, n_old, child_off, n_new, child_list); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -540,34 +583,42 @@ extern "C" int sgb_update_adj(const int* edges, int E, const int* map, int S_new
     SGB_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)S_new * wpr * 4, st));
     if (E > 0) {
         if (!edges) return SGB_ERR_INVALID;
-        adj_set_bits<<<sgb_div_up(E, 256), 256, 0, st>>>(edges, E, map, S_new, wpr, bitmap);
+        { adj_set_bits<<<sgb_div_up(E, 256), 256, 0, st>>>(edges, E, map, S_new, wpr, bitmap); SGB_COUNT_LAUNCH(); }
     }
-    adj_row_count<<<sgb_div_up(S_new, 8), 256, 0, st>>>(bitmap, S_new, wpr, row_cnt);
+    { adj_row_count<<<sgb_div_up(S_new, 8), 256, 0, st>>>(bitmap, S_new, wpr, row_cnt); SGB_COUNT_LAUNCH(); }
     int rc;
     if ((rc = sgb_exclusive_scan_i32(row_cnt, row_off, S_new, scan_ws, sgb_scan_ws_bytes(S_new + 1), st))) return rc;
-    adj_row_write<<<sgb_div_up(S_new, 8), 256, 0, st>>>(bitmap, S_new, wpr, row_off, adj_out, counts);
+    { adj_row_write<<<sgb_div_up(S_new, 8), 256, 0, st>>>(bitmap, S_new, wpr, row_off, adj_out, counts); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
 
-extern "C" size_t sgb_sym_csr_ws_bytes(int S) { return (size_t)(2 * (S + 1)) * sizeof(int) + sgb_scan_ws_bytes(S + 1); }
+extern "C" size_t sgb_sym_csr_ws_bytes(int S) {
+    const size_t wpr = (size_t)(S + 31) / 32;
+    return (size_t)S * wpr * 4 + (size_t)(3 * (S + 1)) * sizeof(int) + sgb_scan_ws_bytes(S + 1);
+}
 extern "C" int sgb_sym_csr(const int* adj, int A, int S, int* row_off, int* nbr, int* eid, void* ws, size_t ws_bytes, void* stream) {
     if (A < 0 || S <= 0 || !row_off || !ws) return SGB_ERR_INVALID;
     if (ws_bytes < sgb_sym_csr_ws_bytes(S)) return SGB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    int* deg = (int*)ws;
-    int* cursor = deg + (S + 1);
-    void* scan_ws = cursor + (S + 1);
-    SGB_CUDA(cudaMemsetAsync(deg, 0, (size_t)(2 * (S + 1)) * sizeof(int), st));
+    const int wpr = (S + 31) / 32;
+    unsigned* bitmap = (unsigned*)ws;
+    int* deg = (int*)(bitmap + (size_t)S * wpr);
+    int* outdeg = deg + (S + 1);
+    int* first = outdeg + (S + 1);
+    void* scan_ws = first + (S + 1);
+    const size_t scan_bytes = sgb_scan_ws_bytes(S + 1);
+    SGB_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)S * wpr * 4, st));
     if (A > 0) {
         if (!adj || !nbr || !eid) return SGB_ERR_INVALID;
-        csr_degree<<<sgb_div_up(A, 256), 256, 0, st>>>(adj, A, deg);
+        { csr_set_bits<<<sgb_div_up(A, 256), 256, 0, st>>>(adj, A, wpr, bitmap); SGB_COUNT_LAUNCH(); }
     }
+    { csr_row_degrees<<<sgb_div_up(S, 8), 256, 0, st>>>(bitmap, S, wpr, deg, outdeg); SGB_COUNT_LAUNCH(); }
     int rc;
-    if ((rc = sgb_exclusive_scan_i32(deg, row_off, S, scan_ws, sgb_scan_ws_bytes(S + 1), st))) return rc;
+    if ((rc = sgb_exclusive_scan_i32(deg, row_off, S, scan_ws, scan_bytes, st))) return rc;
     if (A > 0) {
-        csr_fill<<<sgb_div_up(A, 256), 256, 0, st>>>(adj, A, row_off, cursor, nbr, eid);
-        csr_sort_rows<<<sgb_div_up(S, 128), 128, 0, st>>>(row_off, S, nbr, eid);
+        if ((rc = sgb_exclusive_scan_i32(outdeg, first, S, scan_ws, scan_bytes, st))) return rc;
+        { csr_row_write<<<sgb_div_up(S, 8), 256, 0, st>>>(bitmap, S, wpr, row_off, first, nbr, eid); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
@@ -577,7 +628,7 @@ extern "C" int sgb_edge_dist_fwd(const float* feat, int C, const int* adj, int A
     if (A < 0 || C <= 0) return SGB_ERR_INVALID;
     if (A == 0) return SGB_OK;
     if (!feat || !adj || !dist) return SGB_ERR_INVALID;
-    edge_dist_fwd_kernel<<<sgb_div_up(A, 8), 256, 0, (cudaStream_t)stream>>>(feat, C, adj, A, dist);
+    { edge_dist_fwd_kernel<<<sgb_div_up(A, 8), 256, 0, (cudaStream_t)stream>>>(feat, C, adj, A, dist); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -587,7 +638,7 @@ extern "C" int sgb_edge_dist_bwd(const float* feat, int S, int C, const int* adj
     if (A < 0 || C <= 0 || S <= 0) return SGB_ERR_INVALID;
     if (A == 0) return SGB_OK;
     if (!feat || !adj || !dist || !gdist || !row_off || !eid || !gfeat) return SGB_ERR_INVALID;
-    edge_dist_bwd_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(feat, C, adj, dist, gdist, row_off, eid, S, gfeat);
+    { edge_dist_bwd_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(feat, C, adj, dist, gdist, row_off, eid, S, gfeat); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -595,7 +646,7 @@ extern "C" int sgb_edge_dist_bwd(const float* feat, int S, int C, const int* adj
 extern "C" int sgb_gcn_agg_fwd(const float* X, int S, int C, const float* sims, const int* row_off, const int* nbr, const int* eid,
                                float* AX, float* rowsum, void* stream) {
     if (S <= 0 || C <= 0 || !X || !row_off || !AX || !rowsum) return SGB_ERR_INVALID;
-    gcn_agg_fwd_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(X, C, sims, row_off, nbr, eid, S, AX, rowsum);
+    { gcn_agg_fwd_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(X, C, sims, row_off, nbr, eid, S, AX, rowsum); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -604,10 +655,10 @@ extern "C" int sgb_gcn_agg_bwd(const float* dAX, const float* X, const float* AX
                                float* dX, float* dsims, void* stream) {
     if (S <= 0 || C <= 0 || A < 0 || !dAX || !X || !AX || !rowsum || !row_off || !dX) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    gcn_agg_bwd_x_kernel<<<S, 128, 0, st>>>(dAX, C, sims, rowsum, row_off, nbr, eid, S, dX);
+    { gcn_agg_bwd_x_kernel<<<S, 128, 0, st>>>(dAX, C, sims, rowsum, row_off, nbr, eid, S, dX); SGB_COUNT_LAUNCH(); }
     if (A > 0) {
         if (!adj || !dsims || !sims) return SGB_ERR_INVALID;
-        gcn_agg_bwd_s_kernel<<<sgb_div_up(A, 8), 256, 0, st>>>(dAX, X, AX, C, rowsum, adj, A, dsims);
+        { gcn_agg_bwd_s_kernel<<<sgb_div_up(A, 8), 256, 0, st>>>(dAX, X, AX, C, rowsum, adj, A, dsims); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
@@ -622,8 +673,8 @@ extern "C" int sgb_group_nearby(const int* adj, int A, const int* roots_cur, con
     const int in_smem = state_bytes <= 160 * 1024;
     if (in_smem && state_bytes > 16 * 1024)
         SGB_CUDA(cudaFuncSetAttribute(group_nearby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)state_bytes));
-    group_nearby_kernel<<<1, GN_THREADS, in_smem ? state_bytes : 0, (cudaStream_t)stream>>>(adj, A, roots_cur, dist, th, uf, S1, sweep_cap,
-                                                                                           status, in_smem);
+    { group_nearby_kernel<<<1, GN_THREADS, in_smem ? state_bytes : 0, (cudaStream_t)stream>>>(adj, A, roots_cur, dist, th, uf, S1, sweep_cap,
+                                                                                           status, in_smem); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -633,8 +684,8 @@ extern "C" int sgb_group_unlabeled_step(const float* dist, const int* row_off, c
                                         const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream) {
     if (S <= 0 || S1 <= 0 || !row_off || !roots_cur || !uf || !amin_ws) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    unlabeled_argmin_kernel<<<sgb_div_up(S, 128), 128, 0, st>>>(dist, row_off, nbr, eid, S, amin_ws);
-    unlabeled_union_kernel<<<1, 32, 0, st>>>(amin_ws, S, roots_cur, uf, S1);
+    { unlabeled_argmin_kernel<<<sgb_div_up(S, 128), 128, 0, st>>>(dist, row_off, nbr, eid, S, amin_ws); SGB_COUNT_LAUNCH(); }
+    { unlabeled_union_kernel<<<1, 32, 0, st>>>(amin_ws, S, roots_cur, uf, S1); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -642,8 +693,8 @@ extern "C" int sgb_group_unlabeled_step(const float* dist, const int* row_off, c
 extern "C" int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
                                  const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem, void* stream) {
     if (n_raw <= 0 || !seg_of_point || !seg2cl || !cl_rootpt || !cl_ins || !cl_sem) return SGB_ERR_INVALID;
-    export_labels_kernel<<<sgb_div_up(n_raw, 256), 256, 0, (cudaStream_t)stream>>>(unmap, n_raw, seg_of_point, seg2cl, cl_rootpt,
-                                                                                   cl_ins, cl_sem, out_seg, out_ins, out_sem);
+    { export_labels_kernel<<<sgb_div_up(n_raw, 256), 256, 0, (cudaStream_t)stream>>>(unmap, n_raw, seg_of_point, seg2cl, cl_rootpt,
+                                                                                   cl_ins, cl_sem, out_seg, out_ins, out_sem); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

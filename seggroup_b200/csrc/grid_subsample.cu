@@ -263,19 +263,19 @@ extern "C" int sgb_grid_subsample(const float* xyz, const float* feat, const int
     if (out_batches) SGB_CUDA(cudaMemsetAsync(out_batches, 0, (size_t)B * 4, st));
     const int g = sgb_div_up(N, 256);
     int rc;
-    gs_batch_offsets<<<1, 32, 0, st>>>(batches, B, N, boff, status);
-    gs_batch_bounds<<<B, 256, 0, st>>>(xyz, boff, dl, bp, nullptr);
-    gs_insert<<<g, 256, 0, st>>>(xyz, N, boff, B, bp, dl, tkeys, tfirst, tcount, T - 1, slot_of, status);
-    gs_flag_first<<<g, 256, 0, st>>>(slot_of, tfirst, N, flag);
+    { gs_batch_offsets<<<1, 32, 0, st>>>(batches, B, N, boff, status); SGB_COUNT_LAUNCH(); }
+    { gs_batch_bounds<<<B, 256, 0, st>>>(xyz, boff, dl, bp, nullptr); SGB_COUNT_LAUNCH(); }
+    { gs_insert<<<g, 256, 0, st>>>(xyz, N, boff, B, bp, dl, tkeys, tfirst, tcount, T - 1, slot_of, status); SGB_COUNT_LAUNCH(); }
+    { gs_flag_first<<<g, 256, 0, st>>>(slot_of, tfirst, N, flag); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(flag, rank, N, scan_ws, scan_bytes, st))) return rc;
-    gs_number_voxels<<<g, 256, 0, st>>>(slot_of, flag, rank, N, tcount, tvox, vcount, out_first ? out_first : vfirst, boff, B, out_batches, counts);
+    { gs_number_voxels<<<g, 256, 0, st>>>(slot_of, flag, rank, N, tcount, tvox, vcount, out_first ? out_first : vfirst, boff, B, out_batches, counts); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(vcount, voff, N, scan_ws, scan_bytes, st))) return rc;
-    gs_bucket<<<g, 256, 0, st>>>(slot_of, tvox, N, voff, cursor, list);
-    gs_sort_small<<<g, 256, 0, st>>>(voff, counts, list, big, nbig);
-    gs_ranksort_big<<<148, 256, 0, st>>>(voff, big, nbig, list, scratch);
-    gs_reduce_points<<<g, 256, 0, st>>>(xyz, voff, list, counts, out_xyz);
-    if (fdim) gs_reduce_features<<<sgb_div_up((long long)N * fdim, 256), 256, 0, st>>>(feat, fdim, voff, list, counts, out_feat);
-    if (ldim) gs_reduce_labels<<<sgb_div_up((long long)N * ldim, 256), 256, 0, st>>>(cls, ldim, voff, list, counts, out_cls);
+    { gs_bucket<<<g, 256, 0, st>>>(slot_of, tvox, N, voff, cursor, list); SGB_COUNT_LAUNCH(); }
+    { gs_sort_small<<<g, 256, 0, st>>>(voff, counts, list, big, nbig); SGB_COUNT_LAUNCH(); }
+    { gs_ranksort_big<<<148, 256, 0, st>>>(voff, big, nbig, list, scratch); SGB_COUNT_LAUNCH(); }
+    { gs_reduce_points<<<g, 256, 0, st>>>(xyz, voff, list, counts, out_xyz); SGB_COUNT_LAUNCH(); }
+    if (fdim) { gs_reduce_features<<<sgb_div_up((long long)N * fdim, 256), 256, 0, st>>>(feat, fdim, voff, list, counts, out_feat); SGB_COUNT_LAUNCH(); }
+    if (ldim) { gs_reduce_labels<<<sgb_div_up((long long)N * ldim, 256), 256, 0, st>>>(cls, ldim, voff, list, counts, out_cls); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -284,8 +284,8 @@ extern "C" int sgb_grid_subsample(const float* xyz, const float* feat, const int
 extern "C" int sgb_batch_bounds(const float* xyz, int N, const int* batches, int B, float* minmax, int* boff_out /*[B+1]*/, int* status, void* stream) {
     if (N <= 0 || B <= 0 || !xyz || !minmax || !boff_out || !status) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    gs_batch_offsets<<<1, 32, 0, st>>>(batches, B, N, boff_out, status);
-    gs_batch_bounds<<<B, 256, 0, st>>>(xyz, boff_out, 1.f, nullptr, minmax);
+    { gs_batch_offsets<<<1, 32, 0, st>>>(batches, B, N, boff_out, status); SGB_COUNT_LAUNCH(); }
+    { gs_batch_bounds<<<B, 256, 0, st>>>(xyz, boff_out, 1.f, nullptr, minmax); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

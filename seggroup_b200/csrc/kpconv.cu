@@ -319,13 +319,13 @@ extern "C" int sgb_kpconv_fwd(const float* query_points, const float* support_po
     const int grid = sgb_div_up(n, p.T);
     if (p.cpl == 1) {
         SGB_CUDA(cudaFuncSetAttribute(kpconv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        kpconv_fwd_kernel<1><<<grid, KP_THREADS, p.smem, st>>>(a);
+        { kpconv_fwd_kernel<1><<<grid, KP_THREADS, p.smem, st>>>(a); SGB_COUNT_LAUNCH(); }
     } else if (p.cpl == 2) {
         SGB_CUDA(cudaFuncSetAttribute(kpconv_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        kpconv_fwd_kernel<2><<<grid, KP_THREADS, p.smem, st>>>(a);
+        { kpconv_fwd_kernel<2><<<grid, KP_THREADS, p.smem, st>>>(a); SGB_COUNT_LAUNCH(); }
     } else {
         SGB_CUDA(cudaFuncSetAttribute(kpconv_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        kpconv_fwd_kernel<4><<<grid, KP_THREADS, p.smem, st>>>(a);
+        { kpconv_fwd_kernel<4><<<grid, KP_THREADS, p.smem, st>>>(a); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
@@ -365,16 +365,16 @@ extern "C" int sgb_kpconv_bwd(const float* g, const float* query_points, const f
     cudaStream_t st = (cudaStream_t)stream;
     if (p.cpl == 1) {
         SGB_CUDA(cudaFuncSetAttribute(kpconv_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kpconv_bwd_kernel<1><<<grid, KP_THREADS, smem, st>>>(a, b);
+        { kpconv_bwd_kernel<1><<<grid, KP_THREADS, smem, st>>>(a, b); SGB_COUNT_LAUNCH(); }
     } else if (p.cpl == 2) {
         SGB_CUDA(cudaFuncSetAttribute(kpconv_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kpconv_bwd_kernel<2><<<grid, KP_THREADS, smem, st>>>(a, b);
+        { kpconv_bwd_kernel<2><<<grid, KP_THREADS, smem, st>>>(a, b); SGB_COUNT_LAUNCH(); }
     } else {
         SGB_CUDA(cudaFuncSetAttribute(kpconv_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kpconv_bwd_kernel<4><<<grid, KP_THREADS, smem, st>>>(a, b);
+        { kpconv_bwd_kernel<4><<<grid, KP_THREADS, smem, st>>>(a, b); SGB_COUNT_LAUNCH(); }
     }
     const long long total = (long long)K * Cin * Cout;
-    kpconv_bwd_reduce<<<sgb_div_up(total, 256), 256, 0, st>>>((const float*)ws, grid, total, gK);
+    { kpconv_bwd_reduce<<<sgb_div_up(total, 256), 256, 0, st>>>((const float*)ws, grid, total, gK); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

@@ -255,7 +255,7 @@ backward_finalize_kernel(const double* __restrict__ sums, double M, const float*
 
 using namespace sgb_mlp1;
 
-extern "C" size_t sgb_mlp1_ws_bytes(int S) { return (size_t)(S > 0 ? S : 0) * NE * sizeof(double); }
+extern "C" size_t sgb_mlp1_ws_bytes(int S) { return (size_t)((S > 0 ? S : 0) + 1) * NE * sizeof(double); }
 
 // clouds [S,64,6] (output of sgb_cluster_cloud_transform) -> feat [S,128]; knn_idx [S,64,10] local ids;
 // stats [4][64], var [64], mom [27] as in sgb_edgeconv_fwd.
@@ -267,9 +267,11 @@ extern "C" int sgb_mlp1_fwd(const float* clouds, int S, const float* W, const fl
     if (ws_bytes < sgb_mlp1_ws_bytes(S)) return SGB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     double* part = (double*)ws;
-    knn_gram_kernel<<<S, P, 0, st>>>(clouds, S, knn_idx, part);
-    sgb_bn::bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(part, S, (double)S * P * K, W, nullptr, gamma, beta, stats, var, mom);
-    forward_kernel<<<S, P, 0, st>>>(clouds, knn_idx, S, W, stats, feat, arg_pt);
+    if (!mom) mom = part + (size_t)S * NE;                 // inference: nobody keeps the moments
+    { knn_gram_kernel<<<S, P, 0, st>>>(clouds, S, knn_idx, part); SGB_COUNT_LAUNCH(); }
+    sgb_bn::reduce_partials(part, S, NE, mom, st);
+    { sgb_bn::bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(mom, 1, (double)S * P * K, W, nullptr, gamma, beta, stats, var, nullptr); SGB_COUNT_LAUNCH(); }
+    { forward_kernel<<<S, P, 0, st>>>(clouds, knn_idx, S, W, stats, feat, arg_pt); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -287,9 +289,9 @@ extern "C" int sgb_mlp1_bwd(const float* g, const float* clouds, const int* knn_
     double* sums = (double*)ws;
     float* part = (float*)((unsigned char*)ws + COUT * 8 * sizeof(double));
     const double M = (double)S * P * K;
-    backward_kernel<<<S, P, 0, st>>>(g, clouds, knn_idx, arg_pt, S, W, stats, mom, M, part);
-    backward_reduce_kernel<<<1, 512, 0, st>>>(part, S, sums);
-    backward_finalize_kernel<<<1, 64, 0, st>>>(sums, M, W, stats, mom, gW, gg, gb);
+    { backward_kernel<<<S, P, 0, st>>>(g, clouds, knn_idx, arg_pt, S, W, stats, mom, M, part); SGB_COUNT_LAUNCH(); }
+    sgb_bn::reduce_partials(part, S, COUT * 8, sums, st);
+    { backward_finalize_kernel<<<1, 64, 0, st>>>(sums, M, W, stats, mom, gW, gg, gb); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

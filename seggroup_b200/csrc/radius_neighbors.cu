@@ -233,11 +233,11 @@ extern "C" int sgb_radius_neighbors_count(const float* queries, int Nq, const fl
     if ((rc = sgb_batch_bounds(supports, Ns, s_batches, B, L.minmax, L.sboff, status, st))) return rc;
     // query batch offsets (the queries' own bounds are a by-product: cells are relative to the supports' corner)
     if ((rc = sgb_batch_bounds(queries, Nq, q_batches, B, L.qminmax, L.qboff, status, st))) return rc;
-    rn_insert<<<sgb_div_up(Ns, 256), 256, 0, st>>>(supports, Ns, L.sboff, B, L.minmax, inv_cell, L.tkeys, L.tcount, L.T - 1, L.slot_of, status);
+    { rn_insert<<<sgb_div_up(Ns, 256), 256, 0, st>>>(supports, Ns, L.sboff, B, L.minmax, inv_cell, L.tkeys, L.tcount, L.T - 1, L.slot_of, status); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(L.tcount, L.toff, (int)L.T, L.scan_ws, L.scan_bytes, st))) return rc;
-    rn_bucket<<<sgb_div_up(Ns, 256), 256, 0, st>>>(Ns, L.slot_of, L.toff, L.cursor, L.list);
-    rn_count<<<sgb_div_up(Nq, 128), 128, 0, st>>>(queries, Nq, L.qboff, supports, B, L.minmax, inv_cell, r2, L.tkeys, L.T - 1, L.toff, L.list,
-                                                  L.counts, L.max_count);
+    { rn_bucket<<<sgb_div_up(Ns, 256), 256, 0, st>>>(Ns, L.slot_of, L.toff, L.cursor, L.list); SGB_COUNT_LAUNCH(); }
+    { rn_count<<<sgb_div_up(Nq, 128), 128, 0, st>>>(queries, Nq, L.qboff, supports, B, L.minmax, inv_cell, r2, L.tkeys, L.T - 1, L.toff, L.list,
+                                                  L.counts, L.max_count); SGB_COUNT_LAUNCH(); }
     SGB_CUDA(cudaMemcpyAsync(max_count_out, L.max_count, 4, cudaMemcpyDeviceToDevice, st));
     SGB_CHECK_LAUNCH();
     return SGB_OK;
@@ -255,8 +255,8 @@ extern "C" int sgb_radius_neighbors_fill(const float* queries, int Nq, const flo
     RnLayout L = rn_layout(ws, Nq, Ns, B);
     const float inv_cell = 1.f / (radius * CELL_SLACK);
     const float r2 = radius * radius;
-    rn_fill<<<sgb_div_up(Nq, RN_WARPS), RN_WARPS * 32, 0, st>>>(queries, Nq, L.qboff, supports, Ns, B, L.minmax, inv_cell, r2, L.tkeys, L.T - 1,
-                                                               L.toff, L.list, L.counts, W, neighbors, status);
+    { rn_fill<<<sgb_div_up(Nq, RN_WARPS), RN_WARPS * 32, 0, st>>>(queries, Nq, L.qboff, supports, Ns, B, L.minmax, inv_cell, r2, L.tkeys, L.T - 1,
+                                                               L.toff, L.list, L.counts, W, neighbors, status); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

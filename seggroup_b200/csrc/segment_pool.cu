@@ -1,6 +1,6 @@
 // a10: segment max pooling with argmax (forward) and its scatter backward.
 //
-// Forward layout: one warp owns R consecutive positions of the member list, lanes own channels
+// Forward layout: one warp owns R = 32 consecutive positions of the member list, lanes own channels
 // (float2 per lane -> one 256 B row per warp-load at C=64).  A running (max, first position) is kept
 // in registers while the positions stay inside one segment and is merged into a 64-bit key
 //   (monotone float key << 32) | ~position
@@ -11,8 +11,7 @@
 #include "common.cuh"
 
 namespace {
-constexpr int POOL_R = 64;        // positions per warp
-constexpr int POOL_U = 8;         // rows in flight per warp
+constexpr int POOL_R = 32;        // positions per warp, all in flight at once
 constexpr int POOL_WARPS = 8;
 
 __device__ __forceinline__ bool better(float v, float best) {     // torch.max: NaN wins
@@ -50,36 +49,37 @@ segment_pool_fwd_kernel(const float* __restrict__ feat, int C, const int* __rest
         }
     };
 
-    for (int p = p0; p < p1; p += POOL_U) {
-        float val[POOL_U][VEC];
+    // one coalesced load of the warp's member ids, then all POOL_R row loads in flight at once (the rows are a gather:
+    // latency, not issue rate, bounds this kernel, so memory-level parallelism per warp is what matters)
+    int my_row = 0;
+    if (p0 + lane < p1) my_row = members ? __ldg(members + p0 + lane) : p0 + lane;
+    float val[POOL_R][VEC];
 #pragma unroll
-        for (int u = 0; u < POOL_U; ++u) {
-            const int q = p + u;
-            if (q < p1 && active) {
-                const int row = members ? __ldg(members + q) : q;
-                const float* src = feat + (size_t)row * C + c0;
-                if (VEC == 2) {
-                    float2 t = __ldg(reinterpret_cast<const float2*>(src));
-                    val[u][0] = t.x; val[u][VEC - 1] = t.y;
-                } else {
-                    val[u][0] = __ldg(src);
-                }
+    for (int u = 0; u < POOL_R; ++u) {
+        const int row = __shfl_sync(SGB_FULL_MASK, my_row, u);
+        if (p0 + u < p1 && active) {
+            const float* src = feat + (size_t)row * C + c0;
+            if (VEC == 2) {
+                float2 t = __ldg(reinterpret_cast<const float2*>(src));
+                val[u][0] = t.x; val[u][VEC - 1] = t.y;
+            } else {
+                val[u][0] = __ldg(src);
             }
         }
+    }
 #pragma unroll
-        for (int u = 0; u < POOL_U; ++u) {
-            const int q = p + u;
-            if (q < p1) {
-                while (q >= seg_end) {          // warp-uniform
-                    flush(seg);
-                    ++seg;
-                    seg_end = __ldg(offsets + seg + 1);
-                }
-                if (active) {
+    for (int u = 0; u < POOL_R; ++u) {
+        const int q = p0 + u;
+        if (q < p1) {
+            while (q >= seg_end) {          // warp-uniform
+                flush(seg);
+                ++seg;
+                seg_end = __ldg(offsets + seg + 1);
+            }
+            if (active) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        if (best_pos[v] < 0 || better(val[u][v], best[v])) { best[v] = val[u][v]; best_pos[v] = q; }
-                    }
+                for (int v = 0; v < VEC; ++v) {
+                    if (best_pos[v] < 0 || better(val[u][v], best[v])) { best[v] = val[u][v]; best_pos[v] = q; }
                 }
             }
         }
@@ -125,10 +125,10 @@ extern "C" int sgb_segment_pool_max_fwd(const float* feat, int n_rows, int C, co
     const int warps = sgb_div_up(n_members, POOL_R);
     const bool vec2 = (C % 2 == 0) && (((uintptr_t)feat & 7) == 0);
     dim3 grid(sgb_div_up(warps, POOL_WARPS), sgb_div_up(C, 32 * (vec2 ? 2 : 1)));
-    if (vec2) segment_pool_fwd_kernel<2><<<grid, POOL_WARPS * 32, 0, st>>>(feat, C, members, n_members, offsets, S, keys);
-    else      segment_pool_fwd_kernel<1><<<grid, POOL_WARPS * 32, 0, st>>>(feat, C, members, n_members, offsets, S, keys);
+    if (vec2) { segment_pool_fwd_kernel<2><<<grid, POOL_WARPS * 32, 0, st>>>(feat, C, members, n_members, offsets, S, keys); SGB_COUNT_LAUNCH(); }
+    else      { segment_pool_fwd_kernel<1><<<grid, POOL_WARPS * 32, 0, st>>>(feat, C, members, n_members, offsets, S, keys); SGB_COUNT_LAUNCH(); }
     const long long total = (long long)S * C;
-    segment_pool_decode_kernel<<<sgb_div_up(total, 256), 256, 0, st>>>(keys, members, total, out, argmax);
+    { segment_pool_decode_kernel<<<sgb_div_up(total, 256), 256, 0, st>>>(keys, members, total, out, argmax); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -138,7 +138,7 @@ extern "C" int sgb_segment_pool_max_bwd(const float* grad_out, const int* argmax
     if (S == 0) return SGB_OK;
     if (!grad_out || !argmax || !grad_feat) return SGB_ERR_INVALID;
     const long long total = (long long)S * C;
-    segment_pool_bwd_kernel<<<sgb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, argmax, total, C, grad_feat);
+    { segment_pool_bwd_kernel<<<sgb_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, argmax, total, C, grad_feat); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

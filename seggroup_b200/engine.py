@@ -1,0 +1,111 @@
+"""Scene-parallel executor for one GPU: runs the scenes of a batch concurrently on separate CUDA streams.
+
+A SegGroup scene is a chain of ~600 kernels of which many are latency bound (single-CTA sequential union
+replays, CSR builds over a few thousand rows) and a handful are wide (EdgeConv, kNN).  One scene therefore
+cannot fill 148 SMs; the unit of parallelism on a B200 is the scene (scenes are independent,
+BatchNorm statistics are per scene).  `SceneExecutor` keeps `n_streams` host threads, each bound to its own
+CUDA stream; every thread drives whole scenes through `pipeline.forward_scene` (+ `torch.autograd.grad`), so
+the narrow kernels of one scene overlap the wide kernels of the others and the host-side read-backs of one
+scene (cluster counts) do not idle the device.
+
+Gradient semantics of a training batch = the reference at `len(scenes)` ranks (train.py:165-170 + DDP
+average): mean over scenes of loss_sum / loss_num.  Per-scene gradients are summed in scene order on the
+caller's stream, so the result does not depend on thread scheduling.
+"""
+from __future__ import annotations
+
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import torch
+
+from . import pipeline
+
+
+class SceneExecutor:
+    def __init__(self, device=None, n_streams: int = 4):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_streams = max(1, int(n_streams))
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
+        self._pool = ThreadPoolExecutor(max_workers=self.n_streams, thread_name_prefix="sgb-scene")
+        self._free = list(range(self.n_streams))
+        self._lock = threading.Lock()
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+    # ------------------------------------------------------------------------------------------
+    def _run(self, fn, items):
+        """fn(item, index) is executed for every item on one of the executor's streams; results in item order."""
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+
+        def work(i, item):
+            with self._lock:
+                sid = self._free.pop()
+            try:
+                torch.cuda.set_device(self.device)
+                st = self.streams[sid]
+                st.wait_event(ready)                       # parameters / inputs produced on the caller's stream
+                with torch.cuda.stream(st):
+                    out = fn(item, i)
+                    done = torch.cuda.Event()
+                    done.record(st)
+                return out, done
+            finally:
+                with self._lock:
+                    self._free.append(sid)
+
+        futs = [self._pool.submit(work, i, it) for i, it in enumerate(items)]
+        outs = []
+        for f in futs:
+            out, done = f.result()
+            main.wait_event(done)                          # device-side join, no host synchronisation
+            outs.append(out)
+        return outs
+
+    # ------------------------------------------------------------------------------------------
+    def infer_batch(self, scenes, params, mode="ins_infer", upload=None):
+        """-> list of ForwardResult.  `upload(scene)` (optional) turns a host-side scene into a SceneDevice on the
+        worker's stream (end-to-end path: the H2D copies of one scene overlap the kernels of the others)."""
+        def fn(sc, i):
+            if upload is not None:
+                sc = upload(sc)
+            with torch.no_grad():
+                return pipeline.forward_scene(sc, params, mode=mode)
+        return self._run(fn, scenes)
+
+    def train_batch(self, scenes, params, train_keys, upload=None):
+        """Forward + backward of every scene; accumulates d(mean_i loss_i)/d(param) into `param.grad` (fixed scene
+        order) and returns the mean loss (0-dim device tensor).  params: dict name -> tensor; train_keys: names
+        of the leaves that require grad."""
+        leaves = [params[k] for k in train_keys]
+        n = len(scenes)
+        main = torch.cuda.current_stream(self.device)
+
+        def fn(sc, i):
+            if upload is not None:
+                sc = upload(sc)
+            r = pipeline.forward_scene(sc, params, mode="train")
+            loss = r.loss_raw[0, 0] / r.loss_raw[0, 1] / n
+            grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+            for g in grads:
+                if g is not None:
+                    g.record_stream(main)
+            loss = loss.detach()
+            loss.record_stream(main)
+            return loss, grads
+
+        outs = self._run(fn, scenes)
+        total = torch.zeros((), device=self.device)
+        for loss, grads in outs:
+            total += loss
+            for p, g in zip(leaves, grads):
+                if g is None:
+                    continue
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.add_(g)
+        return total

@@ -54,7 +54,7 @@ def uf_to_device(uf):
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 1_000_003])
+@pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 32768, 32769, 1_000_003])
 def test_scan(n):
     from seggroup_b200 import ops
     x = np.random.default_rng(n).integers(0, 7, n).astype(np.int32)
@@ -342,3 +342,24 @@ def test_edge_dist_and_gcn(C):
     (out * g.cuda()).sum().backward()
     assert rel_err(Xd.grad, Xr.grad) < RTOL
     assert rel_err(Wd.grad, Wr.grad) < RTOL
+
+
+@pytest.mark.parametrize("S,E", [(1, 0), (37, 60), (300, 1500), (1117, 3400), (2999, 20000)])
+def test_sym_csr_exact(S, E):
+    """Rows list (neighbour, edge id) by ascending neighbour; hub rows (one cluster adjacent to most others) included."""
+    from seggroup_b200 import ops
+    rng = np.random.default_rng(S)
+    e = rng.integers(0, S, (E, 2))
+    if S > 2:
+        hub = np.stack([np.full(S // 2, S // 3), rng.permutation(S)[:S // 2]], 1)     # a hub in the middle of the id range
+        e = np.concatenate([e, hub])
+    e = e[e[:, 0] != e[:, 1]] if len(e) else e.reshape(0, 2)
+    adj = np.unique(np.sort(e, 1), axis=0).astype(np.int32).reshape(-1, 2)
+    row_off, nbr, eid = ops.sym_csr(dev(adj, torch.int32), S)
+    A = len(adj)
+    src = np.concatenate([adj[:, 0], adj[:, 1]]); dst = np.concatenate([adj[:, 1], adj[:, 0]]); ids = np.concatenate([np.arange(A), np.arange(A)])
+    order = np.lexsort((dst, src))
+    ref_off = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=S))])
+    assert np.array_equal(row_off.cpu().numpy(), ref_off)
+    assert np.array_equal(nbr.cpu().numpy()[:2 * A], dst[order])
+    assert np.array_equal(eid.cpu().numpy()[:2 * A], ids[order])
