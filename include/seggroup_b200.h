@@ -43,6 +43,14 @@ size_t sgb_scan_ws_bytes(int n);
 /* out[i] = sum(in[0..i-1]); out has n+1 entries (out[n] = total).  in/out may not alias. */
 int sgb_exclusive_scan_i32(const int* in, int* out, int n, void* ws, size_t ws_bytes, void* stream);
 
+/* Dense fp32 GEMM on the tcgen05 tensor cores (TF32 x 3 split, fp32-level accuracy): C [M,N] = A [M,K] * B [N,K]^T,
+ * the shape of nn.Linear (the GCN fc of seggroup/model.py:146-151).  N multiple of 16 and <= 256, K multiple of 4. */
+int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, void* stream);
+/* Bring-up probe: shared memory := the two images (word counts multiples of 256), ONE tcgen05.mma kind::tf32 with M = 128,
+ * K = 8 and the given descriptor fields (start address filled in by the kernel), raw accumulator D [128,N] returned. */
+int sgb_tc_probe(const float* imgA, int wordsA, const float* imgB, int wordsB, unsigned long long descA,
+                 unsigned long long descB, unsigned idesc, int N, float* D, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a10  segment pooling: point features -> segment features
  * replaces seggroup/model.py:278-288 `aggregate_cluster_feature` (use_avg=False at every call
@@ -129,8 +137,9 @@ int sgb_mlp1_bwd(const float* g, const float* clouds, const int* knn_idx, const 
  * max_k lrelu(BN2(W2 lrelu(BN1(W1 e)))) (two_layer = 1, MLP3), e = (x_j - x_i, x_i).
  * argk [N,64] uint8 (may be NULL): arg-max edge per point and channel, needed by the backward.
  * W1 [64,18], W2 [64,64]; stats1, stats2, var1, var2 as in sgb_mlp1_fwd; mom1 [189] / mom2 [4160] fp64 moments of the
- * layer inputs (NULL allowed for mom1 when no backward follows); ctr_out [18] = centre e0 the first
- * moments were taken about (NULL allowed).
+ * layer inputs (NULL allowed when no backward follows); ctr_out [18] = centre e0 the first moments were taken about
+ * (NULL allowed).  With two_layer = 1 and mom2 = NULL the 64x64 contraction runs on the tcgen05 tensor cores (TF32 x 3
+ * split, fp32-level accuracy) in one fused pass that also yields the BatchNorm-2 statistics (csrc/edgeconv_tc.cu).
  * ------------------------------------------------------------------------------------------- */
 size_t sgb_edgeconv_ws_bytes(int N, int two_layer);
 int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_layer,

@@ -337,6 +337,7 @@ extern "C" size_t sgb_edgeconv_ws_bytes(int N, int two_layer) {
     const size_t g = (size_t)persistent_grid(N);
     size_t b = 128 + 256 * 9 * 8 + 192 * 8 + g * NE1 * 8;
     if (two_layer) b += (size_t)(148 * 2) * NE2 * 8;
+    if (two_layer) { b = (b + 255) & ~(size_t)255; b += sgb_ec2_tc_ws_bytes(N); }
     return b;
 }
 
@@ -350,7 +351,7 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
                                 void* ws, size_t ws_bytes, void* stream) {
     if (N <= 0) return N == 0 ? SGB_OK : SGB_ERR_INVALID;
     if (!x9 || !knn || !W1 || !gamma1 || !beta1 || !out || !stats1 || !ws) return SGB_ERR_INVALID;
-    if (two_layer && (!W2 || !gamma2 || !beta2 || !stats2 || !mom2)) return SGB_ERR_INVALID;
+    if (two_layer && (!W2 || !gamma2 || !beta2 || !stats2)) return SGB_ERR_INVALID;
     if (ws_bytes < sgb_edgeconv_ws_bytes(N, two_layer)) return SGB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* w8 = (unsigned char*)ws;
@@ -370,6 +371,12 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     sgb_bn::reduce_partials(g1part, grid, NE1, m1red, st);
     { bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(m1red, 1, M, W1, ctr, gamma1, beta1, stats1, var1, nullptr); SGB_COUNT_LAUNCH(); }
     if (ctr_out) SGB_CUDA(cudaMemcpyAsync(ctr_out, ctr, 18 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (two_layer && !mom2) {
+        // no backward follows (nobody keeps the hidden-layer moments): second layer on the tcgen05 tensor cores
+        size_t off = 128 + 256 * 9 * 8 + 192 * 8 + (size_t)grid * NE1 * 8 + (size_t)(148 * 2) * NE2 * 8;
+        off = (off + 255) & ~(size_t)255;
+        return sgb_ec2_tc_forward(x9, knn, N, W1, stats1, W2, gamma2, beta2, out, argk, stats2, var2, w8 + off, st);
+    }
     if (two_layer) {
         const int g2 = grid < 148 * 2 ? grid : 148 * 2;
         const size_t sm2 = SMEM_STAGE + NE2 * sizeof(double) + sizeof(float) * CIN * COUT;

@@ -1,0 +1,174 @@
+// Dense fp32 GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM) with the
+// TF32 x 3 split of tc_common.cuh:  C[M,N] = A[M,K] * B[N,K]^T  (the shape of nn.Linear / a 1x1 convolution).
+// Used for the dense heads of the segment graph (GCN fc 192x192 / 256x256, model.py:146-151) and as the unit test of
+// the descriptor / TMEM / mbarrier plumbing that the fused EdgeConv and KPConv kernels build on.
+//
+// One CTA (128 threads) owns a 128-row tile of C and all N <= 256 columns; K is consumed in chunks of 32:
+//   all threads: global -> registers -> (hi, lo) split -> canonical no-swizzle smem tiles -> fence.proxy.async
+//   thread 0   : 4 k-steps x 3 tcgen05.mma (hi*hi, lo*hi, hi*lo) per chunk, tcgen05.commit -> mbarrier
+//   all threads: wait on the mbarrier before the tiles are overwritten; after the last chunk every warp reads its
+//                32 TMEM lanes with tcgen05.ld and stores the rows of C.
+// Measured with the probe kernel below (tools/tc_probe*.py): kind::tf32 reads MN-major operands ONLY in the
+// SWIZZLE_128B_BASE32B layout (every other layout type yields zeros), whose swizzle differs from all K-major layouts, so
+// one shared-memory tile cannot serve both X W^T and X^T X; this library keeps its tf32 operands K-major.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+using namespace sgb_tc;
+constexpr int TG_THREADS = 128;
+constexpr int TG_KC = 32;                   // K columns per chunk (8 x 16 B)
+
+__global__ void __launch_bounds__(TG_THREADS)
+gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int tmem_cols) {
+    extern __shared__ __align__(128) unsigned char tg_smem[];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    unsigned char* sA_hi = tg_smem;                          // [128 x 32] fp32
+    unsigned char* sA_lo = sA_hi + 128 * TG_KC * 4;
+    unsigned char* sB_hi = sA_lo + 128 * TG_KC * 4;          // [N x 32]
+    unsigned char* sB_lo = sB_hi + (size_t)N * TG_KC * 4;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * 128;
+
+    if (warp == 0) tmem_alloc(&s_tmem, (uint32_t)tmem_cols);
+    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = make_idesc_tf32(128, N, false, false);
+
+    uint32_t phase = 0;
+    for (int k0 = 0; k0 < K; k0 += TG_KC) {
+        // ---- stage the chunk (zero-filled past M, N, K)
+        {
+            const int r = tid, gm = m0 + r;
+#pragma unroll
+            for (int c4 = 0; c4 < TG_KC / 4; ++c4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int k = k0 + c4 * 4;
+                if (gm < M && k < K) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * K + k));
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                const float4 l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+                const uint32_t off = tile_off(r, c4 * 4, 128);
+                *reinterpret_cast<float4*>(sA_hi + off) = h;
+                *reinterpret_cast<float4*>(sA_lo + off) = l;
+            }
+        }
+        for (int r = tid; r < N; r += TG_THREADS) {
+#pragma unroll
+            for (int c4 = 0; c4 < TG_KC / 4; ++c4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int k = k0 + c4 * 4;
+                if (k < K) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)r * K + k));
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                const float4 l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+                const uint32_t off = tile_off(r, c4 * 4, N);
+                *reinterpret_cast<float4*>(sB_hi + off) = h;
+                *reinterpret_cast<float4*>(sB_lo + off) = l;
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+#pragma unroll
+            for (int i = 0; i < TG_KC / 8; ++i) {
+                const uint32_t a_off = (uint32_t)(2 * i) * (128 * 16), b_off = (uint32_t)(2 * i) * (uint32_t)(N * 16);
+                const uint64_t dah = make_desc(smem_u32(sA_hi) + a_off, 128 * 16, 128);
+                const uint64_t dal = make_desc(smem_u32(sA_lo) + a_off, 128 * 16, 128);
+                const uint64_t dbh = make_desc(smem_u32(sB_hi) + b_off, (uint32_t)N * 16, 128);
+                const uint64_t dbl = make_desc(smem_u32(sB_lo) + b_off, (uint32_t)N * 16, 128);
+                mma_tf32(tmem, dah, dbh, idesc, k0 > 0 || i > 0);
+                mma_tf32(tmem, dal, dbh, idesc, true);
+                mma_tf32(tmem, dah, dbl, idesc, true);
+            }
+            mma_commit(&s_bar);
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+    }
+    fence_after_sync();
+    // ---- epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows m0 + 32w + lane
+    const int row = m0 + warp * 32 + (tid & 31);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        if (row < M) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(C + (size_t)row * N + c0 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+// Descriptor probe (test / bring-up tool): shared memory is loaded verbatim from two host-provided images, ONE
+// tcgen05.mma (M = 128, K = 8) is issued with caller-supplied descriptor fields, and the raw accumulator is returned.
+// tests/test_gpu_tc.py uses it to pin how the hardware walks K-major and MN-major no-swizzle operands.
+__global__ void __launch_bounds__(TG_THREADS)
+probe_kernel(const float* __restrict__ imgA, int wordsA, const float* __restrict__ imgB, int wordsB,
+             unsigned long long descA, unsigned long long descB, unsigned idesc, int N, float* __restrict__ D) {
+    extern __shared__ __align__(1024) unsigned char tg_smem[];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    float* sA = reinterpret_cast<float*>(tg_smem);
+    float* sB = sA + wordsA;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&s_tmem, 256);
+    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    for (int i = tid; i < wordsA; i += TG_THREADS) sA[i] = imgA[i];
+    for (int i = tid; i < wordsB; i += TG_THREADS) sB[i] = imgB[i];
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    if (tid == 0) {
+        const uint64_t da = descA | (uint64_t)((smem_u32(sA) >> 4) & 0x3fff);
+        const uint64_t db = descB | (uint64_t)((smem_u32(sB) >> 4) & 0x3fff);
+        mma_tf32(tmem, da, db, idesc, false);
+        mma_commit(&s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+    fence_after_sync();
+    const int row = warp * 32 + (tid & 31);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) D[(size_t)row * N + c0 + q] = v[q];
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+}  // namespace
+
+extern "C" int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, void* stream) {
+    if (M < 0 || N <= 0 || K <= 0) return SGB_ERR_INVALID;
+    if (M == 0) return SGB_OK;
+    if (!A || !B || !C) return SGB_ERR_INVALID;
+    if (N > 256 || (N & 15) || (K & 3)) return SGB_ERR_UNSUPPORTED;
+    int cols = 32;
+    while (cols < N) cols <<= 1;
+    const size_t smem = (size_t)(2 * 128 + 2 * N) * TG_KC * 4;
+    SGB_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tf32x3_kernel<<<sgb_div_up(M, 128), TG_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, cols); SGB_COUNT_LAUNCH();
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_tc_probe(const float* imgA, int wordsA, const float* imgB, int wordsB, unsigned long long descA,
+                            unsigned long long descB, unsigned idesc, int N, float* D, void* stream) {
+    if (!imgA || !imgB || !D || wordsA <= 0 || wordsB <= 0 || N <= 0 || N > 256 || (N & 15) || (wordsA & 255) || (wordsB & 255)) return SGB_ERR_INVALID;
+    const size_t smem = (size_t)(wordsA + wordsB) * 4;
+    if (smem > 200 * 1024) return SGB_ERR_UNSUPPORTED;
+    SGB_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_kernel<<<1, TG_THREADS, smem, (cudaStream_t)stream>>>(imgA, wordsA, imgB, wordsB, descA, descB, idesc, N, D); SGB_COUNT_LAUNCH();
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}

@@ -156,8 +156,9 @@ def edgeconv_bwd(g, arg, argk, x9, knn, W1, stats1, mom1, e0, W2=None, stats2=No
     return r
 
 
-def edgeconv_fwd(x9, knn, W1, gamma1, beta1, W2=None, gamma2=None, beta2=None, want_argk=True):
-    """x9 [N,9], knn [N,20] -> dict(out [N,64], argk [N,64] u8, stats1, var1, mom1, ctr [, stats2, var2, mom2])."""
+def edgeconv_fwd(x9, knn, W1, gamma1, beta1, W2=None, gamma2=None, beta2=None, want_argk=True, want_backward=True):
+    """x9 [N,9], knn [N,20] -> dict(out [N,64], argk [N,64] u8, stats1, var1, mom1, ctr [, stats2, var2, mom2]).
+    want_backward=False (inference): no moments are kept and the second layer of MLP3 runs on the tcgen05 tensor cores."""
     _chk(x9, F32, "x9"); _chk(knn, I32, "knn")
     N = x9.shape[0]
     dev = x9.device
@@ -166,12 +167,13 @@ def edgeconv_fwd(x9, knn, W1, gamma1, beta1, W2=None, gamma2=None, beta2=None, w
     if two:
         W2 = _chk(W2.reshape(64, 64), F32, "W2")
     o = dict(out=torch.empty(N, 64, dtype=F32, device=dev), stats1=torch.empty(4, 64, dtype=F32, device=dev),
-             var1=torch.empty(64, dtype=F32, device=dev), mom1=torch.empty(189, dtype=torch.float64, device=dev),
+             var1=torch.empty(64, dtype=F32, device=dev),
+             mom1=torch.empty(189, dtype=torch.float64, device=dev) if want_backward else None,
              ctr=torch.empty(18, dtype=F32, device=dev),
-             argk=torch.empty(N, 64, dtype=torch.uint8, device=dev) if want_argk else None)
+             argk=torch.empty(N, 64, dtype=torch.uint8, device=dev) if (want_argk or want_backward) else None)
     if two:
         o.update(stats2=torch.empty(4, 64, dtype=F32, device=dev), var2=torch.empty(64, dtype=F32, device=dev),
-                 mom2=torch.empty(4160, dtype=torch.float64, device=dev))
+                 mom2=torch.empty(4160, dtype=torch.float64, device=dev) if want_backward else None)
     ws = _ws(_lib.call("sgb_edgeconv_ws_bytes", N, int(two)), dev)
     _lib.call("sgb_edgeconv_fwd", x9, knn, N, int(two), W1, gamma1, beta1, W2, gamma2, beta2, o["out"], o["argk"], o["stats1"], o["var1"],
               o["mom1"], o.get("stats2"), o.get("var2"), o.get("mom2"), o["ctr"], ws, ws.numel(), _stream())
@@ -311,3 +313,18 @@ def export_labels(unmap, seg_of_point, level: Level, want_seg=True):
     _lib.call("sgb_export_labels", unmap, n_raw, seg_of_point, level.seg2cl, level.cl_rootpt, level.cl_ins, level.cl_sem,
               seg, ins, sem, _stream())
     return seg, ins, sem
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core primitives (tcgen05, TF32 x 3)
+# ------------------------------------------------------------------------------------------------
+def gemm_tf32x3(A, B):
+    """C [M,N] = A [M,K] @ B [N,K]^T on the tcgen05 tensor cores with the TF32 x 3 split (fp32-level accuracy)."""
+    _chk(A, F32, "A"); _chk(B, F32, "B")
+    M, K = A.shape
+    N = B.shape[0]
+    if B.shape[1] != K:
+        raise ValueError("A [M,K] and B [N,K] must share K")
+    C = torch.empty(M, N, dtype=F32, device=A.device)
+    _lib.call("sgb_gemm_tf32x3", A, B, C, M, N, K, _stream())
+    return C

@@ -257,8 +257,18 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
         W2 = p[pre + ".conv2.0.weight"] if two else None
         g2 = p[pre + ".bn2.weight"] if two else None
         b2 = p[pre + ".bn2.bias"] if two else None
-        fm, feat_pts, stats, var = EdgeConvPoolFn.apply(x9, knn, Lc.cl_pt_off, Lc.order, p[pre + ".conv1.0.weight"],
-                                                        p[pre + ".bn1.weight"], p[pre + ".bn1.bias"], W2, g2, b2)
+        W1, g1, b1 = p[pre + ".conv1.0.weight"], p[pre + ".bn1.weight"], p[pre + ".bn1.bias"]
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (W1, g1, b1, W2, g2, b2)):
+            fm, feat_pts, stats, var = EdgeConvPoolFn.apply(x9, knn, Lc.cl_pt_off, Lc.order, W1, g1, b1, W2, g2, b2)
+        else:
+            # inference: nothing is kept for a backward pass (MLP3's second layer then runs on the tensor cores)
+            o = ops.edgeconv_fwd(x9, knn, W1.contiguous(), g1.contiguous(), b1.contiguous(),
+                                 W2.contiguous() if two else None, g2.contiguous() if two else None, b2.contiguous() if two else None,
+                                 want_argk=False, want_backward=False)
+            feat_pts = o["out"]
+            fm, _ = ops.segment_pool_max(feat_pts, Lc.cl_pt_off, Lc.order, want_argmax=False)
+            stats = torch.stack([o["stats1"], o["stats2"]]) if two else o["stats1"].unsqueeze(0)
+            var = torch.stack([o["var1"], o["var2"]]) if two else o["var1"].unsqueeze(0)
         res.bn_stats[pre + ".bn1"] = (stats[0, 0], var[0], sc.n_points * 20)
         if two:
             res.bn_stats[pre + ".bn2"] = (stats[1, 0], var[1], sc.n_points * 20)
