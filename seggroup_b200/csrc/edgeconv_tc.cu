@@ -12,11 +12,12 @@
 //         max_k lrelu(BN2(z_k)) = lrelu(BN2(max_k z_k))  if gamma2 >= 0,   lrelu(BN2(min_k z_k))  otherwise,
 //     which removes the separate statistics pass of the SIMT path: ONE pass over the edges produces the statistics and
 //     the (max, min, arg) candidates; a light second kernel applies BN2 + LeakyReLU per point.
-// Warp roles (416 threads, 1 CTA / SM, persistent over a contiguous range of points):
+// Warp roles (480 threads, 1 CTA / SM, persistent over a contiguous range of points):
 //   warps 0-3   epilogue: tcgen05.ld of their TMEM sub-partition (an M = 64 accumulator keeps rows 16q..16q+15 on lanes
 //               32q..32q+15), statistics + max/min, coalesced stores of the per-point candidates;
-//   warp  4     TMEM allocation + the single MMA-issuing thread (24 tcgen05.mma per 128-edge tile) + tcgen05.commit;
-//   warps 5-12  producers: gather the edge vectors (L2-resident rows), first layer + BN1 + LeakyReLU on the CUDA cores,
+//   warp  4     TMEM allocation + the single MMA-issuing thread (24 tcgen05.mma per 160-edge tile) + tcgen05.commit;
+//   warps 5-14  producers: gather the edge vectors one tile ahead (register prefetch), first layer + BN1 + LeakyReLU on the
+//               CUDA cores with packed FFMA2,
 //               hi/lo split, 16-byte stores into the canonical no-swizzle K-major tile (conflict free: a warp writes 32
 //               consecutive edge rows of one 16-byte chunk), fence.proxy.async, mbarrier arrive.
 // Pipelines: shared-memory tiles full/empty (2 stages) and TMEM accumulators full/empty (2 buffers), all mbarriers.
@@ -32,40 +33,41 @@ using sgb_ec::COUT;
 using sgb_ec::KNN;
 using sgb_bn::lrelu;
 
-constexpr int TE = 128;                       // edges per tile (TMEM columns per accumulator)
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int TE = 160;                       // edges per tile = 8 points x 20 neighbours (TMEM columns per accumulator)
+constexpr int PTS = TE / KNN;                 // 8
+constexpr int EPI_WARPS = 4, PROD_WARPS = 10;
 constexpr int MMA_WARP = EPI_WARPS;           // warp 4
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 416
-constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int TILE_BYTES = TE * COUT * 4;     // one H tile (hi or lo): 32 KB
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 480
+constexpr int TILE_BYTES = TE * COUT * 4;     // one H tile (hi or lo): 40 KB
 constexpr int W2_BYTES = COUT * COUT * 4;     // 16 KB
-constexpr int TMEM_COLS = 256;                // 2 accumulators x 128 columns
+constexpr int TMEM_COLS = 512;                // 2 accumulators x 160 columns (power of two)
 
 struct Smem {
     // offsets into the dynamic shared memory block (128-byte aligned base)
     static constexpr int w2_hi = 0;
     static constexpr int w2_lo = w2_hi + W2_BYTES;
     static constexpr int h = w2_lo + W2_BYTES;                     // [stage][hi, lo]
-    static constexpr int w1t = h + 4 * TILE_BYTES;                 // [18][64] floats
-    static constexpr int bn1 = w1t + CIN * COUT * 4;               // [3][64]: mean, scale, beta
-    static constexpr int bars = bn1 + 3 * COUT * 4;                // 8 mbarriers
+    static constexpr int w1t = h + 4 * TILE_BYTES;                 // [18][64] floats: BN1 scale folded in
+    static constexpr int b1 = w1t + CIN * COUT * 4;                // [64]: beta1 - scale1 * mean1
+    static constexpr int bars = b1 + COUT * 4;                     // 8 mbarriers
     static constexpr int tmem_slot = bars + 8 * 8;
     static constexpr int total = tmem_slot + 16;
 };
 
+template <bool ARG>
 __global__ void __launch_bounds__(THREADS, 1)
 ec2_tc_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ W1,
               const float* __restrict__ stats1, const float* __restrict__ W2,
               float* __restrict__ zmax, float* __restrict__ zmin, unsigned short* __restrict__ kk, double* __restrict__ part /*[grid][128]*/) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    unsigned char* sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);     // keeps the shared address space (LDS/STS)
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + Smem::bars);       // [2] producers -> MMA
     uint64_t* bar_empty = bar_full + 2;                                      // [2] MMA (commit) -> producers
     uint64_t* bar_tfull = bar_full + 4;                                      // [2] MMA (commit) -> epilogue
     uint64_t* bar_tempty = bar_full + 6;                                     // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Smem::tmem_slot);
     float* s_w1t = reinterpret_cast<float*>(sm + Smem::w1t);
-    float* s_bn1 = reinterpret_cast<float*>(sm + Smem::bn1);
+    float* s_b1 = reinterpret_cast<float*>(sm + Smem::b1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // contiguous, balanced range of points for this CTA
@@ -84,10 +86,9 @@ ec2_tc_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, 
         *reinterpret_cast<float*>(sm + Smem::w2_hi + off) = hi;
         *reinterpret_cast<float*>(sm + Smem::w2_lo + off) = tf32_hi(w - hi);
     }
-    for (int i = tid; i < COUT * CIN; i += THREADS) s_w1t[(i % CIN) * COUT + i / CIN] = __ldg(W1 + i);
-    for (int i = tid; i < COUT; i += THREADS) {
-        s_bn1[i] = stats1[i]; s_bn1[COUT + i] = stats1[128 + i]; s_bn1[2 * COUT + i] = stats1[192 + i];
-    }
+    // first layer with the BatchNorm-1 affine folded in:  v1 = (scale1 W1) e + (beta1 - scale1 mean1)
+    for (int i = tid; i < COUT * CIN; i += THREADS) s_w1t[(i % CIN) * COUT + i / CIN] = __ldg(W1 + i) * stats1[128 + i / CIN];
+    for (int i = tid; i < COUT; i += THREADS) s_b1[i] = fmaf(-stats1[128 + i], stats1[i], stats1[192 + i]);
     if (tid == 0) {
         mbar_init(&bar_full[0], PROD_WARPS); mbar_init(&bar_full[1], PROD_WARPS);
         mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
@@ -103,24 +104,39 @@ ec2_tc_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, 
     const uint32_t tmem = *tmem_slot;
 
     if (warp > MMA_WARP) {
-        // ================= producers
-        const int pt = tid - (MMA_WARP + 1) * 32;       // 0..255
-        const int er = pt & (TE - 1);                   // edge row in the tile
-        const int hsel = pt >> 7;                       // which 32 hidden channels
+        // ================= producers: thread = (edge row, half of the hidden channels)
+        const int pt = tid - (MMA_WARP + 1) * 32;       // 0..319
+        const int er = pt % TE;                         // edge row in the tile
+        const int hsel = pt / TE;                       // which 32 hidden channels
+        // software pipeline over tiles: neighbour index two tiles ahead, gathered rows one tile ahead
+        float en[CIN];                                  // edge vector of the NEXT tile (in flight during this tile's math)
+        int j_next = 0;
+        bool v_next = false;
+        auto issue_index = [&](int t) -> int {
+            const long long g = g_begin + (long long)t * TE + er;
+            return (t < ntiles && g < g_end) ? __ldg(knn + g) : -1;
+        };
+        auto issue_rows = [&](int t, int j) {
+            const long long g = g_begin + (long long)t * TE + er;
+            v_next = j >= 0;
+            if (v_next) {
+                const float* xi = x9 + (size_t)(g / KNN) * 9;
+                const float* xj = x9 + (size_t)j * 9;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) { const float a = __ldg(xi + q); en[q] = __ldg(xj + q) - a; en[9 + q] = a; }
+            }
+        };
+        issue_rows(0, issue_index(0));
+        j_next = issue_index(1);
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            const long long g = g_begin + (long long)t * TE + er;
-            float e[CIN];
-            const bool valid = g < g_end;
-            if (valid) {
-                const int p = (int)(g / KNN);
-                const int j = __ldg(knn + g);
-                const float* xi = x9 + (size_t)p * 9;
-                const float* xj = x9 + (size_t)j * 9;
+            float2 ee[CIN];
+            const bool valid = v_next;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) { const float a = __ldg(xi + q); e[q] = __ldg(xj + q) - a; e[9 + q] = a; }
-            }
+            for (int q = 0; q < CIN; ++q) ee[q] = make_float2(en[q], en[q]);
+            issue_rows(t + 1, j_next);                  // loads land while this tile is computed
+            j_next = issue_index(t + 2);
             mbar_wait(&bar_empty[st], ph ^ 1u);
             unsigned char* dst_hi = sm + Smem::h + (st * 2) * TILE_BYTES;
             unsigned char* dst_lo = dst_hi + TILE_BYTES;
@@ -128,16 +144,15 @@ ec2_tc_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, 
             for (int c4 = hsel * 8; c4 < hsel * 8 + 8; ++c4) {
                 float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
+                    const float4 b = *reinterpret_cast<const float4*>(s_b1 + c4 * 4);
+                    float2 y01 = make_float2(b.x, b.y), y23 = make_float2(b.z, b.w);
 #pragma unroll
                     for (int q = 0; q < CIN; ++q) {
                         const float4 w = *reinterpret_cast<const float4*>(s_w1t + q * COUT + c4 * 4);
-                        y.x = fmaf(w.x, e[q], y.x); y.y = fmaf(w.y, e[q], y.y); y.z = fmaf(w.z, e[q], y.z); y.w = fmaf(w.w, e[q], y.w);
+                        ffma2(y01, make_float2(w.x, w.y), ee[q]);
+                        ffma2(y23, make_float2(w.z, w.w), ee[q]);
                     }
-                    const float4 mu = *reinterpret_cast<const float4*>(s_bn1 + c4 * 4);
-                    const float4 sc = *reinterpret_cast<const float4*>(s_bn1 + COUT + c4 * 4);
-                    const float4 be = *reinterpret_cast<const float4*>(s_bn1 + 2 * COUT + c4 * 4);
-                    y.x = lrelu(fmaf(y.x - mu.x, sc.x, be.x)); y.y = lrelu(fmaf(y.y - mu.y, sc.y, be.y));
-                    y.z = lrelu(fmaf(y.z - mu.z, sc.z, be.z)); y.w = lrelu(fmaf(y.w - mu.w, sc.w, be.w));
+                    y = make_float4(lrelu(y01.x), lrelu(y01.y), lrelu(y23.x), lrelu(y23.y));
                 }
                 const float4 hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
                 const float4 lo = make_float4(tf32_hi(y.x - hi.x), tf32_hi(y.y - hi.y), tf32_hi(y.z - hi.z), tf32_hi(y.w - hi.w));
@@ -161,7 +176,7 @@ ec2_tc_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, 
             fence_after_sync();
             if (lane == 0) {
                 const uint32_t b_hi = smem_u32(sm + Smem::h + (st * 2) * TILE_BYTES), b_lo = b_hi + TILE_BYTES;
-                const uint32_t d = tmem + (uint32_t)(st * TE);
+                const uint32_t d = tmem + (uint32_t)(st * 256);
 #pragma unroll
                 for (int i = 0; i < COUT / 8; ++i) {
                     const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
@@ -177,46 +192,43 @@ ec2_tc_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, 
             __syncwarp();
         }
     } else {
-        // ================= epilogue: warp q owns channels 16q + lane (lanes 0..15)
+        // ================= epilogue: warp q owns channels 16q + lane (lanes 0..15); one point = 20 consecutive columns
         const int c = warp * 16 + (lane & 15);
         const bool owner = lane < 16;
         double S1 = 0.0, S2 = 0.0;
-        float cmax = -INFINITY, cmin = INFINITY;
-        int kmax = 0, kmin = 0;
-        int k = 0;                                      // neighbour slot of the next column
-        long long p = p_begin;                          // point of the next column
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
             mbar_wait(&bar_tfull[st], ph);
             fence_after_sync();
             const long long g0 = g_begin + (long long)t * TE;
-            const int nvalid = (int)min((long long)TE, g_end - g0);
+            const int npts = (int)min((long long)PTS, (g_end - g0) / KNN);
+            const long long p0 = g0 / KNN;
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * 256);
             float s1 = 0.f, s2 = 0.f;
-            for (int c0 = 0; c0 < TE; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * TE + c0), v);
-                if (c0 < nvalid) {
+#pragma unroll 1
+            for (int pp = 0; pp < npts; ++pp) {
+                float v[16], u[4];
+                tmem_ld16(taddr + (uint32_t)(pp * KNN), v);
+                tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
+                float mx = v[0], mn = v[0];
+                int kx = 0, kn = 0;
+                s1 += v[0]; s2 = fmaf(v[0], v[0], s2);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (c0 + i < nvalid) {
-                            const float z = v[i];
-                            s1 += z; s2 = fmaf(z, z, s2);
-                            if (k == 0) { cmax = z; cmin = z; kmax = 0; kmin = 0; }
-                            else {
-                                if (z > cmax) { cmax = z; kmax = k; }
-                                if (z < cmin) { cmin = z; kmin = k; }
-                            }
-                            if (++k == KNN) {
-                                if (owner) {
-                                    zmax[(size_t)p * COUT + c] = cmax;
-                                    zmin[(size_t)p * COUT + c] = cmin;
-                                    kk[(size_t)p * COUT + c] = (unsigned short)(kmax | (kmin << 8));
-                                }
-                                k = 0; ++p;
-                            }
-                        }
+                for (int i = 1; i < KNN; ++i) {
+                    const float z = i < 16 ? v[i] : u[i - 16];
+                    s1 += z; s2 = fmaf(z, z, s2);
+                    if (ARG) {
+                        if (z > mx) { mx = z; kx = i; }
+                        if (z < mn) { mn = z; kn = i; }
+                    } else {
+                        mx = fmaxf(mx, z); mn = fminf(mn, z);
                     }
+                }
+                if (owner) {
+                    const size_t o = (size_t)(p0 + pp) * COUT + c;
+                    zmax[o] = mx; zmin[o] = mn;
+                    if (ARG) kk[o] = (unsigned short)(kx | (kn << 8));
                 }
             }
             S1 += (double)s1; S2 += (double)s2;
@@ -259,7 +271,7 @@ ec2_apply_kernel(const float* __restrict__ zmax, const float* __restrict__ zmin,
     const int c = (int)(i4 & 63);
     const float4 a = *reinterpret_cast<const float4*>(zmax + i4);
     const float4 b = *reinterpret_cast<const float4*>(zmin + i4);
-    const ushort4 kq = *reinterpret_cast<const ushort4*>(kk + i4);
+    const ushort4 kq = argk ? *reinterpret_cast<const ushort4*>(kk + i4) : make_ushort4(0, 0, 0, 0);
     const float za[4] = {a.x, a.y, a.z, a.w}, zb[4] = {b.x, b.y, b.z, b.w};
     const unsigned short kv[4] = {kq.x, kq.y, kq.z, kq.w};
     float o[4];
@@ -300,8 +312,13 @@ int sgb_ec2_tc_forward(const float* x9, const int* knn, int N, const float* W1, 
     unsigned short* kk = (unsigned short*)(zmin + (size_t)N * 64);
     const int grid = tc_grid(N);
     const size_t smem = Smem::total + 128;
-    SGB_CUDA(cudaFuncSetAttribute(ec2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { ec2_tc_kernel<<<grid, THREADS, smem, st>>>(x9, knn, N, W1, stats1, W2, zmax, zmin, kk, part); SGB_COUNT_LAUNCH(); }
+    if (argk) {
+        SGB_CUDA(cudaFuncSetAttribute(ec2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { ec2_tc_kernel<true><<<grid, THREADS, smem, st>>>(x9, knn, N, W1, stats1, W2, zmax, zmin, kk, part); SGB_COUNT_LAUNCH(); }
+    } else {
+        SGB_CUDA(cudaFuncSetAttribute(ec2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { ec2_tc_kernel<false><<<grid, THREADS, smem, st>>>(x9, knn, N, W1, stats1, W2, zmax, zmin, kk, part); SGB_COUNT_LAUNCH(); }
+    }
     sgb_bn::reduce_partials(part, grid, 128, sums, st);
     { bn2_from_sums_kernel<<<1, 64, 0, st>>>(sums, (double)N * KNN, gamma2, beta2, stats2, var2); SGB_COUNT_LAUNCH(); }
     const long long total = (long long)N * 64;

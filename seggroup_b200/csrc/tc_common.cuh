@@ -109,4 +109,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// packed fp32x2 fused multiply-add (Blackwell FFMA2): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}, each lane IEEE fma.rn
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+    unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    acc = *reinterpret_cast<float2*>(&d);
+}
+
 }  // namespace sgb_tc
