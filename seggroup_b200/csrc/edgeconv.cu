@@ -371,11 +371,11 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     sgb_bn::reduce_partials(g1part, grid, NE1, m1red, st);
     { bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(m1red, 1, M, W1, ctr, gamma1, beta1, stats1, var1, nullptr); SGB_COUNT_LAUNCH(); }
     if (ctr_out) SGB_CUDA(cudaMemcpyAsync(ctr_out, ctr, 18 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (two_layer && !mom2) {
-        // no backward follows (nobody keeps the hidden-layer moments): second layer on the tcgen05 tensor cores
+    if (two_layer) {
+        // second layer on the tcgen05 tensor cores (mom2 != NULL: also the hidden-layer second moments for the backward)
         size_t off = 128 + 256 * 9 * 8 + 192 * 8 + (size_t)grid * NE1 * 8 + (size_t)(148 * 2) * NE2 * 8;
         off = (off + 255) & ~(size_t)255;
-        return sgb_ec2_tc_forward(x9, knn, N, W1, stats1, W2, gamma2, beta2, out, argk, stats2, var2, w8 + off, st);
+        return sgb_ec2_tc_forward(x9, knn, N, W1, stats1, W2, gamma2, beta2, out, argk, stats2, var2, mom2, w8 + off, st);
     }
     if (two_layer) {
         const int g2 = grid < 148 * 2 ? grid : 148 * 2;

@@ -36,6 +36,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     return d;                                   // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
 
+// swizzled K-major variant: layout_type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (the swizzle is a function of the
+// absolute shared-memory address, so tile bases must be aligned to the swizzle repeat: 1024 / 512 / 256 bytes)
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return make_desc(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)layout_type << 61);
+}
+
 // ---- instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
     return (1u << 4)                            // c_format = F32

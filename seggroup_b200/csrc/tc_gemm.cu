@@ -112,10 +112,10 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
 __global__ void __launch_bounds__(TG_THREADS)
 probe_kernel(const float* __restrict__ imgA, int wordsA, const float* __restrict__ imgB, int wordsB,
              unsigned long long descA, unsigned long long descB, unsigned idesc, int N, float* __restrict__ D) {
-    extern __shared__ __align__(1024) unsigned char tg_smem[];
+    extern __shared__ __align__(128) unsigned char tg_smem[];
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tmem;
-    float* sA = reinterpret_cast<float*>(tg_smem);
+    float* sA = reinterpret_cast<float*>(tg_smem + ((1024u - (smem_u32(tg_smem) & 1023u)) & 1023u));   // swizzles are address based
     float* sB = sA + wordsA;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) tmem_alloc(&s_tmem, 256);
@@ -165,7 +165,7 @@ extern "C" int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, 
 extern "C" int sgb_tc_probe(const float* imgA, int wordsA, const float* imgB, int wordsB, unsigned long long descA,
                             unsigned long long descB, unsigned idesc, int N, float* D, void* stream) {
     if (!imgA || !imgB || !D || wordsA <= 0 || wordsB <= 0 || N <= 0 || N > 256 || (N & 15) || (wordsA & 255) || (wordsB & 255)) return SGB_ERR_INVALID;
-    const size_t smem = (size_t)(wordsA + wordsB) * 4;
+    const size_t smem = (size_t)(wordsA + wordsB) * 4 + 1024;
     if (smem > 200 * 1024) return SGB_ERR_UNSUPPORTED;
     SGB_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     probe_kernel<<<1, TG_THREADS, smem, (cudaStream_t)stream>>>(imgA, wordsA, imgB, wordsB, descA, descB, idesc, N, D); SGB_COUNT_LAUNCH();

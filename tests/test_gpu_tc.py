@@ -45,13 +45,23 @@ def test_edgeconv_tensor_core_path(n_points, neg_gamma):
     c = lambda k: p[k].detach().cuda()
     args = (x9.cuda(), knn.to(torch.int32).cuda(), c("mlp_3.conv1.0.weight"), c("mlp_3.bn1.weight"), c("mlp_3.bn1.bias"),
             c("mlp_3.conv2.0.weight"), c("mlp_3.bn2.weight"), c("mlp_3.bn2.bias"))
-    simt = ops.edgeconv_fwd(*args, want_backward=True)
+    train = ops.edgeconv_fwd(*args, want_backward=True)        # GRAM variant: also the hidden-layer second moments
     tc = ops.edgeconv_fwd(*args, want_argk=True, want_backward=False)
     torch.cuda.synchronize()
-    assert _rel(tc["out"], ref) < 1e-4, _rel(tc["out"], ref)
-    assert _rel(tc["out"], simt["out"]) < 2e-5, _rel(tc["out"], simt["out"])
-    assert _rel(tc["stats2"], simt["stats2"]) < 2e-5
-    assert _rel(tc["var2"], simt["var2"]) < 2e-5
-    # arg-max edges: identical except where two edges are within rounding of each other
-    same = (tc["argk"] == simt["argk"]).float().mean().item()
+    for o in (tc, train):
+        assert _rel(o["out"], ref) < 1e-4, _rel(o["out"], ref)
+    assert _rel(tc["out"], train["out"]) < 1e-5
+    assert _rel(tc["stats2"], train["stats2"]) < 1e-5
+    assert _rel(tc["var2"], train["var2"]) < 1e-5
+    same = (tc["argk"] == train["argk"]).float().mean().item()
     assert same > 0.999, same
+    # hidden-layer moments against an fp64 evaluation of model.py:131-133 (conv1 -> BN(train) -> LeakyReLU)
+    xi = x9.double().unsqueeze(1).expand(-1, 20, -1)
+    e = torch.cat([x9.double()[knn] - xi, xi], -1).reshape(-1, 18)
+    y = e @ p["mlp_3.conv1.0.weight"].detach().double().reshape(64, 18).t()
+    y = (y - y.mean(0)) / torch.sqrt(y.var(0, unbiased=False) + 1e-5) * p["mlp_3.bn1.weight"].double() + p["mlp_3.bn1.bias"].double()
+    h = torch.nn.functional.leaky_relu(y, 0.2)
+    m2 = train["mom2"].cpu()
+    G = m2[:4096].view(64, 64)
+    assert _rel(0.5 * (G + G.t()), h.t() @ h) < 2e-5, _rel(0.5 * (G + G.t()), h.t() @ h)
+    assert _rel(m2[4096:], h.sum(0)) < 2e-5
