@@ -81,10 +81,13 @@ int sgb_segment_pool_max_bwd(const float* grad_out, const int* argmax, int S, in
  * evaluated exactly as torch-CPU does in fp32 (<.,.> = fma(z,z,fma(y,y,x*x)), |x|^2 = (x*x+y*y)+z*z),
  * ranked (score desc, member position asc).  For n <= k: the first n columns are all members in
  * member order, the remaining columns are 0 (the reference leaves them pointing at global point 0).
- * xyz rows have `stride` floats.  knn is [N,k] int32, every row is written.
+ * xyz rows have `stride` floats.  knn is [N,k] int32, every row is written.  Exact (identical to a brute force over the
+ * cluster): clusters are sorted along their longest axis and every query sweeps outwards until the axis gap alone
+ * rules out a better score (csrc/cluster_knn.cu).
  * ------------------------------------------------------------------------------------------- */
+size_t sgb_cluster_knn_ws_bytes(int N, int S);
 int sgb_cluster_knn(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
-                    int k, int* knn, void* stream);
+                    int k, int* knn, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a4  per-cluster fixed-size clouds

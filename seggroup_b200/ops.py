@@ -73,7 +73,9 @@ def cluster_knn(xyz, order, cl_off, k=20):
         raise ValueError("xyz must be a CUDA float32 tensor with unit inner stride")
     N = order.numel()
     knn = torch.empty(N, k, dtype=I32, device=xyz.device)
-    _lib.call("sgb_cluster_knn", xyz, xyz.stride(0), N, order, cl_off, cl_off.numel() - 1, k, knn, _stream())
+    S = cl_off.numel() - 1
+    ws = _ws(_lib.call("sgb_cluster_knn_ws_bytes", N, S), xyz.device)
+    _lib.call("sgb_cluster_knn", xyz, xyz.stride(0), N, order, cl_off, S, k, knn, ws, ws.numel(), _stream())
     return knn
 
 

@@ -28,7 +28,7 @@ def test_workspace_queries_and_argument_validation():
     with pytest.raises(_lib.SgbError):            # null pointers are rejected before any launch
         _lib.call("sgb_segment_pool_max_fwd", None, 10, 64, None, 10, None, 2, None, None, None, 0, None)
     with pytest.raises(_lib.SgbError):
-        _lib.call("sgb_cluster_knn", None, 3, 10, None, None, 1, 20, None, None)
+        _lib.call("sgb_cluster_knn", None, 3, 10, None, None, 1, 20, None, None, 0, None)
 
 
 def test_ops_refuse_cpu_tensors():

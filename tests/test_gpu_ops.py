@@ -107,6 +107,36 @@ def test_cluster_knn(scene20k):
         assert bad.sum() == 0, "kNN rows differ: %d of %d (first %s)" % (bad.sum(), len(bad), np.nonzero(bad)[0][:5])
 
 
+@pytest.mark.parametrize("case", ["plane_far", "wall", "duplicates", "line"])
+def test_cluster_knn_exact_on_hard_geometry(case):
+    """The sorted sweep must return exactly the brute-force ranking of the reference's fp32 score, also where that
+    score is dominated by cancellation noise (far from the origin), where the sweep axis is degenerate and with ties."""
+    from oracle import seggroup_oracle as O
+    from seggroup_b200 import ops
+    rng = np.random.default_rng(len(case))
+    n_big = 6000
+    if case == "plane_far":
+        big = np.stack([rng.uniform(8, 16, n_big), rng.uniform(-14, -9, n_big), 2.5 + 0.002 * rng.standard_normal(n_big)], 1)
+    elif case == "wall":
+        big = np.stack([np.full(n_big, 3.25), rng.uniform(0, 6, n_big), rng.uniform(0, 2.5, n_big)], 1)
+    elif case == "duplicates":
+        base = np.stack([rng.uniform(0, 4, n_big // 4), rng.uniform(0, 4, n_big // 4), np.zeros(n_big // 4)], 1)
+        big = np.tile(base, (4, 1))[rng.permutation(n_big)]
+    else:
+        big = np.stack([rng.uniform(0, 10, n_big), np.full(n_big, 1.0), np.full(n_big, 1.0)], 1)
+    small = rng.uniform(0, 1, (300, 3))
+    xyz = np.concatenate([big, small]).astype(np.float32)
+    N = len(xyz)
+    perm = rng.permutation(N)
+    members = [perm[np.isin(perm, np.arange(n_big))], perm[~np.isin(perm, np.arange(n_big))]]   # member order = random
+    order = np.concatenate(members).astype(np.int32)
+    off = np.array([0, len(members[0]), N], np.int32)
+    knn = ops.cluster_knn(dev(xyz), dev(order), dev(off), 20).cpu().numpy()
+    ref = O.cluster_knn(torch.from_numpy(xyz), members, 20, tie="canonical").numpy()
+    bad = (knn != ref).any(1)
+    assert bad.sum() == 0, "kNN rows differ: %d of %d (first %s)" % (bad.sum(), len(bad), np.nonzero(bad)[0][:5])
+
+
 def test_cluster_knn_small_clusters():
     """clusters with n <= k: first n columns = members, rest 0 (model.py:513-518)"""
     from seggroup_b200 import ops
