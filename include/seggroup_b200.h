@@ -202,6 +202,22 @@ int sgb_update_adj(const int* edges, int E, const int* map, int S_new, int* adj_
 size_t sgb_sym_csr_ws_bytes(int S);
 int sgb_sym_csr(const int* adj, int A, int S, int* row_off, int* nbr, int* eid, void* ws, size_t ws_bytes, void* stream);
 
+/* One whole clustering level in one call (csrc/level_step.cu): [group_nearby (mode 0) | group_unlabeled_step (mode 1) | no
+ * grouping (mode 2)] -> level_build -> level_children -> update_adj -> sym_csr, i.e. seggroup/model.py:752-770 / 802-815 /
+ * 843-856 / 441-470 between "distances are known" and "features can be pooled".  Synchronises the stream twice (cluster
+ * count, edge count).  edges [E,2] / map: the edge list re-mapped into adj_new (map == NULL: old2new of this step);
+ * roots_old == NULL on the first level (no children CSR).  counts_host [4] (HOST memory) <- S_new, A_new, number of
+ * unlabeled clusters, status word.  Cluster-sized outputs are sized for S1, adj_new for E rows, csr_nbr / csr_eid for 2 E. */
+size_t sgb_level_step_ws_bytes(int S1, int S_old);
+int sgb_level_step(int mode, const int* adj_old, int A_old, const int* roots_old, int S_old, const float* dist, float th,
+                   int sweep_cap, const int* csr_off_old, const int* csr_nbr_old, const int* csr_eid_old,
+                   const int* edges, int E, const int* map,
+                   int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
+                   int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
+                   int* cl_ins, int* cl_sem, int* cl_rootpt, int* old2new, int* child_off, int* child_list,
+                   int* adj_new, int* csr_off, int* csr_nbr, int* csr_eid,
+                   int* status, int* counts_dev, int* counts_host, void* ws, size_t ws_bytes, void* stream);
+
 /* a11  replaces seggroup/model.py:269-274 `calculate_distance` (F.pairwise_distance: ||a - b + 1e-6||_2). */
 int sgb_edge_dist_fwd(const float* feat, int C, const int* adj, int A, float* dist, void* stream);
 int sgb_edge_dist_bwd(const float* feat, int S, int C, const int* adj, int A, const float* dist, const float* gdist,

@@ -130,18 +130,37 @@ def call(name: str, *args):
     return _call(name, *args)
 
 
+_bound = {}        # name -> (function pointer, pointer-argument mask, argument count, checks the status?)
+
+
+def _bind(name):
+    lib = load()
+    restype, argl = _protos[name]
+    fn = getattr(lib, name)
+    b = (fn, tuple(t is ctypes.c_void_p for t, _ in argl), len(argl),
+         restype is ctypes.c_int and name not in ("sgb_version", "sgb_last_cuda_error"))
+    _bound[name] = b
+    return b
+
+
 def _call(name: str, *args):
     """Call `name`; tensors / None / ints are passed as pointers where the prototype has a pointer.
     Raises SgbError on a negative status.  Returns the int / size_t result."""
-    lib = load()
-    restype, argl = _protos[name]
-    if len(args) != len(argl):
-        raise TypeError("%s expects %d arguments (%s), got %d" % (name, len(argl), ", ".join(n for _, n in argl), len(args)))
-    conv = []
-    for (t, _), a in zip(argl, args):
-        conv.append(_ptr(a) if t is ctypes.c_void_p else a)
-    rc = getattr(lib, name)(*conv)
-    if restype is ctypes.c_int and name not in ("sgb_version", "sgb_last_cuda_error") and rc < 0:
+    b = _bound.get(name)
+    if b is None:
+        b = _bind(name)
+    fn, is_ptr, n, checked = b
+    if len(args) != n:
+        raise TypeError("%s expects %d arguments (%s), got %d" % (name, n, ", ".join(nm for _, nm in _protos[name][1]), len(args)))
+    conv = [None] * n
+    for i in range(n):
+        a = args[i]
+        if is_ptr[i] and a is not None and a.__class__ is not int:
+            a = a.data_ptr() if hasattr(a, "data_ptr") else _ptr(a)       # torch tensor -> raw device address (a plain int)
+        conv[i] = a
+    rc = fn(*conv)
+    if checked and rc < 0:
+        lib = load()
         msg = lib.sgb_status_string(rc).decode()
         if rc == -3:
             msg += ": " + lib.sgb_last_cuda_error_string().decode()

@@ -15,7 +15,8 @@ F32 = torch.float32
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of the calling thread's current stream (torch.cuda.current_stream() costs ~15 us per call)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def _chk(t, dtype, name):
@@ -79,15 +80,16 @@ def cluster_knn(xyz, order, cl_off, k=20):
     return knn
 
 
-def cluster_cloud_indices(xyz, order, cl_off, P):
-    """-> (cloud_idx [S,P] i32 point ids, status [1] i32)."""
+def cluster_cloud_indices(xyz, order, cl_off, P, status=None):
+    """-> (cloud_idx [S,P] i32 point ids, status [1] i32; pass `status` to OR the flag into an existing status word)."""
     _chk(order, I32, "order"); _chk(cl_off, I32, "cl_off")
     if not xyz.is_cuda or xyz.dtype != F32 or xyz.stride(1) != 1:
         raise ValueError("xyz must be a CUDA float32 tensor with unit inner stride")
     S = cl_off.numel() - 1
     N = order.numel()
     idx = torch.empty(S, P, dtype=I32, device=xyz.device)
-    status = torch.zeros(1, dtype=I32, device=xyz.device)
+    if status is None:
+        status = torch.zeros(1, dtype=I32, device=xyz.device)
     ws = _ws(_lib.call("sgb_cluster_cloud_ws_bytes", N), xyz.device)
     _lib.call("sgb_cluster_cloud_indices", xyz, xyz.stride(0), N, order, cl_off, S, P, idx, status, ws, ws.numel(), _stream())
     return idx, status
@@ -199,9 +201,53 @@ def scene_init(seg_off, seg_members, weak_label):
 
 
 class Level:
-    """Device arrays of one clustering level (all sized for S1; `S` is read back once, after build)."""
+    """Device arrays of one clustering level (all sized for S1; `S` is read back once, after build).  Levels made by
+    `level_step` also carry their adjacency (`adj` [A,2], `csr`), the map from the previous level (`o2n`, `ch_off`,
+    `ch_list`), the number of unlabeled clusters and the status word read back with the counts."""
     __slots__ = ("S", "roots", "seg2cl", "cl_seg_off", "cl_seg_list", "cl_pt_off", "order", "cl_ins", "cl_sem", "cl_rootpt",
-                 "counts")
+                 "counts", "adj", "csr", "o2n", "ch_off", "ch_list", "n_unlabeled", "status")
+
+
+def level_step(mode, uf, seg_off, seg_members, seg_of_pos, status, old=None, dist=None, th=0.0, edges=None, mapping=None,
+               sweep_cap=64):
+    """One clustering level in one library call (sgb_level_step): mode 0 group_nearby(old.adj, dist, th), 1 one phase-A
+    iteration of group_unlabeled (dist, old.csr), 2 no grouping.  edges/mapping: edge list to re-map (default: old.adj
+    through the old->new cluster map of this step).  Returns the new Level with .adj, .csr, .o2n, .ch_off, .ch_list."""
+    import numpy as np
+    S1 = uf.shape[1]
+    N = seg_members.numel()
+    dev = uf.device
+    S_old = old.S if old is not None else 0
+    if edges is None:
+        edges = old.adj
+    E = edges.shape[0]
+    sizes = [S1, S1, S1 + 1, S1, S1 + 1, N, S1, S1, S1, max(S_old, 1), S1 + 1, max(S_old, 1), 2 * max(E, 1), S1 + 1,
+             2 * max(E, 1), 2 * max(E, 1), 4]
+    buf = torch.empty(sum(sizes), dtype=I32, device=dev)
+    parts, o = [], 0
+    for n in sizes:
+        parts.append(buf[o:o + n]); o += n
+    (roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order, cl_ins, cl_sem, cl_rootpt, o2n, ch_off, ch_list, adj_new, csr_off,
+     csr_nbr, csr_eid, counts) = parts
+    host = np.zeros(4, np.int32)
+    ws = _ws(_lib.call("sgb_level_step_ws_bytes", S1, S_old), dev)
+    oc = old.csr if (old is not None and mode == 1) else (None, None, None)
+    _lib.call("sgb_level_step", int(mode), old.adj if old is not None else None, old.adj.shape[0] if old is not None else 0,
+              old.roots if old is not None else None, S_old, dist, float(th), int(sweep_cap), oc[0], oc[1], oc[2],
+              edges, E, mapping, uf, S1, N, seg_off, seg_members, seg_of_pos,
+              roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order, cl_ins, cl_sem, cl_rootpt, o2n, ch_off, ch_list,
+              adj_new, csr_off, csr_nbr, csr_eid, status, counts, host, ws, ws.numel(), _stream())
+    S, A = int(host[0]), int(host[1])
+    L = Level()
+    L.S, L.counts = S, counts
+    L.roots, L.cl_seg_off, L.cl_pt_off = roots[:S], cl_seg_off[:S + 1], cl_pt_off[:S + 1]
+    L.seg2cl, L.cl_seg_list, L.order = seg2cl, cl_seg_list, order
+    L.cl_ins, L.cl_sem, L.cl_rootpt = cl_ins[:S], cl_sem[:S], cl_rootpt[:S]
+    L.adj = adj_new[:2 * A].view(A, 2)
+    L.csr = (csr_off[:S + 1], csr_nbr[:max(2 * A, 1)], csr_eid[:max(2 * A, 1)])
+    L.o2n, L.ch_off, L.ch_list = (o2n[:S_old], ch_off[:S + 1], ch_list[:S_old]) if old is not None else (None, None, None)
+    L.n_unlabeled, L.status = int(host[2]), int(host[3])
+    return L
 
 
 def level_build(uf, seg_off, seg_members, seg_of_pos):

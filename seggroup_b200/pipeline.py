@@ -224,22 +224,21 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
 
     # ---- graph initialisation (model.py:712-738)
     sop, sos, uf = ops.scene_init(sc.seg_off, sc.seg_members, sc.weak_label)
-    L1 = ops.level_build(uf, sc.seg_off, sc.seg_members, sos)
-    adj_1 = ops.update_adj(sc.adj0, sop, L1.S)
+    step = lambda mode, **kw: ops.level_step(mode, uf, sc.seg_off, sc.seg_members, sos, status, **kw)
+    L1 = step(2, edges=sc.adj0, mapping=sop)
+    adj_1 = L1.adj
     put_labels("layer_1", L1)
     res.levels.append(L1)
 
     # ---- structural grouping layer (model.py:747-783)
-    cloud_idx, st2 = ops.cluster_cloud_indices(sc.data, L1.order, L1.cl_pt_off, 64)
+    cloud_idx, _ = ops.cluster_cloud_indices(sc.data, L1.order, L1.cl_pt_off, 64, status=status)
     clouds = ops.cluster_cloud_transform(sc.data, cloud_idx)
     Feat_1, knn_1, stats, var = Mlp1Fn.apply(clouds, p["mlp_1.conv1.0.weight"], p["mlp_1.bn1.weight"], p["mlp_1.bn1.bias"])
     res.bn_stats["mlp_1.bn1"] = (stats[0], var, L1.S * 640)
     d1 = ops.edge_dist(Feat_1.detach(), adj_1)
-    ops.group_nearby(adj_1, L1.roots, d1, 3.0 if sem_infer else 6.0, uf, status)
-    L2 = ops.level_build(uf, sc.seg_off, sc.seg_members, sos)
-    o2n, ch_off, ch_list = ops.level_children(L1, L2)
-    adj_2 = ops.update_adj(adj_1, o2n, L2.S)
-    Feat_2, _ = SegmentMaxFn.apply(Feat_1, ch_off, ch_list)
+    L2 = step(0, old=L1, dist=d1, th=3.0 if sem_infer else 6.0)
+    adj_2 = L2.adj
+    Feat_2, _ = SegmentMaxFn.apply(Feat_1, L2.ch_off, L2.ch_list)
     put_labels("layer_2", L2)
     res.levels.append(L2)
     if keep_aux:
@@ -247,11 +246,12 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     if sem_infer:
         if sc.real_label is not None and export:
             res.metrics = evaluate(sc.real_label, res.labels["layer_2.sem"], res.labels["layer_2.ins"])
-        res.status = int(status.item()) | int(st2.item())
+        res.status = L2.status
         return res
 
     # ---- semantic grouping layers (model.py:788-865)
-    def semantic_layer(Lc, Feat_c, adj_c, pre, gcn_key, tag, two):
+    def semantic_layer(Lc, Feat_c, pre, gcn_key, tag, two):
+        adj_c = Lc.adj
         knn = ops.cluster_knn(sc.data, Lc.order, Lc.cl_pt_off, 20)
         x9 = ops.centralize(sc.data, Lc.order, Lc.cl_pt_off)
         W2 = p[pre + ".conv2.0.weight"] if two else None
@@ -261,7 +261,7 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
         if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (W1, g1, b1, W2, g2, b2)):
             fm, feat_pts, stats, var = EdgeConvPoolFn.apply(x9, knn, Lc.cl_pt_off, Lc.order, W1, g1, b1, W2, g2, b2)
         else:
-            # inference: nothing is kept for a backward pass (MLP3's second layer then runs on the tensor cores)
+            # inference: nothing is kept for a backward pass
             o = ops.edgeconv_fwd(x9, knn, W1.contiguous(), g1.contiguous(), b1.contiguous(),
                                  W2.contiguous() if two else None, g2.contiguous() if two else None, b2.contiguous() if two else None,
                                  want_argk=False, want_backward=False)
@@ -273,46 +273,38 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
         if two:
             res.bn_stats[pre + ".bn2"] = (stats[1, 0], var[1], sc.n_points * 20)
         Fc = torch.cat([Feat_c, fm], dim=-1)
-        csr = ops.sym_csr(adj_c, Lc.S)
-        Fg = _gcn(p, gcn_key, Fc, adj_c, csr)
+        Fg = _gcn(p, gcn_key, Fc, adj_c, Lc.csr)
         dd = ops.edge_dist(Fg.detach().contiguous(), adj_c)
-        ops.group_nearby(adj_c, Lc.roots, dd, 2.0, uf, status)
-        Ln = ops.level_build(uf, sc.seg_off, sc.seg_members, sos)
-        o2n, ch_off, ch_list = ops.level_children(Lc, Ln)
-        adj_n = ops.update_adj(adj_c, o2n, Ln.S)
-        Fn, _ = SegmentMaxFn.apply(Fg, ch_off, ch_list)
+        Ln = step(0, old=Lc, dist=dd, th=2.0)
+        Fn, _ = SegmentMaxFn.apply(Fg, Ln.ch_off, Ln.ch_list)
         if keep_aux:
             res.aux.update({"knn_" + tag: knn, "Feat_mlp_" + tag: feat_pts, "Feat_gcn_" + tag: Fg.detach(), "dists_" + tag: dd,
                             "x9_" + tag: x9})
-        return Ln, Fn, adj_n
+        return Ln, Fn
 
-    L3, Feat_3, adj_3 = semantic_layer(L2, Feat_2, adj_2, "mlp_2", "gcn_2.fc.weight", "2", False)
+    L3, Feat_3 = semantic_layer(L2, Feat_2, "mlp_2", "gcn_2.fc.weight", "2", False)
     put_labels("layer_3", L3)
-    L4, Feat_4, adj_4 = semantic_layer(L3, Feat_3, adj_3, "mlp_3", "gcn_3.fc.weight", "3", True)
+    L4, Feat_4 = semantic_layer(L3, Feat_3, "mlp_3", "gcn_3.fc.weight", "3", True)
     put_labels("layer_4", L4)
     res.levels += [L3, L4]
     if keep_aux:
-        res.aux.update(adj_3=adj_3, adj_4=adj_4)
+        res.aux.update(adj_3=L3.adj, adj_4=L4.adj)
 
     # ---- final clustering, phase A (model.py:439-470)
-    Lo, Feat, adj = L4, Feat_4, adj_4
+    Lo, Feat = L4, Feat_4
     count_old = Lo.S
     while True:
-        csr = ops.sym_csr(adj, Lo.S)
-        dd = ops.edge_dist(Feat.detach().contiguous(), adj)
-        ops.group_unlabeled_step(dd, csr, Lo.S, Lo.roots, uf)
-        Ln = ops.level_build(uf, sc.seg_off, sc.seg_members, sos)
-        o2n, ch_off, ch_list = ops.level_children(Lo, Ln)
-        adj = ops.update_adj(adj, o2n, Ln.S)
-        Feat, _ = SegmentMaxFn.apply(Feat, ch_off, ch_list)
+        dd = ops.edge_dist(Feat.detach().contiguous(), Lo.adj)
+        Ln = step(1, old=Lo, dist=dd)
+        Feat, _ = SegmentMaxFn.apply(Feat, Ln.ch_off, Ln.ch_list)
         Lo = Ln
         if Lo.S == count_old:
             break
         count_old = Lo.S
     res.aux["phaseA_clusters"] = Lo.S
     # phase B (model.py:472-509) only runs when an unlabeled cluster survives phase A
-    if bool((Lo.cl_ins == -1).any().item()):
-        Lo, Feat, adj = _phase_b(sc, uf, sos, Lo, Feat, adj)
+    if Lo.n_unlabeled > 0:
+        Lo, Feat = _phase_b(sc, uf, sos, status, Lo, Feat)
     L5, Feat_5 = Lo, Feat
     res.levels.append(L5)
     put_labels("final", L5, seg=False)
@@ -320,7 +312,7 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
         res.aux["Feat_5"] = Feat_5.detach()
     if sc.real_label is not None and export:
         res.metrics = evaluate(sc.real_label, res.labels["final.sem"], res.labels["final.ins"])
-    res.status = int(status.item()) | int(st2.item())
+    res.status = L5.status
     if mode == "ins_infer":
         return res
 
@@ -353,7 +345,7 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     return res
 
 
-def _phase_b(sc, uf, sos, Lo, Feat, adj):
+def _phase_b(sc, uf, sos, status, Lo, Feat):
     """model.py:472-509 — nearest labelled cluster by sampled-cloud distance for clusters phase A left unlabeled."""
     P = 1024
     cloud_idx, _ = ops.cluster_cloud_indices(sc.data, Lo.order, Lo.cl_pt_off, P)
@@ -389,8 +381,6 @@ def _phase_b(sc, uf, sos, Lo, Feat, adj):
             nxt[tail[c2]] = c1; tail[c2] = tail[c1]
             merged = True
     uf.copy_(torch.as_tensor(ufh))
-    Ln = ops.level_build(uf, sc.seg_off, sc.seg_members, sos)
-    o2n, ch_off, ch_list = ops.level_children(Lo, Ln)
-    adj = ops.update_adj(adj, o2n, Ln.S)
-    Feat, _ = SegmentMaxFn.apply(Feat, ch_off, ch_list)
-    return Ln, Feat, adj
+    Ln = ops.level_step(2, uf, sc.seg_off, sc.seg_members, sos, status, old=Lo)
+    Feat, _ = SegmentMaxFn.apply(Feat, Ln.ch_off, Ln.ch_list)
+    return Ln, Feat
