@@ -13,7 +13,9 @@ One JSON line is printed by rank 0:
   value        whole-job points/sec, scene inputs already resident in HBM, CUDA-event timed, max over ranks
   e2e          same metric through the host-facing call: every step copies the scenes' inputs from pinned host
                memory and reads the loss back
-  roofline     dominant kernel (EdgeConv forward of MLP3): algorithmic HBM bytes / measured launch time
+  roofline     dominant entry point (EdgeConv forward of MLP3, tcgen05): useful flops / CUDA-event time vs the measured tensor peak;
+               roofline_more: the HBM-bound gather/scatter kernel (segment pooling) vs the measured copy bandwidth
+  inference    pseudo-label generation (ins_infer) points/sec over the same batch
   cpu_baseline the oracle port of the reference CPU path, timed on a bounded sample on this box's host cores
 `--impl reference` times that CPU port alone, as the reference arm.
 """
@@ -170,16 +172,8 @@ def main():
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                                 # > 126 MB L2
 
     def allreduce_grads():
-        if dist is None:
-            return
-        flat = torch.cat([p[k].grad.reshape(-1) for k in train_keys])
-        dist.all_reduce(flat)
-        flat /= world
-        o = 0
-        for k in train_keys:
-            n = p[k].numel()
-            p[k].grad.copy_(flat[o:o + n].view_as(p[k]))
-            o += n
+        if dist is not None:
+            engine.allreduce_flat([p[k].grad for k in train_keys], dist, average=True)
 
     ex = engine.SceneExecutor(dev, n_streams=args.streams)
 
@@ -218,7 +212,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    _lib.time_entry = "sgb_edgeconv_fwd"
+    _lib.time_entry = {"sgb_edgeconv_fwd", "sgb_segment_pool_max_fwd"}
     _lib.timed_events = []
     ms, _ = timed(resident, False, args.steps)
     launches = _lib.launch_count() - launches0
@@ -232,17 +226,46 @@ def main():
     ms_e2e, _ = timed(pinned, True, args.steps)
     e2e = pts_per_step * args.steps / (ms_e2e * 1e-3)
 
+    # ---- pseudo-label inference (ins_infer) over the same resident batch: reported beside the training number
+    with torch.no_grad():
+        ex.infer_batch(resident, p)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            flush_buf.fill_(0)
+            ex.infer_batch(resident, p)
+        e1.record()
+        torch.cuda.synchronize()
+    ms_inf = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms_inf, op=dist.ReduceOp.MAX)
+    ms_inf = float(ms_inf.item())
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        # dominant kernel: EdgeConv forward of MLP3 (two_layer launches are every second call).  Algorithmic bytes
-        # (SURVEY.md 8d): 36 (x9) + 4*20 (knn) + 256 (out) + 64 (arg-max edge kept for backward) per point.
-        ev = [e0.elapsed_time(e1) for (tag, e0, e1) in kernel_events if tag == 1]
+        N = args.points
+        # Dominant entry point by device time (profiles/): EdgeConv forward of MLP3 = first-layer moments (SIMT) + the fused
+        # tcgen05 kernel + BN2/LeakyReLU apply.  GEMM-shaped work -> tensor roofline: useful flops = both 1x1 convolutions over
+        # the N*20 edges; the 64x64 one runs as TF32 x 3 (fp32 parity), i.e. 6x the cost of the same contraction in bf16.
+        ev = [a.elapsed_time(c) for (name, tag, a, c) in kernel_events if name == "sgb_edgeconv_fwd" and tag == 1]
         k_ms = float(np.mean(ev)) if ev else None
-        alg_bytes = args.points * (36 + 80 + 256 + 64)
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
-        roofline = {"bound": "hbm", "kernel": "sgb_edgeconv_fwd (MLP3: moments + moments2 + max pass)", "achieved": achieved,
-                    "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"] if achieved else None,
-                    "traffic": None, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": len(ev)}
+        flops = 2.0 * N * 20 * (18 * 64 + 64 * 64)
+        achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        roofline = {"bound": "tensor", "kernel": "sgb_edgeconv_fwd two_layer (gram1_kernel + ec2_tc_kernel<ARG,GRAM> [tcgen05 kind::tf32 x3] + ec2_apply_kernel)",
+                    "achieved": achieved, "peak": peak_tf, "peak_kind": peak_kind + " bf16 dense (tf32 runs at half of it, the x3 split costs 3 MMAs)",
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None, "traffic": None, "ms_per_launch": k_ms,
+                    "algorithmic_flops_per_launch": flops, "launches_timed": len(ev),
+                    "note": "timed with CUDA events on the launching stream while %d scenes are in flight" % args.streams}
+        # the HBM-bound gather/scatter kernel of the path: point -> segment max pooling (sgb_segment_pool_max_fwd on [N,64])
+        evp = [a.elapsed_time(c) for (name, tag, a, c) in kernel_events if name == "sgb_segment_pool_max_fwd" and tag == N]
+        p_ms = float(np.mean(evp)) if evp else None
+        pool_bytes = N * (4 * 64 + 4) + 16 * 1100 * 64
+        roofline_more = [{"bound": "hbm", "kernel": "sgb_segment_pool_max_fwd [N,64] (segment_pool_fwd_kernel + decode)",
+                          "achieved": pool_bytes / (p_ms * 1e-3) / 1e9 if p_ms else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": pool_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if p_ms else None, "ms_per_launch": p_ms,
+                          "algorithmic_bytes_per_launch": pool_bytes, "launches_timed": len(evp)}]
         cpu = None
         if not args.no_cpu_baseline:
             pps, sec, cores = cpu_port_points_per_sec(args.ref_points)
@@ -255,7 +278,9 @@ def main():
                            "weights": "torch.manual_seed(1) default init, mlp_1.bn1.weight x %g" % GSCALE, "l2": "256 MiB flush buffer written every step",
                            "parallelism": "dp%d" % world if world > 1 else "single", "scenes_in_flight": args.streams},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "inference": {"value": pts_per_step * args.steps / (ms_inf * 1e-3), "unit": UNIT, "ms_per_step": ms_inf / args.steps,
+                              "workload": "pseudo-label generation (ins_infer incl. label export to HBM) over the same batch"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_more": roofline_more, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

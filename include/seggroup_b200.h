@@ -244,6 +244,12 @@ int sgb_group_nearby(const int* adj, int A, const int* roots_cur, const float* d
 int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
                              const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream);
 
+/* a14  phase B of `group_unlabeled_clusters` (model.py:472-509): every cluster phase A left unlabeled (unl [n_unl], ascending
+ * dense ids) joins the first labelled cluster of its candidate list cand [n_unl,S] (all cluster ids by increasing sampled-cloud
+ * distance); further labelled candidates only receive the reference's stale-id point_num drift. */
+int sgb_group_unlabeled_phase_b(const int* unl, int n_unl, const int* cand, int S, const int* roots_cur, int* uf, int S1,
+                                void* stream);
+
 /* a16  replaces seggroup/model.py:525-605 `export_{segment,instance,semantic}_label` up to the text
  * formatting: per raw vertex r (p = unmap[r], int64 as stored in unmap.pth; NULL = identity):
  * seg = root point id of p's cluster, ins/sem = weak label + 1 or -1. */

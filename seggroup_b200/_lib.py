@@ -94,7 +94,7 @@ profile = None
 
 # bench.py bookkeeping: CUDA-event pairs around one chosen entry point (recorded on the launching stream, resolved by the
 # caller after its final synchronize).  Kernel launches are counted inside the library (sgb_launch_count).
-time_entry = None
+time_entry = None          # set of entry-point names whose calls are bracketed by CUDA events
 timed_events = []
 
 
@@ -108,13 +108,15 @@ def enable_profile():
 
 
 def call(name: str, *args):
-    if time_entry is not None and name == time_entry:
+    if time_entry is not None and name in time_entry:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = _call(name, *args)
         e1.record()
-        timed_events.append((args[3] if name == "sgb_edgeconv_fwd" else 0, e0, e1))
+        # tag: two_layer flag for the EdgeConv forward, number of feature rows for the pooling
+        tag = args[3] if name == "sgb_edgeconv_fwd" else (args[1] if name == "sgb_segment_pool_max_fwd" else 0)
+        timed_events.append((name, tag, e0, e1))
         return rc
     if profile is not None and not name.endswith("_bytes"):
         import torch

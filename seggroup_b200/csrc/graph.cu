@@ -481,6 +481,31 @@ __global__ void unlabeled_union_kernel(const int* __restrict__ amin, int S, cons
     }
 }
 
+// group_unlabeled_clusters phase B (model.py:472-509): every cluster that phase A left unlabeled walks the other clusters in
+// order of increasing sampled-cloud distance (`cand` [n_unl][S], sorted by the caller on the device) and joins the first
+// labelled one; the reference keeps calling union() with the now stale id for every further labelled candidate, which only
+// drifts point_num -- reproduced.  Sequential by definition: one thread.
+__global__ void unlabeled_phase_b_kernel(const int* __restrict__ unl, int n_unl, const int* __restrict__ cand, int S,
+                                         const int* __restrict__ roots_cur, int* __restrict__ ufb, int S1) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    UF u(ufb, S1);
+    for (int q = 0; q < n_unl; ++q) {
+        const int i = unl[q];
+        const int c1 = uf_find(u, roots_cur[i]);
+        if (u.ins[c1] != -1) continue;
+        bool merged = false;
+        for (int t = 0; t < S; ++t) {
+            const int j = cand[(size_t)q * S + t];
+            if (j == i) continue;
+            const int c2 = uf_find(u, roots_cur[j]);
+            if (u.ins[c2] == -1) continue;
+            if (merged) { u.pnum[c2] += u.pnum[c1]; continue; }
+            uf_union(u, c1, c2);
+            merged = true;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // label export (model.py:525-605): per raw vertex r, p = unmap[r]: segment = root point id of p's cluster,
 // instance / semantic = weak label + 1 (or -1 when the cluster is unlabeled)
@@ -686,6 +711,18 @@ extern "C" int sgb_group_unlabeled_step(const float* dist, const int* row_off, c
     cudaStream_t st = (cudaStream_t)stream;
     { unlabeled_argmin_kernel<<<sgb_div_up(S, 128), 128, 0, st>>>(dist, row_off, nbr, eid, S, amin_ws); SGB_COUNT_LAUNCH(); }
     { unlabeled_union_kernel<<<1, 32, 0, st>>>(amin_ws, S, roots_cur, uf, S1); SGB_COUNT_LAUNCH(); }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+// phase B of group_unlabeled_clusters: unl [n_unl] dense ids of the unlabeled clusters (ascending), cand [n_unl,S] all cluster
+// ids sorted by increasing cloud distance from the respective unlabeled cluster
+extern "C" int sgb_group_unlabeled_phase_b(const int* unl, int n_unl, const int* cand, int S, const int* roots_cur, int* uf, int S1,
+                                           void* stream) {
+    if (n_unl < 0 || S <= 0 || S1 <= 0 || !roots_cur || !uf) return SGB_ERR_INVALID;
+    if (n_unl == 0) return SGB_OK;
+    if (!unl || !cand) return SGB_ERR_INVALID;
+    { unlabeled_phase_b_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(unl, n_unl, cand, S, roots_cur, uf, S1); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

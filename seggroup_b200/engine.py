@@ -109,3 +109,35 @@ class SceneExecutor:
                 else:
                     p.grad.add_(g)
         return total
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU plumbing: scenes are the shard unit, one process per GPU
+# ------------------------------------------------------------------------------------------------
+def shard_scenes(n_scenes: int, rank: int, world: int):
+    """Scene indices of `rank`: round-robin `rank::world`, WITHOUT the padding duplicates of the reference's
+    DistributedSampler (train.py:102 pads 1,201 scenes to 1,208 at 8 ranks, so 7 scenes are counted twice)."""
+    return list(range(rank, n_scenes, world))
+
+
+def allreduce_flat(tensors, dist_module=None, average=True, extra=None):
+    """ONE all-reduce for a list of tensors (the 147,880 gradients of SegModel = 0.59 MB: latency bound, so bucketing or
+    overlap would only add launches).  `extra`: optional 1-D tensor (e.g. the 165 logging floats of train.py:172-175)
+    appended to the same buffer and returned summed.  In place; works for NCCL (CUDA) and gloo (CPU) process groups."""
+    import torch.distributed as dist
+    d = dist_module or dist
+    if not d.is_available() or not d.is_initialized() or d.get_world_size() == 1:
+        return extra
+    flats = [t.reshape(-1) for t in tensors] + ([extra.reshape(-1).to(tensors[0].dtype)] if extra is not None else [])
+    flat = torch.cat(flats)
+    d.all_reduce(flat)
+    n_extra = extra.numel() if extra is not None else 0
+    body = flat[:flat.numel() - n_extra]
+    if average:
+        body /= d.get_world_size()
+    o = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(body[o:o + n].view_as(t))
+        o += n
+    return flat[flat.numel() - n_extra:].clone() if extra is not None else None

@@ -351,6 +351,11 @@ def group_unlabeled_step(dist, csr, S, roots_cur, uf):
     return amin
 
 
+def group_unlabeled_phase_b(unl, cand, roots_cur, uf):
+    _chk(unl, I32, "unl"); _chk(cand, I32, "cand")
+    _lib.call("sgb_group_unlabeled_phase_b", unl, unl.numel(), cand, cand.shape[1], roots_cur, uf, uf.shape[1], _stream())
+
+
 def export_labels(unmap, seg_of_point, level: Level, want_seg=True):
     """unmap [N_raw] i64 (or None) -> (seg, ins, sem) int32 [N_raw]."""
     dev = seg_of_point.device

@@ -346,41 +346,16 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
 
 
 def _phase_b(sc, uf, sos, status, Lo, Feat):
-    """model.py:472-509 — nearest labelled cluster by sampled-cloud distance for clusters phase A left unlabeled."""
+    """model.py:472-509 — nearest labelled cluster by sampled-cloud distance for clusters phase A left unlabeled.
+    Clouds: FPS kernel; distances / sort: torch device ops on [n_unl, S, 1024]; the order-dependent unions: one kernel."""
     P = 1024
-    cloud_idx, _ = ops.cluster_cloud_indices(sc.data, Lo.order, Lo.cl_pt_off, P)
+    cloud_idx, _ = ops.cluster_cloud_indices(sc.data, Lo.order, Lo.cl_pt_off, P, status=status)
     pts = sc.data[:, :3][cloud_idx.long().view(-1)].view(Lo.S, P, 3)
-    ufh = uf.cpu().numpy()                                  # rare path: replayed on the host state, written back
-    parent, nxt, tail, pnum, ins, sem = ufh
-    roots = Lo.roots.cpu().numpy()
-
-    def find(s):
-        while parent[s] != s:
-            s = parent[s]
-        return s
-
-    for i in range(Lo.S):
-        c1 = find(roots[i])
-        if ins[c1] != -1:
-            continue
-        mean = pts[i].mean(0, keepdim=True).unsqueeze(0)
-        dmin = ((mean - pts) ** 2).sum(2).min(-1)[0]
-        merged = False
-        for j in torch.sort(dmin)[1].tolist():
-            if j == i:
-                continue
-            c2 = find(roots[j])
-            if ins[c2] == -1:
-                continue
-            if merged:
-                pnum[c2] += pnum[c1]                        # stale-id union: only point_num drifts (SURVEY.md 9.2 #12)
-                continue
-            parent[c1] = c2; pnum[c2] += pnum[c1]
-            if ins[c1] != ins[c2]:
-                ins[c2] = -ins[c1] * ins[c2]; sem[c2] = -sem[c1] * sem[c2]
-            nxt[tail[c2]] = c1; tail[c2] = tail[c1]
-            merged = True
-    uf.copy_(torch.as_tensor(ufh))
+    unl = torch.nonzero(Lo.cl_ins == -1).view(-1)                           # ascending dense ids
+    mean = pts[unl].mean(1).view(-1, 1, 1, 3)                               # [n_unl,1,1,3]
+    dmin = ((mean - pts.unsqueeze(0)) ** 2).sum(3).min(-1)[0]               # [n_unl,S]
+    cand = torch.sort(dmin, dim=1)[1].to(I32).contiguous()
+    ops.group_unlabeled_phase_b(unl.to(I32).contiguous(), cand, Lo.roots, uf)
     Ln = ops.level_step(2, uf, sc.seg_off, sc.seg_members, sos, status, old=Lo)
     Feat, _ = SegmentMaxFn.apply(Feat, Ln.ch_off, Ln.ch_list)
     return Ln, Feat

@@ -79,3 +79,20 @@ def test_train_loss_and_grads(scene8k, gscale):
             continue
         errs[k] = _rel(p[k].grad, gr)
     assert max(errs.values()) < 1e-3, errs
+
+
+def test_final_clustering_phase_b(scene8k):
+    """An isolated, unlabeled first cluster survives phase A of group_unlabeled_clusters (its row arg-min is itself), so
+    phase B (sampled-cloud distances, model.py:472-509) must assign it: labels bit-exact against the oracle."""
+    import copy
+    from seggroup_b200 import synth
+    sc = copy.deepcopy(scene8k)
+    seg_pts = sc.seg_members[sc.seg_offsets[0]:sc.seg_offsets[1]]          # segment with the smallest root point = cluster 0
+    assert seg_pts.min() == 0
+    sc.weak_label = sc.weak_label.copy(); sc.weak_label[seg_pts] = -1
+    in_seg = np.zeros(sc.n_points, bool); in_seg[seg_pts] = True
+    sc.adj = sc.adj[~(in_seg[sc.adj[:, 0]] | in_seg[sc.adj[:, 1]])]
+    ref, res, _ = _run_pair(sc, "ins_infer", 4.0)
+    assert ref["phaseA_clusters"] == res.aux["phaseA_clusters"]
+    assert ref["levels"][-1].S == ref["phaseA_clusters"] - 1, "phase B did not fire in the oracle"
+    _check_labels(ref, res)
