@@ -23,6 +23,32 @@ void sgb_count_launch();             // one kernel of this library was launched 
 static inline int sgb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
+#include <atomic>
+// Opt a kernel in to the full 227 KB of dynamic shared memory ONCE per (kernel, device).  The attribute is process-wide
+// state of the function: setting it to the size of each launch is a race between scene threads (one thread lowers it
+// between another thread's set and launch -> "invalid argument"), so every kernel gets the device maximum, set once.
+template <auto Kernel>
+inline cudaError_t sgb_opt_in_smem() {
+    static std::atomic<unsigned> done{0};            // bit per device ordinal
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned bit = 1u << (dev & 31);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, Kernel);
+    if (e != cudaSuccess) return e;
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);   // static + dynamic <= opt-in
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+#define SGB_OPT_IN_SMEM(...) SGB_CUDA((sgb_opt_in_smem<__VA_ARGS__>()))
+#endif
+
+#ifdef __CUDACC__
 #define SGB_FULL_MASK 0xffffffffu
 
 // Monotone map float -> uint32 (a < b  <=>  key(a) < key(b); +NaN sorts above +inf).

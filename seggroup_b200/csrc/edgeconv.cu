@@ -380,16 +380,16 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     if (two_layer) {
         const int g2 = grid < 148 * 2 ? grid : 148 * 2;
         const size_t sm2 = SMEM_STAGE + NE2 * sizeof(double) + sizeof(float) * CIN * COUT;
-        SGB_CUDA(cudaFuncSetAttribute(gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        SGB_OPT_IN_SMEM(gram2_kernel);
         { gram2_kernel<<<g2, WARPS * 32, sm2, st>>>(x9, knn, N, W1, stats1, g2part); SGB_COUNT_LAUNCH(); }
         sgb_bn::reduce_partials(g2part, g2, NE2, mom2, st);
         { bn2_finalize_kernel<<<COUT, 64, 0, st>>>(mom2, M, W2, gamma2, beta2, stats2, var2); SGB_COUNT_LAUNCH(); }
         const size_t smB = SMEM_STAGE + sizeof(float) * COUT * COUT;
-        SGB_CUDA(cudaFuncSetAttribute(forward_max_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+        SGB_OPT_IN_SMEM(forward_max_kernel<true>);
         { forward_max_kernel<true><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, W2, stats2, out, argk); SGB_COUNT_LAUNCH(); }
     } else {
         const size_t smB = sizeof(float) * WARPS * KNN * CINP;
-        SGB_CUDA(cudaFuncSetAttribute(forward_max_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+        SGB_OPT_IN_SMEM(forward_max_kernel<false>);
         { forward_max_kernel<false><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, nullptr, nullptr, out, argk); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();

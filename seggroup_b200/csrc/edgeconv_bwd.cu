@@ -346,7 +346,7 @@ extern "C" int sgb_edgeconv_bwd(const float* g, const int* arg, const unsigned c
         sgb_bn::reduce_partials(part2, nchunk, COUT * 66, t2, st);
         { bwd_mid_kernel<<<COUT, 64, 0, st>>>(t2, M, W2, stats2, mom2, gW2, gg2, gb2, coef); SGB_COUNT_LAUNCH(); }
         const size_t sm = sizeof(float) * (WARPS * KNN * (CINP + COUT) + COUT * COUT + CINP);
-        SGB_CUDA(cudaFuncSetAttribute(bwd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        SGB_OPT_IN_SMEM(bwd_dense_kernel);
         { bwd_dense_kernel<<<gd, WARPS * 32, sm, st>>>(x9, knn, N, W1, stats1, mom1, e0, M, coef, partD); SGB_COUNT_LAUNCH(); }
         sgb_bn::reduce_partials(partD, gd, COUT * NACC, red + COUT * NACC, st);
         { bwd_last_kernel<<<1, 64, 0, st>>>(red, 2, M, W1, stats1, mom1, gW1, gg1, gb1); SGB_COUNT_LAUNCH(); }

@@ -458,17 +458,17 @@ int sgb_ec2_tc_forward(const float* x9, const int* knn, int N, const float* W1, 
     if (gram) {
         const size_t smem = Cfg<true>::total + 1024;
         SGB_CUDA(cudaMemsetAsync(gslots, 0, (size_t)grid * nflush * 128 * GN * 4, st));
-        SGB_CUDA(cudaFuncSetAttribute(ec2_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_OPT_IN_SMEM(ec2_tc_kernel<true, true>);
         { ec2_tc_kernel<true, true><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, zmax, zmin, kk, part, gslots, nflush); SGB_COUNT_LAUNCH(); }
         sgb_bn::reduce_partials(gslots, grid * nflush, 128 * GN, gred, st);
         { mom2_from_gram_kernel<<<1, 64, 0, st>>>(gred, mom2); SGB_COUNT_LAUNCH(); }
     } else if (argk) {
         const size_t smem = Cfg<false>::total + 1024;
-        SGB_CUDA(cudaFuncSetAttribute(ec2_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_OPT_IN_SMEM(ec2_tc_kernel<true, false>);
         { ec2_tc_kernel<true, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, zmax, zmin, kk, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
     } else {
         const size_t smem = Cfg<false>::total + 1024;
-        SGB_CUDA(cudaFuncSetAttribute(ec2_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_OPT_IN_SMEM(ec2_tc_kernel<false, false>);
         { ec2_tc_kernel<false, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, zmax, zmin, kk, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
     }
     sgb_bn::reduce_partials(part, grid, 128, sums, st);

@@ -697,7 +697,7 @@ extern "C" int sgb_group_nearby(const int* adj, int A, const int* roots_cur, con
     const size_t state_bytes = (size_t)6 * S1 * sizeof(int);
     const int in_smem = state_bytes <= 160 * 1024;
     if (in_smem && state_bytes > 16 * 1024)
-        SGB_CUDA(cudaFuncSetAttribute(group_nearby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)state_bytes));
+        SGB_OPT_IN_SMEM(group_nearby_kernel);
     { group_nearby_kernel<<<1, GN_THREADS, in_smem ? state_bytes : 0, (cudaStream_t)stream>>>(adj, A, roots_cur, dist, th, uf, S1, sweep_cap,
                                                                                            status, in_smem); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();

@@ -318,13 +318,13 @@ extern "C" int sgb_kpconv_fwd(const float* query_points, const float* support_po
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = sgb_div_up(n, p.T);
     if (p.cpl == 1) {
-        SGB_CUDA(cudaFuncSetAttribute(kpconv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        SGB_OPT_IN_SMEM(kpconv_fwd_kernel<1>);
         { kpconv_fwd_kernel<1><<<grid, KP_THREADS, p.smem, st>>>(a); SGB_COUNT_LAUNCH(); }
     } else if (p.cpl == 2) {
-        SGB_CUDA(cudaFuncSetAttribute(kpconv_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        SGB_OPT_IN_SMEM(kpconv_fwd_kernel<2>);
         { kpconv_fwd_kernel<2><<<grid, KP_THREADS, p.smem, st>>>(a); SGB_COUNT_LAUNCH(); }
     } else {
-        SGB_CUDA(cudaFuncSetAttribute(kpconv_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        SGB_OPT_IN_SMEM(kpconv_fwd_kernel<4>);
         { kpconv_fwd_kernel<4><<<grid, KP_THREADS, p.smem, st>>>(a); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();
@@ -364,13 +364,13 @@ extern "C" int sgb_kpconv_bwd(const float* g, const float* query_points, const f
     KpBwdArgs b{g, gfeat, (float*)ws, tiles};
     cudaStream_t st = (cudaStream_t)stream;
     if (p.cpl == 1) {
-        SGB_CUDA(cudaFuncSetAttribute(kpconv_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_OPT_IN_SMEM(kpconv_bwd_kernel<1>);
         { kpconv_bwd_kernel<1><<<grid, KP_THREADS, smem, st>>>(a, b); SGB_COUNT_LAUNCH(); }
     } else if (p.cpl == 2) {
-        SGB_CUDA(cudaFuncSetAttribute(kpconv_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_OPT_IN_SMEM(kpconv_bwd_kernel<2>);
         { kpconv_bwd_kernel<2><<<grid, KP_THREADS, smem, st>>>(a, b); SGB_COUNT_LAUNCH(); }
     } else {
-        SGB_CUDA(cudaFuncSetAttribute(kpconv_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGB_OPT_IN_SMEM(kpconv_bwd_kernel<4>);
         { kpconv_bwd_kernel<4><<<grid, KP_THREADS, smem, st>>>(a, b); SGB_COUNT_LAUNCH(); }
     }
     const long long total = (long long)K * Cin * Cout;

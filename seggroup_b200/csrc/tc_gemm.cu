@@ -156,7 +156,7 @@ extern "C" int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, 
     int cols = 32;
     while (cols < N) cols <<= 1;
     const size_t smem = (size_t)(2 * 128 + 2 * N) * TG_KC * 4;
-    SGB_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGB_OPT_IN_SMEM(gemm_tf32x3_kernel);
     gemm_tf32x3_kernel<<<sgb_div_up(M, 128), TG_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, cols); SGB_COUNT_LAUNCH();
     SGB_CHECK_LAUNCH();
     return SGB_OK;
@@ -167,7 +167,7 @@ extern "C" int sgb_tc_probe(const float* imgA, int wordsA, const float* imgB, in
     if (!imgA || !imgB || !D || wordsA <= 0 || wordsB <= 0 || N <= 0 || N > 256 || (N & 15) || (wordsA & 255) || (wordsB & 255)) return SGB_ERR_INVALID;
     const size_t smem = (size_t)(wordsA + wordsB) * 4 + 1024;
     if (smem > 200 * 1024) return SGB_ERR_UNSUPPORTED;
-    SGB_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGB_OPT_IN_SMEM(probe_kernel);
     probe_kernel<<<1, TG_THREADS, smem, (cudaStream_t)stream>>>(imgA, wordsA, imgB, wordsB, descA, descB, idesc, N, D); SGB_COUNT_LAUNCH();
     SGB_CHECK_LAUNCH();
     return SGB_OK;
