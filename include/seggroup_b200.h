@@ -312,6 +312,17 @@ int sgb_kpconv_bwd(const float* g, const float* query_points, const float* suppo
                    int K, float KP_extent, int influence, int closest, float* gfeat, float* gK,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* a20 on the tensor cores: same contract as sgb_kpconv_fwd, with the [n, K*Cin] x [K*Cin, Cout] contraction of
+ * convolution_ops.py:240-247 on tcgen05 (kind::tf32, TF32 x 3 split: fp32-level accuracy, 1e-4 relative holds).
+ * Shapes: Cin multiple of 32, Cout multiple of 16 and <= 256, W <= 64, K <= 32 (sgb_kpconv_tc_supported -> 1);
+ * anything else returns SGB_ERR_UNSUPPORTED and the caller uses sgb_kpconv_fwd.  `ws` holds the pre-split,
+ * pre-swizzled image of K_values (sgb_kpconv_tc_ws_bytes). */
+int sgb_kpconv_tc_supported(int W, int Cin, int Cout, int K, int n0);
+size_t sgb_kpconv_tc_ws_bytes(int Cin, int Cout, int K);
+int sgb_kpconv_fwd_tc(const float* query_points, const float* support_points, const int* neighbors, const float* features,
+                      const float* K_points, const float* K_values, int n, int n0, int W, int Cin, int Cout, int K,
+                      float KP_extent, int influence, int closest, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* HOST function: writes n lines '%d\n' to `path` — the text format of seggroup/model.py:536-546 that the stage-2
  * consumers read (kpconv/datasets/Scannet2.py:148-156).  `values` is a host pointer. */
 int sgb_write_labels_host(const char* path, const int* values, int n);

@@ -99,12 +99,18 @@ def ordered_neighbors(queries, supports, radius):
 # ------------------------------------------------------------------------------------------------ B4
 class _KPConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, s, idx, feats, kpts, kvals, extent, influence, closest):
+    def forward(ctx, q, s, idx, feats, kpts, kvals, extent, influence, closest, use_tc=True):
         n, n0 = q.shape[0], s.shape[0]
         W = idx.shape[1]
         K, Cin, Cout = kvals.shape
         out = torch.empty(n, Cout, dtype=F32, device=q.device)
-        _lib.call("sgb_kpconv_fwd", q, s, idx, feats, kpts, kvals, n, n0, W, Cin, Cout, K, float(extent), influence, closest, out, _stream())
+        if use_tc and _lib.call("sgb_kpconv_tc_supported", W, Cin, Cout, K, n0):
+            # contraction on tcgen05 (TF32 x 3 split, fp32-level accuracy); shapes outside its limits take the SIMT kernel
+            ws = _ws(_lib.call("sgb_kpconv_tc_ws_bytes", Cin, Cout, K), q.device)
+            _lib.call("sgb_kpconv_fwd_tc", q, s, idx, feats, kpts, kvals, n, n0, W, Cin, Cout, K, float(extent), influence, closest, out,
+                      ws, ws.numel(), _stream())
+        else:
+            _lib.call("sgb_kpconv_fwd", q, s, idx, feats, kpts, kvals, n, n0, W, Cin, Cout, K, float(extent), influence, closest, out, _stream())
         ctx.save_for_backward(q, s, idx, feats, kpts, kvals)
         ctx.cfg = (float(extent), influence, closest)
         return out
@@ -120,11 +126,13 @@ class _KPConvFn(torch.autograd.Function):
         ws = _ws(_lib.call("sgb_kpconv_bwd_ws_bytes", n, Cin, Cout, K), q.device)
         _lib.call("sgb_kpconv_bwd", g.contiguous(), q, s, idx, feats, kpts, kvals, n, n0, idx.shape[1], Cin, Cout, K, extent, influence, closest,
                   gf, gk, ws, ws.numel(), _stream())
-        return None, None, None, gf, None, gk, None, None, None
+        return None, None, None, gf, None, gk, None, None, None, None
 
 
-def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent, KP_influence, aggregation_mode):
-    """kpconv/kernels/convolution_ops.py:161-249, same argument order; differentiable w.r.t. features and K_values."""
+def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent, KP_influence, aggregation_mode,
+               tensor_cores=True):
+    """kpconv/kernels/convolution_ops.py:161-249, same argument order; differentiable w.r.t. features and K_values.
+    `tensor_cores=False` forces the fp32 SIMT kernel (tests compare the two)."""
     if KP_influence not in _INFLUENCE:
         raise ValueError('Unknown influence function type (config.KP_influence)')
     if aggregation_mode not in ("sum", "closest"):
@@ -135,7 +143,7 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
         idx = idx.to(I32)
     idx = _chk(idx.contiguous(), I32, "neighbors_indices")
     return _KPConvFn.apply(q, s, idx, features.contiguous(), _chk(K_points.contiguous(), F32, "K_points"), K_values.contiguous(),
-                           KP_extent, _INFLUENCE[KP_influence], int(aggregation_mode == "closest"))
+                           KP_extent, _INFLUENCE[KP_influence], int(aggregation_mode == "closest"), bool(tensor_cores))
 
 
 def KPConv(query_points, support_points, neighbors_indices, features, K_values, fixed='center', KP_extent=1.0,

@@ -137,3 +137,55 @@ def test_kpconv_forward_backward(cin, cout, influence, mode):
     (ref * go.double()).sum().backward()
     assert float((fd.grad.cpu().double() - f64.grad).abs().max()) < 1e-4 * float(f64.grad.abs().max())
     assert float((kd.grad.cpu().double() - k64.grad).abs().max()) < 1e-4 * float(k64.grad.abs().max())
+
+
+@pytest.mark.parametrize("cin,cout,wcap", [(64, 64, 64), (64, 64, 20), (32, 32, 40), (128, 64, 64), (64, 128, 48), (128, 128, 64), (32, 256, 33), (192, 16, 64)])
+@pytest.mark.parametrize("influence,mode", [("linear", "sum"), ("gaussian", "sum"), ("linear", "closest"), ("constant", "sum")])
+def test_kpconv_tensor_core_contraction(cin, cout, wcap, influence, mode):
+    """sgb_kpconv_fwd_tc (tcgen05 contraction, TF32 x 3) against the fp64 restatement of convolution_ops.py:161-249 and
+    against the fp32 SIMT kernel: 1e-4 relative to the former (north_star bar), 5e-5 to the latter (two fp32 summation orders)."""
+    from oracle import kpconv_oracle as K
+    from seggroup_b200 import _lib
+    from seggroup_b200.kpconv_ops import KPConv_ops, batch_ordered_neighbors
+    pts, lens = cloud(7, 5000)
+    sub, _ = K.batch_grid_subsampling(pts, lens, 0.05)
+    qs, _ = K.batch_grid_subsampling(pts, lens, 0.07)          # a query count that is not a multiple of the 128-row tile
+    S, Q = cu(sub), cu(qs)
+    radius, extent = 0.14, 0.055
+    nb = batch_ordered_neighbors(Q, S, None, None, radius)[:, :wcap].contiguous()      # rows are distance sorted: keep the nearest
+    assert nb.shape[1] <= 64 and (nb == len(sub)).any(), "the case must hold shadow neighbours"
+    assert _lib.call("sgb_kpconv_tc_supported", nb.shape[1], cin, cout, 15, len(sub)) == 1
+    g = torch.Generator().manual_seed(cin * 1000 + cout + wcap)
+    kp = (torch.rand(15, 3, generator=g) * 2 - 1) * 0.08
+    kp[0] = 0
+    feats = torch.randn(len(sub), cin, generator=g)
+    kv = torch.randn(15, cin, cout, generator=g) * (1.0 / np.sqrt(cin * 15))
+    launches = _lib.launch_count()
+    out = KPConv_ops(Q, S, nb, feats.cuda(), kp.cuda(), kv.cuda(), extent, influence, mode)
+    assert _lib.launch_count() - launches == 2                  # prep + the tcgen05 kernel: the tensor-core path really ran
+    simt = KPConv_ops(Q, S, nb, feats.cuda(), kp.cuda(), kv.cuda(), extent, influence, mode, tensor_cores=False)
+    ref = K.kpconv_ops(Q.cpu(), S.cpu(), nb.cpu(), feats.double(), kp, kv.double(), extent, influence, mode, dtype=torch.float64)
+    scale = float(ref.abs().max())
+    assert float((out.cpu().double() - ref).abs().max()) < 1e-4 * scale
+    assert float((out - simt).abs().max()) < 5e-5 * scale
+
+
+def test_kpconv_tensor_core_small_and_unsupported():
+    from oracle import kpconv_oracle as K
+    from seggroup_b200 import _lib
+    from seggroup_b200.kpconv_ops import KPConv_ops
+    assert _lib.call("sgb_kpconv_tc_supported", 65, 64, 64, 15, 1000) == 0       # rows wider than 64 neighbours
+    assert _lib.call("sgb_kpconv_tc_supported", 40, 5, 64, 15, 1000) == 0        # first-layer Cin
+    assert _lib.call("sgb_kpconv_tc_supported", 40, 64, 512, 15, 1000) == 0
+    g = torch.Generator().manual_seed(3)
+    for n, n0, W in [(1, 7, 3), (37, 50, 9), (129, 300, 32), (5, 40, 0)]:
+        q = torch.rand(n, 3, generator=g) * 0.2
+        s = torch.rand(n0, 3, generator=g) * 0.2
+        nb = torch.randint(0, n0 + 3, (n, W), generator=g).clamp(max=n0).to(torch.int32)   # id n0 = shadow neighbour
+        kp = (torch.rand(15, 3, generator=g) * 2 - 1) * 0.06
+        feats = torch.randn(n0, 64, generator=g)
+        kv = torch.randn(15, 64, 32, generator=g) * 0.05
+        out = KPConv_ops(q.cuda(), s.cuda(), nb.cuda(), feats.cuda(), kp.cuda(), kv.cuda(), 0.08, "linear", "sum")
+        ref = K.kpconv_ops(q, s, nb, feats.double(), kp, kv.double(), 0.08, "linear", "sum", dtype=torch.float64)
+        assert out.shape == (n, 32)
+        assert float((out.cpu().double() - ref).abs().max()) <= 1e-4 * max(float(ref.abs().max()), 1e-6)

@@ -1,0 +1,183 @@
+"""Per-kernel roofline micro-benchmark of the hot-path kernels (SURVEY.md 8d algorithmic bytes / flops).
+
+    python tools/bench_kernels.py [--points 150000,500000] [--reps 20] [--only pool,kpconv] [--out gpurun_out/kernels.json]
+
+Every timed launch is preceded by a 256 MiB write (L2 flush, outside the CUDA-event bracket), timed with CUDA events on
+the launching stream; the median over `--reps` launches is reported next to the algorithmic bytes (HBM-bound kernels,
+peak = MEASURED_PEAKS.json hbm_gbs) or flops (the tcgen05 contractions, peak = bf16_tflops / 2 for kind::tf32, and the
+TF32 x 3 split spends 3 MMAs per useful product).  One JSON object per kernel, one per line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from seggroup_b200 import _lib, ops, synth  # noqa: E402
+from seggroup_b200 import kpconv_ops as KO  # noqa: E402
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+class Timer:
+    def __init__(self, reps, warm=2):
+        self.reps, self.warm = reps, warm
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def __call__(self, fn):
+        for _ in range(self.warm):
+            fn()
+        ts = []
+        for _ in range(self.reps):
+            self.flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts)), float(np.min(ts))
+
+
+def emit(rows, name, N, ms, ms_min, nbytes=None, flops=None, note="", **kw):
+    P = peaks()
+    r = {"kernel": name, "points": N, "ms_median": round(ms, 5), "ms_min": round(ms_min, 5)}
+    if nbytes is not None:
+        r.update(bound="hbm", algorithmic_bytes=int(nbytes), achieved_gbs=round(nbytes / ms / 1e6, 1), peak_gbs=P["hbm_gbs"],
+                 frac=round(nbytes / ms / 1e6 / P["hbm_gbs"], 4))
+    if flops is not None:
+        r.update(algorithmic_flops=int(flops), achieved_tflops=round(flops / ms / 1e9, 2))
+    if note:
+        r["note"] = note
+    r.update(kw)
+    rows.append(r)
+    print(json.dumps(r), flush=True)
+
+
+def scene_arrays(N, seed=11):
+    sc = synth.make_scene(seed, N)
+    dev = "cuda"
+    t = lambda a, dt=None: (torch.as_tensor(np.ascontiguousarray(a)) if dt is None else torch.as_tensor(np.ascontiguousarray(a)).to(dt)).to(dev)
+    return sc, dict(data=t(sc.data), seg_off=t(sc.seg_offsets, torch.int32), seg_members=t(sc.seg_members, torch.int32),
+                    adj=t(sc.adj, torch.int32), weak=t(sc.weak_label, torch.int32))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", default="150000,500000")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--warm", type=int, default=2)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
+    want = lambda k: not only or k in only
+    _lib.load()
+    T = Timer(args.reps, args.warm)
+    rows = []
+    g = torch.Generator().manual_seed(0)
+    for N in [int(x) for x in args.points.split(",")]:
+        sc, d = scene_arrays(N)
+        S = d["seg_off"].numel() - 1
+        C = 64
+        if want("pool"):
+            feat = torch.randn(N, C, generator=g).cuda()
+            ms, mn = T(lambda: ops.segment_pool_max(feat, d["seg_off"], d["seg_members"]))
+            emit(rows, "segment_pool_max_fwd [N,64] (a10)", N, ms, mn, nbytes=4 * N * C + 4 * N + 16 * S * C, segments=S)
+            out, arg = ops.segment_pool_max(feat, d["seg_off"], d["seg_members"])
+            go = torch.randn(S, C, generator=g).cuda()
+            ms, mn = T(lambda: ops.segment_pool_max_bwd(go, arg, N))
+            emit(rows, "segment_pool_max_bwd [N,64] (zero-fill + scatter)", N, ms, mn, nbytes=8 * S * C + 4 * N * C, segments=S)
+        if want("centralize") or want("knn") or want("edgeconv"):
+            order = d["seg_members"]
+            x9 = ops.centralize(d["data"], order, d["seg_off"])
+        if want("centralize"):
+            ms, mn = T(lambda: ops.centralize(d["data"], order, d["seg_off"]))
+            emit(rows, "centralize (a8)", N, ms, mn, nbytes=24 * N + 4 * N + 36 * N)
+        if want("knn") or want("edgeconv"):
+            knn = ops.cluster_knn(x9, order, d["seg_off"], 20)
+        if want("knn"):
+            ms, mn = T(lambda: ops.cluster_knn(x9, order, d["seg_off"], 20))
+            emit(rows, "cluster_knn k=20 (a7)", N, ms, mn, nbytes=16 * N + 80 * N, note="compute bound: exact per-cluster top-k")
+        if want("edgeconv"):
+            from seggroup_b200.params import init_params
+            p = {k: v.cuda() for k, v in init_params(1, 4.0).items()}
+            a2 = (x9, knn, p["mlp_2.conv1.0.weight"], p["mlp_2.bn1.weight"], p["mlp_2.bn1.bias"])
+            ms, mn = T(lambda: ops.edgeconv_fwd(*a2, want_backward=False))
+            emit(rows, "edgeconv_fwd MLP2 infer (a9)", N, ms, mn, nbytes=36 * N + 80 * N + 256 * N + 64 * N, flops=2.0 * N * 20 * 18 * 64)
+            a3 = a2[:2] + (p["mlp_3.conv1.0.weight"], p["mlp_3.bn1.weight"], p["mlp_3.bn1.bias"], p["mlp_3.conv2.0.weight"], p["mlp_3.bn2.weight"],
+                           p["mlp_3.bn2.bias"])
+            for wb in (False, True):
+                ms, mn = T(lambda: ops.edgeconv_fwd(*a3, want_backward=wb))
+                emit(rows, "edgeconv_fwd MLP3 %s (a9, tcgen05 64x64 layer)" % ("train" if wb else "infer"), N, ms, mn,
+                     nbytes=36 * N + 80 * N + 256 * N + 64 * N, flops=2.0 * N * 20 * (18 * 64 + 64 * 64))
+        if want("export"):
+            from seggroup_b200 import pipeline
+            # label export needs a level; run the model-free part of the pipeline: scene_init + level_build
+            seg_of_point, sos, uf = ops.scene_init(d["seg_off"], d["seg_members"], d["weak"])
+            L = ops.level_build(uf, d["seg_off"], d["seg_members"], sos)
+            unmap = torch.arange(N, dtype=torch.int64, device="cuda")
+            ms, mn = T(lambda: ops.export_labels(unmap, seg_of_point, L))
+            emit(rows, "export_labels (a16)", N, ms, mn, nbytes=8 * N + 4 * N + 12 * N)
+        # ---- KPConv operator set on a 4 cm subsample of a noisy-sheet cloud (SURVEY.md 8d config 5 geometry)
+        if want("grid") or want("neighbors") or want("kpconv"):
+            pts, lens = synth.make_cloud(5, N)
+            P = torch.as_tensor(pts).cuda()
+            Lb = torch.as_tensor(lens).to(torch.int32).cuda()
+            sub, sb = KO.batch_grid_subsampling(P, Lb, 0.04)
+            M = sub.shape[0]
+        if want("grid"):
+            ms, mn = T(lambda: KO.batch_grid_subsampling(P, Lb, 0.04))
+            emit(rows, "grid_subsample dl=0.04 (a18, incl. the size read-back)", N, ms, mn, nbytes=12 * N + 12 * M, voxels=M)
+        if want("neighbors") or want("kpconv"):
+            nb = KO.batch_ordered_neighbors(sub, sub, sb, sb, 0.10)
+            W = nb.shape[1]
+        if want("neighbors"):
+            ms, mn = T(lambda: KO.batch_ordered_neighbors(sub, sub, sb, sb, 0.10))
+            emit(rows, "radius_neighbors r=0.10 (a19, count + read-back + fill)", M, ms, mn, nbytes=24 * M + 4 * M * W, width=W)
+        if want("kpconv"):
+            K = 15
+            extent = 0.04
+            kp = torch.randn(K, 3, generator=g)
+            kp = kp / kp.norm(dim=1, keepdim=True) * 0.06 * torch.rand(K, 1, generator=g) ** (1 / 3)
+            kp[0] = 0
+            kp = kp.cuda()
+            nbc = nb[:, :min(W, 64)].contiguous()
+            Wc = nbc.shape[1]
+            for cin, cout in [(64, 64), (32, 32), (128, 128)]:
+                feats = torch.randn(M, cin, generator=g).cuda()
+                kv = (torch.randn(K, cin, cout, generator=g) / np.sqrt(K * cin)).cuda()
+                by = 4 * M * Wc + 24 * M + 4 * M * cin + 4 * M * cout + 4 * K * cin * cout
+                fl = 2.0 * M * K * cin * cout
+                for tc in (False, True):
+                    ms, mn = T(lambda: KO.KPConv_ops(sub, sub, nbc, feats, kp, kv, extent, "linear", "sum", tensor_cores=tc))
+                    emit(rows, "kpconv_fwd %dx%d %s (a20)" % (cin, cout, "tcgen05 contraction" if tc else "fp32 SIMT"), M, ms, mn, nbytes=by, flops=fl,
+                         width=Wc, note="flops = the K*Cin*Cout contraction only")
+                fd = feats.clone().requires_grad_(True)
+                kd = kv.clone().requires_grad_(True)
+                out = KO.KPConv_ops(sub, sub, nbc, fd, kp, kd, extent, "linear", "sum")
+                go = torch.randn_like(out)
+
+                def bwd():
+                    fd.grad = None; kd.grad = None
+                    out.backward(go, retain_graph=True)
+                ms, mn = T(bwd)
+                emit(rows, "kpconv_bwd %dx%d fp32 SIMT (a20)" % (cin, cout), M, ms, mn, flops=2 * fl, width=Wc)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        json.dump(rows, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
