@@ -323,6 +323,23 @@ int sgb_kpconv_fwd_tc(const float* query_points, const float* support_points, co
                       const float* K_points, const float* K_values, int n, int n0, int W, int Cin, int Cout, int K,
                       float KP_extent, int influence, int closest, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * a21  index pooling beside KPConv (strided shortcut / upsampling blocks)
+ * replaces kpconv/models/network_blocks.py:49-66 `ind_max_pool(x, inds)` and :69-81 `closest_pool(x, inds)`:
+ * x [n1,d] f32, inds [n2,W] int32 with index >= n1 (or < 0) = shadow row.  ind_max_pool: out[i] = max over the W
+ * listed rows, the shadow row being the column minimum of x (:58); closest_pool: out[i] = row inds[i,0], the
+ * shadow row being zeros (:77-80).  Backward = the tf.reduce_max / tf.reduce_min / tf.gather gradients: ties share
+ * the upstream gradient equally, the shadow share flows on to the rows attaining the column minimum.  gx [n1,d] is
+ * overwritten.  `out` of the forward is an input of the backward.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_ind_max_pool_ws_bytes(int d);
+int sgb_ind_max_pool_fwd(const float* x, int n1, int d, const int* inds, int n2, int W, float* out,
+                         void* ws, size_t ws_bytes, void* stream);
+int sgb_ind_max_pool_bwd(const float* g, const float* x, int n1, int d, const int* inds, int n2, int W,
+                         const float* out, float* gx, void* ws, size_t ws_bytes, void* stream);
+int sgb_closest_pool_fwd(const float* x, int n1, int d, const int* inds, int n2, int W, float* out, void* stream);
+int sgb_closest_pool_bwd(const float* g, int n1, int d, const int* inds, int n2, int W, float* gx, void* stream);
+
 /* HOST function: writes n lines '%d\n' to `path` — the text format of seggroup/model.py:536-546 that the stage-2
  * consumers read (kpconv/datasets/Scannet2.py:148-156).  `values` is a host pointer. */
 int sgb_write_labels_host(const char* path, const int* values, int n);

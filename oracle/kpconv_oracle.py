@@ -181,3 +181,21 @@ def kpconv_ops(query_points, support_points, neighbors_indices, features, K_poin
     wf = wf.permute(1, 0, 2)                                                   # :243
     out = torch.matmul(wf, Kv)                                                 # :244  [K, n, Cout]
     return out.sum(dim=0)                                                      # :247
+
+
+# ------------------------------------------------------------------------------------------------
+# index pooling beside KPConv  (kpconv/models/network_blocks.py:49-81)
+# ------------------------------------------------------------------------------------------------
+def ind_max_pool(x, inds):
+    """network_blocks.py:49-66 in torch (CPU): shadow row = column minimum (:58), gather (:61), max over the listed
+    rows (:64).  torch.amax / torch.amin split the gradient equally between ties, as tf.reduce_max / reduce_min do."""
+    import torch
+    xe = torch.cat([x, torch.amin(x, dim=0, keepdim=True)], dim=0)
+    return torch.amax(xe[inds.long()], dim=1)
+
+
+def closest_pool(x, inds):
+    """network_blocks.py:69-81: shadow row = zeros (:77), rows of the first listed index (:80)."""
+    import torch
+    xe = torch.cat([x, torch.zeros(1, x.shape[1], dtype=x.dtype)], dim=0)
+    return xe[inds[:, 0].long()]

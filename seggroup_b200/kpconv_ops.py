@@ -156,6 +156,77 @@ def KPConv(query_points, support_points, neighbors_indices, features, K_values, 
     return KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent, KP_influence, aggregation_mode)
 
 
+# ------------------------------------------------------------------------------------------------ a21
+def _inds(inds):
+    if inds.dtype != I32:
+        inds = inds.to(I32)
+    inds = _chk(inds.contiguous(), I32, "inds")
+    if inds.dim() != 2 or inds.shape[1] < 1:
+        raise ValueError("inds must have shape [n2, max_num]")
+    return inds
+
+
+class _IndMaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inds):
+        n1, d = x.shape
+        n2, W = inds.shape
+        out = torch.empty(n2, d, dtype=F32, device=x.device)
+        ws = _ws(_lib.call("sgb_ind_max_pool_ws_bytes", d), x.device)
+        _lib.call("sgb_ind_max_pool_fwd", x, n1, d, inds, n2, W, out, ws, ws.numel(), _stream())
+        ctx.save_for_backward(x, inds, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, inds, out = ctx.saved_tensors
+        n1, d = x.shape
+        n2, W = inds.shape
+        gx = torch.empty_like(x)
+        ws = _ws(_lib.call("sgb_ind_max_pool_ws_bytes", d), x.device)
+        _lib.call("sgb_ind_max_pool_bwd", g.contiguous(), x, n1, d, inds, n2, W, out, gx, ws, ws.numel(), _stream())
+        return gx, None
+
+
+class _ClosestPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inds):
+        n1, d = x.shape
+        n2, W = inds.shape
+        out = torch.empty(n2, d, dtype=F32, device=x.device)
+        _lib.call("sgb_closest_pool_fwd", x, n1, d, inds, n2, W, out, _stream())
+        ctx.save_for_backward(inds)
+        ctx.shape = (n1, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (inds,) = ctx.saved_tensors
+        n1, d = ctx.shape
+        n2, W = inds.shape
+        gx = torch.empty(n1, d, dtype=F32, device=g.device)
+        _lib.call("sgb_closest_pool_bwd", g.contiguous(), n1, d, inds, n2, W, gx, _stream())
+        return gx, None
+
+
+def ind_max_pool(x, inds):
+    """kpconv/models/network_blocks.py:49-66: x [n1,d], inds [n2,max_num] (index n1 = shadow = column minimum of x)
+    -> [n2,d]; differentiable w.r.t. x (tf.reduce_max gradient: ties share equally)."""
+    x = _chk(x.contiguous(), F32, "x")
+    if x.dim() != 2:
+        raise ValueError("x must have shape [n1, d]")
+    return _IndMaxPoolFn.apply(x, _inds(inds))
+
+
+def closest_pool(x, inds):
+    """kpconv/models/network_blocks.py:69-81: x [n1,d], inds [n2,max_num] (only column 0 is used; index n1 = shadow =
+    zeros) -> [n2,d]; differentiable w.r.t. x."""
+    x = _chk(x.contiguous(), F32, "x")
+    if x.dim() != 2:
+        raise ValueError("x must have shape [n1, d]")
+    return _ClosestPoolFn.apply(x, _inds(inds))
+
+
 # ------------------------------------------------------------------------------------------------ B2
 class _GridSubsamplingModule:
     """Stands in for the numpy C-extension `grid_subsampling` (wrapper.cpp): `compute(...)`."""

@@ -189,3 +189,41 @@ def test_kpconv_tensor_core_small_and_unsupported():
         ref = K.kpconv_ops(q, s, nb, feats.double(), kp, kv.double(), 0.08, "linear", "sum", dtype=torch.float64)
         assert out.shape == (n, 32)
         assert float((out.cpu().double() - ref).abs().max()) <= 1e-4 * max(float(ref.abs().max()), 1e-6)
+
+
+@pytest.mark.parametrize("d,W", [(64, 33), (128, 17), (6, 5), (256, 40), (32, 1)])
+def test_ind_max_pool_and_closest_pool(d, W):
+    """a21 (network_blocks.py:49-81): forward bit-exact (max / copy are exact), gradients to 1e-6 (tie shares)."""
+    from oracle import kpconv_oracle as K
+    from seggroup_b200.kpconv_ops import closest_pool, ind_max_pool
+    rng = np.random.default_rng(d * 100 + W)
+    n1, n2 = 5000, 3000
+    x = rng.standard_normal((n1, d)).astype(np.float32)
+    x[rng.integers(0, n1, 200)] = np.round(x[rng.integers(0, n1, 200)], 1)      # ties between rows
+    inds = rng.integers(0, n1, (n2, W)).astype(np.int32)
+    fill = rng.integers(1, W + 1, n2)                                             # neighbour counts, the rest is shadow (= n1)
+    inds[np.arange(W)[None, :] >= fill[:, None]] = n1
+    inds[:7] = n1                                                                  # cells with only shadow entries
+    inds[7:20, 1:] = inds[7:20, :1]                                                # duplicated listings (ties by construction)
+    g = rng.standard_normal((n2, d)).astype(np.float32)
+    for fn, ofn in ((ind_max_pool, K.ind_max_pool), (closest_pool, K.closest_pool)):
+        xc = torch.tensor(x, requires_grad=True)
+        ref = ofn(xc, torch.tensor(inds))
+        ref.backward(torch.tensor(g))
+        xg = cu(x).requires_grad_(True)
+        out = fn(xg, cu(inds))
+        out.backward(cu(g))
+        assert np.array_equal(out.detach().cpu().numpy(), ref.detach().numpy()), fn.__name__
+        err = (xg.grad.cpu() - xc.grad).abs().max().item()
+        assert err <= 1e-5 * max(1.0, xc.grad.abs().max().item()), (fn.__name__, err)
+
+
+def test_ind_max_pool_int64_indices_and_empty():
+    from seggroup_b200.kpconv_ops import closest_pool, ind_max_pool
+    x = torch.randn(100, 8, device="cuda")
+    inds = torch.randint(0, 101, (50, 4), device="cuda")                          # int64 as TF's gather would accept
+    a = ind_max_pool(x, inds)
+    xe = torch.cat([x, x.amin(0, keepdim=True)])
+    assert torch.equal(a, xe[inds].amax(1))
+    assert closest_pool(x, inds[:0]).shape == (0, 8)
+    assert ind_max_pool(x, inds[:0]).shape == (0, 8)

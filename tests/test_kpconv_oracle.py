@@ -77,3 +77,18 @@ def test_kpconv_ops_shapes_and_modes():
     # a row made only of shadow neighbours contributes nothing for 'linear'
     idx[0] = n0
     assert float(K.kpconv_ops(q, s, idx, f, kp, kv, 0.3, "linear", "sum")[0].abs().max()) == 0.0
+
+
+def test_index_pool_oracle_matches_loop_restatement():
+    """a21 oracle vs a plain numpy loop written from network_blocks.py:49-81."""
+    import torch
+    from oracle import kpconv_oracle as K
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((40, 5)).astype(np.float32)
+    inds = rng.integers(0, 41, (25, 6)).astype(np.int32)
+    xe_max = np.concatenate([x, x.min(0, keepdims=True)])
+    xe_zero = np.concatenate([x, np.zeros((1, 5), np.float32)])
+    want_max = np.stack([xe_max[r].max(0) for r in inds])
+    want_closest = np.stack([xe_zero[r[0]] for r in inds])
+    assert np.array_equal(K.ind_max_pool(torch.tensor(x), torch.tensor(inds)).numpy(), want_max)
+    assert np.array_equal(K.closest_pool(torch.tensor(x), torch.tensor(inds)).numpy(), want_closest)
