@@ -29,9 +29,6 @@ segment_pool_fwd_kernel(const float* __restrict__ feat, int C, const int* __rest
     const int p1 = min(p0 + POOL_R, n_members);
     const int c0 = (blockIdx.y * 32 + lane) * VEC;
     const bool active = c0 < C;
-    int seg = sgb_upper_segment(offsets, S, p0);
-    int seg_end = __ldg(offsets + seg + 1);
-
     float best[VEC];
     int best_pos[VEC];
 #pragma unroll
@@ -67,6 +64,10 @@ segment_pool_fwd_kernel(const float* __restrict__ feat, int C, const int* __rest
             }
         }
     }
+    // the segment lookup (a chain of ~log2(S) dependent loads) is issued AFTER the row gathers so that its latency
+    // hides under theirs instead of preceding them
+    int seg = sgb_upper_segment(offsets, S, p0);
+    int seg_end = __ldg(offsets + seg + 1);
 #pragma unroll
     for (int u = 0; u < POOL_R; ++u) {
         const int q = p0 + u;

@@ -99,6 +99,19 @@ def main():
             go = torch.randn(S, C, generator=g).cuda()
             ms, mn = T(lambda: ops.segment_pool_max_bwd(go, arg, N))
             emit(rows, "segment_pool_max_bwd [N,64] (zero-fill + scatter)", N, ms, mn, nbytes=8 * S * C + 4 * N * C, segments=S)
+        if want("pool") and N <= 200000:
+            # the same kernel over a batch of 8 scenes' member lists concatenated (BASELINE configs[1] batch): 8 x more rows per launch
+            B = 8
+            featB = torch.randn(B * N, C, generator=g).cuda()
+            offB = torch.cat([d["seg_off"][:-1] + i * N for i in range(B)] + [torch.tensor([B * N], dtype=torch.int32, device="cuda")]).to(torch.int32)
+            memB = torch.cat([d["seg_members"] + i * N for i in range(B)]).to(torch.int32)
+            ms, mn = T(lambda: ops.segment_pool_max(featB, offB, memB))
+            emit(rows, "segment_pool_max_fwd [8N,64] (a10, 8 scenes in one launch)", B * N, ms, mn, nbytes=B * (4 * N * C + 4 * N + 16 * S * C), segments=B * S)
+            outB, argB = ops.segment_pool_max(featB, offB, memB)
+            goB = torch.randn(B * S, C, generator=g).cuda()
+            ms, mn = T(lambda: ops.segment_pool_max_bwd(goB, argB, B * N))
+            emit(rows, "segment_pool_max_bwd [8N,64] (8 scenes in one launch)", B * N, ms, mn, nbytes=B * (8 * S * C + 4 * N * C), segments=B * S)
+            del featB, outB, argB, goB
         if want("centralize") or want("knn") or want("edgeconv"):
             order = d["seg_members"]
             x9 = ops.centralize(d["data"], order, d["seg_off"])
@@ -131,7 +144,7 @@ def main():
             ms, mn = T(lambda: ops.export_labels(unmap, seg_of_point, L))
             emit(rows, "export_labels (a16)", N, ms, mn, nbytes=8 * N + 4 * N + 12 * N)
         # ---- KPConv operator set on a 4 cm subsample of a noisy-sheet cloud (SURVEY.md 8d config 5 geometry)
-        if want("grid") or want("neighbors") or want("kpconv"):
+        if want("grid") or want("neighbors") or want("kpconv") or want("kppool"):
             pts, lens = synth.make_cloud(5, N)
             P = torch.as_tensor(pts).cuda()
             Lb = torch.as_tensor(lens).to(torch.int32).cuda()
@@ -140,7 +153,7 @@ def main():
         if want("grid"):
             ms, mn = T(lambda: KO.batch_grid_subsampling(P, Lb, 0.04))
             emit(rows, "grid_subsample dl=0.04 (a18, incl. the size read-back)", N, ms, mn, nbytes=12 * N + 12 * M, voxels=M)
-        if want("neighbors") or want("kpconv"):
+        if want("neighbors") or want("kpconv") or want("kppool"):
             nb = KO.batch_ordered_neighbors(sub, sub, sb, sb, 0.10)
             W = nb.shape[1]
         if want("neighbors"):
@@ -174,6 +187,20 @@ def main():
                     out.backward(go, retain_graph=True)
                 ms, mn = T(bwd)
                 emit(rows, "kpconv_bwd %dx%d fp32 SIMT (a20)" % (cin, cout), M, ms, mn, flops=2 * fl, width=Wc)
+        if want("kppool"):
+            # a21: strided-block shortcut pooling on the same geometry: pool the dl=0.04 features onto a dl=0.08 subsample
+            sub2, sb2 = KO.batch_grid_subsampling(sub, sb, 0.08)
+            pool_inds = KO.batch_ordered_neighbors(sub2, sub, sb2, sb, 0.08)
+            M2, Wp = pool_inds.shape
+            for dch in (64, 128):
+                xf = torch.randn(M, dch, generator=g).cuda()
+                ms, mn = T(lambda: KO.ind_max_pool(xf, pool_inds))
+                emit(rows, "ind_max_pool d=%d (a21)" % dch, M, ms, mn, nbytes=4 * M * dch + 4 * M2 * Wp + 4 * M2 * dch, width=Wp, pooled=M2,
+                     note="gathered rows 4*M2*W*d = %d B are L2 traffic" % (4 * M2 * Wp * dch))
+                up_inds = KO.batch_ordered_neighbors(sub, sub2, sb, sb2, 0.08)[:, :1].contiguous()
+                xc = torch.randn(M2, dch, generator=g).cuda()
+                ms, mn = T(lambda: KO.closest_pool(xc, up_inds))
+                emit(rows, "closest_pool d=%d (a21, upsampling)" % dch, M, ms, mn, nbytes=4 * M2 * dch + 4 * M + 4 * M * dch, pooled=M2)
     if args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         json.dump(rows, open(args.out, "w"), indent=1)
