@@ -32,44 +32,108 @@ __global__ void gs_batch_offsets(const int* __restrict__ batches, int B, int N, 
     }
 }
 
-__global__ void __launch_bounds__(256)
-gs_batch_bounds(const float* __restrict__ xyz, const int* __restrict__ boff, float dl, BatchParams* __restrict__ bp, float* __restrict__ minmax /*[B][6] or null*/) {
-    __shared__ float s_mn[8][3], s_mx[8][3];
-    const int b = blockIdx.x;
-    const int lo = boff[b], hi = boff[b + 1];
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+// Bounding boxes of the batch elements, grid-wide: every warp owns BND_PTS consecutive points (coalesced, BND_PTS/32 per
+// lane), keeps a running (min, max) while its points stay inside one batch element and merges through monotone uint keys
+// with atomicMin / atomicMax (order independent -> bit-identical to any sequential min / max).  A second tiny kernel
+// turns the keys into the floats and the voxel-grid parameters.
+constexpr int BND_WARPS = 4;
+constexpr int BND_PTS = 256;        // points per warp
+
+__global__ void gs_bounds_init(unsigned* __restrict__ keys, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 6) keys[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(BND_WARPS * 32)
+gs_bounds_partial(const float* __restrict__ xyz, int N, const int* __restrict__ boff, int B, unsigned* __restrict__ keys /*[B][6]*/) {
+    const int lane = threadIdx.x & 31;
+    const int w0 = (blockIdx.x * BND_WARPS + (threadIdx.x >> 5)) * BND_PTS;
+    if (w0 >= N) return;
+    const int w1 = min(w0 + BND_PTS, N);
+    float v[BND_PTS / 32][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { const float v = __ldg(xyz + (size_t)i * 3 + d); mn[d] = fminf(mn[d], v); mx[d] = fmaxf(mx[d], v); }
+    for (int k = 0; k < BND_PTS / 32; ++k) {
+        const int i = w0 + k * 32 + lane;
+        if (i < w1) { v[k][0] = __ldg(xyz + (size_t)i * 3); v[k][1] = __ldg(xyz + (size_t)i * 3 + 1); v[k][2] = __ldg(xyz + (size_t)i * 3 + 2); }
     }
+    // batch element of the warp's first point (after the loads are in flight); the warp walks forward from there
+    int b = B > 1 ? sgb_upper_segment(boff, B, w0) : 0;
+    int b_end = __ldg(boff + b + 1);
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    auto flush = [&](int bb) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[d] = fminf(mn[d], __shfl_xor_sync(SGB_FULL_MASK, mn[d], o));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(SGB_FULL_MASK, mx[d], o));
+            }
+        }
+        const float lo = lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]);
+        const float hi = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]);
+        if (lane < 3 && lo <= hi) {                                    // nothing accumulated: +inf > -inf
+            atomicMin(keys + bb * 6 + lane, sgb_float_key(lo));
+            atomicMax(keys + bb * 6 + 3 + lane, sgb_float_key(hi));
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { mn[d] = INFINITY; mx[d] = -INFINITY; }
+    };
+#pragma unroll
+    for (int k = 0; k < BND_PTS / 32; ++k) {
+        const int i0 = w0 + k * 32;
+        if (i0 >= w1) break;                                           // warp-uniform
+        const int i = i0 + lane;
+        if (min(i0 + 32, w1) <= b_end) {                               // the whole 32-point row is inside batch element b
+            if (i < w1) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], v[k][d]); mx[d] = fmaxf(mx[d], v[k][d]); }
+            }
+        } else {                                                       // a row straddling batch elements: one element at a time
+            int lo = i0;
+            while (lo < min(i0 + 32, w1)) {
+                while (lo >= b_end) { flush(b); ++b; b_end = __ldg(boff + b + 1); }
+                const int hi = min(min(i0 + 32, w1), b_end);
+                if (i >= lo && i < hi) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], v[k][d]); mx[d] = fmaxf(mx[d], v[k][d]); }
+                }
+                lo = hi;
+            }
+        }
+    }
+    flush(b);
+}
+
+__global__ void gs_bounds_finish(const unsigned* __restrict__ keys, const int* __restrict__ boff, int B, float dl,
+                                 BatchParams* __restrict__ bp, float* __restrict__ minmax /*[B][6] or null*/) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int lo = boff[b], hi = boff[b + 1];
+    float mn[3], mx[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(SGB_FULL_MASK, mn[d], o));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(SGB_FULL_MASK, mx[d], o));
-        }
+        mn[d] = hi > lo ? sgb_key_float(keys[b * 6 + d]) : INFINITY;
+        mx[d] = hi > lo ? sgb_key_float(keys[b * 6 + 3 + d]) : -INFINITY;
     }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { s_mn[threadIdx.x >> 5][d] = mn[d]; s_mx[threadIdx.x >> 5][d] = mx[d]; }
+    if (minmax) for (int d = 0; d < 3; ++d) { minmax[b * 6 + d] = mn[d]; minmax[b * 6 + 3 + d] = mx[d]; }
+    if (bp) {
+        const float inv = __fdiv_rn(1.f, dl);                       // `1/sampleDl`
+        BatchParams p;
+        p.ox = __fmul_rn(floorf(__fmul_rn(mn[0], inv)), dl);
+        p.oy = __fmul_rn(floorf(__fmul_rn(mn[1], inv)), dl);
+        p.oz = __fmul_rn(floorf(__fmul_rn(mn[2], inv)), dl);
+        p.nx = hi > lo ? (unsigned long long)floorf(__fdiv_rn(__fsub_rn(mx[0], p.ox), dl)) + 1ull : 1ull;
+        p.ny = hi > lo ? (unsigned long long)floorf(__fdiv_rn(__fsub_rn(mx[1], p.oy), dl)) + 1ull : 1ull;
+        bp[b] = p;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
-            for (int d = 0; d < 3; ++d) { s_mn[0][d] = fminf(s_mn[0][d], s_mn[w][d]); s_mx[0][d] = fmaxf(s_mx[0][d], s_mx[w][d]); }
-        if (minmax) for (int d = 0; d < 3; ++d) { minmax[b * 6 + d] = s_mn[0][d]; minmax[b * 6 + 3 + d] = s_mx[0][d]; }
-        if (bp) {
-            const float inv = __fdiv_rn(1.f, dl);                       // `1/sampleDl`
-            BatchParams p;
-            p.ox = __fmul_rn(floorf(__fmul_rn(s_mn[0][0], inv)), dl);
-            p.oy = __fmul_rn(floorf(__fmul_rn(s_mn[0][1], inv)), dl);
-            p.oz = __fmul_rn(floorf(__fmul_rn(s_mn[0][2], inv)), dl);
-            p.nx = hi > lo ? (unsigned long long)floorf(__fdiv_rn(__fsub_rn(s_mx[0][0], p.ox), dl)) + 1ull : 1ull;
-            p.ny = hi > lo ? (unsigned long long)floorf(__fdiv_rn(__fsub_rn(s_mx[0][1], p.oy), dl)) + 1ull : 1ull;
-            bp[b] = p;
-        }
-    }
+}
+
+int bounds_launch(const float* xyz, int N, const int* boff, int B, float dl, BatchParams* bp, float* minmax, unsigned* keys, cudaStream_t st) {
+    gs_bounds_init<<<sgb_div_up(B * 6, 256), 256, 0, st>>>(keys, B); SGB_COUNT_LAUNCH();
+    gs_bounds_partial<<<sgb_div_up(N, BND_WARPS * BND_PTS), BND_WARPS * 32, 0, st>>>(xyz, N, boff, B, keys); SGB_COUNT_LAUNCH();
+    gs_bounds_finish<<<sgb_div_up(B, 128), 128, 0, st>>>(keys, boff, B, dl, bp, minmax); SGB_COUNT_LAUNCH();
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
 }
 
 __device__ __forceinline__ unsigned hash64(unsigned long long k) {
@@ -213,6 +277,7 @@ extern "C" size_t sgb_grid_subsample_ws_bytes(int N, int B) {
     b += 9 * align256((size_t)(N + 2) * 4);                                 // slot, flag, rank, vcount, vfirst, voff, cursor, list, big/scratch
     b += align256((size_t)(N + 2) * 4);
     b += align256((size_t)(B + 1) * 4) + align256((size_t)B * sizeof(BatchParams)) + 256;
+    b += align256((size_t)B * 24);                                          // bounding-box keys
     b += sgb_scan_ws_bytes(N + 1) + 256;
     return b;
 }
@@ -251,6 +316,7 @@ extern "C" int sgb_grid_subsample(const float* xyz, const float* feat, const int
     int* boff = (int*)take((size_t)(B + 1) * 4);
     BatchParams* bp = (BatchParams*)take((size_t)B * sizeof(BatchParams));
     int* nbig = (int*)take(256);
+    unsigned* bkeys = (unsigned*)take((size_t)B * 24);
     void* scan_ws = w;
     const size_t scan_bytes = sgb_scan_ws_bytes(N + 1);
 
@@ -264,7 +330,7 @@ extern "C" int sgb_grid_subsample(const float* xyz, const float* feat, const int
     const int g = sgb_div_up(N, 256);
     int rc;
     { gs_batch_offsets<<<1, 32, 0, st>>>(batches, B, N, boff, status); SGB_COUNT_LAUNCH(); }
-    { gs_batch_bounds<<<B, 256, 0, st>>>(xyz, boff, dl, bp, nullptr); SGB_COUNT_LAUNCH(); }
+    if ((rc = bounds_launch(xyz, N, boff, B, dl, bp, nullptr, bkeys, st))) return rc;
     { gs_insert<<<g, 256, 0, st>>>(xyz, N, boff, B, bp, dl, tkeys, tfirst, tcount, T - 1, slot_of, status); SGB_COUNT_LAUNCH(); }
     { gs_flag_first<<<g, 256, 0, st>>>(slot_of, tfirst, N, flag); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(flag, rank, N, scan_ws, scan_bytes, st))) return rc;
@@ -285,7 +351,6 @@ extern "C" int sgb_batch_bounds(const float* xyz, int N, const int* batches, int
     if (N <= 0 || B <= 0 || !xyz || !minmax || !boff_out || !status) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     { gs_batch_offsets<<<1, 32, 0, st>>>(batches, B, N, boff_out, status); SGB_COUNT_LAUNCH(); }
-    { gs_batch_bounds<<<B, 256, 0, st>>>(xyz, boff_out, 1.f, nullptr, minmax); SGB_COUNT_LAUNCH(); }
-    SGB_CHECK_LAUNCH();
-    return SGB_OK;
+    // the uint keys are accumulated in place: minmax [B][6] is 4-byte words either way, decoded by the finish kernel
+    return bounds_launch(xyz, N, boff_out, B, 1.f, nullptr, minmax, reinterpret_cast<unsigned*>(minmax), st);
 }
