@@ -192,7 +192,14 @@ __global__ void centralize_kernel(const float* __restrict__ data6, int N, const 
     float* o = x9 + (size_t)pid * 9;
     const float2 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
     const float x = a.x, y = a.y, z = b.x;
-    const int c = sgb_upper_segment(cl_off, S, q);      // dependent-load chain: issued after the gathers, hides under them
+    // cluster of position q: ONE binary search per warp (lane 0's position, broadcast), then a short forward walk — the
+    // per-thread search was 12 dependent loads per point and throttled the load/store unit (ncu: lg_throttle)
+    int c = 0;
+    {
+        const int q0 = q - (threadIdx.x & 31);
+        c = sgb_upper_segment(cl_off, S, q0);
+        while (c + 1 < S && q >= __ldg(cl_off + c + 1)) ++c;
+    }
     o[0] = x; o[1] = y; o[2] = z; o[3] = b.y; o[4] = cc.x; o[5] = cc.y;
     o[6] = x - __ldg(mean + c * 3); o[7] = y - __ldg(mean + c * 3 + 1); o[8] = z - __ldg(mean + c * 3 + 2);
 }

@@ -68,6 +68,37 @@ segment_pool_fwd_kernel(const float* __restrict__ feat, int C, const int* __rest
     // hides under theirs instead of preceding them
     int seg = sgb_upper_segment(offsets, S, p0);
     int seg_end = __ldg(offsets + seg + 1);
+    if (p1 - p0 == POOL_R && seg_end >= p1) {
+        // Fast path (most warps: segments are ~150 rows, a warp owns 32): all rows in ONE segment.  Two cheap passes over
+        // the registers instead of a compare-and-track per element: max (FMNMX) + NaN probe (a sum is NaN iff a term is,
+        // or inf - inf: either way the generic loop below takes over), then the FIRST position attaining the max.
+        if (active) {
+            float m[VEC], sum[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { m[v] = val[0][v]; sum[v] = val[0][v]; }
+#pragma unroll
+            for (int u = 1; u < POOL_R; ++u) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { m[v] = fmaxf(m[v], val[u][v]); sum[v] += val[u][v]; }
+            }
+            bool clean = true;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) clean = clean && (sum[v] == sum[v]);
+            if (clean) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    int pos = POOL_R - 1;
+#pragma unroll
+                    for (int u = POOL_R - 2; u >= 0; --u) pos = (val[u][v] == m[v]) ? u : pos;
+                    best[v] = m[v]; best_pos[v] = p0 + pos;
+                }
+                flush(seg);
+                return;
+            }
+        } else {
+            return;
+        }
+    }
 #pragma unroll
     for (int u = 0; u < POOL_R; ++u) {
         const int q = p0 + u;

@@ -20,6 +20,12 @@ full)     timeout 900 ncu --set full --clock-control none --import-source on \
           timeout 900 ncu --set full --clock-control none --import-source on \
             -k regex:'bwd_dense_kernel|group_nearby_kernel|unlabeled_union_kernel|bwd_sparse_kernel' \
             -c 6 -f -o $O/${TAG}_full_train python tools/profile_scene.py 150000 train > $O/${TAG}_full_train.log 2>&1 ;;
+gridrn)   timeout 600 python tools/bench_kernels.py --only pool,centralize,grid,neighbors,kppool --out $O/${TAG}_kernels_gather.json > $O/${TAG}_kernels_gather.log 2>&1; tail -3 $O/${TAG}_kernels_gather.log
+          timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_gridrn.csv \
+            python tools/bench_kernels.py --points 150000 --reps 1 --warm 1 --only grid,neighbors > $O/${TAG}_launches_gridrn.log 2>&1
+          timeout 900 ncu --set full --clock-control none --import-source on \
+            -k regex:'segment_pool_fwd_kernel|rn_search|rn_fill|centralize_kernel|ind_max_pool_fwd|gs_insert|gs_reduce_points|gs_sort_small' \
+            -c 12 -f -o $O/${TAG}_full_gather python tools/bench_kernels.py --points 500000 --reps 1 --warm 0 --only pool,centralize,grid,neighbors,kppool > $O/${TAG}_full_gather.log 2>&1 ;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $O/${TAG}_launches.csv \
             python bench.py --steps 1 --warmup 1 --scenes 1 --points 150000 --no-cpu-baseline --streams 1 > $O/${TAG}_launches.log 2>&1 ;;
 esac
