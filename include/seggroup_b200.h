@@ -110,7 +110,8 @@ int sgb_cluster_cloud_transform(const float* data6, const int* cloud_idx, int S,
 /* a8  replaces seggroup/model.py:429-436 `combine_centralized_pointcloud`:
  * x9[p] = (data6[p], xyz[p] - mean xyz of p's cluster). */
 int sgb_centralize(const float* data6, int N, const int* order, const int* cl_off, int S, float* x9,
-                   float* mean_ws /* [S,3] scratch, holds the cluster means on return */, void* stream);
+                   void* sum_ws /* 24*S bytes of scratch, 8-byte aligned: 64-bit fixed-point coordinate sums per cluster */,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a5/a6  structural-layer MLP on the 64-point segment clouds
@@ -240,7 +241,8 @@ int sgb_group_nearby(const int* adj, int A, const int* roots_cur, const float* d
                      int sweep_cap, int* status, void* stream);
 
 /* a14  one iteration of phase A of seggroup/model.py:439-470 `group_unlabeled_clusters`: row arg-min of
- * the dense distance matrix (fill 1000, first minimum), then union of every unlabeled cluster into it. */
+ * the dense distance matrix (fill 1000, first minimum), then union of every unlabeled cluster into it.
+ * amin_ws: 2*S ints of scratch (arg-min row, then the in-order list of still unlabeled clusters). */
 int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
                              const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream);
 

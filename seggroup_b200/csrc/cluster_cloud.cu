@@ -158,32 +158,47 @@ __global__ void cluster_cloud_transform_kernel(const float* __restrict__ data6, 
     }
 }
 
-// one warp per R positions, running sums flushed at cluster boundaries would need atomics; clusters can be
-// huge, so: pass 1 = per-cluster mean by one CTA per cluster (fp64 accumulate), pass 2 = per point write.
+// Cluster means.  Clusters range from 20 points to a whole room (the late levels: a few dozen clusters of thousands of
+// points), so one CTA per cluster starves the GPU exactly when the clusters are large.  Instead every warp takes 32
+// consecutive positions, converts xyz to 64-bit fixed point (2^-36 m: |x| < 128 m and < 2^20 points per cluster keep the
+// sum inside int64) and adds warp-reduced sums to its cluster with integer atomics.  Integer addition is associative, so
+// the sums -- and the fp32 means rounded from them -- do not depend on the order the warps run in (deterministic), and the
+// mean carries ~1e-11 m of quantisation error, far below the fp32 ulp of a coordinate.
+constexpr double FIX_SCALE = 68719476736.0;           // 2^36
 __global__ void __launch_bounds__(256)
-cluster_mean_kernel(const float* __restrict__ data6, const int* __restrict__ order, const int* __restrict__ cl_off,
-                    float* __restrict__ mean /*[S,3]*/) {
-    __shared__ double s_acc[8][3];
-    const int c = blockIdx.x;
-    const int lo = cl_off[c], hi = cl_off[c + 1];
-    double ax = 0, ay = 0, az = 0;
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const float* p = data6 + (size_t)__ldg(order + i) * 6;
-        ax += (double)__ldg(p); ay += (double)__ldg(p + 1); az += (double)__ldg(p + 2);
+cluster_sum_kernel(const float* __restrict__ data6, int N, const int* __restrict__ order, const int* __restrict__ cl_off, int S,
+                   long long* __restrict__ sums /*[S,3], zeroed*/) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int q0 = q - lane;
+    if (q0 >= N) return;
+    const bool valid = q < N;
+    long long fx = 0, fy = 0, fz = 0;
+    if (valid) {
+        const float2* p = reinterpret_cast<const float2*>(data6 + (size_t)__ldg(order + q) * 6);
+        const float2 a = __ldg(p);
+        const float z = __ldg(reinterpret_cast<const float*>(p + 1));
+        fx = __double2ll_rn((double)a.x * FIX_SCALE); fy = __double2ll_rn((double)a.y * FIX_SCALE); fz = __double2ll_rn((double)z * FIX_SCALE);
     }
-    ax = sgb_warp_sum(ax); ay = sgb_warp_sum(ay); az = sgb_warp_sum(az);
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { s_acc[w][0] = ax; s_acc[w][1] = ay; s_acc[w][2] = az; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        double t = 0;
-        for (int i = 0; i < 8; ++i) t += s_acc[i][threadIdx.x];
-        mean[(size_t)c * 3 + threadIdx.x] = (float)(t / (double)(hi - lo));
+    int c = sgb_upper_segment(cl_off, S, q0);         // one search per warp, then a short forward walk
+    const int c_first_end = __ldg(cl_off + c + 1);
+    if (c_first_end >= min(q0 + 32, N)) {             // the whole warp lies in one cluster (the common case)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(SGB_FULL_MASK, fx, o); fy += __shfl_xor_sync(SGB_FULL_MASK, fy, o); fz += __shfl_xor_sync(SGB_FULL_MASK, fz, o);
+        }
+        if (lane < 3) atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)c * 3 + lane),
+                                (unsigned long long)(lane == 0 ? fx : lane == 1 ? fy : fz));
+    } else if (valid) {
+        while (c + 1 < S && q >= __ldg(cl_off + c + 1)) ++c;
+        atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)c * 3 + 0), (unsigned long long)fx);
+        atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)c * 3 + 1), (unsigned long long)fy);
+        atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)c * 3 + 2), (unsigned long long)fz);
     }
 }
 
 __global__ void centralize_kernel(const float* __restrict__ data6, int N, const int* __restrict__ order,
-                                  const int* __restrict__ cl_off, int S, const float* __restrict__ mean,
+                                  const int* __restrict__ cl_off, int S, const long long* __restrict__ sums,
                                   float* __restrict__ x9) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= N) return;
@@ -201,7 +216,10 @@ __global__ void centralize_kernel(const float* __restrict__ data6, int N, const 
         while (c + 1 < S && q >= __ldg(cl_off + c + 1)) ++c;
     }
     o[0] = x; o[1] = y; o[2] = z; o[3] = b.y; o[4] = cc.x; o[5] = cc.y;
-    o[6] = x - __ldg(mean + c * 3); o[7] = y - __ldg(mean + c * 3 + 1); o[8] = z - __ldg(mean + c * 3 + 2);
+    const double inv = 1.0 / (FIX_SCALE * (double)(__ldg(cl_off + c + 1) - __ldg(cl_off + c)));
+    o[6] = x - (float)((double)__ldg(sums + (size_t)c * 3) * inv);
+    o[7] = y - (float)((double)__ldg(sums + (size_t)c * 3 + 1) * inv);
+    o[8] = z - (float)((double)__ldg(sums + (size_t)c * 3 + 2) * inv);
 }
 }  // namespace
 
@@ -230,13 +248,15 @@ extern "C" int sgb_cluster_cloud_transform(const float* data6, const int* cloud_
 }
 
 extern "C" int sgb_centralize(const float* data6, int N, const int* order, const int* cl_off, int S, float* x9,
-                              float* mean_ws /*[S,3]*/, void* stream) {
+                              void* sum_ws /*24*S bytes*/, void* stream) {
     if (N < 0 || S < 0) return SGB_ERR_INVALID;
     if (N == 0 || S == 0) return SGB_OK;
-    if (!data6 || !order || !cl_off || !x9 || !mean_ws) return SGB_ERR_INVALID;
+    if (!data6 || !order || !cl_off || !x9 || !sum_ws) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    { cluster_mean_kernel<<<S, 256, 0, st>>>(data6, order, cl_off, mean_ws); SGB_COUNT_LAUNCH(); }
-    { centralize_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, mean_ws, x9); SGB_COUNT_LAUNCH(); }
+    long long* sums = (long long*)sum_ws;
+    SGB_CUDA(cudaMemsetAsync(sums, 0, (size_t)S * 3 * sizeof(long long), st));
+    { cluster_sum_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, sums); SGB_COUNT_LAUNCH(); }
+    { centralize_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, sums, x9); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

@@ -52,9 +52,13 @@ inline cudaError_t sgb_opt_in_smem() {
 #define SGB_FULL_MASK 0xffffffffu
 
 // Monotone map float -> uint32 (a < b  <=>  key(a) < key(b); +NaN sorts above +inf).
+// The sign-bit OR is written in PTX: as C, the compiler folds `bits | 0x80000000` on a float into -|f| (FADD with
+// modifiers), which canonicalises a NaN to 0x7fffffff and drops it to the BOTTOM of the key order.
 __device__ __forceinline__ uint32_t sgb_float_key(float f) {
-    uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const uint32_t u = __float_as_uint(f);
+    uint32_t pos;
+    asm("or.b32 %0, %1, 0x80000000;" : "=r"(pos) : "r"(u));
+    return (u & 0x80000000u) ? ~u : pos;
 }
 __device__ __forceinline__ float sgb_key_float(uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;

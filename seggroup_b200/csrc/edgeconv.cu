@@ -113,6 +113,113 @@ gram1_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, c
     }
 }
 
+// Point-per-lane variant of pass A (the one that runs).  gram1_kernel above stages every edge in shared memory and pays two
+// LDS per FMA for all 189 entries; but an edge feature is e_k = (d_k, c) with d_k = x_j - x_i and c = x_i - centre CONSTANT
+// over the 20 edges of a point, so per point
+//     sum_k e_k e_k^T = [ sum_k d_k d_k^T   (sum_k d_k) c^T ]      sum_k e_k = ( sum_k d_k, 20 c )
+//                       [       .               20 c c^T    ]
+// Only the 45 entries of the d d^T block are per-edge work.  A lane owns one point: it gathers its 20 neighbour rows
+// (48-byte padded rows, three 16-byte loads each, several neighbours in flight), keeps d d^T and sum d in registers, and
+// the 189 per-point values are summed over the warp's 32 points by shuffles; lane n % 32 keeps entry n in fp64.
+__global__ void __launch_bounds__(WARPS * 32)
+gram1_pt_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ ctr,
+                double* __restrict__ part /*[grid][NE1]*/) {
+    __shared__ double s_red[WARPS][NE1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float c9[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) c9[t] = __ldg(ctr + 9 + t);
+    double acc[NE1_PER_LANE];
+#pragma unroll
+    for (int m = 0; m < NE1_PER_LANE; ++m) acc[m] = 0.0;
+
+    for (int p0 = (blockIdx.x * WARPS + warp) * 32; p0 < N; p0 += gridDim.x * WARPS * 32) {
+        const int p = p0 + lane;
+        const bool valid = p < N;
+        float xi[9], c[9], s[9], dd[45];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { xi[t] = 0.f; c[t] = 0.f; s[t] = 0.f; }
+#pragma unroll
+        for (int n = 0; n < 45; ++n) dd[n] = 0.f;
+        if (valid) {
+            const float4* r = reinterpret_cast<const float4*>(x12 + (size_t)p * 12);
+            const float4 a0 = __ldg(r), a1 = __ldg(r + 1), a2 = __ldg(r + 2);
+            xi[0] = a0.x; xi[1] = a0.y; xi[2] = a0.z; xi[3] = a0.w; xi[4] = a1.x; xi[5] = a1.y; xi[6] = a1.z; xi[7] = a1.w; xi[8] = a2.x;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) c[t] = xi[t] - c9[t];
+            const int4* kr = reinterpret_cast<const int4*>(knn + (size_t)p * KNN);      // 80-byte rows: 16-byte aligned
+#pragma unroll 1
+            for (int k4 = 0; k4 < KNN / 4; ++k4) {
+                const int4 jj = __ldg(kr + k4);
+                const int js[4] = {jj.x, jj.y, jj.z, jj.w};
+                float4 b0[4], b1[4], b2[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                                           // 12 independent 16-byte gathers in flight
+                    const float4* rj = reinterpret_cast<const float4*>(x12 + (size_t)js[q] * 12);
+                    b0[q] = __ldg(rj); b1[q] = __ldg(rj + 1); b2[q] = __ldg(rj + 2);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float d[9] = {b0[q].x - xi[0], b0[q].y - xi[1], b0[q].z - xi[2], b0[q].w - xi[3], b1[q].x - xi[4],
+                                        b1[q].y - xi[5], b1[q].z - xi[6], b1[q].w - xi[7], b2[q].x - xi[8]};
+                    int n = 0;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        s[t] += d[t];
+#pragma unroll
+                        for (int u = t; u < 9; ++u) { dd[n] = fmaf(d[t], d[u], dd[n]); ++n; }
+                    }
+                }
+            }
+        }
+        // the 189 per-point values in moment order (entry n < 18: sum e_n; then pairs (t, u), t <= u, row by row), summed
+        // over the 32 points of the warp; lane n % 32 accumulates entry n
+        int n = 0;
+        auto emit = [&](float v) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SGB_FULL_MASK, v, o);
+            if ((n & 31) == lane) acc[n >> 5] += (double)v;
+            ++n;
+        };
+#pragma unroll
+        for (int t = 0; t < 9; ++t) emit(s[t]);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) emit(valid ? (float)KNN * c[t] : 0.f);
+        {
+            int q = 0;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                for (int u = t; u < 9; ++u) emit(dd[q++]);
+#pragma unroll
+                for (int u = 0; u < 9; ++u) emit(s[t] * c[u]);
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                for (int u = t; u < 9; ++u) emit((float)KNN * (c[t] * c[u]));
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NE1_PER_LANE; ++m) { const int n = lane + 32 * m; if (n < NE1) s_red[warp][n] = acc[m]; }
+    __syncthreads();
+    for (int n = threadIdx.x; n < NE1; n += blockDim.x) {
+        double sum = 0;
+        for (int w = 0; w < WARPS; ++w) sum += s_red[w][n];
+        part[(size_t)blockIdx.x * NE1 + n] = sum;
+    }
+}
+
+// x9 [N,9] -> x12 [N,12] (48-byte rows: three aligned 16-byte loads per gathered row)
+__global__ void pad_rows12_kernel(const float* __restrict__ x9, long long n12, float* __restrict__ x12) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n12) return;
+    const long long p = i / 12;
+    const int q = (int)(i % 12);
+    x12[i] = q < 9 ? __ldg(x9 + p * 9 + q) : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------
 // pass A2 (MLP3): moments of the hidden activations h = lrelu(BN1(W1 e)):  H = sum h h^T, t = sum h
 // lane owns rows c0, c0+1 of H (128 fp32 accumulators) + its two entries of t.
@@ -338,6 +445,8 @@ extern "C" size_t sgb_edgeconv_ws_bytes(int N, int two_layer) {
     size_t b = 128 + 256 * 9 * 8 + 192 * 8 + g * NE1 * 8;
     if (two_layer) b += (size_t)(148 * 2) * NE2 * 8;
     if (two_layer) { b = (b + 255) & ~(size_t)255; b += sgb_ec2_tc_ws_bytes(N); }
+    b = (b + 255) & ~(size_t)255;
+    b += (size_t)(N > 0 ? N : 0) * 48;                 // x12: 48-byte padded rows for the 16-byte gathers
     return b;
 }
 
@@ -366,16 +475,21 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     const int mb = N < 256 * 256 ? sgb_div_up(N, 256) : 256;
     { x9_mean_partial<<<mb, 256, 0, st>>>(x9, N, mpart); SGB_COUNT_LAUNCH(); }
     { x9_mean_finish<<<1, 32, 0, st>>>(mpart, mb, N, ctr); SGB_COUNT_LAUNCH(); }
-    { gram1_kernel<<<grid, WARPS * 32, 0, st>>>(x9, knn, N, ctr, g1part); SGB_COUNT_LAUNCH(); }
+    float* x12 = (float*)(w8 + (((sgb_edgeconv_ws_bytes(N, two_layer) - (size_t)N * 48)) & ~(size_t)255));
+    { pad_rows12_kernel<<<sgb_div_up((long long)N * 12, 256), 256, 0, st>>>(x9, (long long)N * 12, x12); SGB_COUNT_LAUNCH(); }
+    {
+        const int gp = sgb_div_up(N, WARPS * 32) < 148 * 2 ? sgb_div_up(N, WARPS * 32) : 148 * 2;    // <= grid: the partials fit
+        gram1_pt_kernel<<<gp, WARPS * 32, 0, st>>>(x12, knn, N, ctr, g1part); SGB_COUNT_LAUNCH();
+        sgb_bn::reduce_partials(g1part, gp, NE1, mom1 ? mom1 : g1red, st);
+    }
     double* m1red = mom1 ? mom1 : g1red;
-    sgb_bn::reduce_partials(g1part, grid, NE1, m1red, st);
     { bn1_finalize_kernel<CIN><<<1, 64, 0, st>>>(m1red, 1, M, W1, ctr, gamma1, beta1, stats1, var1, nullptr); SGB_COUNT_LAUNCH(); }
     if (ctr_out) SGB_CUDA(cudaMemcpyAsync(ctr_out, ctr, 18 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (two_layer) {
         // second layer on the tcgen05 tensor cores (mom2 != NULL: also the hidden-layer second moments for the backward)
         size_t off = 128 + 256 * 9 * 8 + 192 * 8 + (size_t)grid * NE1 * 8 + (size_t)(148 * 2) * NE2 * 8;
         off = (off + 255) & ~(size_t)255;
-        return sgb_ec2_tc_forward(x9, knn, N, W1, stats1, W2, gamma2, beta2, out, argk, stats2, var2, mom2, w8 + off, st);
+        return sgb_ec2_tc_forward(x12, knn, N, W1, stats1, W2, gamma2, beta2, out, argk, stats2, var2, mom2, w8 + off, st);
     }
     if (two_layer) {
         const int g2 = grid < 148 * 2 ? grid : 148 * 2;

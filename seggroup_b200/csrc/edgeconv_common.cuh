@@ -51,6 +51,6 @@ __device__ __forceinline__ void conv1(const float (*se)[CINP], int k, const floa
 
 // tensor-core second layer of MLP3 (edgeconv_tc.cu)
 size_t sgb_ec2_tc_ws_bytes(int N);
-int sgb_ec2_tc_forward(const float* x9, const int* knn, int N, const float* W1, const float* stats1, const float* W2,
+int sgb_ec2_tc_forward(const float* x12, const int* knn, int N, const float* W1, const float* stats1, const float* W2,
                        const float* gamma2, const float* beta2, float* out, unsigned char* argk, float* stats2, float* var2,
                        double* mom2, void* ws, cudaStream_t st);

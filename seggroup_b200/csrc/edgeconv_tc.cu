@@ -348,15 +348,6 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
     if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// x9 [N,9] -> x12 [N,12] (48-byte rows: three aligned 16-byte loads per gathered row)
-__global__ void pad_rows_kernel(const float* __restrict__ x9, long long n12, float* __restrict__ x12) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n12) return;
-    const long long p = i / 12;
-    const int q = (int)(i % 12);
-    x12[i] = q < 9 ? __ldg(x9 + p * 9 + q) : 0.f;
-}
-
 // BN2 statistics from the reduced sums (sum z [64], sum z^2 [64]); same stats layout as the SIMT path
 __global__ void __launch_bounds__(64)
 bn2_from_sums_kernel(const double* __restrict__ sums, double M, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -427,18 +418,18 @@ inline int tc_nflush(int N, int grid) {                 // Gram segments per CTA
 }
 }  // namespace sgb_ectc
 
-// workspace: partial sums [148][128] f64, reduced sums [128] f64, reduced Gram [128*GN] f64, x12 [N,12], zmax, zmin [N,64] f32,
+// workspace: partial sums [148][128] f64, reduced sums [128] f64, reduced Gram [128*GN] f64, zmax, zmin [N,64] f32,
 // kk [N,64] u16, Gram slots [148][nflush][128*GN] f32
 size_t sgb_ec2_tc_ws_bytes(int N) {
     using namespace sgb_ectc;
     const int nf = tc_nflush(N, 148) + 1;
-    return (size_t)(148 + 1) * 128 * 8 + (size_t)128 * GN * 8 + (size_t)N * 48 + (size_t)N * 64 * (4 + 4 + 2) +
+    return (size_t)(148 + 1) * 128 * 8 + (size_t)128 * GN * 8 + (size_t)N * 64 * (4 + 4 + 2) +
            (size_t)148 * nf * 128 * GN * 4 + 1024;
 }
 
 // second layer of MLP3 on the tensor cores: stats2/var2 and out/argk as sgb_edgeconv_fwd produces them; mom2 (optional)
 // = second moments of the hidden activations for the backward pass
-int sgb_ec2_tc_forward(const float* x9, const int* knn, int N, const float* W1, const float* stats1, const float* W2,
+int sgb_ec2_tc_forward(const float* x12 /*[N,12]: 48-byte padded rows*/, const int* knn, int N, const float* W1, const float* stats1, const float* W2,
                        const float* gamma2, const float* beta2, float* out, unsigned char* argk, float* stats2, float* var2,
                        double* mom2, void* ws, cudaStream_t st) {
     using namespace sgb_ectc;
@@ -446,15 +437,13 @@ int sgb_ec2_tc_forward(const float* x9, const int* knn, int N, const float* W1, 
     double* part = (double*)w8;
     double* sums = part + 148 * 128;
     double* gred = sums + 128;
-    float* x12 = (float*)(gred + 128 * GN);
-    float* zmax = x12 + (size_t)N * 12;
+    float* zmax = (float*)(gred + 128 * GN);
     float* zmin = zmax + (size_t)N * 64;
     unsigned short* kk = (unsigned short*)(zmin + (size_t)N * 64);
     float* gslots = (float*)(((uintptr_t)(kk + (size_t)N * 64) + 255) & ~(uintptr_t)255);
     const bool gram = mom2 != nullptr;
     const int grid = tc_grid(N, gram ? Cfg<true>::TE : Cfg<false>::TE);
     const int nflush = gram ? tc_nflush(N, grid) : 0;
-    { pad_rows_kernel<<<sgb_div_up((long long)N * 12, 256), 256, 0, st>>>(x9, (long long)N * 12, x12); SGB_COUNT_LAUNCH(); }
     if (gram) {
         const size_t smem = Cfg<true>::total + 1024;
         SGB_CUDA(cudaMemsetAsync(gslots, 0, (size_t)grid * nflush * 128 * GN * 4, st));

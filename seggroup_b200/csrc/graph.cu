@@ -377,12 +377,42 @@ __global__ void gcn_agg_bwd_s_kernel(const float* __restrict__ dAX, const float*
 constexpr int GN_THREADS = 256;
 constexpr int GN_CHUNK = 2048;
 
+// Ordered block-wide compaction: the threads hold one (keep, ru, rv) triple each for 256 consecutive edges; the kept pairs
+// are appended to s_ru / s_rv at `base` in edge order.  Returns the new fill count (block-uniform).
+__device__ __forceinline__ int gn_append(bool keep, int ru, int rv, int* s_ru, int* s_rv, int base, int* s_wcount) {
+    const unsigned bal = __ballot_sync(SGB_FULL_MASK, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_wcount[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < GN_THREADS / 32; ++w) {
+        const int c = s_wcount[w];
+        before += w < warp ? c : 0;
+        total += c;
+    }
+    if (keep) {
+        const int o = base + before + __popc(bal & ((1u << lane) - 1u));
+        s_ru[o] = ru; s_rv[o] = rv;
+    }
+    __syncthreads();
+    return base + total;
+}
+
+// The unions are order dependent (label veto, root choice, member-list order), so they are replayed by ONE thread in edge
+// order, on union-find state held in shared memory.  What the other 255 threads do is shrink that thread's work list: the
+// edges of a chunk are filtered in parallel, in order, down to the ones that can act --
+//   pass 1: dist <= th (NaN compares false -> merge attempt, as in Python);
+//   pass 2: an endpoint cluster has < 5 points at the time the chunk is filtered.  Point counts only grow, so an edge
+//           that fails the test then fails it for the rest of the sweep: the filter is exact, and thread 0 re-checks the
+//           condition at replay time for the ones that passed.
 __global__ void __launch_bounds__(GN_THREADS)
 group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ roots_cur,
                     const float* __restrict__ dist, float th, int* __restrict__ ufb, int S1,
                     int sweep_cap, int* __restrict__ status, int state_in_smem) {
     extern __shared__ int gn_smem[];
     __shared__ int s_ru[GN_CHUNK], s_rv[GN_CHUNK];
+    __shared__ int s_wcount[GN_THREADS / 32];
     __shared__ int s_flag;
     int* base = state_in_smem ? gn_smem : ufb;
     if (state_in_smem) {
@@ -390,55 +420,67 @@ group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ 
     }
     __syncthreads();
     UF u(base, S1);
-    // pass 1: edges in order, skip iff dist > th (NaN compares false -> merge attempt, as in Python)
+    // pass 1
     for (int c0 = 0; c0 < A; c0 += GN_CHUNK) {
         const int n = min(GN_CHUNK, A - c0);
-        for (int i = threadIdx.x; i < n; i += GN_THREADS) {
-            const int e = c0 + i;
-            const bool skip = dist[e] > th;
-            s_ru[i] = skip ? -1 : roots_cur[adj[2 * e]];
-            s_rv[i] = skip ? -1 : roots_cur[adj[2 * e + 1]];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < n; ++i) {
-                if (s_ru[i] < 0) continue;
-                uf_union(u, uf_find(u, s_ru[i]), uf_find(u, s_rv[i]));
+        int fill = 0;
+        for (int i0 = 0; i0 < n; i0 += GN_THREADS) {
+            const int e = c0 + i0 + threadIdx.x;
+            bool keep = false;
+            int ru = 0, rv = 0;
+            if (i0 + threadIdx.x < n && !(dist[e] > th)) {
+                ru = roots_cur[adj[2 * (size_t)e]]; rv = roots_cur[adj[2 * (size_t)e + 1]];
+                keep = true;
             }
+            fill = gn_append(keep, ru, rv, s_ru, s_rv, fill, s_wcount);
+        }
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < fill; ++i) uf_union(u, uf_find(u, s_ru[i]), uf_find(u, s_rv[i]));
         }
         __syncthreads();
     }
     // pass 2: sweeps over ALL edges while some endpoint cluster has < 5 points
     int sweeps = 0;
     while (true) {
-        if (threadIdx.x == 0) s_flag = 0;
-        __syncthreads();
-        int any = 0;
-        for (int e = threadIdx.x; e < A; e += GN_THREADS) {
-            const int c1 = uf_find_ro(u.parent, roots_cur[adj[2 * e]]);
-            const int c2 = uf_find_ro(u.parent, roots_cur[adj[2 * e + 1]]);
-            any |= (u.pnum[c1] < 5 || u.pnum[c2] < 5);
+        if (sweeps >= sweep_cap) {                    // would another sweep still find a small cluster?
+            if (threadIdx.x == 0) s_flag = 0;
+            __syncthreads();
+            int any = 0;
+            for (int e = threadIdx.x; e < A; e += GN_THREADS) {
+                const int c1 = uf_find_ro(u.parent, roots_cur[adj[2 * e]]);
+                const int c2 = uf_find_ro(u.parent, roots_cur[adj[2 * e + 1]]);
+                any |= (u.pnum[c1] < 5 || u.pnum[c2] < 5);
+            }
+            if (any) s_flag = 1;
+            __syncthreads();
+            if (s_flag && threadIdx.x == 0) atomicOr(status, 2);
+            break;
         }
-        if (any) s_flag = 1;
-        __syncthreads();
-        if (!s_flag) break;
-        if (sweeps >= sweep_cap) { if (threadIdx.x == 0) atomicOr(status, 2); break; }
-        ++sweeps;
+        int attempts = 0;
         for (int c0 = 0; c0 < A; c0 += GN_CHUNK) {
             const int n = min(GN_CHUNK, A - c0);
-            for (int i = threadIdx.x; i < n; i += GN_THREADS) {
-                s_ru[i] = roots_cur[adj[2 * (c0 + i)]];
-                s_rv[i] = roots_cur[adj[2 * (c0 + i) + 1]];
+            int fill = 0;
+            for (int i0 = 0; i0 < n; i0 += GN_THREADS) {
+                const int e = c0 + i0 + threadIdx.x;
+                bool keep = false;
+                int ru = 0, rv = 0;
+                if (i0 + threadIdx.x < n) {
+                    ru = roots_cur[adj[2 * (size_t)e]]; rv = roots_cur[adj[2 * (size_t)e + 1]];
+                    keep = u.pnum[uf_find_ro(u.parent, ru)] < 5 || u.pnum[uf_find_ro(u.parent, rv)] < 5;
+                }
+                fill = gn_append(keep, ru, rv, s_ru, s_rv, fill, s_wcount);
             }
-            __syncthreads();
+            attempts += fill;
             if (threadIdx.x == 0) {
-                for (int i = 0; i < n; ++i) {
+                for (int i = 0; i < fill; ++i) {
                     const int c1 = uf_find(u, s_ru[i]), c2 = uf_find(u, s_rv[i]);
                     if (u.pnum[c1] < 5 || u.pnum[c2] < 5) uf_union(u, c1, c2);
                 }
             }
             __syncthreads();
         }
+        if (attempts == 0) break;                     // block-uniform: a sweep that found no small cluster ends the loop
+        ++sweeps;
     }
     __syncthreads();
     if (state_in_smem) {
@@ -471,13 +513,56 @@ __global__ void unlabeled_argmin_kernel(const float* __restrict__ dist, const in
     if (first_fill >= 0 && (bj < 0 || 1000.f < best || (1000.f == best && first_fill < bj))) bj = first_fill;
     amin[i] = bj < 0 ? 0 : bj;
 }
-__global__ void unlabeled_union_kernel(const int* __restrict__ amin, int S, const int* __restrict__ roots_cur, int* __restrict__ ufb, int S1) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    UF u(ufb, S1);
-    for (int i = 0; i < S; ++i) {
-        const int c1 = uf_find(u, roots_cur[i]);
-        if (u.ins[c1] != -1) continue;
-        uf_union(u, c1, uf_find(u, roots_cur[amin[i]]));
+// The ascending sequential unions of phase A.  One thread replays them; the union-find table, the root map and the argmin
+// row live in shared memory for the replay (a dependent shared-memory access costs ~30 cycles, an L2 one ~10x that).
+// A cluster that carries a label keeps it through every later union (model.py:188-190), so the clusters that are labelled
+// when the kernel starts are filtered out in parallel, in order; thread 0 re-checks the rest at replay time.
+constexpr int UU_THREADS = 256;
+__global__ void __launch_bounds__(UU_THREADS)
+unlabeled_union_kernel(const int* __restrict__ amin, int S, const int* __restrict__ roots_cur, int* __restrict__ ufb, int S1,
+                       int state_in_smem, int* __restrict__ list_ws /*[S], used when the state stays in global memory*/) {
+    extern __shared__ int uu_smem[];
+    __shared__ int s_wcount[UU_THREADS / 32];
+    int* base = ufb;
+    const int* s_roots = roots_cur;
+    const int* s_amin = amin;
+    int* s_list = list_ws;
+    if (state_in_smem) {
+        int* r = uu_smem + 6 * S1;
+        int* a = r + S;
+        s_list = a + S;
+        for (int i = threadIdx.x; i < 6 * S1; i += UU_THREADS) uu_smem[i] = ufb[i];
+        for (int i = threadIdx.x; i < S; i += UU_THREADS) { r[i] = roots_cur[i]; a[i] = amin[i]; }
+        base = uu_smem; s_roots = r; s_amin = a;
+    }
+    __syncthreads();
+    UF u(base, S1);
+    int fill = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < S; i0 += UU_THREADS) {
+        const int i = i0 + threadIdx.x;
+        const bool keep = i < S && u.ins[uf_find_ro(u.parent, s_roots[i])] == -1;
+        const unsigned bal = __ballot_sync(SGB_FULL_MASK, keep);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < UU_THREADS / 32; ++w) { const int c = s_wcount[w]; before += w < warp ? c : 0; total += c; }
+        if (keep) s_list[fill + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        fill += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < fill; ++t) {
+            const int i = s_list[t];
+            const int c1 = uf_find(u, s_roots[i]);
+            if (u.ins[c1] != -1) continue;
+            uf_union(u, c1, uf_find(u, s_roots[s_amin[i]]));
+        }
+    }
+    __syncthreads();
+    if (state_in_smem) {
+        for (int i = threadIdx.x; i < 6 * S1; i += UU_THREADS) ufb[i] = uu_smem[i];
     }
 }
 
@@ -704,13 +789,17 @@ extern "C" int sgb_group_nearby(const int* adj, int A, const int* roots_cur, con
     return SGB_OK;
 }
 
-// one iteration of phase A of group_unlabeled_clusters; amin_ws [S] ints
+// one iteration of phase A of group_unlabeled_clusters; amin_ws [2*S] ints
 extern "C" int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
                                         const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream) {
     if (S <= 0 || S1 <= 0 || !row_off || !roots_cur || !uf || !amin_ws) return SGB_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     { unlabeled_argmin_kernel<<<sgb_div_up(S, 128), 128, 0, st>>>(dist, row_off, nbr, eid, S, amin_ws); SGB_COUNT_LAUNCH(); }
-    { unlabeled_union_kernel<<<1, 32, 0, st>>>(amin_ws, S, roots_cur, uf, S1); SGB_COUNT_LAUNCH(); }
+    const size_t state_bytes = ((size_t)6 * S1 + 3 * (size_t)S) * sizeof(int);
+    const int in_smem = state_bytes <= 200 * 1024;
+    if (in_smem && state_bytes > 40 * 1024)
+        SGB_OPT_IN_SMEM(unlabeled_union_kernel);
+    { unlabeled_union_kernel<<<1, UU_THREADS, in_smem ? state_bytes : 0, st>>>(amin_ws, S, roots_cur, uf, S1, in_smem, amin_ws + S); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

@@ -51,7 +51,7 @@ extern "C" int sgb_level_step(int mode, const int* adj_old, int A_old, const int
     if (mode == 0) {
         if ((rc = sgb_group_nearby(adj_old, A_old, roots_old, dist, th, uf, S1, sweep_cap, status, stream))) return rc;
     } else if (mode == 1) {
-        // amin scratch: the head of ws (S_old ints); the level workspace is used afterwards, stream order keeps them apart
+        // amin scratch: the head of ws (2 * S_old ints <= 6 * (S1 + 1)); the level workspace is used afterwards, stream order keeps them apart
         if ((rc = sgb_group_unlabeled_step(dist, csr_off_old, csr_nbr_old, csr_eid_old, S_old, roots_old, uf, S1, (int*)ws, stream))) return rc;
     }
     if ((rc = sgb_level_build(uf, S1, N, seg_off, seg_members, seg_of_pos, roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order,

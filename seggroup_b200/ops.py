@@ -108,8 +108,8 @@ def centralize(data6, order, cl_off):
     N = data6.shape[0]
     S = cl_off.numel() - 1
     x9 = torch.empty(N, 9, dtype=F32, device=data6.device)
-    mean = torch.empty(S, 3, dtype=F32, device=data6.device)
-    _lib.call("sgb_centralize", data6, N, order, cl_off, S, x9, mean, _stream())
+    sums = torch.empty(S, 3, dtype=torch.int64, device=data6.device)      # scratch: fixed-point coordinate sums
+    _lib.call("sgb_centralize", data6, N, order, cl_off, S, x9, sums, _stream())
     return x9
 
 
@@ -346,9 +346,9 @@ def group_nearby(adj, roots_cur, dist, th, uf, status, sweep_cap=64):
 
 def group_unlabeled_step(dist, csr, S, roots_cur, uf):
     row_off, nbr, eid = csr
-    amin = torch.empty(S, dtype=I32, device=uf.device)
+    amin = torch.empty(2 * S, dtype=I32, device=uf.device)      # arg-min row + scratch list
     _lib.call("sgb_group_unlabeled_step", dist, row_off, nbr, eid, S, roots_cur, uf, uf.shape[1], amin, _stream())
-    return amin
+    return amin[:S]
 
 
 def group_unlabeled_phase_b(unl, cand, roots_cur, uf):

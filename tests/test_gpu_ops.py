@@ -92,6 +92,42 @@ def test_segment_pool_max(C, use_members):
     assert np.array_equal(gf, ref)
 
 
+@pytest.mark.parametrize("C", [64, 128, 192])
+@pytest.mark.parametrize("N", [4096, 20011, 131072 + 7])
+def test_segment_pool_staged_edge_cases(C, N):
+    """The shared-memory staged kernel (point-sized pools, C = 64 / 128; C = 192 takes the generic kernel): ragged tail chunk, one-row and two-row segments
+    next to a segment of thousands of rows, whole segments of -inf, NaN rows (torch.max: the FIRST NaN wins), ties."""
+    from seggroup_b200 import ops
+    rng = np.random.default_rng(N + C)
+    feat = rng.integers(-6, 7, (N, C)).astype(np.float32) * 0.125
+    sizes = [1, 2, 1, 31, 32, 33, 64, 3000, 1, 95, 97]
+    while sum(sizes) < N - 600:
+        sizes.append(int(rng.integers(1, 500)))
+    sizes.append(N - sum(sizes))
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    S = len(sizes)
+    members = rng.permutation(N).astype(np.int32)
+    seg_rows = lambda s: members[off[s]:off[s + 1]]
+    feat[seg_rows(5)] = -np.inf                                          # a whole segment of -inf: first member wins
+    feat[seg_rows(7)[100:2000:7], 3] = np.nan                            # NaNs inside the big segment (several chunks)
+    feat[seg_rows(7)[1500], 5] = np.nan
+    feat[seg_rows(9), 0] = np.nan                                        # all-NaN column of a one-row segment
+    feat[seg_rows(S - 1)[-1], 1] = np.nan                                # NaN in the ragged tail chunk
+    out, arg = ops.segment_pool_max(dev(feat), dev(off), dev(members))
+    out, arg = out.cpu().numpy(), arg.cpu().numpy()
+    ref_o, ref_a = torch.empty(S, C), torch.empty(S, C, dtype=torch.long)
+    for s in range(S):
+        v, i = torch.from_numpy(feat[seg_rows(s)]).max(0)                # torch semantics incl. NaN; ties checked below
+        ref_o[s], ref_a[s] = v, i
+    assert np.array_equal(out, ref_o.numpy(), equal_nan=True)
+    for s in range(S):
+        rows = seg_rows(s)
+        f = feat[rows]
+        isn = np.isnan(f)
+        first = np.where(isn.any(0), isn.argmax(0), (f == np.nanmax(np.where(isn, -np.inf, f), 0)).argmax(0))
+        assert np.array_equal(arg[s], rows[first]), s
+
+
 def test_cluster_knn(scene20k):
     from oracle import seggroup_oracle as O
     from seggroup_b200 import ops
