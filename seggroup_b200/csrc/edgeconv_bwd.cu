@@ -12,7 +12,7 @@
 //     dh_e = sparse_e - q0/M - Bm (h_e - hbar),   Bm = W2^T diag(gamma2 invstd2^2 dgamma2) W2 / M
 // whose dense part needs one pass over all edges (recompute h, 64x64 mat-vec, LeakyReLU mask, accumulate
 // sum dv1, sum dv1*zhat1, sum dv1 (e - ebar)^T).  Order of kernels:
-//     sparse -> [mid finalize -> dense] -> last finalize.
+//     sparse -> [mid finalize -> dense (tensor cores, edgeconv_bwd_tc.cu)] -> last finalize.
 // All cross-warp / cross-block sums run in a fixed order (deterministic).
 #include "edgeconv_common.cuh"
 
@@ -165,103 +165,13 @@ bwd_mid_kernel(const double* __restrict__ t2, double M, const float* __restrict_
     }
 }
 
-// MLP3 dense pass over all edges: dv1 = (r - Bm h) * lrelu'(v1); accumulate sum dv1, sum dv1 zhat1, sum dv1 (e - ebar)
-__global__ void __launch_bounds__(WARPS * 32)
-bwd_dense_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ W1,
-                 const float* __restrict__ stats1, const double* __restrict__ mom1, const float* __restrict__ e0, double M,
-                 const float* __restrict__ coef, float* __restrict__ partD /*[grid][64*NACC]*/) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float (*s_e)[KNN][CINP] = reinterpret_cast<float (*)[KNN][CINP]>(smem_raw);
-    float (*s_h)[KNN][COUT] = reinterpret_cast<float (*)[KNN][COUT]>(smem_raw + sizeof(float) * WARPS * KNN * CINP);
-    float (*s_bm)[COUT] = reinterpret_cast<float (*)[COUT]>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT));   // symmetric
-    float* s_ebar = reinterpret_cast<float*>(smem_raw + sizeof(float) * (WARPS * KNN * (CINP + COUT) + COUT * COUT));  // [CINP]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = lane * 2;
-    float w[2][CIN];
-#pragma unroll
-    for (int t = 0; t < CIN; ++t) { w[0][t] = __ldg(W1 + c0 * CIN + t); w[1][t] = __ldg(W1 + (c0 + 1) * CIN + t); }
-    const float mu0 = stats1[c0], mu1 = stats1[c0 + 1], is0 = stats1[64 + c0], is1 = stats1[64 + c0 + 1];
-    const float ga0 = stats1[128 + c0], ga1 = stats1[128 + c0 + 1], be0 = stats1[192 + c0], be1 = stats1[192 + c0 + 1];
-    for (int i = threadIdx.x; i < COUT * COUT; i += blockDim.x) (&s_bm[0][0])[i] = __ldg(coef + i);
-    load_ebar(mom1, e0, M, s_ebar);
-    const float r0 = __ldg(coef + COUT * COUT + c0), r1 = __ldg(coef + COUT * COUT + c0 + 1);
-    __syncthreads();
-    float acc[2][NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
-
-    for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
-        float xi[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) xi[t] = __ldg(x9 + (size_t)p * 9 + t);
-        __syncwarp();
-        stage_edges(x9, knn, p, lane, s_e[warp], xi, nullptr);
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) {
-            float y0, y1;
-            conv1(s_e[warp], k, w, y0, y1);
-            *reinterpret_cast<float2*>(&s_h[warp][k][c0]) =
-                make_float2(lrelu(fmaf(y0 - mu0, ga0, be0)), lrelu(fmaf(y1 - mu1, ga1, be1)));
-        }
-        __syncwarp();
-        float a0[KNN], a1[KNN];
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
-#pragma unroll 2
-        for (int j4 = 0; j4 < COUT / 4; ++j4) {
-            const float2 ba = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 0][c0]);
-            const float2 bb = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 1][c0]);
-            const float2 bc = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 2][c0]);
-            const float2 bd = *reinterpret_cast<const float2*>(&s_bm[j4 * 4 + 3][c0]);
-#pragma unroll
-            for (int k = 0; k < KNN; ++k) {
-                const float4 h = *reinterpret_cast<const float4*>(&s_h[warp][k][j4 * 4]);
-                a0[k] = fmaf(ba.x, h.x, a0[k]); a1[k] = fmaf(ba.y, h.x, a1[k]);
-                a0[k] = fmaf(bb.x, h.y, a0[k]); a1[k] = fmaf(bb.y, h.y, a1[k]);
-                a0[k] = fmaf(bc.x, h.z, a0[k]); a1[k] = fmaf(bc.y, h.z, a1[k]);
-                a0[k] = fmaf(bd.x, h.w, a0[k]); a1[k] = fmaf(bd.y, h.w, a1[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) {
-            float y0, y1;
-            conv1(s_e[warp], k, w, y0, y1);        // recomputed: cheaper than keeping 80 more registers live
-            const float z0 = (y0 - mu0) * is0, z1 = (y1 - mu1) * is1;
-            const float v0 = fmaf(y0 - mu0, ga0, be0), v1 = fmaf(y1 - mu1, ga1, be1);
-            const float dv0 = (r0 - a0[k]) * (v0 > 0.f ? 1.f : SLOPE), dv1 = (r1 - a1[k]) * (v1 > 0.f ? 1.f : SLOPE);
-            acc[0][0] += dv0; acc[1][0] += dv1;
-            acc[0][1] = fmaf(dv0, z0, acc[0][1]); acc[1][1] = fmaf(dv1, z1, acc[1][1]);
-#pragma unroll
-            for (int t4 = 0; t4 < CINP / 4; ++t4) {
-                const float4 ev = *reinterpret_cast<const float4*>(&s_e[warp][k][t4 * 4]);
-                const float e4[4] = {ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int t = t4 * 4 + q;
-                    if (t < CIN) {
-                        const float d = e4[q] - s_ebar[t];
-                        acc[0][2 + t] = fmaf(dv0, d, acc[0][2 + t]);
-                        acc[1][2 + t] = fmaf(dv1, d, acc[1][2 + t]);
-                    }
-                }
-            }
-        }
-    }
-    // block reduction in fixed warp order (reuse the s_h staging area: WARPS*KNN*COUT >= WARPS*COUT*NACC)
-    __syncthreads();
-    float* s_red = &s_h[0][0][0];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) {
-        s_red[warp * (COUT * NACC) + c0 * NACC + i] = acc[0][i];
-        s_red[warp * (COUT * NACC) + (c0 + 1) * NACC + i] = acc[1][i];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < COUT * NACC; i += blockDim.x) {
-        float sum = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < WARPS; ++wv) sum += s_red[wv * (COUT * NACC) + i];
-        partD[(size_t)blockIdx.x * (COUT * NACC) + i] = sum;
-    }
+// x9 [N,9] -> x12 [N,12] (48-byte rows: three aligned 16-byte loads per gathered row)
+__global__ void pad12_kernel(const float* __restrict__ x9, long long n12, float* __restrict__ x12) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n12) return;
+    const long long p = i / 12;
+    const int q = (int)(i % 12);
+    x12[i] = q < 9 ? __ldg(x9 + p * 9 + q) : 0.f;
 }
 
 // dW1 / dgamma1 / dbeta1 from the reduced (sparse [+ dense]) sums red [nred][64*NACC]
@@ -296,10 +206,6 @@ bwd_last_kernel(const double* __restrict__ red, int nred, double M,
     }
 }
 
-inline int bwd_dense_grid(int N) {
-    int g = sgb_div_up(N, WARPS);
-    return g < 148 * 2 ? (g < 1 ? 1 : g) : 148 * 2;
-}
 }  // namespace sgb_ec
 
 using namespace sgb_ec;
@@ -307,8 +213,10 @@ using namespace sgb_ec;
 extern "C" size_t sgb_edgeconv_bwd_ws_bytes(int N, int S, int two_layer) {
     const size_t nchunk = (size_t)sgb_div_up(S, SEG_CHUNK);
     size_t b = nchunk * 8 * COUT * NACC * sizeof(float);
-    if (two_layer) b += nchunk * COUT * 66 * sizeof(float) + (COUT * COUT + COUT) * sizeof(float) + (size_t)bwd_dense_grid(N) * COUT * NACC * sizeof(float);
+    if (two_layer) b += nchunk * COUT * 66 * sizeof(float) + (COUT * COUT + COUT) * sizeof(float);
     b += (size_t)(2 * COUT * NACC + COUT * 66) * sizeof(double);       // reduced sums
+    b = (b + 255) & ~(size_t)255;
+    if (two_layer) b += ((sgb_ec2_bwd_tc_part_bytes(N) + 255) & ~(size_t)255) + (size_t)(N > 0 ? N : 0) * 48;   // dense partials (fp64), x12
     return b + 256;
 }
 
@@ -339,15 +247,17 @@ extern "C" int sgb_edgeconv_bwd(const float* g, const int* arg, const unsigned c
         { bwd_last_kernel<<<1, 64, 0, st>>>(red, 1, M, W1, stats1, mom1, gW1, gg1, gb1); SGB_COUNT_LAUNCH(); }
     } else {
         float* coef = part2 + (size_t)nchunk * COUT * 66;
-        float* partD = coef + COUT * COUT + COUT;
-        const int gd = bwd_dense_grid(N);
+        double* partD = (double*)(((uintptr_t)(coef + COUT * COUT + COUT) + 255) & ~(uintptr_t)255);
+        float* x12 = (float*)((unsigned char*)partD + ((sgb_ec2_bwd_tc_part_bytes(N) + 255) & ~(size_t)255));
+        int gd = 0;
         { bwd_sparse_kernel<true><<<grid, WARPS * 32, 0, st>>>(g, arg, argk, S, x9, knn, W1, stats1, mom1, e0, M, W2, stats2, mom2, part1, part2); SGB_COUNT_LAUNCH(); }
         sgb_bn::reduce_partials(part1, nchunk * 8, COUT * NACC, red, st);
         sgb_bn::reduce_partials(part2, nchunk, COUT * 66, t2, st);
         { bwd_mid_kernel<<<COUT, 64, 0, st>>>(t2, M, W2, stats2, mom2, gW2, gg2, gb2, coef); SGB_COUNT_LAUNCH(); }
-        const size_t sm = sizeof(float) * (WARPS * KNN * (CINP + COUT) + COUT * COUT + CINP);
-        SGB_OPT_IN_SMEM(bwd_dense_kernel);
-        { bwd_dense_kernel<<<gd, WARPS * 32, sm, st>>>(x9, knn, N, W1, stats1, mom1, e0, M, coef, partD); SGB_COUNT_LAUNCH(); }
+        // dense pass over all N*20 edges: the 64x64 mat-vec per edge on the tcgen05 tensor cores (edgeconv_bwd_tc.cu)
+        { pad12_kernel<<<sgb_div_up((long long)N * 12, 256), 256, 0, st>>>(x9, (long long)N * 12, x12); SGB_COUNT_LAUNCH(); }
+        int rc = sgb_ec2_bwd_tc_dense(x12, knn, N, W1, stats1, mom1, e0, M, coef, partD, &gd, st);
+        if (rc) return rc;
         sgb_bn::reduce_partials(partD, gd, COUT * NACC, red + COUT * NACC, st);
         { bwd_last_kernel<<<1, 64, 0, st>>>(red, 2, M, W1, stats1, mom1, gW1, gg1, gb1); SGB_COUNT_LAUNCH(); }
     }

@@ -54,3 +54,8 @@ size_t sgb_ec2_tc_ws_bytes(int N);
 int sgb_ec2_tc_forward(const float* x12, const int* knn, int N, const float* W1, const float* stats1, const float* W2,
                        const float* gamma2, const float* beta2, float* out, unsigned char* argk, float* stats2, float* var2,
                        double* mom2, void* ws, cudaStream_t st);
+
+// tensor-core dense pass of the MLP3 backward (edgeconv_bwd_tc.cu)
+size_t sgb_ec2_bwd_tc_part_bytes(int N);
+int sgb_ec2_bwd_tc_dense(const float* x12, const int* knn, int N, const float* W1, const float* stats1, const double* mom1,
+                         const float* e0, double M, const float* coef, double* part, int* nparts, cudaStream_t st);
