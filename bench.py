@@ -48,27 +48,67 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML in-process (a thread that wakes
+    every 50 ms; an external `nvidia-smi -lms` poller takes driver locks that the four launching threads also need and
+    was measured to slow the step it is supposed to observe), nvidia-smi only if NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index=0, interval=0.05):
+        self.index, self.interval, self.rows, self.proc, self.nv, self.stop_flag = index, interval, [], None, None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
 
     def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, mx, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.interval)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            sm = [r[0] for r in self.rows]
+            mx = [r[1] for r in self.rows if r[1] is not None]
+            reasons = sorted({k for r in self.rows for k in r[2]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +121,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_port_points_per_sec(n_points, steps=1, warmup=0):
@@ -128,9 +168,13 @@ def main():
     ap.add_argument("--ref-points", type=int, default=30000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="scenes in flight per GPU (CUDA streams / host threads)")
+    ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "off"], help="clock sampler during the timed region")
+    ap.add_argument("--switch-interval", type=float, default=0.0, help="sys.setswitchinterval for the scene threads (0 = leave)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.switch_interval > 0:
+        sys.setswitchinterval(args.switch_interval)
 
     from seggroup_b200 import _lib, engine, pipeline, synth
     from seggroup_b200.params import TRAINABLE, init_params
@@ -209,16 +253,18 @@ def main():
         step(resident, False)
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
-    if rank == 0:
+    if args.sampler == "smi":
+        sampler.nv = None
+    if rank == 0 and args.sampler != "off":
         sampler.start()
     launches0 = _lib.launch_count()
-    _lib.time_entry = {"sgb_edgeconv_fwd", "sgb_segment_pool_max_fwd"}
+    _lib.time_entry = {"sgb_edgeconv_fwd", "sgb_edgeconv_bwd", "sgb_segment_pool_max_fwd"}
     _lib.timed_events = []
     ms, _ = timed(resident, False, args.steps)
     launches = _lib.launch_count() - launches0
     kernel_events = _lib.timed_events
     _lib.time_entry = None
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and args.sampler != "off") else None
     pts_per_step = args.scenes * args.points * world
     value = pts_per_step * args.steps / (ms * 1e-3)
     # ---- timed region 2: end to end from pinned host buffers
@@ -266,6 +312,14 @@ def main():
                           "achieved": pool_bytes / (p_ms * 1e-3) / 1e9 if p_ms else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": pool_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if p_ms else None, "ms_per_launch": p_ms,
                           "algorithmic_bytes_per_launch": pool_bytes, "launches_timed": len(evp)}]
+        # backward of MLP3: sparse arg-max edges + the dense pass over all N*20 edges on tcgen05 (Bm h per edge, TF32 x 3)
+        evb = [a.elapsed_time(c) for (name, tag, a, c) in kernel_events if name == "sgb_edgeconv_bwd" and tag == 1]
+        b_ms = float(np.mean(evb)) if evb else None
+        bflops = 2.0 * N * 20 * (18 * 64 + 64 * 64 + 64 * 18)
+        roofline_more.append({"bound": "tensor", "kernel": "sgb_edgeconv_bwd two_layer (bwd_sparse + ec2_bwd_tc_kernel [tcgen05 kind::tf32 x3] + finalize)",
+                              "achieved": bflops / (b_ms * 1e-3) / 1e12 if b_ms else None, "peak": peak_tf, "unit": "TFLOP/s",
+                              "frac": bflops / (b_ms * 1e-3) / 1e12 / peak_tf if b_ms else None, "ms_per_launch": b_ms,
+                              "algorithmic_flops_per_launch": bflops, "launches_timed": len(evb)})
         cpu = None
         if not args.no_cpu_baseline:
             pps, sec, cores = cpu_port_points_per_sec(args.ref_points)

@@ -114,8 +114,9 @@ def call(name: str, *args):
         e0.record()
         rc = _call(name, *args)
         e1.record()
-        # tag: two_layer flag for the EdgeConv forward, number of feature rows for the pooling
-        tag = args[3] if name == "sgb_edgeconv_fwd" else (args[1] if name == "sgb_segment_pool_max_fwd" else 0)
+        # tag: two_layer flag for the EdgeConv forward / backward, number of feature rows for the pooling
+        tag = args[3] if name == "sgb_edgeconv_fwd" else (args[7] if name == "sgb_edgeconv_bwd" else
+                                                          (args[1] if name == "sgb_segment_pool_max_fwd" else 0))
         timed_events.append((name, tag, e0, e1))
         return rc
     if profile is not None and not name.endswith("_bytes"):

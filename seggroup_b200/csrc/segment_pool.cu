@@ -183,10 +183,15 @@ segment_pool_staged_kernel(const float* __restrict__ feat, const int* __restrict
         cp_async_commit();
     };
 
-    int ids_next;
-#pragma unroll
-    for (int k = 0; k < ST_STAGES; ++k) issue(k, load_ids(k));
-    ids_next = load_ids(ST_STAGES);
+    // member ids run three chunks ahead of the row copies they feed (an id load that is consumed one iteration later
+    // is a DRAM round trip on the critical path of every chunk: ncu long-scoreboard stalls)
+    int ids_a, ids_b, ids_c;
+    {
+        const int i0 = load_ids(0), i1 = load_ids(1), i2 = load_ids(2);
+        ids_a = load_ids(ST_STAGES); ids_b = load_ids(ST_STAGES + 1); ids_c = load_ids(ST_STAGES + 2);
+        issue(0, i0); issue(1, i1); issue(2, i2);
+    }
+    static_assert(ST_STAGES == 3, "prologue written for three stages");
 
     const int q_begin = k_begin * ST_ROWS, q_end = min(n_members, (k_begin + k_count) * ST_ROWS);
     int seg = sgb_upper_segment(offsets, S, q_begin);
@@ -256,8 +261,9 @@ segment_pool_staged_kernel(const float* __restrict__ feat, const int* __restrict
             }
         }
         __syncwarp();                                 // every lane is done reading the stage before it is refilled
-        const int ids = ids_next;
-        ids_next = load_ids(k + ST_STAGES + 1);
+        const int ids = ids_a;
+        ids_a = ids_b; ids_b = ids_c;
+        ids_c = load_ids(k + ST_STAGES + 3);
         issue(k + ST_STAGES, ids);                    // commits an (empty) group past the end: keeps wait_group counting uniform
     }
     if (part_begin < q_end) flush(seg, q_end);

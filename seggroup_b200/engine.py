@@ -14,7 +14,6 @@ caller's stream, so the result does not depend on thread scheduling.
 """
 from __future__ import annotations
 
-import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import torch
@@ -28,39 +27,41 @@ class SceneExecutor:
         self.n_streams = max(1, int(n_streams))
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
         self._pool = ThreadPoolExecutor(max_workers=self.n_streams, thread_name_prefix="sgb-scene")
-        self._free = list(range(self.n_streams))
-        self._lock = threading.Lock()
 
     def close(self):
         self._pool.shutdown(wait=True)
 
     # ------------------------------------------------------------------------------------------
     def _run(self, fn, items):
-        """fn(item, index) is executed for every item on one of the executor's streams; results in item order."""
+        """fn(item, index) is executed for every item on one of the executor's streams; results in item order.
+        Item i always runs on stream i % n_streams (lane), in index order within the lane: the caching allocator keeps
+        one pool per stream, so a fixed item -> stream map lets every step after the first reuse the previous step's
+        blocks instead of calling cudaMalloc (a device-wide synchronisation) whenever a stream meets a new shape."""
         main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
+        n_lanes = min(self.n_streams, len(items))
 
-        def work(i, item):
-            with self._lock:
-                sid = self._free.pop()
-            try:
-                torch.cuda.set_device(self.device)
-                st = self.streams[sid]
-                st.wait_event(ready)                       # parameters / inputs produced on the caller's stream
-                with torch.cuda.stream(st):
-                    out = fn(item, i)
+        def lane(sid):
+            torch.cuda.set_device(self.device)
+            st = self.streams[sid]
+            st.wait_event(ready)                           # parameters / inputs produced on the caller's stream
+            outs = []
+            with torch.cuda.stream(st):
+                for i in range(sid, len(items), n_lanes):
+                    out = fn(items[i], i)
                     done = torch.cuda.Event()
                     done.record(st)
-                return out, done
-            finally:
-                with self._lock:
-                    self._free.append(sid)
+                    outs.append((i, out, done))
+            return outs
 
-        futs = [self._pool.submit(work, i, it) for i, it in enumerate(items)]
-        outs = []
+        futs = [self._pool.submit(lane, sid) for sid in range(n_lanes)]
+        res = [None] * len(items)
         for f in futs:
-            out, done = f.result()
+            for i, out, done in f.result():
+                res[i] = (out, done)
+        outs = []
+        for out, done in res:
             main.wait_event(done)                          # device-side join, no host synchronisation
             outs.append(out)
         return outs

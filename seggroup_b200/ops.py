@@ -368,6 +368,26 @@ def export_labels(unmap, seg_of_point, level: Level, want_seg=True):
     return seg, ins, sem
 
 
+_VALID_IDS = {}
+
+
+def evaluate(real_label, sem_pred, ins_pred, sem_valid, ins_valid, status=None):
+    """model.py:608-655 on the device: real_label [n,2] i64, sem_pred / ins_pred [n] i32 -> out [164] f32
+    (IoU_sem [2,40], IoU_ins [2,40], acc [4])."""
+    import numpy as np
+    _chk(real_label, torch.int64, "real_label"); _chk(sem_pred, I32, "sem_pred"); _chk(ins_pred, I32, "ins_pred")
+    n = sem_pred.numel()
+    key = (tuple(sem_valid), tuple(ins_valid))
+    ids = _VALID_IDS.get(key)
+    if ids is None:
+        ids = _VALID_IDS[key] = (np.ascontiguousarray(sem_valid, np.int32), np.ascontiguousarray(ins_valid, np.int32))
+    out = torch.empty(164, dtype=F32, device=sem_pred.device)
+    ws = _ws(_lib.call("sgb_evaluate_ws_bytes"), sem_pred.device)
+    _lib.call("sgb_evaluate", real_label, sem_pred, ins_pred, n, ids[0], len(ids[0]), ids[1], len(ids[1]), out, status, ws, ws.numel(),
+              _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core primitives (tcgen05, TF32 x 3)
 # ------------------------------------------------------------------------------------------------

@@ -145,44 +145,16 @@ class EdgeConvPoolFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
-# metrics (model.py:608-655) — torch ops on the device (histograms over <= 41 x I bins)
+# metrics (model.py:608-655) — sgb_evaluate (evaluate.cu): shared-memory histograms over classes / instance ids
 # ------------------------------------------------------------------------------------------------
 SEM_VALID = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 24, 28, 33, 34, 36, 39]
 INS_VALID = [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 24, 28, 33, 34, 36, 39]
 
 
-def evaluate(real_label, sem_pred, ins_pred):
-    """-> (IoU_sem [1,2,40], IoU_ins [1,2,40], acc [4]) float32 on the device of the inputs."""
-    dev = sem_pred.device
-    sem_true, ins_true = real_label[:, 0], real_label[:, 1]
-    v = sem_true != 0
-    sem_true, ins_true = sem_true[v], ins_true[v]
-    sem_pred, ins_pred = sem_pred[v].long(), ins_pred[v].long()
-    iou_sem = torch.zeros(1, 2, 40, device=dev)
-    iou_ins = torch.zeros(1, 2, 40, device=dev)
-    cls = torch.arange(1, 41, device=dev).view(-1, 1)
-    p, t = sem_pred.view(1, -1) == cls, sem_true.view(1, -1) == cls
-    iou_sem[0, 0] = (p & t).sum(1)
-    iou_sem[0, 1] = (p | t).sum(1)
-    ids = torch.unique(ins_pred)
-    ids = ids[ids != -1]
-    if ids.numel():
-        pi = ins_pred.view(1, -1) == ids.view(-1, 1)
-        ti = ins_true.view(1, -1) == ids.view(-1, 1)
-        inter, union = (pi & ti).sum(1).float(), (pi | ti).sum(1).float()
-        first = pi.float().argmax(1)                       # first point of every predicted instance
-        sem_of = sem_pred[first] - 1
-        ok = (sem_of >= 0) & (sem_of < 40)
-        iou_ins[0, 0].index_add_(0, sem_of[ok], inter[ok])
-        iou_ins[0, 1].index_add_(0, sem_of[ok], union[ok])
-
-    def acc(tt, pp):
-        return (tt == pp).float().mean() if tt.numel() else torch.tensor(float("nan"), device=dev)
-
-    sv = torch.isin(sem_true, torch.tensor(SEM_VALID, device=dev))
-    iv = torch.isin(ins_true, torch.tensor(INS_VALID, device=dev))
-    a = torch.stack([acc(sem_true, sem_pred), acc(ins_true, ins_pred), acc(sem_true[sv], sem_pred[sv]), acc(ins_true[iv], ins_pred[iv])])
-    return iou_sem, iou_ins, a.float()
+def evaluate(real_label, sem_pred, ins_pred, status=None):
+    """-> (IoU_sem [1,2,40], IoU_ins [1,2,40], acc [4]) float32 on the device of the inputs (one fused library pass)."""
+    o = ops.evaluate(real_label.contiguous(), sem_pred.contiguous(), ins_pred.contiguous(), SEM_VALID, INS_VALID, status)
+    return o[:80].view(1, 2, 40), o[80:160].view(1, 2, 40), o[160:164]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -245,7 +217,7 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
         res.aux.update(adj_1=adj_1, cloud_idx_1=cloud_idx, data_1=clouds, knn_1=knn_1, Feat_1=Feat_1.detach(), dists_1=d1, adj_2=adj_2)
     if sem_infer:
         if sc.real_label is not None and export:
-            res.metrics = evaluate(sc.real_label, res.labels["layer_2.sem"], res.labels["layer_2.ins"])
+            res.metrics = evaluate(sc.real_label, res.labels["layer_2.sem"], res.labels["layer_2.ins"], status)
         res.status = L2.status
         return res
 
@@ -311,7 +283,7 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     if keep_aux:
         res.aux["Feat_5"] = Feat_5.detach()
     if sc.real_label is not None and export:
-        res.metrics = evaluate(sc.real_label, res.labels["final.sem"], res.labels["final.ins"])
+        res.metrics = evaluate(sc.real_label, res.labels["final.sem"], res.labels["final.ins"], status)
     res.status = L5.status
     if mode == "ins_infer":
         return res

@@ -429,3 +429,27 @@ def test_sym_csr_exact(S, E):
     assert np.array_equal(row_off.cpu().numpy(), ref_off)
     assert np.array_equal(nbr.cpu().numpy()[:2 * A], dst[order])
     assert np.array_equal(eid.cpu().numpy()[:2 * A], ids[order])
+
+
+@pytest.mark.parametrize("case", ["scene_like", "many_ids", "nothing_valid"])
+def test_evaluate_matches_oracle(case):
+    """sgb_evaluate (a17) against the restatement of model.py:608-655 on random labels: counts exact, accuracies to fp32."""
+    from oracle import seggroup_oracle as O
+    from seggroup_b200 import pipeline
+    rng = np.random.default_rng(len(case))
+    n = 60000
+    n_ids = 40 if case == "scene_like" else 3000                       # > 1024 ids: the global-memory histogram path
+    sem_true = rng.integers(0, 41, n)
+    ins_true = rng.integers(1, n_ids + 1, n)
+    if case == "nothing_valid":
+        sem_true[:] = 0
+    sem_of_id = rng.integers(1, 41, n_ids + 1)
+    ins_pred = np.where(rng.random(n) < 0.7, ins_true, rng.integers(-1, n_ids + 1, n))
+    sem_pred = np.where(ins_pred >= 0, sem_of_id[np.maximum(ins_pred, 0)], -1)
+    sem_pred = np.where(rng.random(n) < 0.05, rng.integers(1, 41, n), sem_pred)     # instances whose first vertex disagrees
+    real = np.stack([sem_true, ins_true], 1).astype(np.int64)
+    ref = O.evaluate(real, sem_pred.astype(np.int64), ins_pred.astype(np.int64))
+    out = pipeline.evaluate(dev(real), dev(sem_pred, torch.int32), dev(ins_pred, torch.int32))
+    for a, b in zip(out, ref):
+        a = a.cpu().numpy().reshape(b.shape)
+        assert np.allclose(a, b, rtol=1e-6, atol=0, equal_nan=True), (case, a, b)

@@ -112,6 +112,27 @@ def main():
             ms, mn = T(lambda: ops.segment_pool_max_bwd(goB, argB, B * N))
             emit(rows, "segment_pool_max_bwd [8N,64] (8 scenes in one launch)", B * N, ms, mn, nbytes=B * (8 * S * C + 4 * N * C), segments=B * S)
             del featB, outB, argB, goB
+        if want("ceiling"):
+            # what the memory system gives the same access pattern without any arithmetic: a library row gather of the
+            # SAME 256-byte rows in the SAME (random) member order, and a plain streaming copy (read + write bytes counted)
+            featC = torch.randn(N, C, generator=g).cuda()
+            idx = d["seg_members"].long()
+            dst = torch.empty_like(featC)
+            ms, mn = T(lambda: torch.index_select(featC, 0, idx, out=dst))
+            emit(rows, "reference: torch.index_select of the [N,64] rows in member order (random 256-B gather + streaming write)", N, ms, mn,
+                 nbytes=2 * 4 * N * C + 8 * N)
+            ms, mn = T(lambda: dst.copy_(featC))
+            emit(rows, "reference: streaming copy of [N,64] (read + write)", N, ms, mn, nbytes=2 * 4 * N * C)
+            if N <= 200000:
+                featB = torch.randn(8 * N, C, generator=g).cuda()
+                idxB = torch.cat([d["seg_members"] + i * N for i in range(8)]).long()
+                dstB = torch.empty_like(featB)
+                ms, mn = T(lambda: torch.index_select(featB, 0, idxB, out=dstB))
+                emit(rows, "reference: torch.index_select of [8N,64] rows in member order", 8 * N, ms, mn, nbytes=8 * (2 * 4 * N * C + 8 * N))
+                ms, mn = T(lambda: dstB.copy_(featB))
+                emit(rows, "reference: streaming copy of [8N,64] (read + write)", 8 * N, ms, mn, nbytes=8 * 2 * 4 * N * C)
+                del featB, idxB, dstB
+            del featC, dst
         if want("centralize") or want("knn") or want("edgeconv"):
             order = d["seg_members"]
             x9 = ops.centralize(d["data"], order, d["seg_off"])
@@ -135,6 +156,12 @@ def main():
                 ms, mn = T(lambda: ops.edgeconv_fwd(*a3, want_backward=wb))
                 emit(rows, "edgeconv_fwd MLP3 %s (a9, tcgen05 64x64 layer)" % ("train" if wb else "infer"), N, ms, mn,
                      nbytes=36 * N + 80 * N + 256 * N + 64 * N, flops=2.0 * N * 20 * (18 * 64 + 64 * 64))
+            # backward of MLP3 fused with the point -> segment pooling (sparse arg-max edges + dense tcgen05 pass)
+            o3 = ops.edgeconv_fwd(*a3, want_backward=True)
+            pooled, arg = ops.segment_pool_max(o3["out"], d["seg_off"], d["seg_members"])
+            gp = torch.randn(S, 64, generator=g).cuda()
+            ms, mn = T(lambda: ops.edgeconv_bwd(gp, arg, o3["argk"], x9, knn, a3[2], o3["stats1"], o3["mom1"], o3["ctr"], a3[5], o3["stats2"], o3["mom2"]))
+            emit(rows, "edgeconv_bwd MLP3 (a9, dense pass on tcgen05)", N, ms, mn, nbytes=36 * N + 80 * N, flops=2.0 * N * 20 * (18 * 64 + 64 * 64 + 64 * 18))
         if want("export"):
             from seggroup_b200 import pipeline
             # label export needs a level; run the model-free part of the pipeline: scene_init + level_build

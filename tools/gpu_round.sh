@@ -14,12 +14,16 @@ kernels)  timeout 900 python tools/bench_kernels.py --out $O/${TAG}_kernels.json
 host)     timeout 600 python tools/host_profile.py > $O/${TAG}_host_profile.txt 2>&1 ;;
 scene)    timeout 600 python tools/profile_scene.py 150000 train > $O/${TAG}_entrypoints_train_150k.txt 2>&1
           timeout 600 python tools/profile_scene.py 150000 ins_infer > $O/${TAG}_entrypoints_ins_infer_150k.txt 2>&1 ;;
-full)     timeout 900 ncu --set full --clock-control none --import-source on \
-            -k regex:'segment_pool_fwd_kernel|ec2_tc_kernel|kpconv_tc_fwd_kernel|knn_sweep_kernel|forward_max_kernel|gram1_kernel|centralize_kernel|ind_max_pool_fwd' \
-            -c 14 -f -o $O/${TAG}_full_kernels python tools/bench_kernels.py --points 500000 --reps 1 --warm 0 --only pool,centralize,knn,edgeconv,kpconv,kppool > $O/${TAG}_full_kernels.log 2>&1
-          timeout 900 ncu --set full --clock-control none --import-source on \
-            -k regex:'bwd_dense_kernel|group_nearby_kernel|unlabeled_union_kernel|bwd_sparse_kernel' \
-            -c 6 -f -o $O/${TAG}_full_train python tools/profile_scene.py 150000 train > $O/${TAG}_full_train.log 2>&1 ;;
+full)     # ncu --set full captures; only the text summaries travel back (gpurun_out/ is capped at 64 MiB)
+          timeout 900 ncu --set full --clock-control none \
+            -k regex:'segment_pool_staged_kernel|ec2_tc_kernel|ec2_bwd_tc_kernel|kpconv_tc_fwd_kernel|knn_sweep_kernel|forward_max_kernel|gram1_pt_kernel|centralize_kernel|ind_max_pool_fwd' \
+            -c 16 -f -o /tmp/${TAG}_full_kernels python tools/bench_kernels.py --points 500000 --reps 1 --warm 0 --only pool,centralize,knn,edgeconv,kpconv,kppool > $O/${TAG}_full_kernels.log 2>&1
+          python tools/ncu_summary.py /tmp/${TAG}_full_kernels.ncu-rep > $O/${TAG}_ncu_full_kernels_500k.txt 2>&1
+          timeout 900 ncu --set full --clock-control none \
+            -k regex:'ec2_tc_kernel|ec2_bwd_tc_kernel|segment_pool_staged_kernel|group_nearby_kernel|unlabeled_union_kernel|bwd_sparse_kernel|gram1_pt_kernel|knn_sweep_kernel' \
+            -c 18 -f -o /tmp/${TAG}_full_train python tools/profile_scene.py 150000 train > $O/${TAG}_full_train.log 2>&1
+          python tools/ncu_summary.py /tmp/${TAG}_full_train.ncu-rep > $O/${TAG}_ncu_full_train_150k.txt 2>&1
+          for f in /tmp/${TAG}_full_train.ncu-rep; do [ $(stat -c %s $f) -lt 40000000 ] && cp $f $O/; done ;;
 gridrn)   timeout 600 python tools/bench_kernels.py --only pool,centralize,grid,neighbors,kppool --out $O/${TAG}_kernels_gather.json > $O/${TAG}_kernels_gather.log 2>&1; tail -3 $O/${TAG}_kernels_gather.log
           timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_gridrn.csv \
             python tools/bench_kernels.py --points 150000 --reps 1 --warm 1 --only grid,neighbors > $O/${TAG}_launches_gridrn.log 2>&1
@@ -27,7 +31,8 @@ gridrn)   timeout 600 python tools/bench_kernels.py --only pool,centralize,grid,
             -k regex:'segment_pool_fwd_kernel|rn_search|rn_fill|centralize_kernel|ind_max_pool_fwd|gs_insert|gs_reduce_points|gs_sort_small' \
             -c 12 -f -o $O/${TAG}_full_gather python tools/bench_kernels.py --points 500000 --reps 1 --warm 0 --only pool,centralize,grid,neighbors,kppool > $O/${TAG}_full_gather.log 2>&1 ;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $O/${TAG}_launches.csv \
-            python bench.py --steps 1 --warmup 1 --scenes 1 --points 150000 --no-cpu-baseline --streams 1 > $O/${TAG}_launches.log 2>&1 ;;
+            python bench.py --steps 1 --warmup 1 --scenes 1 --points 150000 --no-cpu-baseline --streams 1 > $O/${TAG}_launches.log 2>&1
+          python tools/summarize_launches.py $O/${TAG}_launches.csv > $O/${TAG}_launches_train_150k.md 2>&1 ;;
 esac
 done
 ls -la $O | tail -20
