@@ -14,7 +14,7 @@ One JSON line is printed by rank 0:
   e2e          same metric through the host-facing call: every step copies the scenes' inputs from pinned host
                memory and reads the loss back
   roofline     dominant entry point (EdgeConv forward of MLP3, tcgen05): useful flops / CUDA-event time vs the measured tensor peak;
-               roofline_more: the HBM-bound gather/scatter kernel (segment pooling) vs the measured copy bandwidth
+               roofline_more: the HBM-bound gather kernel (segment pooling) vs the measured copy bandwidth, the tcgen05 backward
   inference    pseudo-label generation (ins_infer) points/sec over the same batch
   cpu_baseline the oracle port of the reference CPU path, timed on a bounded sample on this box's host cores
 `--impl reference` times that CPU port alone, as the reference arm.
@@ -299,16 +299,25 @@ def main():
         flops = 2.0 * N * 20 * (18 * 64 + 64 * 64)
         achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        roofline = {"bound": "tensor", "kernel": "sgb_edgeconv_fwd two_layer (gram1_kernel + ec2_tc_kernel<ARG,GRAM> [tcgen05 kind::tf32 x3] + ec2_apply_kernel)",
+        # traffic / pipe utilisation of the dominant kernel of this entry (ec2_tc_kernel<1,1>) from the ncu --set full capture of
+        # the same workload (profiles/r01i_ncu_full_train_150k.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch at
+        # N = 150,000; scaled linearly in N for other sizes)
+        traffic = (19.34e6 + 91.79e6) * (N / 150000.0)
+        roofline = {"bound": "tensor", "kernel": "sgb_edgeconv_fwd two_layer (gram1_pt_kernel + ec2_tc_kernel<ARG,GRAM> [tcgen05 kind::tf32 x3] + ec2_apply_kernel)",
                     "achieved": achieved, "peak": peak_tf, "peak_kind": peak_kind + " bf16 dense (tf32 runs at half of it, the x3 split costs 3 MMAs)",
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None, "traffic": None, "ms_per_launch": k_ms,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None, "traffic": traffic, "ms_per_launch": k_ms,
                     "algorithmic_flops_per_launch": flops, "launches_timed": len(ev),
-                    "note": "timed with CUDA events on the launching stream while %d scenes are in flight" % args.streams}
+                    "frac_of_tf32x3_ceiling": achieved / (peak_tf / 6.0) if achieved else None,
+                    "ncu": {"source": "profiles/r01i_ncu_full_train_150k.txt", "kernel": "ec2_tc_kernel<1,1>", "us_alone": 855.1,
+                            "tensor_pipe_active_pct": 22.6, "l1tex_throughput_pct": 94.1, "limiter": "shared-memory bandwidth (operand tiles + transposed Gram copy)"},
+                    "note": "timed with CUDA events on the launching stream while %d scenes are in flight (alone: 1.00 ms, "
+                            "profiles/r01i_kernels_150k_500k.json)" % args.streams}
         # the HBM-bound gather/scatter kernel of the path: point -> segment max pooling (sgb_segment_pool_max_fwd on [N,64])
         evp = [a.elapsed_time(c) for (name, tag, a, c) in kernel_events if name == "sgb_segment_pool_max_fwd" and tag == N]
         p_ms = float(np.mean(evp)) if evp else None
         pool_bytes = N * (4 * 64 + 4) + 16 * 1100 * 64
-        roofline_more = [{"bound": "hbm", "kernel": "sgb_segment_pool_max_fwd [N,64] (segment_pool_fwd_kernel + decode)",
+        roofline_more = [{"bound": "hbm", "kernel": "sgb_segment_pool_max_fwd [N,64] (memset + segment_pool_staged_kernel + decode)",
+                          "traffic": 39.38e6 * (N / 150000.0), "ncu_kernel_us_alone": 16.4,
                           "achieved": pool_bytes / (p_ms * 1e-3) / 1e9 if p_ms else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": pool_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if p_ms else None, "ms_per_launch": p_ms,
                           "algorithmic_bytes_per_launch": pool_bytes, "launches_timed": len(evp)}]
