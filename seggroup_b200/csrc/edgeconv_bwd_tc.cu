@@ -14,6 +14,12 @@
 //     thread = channel (lanes 0..15 of each warp hold the M = 64 accumulator rows), the partner lane 16 + l takes half of the
 //     18 columns of T for the same channel (dv1 by shuffle), accumulators fp32 per 8 tiles, fp64 across;
 //   * outputs: per-CTA partial sums part[cta][64][20] = (A0, sum dv1 zhat1, T[18]) in fp64, reduced in a fixed order.
+// Measured (profiles/r01i_ncu_full_train_150k.txt): 827 us at 150k points, l1tex 88 %, tensor pipe 16.5 %: the kernel is
+// shared-memory-bandwidth bound, and the largest consumer is the epilogue's broadcast reads of the centred edge vectors
+// (every warp re-reads the 72 bytes of every edge, two distinct addresses per wavefront).  Spreading the epilogue over eight
+// warps with pipelined TMEM loads did not help (0.93 -> 0.96 ms: same shared-memory traffic); the next step is to run
+// T = dv1^T (e - ebar) as a second tcgen05 GEMM over the edges (K = edges, as the forward Gram accumulator does), which needs
+// 80-edge tiles to fit the dv1 operand next to the H tiles.
 #include "common.cuh"
 #include "bn_moments.cuh"
 #include "edgeconv_common.cuh"
