@@ -189,6 +189,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO in the environment) go to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/seggroup_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 

@@ -186,6 +186,10 @@ def main():
         if want("neighbors"):
             ms, mn = T(lambda: KO.batch_ordered_neighbors(sub, sub, sb, sb, 0.10))
             emit(rows, "radius_neighbors r=0.10 (a19, count + read-back + fill)", M, ms, mn, nbytes=24 * M + 4 * M * W, width=W)
+            for rr in (0.05, 0.20):                      # radius sweep on the dl = 0.04 subsample
+                Wr = KO.batch_ordered_neighbors(sub, sub, sb, sb, rr).shape[1]
+                ms, mn = T(lambda: KO.batch_ordered_neighbors(sub, sub, sb, sb, rr))
+                emit(rows, "radius_neighbors r=%.2f (a19, count + read-back + fill)" % rr, M, ms, mn, nbytes=24 * M + 4 * M * Wr, width=Wr)
         if want("kpconv"):
             K = 15
             extent = 0.04
@@ -195,6 +199,16 @@ def main():
             kp = kp.cuda()
             nbc = nb[:, :min(W, 64)].contiguous()
             Wc = nbc.shape[1]
+            if N >= 400000 and want("kpconv"):           # config 5: neighbour-count cap sweep at 64x64 (W cap 16 / 32 / 64 / 128)
+                nb20 = KO.batch_ordered_neighbors(sub, sub, sb, sb, 0.20)
+                feats = torch.randn(M, 64, generator=g).cuda()
+                kv = (torch.randn(K, 64, 64, generator=g) / np.sqrt(K * 64)).cuda()
+                for cap in (16, 32, 64, 128):
+                    nbw = nb20[:, :min(nb20.shape[1], cap)].contiguous()
+                    ms, mn = T(lambda: KO.KPConv_ops(sub, sub, nbw, feats, kp, kv, 0.08, "linear", "sum", tensor_cores=True))
+                    emit(rows, "kpconv_fwd 64x64 %s, r=0.20 neighbours capped at W=%d (a20)" % ("tcgen05" if nbw.shape[1] <= 64 else "fp32 SIMT (W > 64)", nbw.shape[1]), M, ms, mn,
+                         nbytes=4 * M * nbw.shape[1] + 24 * M + 4 * M * 64 * 2 + 4 * K * 64 * 64, flops=2.0 * M * K * 64 * 64, width=nbw.shape[1])
+                del nb20
             for cin, cout in [(64, 64), (32, 32), (128, 128)]:
                 feats = torch.randn(M, cin, generator=g).cuda()
                 kv = (torch.randn(K, cin, cout, generator=g) / np.sqrt(K * cin)).cuda()
