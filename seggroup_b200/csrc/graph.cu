@@ -285,66 +285,127 @@ __global__ void edge_dist_fwd_kernel(const float* __restrict__ feat, int C, cons
     s = sgb_warp_sum(s);
     if (lane == 0) dist[e] = sqrtf(s);
 }
+// The three CSR row kernels below run one CTA per cluster.  A row's incident-edge metadata (edge id -> endpoints, distance,
+// similarity, neighbour row sum) sits behind two or three DEPENDENT global loads; read inside the per-channel loop that
+// chain is paid once per neighbour and a cluster with hundreds of neighbours (a floor) holds the whole launch for
+// > 200 us.  The CTA therefore stages the row's metadata in shared memory cooperatively, CSR_CHUNK entries at a time, and
+// the channel loop is left with one independent feature load per neighbour.  Summation order (ascending CSR position,
+// diagonal in column order) is unchanged, so results are bit-identical to the straightforward loop.
+constexpr int CSR_CHUNK = 256;
+
 // grad_feat[i] += sum over incident edges of +-g[e] * (F[u]-F[v]+eps)/d[e]   (gather over the symmetric CSR)
-__global__ void edge_dist_bwd_kernel(const float* __restrict__ feat, int C, const int* __restrict__ adj, const float* __restrict__ dist,
-                                     const float* __restrict__ gdist, const int* __restrict__ row_off, const int* __restrict__ eid,
-                                     int S, float* __restrict__ gfeat) {
+__global__ void __launch_bounds__(128)
+edge_dist_bwd_kernel(const float* __restrict__ feat, int C, const int* __restrict__ adj, const float* __restrict__ dist,
+                     const float* __restrict__ gdist, const int* __restrict__ row_off, const int* __restrict__ eid,
+                     int S, float* __restrict__ gfeat) {
+    __shared__ int s_u[CSR_CHUNK], s_v[CSR_CHUNK];
+    __shared__ float s_d[CSR_CHUNK], s_g[CSR_CHUNK];
     const int i = blockIdx.x;
     if (i >= S) return;
     const int a = row_off[i], b = row_off[i + 1];
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
         float acc = 0.f;
-        for (int t = a; t < b; ++t) {
-            const int e = eid[t];
-            const int u = adj[2 * e], v = adj[2 * e + 1];
-            const float d = dist[e];
-            const float g = gdist[e];
-            const float diff = (__ldg(feat + (size_t)u * C + c) - __ldg(feat + (size_t)v * C + c)) + 1e-6f;
-            const float val = d > 0.f ? g * diff / d : 0.f;
-            acc += (u == i) ? val : -val;
+        for (int t0 = a; t0 < b; t0 += CSR_CHUNK) {
+            const int n = min(CSR_CHUNK, b - t0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                const int e = eid[t0 + k];
+                s_u[k] = adj[2 * e]; s_v[k] = adj[2 * e + 1]; s_d[k] = dist[e]; s_g[k] = gdist[e];
+            }
+            __syncthreads();
+            if (c < C) {
+#pragma unroll 4
+                for (int k = 0; k < n; ++k) {
+                    const int u = s_u[k], v = s_v[k];
+                    const float d = s_d[k];
+                    const float diff = (__ldg(feat + (size_t)u * C + c) - __ldg(feat + (size_t)v * C + c)) + 1e-6f;
+                    const float val = d > 0.f ? s_g[k] * diff / d : 0.f;
+                    acc += (u == i) ? val : -val;
+                }
+            }
         }
-        gfeat[(size_t)i * C + c] += acc;
+        if (c < C) gfeat[(size_t)i * C + c] += acc;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // GCN aggregation (model.py:305-309, 146-151): A = I + sym(sims); AX = (A / rowsum) X   as a CSR gather
 // ---------------------------------------------------------------------------------------------
-__global__ void gcn_agg_fwd_kernel(const float* __restrict__ X, int C, const float* __restrict__ sims, const int* __restrict__ row_off,
-                                   const int* __restrict__ nbr, const int* __restrict__ eid, int S, float* __restrict__ AX,
-                                   float* __restrict__ rowsum) {
+__global__ void __launch_bounds__(128)
+gcn_agg_fwd_kernel(const float* __restrict__ X, int C, const float* __restrict__ sims, const int* __restrict__ row_off,
+                   const int* __restrict__ nbr, const int* __restrict__ eid, int S, float* __restrict__ AX,
+                   float* __restrict__ rowsum) {
+    __shared__ int s_j[CSR_CHUNK];
+    __shared__ float s_w[CSR_CHUNK];
+    __shared__ float s_rs;
     const int i = blockIdx.x;
     if (i >= S) return;
     const int a = row_off[i], b = row_off[i + 1];
+    // row sum in CSR order (one thread adds, from staged similarities: a fixed, sequential order)
     float rs = 1.f;                                   // diagonal
-    for (int t = a; t < b; ++t) rs += sims[eid[t]];
-    if (threadIdx.x == 0) rowsum[i] = rs;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int t0 = a; t0 < b; t0 += CSR_CHUNK) {
+        const int n = min(CSR_CHUNK, b - t0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += blockDim.x) s_w[k] = sims[eid[t0 + k]];
+        __syncthreads();
+        if (threadIdx.x == 0) for (int k = 0; k < n; ++k) rs += s_w[k];
+    }
+    if (threadIdx.x == 0) { s_rs = rs; rowsum[i] = rs; }
+    __syncthreads();
+    rs = s_rs;
+    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
         float acc = 0.f;
         bool diag_done = false;
-        for (int t = a; t < b; ++t) {                 // ascending column order incl. the diagonal
-            const int j = nbr[t];
-            if (!diag_done && j > i) { acc = fmaf(1.f / rs, __ldg(X + (size_t)i * C + c), acc); diag_done = true; }
-            acc = fmaf(sims[eid[t]] / rs, __ldg(X + (size_t)j * C + c), acc);
+        for (int t0 = a; t0 < b; t0 += CSR_CHUNK) {
+            const int n = min(CSR_CHUNK, b - t0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < n; k += blockDim.x) { s_j[k] = nbr[t0 + k]; s_w[k] = sims[eid[t0 + k]] / rs; }
+            __syncthreads();
+            if (c < C) {
+#pragma unroll 4
+                for (int k = 0; k < n; ++k) {         // ascending column order incl. the diagonal
+                    const int j = s_j[k];
+                    if (!diag_done && j > i) { acc = fmaf(1.f / rs, __ldg(X + (size_t)i * C + c), acc); diag_done = true; }
+                    acc = fmaf(s_w[k], __ldg(X + (size_t)j * C + c), acc);
+                }
+            }
         }
-        if (!diag_done) acc = fmaf(1.f / rs, __ldg(X + (size_t)i * C + c), acc);
-        AX[(size_t)i * C + c] = acc;
+        if (c < C) {
+            if (!diag_done) acc = fmaf(1.f / rs, __ldg(X + (size_t)i * C + c), acc);
+            AX[(size_t)i * C + c] = acc;
+        }
     }
 }
 // dX[j] = sum_i A[i,j]/rs_i * dAX[i]  (structure symmetric: gather over row j, using the neighbour's rowsum)
-__global__ void gcn_agg_bwd_x_kernel(const float* __restrict__ dAX, int C, const float* __restrict__ sims, const float* __restrict__ rowsum,
-                                     const int* __restrict__ row_off, const int* __restrict__ nbr, const int* __restrict__ eid, int S,
-                                     float* __restrict__ dX) {
+__global__ void __launch_bounds__(128)
+gcn_agg_bwd_x_kernel(const float* __restrict__ dAX, int C, const float* __restrict__ sims, const float* __restrict__ rowsum,
+                     const int* __restrict__ row_off, const int* __restrict__ nbr, const int* __restrict__ eid, int S,
+                     float* __restrict__ dX) {
+    __shared__ int s_i[CSR_CHUNK];
+    __shared__ float s_w[CSR_CHUNK];
     const int j = blockIdx.x;
     if (j >= S) return;
     const int a = row_off[j], b = row_off[j + 1];
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc = __ldg(dAX + (size_t)j * C + c) / rowsum[j];
-        for (int t = a; t < b; ++t) {
-            const int i = nbr[t];
-            acc = fmaf(sims[eid[t]] / rowsum[i], __ldg(dAX + (size_t)i * C + c), acc);
+    const float rsj = rowsum[j];
+    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        float acc = c < C ? __ldg(dAX + (size_t)j * C + c) / rsj : 0.f;
+        for (int t0 = a; t0 < b; t0 += CSR_CHUNK) {
+            const int n = min(CSR_CHUNK, b - t0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                const int i = nbr[t0 + k];
+                s_i[k] = i; s_w[k] = sims[eid[t0 + k]] / rowsum[i];
+            }
+            __syncthreads();
+            if (c < C) {
+#pragma unroll 4
+                for (int k = 0; k < n; ++k) acc = fmaf(s_w[k], __ldg(dAX + (size_t)s_i[k] * C + c), acc);
+            }
         }
-        dX[(size_t)j * C + c] = acc;
+        if (c < C) dX[(size_t)j * C + c] = acc;
     }
 }
 // dsims[e=(u,v)] = (dAX[u].X[v] - dAX[u].AX[u]) / rs_u + (dAX[v].X[u] - dAX[v].AX[v]) / rs_v : one warp per edge
