@@ -19,6 +19,18 @@
 namespace {
 constexpr int KNN_THREADS = 128;
 
+// packed fp32x2 FMA (Blackwell FFMA2), each half an IEEE fma.rn:  v = v * a + b   /   acc = a * b + acc
+__device__ __forceinline__ void sgb_ffma2(float2& v, const float2 a, const float2 b) {
+    unsigned long long d = *reinterpret_cast<unsigned long long*>(&v);
+    asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    v = *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ void sgb_ffma2_acc(float2& acc, const float2 a, const float2 b) {
+    unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    acc = *reinterpret_cast<float2*>(&d);
+}
+
 __device__ __forceinline__ float sq_norm_ref(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
@@ -110,7 +122,8 @@ __global__ void __launch_bounds__(KNN_THREADS)
 knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ cl_off, const int* __restrict__ axis,
                  const float4* __restrict__ rec, const int* __restrict__ spos, const int* __restrict__ cid,
                  const unsigned* __restrict__ max_sq, int* __restrict__ knn) {
-    __shared__ float4 s_rec[KNN_THREADS / 32][32];
+    // chunk of 32 candidate records per warp, structure-of-arrays so that two neighbouring candidates load as one float2
+    __shared__ __align__(8) float s_x[KNN_THREADS / 32][32], s_y[KNN_THREADS / 32][32], s_z[KNN_THREADS / 32][32], s_w[KNN_THREADS / 32][32];
     __shared__ int s_pos[KNN_THREADS / 32][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i0 = (blockIdx.x * (KNN_THREADS / 32) + w) * 32;
@@ -130,6 +143,8 @@ knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ c
     const bool searching = have && n > K;
     const float err2 = 2.f * 1.9073486e-6f * __uint_as_float(*max_sq);       // 2 * 2^-19 * max |x|^2
     const float cq = ax == 0 ? me.x : (ax == 1 ? me.y : me.z);
+    const float2 one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
+    const float2 nx2 = make_float2(-me.x, -me.x), ny2 = make_float2(-me.y, -me.y), nz2 = make_float2(-me.z, -me.z);
 
     float sc[K];
     int ps[K];
@@ -137,34 +152,60 @@ knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ c
     for (int t = 0; t < K; ++t) { sc[t] = -INFINITY; ps[t] = 0x7fffffff; }
     float T = INFINITY;                             // stopping / rejection radius^2 = -score_k + 2 err
 
+    auto consider = [&](int t) {                    // exact score of candidate t of the staged chunk; insertion into the top K
+        const float4 cand = make_float4(s_x[w][t], s_y[w][t], s_z[w][t], s_w[w][t]);
+        const float s = score_ref(me.x, me.y, me.z, me.w, cand);
+        const int p = s_pos[w][t];
+        if (s > sc[K - 1] || (s == sc[K - 1] && p < ps[K - 1])) {
+            sc[K - 1] = s; ps[K - 1] = p;
+#pragma unroll
+            for (int q = K - 1; q > 0; --q) {
+                if (sc[q] > sc[q - 1] || (sc[q] == sc[q - 1] && ps[q] < ps[q - 1])) {
+                    const float ts = sc[q]; sc[q] = sc[q - 1]; sc[q - 1] = ts;
+                    const int tp = ps[q]; ps[q] = ps[q - 1]; ps[q - 1] = tp;
+                }
+            }
+            T = -sc[K - 1] + err2;                  // +inf until K records have been seen
+        }
+    };
+
     auto process_chunk = [&](int base) {            // records [base, base + 32) of the sorted order
         const int j = base + lane;
         __syncwarp();
-        if (j >= 0 && j < N) { s_rec[w][lane] = rec[j]; s_pos[w][lane] = spos[j]; }
+        if (j >= 0 && j < N) {
+            const float4 r = rec[j];
+            s_x[w][lane] = r.x; s_y[w][lane] = r.y; s_z[w][lane] = r.z; s_w[w][lane] = r.w; s_pos[w][lane] = spos[j];
+        }
         __syncwarp();
         const int t0 = max(0, lo - base), t1 = min(32, hi - base);          // my cluster's part of the chunk
         const int u0 = max(0, -base), u1 = min(32, N - base);
-        const int a0 = max(u0, t0), a1 = min(u1, t1);
-        if (searching) {
-            for (int t = a0; t < a1; ++t) {
-                const float4 cand = s_rec[w][t];
-                // cheap exact-safe prefilter: score <= -d^2 + err, so a record with d^2 > -score_k + 2 err can never enter
-                const float dx = cand.x - me.x, dy = cand.y - me.y, dz = cand.z - me.z;
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (d2 * 0.999999f > T) continue;
-                const float s = score_ref(me.x, me.y, me.z, me.w, cand);
-                const int p = s_pos[w][t];
-                if (s > sc[K - 1] || (s == sc[K - 1] && p < ps[K - 1])) {
-                    sc[K - 1] = s; ps[K - 1] = p;
+        const int a0 = searching ? max(u0, t0) : 32, a1 = searching ? min(u1, t1) : 0;
+        // Two candidates per step on the packed fp32x2 pipe (FFMA2): the same prefilter value as the scalar expression
+        //     d2 = fma(dz, dz, fma(dy, dy, dx * dx)),   dx = cand.x - me.x   (cand * 1 + (-me) rounds like the subtraction)
+        // bit for bit, so the set of candidates that reach the exact score is unchanged.  Exact-safe prefilter:
+        // score <= -d^2 + err, so a record with d^2 > -score_k + 2 err can never enter.
+        // The threshold T of the chunk start is used for all 32 records (T only shrinks, so this admits a superset; the exact
+        // comparison in consider() decides), which keeps the filter loop branch-free and the insertion code in one place.
+        if (__any_sync(SGB_FULL_MASK, a0 < a1)) {
+            unsigned pass = 0;
 #pragma unroll
-                    for (int q = K - 1; q > 0; --q) {
-                        if (sc[q] > sc[q - 1] || (sc[q] == sc[q - 1] && ps[q] < ps[q - 1])) {
-                            const float ts = sc[q]; sc[q] = sc[q - 1]; sc[q - 1] = ts;
-                            const int tp = ps[q]; ps[q] = ps[q - 1]; ps[q - 1] = tp;
-                        }
-                    }
-                    T = -sc[K - 1] + err2;          // +inf until K records have been seen
-                }
+            for (int t = 0; t < 32; t += 2) {
+                float2 dx = *reinterpret_cast<const float2*>(&s_x[w][t]);
+                float2 dy = *reinterpret_cast<const float2*>(&s_y[w][t]);
+                float2 dz = *reinterpret_cast<const float2*>(&s_z[w][t]);
+                sgb_ffma2(dx, one2, nx2); sgb_ffma2(dy, one2, ny2); sgb_ffma2(dz, one2, nz2);
+                float2 d2 = zero2;
+                sgb_ffma2_acc(d2, dx, dx); sgb_ffma2_acc(d2, dy, dy); sgb_ffma2_acc(d2, dz, dz);
+                pass |= (!(d2.x * 0.999999f > T) ? 1u : 0u) << t;
+                pass |= (!(d2.y * 0.999999f > T) ? 2u : 0u) << t;
+            }
+            // keep bits [a0, a1): my cluster's records of this chunk
+            const unsigned range = (a0 < a1) ? ((a1 >= 32 ? 0xffffffffu : ((1u << a1) - 1u)) & ~((1u << a0) - 1u)) : 0u;
+            pass &= range;
+            while (pass) {
+                const int t = __ffs(pass) - 1;
+                pass &= pass - 1;
+                consider(t);
             }
         }
     };
