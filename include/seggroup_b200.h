@@ -262,7 +262,7 @@ int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point
  * instance prediction and the four accuracies, over the raw vertices with real_label[:,0] != 0.
  * real_label [n,2] int64 (sem 1..40, ins), 16-byte aligned; sem_pred / ins_pred [n] int32 as sgb_export_labels writes them.
  * sem_valid_ids / ins_valid_ids: HOST arrays of class ids (1..63) = SEM_VALID_CLASS_IDS / INS_VALID_CLASS_IDS.
- * out [164] = IoU_sem [2][40], IoU_ins [2][40], acc [4] (fp32).  status: bit 8 is OR-ed in if a predicted id >= 65536. */
+ * out [164] = IoU_sem [2][40], IoU_ins [2][40], acc [4] (fp32).  status: bit 64 is OR-ed in if a predicted id >= 65536. */
 size_t sgb_evaluate_ws_bytes(void);
 int sgb_evaluate(const long long* real_label, const int* sem_pred, const int* ins_pred, int n,
                  const int* sem_valid_ids, int n_sem_valid, const int* ins_valid_ids, int n_ins_valid,

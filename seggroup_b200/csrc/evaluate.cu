@@ -13,7 +13,7 @@
 namespace {
 constexpr int EV_THREADS = 256;
 constexpr int EV_SMEM_IDS = 1024;       // instance ids below this are histogrammed in shared memory first
-constexpr int EV_MAX_IDS = 65536;       // ids at or above this are not supported (status bit 8)
+constexpr int EV_MAX_IDS = 65536;       // ids at or above this are not supported (status bit 64)
 constexpr int EV_NCNT = 8;              // n_valid, sem_eq, ins_eq, n_semsel, semsel_eq, n_inssel, inssel_eq, overflow
 
 struct EvWs {
@@ -115,7 +115,7 @@ evaluate_finalize_kernel(EvWs w, const int* __restrict__ sem_pred, float* __rest
         const int den[4] = {w.cnt[0], w.cnt[0], w.cnt[3], w.cnt[5]};
         out[160 + threadIdx.x] = (float)((double)num[threadIdx.x] / (double)den[threadIdx.x]);      // 0/0 -> NaN as np.mean([])
     }
-    if (threadIdx.x == 0 && w.cnt[7] && status) atomicOr(status, 8);
+    if (threadIdx.x == 0 && w.cnt[7] && status) atomicOr(status, 64);
 }
 }  // namespace
 

@@ -668,6 +668,221 @@ __global__ void export_labels_kernel(const long long* __restrict__ unmap, int n_
     if (out_ins) out_ins[r] = ins != -1 ? ins + 1 : -1;
     if (out_sem) out_sem[r] = sem != -1 ? sem + 1 : -1;
 }
+__global__ void count_unlabeled_kernel(const int* __restrict__ cl_ins, const int* __restrict__ counts, int* __restrict__ out) {
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int S = counts[0];
+    int n = 0;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) n += cl_ins[i] == -1;
+    n = sgb_warp_sum(n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0) out[2] = s_n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-graph path: one CTA per step.  With S <= SMALL_S clusters every phase of a level (flag -> scan -> assign -> walk ->
+// scan -> fill ...) is a few thousand elements: as separate launches each phase costs a launch (~3 us of stream time, 27 of
+// them per clustering level); as one 1024-thread CTA the phases are separated by __syncthreads and the scans run in place.
+// The phase bodies are the kernels above, re-indexed by (threadIdx.x, blockDim.x).  Arrays written in one phase and read in
+// a later one are passed WITHOUT const/__restrict__ so that no read goes through the non-coherent path.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_S = 8192;
+constexpr int SMALL_THREADS = 1024;
+
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total); in and out must not alias; all threads of the CTA call it
+__device__ void block_scan_excl(const int* in, int n, int* out, int* s_warp /*[34] shared*/) {
+    const int t = threadIdx.x, lane = t & 31, wp = t >> 5, nt = blockDim.x;
+    const int per = (n + nt - 1) / nt;
+    const int b = min(n, t * per), e = min(n, b + per);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += in[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(SGB_FULL_MASK, inc, o); if (lane >= o) inc += v; }
+    __syncthreads();                                   // s_warp may still be read by a previous call
+    if (lane == 31) s_warp[wp] = inc;
+    __syncthreads();
+    if (wp == 0) {
+        const int v = lane < (nt >> 5) ? s_warp[lane] : 0;
+        int iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(SGB_FULL_MASK, iv, o); if (lane >= o) iv += u; }
+        s_warp[lane] = iv - v;
+        if (lane == 31) s_warp[32] = iv;
+    }
+    __syncthreads();
+    int run = s_warp[wp] + inc - sum;
+    for (int i = b; i < e; ++i) { out[i] = run; run += in[i]; }
+    if (t == 0) out[n] = s_warp[32];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+level_build_small(const int* __restrict__ ufb, int S, const int* __restrict__ seg_off, const int* __restrict__ seg_members,
+                  int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* cl_ins, int* cl_sem, int* cl_rootpt,
+                  int* counts, int* flag, int* dense, int* cl_nseg, int* cl_npt, int* seg_rank, int* seg_start) {
+    __shared__ int s_warp[34];
+    __shared__ int s_unl;
+    const int* parent = ufb;
+    const int* next = ufb + S;
+    if (threadIdx.x == 0) s_unl = 0;
+    for (int s0 = threadIdx.x; s0 < S; s0 += blockDim.x) flag[s0] = parent[s0] == s0 ? 1 : 0;
+    __syncthreads();
+    block_scan_excl(flag, S, dense, s_warp);
+    const int nc = dense[S];
+    for (int s0 = threadIdx.x; s0 < S; s0 += blockDim.x) {                // level_assign
+        const int r = uf_find_ro(parent, s0);
+        const int c = dense[r];
+        seg2cl[s0] = c;
+        if (r == s0) {
+            roots[c] = s0;
+            cl_ins[c] = ufb[4 * S + s0];
+            cl_sem[c] = ufb[5 * S + s0];
+            cl_rootpt[c] = __ldg(seg_members + __ldg(seg_off + s0));
+        }
+    }
+    __syncthreads();
+    int unl = 0;
+    for (int c = threadIdx.x; c < S; c += blockDim.x) {                   // level_walk_lists (+ count of unlabeled clusters)
+        if (c >= nc) { cl_nseg[c] = 0; cl_npt[c] = 0; continue; }
+        int sgm = roots[c], i = 0, pts = 0;
+        while (sgm >= 0) {
+            seg_rank[sgm] = i; seg_start[sgm] = pts;
+            pts += __ldg(seg_off + sgm + 1) - __ldg(seg_off + sgm);
+            ++i;
+            sgm = next[sgm];
+        }
+        cl_nseg[c] = i; cl_npt[c] = pts;
+        unl += cl_ins[c] == -1;
+    }
+    unl = sgb_warp_sum(unl);
+    if ((threadIdx.x & 31) == 0 && unl) atomicAdd(&s_unl, unl);
+    __syncthreads();
+    block_scan_excl(cl_nseg, S, cl_seg_off, s_warp);
+    block_scan_excl(cl_npt, S, cl_pt_off, s_warp);
+    for (int s0 = threadIdx.x; s0 < S; s0 += blockDim.x) cl_seg_list[cl_seg_off[seg2cl[s0]] + seg_rank[s0]] = s0;   // level_fill_seglist
+    if (threadIdx.x == 0) { counts[0] = nc; counts[2] = s_unl; }
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+children_small(const int* __restrict__ roots_old, int n_old, const int* __restrict__ seg2cl_new, int n_new,
+               int* old2new, int* child_off, int* child_list, int* cnt) {
+    __shared__ int s_warp[34];
+    for (int c = threadIdx.x; c <= n_new; c += blockDim.x) cnt[c] = 0;
+    for (int j = threadIdx.x; j < n_old; j += blockDim.x) old2new[j] = seg2cl_new[roots_old[j]];
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_old; j += blockDim.x) atomicAdd(cnt + old2new[j], 1);
+    __syncthreads();
+    block_scan_excl(cnt, n_new, child_off, s_warp);
+    const int lane = threadIdx.x & 31;
+    for (int c = threadIdx.x >> 5; c < n_new; c += blockDim.x >> 5) {     // children_fill: one warp per new cluster
+        int w = child_off[c];
+        const int end = child_off[c + 1];
+        for (int j0 = 0; j0 < n_old && w < end; j0 += 32) {
+            const int j = j0 + lane;
+            const bool hit = j < n_old && old2new[j] == c;
+            const unsigned m = __ballot_sync(SGB_FULL_MASK, hit);
+            if (hit) child_list[w + __popc(m & ((1u << lane) - 1))] = j;
+            w += __popc(m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+adj_rows_small(const unsigned* bitmap, int S, int wpr, int* row_cnt, int* row_off, int* adj_out, int* counts) {
+    __shared__ int s_warp[34];
+    const int lane = threadIdx.x & 31;
+    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {         // adj_row_count
+        int c = 0;
+        for (int w = lane; w < wpr; w += 32) c += __popc(bitmap[(size_t)r * wpr + w]);
+        c = sgb_warp_sum(c);
+        if (lane == 0) row_cnt[r] = c;
+    }
+    __syncthreads();
+    block_scan_excl(row_cnt, S, row_off, s_warp);
+    if (threadIdx.x == 0) counts[1] = row_off[S];
+    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {         // adj_row_write
+        int w0 = row_off[r];
+        for (int wb = 0; wb < wpr; wb += 32) {
+            const int w = wb + lane;
+            const unsigned bits = w < wpr ? bitmap[(size_t)r * wpr + w] : 0u;
+            const int c = __popc(bits);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(SGB_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+            int pos = w0 + inc - c;
+            unsigned b = bits;
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                adj_out[2 * (size_t)pos] = r;
+                adj_out[2 * (size_t)pos + 1] = w * 32 + bit;
+                ++pos;
+            }
+            w0 += __shfl_sync(SGB_FULL_MASK, inc, 31);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+csr_rows_small(const unsigned* bitmap, int S, int wpr, int has_edges, int* deg, int* outdeg, int* row_off, int* first, int* nbr, int* eid) {
+    __shared__ int s_warp[34];
+    const int lane = threadIdx.x & 31;
+    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {         // csr_row_degrees
+        int d = 0, o = 0;
+        for (int w = lane; w < wpr; w += 32) {
+            const unsigned bits = bitmap[(size_t)r * wpr + w];
+            d += __popc(bits);
+            o += __popc(bits_above(bits, w, r));
+        }
+        d = sgb_warp_sum(d); o = sgb_warp_sum(o);
+        if (lane == 0) { deg[r] = d; outdeg[r] = o; }
+    }
+    __syncthreads();
+    block_scan_excl(deg, S, row_off, s_warp);
+    if (!has_edges) return;
+    block_scan_excl(outdeg, S, first, s_warp);
+    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {         // csr_row_write
+        const int base = row_off[r];
+        const int indeg = (row_off[r + 1] - base) - (first[r + 1] - first[r]);
+        const int first_r = first[r];
+        int w0 = base;
+        for (int wb = 0; wb < wpr; wb += 32) {
+            const int w = wb + lane;
+            const unsigned bits = w < wpr ? bitmap[(size_t)r * wpr + w] : 0u;
+            const int c = __popc(bits);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(SGB_FULL_MASK, inc, o); if (lane >= o) inc += t; }
+            int pos = w0 + inc - c;
+            unsigned b = bits;
+            while (b) {
+                const int j = w * 32 + __ffs(b) - 1;
+                b &= b - 1;
+                int e;
+                if (j > r) {
+                    e = first_r + (pos - base - indeg);
+                } else {                               // edge (j, r): rank of r among the bits above the diagonal of row j
+                    const unsigned* rowj = bitmap + (size_t)j * wpr;
+                    int rank = 0;
+                    for (int ww = j >> 5; ww <= (r >> 5); ++ww) {
+                        unsigned bb = bits_above(rowj[ww], ww, j);
+                        const int hi = r - ww * 32;    // keep columns < r
+                        if (hi < 32) bb &= (hi <= 0 ? 0u : (0xffffffffu >> (32 - hi)));
+                        rank += __popc(bb);
+                    }
+                    e = first[j] + rank;
+                }
+                nbr[pos] = j; eid[pos] = e;
+                ++pos;
+            }
+            w0 += __shfl_sync(SGB_FULL_MASK, inc, 31);
+        }
+    }
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -703,6 +918,13 @@ extern "C" int sgb_level_build(const int* uf, int S1, int N, const int* seg_off,
     const size_t scan_bytes = sgb_scan_ws_bytes(S1 + 1);
     const int g = sgb_div_up(S1, 256);
     int rc;
+    if (S1 <= SMALL_S) {                  // one CTA for every cluster-sized phase (counts[0] = clusters, counts[2] = unlabeled ones)
+        { level_build_small<<<1, SMALL_THREADS, 0, st>>>(uf, S1, seg_off, seg_members, roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off,
+                                                         cl_ins, cl_sem, cl_rootpt, counts, flag, dense, cl_nseg, cl_npt, seg_rank, seg_start); SGB_COUNT_LAUNCH(); }
+        { level_fill_order<<<sgb_div_up(N, 256), 256, 0, st>>>(N, seg_of_pos, seg_off, seg_members, seg2cl, seg_start, cl_pt_off, order); SGB_COUNT_LAUNCH(); }
+        SGB_CHECK_LAUNCH();
+        return SGB_OK;
+    }
     { level_flag_roots<<<g, 256, 0, st>>>(uf, S1, flag); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(flag, dense, S1, scan_ws, scan_bytes, st))) return rc;
     { level_assign<<<g, 256, 0, st>>>(uf, S1, dense, seg_off, seg_members, roots, seg2cl, cl_ins, cl_sem, cl_rootpt, counts); SGB_COUNT_LAUNCH(); }
@@ -711,6 +933,7 @@ extern "C" int sgb_level_build(const int* uf, int S1, int N, const int* seg_off,
     if ((rc = sgb_exclusive_scan_i32(cl_npt, cl_pt_off, S1, scan_ws, scan_bytes, st))) return rc;
     { level_fill_seglist<<<g, 256, 0, st>>>(S1, seg2cl, seg_rank, cl_seg_off, cl_seg_list); SGB_COUNT_LAUNCH(); }
     { level_fill_order<<<sgb_div_up(N, 256), 256, 0, st>>>(N, seg_of_pos, seg_off, seg_members, seg2cl, seg_start, cl_pt_off, order); SGB_COUNT_LAUNCH(); }
+    { count_unlabeled_kernel<<<1, 256, 0, st>>>(cl_ins, counts, counts); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -725,6 +948,11 @@ extern "C" int sgb_level_children(const int* roots_old, int n_old, const int* se
     cudaStream_t st = (cudaStream_t)stream;
     int* cnt = (int*)ws;
     void* scan_ws = cnt + (n_new + 1);
+    if (n_old <= SMALL_S && n_new <= SMALL_S) {
+        { children_small<<<1, SMALL_THREADS, 0, st>>>(roots_old, n_old, seg2cl_new, n_new, old2new, child_off, child_list, cnt); SGB_COUNT_LAUNCH(); }
+        SGB_CHECK_LAUNCH();
+        return SGB_OK;
+    }
     SGB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n_new + 1) * sizeof(int), st));
     { gather_old2new<<<sgb_div_up(n_old, 256), 256, 0, st>>>(roots_old, n_old, seg2cl_new, old2new); SGB_COUNT_LAUNCH(); }
     { children_count<<<sgb_div_up(n_old, 256), 256, 0, st>>>(old2new, n_old, cnt, n_new); SGB_COUNT_LAUNCH(); }
@@ -756,6 +984,11 @@ extern "C" int sgb_update_adj(const int* edges, int E, const int* map, int S_new
         if (!edges) return SGB_ERR_INVALID;
         { adj_set_bits<<<sgb_div_up(E, 256), 256, 0, st>>>(edges, E, map, S_new, wpr, bitmap); SGB_COUNT_LAUNCH(); }
     }
+    if (S_new <= SMALL_S) {
+        { adj_rows_small<<<1, SMALL_THREADS, 0, st>>>(bitmap, S_new, wpr, row_cnt, row_off, adj_out, counts); SGB_COUNT_LAUNCH(); }
+        SGB_CHECK_LAUNCH();
+        return SGB_OK;
+    }
     { adj_row_count<<<sgb_div_up(S_new, 8), 256, 0, st>>>(bitmap, S_new, wpr, row_cnt); SGB_COUNT_LAUNCH(); }
     int rc;
     if ((rc = sgb_exclusive_scan_i32(row_cnt, row_off, S_new, scan_ws, sgb_scan_ws_bytes(S_new + 1), st))) return rc;
@@ -783,6 +1016,11 @@ extern "C" int sgb_sym_csr(const int* adj, int A, int S, int* row_off, int* nbr,
     if (A > 0) {
         if (!adj || !nbr || !eid) return SGB_ERR_INVALID;
         { csr_set_bits<<<sgb_div_up(A, 256), 256, 0, st>>>(adj, A, wpr, bitmap); SGB_COUNT_LAUNCH(); }
+    }
+    if (S <= SMALL_S) {
+        { csr_rows_small<<<1, SMALL_THREADS, 0, st>>>(bitmap, S, wpr, A > 0 ? 1 : 0, deg, outdeg, row_off, first, nbr, eid); SGB_COUNT_LAUNCH(); }
+        SGB_CHECK_LAUNCH();
+        return SGB_OK;
     }
     { csr_row_degrees<<<sgb_div_up(S, 8), 256, 0, st>>>(bitmap, S, wpr, deg, outdeg); SGB_COUNT_LAUNCH(); }
     int rc;

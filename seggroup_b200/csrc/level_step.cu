@@ -17,20 +17,6 @@ extern "C" size_t sgb_level_step_ws_bytes(int S1, int S_old) {
     return a + 256;
 }
 
-namespace {
-__global__ void count_unlabeled_kernel(const int* __restrict__ cl_ins, const int* __restrict__ counts, int* __restrict__ out) {
-    __shared__ int s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const int S = counts[0];
-    int n = 0;
-    for (int i = threadIdx.x; i < S; i += blockDim.x) n += cl_ins[i] == -1;
-    n = sgb_warp_sum(n);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s_n, n);
-    __syncthreads();
-    if (threadIdx.x == 0) out[2] = s_n;
-}
-}  // namespace
 
 // mode 0: group_nearby(adj_old, dist, th); 1: group_unlabeled_step(dist, csr_old); 2: no grouping (level of the input graph).
 // edges/E/map: the edge list to re-map for the new adjacency; map == NULL -> old2new of this step (edges = adj_old).
@@ -56,7 +42,7 @@ extern "C" int sgb_level_step(int mode, const int* adj_old, int A_old, const int
     }
     if ((rc = sgb_level_build(uf, S1, N, seg_off, seg_members, seg_of_pos, roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order,
                               cl_ins, cl_sem, cl_rootpt, counts_dev, ws, ws_bytes, stream))) return rc;
-    { count_unlabeled_kernel<<<1, 256, 0, st>>>(cl_ins, counts_dev, counts_dev); SGB_COUNT_LAUNCH(); }
+    // sgb_level_build leaves counts_dev[0] = clusters and counts_dev[2] = clusters without a label
     SGB_CUDA(cudaMemcpyAsync(counts_host, counts_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SGB_CUDA(cudaStreamSynchronize(st));
     const int S_new = counts_host[0];
