@@ -776,16 +776,27 @@ children_small(const int* __restrict__ roots_old, int n_old, const int* __restri
     for (int j = threadIdx.x; j < n_old; j += blockDim.x) atomicAdd(cnt + old2new[j], 1);
     __syncthreads();
     block_scan_excl(cnt, n_new, child_off, s_warp);
-    const int lane = threadIdx.x & 31;
-    for (int c = threadIdx.x >> 5; c < n_new; c += blockDim.x >> 5) {     // children_fill: one warp per new cluster
-        int w = child_off[c];
-        const int end = child_off[c + 1];
-        for (int j0 = 0; j0 < n_old && w < end; j0 += 32) {
+    // ordered fill in O(n_old): ONE warp walks the old clusters in ascending order, 32 at a time; lanes with the same new
+    // cluster (match_any) take consecutive slots behind that cluster's cursor, so every child list comes out ascending
+    // (the multi-CTA children_fill scans all of old2new once per new cluster: fine on 148 SMs, quadratic inside one CTA)
+    for (int c = threadIdx.x; c < n_new; c += blockDim.x) cnt[c] = child_off[c];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        volatile int* cursor = cnt;
+        for (int j0 = 0; j0 < n_old; j0 += 32) {
             const int j = j0 + lane;
-            const bool hit = j < n_old && old2new[j] == c;
-            const unsigned m = __ballot_sync(SGB_FULL_MASK, hit);
-            if (hit) child_list[w + __popc(m & ((1u << lane) - 1))] = j;
-            w += __popc(m);
+            const bool valid = j < n_old;
+            const int dest = valid ? old2new[j] : -1 - lane;
+            const unsigned m = __match_any_sync(SGB_FULL_MASK, dest);
+            const int rank = __popc(m & ((1u << lane) - 1u));
+            const int base = valid ? cursor[dest] : 0;
+            __syncwarp();
+            if (valid) {
+                child_list[base + rank] = j;
+                if (rank == 0) cursor[dest] = base + __popc(m);
+            }
+            __syncwarp();
         }
     }
 }
@@ -827,7 +838,7 @@ adj_rows_small(const unsigned* bitmap, int S, int wpr, int* row_cnt, int* row_of
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS)
-csr_rows_small(const unsigned* bitmap, int S, int wpr, int has_edges, int* deg, int* outdeg, int* row_off, int* first, int* nbr, int* eid) {
+csr_degrees_small(const unsigned* bitmap, int S, int wpr, int has_edges, int* deg, int* outdeg, int* row_off, int* first) {
     __shared__ int s_warp[34];
     const int lane = threadIdx.x & 31;
     for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {         // csr_row_degrees
@@ -844,43 +855,6 @@ csr_rows_small(const unsigned* bitmap, int S, int wpr, int has_edges, int* deg, 
     block_scan_excl(deg, S, row_off, s_warp);
     if (!has_edges) return;
     block_scan_excl(outdeg, S, first, s_warp);
-    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {         // csr_row_write
-        const int base = row_off[r];
-        const int indeg = (row_off[r + 1] - base) - (first[r + 1] - first[r]);
-        const int first_r = first[r];
-        int w0 = base;
-        for (int wb = 0; wb < wpr; wb += 32) {
-            const int w = wb + lane;
-            const unsigned bits = w < wpr ? bitmap[(size_t)r * wpr + w] : 0u;
-            const int c = __popc(bits);
-            int inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(SGB_FULL_MASK, inc, o); if (lane >= o) inc += t; }
-            int pos = w0 + inc - c;
-            unsigned b = bits;
-            while (b) {
-                const int j = w * 32 + __ffs(b) - 1;
-                b &= b - 1;
-                int e;
-                if (j > r) {
-                    e = first_r + (pos - base - indeg);
-                } else {                               // edge (j, r): rank of r among the bits above the diagonal of row j
-                    const unsigned* rowj = bitmap + (size_t)j * wpr;
-                    int rank = 0;
-                    for (int ww = j >> 5; ww <= (r >> 5); ++ww) {
-                        unsigned bb = bits_above(rowj[ww], ww, j);
-                        const int hi = r - ww * 32;    // keep columns < r
-                        if (hi < 32) bb &= (hi <= 0 ? 0u : (0xffffffffu >> (32 - hi)));
-                        rank += __popc(bb);
-                    }
-                    e = first[j] + rank;
-                }
-                nbr[pos] = j; eid[pos] = e;
-                ++pos;
-            }
-            w0 += __shfl_sync(SGB_FULL_MASK, inc, 31);
-        }
-    }
 }
 
 }  // namespace
@@ -1018,7 +992,10 @@ extern "C" int sgb_sym_csr(const int* adj, int A, int S, int* row_off, int* nbr,
         { csr_set_bits<<<sgb_div_up(A, 256), 256, 0, st>>>(adj, A, wpr, bitmap); SGB_COUNT_LAUNCH(); }
     }
     if (S <= SMALL_S) {
-        { csr_rows_small<<<1, SMALL_THREADS, 0, st>>>(bitmap, S, wpr, A > 0 ? 1 : 0, deg, outdeg, row_off, first, nbr, eid); SGB_COUNT_LAUNCH(); }
+        // degrees + both scans in one CTA; the row write ranks every lower-triangle edge inside its partner row
+        // (up to wpr words per edge), which wants all the SMs: one warp per row
+        { csr_degrees_small<<<1, SMALL_THREADS, 0, st>>>(bitmap, S, wpr, A > 0 ? 1 : 0, deg, outdeg, row_off, first); SGB_COUNT_LAUNCH(); }
+        if (A > 0) { csr_row_write<<<sgb_div_up(S, 8), 256, 0, st>>>(bitmap, S, wpr, row_off, first, nbr, eid); SGB_COUNT_LAUNCH(); }
         SGB_CHECK_LAUNCH();
         return SGB_OK;
     }
