@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="scenes in flight per GPU (CUDA streams / host threads)")
     ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "off"], help="clock sampler during the timed region")
     ap.add_argument("--switch-interval", type=float, default=0.0, help="sys.setswitchinterval for the scene threads (0 = leave)")
+    ap.add_argument("--gc", default="frozen", choices=["frozen", "default"],
+                    help="frozen: collect + gc.freeze() after setup and no cyclic collections inside the timed regions")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -238,10 +240,20 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        marks = [time.perf_counter()]
+        mallocs = []
         for _ in range(n_steps):
             last = step(scenes, from_host)
             if from_host:
                 last = float(last.item())                   # device -> host read of the step's loss
+            marks.append(time.perf_counter())
+            if os.environ.get("SGB_BENCH_DEBUG"):
+                ms_ = torch.cuda.memory_stats(dev)
+                mallocs.append((ms_.get("num_device_alloc", 0), ms_.get("num_device_free", 0), ms_.get("num_alloc_retries", 0)))
+        if os.environ.get("SGB_BENCH_DEBUG") and rank == 0:  # host-side progress per step (not part of the measurement)
+            sys.stderr.write("host ms per step (%s): %s\n" % ("e2e" if from_host else "resident",
+                                                               " ".join("%.1f" % ((b - a) * 1e3) for a, b in zip(marks[:-1], marks[1:]))))
+            sys.stderr.write("cudaMalloc/cudaFree/retries after each step: %s\n" % " ".join("%d/%d/%d" % m for m in mallocs))
         e1.record()
         torch.cuda.synchronize()
         if dist is not None:
@@ -251,8 +263,28 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), last
 
+    import gc
+    if os.environ.get("SGB_BENCH_DEBUG"):
+        t_gc = {}
+
+        def _gc_cb(phase, info):
+            if phase == "start":
+                t_gc["t"] = time.perf_counter()
+            else:
+                dt = (time.perf_counter() - t_gc.get("t", time.perf_counter())) * 1e3
+                if dt > 5.0:
+                    sys.stderr.write("gc gen%d took %.1f ms (collected %d)\n" % (info["generation"], dt, info["collected"]))
+        gc.callbacks.append(_gc_cb)
     for _ in range(args.warmup):
         step(resident, False)
+    if args.gc == "frozen":
+        # The step is driven by Python threads; a generation-2 cyclic collection over the interpreter's whole heap (torch,
+        # numpy, the scene objects: measured 100-400 ms) inside a timed step would be charged to that step.  Everything that
+        # exists after set-up and warm-up is moved to the permanent generation, and the collector is paused during the timed
+        # regions (reference counting still frees the per-step tensors; a collection runs between the regions).
+        gc.collect()
+        gc.freeze()
+        gc.disable()
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
     if args.sampler == "smi":
@@ -270,11 +302,15 @@ def main():
     pts_per_step = args.scenes * args.points * world
     value = pts_per_step * args.steps / (ms * 1e-3)
     # ---- timed region 2: end to end from pinned host buffers
+    if args.gc == "frozen":
+        gc.collect()
     step(pinned, True)
     ms_e2e, _ = timed(pinned, True, args.steps)
     e2e = pts_per_step * args.steps / (ms_e2e * 1e-3)
 
     # ---- pseudo-label inference (ins_infer) over the same resident batch: reported beside the training number
+    if args.gc == "frozen":
+        gc.collect()
     with torch.no_grad():
         ex.infer_batch(resident, p)
         torch.cuda.synchronize()
