@@ -21,6 +21,22 @@ import torch
 from . import pipeline
 
 
+_reserved = set()      # (device index, raw stream) pairs whose allocator pool has been pre-sized
+
+
+def reserve_current_stream(nbytes: int = 1 << 30, device=None):
+    """Pre-size the caching allocator's pool of the CURRENT stream once (see SceneExecutor.reserve for why)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    if key in _reserved or nbytes <= 0:
+        return
+    _reserved.add(key)
+    big = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    small = [torch.empty(1 << 20, dtype=torch.uint8, device=dev) for _ in range(64)]
+    tiny = [torch.empty(256 << 10, dtype=torch.uint8, device=dev) for _ in range(128)]
+    del big, small, tiny
+
+
 class SceneExecutor:
     def __init__(self, device=None, n_streams: int = 4, reserve_bytes_per_stream: int = 3 << 30):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, pipeline
+from . import _lib, engine, pipeline
 from .pipeline import SceneDevice
 
 
@@ -207,6 +207,7 @@ class SegModel(nn.Module):
         if self.write_files and not os.path.exists(output_root):
             os.makedirs(output_root, exist_ok=True)
 
+        engine.reserve_current_stream(device=data.device)      # once per stream: no cudaMalloc in later forwards
         sc = self._scene(scene_name, data, weak_label)
         mode = "sem_infer" if self.sem_infer else ("ins_infer" if self.ins_infer else "train")
         res = pipeline.forward_scene(sc, self._params(), mode=mode, classifier=self.classifier)
