@@ -61,61 +61,9 @@ __global__ void x9_mean_finish(const double* __restrict__ part, int nb, int N, f
 // ------------------------------------------------------------------------------------------------
 constexpr int NE1_PER_LANE = (NE1 + 31) / 32;   // 6
 
-__global__ void __launch_bounds__(WARPS * 32)
-gram1_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ ctr,
-             double* __restrict__ part /*[grid][NE1]*/) {
-    __shared__ __align__(16) float s_e[WARPS][KNN][CINP];
-    __shared__ double s_red[WARPS][NE1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float (*se)[CINP] = s_e[warp];
-    int et[NE1_PER_LANE], eu[NE1_PER_LANE];
-#pragma unroll
-    for (int m = 0; m < NE1_PER_LANE; ++m) {
-        const int n = lane + 32 * m;
-        et[m] = -1; eu[m] = 0;
-        if (n < CIN) { et[m] = n; eu[m] = -1; }
-        else if (n < NE1) {
-            int q = n - CIN, t = 0;
-            while (q >= CIN - t) { q -= CIN - t; ++t; }
-            et[m] = t; eu[m] = t + q;
-        }
-    }
-    float c9[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) c9[t] = __ldg(ctr + 9 + t);
-    double acc[NE1_PER_LANE];
-#pragma unroll
-    for (int m = 0; m < NE1_PER_LANE; ++m) acc[m] = 0.0;
-
-    for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
-        float xi[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) xi[t] = __ldg(x9 + (size_t)p * 9 + t);
-        __syncwarp();
-        stage_edges(x9, knn, p, lane, se, xi, c9);
-#pragma unroll
-        for (int m = 0; m < NE1_PER_LANE; ++m) {
-            if (et[m] >= 0) {
-                float a = 0.f;
-                if (eu[m] < 0) { for (int k = 0; k < KNN; ++k) a += se[k][et[m]]; }
-                else { for (int k = 0; k < KNN; ++k) a = fmaf(se[k][et[m]], se[k][eu[m]], a); }
-                acc[m] += (double)a;
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < NE1_PER_LANE; ++m) { const int n = lane + 32 * m; if (n < NE1) s_red[warp][n] = acc[m]; }
-    __syncthreads();
-    for (int n = threadIdx.x; n < NE1; n += blockDim.x) {
-        double s = 0;
-        for (int w = 0; w < WARPS; ++w) s += s_red[w][n];
-        part[(size_t)blockIdx.x * NE1 + n] = s;
-    }
-}
-
-// Point-per-lane variant of pass A (the one that runs).  gram1_kernel above stages every edge in shared memory and pays two
-// LDS per FMA for all 189 entries; but an edge feature is e_k = (d_k, c) with d_k = x_j - x_i and c = x_i - centre CONSTANT
-// over the 20 edges of a point, so per point
+// One point per lane.  (The first version staged every edge of a point in shared memory, one warp per point, and paid two
+// LDS per FMA for all 189 entries: 230 us at 150k points, l1tex 91 %.)  An edge feature is e_k = (d_k, c) with
+// d_k = x_j - x_i and c = x_i - centre CONSTANT over the 20 edges of a point, so per point
 //     sum_k e_k e_k^T = [ sum_k d_k d_k^T   (sum_k d_k) c^T ]      sum_k e_k = ( sum_k d_k, 20 c )
 //                       [       .               20 c c^T    ]
 // Only the 45 entries of the d d^T block are per-edge work.  A lane owns one point: it gathers its 20 neighbour rows
@@ -221,128 +169,6 @@ __global__ void pad_rows12_kernel(const float* __restrict__ x9, long long n12, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass A2 (MLP3): moments of the hidden activations h = lrelu(BN1(W1 e)):  H = sum h h^T, t = sum h
-// lane owns rows c0, c0+1 of H (128 fp32 accumulators) + its two entries of t.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS * 32, 1)
-gram2_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ W1,
-             const float* __restrict__ stats1, double* __restrict__ part /*[grid][NE2]*/) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float (*s_e)[KNN][CINP] = reinterpret_cast<float (*)[KNN][CINP]>(smem_raw);
-    float (*s_h)[KNN][COUT] = reinterpret_cast<float (*)[KNN][COUT]>(smem_raw + sizeof(float) * WARPS * KNN * CINP);
-    double* s_acc = reinterpret_cast<double*>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT));   // [NE2]
-    float (*s_w1t)[COUT] = reinterpret_cast<float (*)[COUT]>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT) + sizeof(double) * NE2);  // [t][c]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = lane * 2;
-    for (int i = threadIdx.x; i < COUT * CIN; i += blockDim.x) s_w1t[i % CIN][i / CIN] = __ldg(W1 + i);
-    const float mean0 = stats1[c0], mean1 = stats1[c0 + 1];
-    const float sc0 = stats1[128 + c0], sc1 = stats1[128 + c0 + 1];
-    const float be0 = stats1[192 + c0], be1 = stats1[192 + c0 + 1];
-    float acc[2][COUT];
-#pragma unroll
-    for (int i = 0; i < COUT; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
-    float t0 = 0.f, t1 = 0.f;
-    for (int i = threadIdx.x; i < NE2; i += blockDim.x) s_acc[i] = 0.0;
-    __syncthreads();
-
-    for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
-        float xi[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) xi[t] = __ldg(x9 + (size_t)p * 9 + t);
-        __syncwarp();
-        stage_edges(x9, knn, p, lane, s_e[warp], xi, nullptr);
-#pragma unroll 2
-        for (int k = 0; k < KNN; ++k) {
-            float y0 = 0.f, y1 = 0.f;
-#pragma unroll
-            for (int t = 0; t < CIN; ++t) {
-                const float2 wv = *reinterpret_cast<const float2*>(&s_w1t[t][c0]);
-                const float ev = s_e[warp][k][t];
-                y0 = fmaf(wv.x, ev, y0); y1 = fmaf(wv.y, ev, y1);
-            }
-            const float h0 = lrelu(fmaf(y0 - mean0, sc0, be0));
-            const float h1 = lrelu(fmaf(y1 - mean1, sc1, be1));
-            *reinterpret_cast<float2*>(&s_h[warp][k][c0]) = make_float2(h0, h1);
-            t0 += h0; t1 += h1;
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int k = 0; k < KNN; ++k) {
-            const float2 hh = *reinterpret_cast<const float2*>(&s_h[warp][k][c0]);
-#pragma unroll
-            for (int j4 = 0; j4 < COUT / 4; ++j4) {
-                const float4 v = *reinterpret_cast<const float4*>(&s_h[warp][k][j4 * 4]);
-                acc[0][j4 * 4 + 0] = fmaf(hh.x, v.x, acc[0][j4 * 4 + 0]);
-                acc[0][j4 * 4 + 1] = fmaf(hh.x, v.y, acc[0][j4 * 4 + 1]);
-                acc[0][j4 * 4 + 2] = fmaf(hh.x, v.z, acc[0][j4 * 4 + 2]);
-                acc[0][j4 * 4 + 3] = fmaf(hh.x, v.w, acc[0][j4 * 4 + 3]);
-                acc[1][j4 * 4 + 0] = fmaf(hh.y, v.x, acc[1][j4 * 4 + 0]);
-                acc[1][j4 * 4 + 1] = fmaf(hh.y, v.y, acc[1][j4 * 4 + 1]);
-                acc[1][j4 * 4 + 2] = fmaf(hh.y, v.z, acc[1][j4 * 4 + 2]);
-                acc[1][j4 * 4 + 3] = fmaf(hh.y, v.w, acc[1][j4 * 4 + 3]);
-                if ((j4 & 3) == 3) asm volatile("" ::: "memory");   // keep at most 4 float4 loads in flight (register budget)
-            }
-        }
-    }
-    // fixed-order (warp 0, 1, ...) accumulation into the fp64 block sums
-#pragma unroll 1
-    for (int wv = 0; wv < WARPS; ++wv) {
-        __syncthreads();
-        if (warp == wv) {
-#pragma unroll
-            for (int j = 0; j < COUT; ++j) {
-                s_acc[c0 * COUT + j] += (double)acc[0][j];
-                s_acc[(c0 + 1) * COUT + j] += (double)acc[1][j];
-            }
-            s_acc[COUT * COUT + c0] += (double)t0;
-            s_acc[COUT * COUT + c0 + 1] += (double)t1;
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NE2; i += blockDim.x) part[(size_t)blockIdx.x * NE2 + i] = s_acc[i];
-}
-
-__global__ void __launch_bounds__(256)
-gram2_reduce_kernel(const double* __restrict__ part, int nb, double* __restrict__ moments /*[NE2]*/) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NE2) return;
-    double s = 0;
-    for (int b = 0; b < nb; ++b) s += part[(size_t)b * NE2 + i];
-    moments[i] = s;
-}
-
-// one CTA per output channel c, thread j owns row j of the (symmetrised) H:  E[z_c^2] = w^T H w / M
-__global__ void __launch_bounds__(64)
-bn2_finalize_kernel(const double* __restrict__ moments, double M, const float* __restrict__ W2, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, float* __restrict__ stats, float* __restrict__ var_out) {
-    __shared__ double s_w[COUT];
-    __shared__ double s_q[COUT];
-    __shared__ double s_m[COUT];
-    const int c = blockIdx.x, j = threadIdx.x;
-    s_w[j] = (double)W2[c * COUT + j];
-    __syncthreads();
-    double r = 0;
-    // H is accumulated as full 64x64 (rows by owner lane); symmetrise to cancel the fp32 asymmetry
-    for (int i = 0; i < COUT; ++i) r += 0.5 * (moments[j * COUT + i] + moments[i * COUT + j]) * s_w[i];
-    s_q[j] = s_w[j] * r;
-    s_m[j] = s_w[j] * moments[COUT * COUT + j];
-    __syncthreads();
-    if (j == 0) {
-        double mean = 0, ez2 = 0;
-        for (int i = 0; i < COUT; ++i) { mean += s_m[i]; ez2 += s_q[i]; }      // fixed order
-        mean /= M; ez2 /= M;
-        double var = ez2 - mean * mean;
-        if (var < 0) var = 0;
-        const double invstd = 1.0 / sqrt(var + (double)BN_EPS);
-        stats[c] = (float)mean;
-        stats[64 + c] = (float)invstd;
-        stats[128 + c] = (float)((double)gamma[c] * invstd);
-        stats[192 + c] = beta[c];
-        if (var_out) var_out[c] = (float)var;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // pass B: out[p, c] = max_k of the edge MLP
 // ------------------------------------------------------------------------------------------------
 template <bool TWO>
@@ -434,16 +260,14 @@ inline int persistent_grid(int N) {
     const int cap = 148 * 4;
     return g < cap ? (g < 1 ? 1 : g) : cap;
 }
-constexpr size_t SMEM_STAGE = sizeof(float) * WARPS * KNN * (CINP + COUT);
 }  // namespace sgb_ec
 
 using namespace sgb_ec;
 
-// workspace layout (bytes): [ctr 16 floats][mean partials 256*9 dbl][reduced gram1 192 dbl][gram1 partials grid*NE1 dbl][gram2 partials grid*NE2 dbl]
+// workspace layout (bytes): [ctr 16 floats][mean partials 256*9 dbl][reduced gram1 192 dbl][gram1 partials grid*NE1 dbl][tcgen05 workspace (two_layer)][x12]
 extern "C" size_t sgb_edgeconv_ws_bytes(int N, int two_layer) {
     const size_t g = (size_t)persistent_grid(N);
     size_t b = 128 + 256 * 9 * 8 + 192 * 8 + g * NE1 * 8;
-    if (two_layer) b += (size_t)(148 * 2) * NE2 * 8;
     if (two_layer) { b = (b + 255) & ~(size_t)255; b += sgb_ec2_tc_ws_bytes(N); }
     b = (b + 255) & ~(size_t)255;
     b += (size_t)(N > 0 ? N : 0) * 48;                 // x12: 48-byte padded rows for the 16-byte gathers
@@ -469,7 +293,6 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     double* g1red = mpart + 256 * 9;      // [NE1 -> 192] reduced first-layer moments when the caller keeps none
     double* g1part = g1red + 192;
     const int grid = persistent_grid(N);
-    double* g2part = g1part + (size_t)grid * NE1;
     const double M = (double)N * KNN;
 
     const int mb = N < 256 * 256 ? sgb_div_up(N, 256) : 256;
@@ -487,21 +310,11 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     if (ctr_out) SGB_CUDA(cudaMemcpyAsync(ctr_out, ctr, 18 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (two_layer) {
         // second layer on the tcgen05 tensor cores (mom2 != NULL: also the hidden-layer second moments for the backward)
-        size_t off = 128 + 256 * 9 * 8 + 192 * 8 + (size_t)grid * NE1 * 8 + (size_t)(148 * 2) * NE2 * 8;
+        size_t off = 128 + 256 * 9 * 8 + 192 * 8 + (size_t)grid * NE1 * 8;
         off = (off + 255) & ~(size_t)255;
         return sgb_ec2_tc_forward(x12, knn, N, W1, stats1, W2, gamma2, beta2, out, argk, stats2, var2, mom2, w8 + off, st);
     }
-    if (two_layer) {
-        const int g2 = grid < 148 * 2 ? grid : 148 * 2;
-        const size_t sm2 = SMEM_STAGE + NE2 * sizeof(double) + sizeof(float) * CIN * COUT;
-        SGB_OPT_IN_SMEM(gram2_kernel);
-        { gram2_kernel<<<g2, WARPS * 32, sm2, st>>>(x9, knn, N, W1, stats1, g2part); SGB_COUNT_LAUNCH(); }
-        sgb_bn::reduce_partials(g2part, g2, NE2, mom2, st);
-        { bn2_finalize_kernel<<<COUT, 64, 0, st>>>(mom2, M, W2, gamma2, beta2, stats2, var2); SGB_COUNT_LAUNCH(); }
-        const size_t smB = SMEM_STAGE + sizeof(float) * COUT * COUT;
-        SGB_OPT_IN_SMEM(forward_max_kernel<true>);
-        { forward_max_kernel<true><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, W2, stats2, out, argk); SGB_COUNT_LAUNCH(); }
-    } else {
+    {                                      // single layer (MLP2): recompute the edge layer per neighbour, max over k
         const size_t smB = sizeof(float) * WARPS * KNN * CINP;
         SGB_OPT_IN_SMEM(forward_max_kernel<false>);
         { forward_max_kernel<false><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, nullptr, nullptr, out, argk); SGB_COUNT_LAUNCH(); }
