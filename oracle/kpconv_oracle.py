@@ -199,3 +199,73 @@ def closest_pool(x, inds):
     import torch
     xe = torch.cat([x, torch.zeros(1, x.shape[1], dtype=x.dtype)], dim=0)
     return xe[inds[:, 0].long()]
+
+
+# ------------------------------------------------------------------------------------------------
+# rigid KPFCNN blocks  (kpconv/models/network_blocks.py:147-337, 530-581, 824-948), torch-CPU restatement
+# ------------------------------------------------------------------------------------------------
+def batch_norm_train(x, gamma, beta, eps=1e-6):
+    """network_blocks.py:147-158 with training=True: tf.layers.batch_normalization = batch mean / biased variance."""
+    mean = x.mean(dim=0, keepdim=True)
+    var = ((x - mean) ** 2).mean(dim=0, keepdim=True)
+    return (x - mean) / (var + eps).sqrt() * gamma + beta
+
+
+def block_forward(name, P, layer_ind, inputs, features, radius, config, pre_activations=None, lrelu_masks=None):
+    """One block of network_blocks.py in training mode.  P: dict of the block's variables (fp64 tensors) named as in
+    seggroup_b200.kpconv_blocks; inputs: dict of per-layer lists `points`, `neighbors`, `pools`, `upsamples`.
+    pre_activations: optional list that receives every LeakyReLU input.
+    lrelu_masks: optional iterator of boolean tensors (x > 0 as another implementation saw it), consumed in call order: the
+    BACKWARD of each LeakyReLU then uses that active set instead of its own.  At the kink the derivative jumps from 0.2 to 1,
+    so two implementations whose pre-activations differ in the last bits disagree there by construction; gradient parity is
+    therefore defined for a common active set (the tests check that the two sets differ only within rounding of zero)."""
+    import torch
+    dt = torch.float64
+
+    class _LreluMasked(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, mask):
+            ctx.save_for_backward(mask)
+            return torch.nn.functional.leaky_relu(x, 0.2)
+
+        @staticmethod
+        def backward(ctx, g):
+            (mask,) = ctx.saved_tensors
+            return g * torch.where(mask, torch.ones_like(g), torch.full_like(g, 0.2)), None
+
+    def _lrelu(x):                                                             # :166-167
+        if pre_activations is not None:
+            pre_activations.append(x.detach())
+        if lrelu_masks is not None:
+            return _LreluMasked.apply(x, next(lrelu_masks))
+        return torch.nn.functional.leaky_relu(x, 0.2)
+
+    def bn(x, pre):
+        return batch_norm_train(x, P[pre + ".bn.weight"], P[pre + ".bn.bias"])
+
+    def kp(q, s, idx, f, w):                                                   # :84-101
+        extent = config.KP_extent * radius / config.density_parameter
+        return kpconv_ops(q, s, idx, f, config.K_points.to(dt) * (1.5 * extent), w, extent, config.KP_influence, config.convolution_mode, dtype=dt)
+
+    pts, nbs, pools = inputs["points"], inputs["neighbors"], inputs["pools"]
+    if name == "unary":                                                        # :176-188
+        return _lrelu(bn(features @ P["w"], "bn"))
+    if name in ("simple", "simple_strided"):                                   # :191-238
+        st = name.endswith("strided")
+        q, s, idx = (pts[layer_ind + 1], pts[layer_ind], pools[layer_ind]) if st else (pts[layer_ind], pts[layer_ind], nbs[layer_ind])
+        return _lrelu(bn(kp(q, s, idx, features, P["w"]), "bn"))
+    if name in ("resnetb", "resnetb_strided"):                                 # :290-337, 530-581
+        st = name.endswith("strided")
+        x = _lrelu(bn(features @ P["conv1_w"], "conv1_bn"))
+        q, s, idx = (pts[layer_ind + 1], pts[layer_ind], pools[layer_ind]) if st else (pts[layer_ind], pts[layer_ind], nbs[layer_ind])
+        x = _lrelu(bn(kp(q, s, idx, x, P["conv2_w"]), "conv2_bn"))
+        x = bn(x @ P["conv3_w"], "conv3_bn")
+        shortcut = ind_max_pool(features, pools[layer_ind]) if st else features
+        if "shortcut_w" in P:
+            shortcut = bn(shortcut @ P["shortcut_w"], "shortcut_bn")
+        return _lrelu(x + shortcut)
+    if name == "max_pool":                                                     # :824-832
+        return ind_max_pool(features, pools[layer_ind])
+    if name == "nearest_upsample":                                             # :940-948
+        return closest_pool(features, inputs["upsamples"][layer_ind - 1])
+    raise ValueError("Unknown block name in the architecture definition : " + name)

@@ -110,7 +110,7 @@ def test_batch_neighbors_vs_compiled_reference():
     assert np.array_equal(nb, K.canonical_rows(ref, sub, sub))
 
 
-@pytest.mark.parametrize("cin,cout", [(5, 64), (64, 64), (128, 128), (64, 32)])
+@pytest.mark.parametrize("cin,cout", [(5, 64), (64, 64), (128, 128), (64, 32), (16, 16), (4, 32), (32, 32)])
 @pytest.mark.parametrize("influence,mode", [("linear", "sum"), ("gaussian", "sum"), ("linear", "closest"), ("constant", "sum")])
 def test_kpconv_forward_backward(cin, cout, influence, mode):
     from oracle import kpconv_oracle as K
@@ -227,3 +227,87 @@ def test_ind_max_pool_int64_indices_and_empty():
     assert torch.equal(a, xe[inds].amax(1))
     assert closest_pool(x, inds[:0]).shape == (0, 8)
     assert ind_max_pool(x, inds[:0]).shape == (0, 8)
+
+
+def test_kpfcnn_rigid_blocks_forward_backward():
+    """a two-level encoder / decoder built from the rigid blocks of network_blocks.py (simple, resnetb,
+    resnetb_strided, nearest_upsample, unary) on the library operators, against the fp64 restatement of the same blocks:
+    the chained forward within 1e-4 relative; per block, on the same input, output within 1e-4 and input / parameter
+    gradients within 2e-4 of their largest entry (for the GPU's LeakyReLU active set)."""
+    from types import SimpleNamespace
+    from oracle import kpconv_oracle as K
+    from seggroup_b200 import kpconv_blocks as B
+    from seggroup_b200.kpconv_ops import batch_ordered_neighbors
+    pts, lens = cloud(11, 4000)
+    p0, _ = K.batch_grid_subsampling(pts, lens, 0.06)
+    p1, _ = K.batch_grid_subsampling(p0, np.array([len(p0)], np.int32), 0.12)
+    P0, P1 = cu(p0), cu(p1)
+    r0, r1 = 0.15, 0.30
+    inputs = {"points": [P0, P1], "neighbors": [batch_ordered_neighbors(P0, P0, None, None, r0)[:, :40].contiguous(),
+                                                 batch_ordered_neighbors(P1, P1, None, None, r1)[:, :40].contiguous()],
+              "pools": [batch_ordered_neighbors(P1, P0, None, None, r0)[:, :40].contiguous()],
+              "upsamples": [batch_ordered_neighbors(P0, P1, None, None, r1)[:, :1].contiguous()]}
+    g = torch.Generator().manual_seed(3)
+    kp = torch.rand(15, 3, generator=g) * 2 - 1
+    kp = kp / kp.norm(dim=1, keepdim=True) * torch.rand(15, 1, generator=g) ** (1 / 3)
+    kp[0] = 0
+    cfg = SimpleNamespace(KP_extent=1.0, density_parameter=5.0, KP_influence="linear", convolution_mode="sum", num_kernel_points=15,
+                          use_batch_norm=True, batch_norm_momentum=0.99, fixed_kernel_points="center", K_points=kp)
+    torch.manual_seed(5)
+    arch = [("simple", 0, 4, 32, r0), ("resnetb", 0, 32, 32, r0), ("resnetb_strided", 0, 64, 64, r0), ("resnetb", 1, 128, 64, r1),
+            ("nearest_upsample", 1, None, None, r1), ("unary", 0, 128, 32, r0)]
+    blocks = [B.get_block_ops(n)(cin, fd, cfg).cuda() for n, _, cin, fd, _ in arch]
+    for b in blocks:                                        # non-trivial BN affine parameters
+        for nme, prm in b.named_parameters():
+            if nme.endswith("bn.weight"):
+                prm.data = 0.5 + torch.rand_like(prm)
+            if nme.endswith("bn.bias"):
+                prm.data = 0.2 * torch.randn_like(prm)
+    feats = torch.randn(len(p0), 4, generator=g)
+
+    # chained forward (the whole encoder / decoder) against the fp64 restatement
+    x = feats.cuda()
+    with torch.no_grad():
+        for b, (n, li, _, _, rad) in zip(blocks, arch):
+            x = b(li, inputs, x, rad, cfg, True)
+    cpu_inputs = {k: [t.cpu() for t in v] for k, v in inputs.items()}
+    y = feats.double()
+    stage_in = []
+    with torch.no_grad():
+        for b, (n, li, _, _, rad) in zip(blocks, arch):
+            stage_in.append(y)
+            Pd = {k: v.detach().cpu().double() for k, v in b.named_parameters()}
+            y = K.block_forward(n, Pd, li, cpu_inputs, y, rad, cfg)
+    assert float((x.cpu().double() - y).abs().max()) < 1e-4 * float(y.abs().max())
+
+    # every block on the SAME input (the fp64 features of that stage): output, input gradient and parameter gradients.
+    # LeakyReLU's derivative jumps at 0, so gradients are compared for a common active set: the restatement's backward uses
+    # the sign pattern the GPU saw, and the two patterns may differ only where the fp64 pre-activation is zero to rounding.
+    import torch.nn.functional as F
+    for b, (n, li, _, _, rad), fin in zip(blocks, arch, stage_in):
+        masks = []
+        orig_lrelu = B.leaky_relu
+        B.leaky_relu = lambda f, alpha=0.2: (masks.append((f.detach() > 0).cpu()), F.leaky_relu(f, alpha))[1]
+        try:
+            fd = fin.float().cuda().requires_grad_(True)
+            out = b(li, inputs, fd, rad, cfg, True)
+        finally:
+            B.leaky_relu = orig_lrelu
+        go = torch.randn(out.shape, generator=g)
+        (out * go.cuda()).sum().backward()
+        f64 = fin.float().double().requires_grad_(True)
+        Pd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in b.named_parameters()}
+        pre = []
+        ref = K.block_forward(n, Pd, li, cpu_inputs, f64, rad, cfg, pre_activations=pre, lrelu_masks=iter(masks))
+        assert len(pre) == len(masks), n
+        for xr, m in zip(pre, masks):
+            flipped = (xr > 0) != m
+            assert float(xr[flipped].abs().max() if flipped.any() else 0.0) < 1e-4 * float(xr.abs().max()), n
+        (ref * go.double()).sum().backward()
+        assert float((out.detach().cpu().double() - ref.detach()).abs().max()) < 1e-4 * float(ref.detach().abs().max()), n
+        assert float((fd.grad.cpu().double() - f64.grad).abs().max()) < 2e-4 * float(f64.grad.abs().max()) + 1e-12, n
+        for k, v in b.named_parameters():
+            gref = Pd[k].grad
+            assert gref is not None, (n, k)
+            assert float((v.grad.cpu().double() - gref).abs().max()) < 2e-4 * float(gref.abs().max()) + 1e-9, (n, k)
+            v.grad = None
