@@ -171,15 +171,11 @@ __global__ void pad_rows12_kernel(const float* __restrict__ x9, long long n12, f
 // ------------------------------------------------------------------------------------------------
 // pass B: out[p, c] = max_k of the edge MLP
 // ------------------------------------------------------------------------------------------------
-template <bool TWO>
 __global__ void __launch_bounds__(WARPS * 32)
 forward_max_kernel(const float* __restrict__ x9, const int* __restrict__ knn, int N, const float* __restrict__ W1,
-                   const float* __restrict__ stats1, const float* __restrict__ W2, const float* __restrict__ stats2,
-                   float* __restrict__ out, unsigned char* __restrict__ argk) {
+                   const float* __restrict__ stats1, float* __restrict__ out, unsigned char* __restrict__ argk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float (*s_e)[KNN][CINP] = reinterpret_cast<float (*)[KNN][CINP]>(smem_raw);
-    float (*s_h)[KNN][COUT] = reinterpret_cast<float (*)[KNN][COUT]>(smem_raw + sizeof(float) * WARPS * KNN * CINP);
-    float (*s_w2t)[COUT] = reinterpret_cast<float (*)[COUT]>(smem_raw + sizeof(float) * WARPS * KNN * (CINP + COUT));  // [j][c]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = lane * 2;
     float w[2][CIN];
@@ -188,17 +184,6 @@ forward_max_kernel(const float* __restrict__ x9, const int* __restrict__ knn, in
     const float mean0 = stats1[c0], mean1 = stats1[c0 + 1];
     const float sc0 = stats1[128 + c0], sc1 = stats1[128 + c0 + 1];
     const float be0 = stats1[192 + c0], be1 = stats1[192 + c0 + 1];
-    float m2_0 = 0.f, m2_1 = 0.f, s2_0 = 0.f, s2_1 = 0.f, b2_0 = 0.f, b2_1 = 0.f;
-    if (TWO) {
-        for (int i = threadIdx.x; i < COUT * COUT; i += blockDim.x) {
-            const int c = i / COUT, j = i % COUT;
-            s_w2t[j][c] = __ldg(W2 + i);
-        }
-        m2_0 = stats2[c0]; m2_1 = stats2[c0 + 1];
-        s2_0 = stats2[128 + c0]; s2_1 = stats2[128 + c0 + 1];
-        b2_0 = stats2[192 + c0]; b2_1 = stats2[192 + c0 + 1];
-        __syncthreads();
-    }
     for (int p = blockIdx.x * WARPS + warp; p < N; p += gridDim.x * WARPS) {
         float xi[9];
 #pragma unroll
@@ -207,48 +192,13 @@ forward_max_kernel(const float* __restrict__ x9, const int* __restrict__ knn, in
         stage_edges(x9, knn, p, lane, s_e[warp], xi, nullptr);
         float best0 = -INFINITY, best1 = -INFINITY;
         int bk0 = 0, bk1 = 0;
-        if (!TWO) {
 #pragma unroll
-            for (int k = 0; k < KNN; ++k) {
-                float y0, y1;
-                conv1(s_e[warp], k, w, y0, y1);
-                const float a0 = lrelu(fmaf(y0 - mean0, sc0, be0)), a1 = lrelu(fmaf(y1 - mean1, sc1, be1));
-                if (a0 > best0) { best0 = a0; bk0 = k; }
-                if (a1 > best1) { best1 = a1; bk1 = k; }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < KNN; ++k) {
-                float y0, y1;
-                conv1(s_e[warp], k, w, y0, y1);
-                *reinterpret_cast<float2*>(&s_h[warp][k][c0]) =
-                    make_float2(lrelu(fmaf(y0 - mean0, sc0, be0)), lrelu(fmaf(y1 - mean1, sc1, be1)));
-            }
-            __syncwarp();
-            float z0[KNN], z1[KNN];
-#pragma unroll
-            for (int k = 0; k < KNN; ++k) { z0[k] = 0.f; z1[k] = 0.f; }
-#pragma unroll 2
-            for (int j4 = 0; j4 < COUT / 4; ++j4) {
-                const float2 wa = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 0][c0]);
-                const float2 wb = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 1][c0]);
-                const float2 wc = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 2][c0]);
-                const float2 wd = *reinterpret_cast<const float2*>(&s_w2t[j4 * 4 + 3][c0]);
-#pragma unroll
-                for (int k = 0; k < KNN; ++k) {
-                    const float4 v = *reinterpret_cast<const float4*>(&s_h[warp][k][j4 * 4]);
-                    z0[k] = fmaf(wa.x, v.x, z0[k]); z1[k] = fmaf(wa.y, v.x, z1[k]);
-                    z0[k] = fmaf(wb.x, v.y, z0[k]); z1[k] = fmaf(wb.y, v.y, z1[k]);
-                    z0[k] = fmaf(wc.x, v.z, z0[k]); z1[k] = fmaf(wc.y, v.z, z1[k]);
-                    z0[k] = fmaf(wd.x, v.w, z0[k]); z1[k] = fmaf(wd.y, v.w, z1[k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < KNN; ++k) {
-                const float a0 = lrelu(fmaf(z0[k] - m2_0, s2_0, b2_0)), a1 = lrelu(fmaf(z1[k] - m2_1, s2_1, b2_1));
-                if (a0 > best0) { best0 = a0; bk0 = k; }
-                if (a1 > best1) { best1 = a1; bk1 = k; }
-            }
+        for (int k = 0; k < KNN; ++k) {
+            float y0, y1;
+            conv1(s_e[warp], k, w, y0, y1);
+            const float a0 = lrelu(fmaf(y0 - mean0, sc0, be0)), a1 = lrelu(fmaf(y1 - mean1, sc1, be1));
+            if (a0 > best0) { best0 = a0; bk0 = k; }
+            if (a1 > best1) { best1 = a1; bk1 = k; }
         }
         *reinterpret_cast<float2*>(out + (size_t)p * COUT + c0) = make_float2(best0, best1);
         if (argk) *reinterpret_cast<uchar2*>(argk + (size_t)p * COUT + c0) = make_uchar2((unsigned char)bk0, (unsigned char)bk1);
@@ -316,8 +266,8 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
     }
     {                                      // single layer (MLP2): recompute the edge layer per neighbour, max over k
         const size_t smB = sizeof(float) * WARPS * KNN * CINP;
-        SGB_OPT_IN_SMEM(forward_max_kernel<false>);
-        { forward_max_kernel<false><<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, nullptr, nullptr, out, argk); SGB_COUNT_LAUNCH(); }
+        SGB_OPT_IN_SMEM(forward_max_kernel);
+        { forward_max_kernel<<<grid, WARPS * 32, smB, st>>>(x9, knn, N, W1, stats1, out, argk); SGB_COUNT_LAUNCH(); }
     }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
