@@ -55,3 +55,36 @@ def test_reference_still_agrees_when_present(scene, tmp_path):
     gold = load_golden("sem_infer", 4.0)
     for k, v in res["labels"].items():
         assert np.array_equal(v, gold["label/" + k]), k
+
+
+# ---- BASELINE.json configs[0]: one scene of 50,000 points / ~350 segments (oracle/make_golden_50k.py)
+def load_golden_50k(mode):
+    return np.load(os.path.join(GOLDEN, "seggroup50k_%s_g4.npz" % mode))
+
+
+@pytest.fixture(scope="module")
+def scene50k():
+    from seggroup_b200 import synth
+    return synth.make_scene(7, 50000)
+
+
+@pytest.mark.parametrize("mode", ["ins_infer", "train"])
+def test_oracle_matches_reference_golden_50k(scene50k, mode):
+    from oracle import seggroup_oracle as O
+    gold = load_golden_50k(mode)
+    params = O.init_params(1, 4.0)
+    torch.manual_seed(1001)
+    out = O.forward(scene50k, params, mode=mode, tie="torch", want_grads=(mode == "train"))
+    for k in gold.files:
+        if k.startswith("label/"):
+            assert np.array_equal(out["labels"][k[6:]], gold[k]), k
+    metrics = [gold["out/%d" % i] for i in range(4 if mode == "train" else 3)]
+    if mode == "train":
+        assert np.allclose(out["loss_raw"], metrics[0], rtol=1e-5)
+        metrics = metrics[1:]
+        for k in O.TRAINABLE:
+            if "grad/" + k in gold.files:
+                gr = gold["grad/" + k]
+                assert np.abs(out["grads"][k].numpy() - gr).max() <= 1e-5 * np.abs(gr).max() + 1e-9, k
+    for a, b in zip(out["metrics"], metrics):
+        assert np.allclose(a, b, atol=1e-6)
