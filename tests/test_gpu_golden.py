@@ -77,12 +77,12 @@ def test_cuda_matches_reference_golden_50k(mode):
         metrics = metrics[1:]
         (res.loss_raw[:, 0].sum() / res.loss_raw[:, 1].sum()).backward()
         # Gradients.  The classifier head must match the reference fixture (1e-3 of the largest entry).  Below the head the
-        # gradient of every segment max pooling goes to ONE of the maximal rows, and the pooled GCN features are ReLU outputs,
-        # i.e. full of exact ties at 0: which row wins is not defined by the reference (torch's CPU reduction, its CUDA
-        # reduction and a first-maximum rule all pick differently).  Swapping torch's CPU order for the first-maximum rule in
-        # the ORACLE alone (tie="canonical") already moves these gradients by 1-3 % in relative L2 at this size (< 1e-3 at 8k
-        # points, where few ties occur), so that is the resolution at which the fixture can pin them; the CUDA path must
-        # stay within that distance of both the fixture and the first-maximum restatement.
+        # result depends on which of several EXACTLY tied candidates torch.topk puts into a kNN list (coincident points:
+        # duplicated vertices, tiled members of the 64-point clouds) — implementation-defined in the reference (model.py:35).
+        # Switching only that rule in the ORACLE (tie="canonical": score desc, position asc, the rule of the kernels) keeps
+        # every label, moves the loss by 9e-6 and these gradients by 1-3 % in relative L2 at this size (< 1e-3 at 8k points),
+        # so that is the resolution at which the fixture pins them; the CUDA path must stay within that distance of both the
+        # fixture and the canonical-rule restatement.
         from oracle import seggroup_oracle as O
         params_cpu = O.init_params(1, 4.0)              # (seeds torch itself: the dropout seed comes after it)
         torch.manual_seed(1001)
@@ -96,6 +96,6 @@ def test_cuda_matches_reference_golden_50k(mode):
                     assert np.abs(gg - gr).max() / (np.abs(gr).max() + 1e-30) < 1e-3, k
                 else:
                     assert np.linalg.norm(gg - gr) / (np.linalg.norm(gr) + 1e-30) < 5e-2, ("vs the torch-CPU fixture", k)
-                    assert np.linalg.norm(gg - gc) / (np.linalg.norm(gc) + 1e-30) < 5e-2, ("vs the first-maximum rule", k)
+                    assert np.linalg.norm(gg - gc) / (np.linalg.norm(gc) + 1e-30) < 5e-2, ("vs the canonical kNN tie rule", k)
     for a, b in zip(res.metrics, metrics):
         assert np.allclose(a.cpu().numpy(), b, atol=1e-6)
