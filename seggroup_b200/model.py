@@ -90,10 +90,36 @@ def _get_writer():
     return _writer
 
 
-def load_scene_files(scene_name: str, data_root: str = os.path.join("dataset", "scannet")):
+def _side_paths(scene_name, data_root):
+    return (os.path.join(data_root, "adj", "mesh", "resampled", scene_name, scene_name + ".adj.pth"),
+            os.path.join(data_root, "data", "resampled", scene_name, scene_name + ".unmap.pth"),
+            os.path.join(data_root, "label", "real", "resampled", scene_name, scene_name + ".seg.json"))
+
+
+def load_scene_files(scene_name: str, data_root: str = os.path.join("dataset", "scannet"), cache_dir: str | None = None):
     """Host-side parse of the side files SegModel.forward reads (model.py:696-699, 713-724):
     adj.pth [E0,2] i64, unmap.pth [N_raw] i64, seg.json (list of member lists).  Returns numpy arrays:
-    (adj int32 [E0,2], unmap int64, seg_off int32 [S1+1], seg_members int32 [N])."""
+    (adj int32 [E0,2], unmap int64, seg_off int32 [S1+1], seg_members int32 [N]).
+
+    cache_dir (optional): binary CSR cache of the parsed forms, one `.npz` per scene.  seg.json is a JSON
+    list of N Python lists (the reference re-parses it on every forward: ~0.1 s per 150k-point scene, more than the whole
+    forward takes on the device); the cache stores the four arrays as they are uploaded and is rebuilt whenever one of the
+    three source files is newer than it."""
+    if cache_dir is not None:
+        cpath = os.path.join(cache_dir, scene_name + ".sgbcache.npz")
+        try:
+            src_mtime = max(os.path.getmtime(p) for p in _side_paths(scene_name, data_root))
+            if os.path.getmtime(cpath) >= src_mtime:
+                with np.load(cpath) as z:
+                    return z["adj"], z["unmap"], z["seg_off"], z["seg_members"]
+        except Exception:                                        # missing, stale, truncated or foreign file: rebuild
+            pass
+        out = load_scene_files(scene_name, data_root, None)
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = cpath + ".tmp%d.npz" % os.getpid()
+        np.savez(tmp, adj=out[0], unmap=out[1], seg_off=out[2], seg_members=out[3])
+        os.replace(tmp, cpath)                                   # atomic: concurrent ranks may build the same scene
+        return out
     adj = torch.load(os.path.join(data_root, "adj", "mesh", "resampled", scene_name, scene_name + ".adj.pth"))
     unmap = torch.load(os.path.join(data_root, "data", "resampled", scene_name, scene_name + ".unmap.pth"))
     with open(os.path.join(data_root, "label", "real", "resampled", scene_name, scene_name + ".seg.json"), "r") as f:
@@ -129,6 +155,7 @@ class SegModel(nn.Module):
         self.classifier = Classifier(dim_in=256, dim_out=40)
         # not part of the reference surface
         self.cache_scenes = True
+        self.scene_cache_dir = os.environ.get("SGB_SCENE_CACHE_DIR") or None      # opt-in binary CSR cache of the side files
         self.async_export = True
         self.write_files = True
         self._scene_cache = {}
@@ -149,7 +176,7 @@ class SegModel(nn.Module):
         key = (scene_name, dev)
         side = self._scene_cache.get(key) if self.cache_scenes else None
         if side is None:
-            adj, unmap, seg_off, seg_members = load_scene_files(scene_name, self.data_root)
+            adj, unmap, seg_off, seg_members = load_scene_files(scene_name, self.data_root, self.scene_cache_dir)
             real = torch.load(os.path.join(self.data_root, 'label', 'real', 'raw', scene_name, scene_name + '.label.pth'))
             t = lambda a: torch.as_tensor(a).to(dev, non_blocking=True)
             side = dict(adj0=t(adj), unmap=t(unmap), seg_off=t(seg_off), seg_members=t(seg_members), real=real.to(dev))
