@@ -4,9 +4,11 @@ neighbours and the rigid KPConv operator.  Only tests/, __graft_entry__.smoke() 
 Pinning: grid subsampling and neighbours are checked against the compiled, unmodified reference cores
 (oracle/_ref, tests/test_kpconv_oracle.py) through the canonical forms defined here — the reference's output
 ORDER is libstdc++ hash-map iteration order / std::sort tie order, which no other implementation can follow
-(SURVEY.md 7.3 #4, #5).  `kpconv_ops` restates kpconv/kernels/convolution_ops.py:161-249 (TensorFlow is not
-installable here, so it is pinned only by derivation: PARITY UNPINNED for that function, fp64 evaluation is the
-golden).
+(SURVEY.md 7.3 #4, #5).  `kpconv_ops`, `kpconv_deform_ops`, `kpconv_deformable`, the index
+pools and `block_forward` restate kpconv/kernels/convolution_ops.py:161-493 and kpconv/models/network_blocks.py; they are
+pinned by golden vectors minted by EXECUTING those unmodified reference files on a torch-backed stand-in for the TensorFlow
+primitives they call (oracle/tf_shim.py, oracle/make_golden_kpconv.py, tests/test_kpconv_reference_pin.py; TensorFlow
+itself is not installable here): outputs and gradients agree to 2e-6 in float64.
 
 Canonical forms:
   * subsampled voxels are listed per batch element in order of FIRST OCCURRENCE (the point with the smallest
@@ -184,6 +186,67 @@ def kpconv_ops(query_points, support_points, neighbors_indices, features, K_poin
 
 
 # ------------------------------------------------------------------------------------------------
+# deformable KPConv  (kpconv/kernels/convolution_ops.py:252-493)
+# ------------------------------------------------------------------------------------------------
+def kpconv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations, K_values,
+                      KP_extent, KP_influence="linear", mode="sum"):
+    """convolution_ops.py:371-493 in torch (differentiable w.r.t. features, K_values, offsets, modulations).
+
+    The reference compacts every neighbour row to the neighbours that lie within KP_extent of at least one DEFORMED kernel
+    point (:429-445: in_range -> top_k -> batch_gather, dropped entries re-pointed at the shadow row, whose feature is zero).
+    Dropping a neighbour == multiplying all its K influence weights by zero, which is how it is written here: no data-dependent
+    shapes, same result (for 'linear' the mask is implied by the clamp; for 'gaussian' / 'constant' / 'closest' it is not)."""
+    import torch
+    dt = features.dtype
+    q = query_points.to(dt); s = support_points.to(dt); Kp = K_points.to(dt)
+    idx = neighbors_indices.long()
+    n_kp = Kp.shape[0]
+    s = torch.cat([s, torch.ones_like(s[:1, :]) * 1000], dim=0)                # :405-406 (shadow point at 1000, not 1e6)
+    nb = s[idx] - q.unsqueeze(1)                                               # :409-412  [n, W, 3]
+    dkp = offsets.to(dt) + Kp                                                  # :415      [n, K, 3]
+    sq = ((nb.unsqueeze(2) - dkp.unsqueeze(1)) ** 2).sum(dim=3)                # :418-423  [n, W, K]
+    in_range = (sq < KP_extent ** 2).any(dim=2)                                # :426      [n, W]
+    if KP_influence == "constant":                                             # :450-453
+        w = (sq < KP_extent ** 2).to(dt)
+    elif KP_influence == "linear":                                             # :455-458
+        w = torch.clamp(1 - torch.sqrt(sq) / KP_extent, min=0.0)
+    elif KP_influence == "gaussian":                                           # :460-464
+        w = torch.exp(-sq / (2 * (KP_extent * 0.3) ** 2 + 1e-9))
+    else:
+        raise ValueError("Unknown influence function type (config.KP_influence)")
+    if mode == "closest":                                                      # :469-471
+        w = w * torch.nn.functional.one_hot(torch.argmin(sq, dim=2), n_kp).to(dt)
+    elif mode != "sum":
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    w = w * in_range.unsqueeze(2).to(dt)                                       # :429-445 (see above)
+    f = torch.cat([features, torch.zeros_like(features[:1, :])], dim=0)        # :476
+    wf = torch.matmul(w.transpose(1, 2), f[idx])                               # :479-482  [n, K, Cin]
+    if modulations is not None:                                                # :485-486
+        wf = wf * modulations.to(dt).unsqueeze(2)
+    return torch.matmul(wf.permute(1, 0, 2), K_values.to(dt)).sum(dim=0)        # :489-493
+
+
+def kpconv_deformable(query_points, support_points, neighbors_indices, features, K_points, K_values, K_values0, b0, KP_extent,
+                      KP_influence="linear", aggregation_mode="sum", modulated=False):
+    """convolution_ops.py:252-368 with K_points explicit: a rigid KPConv with its own weights K_values0 [K, Cin, 3K (+K)]
+    and bias b0 produces per-query kernel-point offsets (in units of KP_extent) and, if `modulated`, 2*sigmoid modulations;
+    the deformed convolution then uses K_values."""
+    import torch
+    n_kp = K_points.shape[0]
+    f0 = kpconv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values0, KP_extent, KP_influence,
+                    aggregation_mode, dtype=features.dtype) + b0                # :324-332
+    if modulated:                                                              # :334-342
+        offsets = f0[:, :3 * n_kp].reshape(-1, n_kp, 3)
+        modulations = 2 * torch.sigmoid(f0[:, 3 * n_kp:])
+    else:                                                                      # :344-350
+        offsets = f0.reshape(-1, n_kp, 3)
+        modulations = None
+    offsets = offsets * KP_extent                                              # :353
+    return kpconv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations, K_values,
+                             KP_extent, KP_influence, aggregation_mode)
+
+
+# ------------------------------------------------------------------------------------------------
 # index pooling beside KPConv  (kpconv/models/network_blocks.py:49-81)
 # ------------------------------------------------------------------------------------------------
 def ind_max_pool(x, inds):
@@ -254,11 +317,17 @@ def block_forward(name, P, layer_ind, inputs, features, radius, config, pre_acti
         st = name.endswith("strided")
         q, s, idx = (pts[layer_ind + 1], pts[layer_ind], pools[layer_ind]) if st else (pts[layer_ind], pts[layer_ind], nbs[layer_ind])
         return _lrelu(bn(kp(q, s, idx, features, P["w"]), "bn"))
-    if name in ("resnetb", "resnetb_strided"):                                 # :290-337, 530-581
+    if name in ("resnetb", "resnetb_strided", "resnetb_deformable", "resnetb_deformable_strided"):   # :290-337, 393-440, 530-581, 641-692
         st = name.endswith("strided")
         x = _lrelu(bn(features @ P["conv1_w"], "conv1_bn"))
         q, s, idx = (pts[layer_ind + 1], pts[layer_ind], pools[layer_ind]) if st else (pts[layer_ind], pts[layer_ind], nbs[layer_ind])
-        x = _lrelu(bn(kp(q, s, idx, x, P["conv2_w"]), "conv2_bn"))
+        if "deformable" in name:                                               # :104-122 -> convolution_ops.py:252-368
+            extent = config.KP_extent * radius / config.density_parameter
+            x = kpconv_deformable(q.to(dt), s.to(dt), idx, x, config.K_points.to(dt) * (1.5 * extent), P["conv2_w"], P["conv2_offset_w"],
+                                  P["conv2_offset_b"], extent, config.KP_influence, config.convolution_mode, getattr(config, "modulated", False))
+            x = _lrelu(bn(x, "conv2_bn"))
+        else:
+            x = _lrelu(bn(kp(q, s, idx, x, P["conv2_w"]), "conv2_bn"))
         x = bn(x @ P["conv3_w"], "conv3_bn")
         shortcut = ind_max_pool(features, pools[layer_ind]) if st else features
         if "shortcut_w" in P:

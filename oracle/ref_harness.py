@@ -162,6 +162,13 @@ def run_reference(tree_root: str, scene_index: int, *, mode: str = "train", seed
                 f = getattr(mod, fn)
                 f.__defaults__ = (data.shape[0],)
         cap = Capture(mod) if capture else contextlib.nullcontext()
+        # ReLU margin of the two GCN layers (model.py:151): a pre-activation within rounding of zero makes the gradient
+        # implementation-defined (the derivative jumps there), so fixtures record how close the reference got to the kink.
+        # Forward hooks observe; they do not change what the reference computes.
+        margins = {}
+        hooks = [getattr(model, g).fc.register_forward_hook(
+            lambda m, i, o, g=g: margins.__setitem__(g, (float(o.detach().abs().min()), float(o.detach().abs().max()))))
+            for g in ("gcn_2", "gcn_3")]
         torch.manual_seed(seed + 1000)   # dropout mask seed (classifier, model.py:159)
         with cap:
             if mode == "train":
@@ -169,7 +176,9 @@ def run_reference(tree_root: str, scene_index: int, *, mode: str = "train", seed
             else:
                 with torch.no_grad():
                     out = model(data.unsqueeze(0), weak_label.unsqueeze(0), info.unsqueeze(0))
-        res = {"init_state": init_state, "out": [o.detach().clone() for o in out]}
+        for h in hooks:
+            h.remove()
+        res = {"init_state": init_state, "out": [o.detach().clone() for o in out], "relu_margin": margins}
         if mode == "train" and backward:
             loss_raw = out[0]
             loss = torch.sum(loss_raw[:, 0]) / torch.sum(loss_raw[:, 1])

@@ -307,8 +307,25 @@ def edge_distance(feat, adj):
     return F.pairwise_distance(feat[adj[:, 0], :], feat[adj[:, 1], :])
 
 
-def gcn_forward(w, feat, adj, sims):
+class _ReluWithActiveSet(torch.autograd.Function):
+    """relu(z) whose BACKWARD uses a given active set instead of z > 0.  The derivative of ReLU jumps at 0, so two
+    implementations whose pre-activations differ in the last bits disagree on the gradient of an entry that is zero to
+    rounding; gradient parity is therefore defined for a common active set (the tests check that the two sets differ only where
+    |z| is within rounding of zero)."""
+    @staticmethod
+    def forward(ctx, z, mask):
+        ctx.save_for_backward(mask)
+        return F.relu(z)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * mask.to(g.dtype), None
+
+
+def gcn_forward(w, feat, adj, sims, keep=None, tag="", relu_mask=None):
     """model.py:305-309 + 141-151 — dense A = I + sym(sims), row-normalise, relu(fc(A X))."""
+    keep = keep or (lambda name, t: t)
     S = feat.shape[0]
     A = torch.eye(S)
     adj = torch.as_tensor(adj, dtype=torch.long)
@@ -316,7 +333,9 @@ def gcn_forward(w, feat, adj, sims):
         A[adj[:, 0], adj[:, 1]] = sims
         A[adj[:, 1], adj[:, 0]] = sims
     A = A / A.sum(1, keepdim=True).repeat(1, S)
-    return F.relu(F.linear(A.mm(feat), w))
+    AX = keep("AX_" + tag, A.mm(feat))
+    Z = keep("Z_" + tag, F.linear(AX, w))
+    return F.relu(Z) if relu_mask is None else _ReluWithActiveSet.apply(Z, relu_mask)
 
 
 def centralized(data, clusters):
@@ -395,16 +414,24 @@ def children_groups(new: Level, old: Level):
     return g
 
 
-def forward(scene, params, mode="train", tie="torch", dropout_mask=None, want_grads=False):
+def forward(scene, params, mode="train", tie="torch", dropout_mask=None, want_grads=False, relu_masks=None):
     """Restatement of SegModel.forward (model.py:684-932) for one scene.
 
     scene: seggroup_b200.synth.Scene (or anything with the same fields).  params: state_dict-keyed dict.
+    relu_masks: optional {"2": bool [S2,192], "3": bool [S3,256]} active sets for the BACKWARD of the two GCN ReLUs.
     Returns a dict of outputs and intermediates; with want_grads the trainable params get .grad."""
     p = {k: v.clone() for k, v in params.items()}
     if want_grads:
         for k in TRAINABLE:
             p[k].requires_grad_(True)
     out = {}
+    live = out["_live"] = {}        # non-detached stage tensors (retain_grad) for stage-by-stage gradient comparisons
+
+    def keep(name, t):
+        if want_grads and t.requires_grad:
+            t.retain_grad()
+        live[name] = t
+        return t
     data = torch.from_numpy(np.ascontiguousarray(scene.data))
     N = data.shape[0]
     unmap = np.asarray(scene.unmap, np.int64)
@@ -437,12 +464,13 @@ def forward(scene, params, mode="train", tie="torch", dropout_mask=None, want_gr
     Feat_1, knn_1 = mlp1_forward(p, clouds, tie)
     out["knn_1"] = knn_1
     out["Feat_1"] = Feat_1.detach().clone()
+    keep("Feat_1", Feat_1)
     d1 = edge_distance(Feat_1, adj_1)
     out["dists_1"] = d1.detach().clone()
     _, adj_unc = group_nearby(uf, d1.detach().numpy(), adj_1, L1.roots, 3 if sem_infer else 6)
     L2 = Level(uf)
     adj_2 = update_adj(adj_unc, L2.seg2cluster[L1.roots])
-    Feat_2 = segment_max(Feat_1, children_groups(L2, L1))
+    Feat_2 = keep("Feat_2", segment_max(Feat_1, children_groups(L2, L1)))
     labels["layer_2.seg"], labels["layer_2.ins"], labels["layer_2.sem"] = L2.point_labels(N, unmap)
     out["adj_2"] = adj_2
     out["levels"] = [L1, L2]
@@ -458,17 +486,17 @@ def forward(scene, params, mode="train", tie="torch", dropout_mask=None, want_gr
         fm = mlp(p, x9, knn)
         out["knn_" + tag] = knn
         out["Feat_mlp_" + tag] = fm.detach().clone()
-        fm = segment_max(fm, Lc.points)
-        Fc = torch.cat([Feat_c, fm], dim=-1)
-        sims = torch.exp(-edge_distance(Fc, adj_c) * (1 / 8))
-        Fc = gcn_forward(p[gcn_key], Fc, adj_c, sims)
+        fm = keep("pool_" + tag, segment_max(fm, Lc.points))
+        Fc = keep("cat_" + tag, torch.cat([Feat_c, fm], dim=-1))
+        sims = keep("sims_" + tag, torch.exp(-keep("d_" + tag, edge_distance(Fc, adj_c)) * (1 / 8)))
+        Fc = keep("gcn_" + tag, gcn_forward(p[gcn_key], Fc, adj_c, sims, keep, tag, (relu_masks or {}).get(tag)))
         out["Feat_gcn_" + tag] = Fc.detach().clone()
         dd = edge_distance(Fc, adj_c)
         out["dists_" + tag] = dd.detach().clone()
         _, unc = group_nearby(uf, dd.detach().numpy(), adj_c, Lc.roots, 2)
         Ln = Level(uf)
         adj_n = update_adj(unc, Ln.seg2cluster[Lc.roots])
-        Fn = segment_max(Fc, children_groups(Ln, Lc))
+        Fn = keep("Feat_" + str(int(tag) + 1), segment_max(Fc, children_groups(Ln, Lc)))
         return Ln, Fn, adj_n
 
     L3, Feat_3, adj_3 = semantic_layer(L2, Feat_2, adj_2, mlp2_forward, "gcn_2.fc.weight", "2")
@@ -530,6 +558,7 @@ def forward(scene, params, mode="train", tie="torch", dropout_mask=None, want_gr
     L5, Feat_5 = Lo, Feat
     out["levels"].append(L5)
     out["Feat_5"] = Feat_5.detach().clone()
+    keep("Feat_5", Feat_5)
     _, labels["final.ins"], labels["final.sem"] = L5.point_labels(N, unmap)
     out["labels"] = labels
     out["metrics"] = evaluate(np.asarray(scene.real_label), labels["final.sem"], labels["final.ins"])

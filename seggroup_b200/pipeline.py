@@ -169,11 +169,12 @@ class ForwardResult:
     status: int = 0
 
 
-def _gcn(p, key, Fc, adj, csr):
-    d = EdgeDistFn.apply(Fc, adj, *csr)
-    sims = torch.exp(-d * (1 / 8))
-    AX = GcnAggFn.apply(Fc, sims, adj, *csr)
-    return F.relu(F.linear(AX, p[key]))
+def _gcn(p, key, Fc, adj, csr, keep=None, tag=""):
+    keep = keep or (lambda name, t: t)
+    d = keep("d_" + tag, EdgeDistFn.apply(Fc, adj, *csr))
+    sims = keep("sims_" + tag, torch.exp(-d * (1 / 8)))
+    AX = keep("AX_" + tag, GcnAggFn.apply(Fc, sims, adj, *csr))
+    return F.relu(keep("Z_" + tag, F.linear(AX, p[key])))
 
 
 def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool = False, dropout_mask=None,
@@ -185,6 +186,15 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     sem_infer = mode == "sem_infer"
     dev = sc.data.device
     status = torch.zeros(1, dtype=I32, device=dev)
+    live = res.aux.setdefault("_live", {}) if keep_aux else None
+
+    def keep(name, t):
+        """parity tests: keep the (non-detached) stage tensor and its gradient"""
+        if live is not None:
+            if t.requires_grad:
+                t.retain_grad()
+            live[name] = t
+        return t
 
     def put_labels(tag, L, seg=True):
         if not export:
@@ -210,7 +220,9 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     d1 = ops.edge_dist(Feat_1.detach(), adj_1)
     L2 = step(0, old=L1, dist=d1, th=3.0 if sem_infer else 6.0)
     adj_2 = L2.adj
-    Feat_2, _ = SegmentMaxFn.apply(Feat_1, L2.ch_off, L2.ch_list)
+    keep("Feat_1", Feat_1)
+    Feat_2, arg_2 = SegmentMaxFn.apply(Feat_1, L2.ch_off, L2.ch_list)
+    keep("Feat_2", Feat_2)
     put_labels("layer_2", L2)
     res.levels.append(L2)
     if keep_aux:
@@ -244,11 +256,13 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
         res.bn_stats[pre + ".bn1"] = (stats[0, 0], var[0], sc.n_points * 20)
         if two:
             res.bn_stats[pre + ".bn2"] = (stats[1, 0], var[1], sc.n_points * 20)
-        Fc = torch.cat([Feat_c, fm], dim=-1)
-        Fg = _gcn(p, gcn_key, Fc, adj_c, Lc.csr)
+        keep("pool_" + tag, fm)
+        Fc = keep("cat_" + tag, torch.cat([Feat_c, fm], dim=-1))
+        Fg = keep("gcn_" + tag, _gcn(p, gcn_key, Fc, adj_c, Lc.csr, keep, tag))
         dd = ops.edge_dist(Fg.detach().contiguous(), adj_c)
         Ln = step(0, old=Lc, dist=dd, th=2.0)
         Fn, _ = SegmentMaxFn.apply(Fg, Ln.ch_off, Ln.ch_list)
+        keep("Feat_" + str(int(tag) + 1), Fn)
         if keep_aux:
             res.aux.update({"knn_" + tag: knn, "Feat_mlp_" + tag: feat_pts, "Feat_gcn_" + tag: Fg.detach(), "dists_" + tag: dd,
                             "x9_" + tag: x9})
@@ -282,6 +296,7 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     put_labels("final", L5, seg=False)
     if keep_aux:
         res.aux["Feat_5"] = Feat_5.detach()
+        keep("Feat_5", Feat_5)
     if sc.real_label is not None and export:
         res.metrics = evaluate(sc.real_label, res.labels["final.sem"], res.labels["final.ins"], status)
     res.status = L5.status
