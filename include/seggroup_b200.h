@@ -88,6 +88,10 @@ int sgb_segment_pool_max_bwd(const float* grad_out, const int* argmax, int S, in
 size_t sgb_cluster_knn_ws_bytes(int N, int S);
 int sgb_cluster_knn(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
                     int k, int* knn, void* ws, size_t ws_bytes, void* stream);
+/* scene batch: neighbour ids are written RELATIVE to the scene's first point (scene_pt_off [n_scenes+1], device), i.e. exactly
+ * the lists the reference builds for that scene alone, incl. the "unfilled columns point at point 0" rule of model.py:513-518. */
+int sgb_cluster_knn_scenes(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
+                           int k, int* knn, const int* scene_pt_off, int n_scenes, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a4  per-cluster fixed-size clouds
@@ -186,6 +190,15 @@ size_t sgb_level_ws_bytes(int S1);
 int sgb_level_build(const int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
                     int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
                     int* cl_ins, int* cl_sem, int* cl_rootpt, int* counts, void* ws, size_t ws_bytes, void* stream);
+/* Scene batches.  seggroup/train.py:92 forces batch size 1 (one scene per rank per step, model.py:684-693 unpacks it); the
+ * `*_scenes` entry points take SEVERAL scenes concatenated into one block-diagonal graph (point / segment ids offset by the
+ * scene's base, no edge between scenes) so that one launch serves the whole batch, and keep every per-scene rule of the
+ * reference: scene_seg_off / scene_cl_off / scene_pt_off [n_scenes+1] (device) are the level-1 segment, cluster and point
+ * ranges of the scenes.  With n_scenes == 1 and NULL scene arrays they are the single-scene entry points. */
+int sgb_level_build_scenes(const int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
+                           int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
+                           int* cl_ins, int* cl_sem, int* cl_rootpt, int* counts,
+                           const int* scene_seg_off, int n_scenes, int* scene_cl_off, void* ws, size_t ws_bytes, void* stream);
 /* cluster_new_to_old (model.py:760-768): old2new [n_old]; child_off [n_new+1] / child_list [n_old] = old dense
  * cluster ids of every new cluster, ascending. */
 size_t sgb_children_ws_bytes(int n_new);
@@ -218,6 +231,18 @@ int sgb_level_step(int mode, const int* adj_old, int A_old, const int* roots_old
                    int* cl_ins, int* cl_sem, int* cl_rootpt, int* old2new, int* child_off, int* child_list,
                    int* adj_new, int* csr_off, int* csr_nbr, int* csr_eid,
                    int* status, int* counts_dev, int* counts_host, void* ws, size_t ws_bytes, void* stream);
+/* scene batch: counts_dev / counts_host hold 4 + n_scenes + 1 ints (the four counters, then scene_cl_off_new); the order-dependent
+ * replays run one CTA per scene (max_scene_segs / max_scene_cl_old size their shared-memory state). */
+int sgb_level_step_scenes(int mode, const int* adj_old, int A_old, const int* roots_old, int S_old, const float* dist, float th,
+                          int sweep_cap, const int* csr_off_old, const int* csr_nbr_old, const int* csr_eid_old,
+                          const int* edges, int E, const int* map,
+                          int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
+                          int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
+                          int* cl_ins, int* cl_sem, int* cl_rootpt, int* old2new, int* child_off, int* child_list,
+                          int* adj_new, int* csr_off, int* csr_nbr, int* csr_eid,
+                          int* status, int* counts_dev, int* counts_host,
+                          const int* scene_seg_off, const int* scene_cl_off_old, int* scene_cl_off_new, int n_scenes,
+                          int max_scene_segs, int max_scene_cl_old, void* ws, size_t ws_bytes, void* stream);
 
 /* a11  replaces seggroup/model.py:269-274 `calculate_distance` (F.pairwise_distance: ||a - b + 1e-6||_2). */
 int sgb_edge_dist_fwd(const float* feat, int C, const int* adj, int A, float* dist, void* stream);
@@ -239,12 +264,21 @@ int sgb_gcn_agg_bwd(const float* dAX, const float* X, const float* AX, int S, in
  * reference loops forever in that case). */
 int sgb_group_nearby(const int* adj, int A, const int* roots_cur, const float* dist, float th, int* uf, int S1,
                      int sweep_cap, int* status, void* stream);
+int sgb_group_nearby_scenes(const int* adj, int A, const int* roots_cur, int S_cur, const float* dist, float th, int* uf, int S1,
+                            int sweep_cap, int* status, const int* scene_seg_off, const int* scene_cl_off, int n_scenes,
+                            int max_scene_segs, void* stream);
 
 /* a14  one iteration of phase A of seggroup/model.py:439-470 `group_unlabeled_clusters`: row arg-min of
  * the dense distance matrix (fill 1000, first minimum), then union of every unlabeled cluster into it.
  * amin_ws: 2*S ints of scratch (arg-min row, then the in-order list of still unlabeled clusters). */
 int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
                              const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream);
+/* scene batch: the dense distance matrix of model.py:312-316 is per scene, so a row's arg-min ranges over its own scene's
+ * clusters (an isolated unlabeled cluster joins the FIRST cluster of its scene, as torch.min over an all-1000 row does). */
+int sgb_group_unlabeled_step_scenes(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
+                                    const int* roots_cur, int* uf, int S1, int* amin_ws,
+                                    const int* scene_seg_off, const int* scene_cl_off, int n_scenes, int max_scene_segs,
+                                    int max_scene_cl, void* stream);
 
 /* a14  phase B of `group_unlabeled_clusters` (model.py:472-509): every cluster phase A left unlabeled (unl [n_unl], ascending
  * dense ids) joins the first labelled cluster of its candidate list cand [n_unl,S] (all cluster ids by increasing sampled-cloud
@@ -257,6 +291,10 @@ int sgb_group_unlabeled_phase_b(const int* unl, int n_unl, const int* cand, int 
  * seg = root point id of p's cluster, ins/sem = weak label + 1 or -1. */
 int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
                       const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem, void* stream);
+/* scene batch: the segment label is the cluster's root point id INSIDE its scene (model.py:527-531) */
+int sgb_export_labels_scenes(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
+                             const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem,
+                             const int* scene_pt_off, int n_scenes, void* stream);
 
 /* a17  replaces seggroup/model.py:608-655 `evaluate`: 40-class intersection / union counts of the semantic and the
  * instance prediction and the four accuracies, over the raw vertices with real_label[:,0] != 0.

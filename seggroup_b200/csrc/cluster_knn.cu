@@ -121,7 +121,7 @@ template <int K>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ cl_off, const int* __restrict__ axis,
                  const float4* __restrict__ rec, const int* __restrict__ spos, const int* __restrict__ cid,
-                 const unsigned* __restrict__ max_sq, int* __restrict__ knn) {
+                 const unsigned* __restrict__ max_sq, int* __restrict__ knn, const int* __restrict__ scene_pt_off, int n_scenes) {
     // chunk of 32 candidate records per warp, structure-of-arrays so that two neighbouring candidates load as one float2
     __shared__ __align__(8) float s_x[KNN_THREADS / 32][32], s_y[KNN_THREADS / 32][32], s_z[KNN_THREADS / 32][32], s_w[KNN_THREADS / 32][32];
     __shared__ int s_pos[KNN_THREADS / 32][32];
@@ -229,13 +229,16 @@ knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ c
         else { process_chunk(R); R += 32; }
     }
     if (!have) return;
-    int* out = knn + (size_t)__ldg(order + pos_i) * K;
+    const int me_pt = __ldg(order + pos_i);
+    int* out = knn + (size_t)me_pt * K;
+    // scene batch: ids relative to the first point of the query's scene (what the reference builds for that scene alone)
+    const int base = scene_pt_off ? __ldg(scene_pt_off + sgb_upper_segment(scene_pt_off, n_scenes, me_pt)) : 0;
     if (n <= K) {                                  // model.py:516-518: all members in member order, the rest stays 0
 #pragma unroll
-        for (int t = 0; t < K; ++t) out[t] = (t < n) ? __ldg(order + lo + t) : 0;
+        for (int t = 0; t < K; ++t) out[t] = (t < n) ? __ldg(order + lo + t) - base : 0;
     } else {
 #pragma unroll
-        for (int t = 0; t < K; ++t) out[t] = __ldg(order + ps[t]);
+        for (int t = 0; t < K; ++t) out[t] = __ldg(order + ps[t]) - base;
     }
 }
 
@@ -273,6 +276,12 @@ extern "C" size_t sgb_cluster_knn_ws_bytes(int N, int S) { return knn_layout(nul
 
 extern "C" int sgb_cluster_knn(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
                                int k, int* knn, void* ws, size_t ws_bytes, void* stream) {
+    return sgb_cluster_knn_scenes(xyz, stride, N, order, cl_off, S, k, knn, nullptr, 1, ws, ws_bytes, stream);
+}
+extern "C" int sgb_cluster_knn_scenes(const float* xyz, int stride, int N, const int* order, const int* cl_off, int S,
+                                      int k, int* knn, const int* scene_pt_off, int n_scenes, void* ws, size_t ws_bytes, void* stream) {
+    if (n_scenes < 1 || (n_scenes > 1 && !scene_pt_off)) return SGB_ERR_INVALID;
+    if (n_scenes == 1) scene_pt_off = nullptr;
     if (N < 0 || S < 0 || stride < 3) return SGB_ERR_INVALID;
     if (N == 0) return SGB_OK;
     if (!xyz || !order || !cl_off || !knn || S == 0 || !ws) return SGB_ERR_INVALID;
@@ -289,9 +298,9 @@ extern "C" int sgb_cluster_knn(const float* xyz, int stride, int N, const int* o
     size_t tmp = w.cub_bytes;
     SGB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, N, 0, 32 + cbits, st));
     { knn_gather_kernel<<<grid, KNN_THREADS, 0, st>>>(xyz, stride, N, order, w.keys_out, w.vals_out, w.rec, w.cid); SGB_COUNT_LAUNCH(); }
-    if (k == 20) { knn_sweep_kernel<20><<<grid, KNN_THREADS, 0, st>>>(N, order, cl_off, w.axis, w.rec, w.vals_out, w.cid, w.max_sq, knn); SGB_COUNT_LAUNCH(); }
-    else if (k == 10) { knn_sweep_kernel<10><<<grid, KNN_THREADS, 0, st>>>(N, order, cl_off, w.axis, w.rec, w.vals_out, w.cid, w.max_sq, knn); SGB_COUNT_LAUNCH(); }
-    else { knn_sweep_kernel<16><<<grid, KNN_THREADS, 0, st>>>(N, order, cl_off, w.axis, w.rec, w.vals_out, w.cid, w.max_sq, knn); SGB_COUNT_LAUNCH(); }
+    if (k == 20) { knn_sweep_kernel<20><<<grid, KNN_THREADS, 0, st>>>(N, order, cl_off, w.axis, w.rec, w.vals_out, w.cid, w.max_sq, knn, scene_pt_off, n_scenes); SGB_COUNT_LAUNCH(); }
+    else if (k == 10) { knn_sweep_kernel<10><<<grid, KNN_THREADS, 0, st>>>(N, order, cl_off, w.axis, w.rec, w.vals_out, w.cid, w.max_sq, knn, scene_pt_off, n_scenes); SGB_COUNT_LAUNCH(); }
+    else { knn_sweep_kernel<16><<<grid, KNN_THREADS, 0, st>>>(N, order, cl_off, w.axis, w.rec, w.vals_out, w.cid, w.max_sq, knn, scene_pt_off, n_scenes); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

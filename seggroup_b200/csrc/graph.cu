@@ -16,7 +16,29 @@ struct UF {
     int* parent; int* next; int* tail; int* pnum; int* ins; int* sem;
     __host__ __device__ UF(int* base, int S) : parent(base), next(base + S), tail(base + 2 * S), pnum(base + 3 * S),
                                                ins(base + 4 * S), sem(base + 5 * S) {}
+    // rows of length n holding the entries [s0, s0 + n) of a table: indexed by the GLOBAL segment id (base - s0)
+    __host__ __device__ UF(int* base, int n, int s0) : parent(base - s0), next(base + n - s0), tail(base + 2 * n - s0),
+                                                       pnum(base + 3 * n - s0), ins(base + 4 * n - s0), sem(base + 5 * n - s0) {}
 };
+
+// Scene batches (block-diagonal graphs: several scenes concatenated, ids offset, no edge between scenes).  The order-dependent
+// replays run one CTA per scene.  scene_seg_off [B+1]: level-1 segment range of every scene; scene_cl_off [B+1]: its cluster
+// range at the level the kernel works on (clusters are numbered by ascending root segment, so a scene's clusters are
+// contiguous).  NULL = one scene covering everything.
+struct SceneRange { int s0, s1, c0, c1; };
+__device__ __forceinline__ SceneRange scene_range(const int* __restrict__ scene_seg_off, const int* __restrict__ scene_cl_off, int b,
+                                                  int S1, int S_cur) {
+    SceneRange r;
+    r.s0 = scene_seg_off ? scene_seg_off[b] : 0;  r.s1 = scene_seg_off ? scene_seg_off[b + 1] : S1;
+    r.c0 = scene_cl_off ? scene_cl_off[b] : 0;    r.c1 = scene_cl_off ? scene_cl_off[b + 1] : S_cur;
+    return r;
+}
+// first edge of a lexicographically sorted (u < v) edge list whose first endpoint is >= c
+__device__ __forceinline__ int edge_lower_bound(const int* __restrict__ adj, int A, int c) {
+    int lo = 0, hi = A;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (adj[2 * (size_t)mid] < c) lo = mid + 1; else hi = mid; }
+    return lo;
+}
 
 __device__ __forceinline__ int uf_find(const UF& u, int s) {            // path halving (single writer)
     while (u.parent[s] != s) { u.parent[s] = u.parent[u.parent[s]]; s = u.parent[s]; }
@@ -72,9 +94,11 @@ __global__ void level_flag_roots(const int* __restrict__ parent, int S, int* __r
 __global__ void level_assign(const int* __restrict__ ufb, int S, const int* __restrict__ dense /*scan of flags, [S+1]*/,
                              const int* __restrict__ seg_off, const int* __restrict__ seg_members,
                              int* __restrict__ roots, int* __restrict__ seg2cl, int* __restrict__ cl_ins, int* __restrict__ cl_sem,
-                             int* __restrict__ cl_rootpt, int* __restrict__ counts) {
+                             int* __restrict__ cl_rootpt, int* __restrict__ counts,
+                             const int* __restrict__ scene_seg_off, int n_scenes, int* __restrict__ scene_cl_off) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) counts[0] = dense[S];
+    if (scene_cl_off && s <= n_scenes) scene_cl_off[s] = dense[scene_seg_off[s]];   // clusters are numbered by ascending root segment
     if (s >= S) return;
     const int* parent = ufb;
     const int r = uf_find_ro(parent, s);
@@ -468,19 +492,27 @@ __device__ __forceinline__ int gn_append(bool keep, int ru, int rv, int* s_ru, i
 //           that fails the test then fails it for the rest of the sweep: the filter is exact, and thread 0 re-checks the
 //           condition at replay time for the ones that passed.
 __global__ void __launch_bounds__(GN_THREADS)
-group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ roots_cur,
-                    const float* __restrict__ dist, float th, int* __restrict__ ufb, int S1,
-                    int sweep_cap, int* __restrict__ status, int state_in_smem) {
+group_nearby_kernel(const int* __restrict__ adj_all, int A_all, const int* __restrict__ roots_cur, int S_cur,
+                    const float* __restrict__ dist_all, float th, int* __restrict__ ufb, int S1,
+                    int sweep_cap, int* __restrict__ status, int state_in_smem,
+                    const int* __restrict__ scene_seg_off, const int* __restrict__ scene_cl_off) {
     extern __shared__ int gn_smem[];
     __shared__ int s_ru[GN_CHUNK], s_rv[GN_CHUNK];
     __shared__ int s_wcount[GN_THREADS / 32];
     __shared__ int s_flag;
-    int* base = state_in_smem ? gn_smem : ufb;
+    __shared__ int s_e0, s_e1;
+    const SceneRange sr = scene_range(scene_seg_off, scene_cl_off, blockIdx.x, S1, S_cur);
+    if (threadIdx.x == 0) { s_e0 = edge_lower_bound(adj_all, A_all, sr.c0); s_e1 = edge_lower_bound(adj_all, A_all, sr.c1); }
+    const int n_loc = sr.s1 - sr.s0;
     if (state_in_smem) {
-        for (int i = threadIdx.x; i < 6 * S1; i += GN_THREADS) gn_smem[i] = ufb[i];
+        for (int r = 0; r < 6; ++r)
+            for (int i = threadIdx.x; i < n_loc; i += GN_THREADS) gn_smem[r * n_loc + i] = ufb[(size_t)r * S1 + sr.s0 + i];
     }
     __syncthreads();
-    UF u(base, S1);
+    const int* adj = adj_all + 2 * (size_t)s_e0;
+    const float* dist = dist_all + s_e0;
+    const int A = s_e1 - s_e0;
+    const UF u = state_in_smem ? UF(gn_smem, n_loc, sr.s0) : UF(ufb, S1);
     // pass 1
     for (int c0 = 0; c0 < A; c0 += GN_CHUNK) {
         const int n = min(GN_CHUNK, A - c0);
@@ -545,7 +577,8 @@ group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ 
     }
     __syncthreads();
     if (state_in_smem) {
-        for (int i = threadIdx.x; i < 6 * S1; i += GN_THREADS) ufb[i] = gn_smem[i];
+        for (int r = 0; r < 6; ++r)
+            for (int i = threadIdx.x; i < n_loc; i += GN_THREADS) ufb[(size_t)r * S1 + sr.s0 + i] = gn_smem[r * n_loc + i];
     }
 }
 
@@ -553,13 +586,20 @@ group_nearby_kernel(const int* __restrict__ adj, int A, const int* __restrict__ 
 // row argmin of the dense distance matrix (fill 1000, first minimum) from the symmetric CSR, then the
 // sequential unions of unlabeled clusters in ascending order.
 __global__ void unlabeled_argmin_kernel(const float* __restrict__ dist, const int* __restrict__ row_off, const int* __restrict__ nbr,
-                                        const int* __restrict__ eid, int S, int* __restrict__ amin) {
+                                        const int* __restrict__ eid, int S, int* __restrict__ amin,
+                                        const int* __restrict__ scene_cl_off, int n_scenes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
+    // the dense matrix of the reference is per scene: its columns are this scene's clusters [c0, c1)
+    int c0 = 0, c1 = S;
+    if (scene_cl_off) {
+        const int b = sgb_upper_segment(scene_cl_off, n_scenes, i);
+        c0 = scene_cl_off[b]; c1 = scene_cl_off[b + 1];
+    }
     const int a = row_off[i], b = row_off[i + 1];
     // dense row: dm[i][j] = dist(e) for neighbours, 1000 elsewhere (diagonal included)
     float best = INFINITY; int bj = -1;
-    int expect = 0;                                   // smallest column not yet known to be a neighbour
+    int expect = c0;                                  // smallest column not yet known to be a neighbour
     int first_fill = -1;
     for (int t = a; t < b; ++t) {
         const int j = nbr[t];
@@ -569,10 +609,10 @@ __global__ void unlabeled_argmin_kernel(const float* __restrict__ dist, const in
         const float d = dist[eid[t]];
         if (d < best) { best = d; bj = j; }
     }
-    if (first_fill < 0 && expect < S) first_fill = expect;
+    if (first_fill < 0 && expect < c1) first_fill = expect;
     // candidates: (best, bj) among edges, (1000, first_fill) among the filled entries; first minimum wins
     if (first_fill >= 0 && (bj < 0 || 1000.f < best || (1000.f == best && first_fill < bj))) bj = first_fill;
-    amin[i] = bj < 0 ? 0 : bj;
+    amin[i] = bj < 0 ? c0 : bj;
 }
 // The ascending sequential unions of phase A.  One thread replays them; the union-find table, the root map and the argmin
 // row live in shared memory for the replay (a dependent shared-memory access costs ~30 cycles, an L2 one ~10x that).
@@ -580,29 +620,33 @@ __global__ void unlabeled_argmin_kernel(const float* __restrict__ dist, const in
 // when the kernel starts are filtered out in parallel, in order; thread 0 re-checks the rest at replay time.
 constexpr int UU_THREADS = 256;
 __global__ void __launch_bounds__(UU_THREADS)
-unlabeled_union_kernel(const int* __restrict__ amin, int S, const int* __restrict__ roots_cur, int* __restrict__ ufb, int S1,
-                       int state_in_smem, int* __restrict__ list_ws /*[S], used when the state stays in global memory*/) {
+unlabeled_union_kernel(const int* __restrict__ amin, int S_all, const int* __restrict__ roots_cur, int* __restrict__ ufb, int S1,
+                       int state_in_smem, int* __restrict__ list_ws /*[S], used when the state stays in global memory*/,
+                       const int* __restrict__ scene_seg_off, const int* __restrict__ scene_cl_off) {
     extern __shared__ int uu_smem[];
     __shared__ int s_wcount[UU_THREADS / 32];
-    int* base = ufb;
+    const SceneRange sr = scene_range(scene_seg_off, scene_cl_off, blockIdx.x, S1, S_all);
+    const int n_loc = sr.s1 - sr.s0, S = sr.c1 - sr.c0;
+    // cluster-indexed arrays of this scene, indexed by the GLOBAL dense id
     const int* s_roots = roots_cur;
     const int* s_amin = amin;
-    int* s_list = list_ws;
+    int* s_list = list_ws + sr.c0;
     if (state_in_smem) {
-        int* r = uu_smem + 6 * S1;
+        int* r = uu_smem + 6 * n_loc;
         int* a = r + S;
         s_list = a + S;
-        for (int i = threadIdx.x; i < 6 * S1; i += UU_THREADS) uu_smem[i] = ufb[i];
-        for (int i = threadIdx.x; i < S; i += UU_THREADS) { r[i] = roots_cur[i]; a[i] = amin[i]; }
-        base = uu_smem; s_roots = r; s_amin = a;
+        for (int q = 0; q < 6; ++q)
+            for (int i = threadIdx.x; i < n_loc; i += UU_THREADS) uu_smem[q * n_loc + i] = ufb[(size_t)q * S1 + sr.s0 + i];
+        for (int i = threadIdx.x; i < S; i += UU_THREADS) { r[i] = roots_cur[sr.c0 + i]; a[i] = amin[sr.c0 + i]; }
+        s_roots = r - sr.c0; s_amin = a - sr.c0;
     }
     __syncthreads();
-    UF u(base, S1);
+    const UF u = state_in_smem ? UF(uu_smem, n_loc, sr.s0) : UF(ufb, S1);
     int fill = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i0 = 0; i0 < S; i0 += UU_THREADS) {
-        const int i = i0 + threadIdx.x;
-        const bool keep = i < S && u.ins[uf_find_ro(u.parent, s_roots[i])] == -1;
+        const int i = sr.c0 + i0 + threadIdx.x;
+        const bool keep = i < sr.c1 && u.ins[uf_find_ro(u.parent, s_roots[i])] == -1;
         const unsigned bal = __ballot_sync(SGB_FULL_MASK, keep);
         if (lane == 0) s_wcount[warp] = __popc(bal);
         __syncthreads();
@@ -623,7 +667,8 @@ unlabeled_union_kernel(const int* __restrict__ amin, int S, const int* __restric
     }
     __syncthreads();
     if (state_in_smem) {
-        for (int i = threadIdx.x; i < 6 * S1; i += UU_THREADS) ufb[i] = uu_smem[i];
+        for (int q = 0; q < 6; ++q)
+            for (int i = threadIdx.x; i < n_loc; i += UU_THREADS) ufb[(size_t)q * S1 + sr.s0 + i] = uu_smem[q * n_loc + i];
     }
 }
 
@@ -658,12 +703,15 @@ __global__ void unlabeled_phase_b_kernel(const int* __restrict__ unl, int n_unl,
 // ---------------------------------------------------------------------------------------------
 __global__ void export_labels_kernel(const long long* __restrict__ unmap, int n_raw, const int* __restrict__ seg_of_point,
                                      const int* __restrict__ seg2cl, const int* __restrict__ cl_rootpt, const int* __restrict__ cl_ins,
-                                     const int* __restrict__ cl_sem, int* __restrict__ out_seg, int* __restrict__ out_ins, int* __restrict__ out_sem) {
+                                     const int* __restrict__ cl_sem, int* __restrict__ out_seg, int* __restrict__ out_ins, int* __restrict__ out_sem,
+                                     const int* __restrict__ scene_pt_off, int n_scenes) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_raw) return;
     const int p = unmap ? (int)unmap[r] : r;
     const int c = seg2cl[seg_of_point[p]];
-    if (out_seg) out_seg[r] = cl_rootpt[c];
+    // scene batch: the segment label is the root point id INSIDE its scene
+    const int base = scene_pt_off ? scene_pt_off[sgb_upper_segment(scene_pt_off, n_scenes, p)] : 0;
+    if (out_seg) out_seg[r] = cl_rootpt[c] - base;
     const int ins = cl_ins[c], sem = cl_sem[c];
     if (out_ins) out_ins[r] = ins != -1 ? ins + 1 : -1;
     if (out_sem) out_sem[r] = sem != -1 ? sem + 1 : -1;
@@ -688,7 +736,7 @@ __global__ void count_unlabeled_kernel(const int* __restrict__ cl_ins, const int
 // The phase bodies are the kernels above, re-indexed by (threadIdx.x, blockDim.x).  Arrays written in one phase and read in
 // a later one are passed WITHOUT const/__restrict__ so that no read goes through the non-coherent path.
 // ---------------------------------------------------------------------------------------------
-constexpr int SMALL_S = 8192;
+constexpr int SMALL_S = 2048;
 constexpr int SMALL_THREADS = 1024;
 
 // out[0..n] = exclusive scan of in[0..n) (out[n] = total); in and out must not alias; all threads of the CTA call it
@@ -722,7 +770,8 @@ __device__ void block_scan_excl(const int* in, int n, int* out, int* s_warp /*[3
 __global__ void __launch_bounds__(SMALL_THREADS)
 level_build_small(const int* __restrict__ ufb, int S, const int* __restrict__ seg_off, const int* __restrict__ seg_members,
                   int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* cl_ins, int* cl_sem, int* cl_rootpt,
-                  int* counts, int* flag, int* dense, int* cl_nseg, int* cl_npt, int* seg_rank, int* seg_start) {
+                  int* counts, int* flag, int* dense, int* cl_nseg, int* cl_npt, int* seg_rank, int* seg_start,
+                  const int* __restrict__ scene_seg_off, int n_scenes, int* scene_cl_off) {
     __shared__ int s_warp[34];
     __shared__ int s_unl;
     const int* parent = ufb;
@@ -732,6 +781,8 @@ level_build_small(const int* __restrict__ ufb, int S, const int* __restrict__ se
     __syncthreads();
     block_scan_excl(flag, S, dense, s_warp);
     const int nc = dense[S];
+    if (scene_cl_off)
+        for (int b = threadIdx.x; b <= n_scenes; b += blockDim.x) scene_cl_off[b] = dense[scene_seg_off[b]];
     for (int s0 = threadIdx.x; s0 < S; s0 += blockDim.x) {                // level_assign
         const int r = uf_find_ro(parent, s0);
         const int c = dense[r];
@@ -878,6 +929,16 @@ extern "C" size_t sgb_level_ws_bytes(int S1) { return (size_t)(6 * (S1 + 1)) * s
 extern "C" int sgb_level_build(const int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
                                int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
                                int* cl_ins, int* cl_sem, int* cl_rootpt, int* counts, void* ws, size_t ws_bytes, void* stream) {
+    return sgb_level_build_scenes(uf, S1, N, seg_off, seg_members, seg_of_pos, roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order,
+                                  cl_ins, cl_sem, cl_rootpt, counts, nullptr, 1, nullptr, ws, ws_bytes, stream);
+}
+// scene batch: scene_seg_off [n_scenes+1] (device) -> scene_cl_off [n_scenes+1] (device): cluster range of every scene
+extern "C" int sgb_level_build_scenes(const int* uf, int S1, int N, const int* seg_off, const int* seg_members, const int* seg_of_pos,
+                                      int* roots, int* seg2cl, int* cl_seg_off, int* cl_seg_list, int* cl_pt_off, int* order,
+                                      int* cl_ins, int* cl_sem, int* cl_rootpt, int* counts,
+                                      const int* scene_seg_off, int n_scenes, int* scene_cl_off,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    if (scene_cl_off && (!scene_seg_off || n_scenes < 1)) return SGB_ERR_INVALID;
     if (S1 <= 0 || N <= 0 || !uf || !seg_off || !seg_members || !seg_of_pos || !roots || !seg2cl || !cl_seg_off || !cl_seg_list ||
         !cl_pt_off || !order || !cl_ins || !cl_sem || !cl_rootpt || !counts || !ws) return SGB_ERR_INVALID;
     if (ws_bytes < sgb_level_ws_bytes(S1)) return SGB_ERR_WORKSPACE;
@@ -894,14 +955,16 @@ extern "C" int sgb_level_build(const int* uf, int S1, int N, const int* seg_off,
     int rc;
     if (S1 <= SMALL_S) {                  // one CTA for every cluster-sized phase (counts[0] = clusters, counts[2] = unlabeled ones)
         { level_build_small<<<1, SMALL_THREADS, 0, st>>>(uf, S1, seg_off, seg_members, roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off,
-                                                         cl_ins, cl_sem, cl_rootpt, counts, flag, dense, cl_nseg, cl_npt, seg_rank, seg_start); SGB_COUNT_LAUNCH(); }
+                                                         cl_ins, cl_sem, cl_rootpt, counts, flag, dense, cl_nseg, cl_npt, seg_rank, seg_start,
+                                                         scene_seg_off, n_scenes, scene_cl_off); SGB_COUNT_LAUNCH(); }
         { level_fill_order<<<sgb_div_up(N, 256), 256, 0, st>>>(N, seg_of_pos, seg_off, seg_members, seg2cl, seg_start, cl_pt_off, order); SGB_COUNT_LAUNCH(); }
         SGB_CHECK_LAUNCH();
         return SGB_OK;
     }
     { level_flag_roots<<<g, 256, 0, st>>>(uf, S1, flag); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(flag, dense, S1, scan_ws, scan_bytes, st))) return rc;
-    { level_assign<<<g, 256, 0, st>>>(uf, S1, dense, seg_off, seg_members, roots, seg2cl, cl_ins, cl_sem, cl_rootpt, counts); SGB_COUNT_LAUNCH(); }
+    { level_assign<<<g, 256, 0, st>>>(uf, S1, dense, seg_off, seg_members, roots, seg2cl, cl_ins, cl_sem, cl_rootpt, counts,
+                                      scene_seg_off, n_scenes, scene_cl_off); SGB_COUNT_LAUNCH(); }
     { level_walk_lists<<<g, 256, 0, st>>>(uf, S1, counts, roots, seg_off, cl_nseg, cl_npt, seg_rank, seg_start); SGB_COUNT_LAUNCH(); }
     if ((rc = sgb_exclusive_scan_i32(cl_nseg, cl_seg_off, S1, scan_ws, scan_bytes, st))) return rc;
     if ((rc = sgb_exclusive_scan_i32(cl_npt, cl_pt_off, S1, scan_ws, scan_bytes, st))) return rc;
@@ -1052,15 +1115,24 @@ extern "C" int sgb_gcn_agg_bwd(const float* dAX, const float* X, const float* AX
 
 extern "C" int sgb_group_nearby(const int* adj, int A, const int* roots_cur, const float* dist, float th, int* uf, int S1,
                                 int sweep_cap, int* status, void* stream) {
-    if (A < 0 || S1 <= 0 || !uf || !status) return SGB_ERR_INVALID;
+    return sgb_group_nearby_scenes(adj, A, roots_cur, 0, dist, th, uf, S1, sweep_cap, status, nullptr, nullptr, 1, S1, stream);
+}
+// scene batch: one CTA per scene replays that scene's edges.  scene_seg_off / scene_cl_off [n_scenes+1] (device; cluster offsets of
+// the level `adj` / `roots_cur` belong to), max_scene_segs = largest level-1 segment count of a scene (sizes the shared memory).
+extern "C" int sgb_group_nearby_scenes(const int* adj, int A, const int* roots_cur, int S_cur, const float* dist, float th, int* uf, int S1,
+                                       int sweep_cap, int* status, const int* scene_seg_off, const int* scene_cl_off, int n_scenes,
+                                       int max_scene_segs, void* stream) {
+    if (A < 0 || S1 <= 0 || !uf || !status || n_scenes < 1) return SGB_ERR_INVALID;
     if (A == 0) return SGB_OK;
     if (!adj || !roots_cur || !dist) return SGB_ERR_INVALID;
-    const size_t state_bytes = (size_t)6 * S1 * sizeof(int);
+    if (n_scenes > 1 && (!scene_seg_off || !scene_cl_off)) return SGB_ERR_INVALID;
+    if (!scene_seg_off) { n_scenes = 1; max_scene_segs = S1; }
+    const size_t state_bytes = (size_t)6 * max_scene_segs * sizeof(int);
     const int in_smem = state_bytes <= 160 * 1024;
     if (in_smem && state_bytes > 16 * 1024)
         SGB_OPT_IN_SMEM(group_nearby_kernel);
-    { group_nearby_kernel<<<1, GN_THREADS, in_smem ? state_bytes : 0, (cudaStream_t)stream>>>(adj, A, roots_cur, dist, th, uf, S1, sweep_cap,
-                                                                                           status, in_smem); SGB_COUNT_LAUNCH(); }
+    { group_nearby_kernel<<<n_scenes, GN_THREADS, in_smem ? state_bytes : 0, (cudaStream_t)stream>>>(
+          adj, A, roots_cur, S_cur, dist, th, uf, S1, sweep_cap, status, in_smem, scene_seg_off, scene_cl_off); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -1068,14 +1140,25 @@ extern "C" int sgb_group_nearby(const int* adj, int A, const int* roots_cur, con
 // one iteration of phase A of group_unlabeled_clusters; amin_ws [2*S] ints
 extern "C" int sgb_group_unlabeled_step(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
                                         const int* roots_cur, int* uf, int S1, int* amin_ws, void* stream) {
-    if (S <= 0 || S1 <= 0 || !row_off || !roots_cur || !uf || !amin_ws) return SGB_ERR_INVALID;
+    return sgb_group_unlabeled_step_scenes(dist, row_off, nbr, eid, S, roots_cur, uf, S1, amin_ws, nullptr, nullptr, 1, S1, S, stream);
+}
+// scene batch: the dense distance matrix of the reference is per scene (arg-min columns = the scene's own clusters; an isolated
+// unlabeled cluster joins the FIRST cluster of its scene); max_scene_cl = largest cluster count of a scene at this level.
+extern "C" int sgb_group_unlabeled_step_scenes(const float* dist, const int* row_off, const int* nbr, const int* eid, int S,
+                                               const int* roots_cur, int* uf, int S1, int* amin_ws,
+                                               const int* scene_seg_off, const int* scene_cl_off, int n_scenes, int max_scene_segs,
+                                               int max_scene_cl, void* stream) {
+    if (S <= 0 || S1 <= 0 || !row_off || !roots_cur || !uf || !amin_ws || n_scenes < 1) return SGB_ERR_INVALID;
+    if (n_scenes > 1 && (!scene_seg_off || !scene_cl_off)) return SGB_ERR_INVALID;
+    if (!scene_seg_off) { n_scenes = 1; max_scene_segs = S1; max_scene_cl = S; }
     cudaStream_t st = (cudaStream_t)stream;
-    { unlabeled_argmin_kernel<<<sgb_div_up(S, 128), 128, 0, st>>>(dist, row_off, nbr, eid, S, amin_ws); SGB_COUNT_LAUNCH(); }
-    const size_t state_bytes = ((size_t)6 * S1 + 3 * (size_t)S) * sizeof(int);
+    { unlabeled_argmin_kernel<<<sgb_div_up(S, 128), 128, 0, st>>>(dist, row_off, nbr, eid, S, amin_ws, scene_cl_off, n_scenes); SGB_COUNT_LAUNCH(); }
+    const size_t state_bytes = ((size_t)6 * max_scene_segs + 3 * (size_t)max_scene_cl) * sizeof(int);
     const int in_smem = state_bytes <= 200 * 1024;
     if (in_smem && state_bytes > 40 * 1024)
         SGB_OPT_IN_SMEM(unlabeled_union_kernel);
-    { unlabeled_union_kernel<<<1, UU_THREADS, in_smem ? state_bytes : 0, st>>>(amin_ws, S, roots_cur, uf, S1, in_smem, amin_ws + S); SGB_COUNT_LAUNCH(); }
+    { unlabeled_union_kernel<<<n_scenes, UU_THREADS, in_smem ? state_bytes : 0, st>>>(amin_ws, S, roots_cur, uf, S1, in_smem, amin_ws + S,
+                                                                                      scene_seg_off, scene_cl_off); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
@@ -1094,9 +1177,16 @@ extern "C" int sgb_group_unlabeled_phase_b(const int* unl, int n_unl, const int*
 
 extern "C" int sgb_export_labels(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
                                  const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem, void* stream) {
-    if (n_raw <= 0 || !seg_of_point || !seg2cl || !cl_rootpt || !cl_ins || !cl_sem) return SGB_ERR_INVALID;
+    return sgb_export_labels_scenes(unmap, n_raw, seg_of_point, seg2cl, cl_rootpt, cl_ins, cl_sem, out_seg, out_ins, out_sem, nullptr, 1, stream);
+}
+// scene batch: scene_pt_off [n_scenes+1] (device) point range of every scene; segment labels are root point ids inside the scene
+extern "C" int sgb_export_labels_scenes(const long long* unmap, int n_raw, const int* seg_of_point, const int* seg2cl, const int* cl_rootpt,
+                                        const int* cl_ins, const int* cl_sem, int* out_seg, int* out_ins, int* out_sem,
+                                        const int* scene_pt_off, int n_scenes, void* stream) {
+    if (n_raw <= 0 || !seg_of_point || !seg2cl || !cl_rootpt || !cl_ins || !cl_sem || n_scenes < 1) return SGB_ERR_INVALID;
     { export_labels_kernel<<<sgb_div_up(n_raw, 256), 256, 0, (cudaStream_t)stream>>>(unmap, n_raw, seg_of_point, seg2cl, cl_rootpt,
-                                                                                   cl_ins, cl_sem, out_seg, out_ins, out_sem); SGB_COUNT_LAUNCH(); }
+                                                                                   cl_ins, cl_sem, out_seg, out_ins, out_sem,
+                                                                                   n_scenes > 1 ? scene_pt_off : nullptr, n_scenes); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

@@ -38,11 +38,15 @@ def reserve_current_stream(nbytes: int = 1 << 30, device=None):
 
 
 class SceneExecutor:
-    def __init__(self, device=None, n_streams: int = 4, reserve_bytes_per_stream: int = 3 << 30):
+    def __init__(self, device=None, n_streams: int = 4, reserve_bytes_per_stream: int = 3 << 30, fused: bool = True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.n_streams = max(1, int(n_streams))
+        self.fused = bool(fused)
+        self.last_result = None
+        if self.fused:
+            n_streams = 0                      # fused batches run on the caller's stream: no lanes, no host threads
+        self.n_streams = max(0 if self.fused else 1, int(n_streams))
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
-        self._pool = ThreadPoolExecutor(max_workers=self.n_streams, thread_name_prefix="sgb-scene")
+        self._pool = ThreadPoolExecutor(max_workers=max(1, self.n_streams), thread_name_prefix="sgb-scene")
         self.reserve(reserve_bytes_per_stream)
 
     def reserve(self, nbytes: int):
@@ -101,9 +105,16 @@ class SceneExecutor:
         return outs
 
     # ------------------------------------------------------------------------------------------
-    def infer_batch(self, scenes, params, mode="ins_infer", upload=None):
-        """-> list of ForwardResult.  `upload(scene)` (optional) turns a host-side scene into a SceneDevice on the
-        worker's stream (end-to-end path: the H2D copies of one scene overlap the kernels of the others)."""
+    def infer_batch(self, scenes, params, mode="ins_infer", upload=None, fused=None):
+        """-> list of ForwardResult (fused: ONE ForwardResult for the whole batch, see train_batch).  `upload(scene)` (optional)
+        turns a host-side scene into a SceneDevice on the worker's stream (end-to-end path: the H2D copies of one scene overlap
+        the kernels of the others)."""
+        if self.fused if fused is None else fused:
+            batch = scenes if isinstance(scenes, pipeline.SceneDevice) else pipeline.SceneDevice.concat(
+                [upload(s) if upload is not None else s for s in scenes])
+            with torch.no_grad():
+                return pipeline.forward_scene(batch, params, mode=mode)
+
         def fn(sc, i):
             if upload is not None:
                 sc = upload(sc)
@@ -111,11 +122,30 @@ class SceneExecutor:
                 return pipeline.forward_scene(sc, params, mode=mode)
         return self._run(fn, scenes)
 
-    def train_batch(self, scenes, params, train_keys, upload=None):
+    def train_batch(self, scenes, params, train_keys, upload=None, fused=None):
         """Forward + backward of every scene; accumulates d(mean_i loss_i)/d(param) into `param.grad` (fixed scene
         order) and returns the mean loss (0-dim device tensor).  params: dict name -> tensor; train_keys: names
-        of the leaves that require grad."""
+        of the leaves that require grad.
+        fused (default): the scenes are concatenated into ONE block-diagonal batch (pipeline.SceneDevice.concat; `scenes` may
+        already be such a batch) and driven by one forward / backward on the caller's stream — every graph / kNN / pooling /
+        export launch serves all scenes, the order-dependent replays run one CTA per scene, BatchNorm statistics stay per
+        scene.  fused=False: one scene per CUDA stream / host thread (the round-1 executor)."""
         leaves = [params[k] for k in train_keys]
+        if self.fused if fused is None else fused:
+            batch = scenes if isinstance(scenes, pipeline.SceneDevice) else pipeline.SceneDevice.concat(
+                [upload(s) if upload is not None else s for s in scenes])
+            r = pipeline.forward_scene(batch, params, mode="train")
+            loss = (r.loss_raw[:, 0] / r.loss_raw[:, 1]).mean()                 # mean over scenes of loss_sum / loss_num (train.py:165-170 + DDP)
+            grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+            for pp, g in zip(leaves, grads):
+                if g is None:
+                    continue
+                if pp.grad is None:
+                    pp.grad = g
+                else:
+                    pp.grad.add_(g)
+            self.last_result = r
+            return loss.detach()
         n = len(scenes)
         main = torch.cuda.current_stream(self.device)
 

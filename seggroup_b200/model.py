@@ -237,7 +237,7 @@ class SegModel(nn.Module):
         engine.reserve_current_stream(device=data.device)      # once per stream: no cudaMalloc in later forwards
         sc = self._scene(scene_name, data, weak_label)
         mode = "sem_infer" if self.sem_infer else ("ins_infer" if self.ins_infer else "train")
-        res = pipeline.forward_scene(sc, self._params(), mode=mode, classifier=self.classifier)
+        res = pipeline.forward_scene(sc, self._params(), mode=mode, classifier=self.classifier, sweep_cap=self.SWEEP_CAP)
         if res.status & 2:
             import warnings
             warnings.warn("scene %s: small-cluster sweep capped at %d iterations (the reference would not terminate)"

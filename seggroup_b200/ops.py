@@ -67,8 +67,9 @@ def segment_pool_max_bwd(grad_out, argmax, n_rows):
     return g
 
 
-def cluster_knn(xyz, order, cl_off, k=20):
-    """xyz [N,>=3] f32 (row stride = xyz.stride(0)); order [N] i32; cl_off [S+1] i32 -> knn [N,k] i32."""
+def cluster_knn(xyz, order, cl_off, k=20, scene_pt_off=None):
+    """xyz [N,>=3] f32 (row stride = xyz.stride(0)); order [N] i32; cl_off [S+1] i32 -> knn [N,k] i32.
+    scene_pt_off [B+1] i32 (device, scene batch): ids are written relative to the first point of the query's scene."""
     _chk(order, I32, "order"); _chk(cl_off, I32, "cl_off")
     if not xyz.is_cuda or xyz.dtype != F32 or xyz.stride(1) != 1:
         raise ValueError("xyz must be a CUDA float32 tensor with unit inner stride")
@@ -76,7 +77,11 @@ def cluster_knn(xyz, order, cl_off, k=20):
     knn = torch.empty(N, k, dtype=I32, device=xyz.device)
     S = cl_off.numel() - 1
     ws = _ws(_lib.call("sgb_cluster_knn_ws_bytes", N, S), xyz.device)
-    _lib.call("sgb_cluster_knn", xyz, xyz.stride(0), N, order, cl_off, S, k, knn, ws, ws.numel(), _stream())
+    if scene_pt_off is None:
+        _lib.call("sgb_cluster_knn", xyz, xyz.stride(0), N, order, cl_off, S, k, knn, ws, ws.numel(), _stream())
+    else:
+        _lib.call("sgb_cluster_knn_scenes", xyz, xyz.stride(0), N, order, cl_off, S, k, knn, _chk(scene_pt_off, I32, "scene_pt_off"),
+                  scene_pt_off.numel() - 1, ws, ws.numel(), _stream())
     return knn
 
 
@@ -113,14 +118,17 @@ def centralize(data6, order, cl_off):
     return x9
 
 
-def mlp1_fwd(clouds, W, gamma, beta):
-    """clouds [S,64,6] -> dict(feat [S,128], knn [S,64,10], arg_pt [S,64], stats [4,64], var [64], mom [27] f64)."""
+def mlp1_fwd(clouds, W, gamma, beta, feat=None, knn=None, arg_pt=None):
+    """clouds [S,64,6] -> dict(feat [S,128], knn [S,64,10], arg_pt [S,64], stats [4,64], var [64], mom [27] f64).
+    feat / knn / arg_pt: optional preallocated outputs (row slices of a scene batch's arrays)."""
     _chk(clouds, F32, "clouds")
     S = clouds.shape[0]
     dev = clouds.device
     W = _chk(W.reshape(64, 6), F32, "W")
-    out = dict(feat=torch.empty(S, 128, dtype=F32, device=dev), knn=torch.empty(S, 64, 10, dtype=I32, device=dev),
-               arg_pt=torch.empty(S, 64, dtype=I32, device=dev), stats=torch.empty(4, 64, dtype=F32, device=dev),
+    out = dict(feat=torch.empty(S, 128, dtype=F32, device=dev) if feat is None else _chk(feat, F32, "feat"),
+               knn=torch.empty(S, 64, 10, dtype=I32, device=dev) if knn is None else _chk(knn, I32, "knn"),
+               arg_pt=torch.empty(S, 64, dtype=I32, device=dev) if arg_pt is None else _chk(arg_pt, I32, "arg_pt"),
+               stats=torch.empty(4, 64, dtype=F32, device=dev),
                var=torch.empty(64, dtype=F32, device=dev), mom=torch.empty(27, dtype=torch.float64, device=dev))
     ws = _ws(_lib.call("sgb_mlp1_ws_bytes", S), dev)
     _lib.call("sgb_mlp1_fwd", clouds, S, W, gamma, beta, out["feat"], out["knn"], out["arg_pt"], out["stats"], out["var"],
@@ -160,9 +168,10 @@ def edgeconv_bwd(g, arg, argk, x9, knn, W1, stats1, mom1, e0, W2=None, stats2=No
     return r
 
 
-def edgeconv_fwd(x9, knn, W1, gamma1, beta1, W2=None, gamma2=None, beta2=None, want_argk=True, want_backward=True):
+def edgeconv_fwd(x9, knn, W1, gamma1, beta1, W2=None, gamma2=None, beta2=None, want_argk=True, want_backward=True, out=None, argk=None):
     """x9 [N,9], knn [N,20] -> dict(out [N,64], argk [N,64] u8, stats1, var1, mom1, ctr [, stats2, var2, mom2]).
-    want_backward=False (inference): no moments are kept and the second layer of MLP3 runs on the tcgen05 tensor cores."""
+    want_backward=False (inference): no moments are kept and the second layer of MLP3 runs on the tcgen05 tensor cores.
+    out / argk: optional preallocated outputs (row slices of a scene batch's arrays)."""
     _chk(x9, F32, "x9"); _chk(knn, I32, "knn")
     N = x9.shape[0]
     dev = x9.device
@@ -170,11 +179,12 @@ def edgeconv_fwd(x9, knn, W1, gamma1, beta1, W2=None, gamma2=None, beta2=None, w
     W1 = _chk(W1.reshape(64, 18), F32, "W1")
     if two:
         W2 = _chk(W2.reshape(64, 64), F32, "W2")
-    o = dict(out=torch.empty(N, 64, dtype=F32, device=dev), stats1=torch.empty(4, 64, dtype=F32, device=dev),
+    o = dict(out=torch.empty(N, 64, dtype=F32, device=dev) if out is None else _chk(out, F32, "out"), stats1=torch.empty(4, 64, dtype=F32, device=dev),
              var1=torch.empty(64, dtype=F32, device=dev),
              mom1=torch.empty(189, dtype=torch.float64, device=dev) if want_backward else None,
              ctr=torch.empty(18, dtype=F32, device=dev),
-             argk=torch.empty(N, 64, dtype=torch.uint8, device=dev) if (want_argk or want_backward) else None)
+             argk=(torch.empty(N, 64, dtype=torch.uint8, device=dev) if argk is None else _chk(argk, torch.uint8, "argk"))
+             if (want_argk or want_backward) else None)
     if two:
         o.update(stats2=torch.empty(4, 64, dtype=F32, device=dev), var2=torch.empty(64, dtype=F32, device=dev),
                  mom2=torch.empty(4160, dtype=torch.float64, device=dev) if want_backward else None)
@@ -205,11 +215,24 @@ class Level:
     `level_step` also carry their adjacency (`adj` [A,2], `csr`), the map from the previous level (`o2n`, `ch_off`,
     `ch_list`), the number of unlabeled clusters and the status word read back with the counts."""
     __slots__ = ("S", "roots", "seg2cl", "cl_seg_off", "cl_seg_list", "cl_pt_off", "order", "cl_ins", "cl_sem", "cl_rootpt",
-                 "counts", "adj", "csr", "o2n", "ch_off", "ch_list", "n_unlabeled", "status")
+                 "counts", "adj", "csr", "o2n", "ch_off", "ch_list", "n_unlabeled", "status",
+                 "scene_cl_off", "d_scene_cl_off")       # scene batch: cluster range of every scene (host list / device [B+1])
+
+
+class SceneSplit:
+    """Scene partition of a batch (several scenes concatenated block-diagonally): host offsets + their device copies."""
+    __slots__ = ("n", "pt_off", "seg_off", "raw_off", "d_pt_off", "d_seg_off", "max_segs")
+
+    def __init__(self, pt_off, seg_off, raw_off, device):
+        self.n = len(pt_off) - 1
+        self.pt_off, self.seg_off, self.raw_off = [int(v) for v in pt_off], [int(v) for v in seg_off], [int(v) for v in raw_off]
+        self.d_pt_off = torch.tensor(self.pt_off, dtype=I32, device=device)
+        self.d_seg_off = torch.tensor(self.seg_off, dtype=I32, device=device)
+        self.max_segs = max(b - a for a, b in zip(self.seg_off[:-1], self.seg_off[1:]))
 
 
 def level_step(mode, uf, seg_off, seg_members, seg_of_pos, status, old=None, dist=None, th=0.0, edges=None, mapping=None,
-               sweep_cap=64):
+               sweep_cap=64, split=None):
     """One clustering level in one library call (sgb_level_step): mode 0 group_nearby(old.adj, dist, th), 1 one phase-A
     iteration of group_unlabeled (dist, old.csr), 2 no grouping.  edges/mapping: edge list to re-map (default: old.adj
     through the old->new cluster map of this step).  Returns the new Level with .adj, .csr, .o2n, .ch_off, .ch_list."""
@@ -221,24 +244,33 @@ def level_step(mode, uf, seg_off, seg_members, seg_of_pos, status, old=None, dis
     if edges is None:
         edges = old.adj
     E = edges.shape[0]
+    B = split.n if split is not None and split.n > 1 else 1
     sizes = [S1, S1, S1 + 1, S1, S1 + 1, N, S1, S1, S1, max(S_old, 1), S1 + 1, max(S_old, 1), 2 * max(E, 1), S1 + 1,
-             2 * max(E, 1), 2 * max(E, 1), 4]
+             2 * max(E, 1), 2 * max(E, 1), 4 + B + 1, B + 1]
     buf = torch.empty(sum(sizes), dtype=I32, device=dev)
     parts, o = [], 0
     for n in sizes:
         parts.append(buf[o:o + n]); o += n
     (roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order, cl_ins, cl_sem, cl_rootpt, o2n, ch_off, ch_list, adj_new, csr_off,
-     csr_nbr, csr_eid, counts) = parts
-    host = np.zeros(4, np.int32)
+     csr_nbr, csr_eid, counts, scl) = parts
+    host = np.zeros(4 + B + 1, np.int32)
     ws = _ws(_lib.call("sgb_level_step_ws_bytes", S1, S_old), dev)
     oc = old.csr if (old is not None and mode == 1) else (None, None, None)
-    _lib.call("sgb_level_step", int(mode), old.adj if old is not None else None, old.adj.shape[0] if old is not None else 0,
+    common = (int(mode), old.adj if old is not None else None, old.adj.shape[0] if old is not None else 0,
               old.roots if old is not None else None, S_old, dist, float(th), int(sweep_cap), oc[0], oc[1], oc[2],
               edges, E, mapping, uf, S1, N, seg_off, seg_members, seg_of_pos,
               roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order, cl_ins, cl_sem, cl_rootpt, o2n, ch_off, ch_list,
-              adj_new, csr_off, csr_nbr, csr_eid, status, counts, host, ws, ws.numel(), _stream())
+              adj_new, csr_off, csr_nbr, csr_eid, status, counts, host)
+    if B == 1:
+        _lib.call("sgb_level_step", *common, ws, ws.numel(), _stream())
+    else:
+        max_cl_old = max(b - a for a, b in zip(old.scene_cl_off[:-1], old.scene_cl_off[1:])) if old is not None else 0
+        _lib.call("sgb_level_step_scenes", *common, split.d_seg_off, old.d_scene_cl_off if old is not None else None, scl, B,
+                  split.max_segs, max_cl_old, ws, ws.numel(), _stream())
     S, A = int(host[0]), int(host[1])
     L = Level()
+    L.scene_cl_off = [int(v) for v in host[4:4 + B + 1]] if B > 1 else [0, S]
+    L.d_scene_cl_off = scl if B > 1 else None
     L.S, L.counts = S, counts
     L.roots, L.cl_seg_off, L.cl_pt_off = roots[:S], cl_seg_off[:S + 1], cl_pt_off[:S + 1]
     L.seg2cl, L.cl_seg_list, L.order = seg2cl, cl_seg_list, order
@@ -356,15 +388,19 @@ def group_unlabeled_phase_b(unl, cand, roots_cur, uf):
     _lib.call("sgb_group_unlabeled_phase_b", unl, unl.numel(), cand, cand.shape[1], roots_cur, uf, uf.shape[1], _stream())
 
 
-def export_labels(unmap, seg_of_point, level: Level, want_seg=True):
-    """unmap [N_raw] i64 (or None) -> (seg, ins, sem) int32 [N_raw]."""
+def export_labels(unmap, seg_of_point, level: Level, want_seg=True, split=None):
+    """unmap [N_raw] i64 (or None) -> (seg, ins, sem) int32 [N_raw].  split (scene batch): segment labels are point ids inside the scene."""
     dev = seg_of_point.device
     n_raw = unmap.numel() if unmap is not None else seg_of_point.numel()
     seg = torch.empty(n_raw, dtype=I32, device=dev) if want_seg else None
     ins = torch.empty(n_raw, dtype=I32, device=dev)
     sem = torch.empty(n_raw, dtype=I32, device=dev)
-    _lib.call("sgb_export_labels", unmap, n_raw, seg_of_point, level.seg2cl, level.cl_rootpt, level.cl_ins, level.cl_sem,
-              seg, ins, sem, _stream())
+    if split is None or split.n == 1:
+        _lib.call("sgb_export_labels", unmap, n_raw, seg_of_point, level.seg2cl, level.cl_rootpt, level.cl_ins, level.cl_sem,
+                  seg, ins, sem, _stream())
+    else:
+        _lib.call("sgb_export_labels_scenes", unmap, n_raw, seg_of_point, level.seg2cl, level.cl_rootpt, level.cl_ins, level.cl_sem,
+                  seg, ins, sem, split.d_pt_off, split.n, _stream())
     return seg, ins, sem
 
 

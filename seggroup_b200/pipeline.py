@@ -33,10 +33,44 @@ class SceneDevice:
     unmap: torch.Tensor | None  # [N_raw] i64 or None (identity)
     real_label: torch.Tensor | None = None   # [N_raw,2] i64 (sem, ins) for evaluate()
     name: str = ""
+    split: ops.SceneSplit | None = None      # scene batch: several scenes concatenated block-diagonally (None = one scene)
 
     @property
     def n_points(self):
         return self.data.shape[0]
+
+    @property
+    def n_scenes(self):
+        return 1 if self.split is None else self.split.n
+
+    def ranges(self):
+        """(point, level-1 segment, raw vertex) offsets of the scenes: three host lists of n_scenes + 1 entries."""
+        if self.split is None:
+            n_raw = self.unmap.numel() if self.unmap is not None else self.n_points
+            return [0, self.n_points], [0, self.seg_off.numel() - 1], [0, n_raw]
+        return self.split.pt_off, self.split.seg_off, self.split.raw_off
+
+    @staticmethod
+    def concat(scenes):
+        """Several resident scenes -> ONE block-diagonal scene batch (device-side concatenation, point / segment ids offset by
+        the scene's base).  Scenes are independent in the reference (one scene per rank per step, train.py:92; BatchNorm
+        statistics, graphs and labels are per scene): a batch shares launches, not state."""
+        if len(scenes) == 1:
+            return scenes[0]
+        dev = scenes[0].data.device
+        pt, sg, rw = [0], [0], [0]
+        for sc in scenes:
+            pt.append(pt[-1] + sc.n_points)
+            sg.append(sg[-1] + sc.seg_off.numel() - 1)
+            rw.append(rw[-1] + (sc.unmap.numel() if sc.unmap is not None else sc.n_points))
+        cat = torch.cat
+        seg_off = cat([scenes[0].seg_off[:1]] + [sc.seg_off[1:] + pt[i] for i, sc in enumerate(scenes)])
+        unmap = cat([(sc.unmap if sc.unmap is not None else torch.arange(sc.n_points, device=dev)) + pt[i] for i, sc in enumerate(scenes)])
+        real = cat([sc.real_label for sc in scenes]) if all(sc.real_label is not None for sc in scenes) else None
+        return SceneDevice(data=cat([sc.data for sc in scenes]), weak_label=cat([sc.weak_label for sc in scenes]), seg_off=seg_off,
+                           seg_members=cat([sc.seg_members + pt[i] for i, sc in enumerate(scenes)]),
+                           adj0=cat([sc.adj0 + pt[i] for i, sc in enumerate(scenes)]), unmap=unmap, real_label=real,
+                           name="+".join(sc.name for sc in scenes), split=ops.SceneSplit(pt, sg, rw, dev))
 
     @staticmethod
     def from_host(scene, device="cuda", non_blocking=False):
@@ -97,51 +131,92 @@ class GcnAggFn(torch.autograd.Function):
         return dX, dsims, None, None, None, None
 
 
+def _acc(total, part):
+    return part if total is None else total + part
+
+
 class Mlp1Fn(torch.autograd.Function):
-    """MLP1 (model.py:65-80) on the segment clouds; BN statistics are returned for the running-stat update."""
+    """MLP1 (model.py:65-80) on the segment clouds; BN statistics are returned for the running-stat update.
+    seg_ranges: level-1 segment range of every scene of the batch — BatchNorm statistics are per scene (one scene per forward
+    in the reference), so the kernels run once per range on row slices of the batch arrays."""
     @staticmethod
-    def forward(ctx, clouds, W, gamma, beta):
-        o = ops.mlp1_fwd(clouds, W.contiguous(), gamma.contiguous(), beta.contiguous())
-        ctx.save_for_backward(clouds, W, o["knn"], o["arg_pt"], o["stats"], o["mom"])
-        ctx.mark_non_differentiable(o["knn"], o["stats"], o["var"])
-        return o["feat"], o["knn"], o["stats"], o["var"]
+    def forward(ctx, clouds, W, gamma, beta, seg_ranges):
+        S = clouds.shape[0]
+        dev = clouds.device
+        Wc, gc, bc = W.contiguous(), gamma.contiguous(), beta.contiguous()
+        feat = torch.empty(S, 128, dtype=torch.float32, device=dev)
+        knn = torch.empty(S, 64, 10, dtype=I32, device=dev)
+        arg_pt = torch.empty(S, 64, dtype=I32, device=dev)
+        stats, var, mom = [], [], []
+        for lo, hi in seg_ranges:
+            o = ops.mlp1_fwd(clouds[lo:hi], Wc, gc, bc, feat=feat[lo:hi], knn=knn[lo:hi], arg_pt=arg_pt[lo:hi])
+            stats.append(o["stats"]); var.append(o["var"]); mom.append(o["mom"])
+        stats, var, mom = torch.stack(stats), torch.stack(var), torch.stack(mom)
+        ctx.save_for_backward(clouds, W, knn, arg_pt, stats, mom)
+        ctx.seg_ranges = seg_ranges
+        ctx.mark_non_differentiable(knn, stats, var)
+        return feat, knn, stats, var                      # stats [B,4,64], var [B,64]
 
     @staticmethod
     def backward(ctx, g, *_):
         clouds, W, knn, arg_pt, stats, mom = ctx.saved_tensors
-        gW, gg, gb = ops.mlp1_bwd(g.contiguous(), clouds, knn, arg_pt, W, stats, mom)
-        return None, gW.view_as(W), gg, gb
+        g = g.contiguous()
+        gW = gg = gb = None
+        for b, (lo, hi) in enumerate(ctx.seg_ranges):       # fixed scene order -> deterministic sums
+            w_, g_, b_ = ops.mlp1_bwd(g[lo:hi], clouds[lo:hi], knn[lo:hi], arg_pt[lo:hi], W, stats[b], mom[b])
+            gW, gg, gb = _acc(gW, w_), _acc(gg, g_), _acc(gb, b_)
+        return None, gW.view_as(W), gg, gb, None
 
 
 class EdgeConvPoolFn(torch.autograd.Function):
     """MLP2 / MLP3 (model.py:106-138) fused with the point -> segment max pooling that always follows
-    (model.py:793, 834): returns the pooled [S,64] features."""
+    (model.py:793, 834): returns the pooled [S,64] features.  pt_ranges / cl_ranges: point and cluster range of every scene of
+    the batch; the EdgeConv kernels (BatchNorm over one scene's N*20 edges) run once per scene on row slices, `knn` holds
+    scene-relative ids, the pooling runs once over the whole batch."""
     @staticmethod
-    def forward(ctx, x9, knn, cl_pt_off, order, W1, g1, b1, W2, g2, b2):
+    def forward(ctx, x9, knn, cl_pt_off, order, W1, g1, b1, W2, g2, b2, pt_ranges, cl_ranges):
         two = W2 is not None
-        o = ops.edgeconv_fwd(x9, knn, W1.contiguous(), g1.contiguous(), b1.contiguous(),
-                             W2.contiguous() if two else None, g2.contiguous() if two else None, b2.contiguous() if two else None)
-        pooled, arg = ops.segment_pool_max(o["out"], cl_pt_off, order)
-        ctx.two = two
-        saved = [x9, knn, arg, o["argk"], W1, o["stats1"], o["mom1"], o["ctr"]]
+        N = x9.shape[0]
+        dev = x9.device
+        out = torch.empty(N, 64, dtype=torch.float32, device=dev)
+        argk = torch.empty(N, 64, dtype=torch.uint8, device=dev)
+        cW1, cg1, cb1 = W1.contiguous(), g1.contiguous(), b1.contiguous()
+        cW2, cg2, cb2 = (W2.contiguous(), g2.contiguous(), b2.contiguous()) if two else (None, None, None)
+        per = []
+        for lo, hi in pt_ranges:
+            per.append(ops.edgeconv_fwd(x9[lo:hi], knn[lo:hi], cW1, cg1, cb1, cW2, cg2, cb2, out=out[lo:hi], argk=argk[lo:hi]))
+        pooled, arg = ops.segment_pool_max(out, cl_pt_off, order)
+        ctx.two, ctx.pt_ranges, ctx.cl_ranges = two, pt_ranges, cl_ranges
+        st = lambda k: torch.stack([o[k] for o in per])
+        saved = [x9, knn, arg, argk, W1, st("stats1"), st("mom1"), st("ctr")]
         if two:
-            saved += [W2, o["stats2"], o["mom2"]]
+            saved += [W2, st("stats2"), st("mom2")]
         ctx.save_for_backward(*saved)
-        stats = torch.stack([o["stats1"], o["stats2"]]) if two else o["stats1"].unsqueeze(0)
-        var = torch.stack([o["var1"], o["var2"]]) if two else o["var1"].unsqueeze(0)
-        ctx.mark_non_differentiable(stats, var, o["out"])
-        return pooled, o["out"], stats, var
+        stats = torch.stack([st("stats1"), st("stats2")], 1) if two else st("stats1").unsqueeze(1)      # [B,L,4,64]
+        var = torch.stack([st("var1"), st("var2")], 1) if two else st("var1").unsqueeze(1)              # [B,L,64]
+        ctx.mark_non_differentiable(stats, var, out)
+        return pooled, out, stats, var
 
     @staticmethod
     def backward(ctx, g, *_):
         sv = ctx.saved_tensors
         x9, knn, arg, argk, W1, stats1, mom1, ctr = sv[:8]
-        if ctx.two:
+        two = ctx.two
+        if two:
             W2, stats2, mom2 = sv[8:]
-            r = ops.edgeconv_bwd(g.contiguous(), arg, argk, x9, knn, W1, stats1, mom1, ctr, W2, stats2, mom2)
-            return (None, None, None, None, r["gW1"].view_as(W1), r["gg1"], r["gb1"], r["gW2"].view_as(W2), r["gg2"], r["gb2"])
-        r = ops.edgeconv_bwd(g.contiguous(), arg, argk, x9, knn, W1, stats1, mom1, ctr)
-        return (None, None, None, None, r["gW1"].view_as(W1), r["gg1"], r["gb1"], None, None, None)
+        g = g.contiguous()
+        acc = {}
+        for b, ((lo, hi), (c0, c1)) in enumerate(zip(ctx.pt_ranges, ctx.cl_ranges)):
+            arg_b = arg[c0:c1] if lo == 0 else arg[c0:c1] - lo          # arg-max rows relative to the scene's first point
+            if two:
+                r = ops.edgeconv_bwd(g[c0:c1], arg_b, argk[lo:hi], x9[lo:hi], knn[lo:hi], W1, stats1[b], mom1[b], ctr[b], W2, stats2[b], mom2[b])
+            else:
+                r = ops.edgeconv_bwd(g[c0:c1], arg_b, argk[lo:hi], x9[lo:hi], knn[lo:hi], W1, stats1[b], mom1[b], ctr[b])
+            for k, v in r.items():
+                acc[k] = _acc(acc.get(k), v)
+        if two:
+            return (None, None, None, None, acc["gW1"].view_as(W1), acc["gg1"], acc["gb1"], acc["gW2"].view_as(W2), acc["gg2"], acc["gb2"], None, None)
+        return (None, None, None, None, acc["gW1"].view_as(W1), acc["gg1"], acc["gb1"], None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -160,13 +235,21 @@ def evaluate(real_label, sem_pred, ins_pred, status=None):
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class ForwardResult:
-    labels: dict = field(default_factory=dict)      # 'layer_1.seg' ... 'final.sem' -> int32 [N_raw] (device)
-    metrics: tuple | None = None                    # (IoU_sem, IoU_ins, acc)
-    loss_raw: torch.Tensor | None = None            # [1,2] (sum, count)
+    labels: dict = field(default_factory=dict)      # 'layer_1.seg' ... 'final.sem' -> int32 [N_raw] (device; a batch: all scenes concatenated)
+    metrics: tuple | None = None                    # (IoU_sem, IoU_ins, acc) of the scene (a batch: of scene 0; all in metrics_scenes)
+    loss_raw: torch.Tensor | None = None            # [B,2] (sum, count) per scene
     levels: list = field(default_factory=list)
-    bn_stats: dict = field(default_factory=dict)    # prefix -> (batch mean [64], biased var [64], count)
+    bn_stats: dict = field(default_factory=dict)    # prefix -> (batch mean [64], biased var [64], count) (a batch: scene 0)
     aux: dict = field(default_factory=dict)         # intermediates for the parity tests
     status: int = 0
+    metrics_scenes: list = field(default_factory=list)   # per scene (IoU_sem, IoU_ins, acc)
+    raw_off: list = field(default_factory=list)     # raw-vertex offsets of the scenes inside the label vectors
+    bn_stats_scenes: dict = field(default_factory=dict)  # prefix -> (mean [B,64], var [B,64], counts list)
+
+    def scene_labels(self, b):
+        """label vectors of scene b of a batch"""
+        lo, hi = self.raw_off[b], self.raw_off[b + 1]
+        return {k: v[lo:hi] for k, v in self.labels.items()}
 
 
 def _gcn(p, key, Fc, adj, csr, keep=None, tag=""):
@@ -177,15 +260,28 @@ def _gcn(p, key, Fc, adj, csr, keep=None, tag=""):
     return F.relu(keep("Z_" + tag, F.linear(AX, p[key])))
 
 
+def _pairs(off):
+    return list(zip(off[:-1], off[1:]))
+
+
 def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool = False, dropout_mask=None,
-                  export: bool = True, classifier=None) -> ForwardResult:
+                  export: bool = True, classifier=None, sweep_cap: int = 64) -> ForwardResult:
     """p: dict of parameter tensors keyed like the reference state_dict (mlp_1.conv1.0.weight, ...).
     classifier: optional callable Feat_6 -> logits (the nn.Module head of SegModel, which then owns its
-    BatchNorm1d buffers and dropout RNG); without it the head is evaluated functionally from `p`."""
+    BatchNorm1d buffers and dropout RNG); without it the head is evaluated functionally from `p`.
+    sc may be a scene batch (SceneDevice.concat): every launch of the graph / kNN / pooling / export kernels then serves all
+    scenes, while everything the reference defines per scene stays per scene (BatchNorm statistics, the order-dependent
+    grouping replays, arg-min columns, kNN lists, segment labels, metrics, the classifier head and its loss).
+    dropout_mask: [I,128] bool (one scene) or a list of them (batch)."""
     res = ForwardResult()
     sem_infer = mode == "sem_infer"
     dev = sc.data.device
     status = torch.zeros(1, dtype=I32, device=dev)
+    split = sc.split
+    B = sc.n_scenes
+    pt_off, seg_off_s, raw_off = sc.ranges()
+    pt_ranges, seg_ranges = _pairs(pt_off), _pairs(seg_off_s)
+    res.raw_off = list(raw_off)
     live = res.aux.setdefault("_live", {}) if keep_aux else None
 
     def keep(name, t):
@@ -199,14 +295,26 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     def put_labels(tag, L, seg=True):
         if not export:
             return
-        s, i, m = ops.export_labels(sc.unmap, sop, L, want_seg=seg)
+        s, i, m = ops.export_labels(sc.unmap, sop, L, want_seg=seg, split=split)
         if seg:
             res.labels[tag + ".seg"] = s
         res.labels[tag + ".ins"], res.labels[tag + ".sem"] = i, m
 
+    def put_metrics(sem_key, ins_key):
+        if sc.real_label is None or not export:
+            return
+        for lo, hi in _pairs(raw_off):
+            res.metrics_scenes.append(evaluate(sc.real_label[lo:hi], res.labels[sem_key][lo:hi], res.labels[ins_key][lo:hi], status))
+        res.metrics = res.metrics_scenes[0]
+
+    def put_bn(prefix, mean, var, counts):
+        """mean / var [B,64]"""
+        res.bn_stats[prefix] = (mean[0], var[0], counts[0])
+        res.bn_stats_scenes[prefix] = (mean, var, counts)
+
     # ---- graph initialisation (model.py:712-738)
     sop, sos, uf = ops.scene_init(sc.seg_off, sc.seg_members, sc.weak_label)
-    step = lambda mode, **kw: ops.level_step(mode, uf, sc.seg_off, sc.seg_members, sos, status, **kw)
+    step = lambda mode, **kw: ops.level_step(mode, uf, sc.seg_off, sc.seg_members, sos, status, sweep_cap=sweep_cap, split=split, **kw)
     L1 = step(2, edges=sc.adj0, mapping=sop)
     adj_1 = L1.adj
     put_labels("layer_1", L1)
@@ -215,8 +323,8 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     # ---- structural grouping layer (model.py:747-783)
     cloud_idx, _ = ops.cluster_cloud_indices(sc.data, L1.order, L1.cl_pt_off, 64, status=status)
     clouds = ops.cluster_cloud_transform(sc.data, cloud_idx)
-    Feat_1, knn_1, stats, var = Mlp1Fn.apply(clouds, p["mlp_1.conv1.0.weight"], p["mlp_1.bn1.weight"], p["mlp_1.bn1.bias"])
-    res.bn_stats["mlp_1.bn1"] = (stats[0], var, L1.S * 640)
+    Feat_1, knn_1, stats, var = Mlp1Fn.apply(clouds, p["mlp_1.conv1.0.weight"], p["mlp_1.bn1.weight"], p["mlp_1.bn1.bias"], seg_ranges)
+    put_bn("mlp_1.bn1", stats[:, 0], var, [(hi - lo) * 640 for lo, hi in seg_ranges])
     d1 = ops.edge_dist(Feat_1.detach(), adj_1)
     L2 = step(0, old=L1, dist=d1, th=3.0 if sem_infer else 6.0)
     adj_2 = L2.adj
@@ -228,34 +336,36 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     if keep_aux:
         res.aux.update(adj_1=adj_1, cloud_idx_1=cloud_idx, data_1=clouds, knn_1=knn_1, Feat_1=Feat_1.detach(), dists_1=d1, adj_2=adj_2)
     if sem_infer:
-        if sc.real_label is not None and export:
-            res.metrics = evaluate(sc.real_label, res.labels["layer_2.sem"], res.labels["layer_2.ins"], status)
+        put_metrics("layer_2.sem", "layer_2.ins")
         res.status = L2.status
         return res
 
     # ---- semantic grouping layers (model.py:788-865)
     def semantic_layer(Lc, Feat_c, pre, gcn_key, tag, two):
         adj_c = Lc.adj
-        knn = ops.cluster_knn(sc.data, Lc.order, Lc.cl_pt_off, 20)
+        knn = ops.cluster_knn(sc.data, Lc.order, Lc.cl_pt_off, 20, scene_pt_off=split.d_pt_off if B > 1 else None)
         x9 = ops.centralize(sc.data, Lc.order, Lc.cl_pt_off)
         W2 = p[pre + ".conv2.0.weight"] if two else None
         g2 = p[pre + ".bn2.weight"] if two else None
         b2 = p[pre + ".bn2.bias"] if two else None
         W1, g1, b1 = p[pre + ".conv1.0.weight"], p[pre + ".bn1.weight"], p[pre + ".bn1.bias"]
         if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (W1, g1, b1, W2, g2, b2)):
-            fm, feat_pts, stats, var = EdgeConvPoolFn.apply(x9, knn, Lc.cl_pt_off, Lc.order, W1, g1, b1, W2, g2, b2)
+            fm, feat_pts, stats, var = EdgeConvPoolFn.apply(x9, knn, Lc.cl_pt_off, Lc.order, W1, g1, b1, W2, g2, b2,
+                                                            pt_ranges, _pairs(Lc.scene_cl_off))
         else:
             # inference: nothing is kept for a backward pass
-            o = ops.edgeconv_fwd(x9, knn, W1.contiguous(), g1.contiguous(), b1.contiguous(),
-                                 W2.contiguous() if two else None, g2.contiguous() if two else None, b2.contiguous() if two else None,
-                                 want_argk=False, want_backward=False)
-            feat_pts = o["out"]
+            feat_pts = torch.empty(x9.shape[0], 64, dtype=torch.float32, device=dev)
+            per = [ops.edgeconv_fwd(x9[lo:hi], knn[lo:hi], W1.contiguous(), g1.contiguous(), b1.contiguous(),
+                                    W2.contiguous() if two else None, g2.contiguous() if two else None, b2.contiguous() if two else None,
+                                    want_argk=False, want_backward=False, out=feat_pts[lo:hi]) for lo, hi in pt_ranges]
             fm, _ = ops.segment_pool_max(feat_pts, Lc.cl_pt_off, Lc.order, want_argmax=False)
-            stats = torch.stack([o["stats1"], o["stats2"]]) if two else o["stats1"].unsqueeze(0)
-            var = torch.stack([o["var1"], o["var2"]]) if two else o["var1"].unsqueeze(0)
-        res.bn_stats[pre + ".bn1"] = (stats[0, 0], var[0], sc.n_points * 20)
+            st = lambda k: torch.stack([o[k] for o in per])
+            stats = torch.stack([st("stats1"), st("stats2")], 1) if two else st("stats1").unsqueeze(1)
+            var = torch.stack([st("var1"), st("var2")], 1) if two else st("var1").unsqueeze(1)
+        counts = [(hi - lo) * 20 for lo, hi in pt_ranges]
+        put_bn(pre + ".bn1", stats[:, 0, 0], var[:, 0], counts)
         if two:
-            res.bn_stats[pre + ".bn2"] = (stats[1, 0], var[1], sc.n_points * 20)
+            put_bn(pre + ".bn2", stats[:, 1, 0], var[:, 1], counts)
         keep("pool_" + tag, fm)
         Fc = keep("cat_" + tag, torch.cat([Feat_c, fm], dim=-1))
         Fg = keep("gcn_" + tag, _gcn(p, gcn_key, Fc, adj_c, Lc.csr, keep, tag))
@@ -276,7 +386,8 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     if keep_aux:
         res.aux.update(adj_3=L3.adj, adj_4=L4.adj)
 
-    # ---- final clustering, phase A (model.py:439-470)
+    # ---- final clustering, phase A (model.py:439-470).  In a batch the loop runs until NO scene changes: an iteration on a
+    # ---- scene that has converged unions nothing (its unlabeled clusters have no neighbour left or none exist).
     Lo, Feat = L4, Feat_4
     count_old = Lo.S
     while True:
@@ -290,59 +401,83 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     res.aux["phaseA_clusters"] = Lo.S
     # phase B (model.py:472-509) only runs when an unlabeled cluster survives phase A
     if Lo.n_unlabeled > 0:
-        Lo, Feat = _phase_b(sc, uf, sos, status, Lo, Feat)
+        Lo, Feat = _phase_b(sc, uf, sos, status, Lo, Feat, split, sweep_cap)
     L5, Feat_5 = Lo, Feat
     res.levels.append(L5)
     put_labels("final", L5, seg=False)
     if keep_aux:
         res.aux["Feat_5"] = Feat_5.detach()
         keep("Feat_5", Feat_5)
-    if sc.real_label is not None and export:
-        res.metrics = evaluate(sc.real_label, res.labels["final.sem"], res.labels["final.ins"], status)
+    put_metrics("final.sem", "final.ins")
     res.status = L5.status
     if mode == "ins_infer":
         return res
 
-    # ---- classifier (model.py:902-932): per-instance max, MLP head, label-smoothed CE (sum)
-    ins = L5.cl_ins.cpu().numpy()
-    sem = L5.cl_sem.cpu().numpy()
-    uniq = np.unique(ins)
-    order = np.argsort(ins, kind="stable").astype(np.int32)
-    off = np.concatenate([[0], np.cumsum([(ins == u).sum() for u in uniq])]).astype(np.int32)
-    sem_gt = torch.as_tensor(np.array([sem[order[off[i]]] for i in range(len(uniq))], np.int64), device=dev)
-    Feat_6, _ = SegmentMaxFn.apply(Feat_5, torch.as_tensor(off, device=dev), torch.as_tensor(order, device=dev))
-    if classifier is not None:
-        logits = classifier(Feat_6)
+    # ---- classifier (model.py:902-932): per-instance max, MLP head, label-smoothed CE (sum) — per scene
+    ins, sem = L5.cl_ins.long(), L5.cl_sem.long()
+    if B == 1:
+        key = ins + 1
+        kmul = None
     else:
-        h = F.linear(Feat_6, p["classifier.linear1.weight"])
-        h = F.batch_norm(h, None, None, p["classifier.bn1.weight"], p["classifier.bn1.bias"], True, 0.1, 1e-5)
-        h = F.leaky_relu(h, 0.2)
-        if dropout_mask is None:
-            h = F.dropout(h, 0.5, True)
+        kmul = int(ins.max().item()) + 2
+        scene_of_cl = torch.repeat_interleave(torch.arange(B, device=dev), torch.tensor([b - a for a, b in _pairs(L5.scene_cl_off)], device=dev))
+        key = scene_of_cl * kmul + ins + 1
+    uniq, inv = torch.unique(key, return_inverse=True)                 # ascending: per scene ascending weak ins label (np.unique, model.py:905)
+    order = torch.argsort(inv, stable=True).to(I32)                    # clusters of a group in ascending order
+    off = torch.zeros(uniq.numel() + 1, dtype=I32, device=dev)
+    off[1:] = torch.cumsum(torch.bincount(inv, minlength=uniq.numel()), 0)
+    sem_gt = sem[order[off[:-1].long()].long()]                        # sem label of the first cluster of the group (model.py:916)
+    Feat_6, _ = SegmentMaxFn.apply(Feat_5, off, order)
+    g_off = [0, int(uniq.numel())] if B == 1 else [0] + torch.cumsum(torch.bincount(uniq // kmul, minlength=B), 0).tolist()
+    masks = dropout_mask if isinstance(dropout_mask, (list, tuple)) else [dropout_mask] * B
+    losses, logits_all = [], []
+    for b, (g0, g1) in enumerate(_pairs(g_off)):
+        f6 = Feat_6[g0:g1]
+        if classifier is not None:
+            logits = classifier(f6)
         else:
-            h = h * dropout_mask.to(h.dtype) * 2.0
-        logits = F.linear(h, p["classifier.linear2.weight"], p["classifier.linear2.bias"])
-    eps, n_class = 0.2, logits.size(1)
-    one_hot = torch.zeros_like(logits).scatter(1, sem_gt.view(-1, 1), 1)
-    one_hot = one_hot * (1 - eps) + (1 - one_hot) * eps / (n_class - 1)
-    loss_sum = -(one_hot * F.log_softmax(logits, dim=1)).sum()
-    res.loss_raw = torch.cat([loss_sum.view(1), torch.tensor([float(len(uniq))], device=dev)]).unsqueeze(0)
+            h = F.linear(f6, p["classifier.linear1.weight"])
+            h = F.batch_norm(h, None, None, p["classifier.bn1.weight"], p["classifier.bn1.bias"], True, 0.1, 1e-5)
+            h = F.leaky_relu(h, 0.2)
+            if masks[b] is None:
+                h = F.dropout(h, 0.5, True)
+            else:
+                h = h * masks[b].to(h.dtype) * 2.0
+            logits = F.linear(h, p["classifier.linear2.weight"], p["classifier.linear2.bias"])
+        eps, n_class = 0.2, logits.size(1)
+        one_hot = torch.zeros_like(logits).scatter(1, sem_gt[g0:g1].view(-1, 1), 1)
+        one_hot = one_hot * (1 - eps) + (1 - one_hot) * eps / (n_class - 1)
+        loss_sum = -(one_hot * F.log_softmax(logits, dim=1)).sum()
+        losses.append(torch.stack([loss_sum, torch.full((), float(g1 - g0), dtype=loss_sum.dtype, device=dev)]))
+        logits_all.append(logits)
+    res.loss_raw = torch.stack(losses)                                 # [B,2] = (sum, count) per scene (model.py:932 returns [1,2])
     if keep_aux:
-        res.aux["logits"] = logits.detach()
+        res.aux["logits"] = torch.cat(logits_all).detach()
     return res
 
 
-def _phase_b(sc, uf, sos, status, Lo, Feat):
+def _phase_b(sc, uf, sos, status, Lo, Feat, split, sweep_cap=64):
     """model.py:472-509 — nearest labelled cluster by sampled-cloud distance for clusters phase A left unlabeled.
-    Clouds: FPS kernel; distances / sort: torch device ops on [n_unl, S, 1024]; the order-dependent unions: one kernel."""
+    Clouds: FPS kernel; distances / sort: torch device ops, one unlabeled cluster chunk at a time ([chunk, S_scene, 1024]);
+    the order-dependent unions: one kernel launch per scene that still has an unlabeled cluster."""
     P = 1024
     cloud_idx, _ = ops.cluster_cloud_indices(sc.data, Lo.order, Lo.cl_pt_off, P, status=status)
-    pts = sc.data[:, :3][cloud_idx.long().view(-1)].view(Lo.S, P, 3)
-    unl = torch.nonzero(Lo.cl_ins == -1).view(-1)                           # ascending dense ids
-    mean = pts[unl].mean(1).view(-1, 1, 1, 3)                               # [n_unl,1,1,3]
-    dmin = ((mean - pts.unsqueeze(0)) ** 2).sum(3).min(-1)[0]               # [n_unl,S]
-    cand = torch.sort(dmin, dim=1)[1].to(I32).contiguous()
-    ops.group_unlabeled_phase_b(unl.to(I32).contiguous(), cand, Lo.roots, uf)
-    Ln = ops.level_step(2, uf, sc.seg_off, sc.seg_members, sos, status, old=Lo)
+    xyz = sc.data[:, :3]
+    unl_all = torch.nonzero(Lo.cl_ins == -1).view(-1)                       # ascending dense ids
+    for c0, c1 in _pairs(Lo.scene_cl_off):
+        unl = unl_all[(unl_all >= c0) & (unl_all < c1)]
+        if unl.numel() == 0 or c1 - c0 < 2:
+            continue
+        pts = xyz[cloud_idx[c0:c1].long().view(-1)].view(c1 - c0, P, 3)     # this scene's clouds
+        mean = pts[(unl - c0)].mean(1)                                      # [n_unl,3]
+        cand = []
+        chunk = max(1, (64 << 20) // ((c1 - c0) * P * 16))                  # <= ~64 MB of temporaries per chunk
+        for q in range(0, unl.numel(), chunk):
+            m = mean[q:q + chunk].view(-1, 1, 1, 3)
+            dmin = ((m - pts.unsqueeze(0)) ** 2).sum(3).min(-1)[0]          # [chunk, S_scene]
+            cand.append(torch.sort(dmin, dim=1)[1])
+        cand = (torch.cat(cand) + c0).to(I32).contiguous()                  # candidate cluster ids (batch-wide dense ids)
+        ops.group_unlabeled_phase_b(unl.to(I32).contiguous(), cand, Lo.roots, uf)
+    Ln = ops.level_step(2, uf, sc.seg_off, sc.seg_members, sos, status, old=Lo, sweep_cap=sweep_cap, split=split)
     Feat, _ = SegmentMaxFn.apply(Feat, Ln.ch_off, Ln.ch_list)
     return Ln, Feat

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--points", type=int, default=50000)
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--g", type=float, default=4.0)
+    ap.add_argument("--fixture", default="", help="tests/golden stem with %s for the mode, e.g. seggroup50k_s9_%s_g4")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "diag_parity.txt"))
     a = ap.parse_args()
     from oracle import seggroup_oracle as O
@@ -127,6 +128,27 @@ def main():
             continue
         gr = gr.numpy(); gc = p[k].grad.cpu().numpy()
         say("%-28s %.3e  (%.3e)" % (k, rel(gc, gr), np.abs(gc - gr).max() / (np.abs(gr).max() + 1e-30)))
+    # the same comparison with the CUDA path's ReLU active set imposed on the oracle's backward (one entry of Z within rounding
+    # of zero flips the derivative 0 <-> 1 and that alone moves every gradient upstream of it)
+    masks = {t: (lc["Z_" + t].detach() > 0).cpu() for t in ("2", "3")}
+    for t in ("2", "3"):
+        zr = lr["Z_" + t].detach()
+        flipped = (zr > 0) != masks[t]
+        say("ReLU of gcn_%s: %d of %d activations differ; largest |Z| among them %.3e (max |Z| %.3e, min |Z| %.3e)" % (
+            t, int(flipped.sum()), flipped.numel(), float(zr[flipped].abs().max()) if flipped.any() else 0.0, float(zr.abs().max()), float(zr.abs().min())))
+    ref2 = O.forward(scene, params_cpu, mode="train", tie="canonical", dropout_mask=mask, want_grads=True, relu_masks=masks)
+    gold = None
+    if a.fixture:
+        gold = np.load(os.path.join(ROOT, "tests", "golden", (a.fixture % "train") + ".npz"))
+        say("fixture %s: relu margin %s, reference CPU seconds %.1f" % (a.fixture, gold["relu_margin"].tolist() if "relu_margin" in gold.files else None,
+                                                                         float(gold["reference_cpu_seconds"]) if "reference_cpu_seconds" in gold.files else -1))
+    say("\n== parameter gradients, relative L2 error: vs oracle(canonical) | vs oracle(canonical, CUDA's ReLU active set) | vs the reference fixture")
+    for k in TRAINABLE:
+        if ref["grads"][k] is None or p[k].grad is None:
+            continue
+        gc = p[k].grad.cpu().numpy()
+        say("%-28s %.3e | %.3e | %s" % (k, rel(gc, ref["grads"][k].numpy()), rel(gc, ref2["grads"][k].numpy()),
+                                       ("%.3e" % rel(gc, gold["grad/" + k])) if gold is not None and ("grad/" + k) in gold.files else "-"))
     # smallest edge distances feeding d(dist)/d(feat) = diff / d  (ill-conditioned when d ~ eps * sqrt(C))
     say("\n== smallest edge distances per level (pairwise_distance eps = 1e-6)")
     for k in ("dists_1", "dists_2", "dists_3"):
