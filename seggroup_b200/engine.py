@@ -60,7 +60,7 @@ class SceneExecutor:
         main = torch.cuda.current_stream(self.device)
         for st in self.streams + [main]:
             with torch.cuda.stream(st):
-                big = torch.empty(nbytes if st is not main else nbytes // 4, dtype=torch.uint8, device=self.device)
+                big = torch.empty(nbytes if (st is not main or self.fused) else nbytes // 4, dtype=torch.uint8, device=self.device)
                 small = [torch.empty(1 << 20, dtype=torch.uint8, device=self.device) for _ in range(64)]      # small-pool segments (2 MB each hold two)
                 tiny = [torch.empty(256 << 10, dtype=torch.uint8, device=self.device) for _ in range(128)]
                 del big, small, tiny
@@ -179,10 +179,18 @@ class SceneExecutor:
 # ------------------------------------------------------------------------------------------------
 # multi-GPU plumbing: scenes are the shard unit, one process per GPU
 # ------------------------------------------------------------------------------------------------
-def shard_scenes(n_scenes: int, rank: int, world: int):
-    """Scene indices of `rank`: round-robin `rank::world`, WITHOUT the padding duplicates of the reference's
-    DistributedSampler (train.py:102 pads 1,201 scenes to 1,208 at 8 ranks, so 7 scenes are counted twice)."""
-    return list(range(rank, n_scenes, world))
+def shard_scenes(n_scenes: int, rank: int, world: int, pad: bool = False):
+    """Scene indices of `rank`: round-robin `rank::world`, by default WITHOUT the padding duplicates of the reference's
+    DistributedSampler (train.py:102 pads 1,201 scenes to 1,208 at 8 ranks, so 7 scenes are counted twice).
+    HAZARD: without padding the ranks get unequal counts (1,201 scenes on 8 ranks: 151 on rank 0, 150 elsewhere).  That is
+    what inference wants (no collective until the final reduce), but a loop that issues a collective PER STEP (training with
+    allreduce_flat) would leave the rank with the extra scene blocked in NCCL forever: use pad=True there — it repeats scenes
+    from the head of the list exactly like DistributedSampler, so every rank takes ceil(n / world) steps."""
+    if not pad:
+        return list(range(rank, n_scenes, world))
+    per = -(-n_scenes // world)
+    idx = list(range(n_scenes)) + list(range(per * world - n_scenes))
+    return idx[rank:per * world:world]
 
 
 def allreduce_flat(tensors, dist_module=None, average=True, extra=None):
@@ -192,7 +200,7 @@ def allreduce_flat(tensors, dist_module=None, average=True, extra=None):
     import torch.distributed as dist
     d = dist_module or dist
     if not d.is_available() or not d.is_initialized() or d.get_world_size() == 1:
-        return extra
+        return extra.reshape(-1).to(tensors[0].dtype).clone() if extra is not None else None      # same dtype / fresh tensor as the multi-rank path
     flats = [t.reshape(-1) for t in tensors] + ([extra.reshape(-1).to(tensors[0].dtype)] if extra is not None else [])
     flat = torch.cat(flats)
     d.all_reduce(flat)

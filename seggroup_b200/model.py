@@ -18,6 +18,7 @@ from __future__ import annotations
 import atexit
 import json
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -85,7 +86,9 @@ _writer = None
 def _get_writer():
     global _writer
     if _writer is None:
-        _writer = ThreadPoolExecutor(max_workers=2, thread_name_prefix="sgb-export")
+        # text formatting of 14 files x 150k lines per scene is ~15 ms of host time per scene: a pool keeps up with batches
+        n = int(os.environ.get("SGB_EXPORT_THREADS", "0")) or max(2, min(32, (os.cpu_count() or 4) - 2))   # pure C inside, GIL released
+        _writer = ThreadPoolExecutor(max_workers=n, thread_name_prefix="sgb-export")
         atexit.register(lambda: _writer.shutdown(wait=True))
     return _writer
 
@@ -160,6 +163,12 @@ class SegModel(nn.Module):
         self.write_files = True
         self._scene_cache = {}
         self._pending = []
+        self._pinned_pool = {}
+        self._path_locks = {}
+        self._io_lock = threading.Lock()
+        self._copy_stream = None
+        self._made_dirs = set()
+        self.d2h_bytes = 0                     # label bytes copied to the host so far (bench bookkeeping)
         self.last_result = None
         if visualize:
             raise NotImplementedError("visualize=True needs the ScanNet raw meshes and plyfile (out of scope, SURVEY.md 2.1 #5)")
@@ -186,69 +195,133 @@ class SegModel(nn.Module):
                            seg_off=side["seg_off"], seg_members=side["seg_members"], adj0=side["adj0"], unmap=side["unmap"],
                            real_label=side["real"], name=scene_name)
 
-    def _update_bn(self, bn_stats):
-        """Running-statistics update of training-mode BatchNorm (momentum 0.1, unbiased variance); the buffers
-        are never read (the reference never calls .eval()) but they are part of the checkpoint."""
+    def _update_bn(self, res):
+        """Running-statistics update of training-mode BatchNorm (momentum 0.1, unbiased variance), one update per scene in
+        batch order; the buffers are never read (the reference never calls .eval()) but they are part of the checkpoint."""
         mods = {"mlp_1.bn1": self.mlp_1.bn1, "mlp_2.bn1": self.mlp_2.bn1, "mlp_3.bn1": self.mlp_3.bn1, "mlp_3.bn2": self.mlp_3.bn2}
         with torch.no_grad():
-            for k, (mean, var, count) in bn_stats.items():
+            for k, (mean, var, counts) in res.bn_stats_scenes.items():
                 bn = mods.get(k)
                 if bn is None or not bn.training:
                     continue
                 m = bn.momentum
-                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1 - m).add_(var * (count / max(count - 1, 1)), alpha=m)
-                bn.num_batches_tracked += 1
+                for b, count in enumerate(counts):
+                    bn.running_mean.mul_(1 - m).add_(mean[b], alpha=m)
+                    bn.running_var.mul_(1 - m).add_(var[b] * (count / max(count - 1, 1)), alpha=m)
+                bn.num_batches_tracked += len(counts)
 
-    def _export(self, output_root, labels):
-        if not self.write_files:
+    # ---- label export (model.py:525-605): D2H on a side stream into pinned buffers, text formatting on writer threads
+    def _pinned(self, shape):
+        key = tuple(shape)
+        with self._io_lock:
+            pool = self._pinned_pool.setdefault(key, [])
+            if pool:
+                return pool.pop()
+        return torch.empty(key, dtype=torch.int32, pin_memory=True)
+
+    def _check_pending(self, wait=False):
+        """Surface writer failures (disk full, directory removed, ...): the reference writes synchronously and raises."""
+        keep = []
+        for f in self._pending:
+            if wait or f.done():
+                f.result()                         # re-raises the writer's exception in the caller
+            else:
+                keep.append(f)
+        self._pending = keep
+
+    def _export(self, output_roots, res):
+        """output_roots: one directory per scene of the batch.  One device->host copy of all label vectors of the batch."""
+        if not self.write_files or not res.labels:
             return
-        host = {k: v.cpu().numpy() for k, v in labels.items()}           # D2H of 14 x N_raw int32
+        self._check_pending()
+        keys = list(res.labels)
+        dev = res.labels[keys[0]].device
+        stacked = torch.stack([res.labels[k] for k in keys])               # [n_files, raw vertices of the batch] int32
+        host = self._pinned(stacked.shape)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            host.copy_(stacked, non_blocking=True)
+            stacked.record_stream(self._copy_stream)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        self.d2h_bytes += stacked.numel() * 4
+        raw_off = res.raw_off
+        n_tasks = len(keys) * len(output_roots)
+        state = {"left": n_tasks}
 
-        def write():
-            for k, v in host.items():
-                _lib.call("sgb_write_labels_host", os.path.join(output_root, k + ".txt").encode(), v, int(v.shape[0]))
+        def write(i, b):
+            done.synchronize()
+            lo, hi = raw_off[b], raw_off[b + 1]
+            path = os.path.join(output_roots[b], keys[i] + ".txt")
+            with self._path_lock(path):                                     # two forwards of the same scene / epoch: never interleaved
+                _lib.call("sgb_write_labels_host", path.encode(), host[i, lo:hi].numpy(), hi - lo)
+            with self._io_lock:
+                state["left"] -= 1
+                if state["left"] == 0:
+                    self._pinned_pool.setdefault(tuple(host.shape), []).append(host)
 
         if self.async_export:
-            self._pending = [f for f in self._pending if not f.done()]
-            self._pending.append(_get_writer().submit(write))
+            w = _get_writer()
+            self._pending += [w.submit(write, i, b) for b in range(len(output_roots)) for i in range(len(keys))]
         else:
-            write()
+            for b in range(len(output_roots)):
+                for i in range(len(keys)):
+                    write(i, b)
+
+    def _path_lock(self, path):
+        with self._io_lock:
+            lk = self._path_locks.get(path)
+            if lk is None:
+                lk = self._path_locks[path] = threading.Lock()
+            return lk
 
     def flush_exports(self):
-        for f in self._pending:
-            f.result()
-        self._pending = []
+        """Wait for every label file submitted so far; raises if a write failed."""
+        self._check_pending(wait=True)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, data, weak_label, info):
-        data, weak_label, info = data[0], weak_label[0], info[0]
+        """data [B,N,6] f32, weak_label [B,N,2] i64, info [B,1] i64 — B = 1 is the reference's call (train.py:92 forces batch
+        size 1, model.py:684-693 unpacks element 0); B > 1 runs the B scenes as one block-diagonal batch (per-scene BatchNorm
+        statistics, labels, metrics and loss) and returns loss [B,2], IoU_sem [B,2,40], IoU_ins [B,2,40], acc [B,4]."""
         if not data.is_cuda:
             raise _lib.SgbError("seggroup_b200.SegModel runs on CUDA only (got a %s tensor)" % data.device)
-        self.point_num = data.shape[0]
-        scene_name = self.scene_list[int(info)][:-1]
-        if self.epoch in ['sem_infer', 'ins_infer']:
-            output_root = os.path.join('results', self.exp_name, scene_name, self.epoch)
-        else:
-            output_root = os.path.join('results', self.exp_name, scene_name, 'epoch_' + self.epoch)
-        if self.write_files and not os.path.exists(output_root):
-            os.makedirs(output_root, exist_ok=True)
-
-        engine.reserve_current_stream(device=data.device)      # once per stream: no cudaMalloc in later forwards
-        sc = self._scene(scene_name, data, weak_label)
+        B = data.shape[0]
+        self.point_num = data.shape[1]
         mode = "sem_infer" if self.sem_infer else ("ins_infer" if self.ins_infer else "train")
-        res = pipeline.forward_scene(sc, self._params(), mode=mode, classifier=self.classifier, sweep_cap=self.SWEEP_CAP)
-        if res.status & 2:
-            import warnings
-            warnings.warn("scene %s: small-cluster sweep capped at %d iterations (the reference would not terminate)"
-                          % (scene_name, self.SWEEP_CAP))
-        if res.status & 1:
-            raise RuntimeError("scene %s: a segment with all points coincident needs farthest-point picks "
-                               "(the reference raises here as well, model.py:407-412)" % scene_name)
-        self._update_bn(res.bn_stats)
-        self._export(output_root, res.labels)
+        names = [self.scene_list[int(i)][:-1] for i in info.reshape(-1).tolist()]
+        stage = self.epoch if self.epoch in ['sem_infer', 'ins_infer'] else 'epoch_' + self.epoch
+        roots = [os.path.join('results', self.exp_name, n, stage) for n in names]
+        if self.write_files:
+            for r in roots:
+                if r not in self._made_dirs:
+                    os.makedirs(r, exist_ok=True)
+                    self._made_dirs.add(r)
+        with torch.cuda.device(data.device):                    # kernels launch on the tensors' device, whatever the current one is
+            engine.reserve_current_stream(device=data.device)  # once per stream: no cudaMalloc in later forwards
+            scenes = [self._scene(names[b], data[b], weak_label[b]) for b in range(B)]
+            sc = SceneDevice.concat(scenes)
+            res = pipeline.forward_scene(sc, self._params(), mode=mode, classifier=self.classifier, sweep_cap=self.SWEEP_CAP)
+            if res.status & 2:
+                import warnings
+                warnings.warn("scene %s: small-cluster sweep capped at %d iterations (the reference would not terminate)"
+                              % ("+".join(names), self.SWEEP_CAP))
+            if res.status & 1:
+                raise RuntimeError("scene %s: a segment with all points coincident needs farthest-point picks "
+                                   "(the reference raises here as well, model.py:407-412)" % "+".join(names))
+            self._update_bn(res)
+            self._export(roots, res)
         self.last_result = res
-        IoU_sem, IoU_ins, acc = res.metrics
+        if B == 1:
+            IoU_sem, IoU_ins, acc = res.metrics
+        else:
+            IoU_sem = torch.cat([m[0] for m in res.metrics_scenes])
+            IoU_ins = torch.cat([m[1] for m in res.metrics_scenes])
+            acc = torch.stack([m[2] for m in res.metrics_scenes])
         if mode != "train":
             return IoU_sem, IoU_ins, acc
         return res.loss_raw, IoU_sem, IoU_ins, acc

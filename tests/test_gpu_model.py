@@ -99,3 +99,62 @@ def test_cpu_input_is_refused(tree, scene8k):
     d, w, i = _inputs(scene8k)
     with pytest.raises(SgbError):
         model(d.cpu(), w.cpu(), i.cpu())
+
+
+def test_batched_forward_equals_per_scene_calls(tmp_path):
+    """B > 1 through the nn.Module (a DataLoader with batch_size = B): loss / metrics per scene and the 14 files of every scene
+    equal what B separate calls produce."""
+    from seggroup_b200 import synth
+    from seggroup_b200.model import SegModel
+    scenes = [synth.make_scene(31, 6000, name="scene_a"), synth.make_scene(32, 6000, name="scene_b"), synth.make_scene(33, 6000, name="scene_c")]
+    synth.write_scene_tree(str(tmp_path), scenes)
+    old = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        torch.manual_seed(1)
+        model = SegModel(exp_name="b").to("cuda")
+        with torch.no_grad():
+            model.mlp_1.bn1.weight.mul_(4.0)
+        model.classifier.dp1.p = 0.0
+        model.epoch = "1"
+        data = torch.stack([torch.from_numpy(s.data.copy()) for s in scenes]).cuda()
+        weak = torch.stack([torch.from_numpy(s.weak_label.copy()) for s in scenes]).cuda()
+        info = torch.arange(3).view(3, 1).cuda()
+        single = [model(data[b:b + 1], weak[b:b + 1], info[b:b + 1]) for b in range(3)]
+        model.flush_exports()
+        files = {}
+        for s in scenes:
+            root = os.path.join("results", "b", s.name, "epoch_1")
+            files[s.name] = {f: open(os.path.join(root, f), "rb").read() for f in sorted(os.listdir(root))}
+            assert len(files[s.name]) == 14
+        model.exp_name = "b2"
+        out = model(data, weak, info)
+        model.flush_exports()
+        assert out[0].shape == (3, 2) and out[1].shape == (3, 2, 40) and out[2].shape == (3, 2, 40) and out[3].shape == (3, 4)
+        for b, s in enumerate(scenes):
+            assert torch.allclose(out[0][b], single[b][0][0], rtol=1e-6)
+            assert torch.equal(out[1][b], single[b][1][0]) and torch.equal(out[2][b], single[b][2][0]) and torch.equal(out[3][b], single[b][3])
+            root = os.path.join("results", "b2", s.name, "epoch_1")
+            for f, blob in files[s.name].items():
+                assert open(os.path.join(root, f), "rb").read() == blob, (s.name, f)
+        loss = (out[0][:, 0] / out[0][:, 1]).mean()
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+        assert int(model.mlp_2.bn1.num_batches_tracked) == 6               # 3 single calls + one batch of 3
+    finally:
+        os.chdir(old)
+
+
+def test_export_failure_is_raised(tree, scene8k):
+    """A label file that cannot be written must surface (the reference writes synchronously and raises)."""
+    from seggroup_b200._lib import SgbError
+    from seggroup_b200.model import SegModel
+    model = SegModel(exp_name="x", ins_infer=True).to("cuda")
+    model.epoch = "ins_infer"
+    root = os.path.join("results", "x", scene8k.name, "ins_infer")
+    os.makedirs(root)
+    os.makedirs(os.path.join(root, "final.sem.txt"))                       # a directory where a file has to go
+    with torch.no_grad():
+        model(*_inputs(scene8k))
+    with pytest.raises(SgbError):
+        model.flush_exports()
