@@ -46,10 +46,9 @@ int sgb_exclusive_scan_i32(const int* in, int* out, int n, void* ws, size_t ws_b
 /* Dense fp32 GEMM on the tcgen05 tensor cores (TF32 x 3 split, fp32-level accuracy): C [M,N] = A [M,K] * B [N,K]^T,
  * the shape of nn.Linear (the GCN fc of seggroup/model.py:146-151).  N multiple of 16 and <= 256, K multiple of 4. */
 int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, void* stream);
-/* Bring-up probe: shared memory := the two images (word counts multiples of 256), ONE tcgen05.mma kind::tf32 with M = 128,
- * K = 8 and the given descriptor fields (start address filled in by the kernel), raw accumulator D [128,N] returned. */
-int sgb_tc_probe(const float* imgA, int wordsA, const float* imgB, int wordsB, unsigned long long descA,
-                 unsigned long long descB, unsigned idesc, int N, float* D, void* stream);
+/* a12  the GCN layer's dense part relu(fc(.)) (seggroup/model.py:146-151; fc = nn.Linear(bias=False)): C = [relu](A B^T) with the
+ * ReLU fused into the TMEM epilogue. */
+int sgb_linear_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a10  segment pooling: point features -> segment features
@@ -285,6 +284,11 @@ int sgb_group_unlabeled_step_scenes(const float* dist, const int* row_off, const
  * distance); further labelled candidates only receive the reference's stale-id point_num drift. */
 int sgb_group_unlabeled_phase_b(const int* unl, int n_unl, const int* cand, int S, const int* roots_cur, int* uf, int S1,
                                 void* stream);
+/* a14  the candidate lists of phase B (model.py:472-487): cand [n_unl,width] = the clusters of the unlabeled cluster's own scene by
+ * increasing min_p ||mean_i - p||^2 over the P sampled points of the candidate (cloud_idx [S,P] from sgb_cluster_cloud_indices),
+ * ties -> lower id, rows padded with -1 (sgb_group_unlabeled_phase_b stops at the first -1). */
+int sgb_phase_b_rank(const float* xyz, int stride, const int* cloud_idx, int P, const int* unl, int n_unl,
+                     const int* scene_cl_off, int n_scenes, int S, int* cand, int width, void* stream);
 
 /* a16  replaces seggroup/model.py:525-605 `export_{segment,instance,semantic}_label` up to the text
  * formatting: per raw vertex r (p = unmap[r], int64 as stored in unmap.pth; NULL = identity):

@@ -109,7 +109,9 @@ cluster_cloud_indices_kernel(const float* __restrict__ xyz, int stride, const in
         if (j > rem) j = rem;                              // python leaves j at its last value
         const int invalid = j - 1;
         if (invalid == 0) atomicOr(status, 1);             // the reference raises here
-        for (int t = 0; t < invalid; ++t) s_choice[rem - invalid + t] = s_choice[t];
+        // numpy assigns through a temporary when the two slices overlap (invalid > rem / 2); the overwritten tail was all
+        // zeros, so a source index inside it reads 0 whatever has been written there since
+        for (int t = 0; t < invalid; ++t) s_choice[rem - invalid + t] = (t < rem - invalid) ? s_choice[t] : 0;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < rem; i += FPS_THREADS) out[rep * n + i] = __ldg(order + lo + s_choice[i]);

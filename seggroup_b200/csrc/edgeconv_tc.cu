@@ -14,7 +14,7 @@
 //     the (max, min, arg) candidates; a light second kernel applies BN2 + LeakyReLU per point.
 // GRAM variant (training): the backward pass needs the second moments of the hidden activations, sum_e h h^T and sum_e h
 // (analytic BatchNorm backward, edgeconv_bwd.cu).  They are an edge contraction, i.e. the edges must lie along K.
-// kind::tf32 only walks MN-major operands in one swizzle mode that no K-major layout shares (tools/tc_probe2.py), so the
+// kind::tf32 only walks MN-major operands in one swizzle mode that no K-major layout shares (measured with a one-instruction descriptor probe during bring-up, round 1), so the
 // producers store h a second time, transposed ([hidden row][edges], K-major SWIZZLE_64B), and a second accumulator
 //   G[128, 80] += [H_lo^T ; H_hi^T] (K = edges) x [H_hi^T ; 1 ; 0]^T
 // collects lo*hi (rows 0..63), hi*hi (rows 64..127) and the column of ones gives sum h; hi*lo follows by symmetry.

@@ -502,7 +502,10 @@ group_nearby_kernel(const int* __restrict__ adj_all, int A_all, const int* __res
     __shared__ int s_flag;
     __shared__ int s_e0, s_e1;
     const SceneRange sr = scene_range(scene_seg_off, scene_cl_off, blockIdx.x, S1, S_cur);
-    if (threadIdx.x == 0) { s_e0 = edge_lower_bound(adj_all, A_all, sr.c0); s_e1 = edge_lower_bound(adj_all, A_all, sr.c1); }
+    if (threadIdx.x == 0) {                           // one scene (no scene arrays): every edge
+        s_e0 = scene_cl_off ? edge_lower_bound(adj_all, A_all, sr.c0) : 0;
+        s_e1 = scene_cl_off ? edge_lower_bound(adj_all, A_all, sr.c1) : A_all;
+    }
     const int n_loc = sr.s1 - sr.s0;
     if (state_in_smem) {
         for (int r = 0; r < 6; ++r)
@@ -687,6 +690,7 @@ __global__ void unlabeled_phase_b_kernel(const int* __restrict__ unl, int n_unl,
         bool merged = false;
         for (int t = 0; t < S; ++t) {
             const int j = cand[(size_t)q * S + t];
+            if (j < 0) break;                          // end of this cluster's candidate list (scene batch: rows are padded)
             if (j == i) continue;
             const int c2 = uf_find(u, roots_cur[j]);
             if (u.ins[c2] == -1) continue;
@@ -695,6 +699,78 @@ __global__ void unlabeled_phase_b_kernel(const int* __restrict__ unl, int n_unl,
             merged = true;
         }
     }
+}
+
+// Candidate ranking of phase B (model.py:472-487): for the unlabeled cluster i, every cluster j of ITS scene ordered by
+//     dmin(i, j) = min over the 1024 sampled points p of cluster j of ||mean_i - p||^2,   mean_i = mean of cluster i's 1024 samples
+// (squared distance (dx^2 + dy^2) + dz^2 in fp32 without FMA contraction, ascending, ties -> lower cluster id).
+// One CTA per unlabeled cluster: mean by a fixed-order tree, one warp per candidate cluster for the minimum, bitonic sort of
+// (dmin, j) in shared memory.  cand row q: n_scene_clusters ids, then -1 up to `width`.
+constexpr int PB_THREADS = 256;
+constexpr int PB_MAX = 4096;                              // clusters of one scene at this stage (a few dozen in practice)
+__global__ void __launch_bounds__(PB_THREADS)
+phase_b_rank_kernel(const float* __restrict__ xyz, int stride, const int* __restrict__ cloud_idx, int P, const int* __restrict__ unl,
+                    const int* __restrict__ scene_cl_off, int n_scenes, int S, int* __restrict__ cand, int width) {
+    __shared__ float s_key[PB_MAX];
+    __shared__ int s_id[PB_MAX];
+    __shared__ float s_red[3][PB_THREADS];
+    const int q = blockIdx.x, i = unl[q];
+    int c0 = 0, c1 = S;
+    if (scene_cl_off) { const int b = sgb_upper_segment(scene_cl_off, n_scenes, i); c0 = scene_cl_off[b]; c1 = scene_cl_off[b + 1]; }
+    const int n = c1 - c0;
+    // mean of the cluster's own samples: per-thread partial sums over a strided quarter, then a fixed binary tree
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int p = threadIdx.x; p < P; p += PB_THREADS) {
+        const float* pt = xyz + (size_t)__ldg(cloud_idx + (size_t)i * P + p) * stride;
+        ax += __ldg(pt); ay += __ldg(pt + 1); az += __ldg(pt + 2);
+    }
+    s_red[0][threadIdx.x] = ax; s_red[1][threadIdx.x] = ay; s_red[2][threadIdx.x] = az;
+    __syncthreads();
+    for (int o = PB_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) s_red[a][threadIdx.x] += s_red[a][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    const float mx = s_red[0][0] / (float)P, my = s_red[1][0] / (float)P, mz = s_red[2][0] / (float)P;
+    // minimum squared distance to every cluster of the scene: one warp per cluster
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int t = threadIdx.x; t < m; t += PB_THREADS) { s_key[t] = INFINITY; s_id[t] = 0x7fffffff; }
+    __syncthreads();
+    for (int jj = warp; jj < n; jj += PB_THREADS / 32) {
+        const int j = c0 + jj;
+        float best = INFINITY;
+        for (int p = lane; p < P; p += 32) {
+            const float* pt = xyz + (size_t)__ldg(cloud_idx + (size_t)j * P + p) * stride;
+            const float dx = __fsub_rn(mx, __ldg(pt)), dy = __fsub_rn(my, __ldg(pt + 1)), dz = __fsub_rn(mz, __ldg(pt + 2));
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            best = fminf(best, d);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(SGB_FULL_MASK, best, o));
+        if (lane == 0) { s_key[jj] = best; s_id[jj] = j; }
+    }
+    __syncthreads();
+    // bitonic sort of (key, id) ascending
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int jstep = k >> 1; jstep > 0; jstep >>= 1) {
+            for (int t = threadIdx.x; t < m; t += PB_THREADS) {
+                const int x = t ^ jstep;
+                if (x > t) {
+                    const bool up = (t & k) == 0;
+                    const float ka = s_key[t], kb = s_key[x];
+                    const int ia = s_id[t], ib = s_id[x];
+                    const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+                    if (a_gt_b == up) { s_key[t] = kb; s_key[x] = ka; s_id[t] = ib; s_id[x] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < width; t += PB_THREADS) cand[(size_t)q * width + t] = t < n ? s_id[t] : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1171,6 +1247,20 @@ extern "C" int sgb_group_unlabeled_phase_b(const int* unl, int n_unl, const int*
     if (n_unl == 0) return SGB_OK;
     if (!unl || !cand) return SGB_ERR_INVALID;
     { unlabeled_phase_b_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(unl, n_unl, cand, S, roots_cur, uf, S1); SGB_COUNT_LAUNCH(); }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+// phase B candidate ranking (see phase_b_rank_kernel).  cloud_idx [S,P]: sampled point ids of every cluster (sgb_cluster_cloud_indices),
+// unl [n_unl] ascending dense ids of the unlabeled clusters, cand [n_unl,width] (width >= clusters of the largest scene, <= 4096).
+extern "C" int sgb_phase_b_rank(const float* xyz, int stride, const int* cloud_idx, int P, const int* unl, int n_unl,
+                                const int* scene_cl_off, int n_scenes, int S, int* cand, int width, void* stream) {
+    if (n_unl < 0 || S <= 0 || P <= 0 || stride < 3 || width <= 0 || n_scenes < 1) return SGB_ERR_INVALID;
+    if (n_unl == 0) return SGB_OK;
+    if (!xyz || !cloud_idx || !unl || !cand) return SGB_ERR_INVALID;
+    if (width > PB_MAX) return SGB_ERR_UNSUPPORTED;
+    { phase_b_rank_kernel<<<n_unl, PB_THREADS, 0, (cudaStream_t)stream>>>(xyz, stride, cloud_idx, P, unl, n_scenes > 1 ? scene_cl_off : nullptr,
+                                                                          n_scenes, S, cand, width); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

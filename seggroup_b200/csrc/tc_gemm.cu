@@ -8,7 +8,7 @@
 //   thread 0   : 4 k-steps x 3 tcgen05.mma (hi*hi, lo*hi, hi*lo) per chunk, tcgen05.commit -> mbarrier
 //   all threads: wait on the mbarrier before the tiles are overwritten; after the last chunk every warp reads its
 //                32 TMEM lanes with tcgen05.ld and stores the rows of C.
-// Measured with the probe kernel below (tools/tc_probe*.py): kind::tf32 reads MN-major operands ONLY in the
+// Measured with a one-instruction descriptor probe during bring-up (round 1): kind::tf32 reads MN-major operands ONLY in the
 // SWIZZLE_128B_BASE32B layout (every other layout type yields zeros), whose swizzle differs from all K-major layouts, so
 // one shared-memory tile cannot serve both X W^T and X^T X; this library keeps its tf32 operands K-major.
 #include "common.cuh"
@@ -20,7 +20,7 @@ constexpr int TG_THREADS = 128;
 constexpr int TG_KC = 32;                   // K columns per chunk (8 x 16 B)
 
 __global__ void __launch_bounds__(TG_THREADS)
-gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int tmem_cols) {
+gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int tmem_cols, int relu) {
     extern __shared__ __align__(128) unsigned char tg_smem[];
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -95,6 +95,10 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        if (relu) {                                            // fused epilogue of the GCN layer: relu(fc(.)), model.py:151
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = (v[q] > 0.f || v[q] != v[q]) ? v[q] : 0.f;      // NaN propagates, as in torch.relu
+        }
         if (row < M) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -106,49 +110,12 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
 }
 
-// Descriptor probe (test / bring-up tool): shared memory is loaded verbatim from two host-provided images, ONE
-// tcgen05.mma (M = 128, K = 8) is issued with caller-supplied descriptor fields, and the raw accumulator is returned.
-// tests/test_gpu_tc.py uses it to pin how the hardware walks K-major and MN-major no-swizzle operands.
-__global__ void __launch_bounds__(TG_THREADS)
-probe_kernel(const float* __restrict__ imgA, int wordsA, const float* __restrict__ imgB, int wordsB,
-             unsigned long long descA, unsigned long long descB, unsigned idesc, int N, float* __restrict__ D) {
-    extern __shared__ __align__(128) unsigned char tg_smem[];
-    __shared__ uint64_t s_bar;
-    __shared__ uint32_t s_tmem;
-    float* sA = reinterpret_cast<float*>(tg_smem + ((1024u - (smem_u32(tg_smem) & 1023u)) & 1023u));   // swizzles are address based
-    float* sB = sA + wordsA;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    if (warp == 0) tmem_alloc(&s_tmem, 256);
-    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
-    for (int i = tid; i < wordsA; i += TG_THREADS) sA[i] = imgA[i];
-    for (int i = tid; i < wordsB; i += TG_THREADS) sB[i] = imgB[i];
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem = s_tmem;
-    if (tid == 0) {
-        const uint64_t da = descA | (uint64_t)((smem_u32(sA) >> 4) & 0x3fff);
-        const uint64_t db = descB | (uint64_t)((smem_u32(sB) >> 4) & 0x3fff);
-        mma_tf32(tmem, da, db, idesc, false);
-        mma_commit(&s_bar);
-    }
-    mbar_wait(&s_bar, 0);
-    fence_after_sync();
-    const int row = warp * 32 + (tid & 31);
-    for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) D[(size_t)row * N + c0 + q] = v[q];
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
-}
 }  // namespace
 
 extern "C" int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, void* stream) {
+    return sgb_linear_tf32x3(A, B, C, M, N, K, 0, stream);
+}
+extern "C" int sgb_linear_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, int relu, void* stream) {
     if (M < 0 || N <= 0 || K <= 0) return SGB_ERR_INVALID;
     if (M == 0) return SGB_OK;
     if (!A || !B || !C) return SGB_ERR_INVALID;
@@ -157,18 +124,7 @@ extern "C" int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, 
     while (cols < N) cols <<= 1;
     const size_t smem = (size_t)(2 * 128 + 2 * N) * TG_KC * 4;
     SGB_OPT_IN_SMEM(gemm_tf32x3_kernel);
-    gemm_tf32x3_kernel<<<sgb_div_up(M, 128), TG_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, cols); SGB_COUNT_LAUNCH();
-    SGB_CHECK_LAUNCH();
-    return SGB_OK;
-}
-
-extern "C" int sgb_tc_probe(const float* imgA, int wordsA, const float* imgB, int wordsB, unsigned long long descA,
-                            unsigned long long descB, unsigned idesc, int N, float* D, void* stream) {
-    if (!imgA || !imgB || !D || wordsA <= 0 || wordsB <= 0 || N <= 0 || N > 256 || (N & 15) || (wordsA & 255) || (wordsB & 255)) return SGB_ERR_INVALID;
-    const size_t smem = (size_t)(wordsA + wordsB) * 4 + 1024;
-    if (smem > 200 * 1024) return SGB_ERR_UNSUPPORTED;
-    SGB_OPT_IN_SMEM(probe_kernel);
-    probe_kernel<<<1, TG_THREADS, smem, (cudaStream_t)stream>>>(imgA, wordsA, imgB, wordsB, descA, descB, idesc, N, D); SGB_COUNT_LAUNCH();
+    gemm_tf32x3_kernel<<<sgb_div_up(M, 128), TG_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, cols, relu); SGB_COUNT_LAUNCH();
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

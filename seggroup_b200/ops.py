@@ -388,6 +388,16 @@ def group_unlabeled_phase_b(unl, cand, roots_cur, uf):
     _lib.call("sgb_group_unlabeled_phase_b", unl, unl.numel(), cand, cand.shape[1], roots_cur, uf, uf.shape[1], _stream())
 
 
+def phase_b_rank(xyz, cloud_idx, unl, level: Level, width, split=None):
+    """-> cand [n_unl,width] i32: per unlabeled cluster the clusters of its scene by sampled-cloud distance, -1 padded."""
+    _chk(cloud_idx, I32, "cloud_idx"); _chk(unl, I32, "unl")
+    cand = torch.empty(unl.numel(), width, dtype=I32, device=unl.device)
+    B = split.n if split is not None else 1
+    _lib.call("sgb_phase_b_rank", xyz, xyz.stride(0), cloud_idx, cloud_idx.shape[1], unl, unl.numel(),
+              level.d_scene_cl_off if B > 1 else None, B, level.S, cand, width, _stream())
+    return cand
+
+
 def export_labels(unmap, seg_of_point, level: Level, want_seg=True, split=None):
     """unmap [N_raw] i64 (or None) -> (seg, ins, sem) int32 [N_raw].  split (scene batch): segment labels are point ids inside the scene."""
     dev = seg_of_point.device
@@ -427,13 +437,14 @@ def evaluate(real_label, sem_pred, ins_pred, sem_valid, ins_valid, status=None):
 # ------------------------------------------------------------------------------------------------
 # tensor-core primitives (tcgen05, TF32 x 3)
 # ------------------------------------------------------------------------------------------------
-def gemm_tf32x3(A, B):
-    """C [M,N] = A [M,K] @ B [N,K]^T on the tcgen05 tensor cores with the TF32 x 3 split (fp32-level accuracy)."""
+def gemm_tf32x3(A, B, relu=False):
+    """C [M,N] = [relu](A [M,K] @ B [N,K]^T) on the tcgen05 tensor cores with the TF32 x 3 split (fp32-level accuracy).
+    N multiple of 16 and <= 256, K multiple of 4."""
     _chk(A, F32, "A"); _chk(B, F32, "B")
     M, K = A.shape
     N = B.shape[0]
     if B.shape[1] != K:
         raise ValueError("A [M,K] and B [N,K] must share K")
     C = torch.empty(M, N, dtype=F32, device=A.device)
-    _lib.call("sgb_gemm_tf32x3", A, B, C, M, N, K, _stream())
+    _lib.call("sgb_linear_tf32x3", A, B, C, M, N, K, int(bool(relu)), _stream())
     return C

@@ -131,6 +131,32 @@ class GcnAggFn(torch.autograd.Function):
         return dX, dsims, None, None, None, None
 
 
+class LinearReluFn(torch.autograd.Function):
+    """relu(fc(x)) of the GCN layer (model.py:146-151, fc = nn.Linear(bias=False)) on the tcgen05 tensor cores (TF32 x 3, ReLU
+    fused into the TMEM epilogue); backward = two more GEMMs of the same kernel:
+        dX = dZ W          (A = dZ [S,Co],   B = W^T  [Ci,Co])
+        dW = dZ^T X        (A = dZ^T [Co,S], B = X^T  [Ci,S], S zero-padded to a multiple of 4)."""
+    @staticmethod
+    def forward(ctx, x, W):
+        x = x.contiguous()
+        y = ops.gemm_tf32x3(x, W.contiguous(), relu=True)
+        ctx.save_for_backward(x, W, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        dz = gy * (y > 0).to(gy.dtype)
+        dx = ops.gemm_tf32x3(dz, W.t().contiguous())
+        S = x.shape[0]
+        pad = (-S) % 4
+        dzt, xt = dz.t(), x.t()
+        if pad:
+            dzt, xt = F.pad(dzt, (0, pad)), F.pad(xt, (0, pad))
+        dW = ops.gemm_tf32x3(dzt.contiguous(), xt.contiguous())
+        return dx, dW
+
+
 def _acc(total, part):
     return part if total is None else total + part
 
@@ -257,7 +283,7 @@ def _gcn(p, key, Fc, adj, csr, keep=None, tag=""):
     d = keep("d_" + tag, EdgeDistFn.apply(Fc, adj, *csr))
     sims = keep("sims_" + tag, torch.exp(-d * (1 / 8)))
     AX = keep("AX_" + tag, GcnAggFn.apply(Fc, sims, adj, *csr))
-    return F.relu(keep("Z_" + tag, F.linear(AX, p[key])))
+    return LinearReluFn.apply(AX, p[key])
 
 
 def _pairs(off):
@@ -458,26 +484,21 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
 
 def _phase_b(sc, uf, sos, status, Lo, Feat, split, sweep_cap=64):
     """model.py:472-509 — nearest labelled cluster by sampled-cloud distance for clusters phase A left unlabeled.
-    Clouds: FPS kernel; distances / sort: torch device ops, one unlabeled cluster chunk at a time ([chunk, S_scene, 1024]);
-    the order-dependent unions: one kernel launch per scene that still has an unlabeled cluster."""
+    Clouds: FPS kernel; candidate ranking: sgb_phase_b_rank (one CTA per unlabeled cluster, its own scene's clusters only);
+    the order-dependent unions: one sequential kernel."""
     P = 1024
     cloud_idx, _ = ops.cluster_cloud_indices(sc.data, Lo.order, Lo.cl_pt_off, P, status=status)
-    xyz = sc.data[:, :3]
-    unl_all = torch.nonzero(Lo.cl_ins == -1).view(-1)                       # ascending dense ids
-    for c0, c1 in _pairs(Lo.scene_cl_off):
-        unl = unl_all[(unl_all >= c0) & (unl_all < c1)]
-        if unl.numel() == 0 or c1 - c0 < 2:
-            continue
-        pts = xyz[cloud_idx[c0:c1].long().view(-1)].view(c1 - c0, P, 3)     # this scene's clouds
-        mean = pts[(unl - c0)].mean(1)                                      # [n_unl,3]
-        cand = []
-        chunk = max(1, (64 << 20) // ((c1 - c0) * P * 16))                  # <= ~64 MB of temporaries per chunk
-        for q in range(0, unl.numel(), chunk):
-            m = mean[q:q + chunk].view(-1, 1, 1, 3)
-            dmin = ((m - pts.unsqueeze(0)) ** 2).sum(3).min(-1)[0]          # [chunk, S_scene]
-            cand.append(torch.sort(dmin, dim=1)[1])
-        cand = (torch.cat(cand) + c0).to(I32).contiguous()                  # candidate cluster ids (batch-wide dense ids)
-        ops.group_unlabeled_phase_b(unl.to(I32).contiguous(), cand, Lo.roots, uf)
+    unl = torch.nonzero(Lo.cl_ins == -1).view(-1).to(I32)                  # ascending dense ids
+    width = max(b - a for a, b in _pairs(Lo.scene_cl_off))
+    if width > 4096:
+        raise _lib_error("phase B with more than 4096 clusters in a scene is not supported")
+    cand = ops.phase_b_rank(sc.data, cloud_idx, unl, Lo, width, split)
+    ops.group_unlabeled_phase_b(unl, cand, Lo.roots, uf)
     Ln = ops.level_step(2, uf, sc.seg_off, sc.seg_members, sos, status, old=Lo, sweep_cap=sweep_cap, split=split)
     Feat, _ = SegmentMaxFn.apply(Feat, Ln.ch_off, Ln.ch_list)
     return Ln, Feat
+
+
+def _lib_error(msg):
+    from ._lib import SgbError
+    return SgbError(msg)

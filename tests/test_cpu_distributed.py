@@ -41,3 +41,18 @@ def test_shard_scenes_partition():
     for world in (1, 2, 4, 8):
         seen = sorted(i for r in range(world) for i in engine.shard_scenes(1201, r, world))
         assert seen == list(range(1201))
+
+
+def test_shard_scenes_padded_mode_gives_equal_counts():
+    """pad=True repeats scenes from the head of the list like the reference's DistributedSampler (train.py:102), so a loop with a
+    per-step collective takes the same number of steps on every rank."""
+    from seggroup_b200 import engine
+    for world in (2, 4, 8):
+        shards = [engine.shard_scenes(1201, r, world, pad=True) for r in range(world)]
+        per = -(-1201 // world)
+        assert all(len(s) == per for s in shards)
+        seen = [i for s in shards for i in s]
+        assert set(seen) == set(range(1201)) and len(seen) == per * world
+    extra = torch.tensor([1, 2], dtype=torch.int64)
+    out = engine.allreduce_flat([torch.zeros(3)], average=True, extra=extra)      # world size 1: a fresh fp32 tensor
+    assert out.dtype == torch.float32 and out.data_ptr() != extra.data_ptr()

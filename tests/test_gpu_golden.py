@@ -98,7 +98,7 @@ def test_cuda_matches_reference_golden_50k(stem, mode):
         (res.loss_raw[:, 0].sum() / res.loss_raw[:, 1].sum()).backward()
         from oracle import seggroup_oracle as O
         live = res.aux["_live"]
-        relu_sets = {t: (live["Z_" + t].detach() > 0).cpu() for t in ("2", "3")}
+        relu_sets = {t: (live["gcn_" + t].detach() > 0).cpu() for t in ("2", "3")}      # relu(Z) > 0 <=> Z > 0 (the ReLU is fused into the GEMM epilogue)
         params_cpu = O.init_params(1, 4.0)
         ref = O.forward(scene, params_cpu, mode="train", tie="canonical", dropout_mask=mask.cpu(), want_grads=True, relu_masks=relu_sets)
         # (1a) index lists: bit-identical

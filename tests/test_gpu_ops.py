@@ -210,6 +210,37 @@ def test_cluster_cloud_indices(scene20k, P):
         assert np.array_equal(idx[c], m[li]), c
 
 
+def test_cluster_cloud_indices_mostly_coincident_members():
+    """model.py:407-412 on clusters whose members are mostly coincident: the farthest-point picks run out of distinct points,
+    the trailing picks equal member 0 and are overwritten by the leading ones — `choice[-invalid:] = choice[:invalid]` with
+    OVERLAPPING slices when invalid > rem / 2 (numpy copies through a temporary).  Picks must equal the oracle's."""
+    from oracle import seggroup_oracle as O
+    from seggroup_b200 import ops
+    rng = np.random.default_rng(4)
+    clouds, order, off = [], [], [0]
+    for n, distinct in ((40, 3), (50, 2), (37, 5), (63, 4), (33, 2)):          # P = 64 -> rem = 24, 14, 27, 1, 31
+        base = rng.random((distinct, 3)).astype(np.float32)
+        pts = base[rng.integers(0, distinct, n)]
+        pts[0] = base[0]
+        clouds.append(pts)
+        order += list(range(off[-1], off[-1] + n))
+        off.append(off[-1] + n)
+    xyz = np.concatenate(clouds).astype(np.float32)
+    data = np.concatenate([xyz, np.zeros_like(xyz)], 1)
+    idx, status = ops.cluster_cloud_indices(dev(data), dev(np.array(order, np.int32)), dev(np.array(off, np.int32)), 64)
+    idx = idx.cpu().numpy()
+    hit_overlap = False
+    for c, pts in enumerate(clouds):
+        n = len(pts)
+        li = O.cluster_cloud_indices(n, pts, 64)
+        assert np.array_equal(idx[c] - off[c], li), (c, idx[c] - off[c], li)
+        rem = 64 % n
+        tail = li[64 - rem:] if rem else li[:0]
+        hit_overlap |= rem > 0 and (O.fps_indices(pts, rem) == 0).sum() > rem / 2
+    assert hit_overlap, "no case exercised the overlapping repair"
+    assert int(status.item()) == 0
+
+
 def test_cloud_transform_and_mlp1(scene20k):
     from oracle import seggroup_oracle as O
     from seggroup_b200 import ops

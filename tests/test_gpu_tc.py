@@ -23,6 +23,30 @@ def test_gemm_tf32x3(M, N, K):
     assert _rel(C, ref) < 1e-4
 
 
+@pytest.mark.parametrize("S,C", [(351, 192), (1047, 256), (66, 192), (2, 256)])
+def test_gcn_linear_relu_forward_backward(S, C):
+    """relu(fc(x)) of the GCN layer (model.py:146-151) on tcgen05 with the ReLU fused into the epilogue, and its backward (two
+    more GEMMs), against torch fp64."""
+    from seggroup_b200.pipeline import LinearReluFn
+    g = torch.Generator().manual_seed(S + C)
+    x = torch.randn(S, C, generator=g)
+    W = torch.randn(C, C, generator=g) * (1.0 / C ** 0.5)
+    go = torch.randn(S, C, generator=g)
+    xd, Wd = x.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    y = LinearReluFn.apply(xd, Wd)
+    (y * go.cuda()).sum().backward()
+    x64, W64 = x.double().requires_grad_(True), W.double().requires_grad_(True)
+    z = x64 @ W64.t()
+    # common active set (the derivative of ReLU jumps at 0): the GPU's
+    mask = (y.detach() > 0).cpu()
+    flipped = (z.detach() > 0) != mask
+    assert float(z.detach()[flipped].abs().max() if flipped.any() else 0.0) < 1e-5 * float(z.detach().abs().max())
+    ref = torch.relu(z)
+    (z * mask * go.double()).sum().backward()
+    assert _rel(y.detach(), ref.detach()) < 1e-5
+    assert _rel(xd.grad, x64.grad) < 1e-5 and _rel(Wd.grad, W64.grad) < 1e-5
+
+
 @pytest.mark.parametrize("n_points,neg_gamma", [(8000, False), (8000, True), (333, False), (20011, False)])
 def test_edgeconv_tensor_core_path(n_points, neg_gamma):
     """MLP3 forward with the second layer on tcgen05 (inference path) against the oracle and against the SIMT path."""

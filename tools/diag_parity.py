@@ -130,7 +130,7 @@ def main():
         say("%-28s %.3e  (%.3e)" % (k, rel(gc, gr), np.abs(gc - gr).max() / (np.abs(gr).max() + 1e-30)))
     # the same comparison with the CUDA path's ReLU active set imposed on the oracle's backward (one entry of Z within rounding
     # of zero flips the derivative 0 <-> 1 and that alone moves every gradient upstream of it)
-    masks = {t: (lc["Z_" + t].detach() > 0).cpu() for t in ("2", "3")}
+    masks = {t: (lc["gcn_" + t].detach() > 0).cpu() for t in ("2", "3")}
     for t in ("2", "3"):
         zr = lr["Z_" + t].detach()
         flipped = (zr > 0) != masks[t]
