@@ -338,3 +338,79 @@ def block_forward(name, P, layer_ind, inputs, features, radius, config, pre_acti
     if name == "nearest_upsample":                                             # :940-948
         return closest_pool(features, inputs["upsamples"][layer_ind - 1])
     raise ValueError("Unknown block name in the architecture definition : " + name)
+
+
+# ------------------------------------------------------------------------------------------------
+# KPConv input pipeline  (kpconv/datasets/common.py:377-384, 432-475, 551-652, 1021-1158), numpy restatement
+# ------------------------------------------------------------------------------------------------
+def stack_batch_inds(stacks_len):
+    """common.py:432-475"""
+    lens = np.asarray(stacks_len, np.int64)
+    num_points, max_points = int(lens.sum()), int(lens.max())
+    rows, p = [], 0
+    for n in lens:
+        rows.append(np.concatenate([np.arange(p, p + n), np.full(max_points - n, num_points)]))
+        p += n
+    out = np.stack(rows)
+    if num_points == max_points * len(lens):
+        out = np.concatenate([out, np.full((len(lens), 1), num_points)], 1)
+    return out.astype(np.int32)
+
+
+def segmentation_inputs(config, stacked_points, stacked_features, point_labels, stacks_lengths, batch_inds, neighborhood_limits):
+    """common.py:1021-1143 with the oracle's canonical subsampling / neighbour functions."""
+    pts = np.asarray(stacked_points, np.float32); lens = np.asarray(stacks_lengths, np.int32)
+    weights = (lens.min().astype(np.float32) / lens.astype(np.float32))[np.asarray(batch_inds)]
+    r_normal = config.first_subsampling_dl * config.KP_extent * 2.5
+    P, NB, PL, UP, BL = [], [], [], [], []
+    layer_blocks = []
+    arch = config.architecture
+    for block_i, block in enumerate(arch):
+        if "global" in block or "upsample" in block:
+            break
+        if not ("pool" in block or "strided" in block):
+            layer_blocks += [block]
+            if block_i < len(arch) - 1 and not ("upsample" in arch[block_i + 1]):
+                continue
+        if layer_blocks:
+            deform = any("deformable" in b for b in layer_blocks[:-1])
+            r = r_normal * config.density_parameter / (config.KP_extent * 2.5) if deform else r_normal
+            conv_i = batch_neighbors(pts, pts, lens, lens, r)
+        else:
+            conv_i = np.zeros((0, 1), np.int32)
+        if "pool" in block or "strided" in block:
+            dl = 2 * r_normal / (config.KP_extent * 2.5)
+            pool_p, pool_b = batch_grid_subsampling(pts, lens, dl)
+            r = r_normal * config.density_parameter / (config.KP_extent * 2.5) if "deformable" in block else r_normal
+            pool_i = batch_neighbors(pool_p, pts, pool_b, lens, r)
+            up_i = batch_neighbors(pts, pool_p, lens, pool_b, 2 * r)
+        else:
+            pool_i = np.zeros((0, 1), np.int32); up_i = np.zeros((0, 1), np.int32)
+            pool_p = np.zeros((0, 3), np.float32); pool_b = np.zeros((0,), np.int32)
+        if neighborhood_limits is not None:
+            lim = int(neighborhood_limits[len(P)])
+            conv_i, pool_i, up_i = conv_i[:, :lim], pool_i[:, :lim], up_i[:, :lim]
+        P.append(pts); NB.append(conv_i); PL.append(pool_i); UP.append(up_i); BL.append(lens)
+        pts, lens = pool_p, pool_b
+        r_normal *= 2
+        layer_blocks = []
+    return P + NB + PL + UP + [np.asarray(stacked_features), weights, stack_batch_inds(BL[0]), stack_batch_inds(BL[-1]), np.asarray(point_labels)]
+
+
+def calibrate_neighbors(batches, config, keep_ratio=0.8, samples_threshold=10000):
+    """common.py:595-647"""
+    hist_n = int(np.ceil(4 / 3 * np.pi * (config.density_parameter + 1) ** 3))
+    hists = None
+    for b in batches:
+        li = segmentation_inputs(config, *b, neighborhood_limits=None)
+        L = (len(li) - 5) // 4
+        hs = []
+        for nb in li[L:2 * L]:
+            counts = np.sum(nb < nb.shape[0], axis=1) if nb.shape[0] else np.zeros(0, np.int64)
+            hs.append(np.bincount(counts, minlength=hist_n)[:hist_n])
+        hs = np.vstack(hs)
+        hists = hs if hists is None else hists + hs
+        if np.min(np.sum(hists, axis=1)) >= samples_threshold:
+            break
+    cumsum = np.cumsum(hists.T, axis=0)
+    return np.sum(cumsum < (keep_ratio * cumsum[hist_n - 1, :]), axis=0)

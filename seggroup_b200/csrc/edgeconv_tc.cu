@@ -20,14 +20,22 @@
 // collects lo*hi (rows 0..63), hi*hi (rows 64..127) and the column of ones gives sum h; hi*lo follows by symmetry.
 // G is flushed to global fp32 slots every FLUSH tiles and summed in fp64 in a fixed order (TMEM accumulates in fp32).
 //
-// Warp roles (480 threads, 1 CTA / SM, persistent over a contiguous range of points):
+// Warp roles (416 threads, 1 CTA / SM, persistent over a contiguous range of points):
 //   warps 0-3   epilogue: tcgen05.ld of their TMEM sub-partition (an M = 64 accumulator keeps rows 16q..16q+15 on lanes
 //               32q..32q+15), statistics + max/min over 20 consecutive columns, stores of the per-point candidates;
 //   warp  4     TMEM allocation + the single MMA-issuing thread + tcgen05.commit;
-//   warps 5-14  producers: gather the (48-byte padded) rows one tile ahead into registers, first layer + BN1 (folded
-//               into the weights) + LeakyReLU on the CUDA cores with packed FFMA2, hi/lo split, 16-byte stores into the
-//               canonical no-swizzle K-major tile, fence.proxy.async, mbarrier arrive.
-// Pipelines: shared-memory tiles full/empty (2 stages) and TMEM accumulators full/empty (2 buffers), all mbarriers.
+//   warps 5-12  producers.  (a) gather: thread g < TE copies the (48-byte padded) row x_j of edge g, thread p < TE / 20 the row x_i of
+//               point p, into a shared ring RING - 1 tiles ahead with cp.async (neighbour indices by LDG two tiles before that):
+//               the random row gathers cost ~1 us of latency against ~0.5 us per tile, so one tile of register look-ahead (round
+//               1) left the producers waiting on the scoreboard; (b) first layer: a thread owns ONE
+//               16-byte chunk of the hidden vector (4 channels) for the whole kernel, so its 72 first-layer weights (BN1
+//               folded in) live in REGISTERS — round 1 re-read them from shared memory for every edge, 72 LDS.128 per thread
+//               and tile, which was the largest consumer of a shared-memory-bound kernel (l1tex 93 %, tensor pipe 22 %) — and
+//               walks the tile in blocks of 8 edges (lane & 7 = edge, lane >> 3 = which of the warp's 4 chunks): 5 broadcast
+//               LDS.128 of the two rows (9 subtractions rebuild the edge vector), 36 packed FFMA2, LeakyReLU, hi/lo split, 16-byte stores into the canonical
+//               no-swizzle K-major tile (+ the 4-byte transposed stores of the Gram variant), fence.proxy.async, mbarrier arrive.
+// Pipelines: shared-memory tiles full/empty (2 stages), the gather ring (producer-internal: cp.async groups + one named barrier
+// per tile) and TMEM accumulators full/empty (2 buffers).
 #include "common.cuh"
 #include "bn_moments.cuh"
 #include "edgeconv_common.cuh"
@@ -40,22 +48,22 @@ using sgb_ec::COUT;
 using sgb_ec::KNN;
 using sgb_bn::lrelu;
 
-constexpr int EPI_WARPS = 4, PROD_WARPS = 10;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS;           // warp 4
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 480
-constexpr int PROD_THREADS = PROD_WARPS * 32; // 320
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 416
+constexpr int PROD_THREADS = PROD_WARPS * 32; // 256
+// raw gather ring: per tile the 48-byte rows x_j of its TE edges, the rows x_i of its TE / 20 points and a validity word per edge,
+// filled by cp.async several tiles ahead (no registers held across the latency of the random row gathers)
 constexpr int W2_BYTES = COUT * COUT * 4;     // 16 KB
 constexpr int TMEM_COLS = 512;
 constexpr int FLUSH = 32;                     // tiles per Gram segment
 constexpr int GN = 80;                        // Gram accumulator columns: 64 hidden + ones + 15 zero rows
 constexpr int GR = 144;                       // rows of the transposed tile: 64 lo + 64 hi + 16 extra
-constexpr int W1T_STRIDE = 80;                // floats per q-row of the staged first-layer weights (4 parts x (16 + 4 pad))
 
 template <bool GRAM> struct Cfg {
     static constexpr int TE = GRAM ? 80 : 160;                     // edges per tile (TMEM columns per z accumulator)
     static constexpr int PTS = TE / KNN;                           // points per tile
-    static constexpr int PPE = PROD_THREADS / TE;                  // producer threads per edge (4 : 2)
-    static constexpr int CPT = 16 / PPE;                           // 16-byte chunks (4 hidden channels) per producer thread
+    static constexpr int BLOCKS = TE / 8;                          // 8-edge blocks per tile; a group of 4 producer warps takes every 2nd one
     static constexpr int TILE_BYTES = TE * COUT * 4;               // one K-major H tile (hi or lo)
     static constexpr int HT_BYTES = GRAM ? GR * TE * 4 : 0;        // transposed tile (lo, hi, extra rows)
     static constexpr int STAGE_BYTES = 2 * TILE_BYTES + HT_BYTES;  // multiple of 1024 in both variants
@@ -63,9 +71,10 @@ template <bool GRAM> struct Cfg {
     static constexpr int w2_hi = 0;
     static constexpr int w2_lo = w2_hi + W2_BYTES;
     static constexpr int stage0 = w2_lo + W2_BYTES;
-    static constexpr int w1t = stage0 + 2 * STAGE_BYTES;           // [18][W1T_STRIDE] floats: BN1 scale folded in
-    static constexpr int b1 = w1t + CIN * W1T_STRIDE * 4;          // [64]: beta1 - scale1 * mean1
-    static constexpr int bars = b1 + COUT * 4;                     // 12 mbarriers
+    static constexpr int RING = GRAM ? 4 : 3;                      // tiles in flight in the gather ring
+    static constexpr int RAW_BYTES = TE * 48 + PTS * 48 + TE * 4;  // x_j rows, x_i rows, validity words
+    static constexpr int raw0 = stage0 + 2 * STAGE_BYTES;
+    static constexpr int bars = raw0 + RING * RAW_BYTES;           // 12 mbarriers
     static constexpr int tmem_slot = bars + 12 * 8;
     static constexpr int total = tmem_slot + 16;
     static constexpr int Z_COL = 128 + (GRAM ? 0 : 128);           // TMEM column stride of the two z accumulators
@@ -87,8 +96,8 @@ __device__ __forceinline__ uint32_t ht_off(int r, int e) {
 template <bool ARG, bool GRAM>
 __global__ void __launch_bounds__(THREADS, 1)
 ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ W1,
-              const float* __restrict__ stats1, const float* __restrict__ W2,
-              float* __restrict__ zmax, float* __restrict__ zmin, unsigned short* __restrict__ kk, double* __restrict__ part /*[grid][128]*/,
+              const float* __restrict__ stats1, const float* __restrict__ W2, const float* __restrict__ gamma2,
+              float* __restrict__ zsel, unsigned char* __restrict__ ksel, double* __restrict__ part /*[grid][128]*/,
               float* __restrict__ gslots /*[grid][nflush][128*GN]*/, int nflush) {
     using C = Cfg<GRAM>;
     constexpr int TE = C::TE;
@@ -101,8 +110,6 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
     uint64_t* bar_gfull = bar_full + 8;                                      // [2] MMA (commit) -> epilogue: Gram segment complete
     uint64_t* bar_gempty = bar_full + 10;                                    // [2] epilogue -> MMA: Gram accumulator flushed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::tmem_slot);
-    float* s_w1t = reinterpret_cast<float*>(sm + C::w1t);
-    float* s_b1 = reinterpret_cast<float*>(sm + C::b1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // contiguous, balanced range of points for this CTA
@@ -121,13 +128,6 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
         *reinterpret_cast<float*>(sm + C::w2_hi + off) = hi;
         *reinterpret_cast<float*>(sm + C::w2_lo + off) = tf32_hi(w - hi);
     }
-    // first layer with the BatchNorm-1 affine folded in:  v1 = (scale1 W1) e + (beta1 - scale1 mean1);
-    // staged [q][channel] with a 16-byte pad after every 16 channels so that the producer parts read distinct banks
-    for (int i = tid; i < COUT * CIN; i += THREADS) {
-        const int c = i / CIN, q = i % CIN;
-        s_w1t[q * W1T_STRIDE + (c >> 4) * 20 + (c & 15)] = __ldg(W1 + i) * stats1[128 + c];
-    }
-    for (int i = tid; i < COUT; i += THREADS) s_b1[i] = fmaf(-stats1[128 + i], stats1[i], stats1[192 + i]);
     if (GRAM) {                                                     // extra rows of the transposed tiles: ones, then zeros
         for (int s = 0; s < 2; ++s) {
             unsigned char* ht = sm + C::stage0 + s * C::STAGE_BYTES + 2 * C::TILE_BYTES;
@@ -154,77 +154,107 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
     const uint32_t tmem = *tmem_slot;
 
     if (warp > MMA_WARP) {
-        // ================= producers: thread = (edge row, part of the hidden channels); a warp holds 32/PPE consecutive edges
-        constexpr int PPE = C::PPE, CPT = C::CPT;
-        const int pw = warp - (MMA_WARP + 1);
-        const int er = pw * (32 / PPE) + lane / PPE;    // edge row in the tile
-        const int part_id = lane % PPE;                 // 16-byte chunks part_id*CPT .. part_id*CPT + CPT - 1 of the hidden vector
-        // software pipeline over tiles: neighbour index two tiles ahead, gathered rows one tile ahead
-        float en[CIN];                                  // edge vector of the NEXT tile (in flight during this tile's math)
-        int j_next = 0;
-        bool v_next = false;
-        auto issue_index = [&](int t) -> int {
-            const long long g = g_begin + (long long)t * TE + er;
-            return (t < ntiles && g < g_end) ? __ldg(knn + g) : -1;
-        };
-        auto issue_rows = [&](int t, int j) {
-            const long long g = g_begin + (long long)t * TE + er;
-            v_next = j >= 0;
-            if (v_next) {
-                const float4* xi = reinterpret_cast<const float4*>(x12 + (size_t)(g / KNN) * 12);
-                const float4* xj = reinterpret_cast<const float4*>(x12 + (size_t)j * 12);
-                const float4 a0 = __ldg(xi), a1 = __ldg(xi + 1), a2 = __ldg(xi + 2);
-                const float4 b0 = __ldg(xj), b1 = __ldg(xj + 1), b2 = __ldg(xj + 2);
-                en[0] = b0.x - a0.x; en[1] = b0.y - a0.y; en[2] = b0.z - a0.z; en[3] = b0.w - a0.w;
-                en[4] = b1.x - a1.x; en[5] = b1.y - a1.y; en[6] = b1.z - a1.z; en[7] = b1.w - a1.w;
-                en[8] = b2.x - a2.x;
-                en[9] = a0.x; en[10] = a0.y; en[11] = a0.z; en[12] = a0.w;
-                en[13] = a1.x; en[14] = a1.y; en[15] = a1.z; en[16] = a1.w; en[17] = a2.x;
+        // ================= producers
+        const int pw = warp - (MMA_WARP + 1);           // 0..7
+        const int ptid = pw * 32 + lane;                // 0..255: gather role = edge row `ptid` of the tile (if < TE)
+        const int grp = pw >> 2;                        // which half of the 8-edge blocks this warp computes
+        const int part = lane >> 3;                     // hidden channels 16 part .. 16 part + 15 (the Gram row mapping of ht_row)
+        const int c4 = part * 4 + (pw & 3);             // my 16-byte chunk of the hidden vector: channels 4 c4 .. 4 c4 + 3, for the whole kernel
+        const int eb = lane & 7;                        // my edge inside an 8-edge block
+        // first layer with the BatchNorm-1 affine folded in:  v1 = (scale1 W1) e + (beta1 - scale1 mean1), in registers
+        float2 w01[CIN], w23[CIN];
+        float4 bias;
+        {
+            float sc[4], bb[4];
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int c = 4 * c4 + s4;
+                sc[s4] = stats1[128 + c];
+                bb[s4] = fmaf(-stats1[128 + c], stats1[c], stats1[192 + c]);
             }
+#pragma unroll
+            for (int q = 0; q < CIN; ++q) {
+                w01[q] = make_float2(__ldg(W1 + (4 * c4 + 0) * CIN + q) * sc[0], __ldg(W1 + (4 * c4 + 1) * CIN + q) * sc[1]);
+                w23[q] = make_float2(__ldg(W1 + (4 * c4 + 2) * CIN + q) * sc[2], __ldg(W1 + (4 * c4 + 3) * CIN + q) * sc[3]);
+            }
+            bias = make_float4(bb[0], bb[1], bb[2], bb[3]);
+        }
+        // gather pipeline: neighbour indices by LDG two iterations before they are needed, rows by cp.async RING - 1 tiles ahead
+        constexpr int RING = C::RING;
+        const bool gatherer = ptid < TE;                // fetches x_j of edge row `ptid`
+        const bool pgatherer = ptid < C::PTS;           // fetches x_i of point `ptid` of the tile
+        auto issue_index = [&](int t) -> int {
+            const long long g = g_begin + (long long)t * TE + ptid;
+            return (gatherer && t < ntiles && g < g_end) ? __ldg(knn + g) : -1;
         };
-        issue_rows(0, issue_index(0));
-        j_next = issue_index(1);
+        auto cp16 = [&](void* dst, const float* src, bool valid) {       // 16-byte async copy, zero fill when !valid
+            const uint32_t n = valid ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+        };
+        auto issue_rows = [&](int t, int j) {           // every thread commits one (possibly empty) group per call
+            unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
+            if (gatherer) {
+                const bool v = j >= 0;
+                const float* src = x12 + (size_t)(v ? j : 0) * 12;
+                unsigned char* dst = raw + ptid * 48;
+                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
+                *reinterpret_cast<uint32_t*>(raw + TE * 48 + C::PTS * 48 + ptid * 4) = v ? 1u : 0u;
+            }
+            if (pgatherer) {
+                const long long pt = g_begin / KNN + (long long)t * C::PTS + ptid;
+                const bool v = t < ntiles && pt < (long long)p_end;
+                const float* src = x12 + (size_t)(v ? pt : 0) * 12;
+                unsigned char* dst = raw + TE * 48 + ptid * 48;
+                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll 1
+        for (int tt = 0; tt < RING - 1; ++tt) issue_rows(tt, issue_index(tt));
+        int jA = issue_index(RING - 1), jB = issue_index(RING), jC = issue_index(RING + 1);
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            float2 ee[CIN];
-            const bool valid = v_next;
-#pragma unroll
-            for (int q = 0; q < CIN; ++q) ee[q] = make_float2(en[q], en[q]);
-            issue_rows(t + 1, j_next);                  // loads land while this tile is computed
-            j_next = issue_index(t + 2);
+            asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory");     // my copies for tile t have landed
+            asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");         // everybody's have, and everybody is done with tile t - 1
+            issue_rows(t + RING - 1, jA);               // refill the slot tile t - 1 used
+            jA = jB; jB = jC;
+            jC = issue_index(t + RING + 2);
+            const unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
             mbar_wait(&bar_empty[st], ph ^ 1u);
             unsigned char* dst_hi = sm + C::stage0 + st * C::STAGE_BYTES;
             unsigned char* dst_lo = dst_hi + C::TILE_BYTES;
             unsigned char* dst_t = dst_lo + C::TILE_BYTES;
-#pragma unroll 2
-            for (int i4 = 0; i4 < CPT; ++i4) {
-                const int c4 = part_id * CPT + i4;      // 16-byte chunk = hidden channels 4 c4 .. 4 c4 + 3
-                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    const float4 b = *reinterpret_cast<const float4*>(s_b1 + c4 * 4);
-                    float2 y01 = make_float2(b.x, b.y), y23 = make_float2(b.z, b.w);
-                    const float* wrow = s_w1t + (c4 >> 2) * 20 + (c4 & 3) * 4;
+#pragma unroll 1
+            for (int blk = grp; blk < C::BLOCKS; blk += 2) {
+                const int er = blk * 8 + eb;            // edge row in the tile
+                const float4* rj = reinterpret_cast<const float4*>(raw + er * 48);                       // 48-byte stride: conflict-free
+                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + (er / KNN) * 48);     // the edge's own point (broadcast)
+                const float4 b0 = rj[0], b1 = rj[1], b2 = rj[2];
+                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
+                const float ev[CIN] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w, b1.x - a1.x, b1.y - a1.y, b1.z - a1.z, b1.w - a1.w, b2.x - a2.x,
+                                       a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+                float2 y01 = make_float2(bias.x, bias.y), y23 = make_float2(bias.z, bias.w);
 #pragma unroll
-                    for (int q = 0; q < CIN; ++q) {
-                        const float4 w = *reinterpret_cast<const float4*>(wrow + q * W1T_STRIDE);
-                        ffma2(y01, make_float2(w.x, w.y), ee[q]);
-                        ffma2(y23, make_float2(w.z, w.w), ee[q]);
-                    }
-                    y = make_float4(lrelu(y01.x), lrelu(y01.y), lrelu(y23.x), lrelu(y23.y));
+                for (int q = 0; q < CIN; ++q) {
+                    const float2 ee = make_float2(ev[q], ev[q]);
+                    ffma2(y01, w01[q], ee);
+                    ffma2(y23, w23[q], ee);
                 }
+                const bool valid = *reinterpret_cast<const uint32_t*>(raw + TE * 48 + C::PTS * 48 + er * 4) != 0u;
+                const float4 y = valid ? make_float4(lrelu(y01.x), lrelu(y01.y), lrelu(y23.x), lrelu(y23.y)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
                 const float4 lo = make_float4(tf32_hi(y.x - hi.x), tf32_hi(y.y - hi.y), tf32_hi(y.z - hi.z), tf32_hi(y.w - hi.w));
                 const uint32_t off = (uint32_t)c4 * (TE * 16) + (uint32_t)(er >> 3) * 128 + (uint32_t)(er & 7) * 16;
                 *reinterpret_cast<float4*>(dst_hi + off) = hi;
                 *reinterpret_cast<float4*>(dst_lo + off) = lo;
-                if (GRAM) {                             // transposed copy: rows 0..63 lo, 64..127 hi (GRAM: part_id = c4 / 4)
+                if (GRAM) {                             // transposed copy: rows 0..63 lo, 64..127 hi
                     const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int r = ht_row(part_id, i4 * 4 + s);
-                        *reinterpret_cast<float*>(dst_t + ht_off(r, er)) = lv[s];
-                        *reinterpret_cast<float*>(dst_t + ht_off(64 + r, er)) = hv[s];
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        const int r = ht_row(part, (pw & 3) * 4 + s4);
+                        *reinterpret_cast<float*>(dst_t + ht_off(r, er)) = lv[s4];
+                        *reinterpret_cast<float*>(dst_t + ht_off(64 + r, er)) = hv[s4];
                     }
                 }
             }
@@ -278,6 +308,7 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
         // ================= epilogue: warp q owns channels 16q + lane (lanes 0..15); one point = 20 consecutive columns
         const int c = warp * 16 + (lane & 15);
         const bool owner = lane < 16;
+        const bool up = __ldg(gamma2 + c) > 0.f;
         double S1 = 0.0, S2 = 0.0;
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
@@ -289,31 +320,34 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
             const long long p0 = g0 / KNN;
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * C::Z_COL);
             float s1 = 0.f, s2 = 0.f;
+            // BN2 + LeakyReLU is monotone per channel, increasing iff gamma2 > 0: only that extreme of the 20 pre-activations (and its
+            // neighbour slot) is kept — one candidate array instead of max AND min (round 1), half the compare/select work.
+            // Warp-uniform fast paths for the usual cases (all scales positive / all negative).
+            auto scan = [&](auto better) {
 #pragma unroll 1
-            for (int pp = 0; pp < npts; ++pp) {
-                float v[16], u[4];
-                tmem_ld16(taddr + (uint32_t)(pp * KNN), v);
-                tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
-                float mx = v[0], mn = v[0];
-                int kx = 0, kn = 0;
-                s1 += v[0]; s2 = fmaf(v[0], v[0], s2);
+                for (int pp = 0; pp < npts; ++pp) {
+                    float v[16], u[4];
+                    tmem_ld16(taddr + (uint32_t)(pp * KNN), v);
+                    tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
+                    float best = v[0];
+                    int kb = 0;
+                    s1 += v[0]; s2 = fmaf(v[0], v[0], s2);
 #pragma unroll
-                for (int i = 1; i < KNN; ++i) {
-                    const float z = i < 16 ? v[i] : u[i - 16];
-                    s1 += z; s2 = fmaf(z, z, s2);
-                    if (ARG) {
-                        if (z > mx) { mx = z; kx = i; }
-                        if (z < mn) { mn = z; kn = i; }
-                    } else {
-                        mx = fmaxf(mx, z); mn = fminf(mn, z);
+                    for (int i = 1; i < KNN; ++i) {
+                        const float z = i < 16 ? v[i] : u[i - 16];
+                        s1 += z; s2 = fmaf(z, z, s2);
+                        if (better(z, best)) { best = z; if (ARG) kb = i; }
+                    }
+                    if (owner) {
+                        const size_t o = (size_t)(p0 + pp) * COUT + c;
+                        zsel[o] = best;
+                        if (ARG) ksel[o] = (unsigned char)kb;
                     }
                 }
-                if (owner) {
-                    const size_t o = (size_t)(p0 + pp) * COUT + c;
-                    zmax[o] = mx; zmin[o] = mn;
-                    if (ARG) kk[o] = (unsigned short)(kx | (kn << 8));
-                }
-            }
+            };
+            if (__all_sync(SGB_FULL_MASK, up)) scan([](float z, float b) { return z > b; });
+            else if (__all_sync(SGB_FULL_MASK, !up)) scan([](float z, float b) { return z < b; });
+            else scan([up](float z, float b) { return up ? z > b : z < b; });
             S1 += (double)s1; S2 += (double)s2;
             fence_before_sync();
             __syncwarp();
@@ -381,27 +415,24 @@ mom2_from_gram_kernel(const double* __restrict__ R, double* __restrict__ mom2) {
     mom2[COUT * COUT + j] = R[(64 + rj) * GN + 64] + R[rj * GN + 64];
 }
 
-// out[p, c] = lrelu(BN2(z*)), z* = max or min candidate by the sign of the BN scale; argk = its neighbour slot
+// out[p, c] = lrelu(BN2(z*)), z* = the extreme the forward kernel kept for the sign of the BN scale; argk = its neighbour slot
 __global__ void __launch_bounds__(256)
-ec2_apply_kernel(const float* __restrict__ zmax, const float* __restrict__ zmin, const unsigned short* __restrict__ kk,
+ec2_apply_kernel(const float* __restrict__ zsel, const unsigned char* __restrict__ ksel,
                  const float* __restrict__ stats2, long long total, float* __restrict__ out, unsigned char* __restrict__ argk) {
     const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i4 >= total) return;
     const int c = (int)(i4 & 63);
-    const float4 a = *reinterpret_cast<const float4*>(zmax + i4);
-    const float4 b = *reinterpret_cast<const float4*>(zmin + i4);
-    const ushort4 kq = argk ? *reinterpret_cast<const ushort4*>(kk + i4) : make_ushort4(0, 0, 0, 0);
-    const float za[4] = {a.x, a.y, a.z, a.w}, zb[4] = {b.x, b.y, b.z, b.w};
-    const unsigned short kv[4] = {kq.x, kq.y, kq.z, kq.w};
+    const float4 a = *reinterpret_cast<const float4*>(zsel + i4);
+    const uchar4 kq = argk ? *reinterpret_cast<const uchar4*>(ksel + i4) : make_uchar4(0, 0, 0, 0);
+    const float za[4] = {a.x, a.y, a.z, a.w};
+    const unsigned char kv[4] = {kq.x, kq.y, kq.z, kq.w};
     float o[4];
     unsigned char ak[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float mean = stats2[c + q], scale = stats2[128 + c + q], beta = stats2[192 + c + q];
-        const bool up = scale > 0.f;
-        const float z = up ? za[q] : zb[q];
-        o[q] = lrelu(fmaf(z - mean, scale, beta));
-        ak[q] = scale == 0.f ? (unsigned char)0 : (unsigned char)(up ? (kv[q] & 0xff) : (kv[q] >> 8));
+        o[q] = lrelu(fmaf(za[q] - mean, scale, beta));
+        ak[q] = scale == 0.f ? (unsigned char)0 : kv[q];
     }
     *reinterpret_cast<float4*>(out + i4) = make_float4(o[0], o[1], o[2], o[3]);
     if (argk) *reinterpret_cast<uchar4*>(argk + i4) = make_uchar4(ak[0], ak[1], ak[2], ak[3]);
@@ -418,12 +449,12 @@ inline int tc_nflush(int N, int grid) {                 // Gram segments per CTA
 }
 }  // namespace sgb_ectc
 
-// workspace: partial sums [148][128] f64, reduced sums [128] f64, reduced Gram [128*GN] f64, zmax, zmin [N,64] f32,
-// kk [N,64] u16, Gram slots [148][nflush][128*GN] f32
+// workspace: partial sums [148][128] f64, reduced sums [128] f64, reduced Gram [128*GN] f64, zsel [N,64] f32, ksel [N,64] u8,
+// Gram slots [148][nflush][128*GN] f32
 size_t sgb_ec2_tc_ws_bytes(int N) {
     using namespace sgb_ectc;
     const int nf = tc_nflush(N, 148) + 1;
-    return (size_t)(148 + 1) * 128 * 8 + (size_t)128 * GN * 8 + (size_t)N * 64 * (4 + 4 + 2) +
+    return (size_t)(148 + 1) * 128 * 8 + (size_t)128 * GN * 8 + (size_t)N * 64 * (4 + 1) +
            (size_t)148 * nf * 128 * GN * 4 + 1024;
 }
 
@@ -437,10 +468,9 @@ int sgb_ec2_tc_forward(const float* x12 /*[N,12]: 48-byte padded rows*/, const i
     double* part = (double*)w8;
     double* sums = part + 148 * 128;
     double* gred = sums + 128;
-    float* zmax = (float*)(gred + 128 * GN);
-    float* zmin = zmax + (size_t)N * 64;
-    unsigned short* kk = (unsigned short*)(zmin + (size_t)N * 64);
-    float* gslots = (float*)(((uintptr_t)(kk + (size_t)N * 64) + 255) & ~(uintptr_t)255);
+    float* zsel = (float*)(gred + 128 * GN);
+    unsigned char* ksel = (unsigned char*)(zsel + (size_t)N * 64);
+    float* gslots = (float*)(((uintptr_t)(ksel + (size_t)N * 64) + 255) & ~(uintptr_t)255);
     const bool gram = mom2 != nullptr;
     const int grid = tc_grid(N, gram ? Cfg<true>::TE : Cfg<false>::TE);
     const int nflush = gram ? tc_nflush(N, grid) : 0;
@@ -448,22 +478,22 @@ int sgb_ec2_tc_forward(const float* x12 /*[N,12]: 48-byte padded rows*/, const i
         const size_t smem = Cfg<true>::total + 1024;
         SGB_CUDA(cudaMemsetAsync(gslots, 0, (size_t)grid * nflush * 128 * GN * 4, st));
         SGB_OPT_IN_SMEM(ec2_tc_kernel<true, true>);
-        { ec2_tc_kernel<true, true><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, zmax, zmin, kk, part, gslots, nflush); SGB_COUNT_LAUNCH(); }
+        { ec2_tc_kernel<true, true><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, gslots, nflush); SGB_COUNT_LAUNCH(); }
         sgb_bn::reduce_partials(gslots, grid * nflush, 128 * GN, gred, st);
         { mom2_from_gram_kernel<<<1, 64, 0, st>>>(gred, mom2); SGB_COUNT_LAUNCH(); }
     } else if (argk) {
         const size_t smem = Cfg<false>::total + 1024;
         SGB_OPT_IN_SMEM(ec2_tc_kernel<true, false>);
-        { ec2_tc_kernel<true, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, zmax, zmin, kk, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
+        { ec2_tc_kernel<true, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
     } else {
         const size_t smem = Cfg<false>::total + 1024;
         SGB_OPT_IN_SMEM(ec2_tc_kernel<false, false>);
-        { ec2_tc_kernel<false, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, zmax, zmin, kk, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
+        { ec2_tc_kernel<false, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
     }
     sgb_bn::reduce_partials(part, grid, 128, sums, st);
     { bn2_from_sums_kernel<<<1, 64, 0, st>>>(sums, (double)N * KNN, gamma2, beta2, stats2, var2); SGB_COUNT_LAUNCH(); }
     const long long total = (long long)N * 64;
-    { ec2_apply_kernel<<<sgb_div_up(total / 4, 256), 256, 0, st>>>(zmax, zmin, kk, stats2, total, out, argk); SGB_COUNT_LAUNCH(); }
+    { ec2_apply_kernel<<<sgb_div_up(total / 4, 256), 256, 0, st>>>(zsel, ksel, stats2, total, out, argk); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

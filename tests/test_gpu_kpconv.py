@@ -311,3 +311,40 @@ def test_kpfcnn_rigid_blocks_forward_backward():
             assert gref is not None, (n, k)
             assert float((v.grad.cpu().double() - gref).abs().max()) < 2e-4 * float(gref.abs().max()) + 1e-9, (n, k)
             v.grad = None
+
+
+def test_kpconv_input_pipeline_matches_restatement():
+    """tf_segmentation_inputs / big_neighborhood_filter / tf_stack_batch_inds / calibrate_neighbors
+    (kpconv/datasets/common.py:377-384, 432-475, 551-652, 1021-1158) on the CUDA operators against the numpy restatement built
+    on the oracle's pinned subsampling / neighbour functions: every index tensor of the flat input list bit-identical."""
+    from types import SimpleNamespace
+    from oracle import kpconv_oracle as K
+    from seggroup_b200 import kpconv_inputs as KI
+    cfg = SimpleNamespace(architecture=["simple", "resnetb", "resnetb_strided", "resnetb", "resnetb_deformable_strided", "resnetb_deformable",
+                                        "nearest_upsample", "unary", "nearest_upsample", "unary"],
+                          first_subsampling_dl=0.04, KP_extent=1.0, density_parameter=5.0, num_layers=3)
+    batches = []
+    for seed in (3, 4):
+        pts, lens = cloud(seed, 4000, batches=3)
+        sub, sl = K.batch_grid_subsampling(pts, lens, cfg.first_subsampling_dl)
+        feats = np.ones((len(sub), 1), np.float32)
+        labels = np.arange(len(sub), dtype=np.int32) % 20
+        binds = np.repeat(np.arange(len(sl)), sl).astype(np.int32)
+        batches.append((sub, feats, labels, sl, binds))
+    to_dev = lambda b: (cu(b[0]), cu(b[1]), cu(b[2]), cu(b[3], torch.int32), cu(b[4], torch.int32))
+    lim_ref = K.calibrate_neighbors(batches, cfg, keep_ratio=0.8, samples_threshold=10 ** 9)
+    lim = KI.calibrate_neighbors([to_dev(b) for b in batches], cfg, keep_ratio=0.8, samples_threshold=10 ** 9)
+    assert np.array_equal(lim, lim_ref) and len(lim) == 3 and (lim > 0).all()
+    ref = K.segmentation_inputs(cfg, *batches[0], neighborhood_limits=lim_ref)
+    got = KI.segmentation_inputs(cfg, *to_dev(batches[0]), neighborhood_limits=lim)
+    assert len(got) == len(ref) == 4 * 3 + 5
+    for i, (a, b) in enumerate(zip(got, ref)):
+        a = a.cpu().numpy()
+        assert a.shape == b.shape, (i, a.shape, b.shape)
+        if a.dtype.kind == "f":
+            assert np.array_equal(a, b.astype(a.dtype)), i                   # subsampled points / weights: bit-identical fp32
+        else:
+            assert np.array_equal(a, b), i
+    assert torch.equal(KI.get_batch_inds(cu(batches[0][3], torch.int32)).cpu(), torch.as_tensor(batches[0][4]))
+    eq = KI.stack_batch_inds(torch.tensor([4, 4, 4], dtype=torch.int32, device="cuda")).cpu().numpy()
+    assert np.array_equal(eq, K.stack_batch_inds([4, 4, 4])) and eq.shape == (3, 5)
