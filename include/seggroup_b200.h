@@ -49,6 +49,9 @@ int sgb_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int 
 /* a12  the GCN layer's dense part relu(fc(.)) (seggroup/model.py:146-151; fc = nn.Linear(bias=False)): C = [relu](A B^T) with the
  * ReLU fused into the TMEM epilogue. */
 int sgb_linear_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, int relu, void* stream);
+/* split-K form for the weight gradient dW = dZ^T X (K = number of clusters, thousands; M, N <= 256): Cpart [ceil(K / k_per_split), M, N],
+ * one slab per K range of k_per_split (multiple of 32) columns; the caller sums the slabs in order. */
+int sgb_gemm_tf32x3_splitk(const float* A, const float* B, float* Cpart, int M, int N, int K, int k_per_split, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a10  segment pooling: point features -> segment features
@@ -289,6 +292,25 @@ int sgb_group_unlabeled_phase_b(const int* unl, int n_unl, const int* cand, int 
  * ties -> lower id, rows padded with -1 (sgb_group_unlabeled_phase_b stops at the first -1). */
 int sgb_phase_b_rank(const float* xyz, int stride, const int* cloud_idx, int P, const int* unl, int n_unl,
                      const int* scene_cl_off, int n_scenes, int S, int* cand, int width, void* stream);
+
+/* a15  the classifier head and its loss, fused, one CTA per scene (forward and backward).
+ * replaces seggroup/model.py:154-166 `Classifier.forward` (Linear 256->128 without bias, BatchNorm1d with BATCH statistics — the
+ * reference never calls .eval() —, LeakyReLU 0.2, Dropout, Linear 128->40) on the per-instance features of model.py:902-921 and
+ * seggroup/util.py:12-29 `cross_entropy_loss` (label smoothing 0.2, summed over the instances of the scene).
+ * feat [G,256] instance features of all scenes, g_off [n_scenes+1] (device) instance range of every scene (>= 2 instances each:
+ * torch's BatchNorm1d raises for one), gold [G] int32 target class, mask [G,128] 0/1 floats or NULL, drop_scale = 1/(1-p).
+ * fwd out: hpre [G,128] (Linear1 output), stats [n_scenes,256] (batch mean, biased variance per scene), logits [G,40],
+ * loss_raw [n_scenes,2] = (loss sum, instance count) as model.py:932 returns it.
+ * bwd: grad_loss_sum [n_scenes]; scratch [G,128]; dfeat [G,256]; per-scene partial gradients dW1_part [n_scenes,128,256],
+ * dgamma_part / dbeta_part [n_scenes,128], dW2_part [n_scenes,40,128], db2_part [n_scenes,40] (sum them in scene order). */
+int sgb_classifier_head_fwd(const float* feat, int G, const int* g_off, int n_scenes, const int* gold,
+                            const float* W1, const float* gamma, const float* beta, const float* W2, const float* b2,
+                            const float* mask, float drop_scale, float* hpre, float* stats, float* logits, float* loss_raw, void* stream);
+int sgb_classifier_head_bwd(const float* feat, int G, const int* g_off, int n_scenes, const int* gold,
+                            const float* W1, const float* gamma, const float* beta, const float* W2,
+                            const float* mask, float drop_scale, const float* hpre, const float* stats, const float* logits,
+                            const float* grad_loss_sum, float* scratch, float* dfeat, float* dW1_part, float* dgamma_part,
+                            float* dbeta_part, float* dW2_part, float* db2_part, void* stream);
 
 /* a16  replaces seggroup/model.py:525-605 `export_{segment,instance,semantic}_label` up to the text
  * formatting: per raw vertex r (p = unmap[r], int64 as stored in unmap.pth; NULL = identity):

@@ -72,7 +72,7 @@ template <bool GRAM> struct Cfg {
     static constexpr int w2_lo = w2_hi + W2_BYTES;
     static constexpr int stage0 = w2_lo + W2_BYTES;
     static constexpr int RING = GRAM ? 4 : 3;                      // tiles in flight in the gather ring
-    static constexpr int RAW_BYTES = TE * 48 + PTS * 48 + TE * 4;  // x_j rows, x_i rows, validity words
+    static constexpr int RAW_BYTES = TE * 48 + PTS * 48 + TE * 8;  // x_j rows, x_i rows, validity words, neighbour indices of a LATER tile
     static constexpr int raw0 = stage0 + 2 * STAGE_BYTES;
     static constexpr int bars = raw0 + RING * RAW_BYTES;           // 12 mbarriers
     static constexpr int tmem_slot = bars + 12 * 8;
@@ -183,15 +183,24 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
         constexpr int RING = C::RING;
         const bool gatherer = ptid < TE;                // fetches x_j of edge row `ptid`
         const bool pgatherer = ptid < C::PTS;           // fetches x_i of point `ptid` of the tile
-        auto issue_index = [&](int t) -> int {
+        // Neighbour indices travel through shared memory as well (4-byte cp.async, RING - 1 tiles before the rows that need them):
+        // held in rotating registers, the first register move after the LDG waits for it, i.e. one tile of look-ahead at best.
+        auto edge_in_range = [&](int t) -> bool {
             const long long g = g_begin + (long long)t * TE + ptid;
-            return (gatherer && t < ntiles && g < g_end) ? __ldg(knn + g) : -1;
+            return gatherer && t < ntiles && g < g_end;
         };
         auto cp16 = [&](void* dst, const float* src, bool valid) {       // 16-byte async copy, zero fill when !valid
             const uint32_t n = valid ? 16u : 0u;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
         };
-        auto issue_rows = [&](int t, int j) {           // every thread commits one (possibly empty) group per call
+        auto issue_index_copy = [&](int t) {            // index of my edge of tile t -> index slot t % RING
+            if (edge_in_range(t)) {
+                unsigned char* slot = sm + C::raw0 + (t % RING) * C::RAW_BYTES + TE * 48 + C::PTS * 48 + TE * 4 + ptid * 4;
+                const int* src = knn + (g_begin + (long long)t * TE + ptid);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(slot)), "l"(src) : "memory");
+            }
+        };
+        auto issue_rows = [&](int t, int j) {           // j < 0: edge out of range.  Every thread commits one (possibly empty) group per call
             unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
             if (gatherer) {
                 const bool v = j >= 0;
@@ -207,19 +216,21 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                 unsigned char* dst = raw + TE * 48 + ptid * 48;
                 cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
             }
+            issue_index_copy(t + RING - 1);             // lands before rows(t + RING - 1) are issued (same group as rows(t))
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        auto staged_index = [&](int t) -> int {         // read back my own copy (complete: its group has been waited for)
+            if (!edge_in_range(t)) return -1;
+            return *reinterpret_cast<const volatile int*>(sm + C::raw0 + (t % RING) * C::RAW_BYTES + TE * 48 + C::PTS * 48 + TE * 4 + ptid * 4);
+        };
 #pragma unroll 1
-        for (int tt = 0; tt < RING - 1; ++tt) issue_rows(tt, issue_index(tt));
-        int jA = issue_index(RING - 1), jB = issue_index(RING), jC = issue_index(RING + 1);
+        for (int tt = 0; tt < RING - 1; ++tt) issue_rows(tt, edge_in_range(tt) ? __ldg(knn + (g_begin + (long long)tt * TE + ptid)) : -1);
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory");     // my copies for tile t have landed
+            asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory");     // my copies for tile t (and the indices of tile t + RING - 1) have landed
             asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");         // everybody's have, and everybody is done with tile t - 1
-            issue_rows(t + RING - 1, jA);               // refill the slot tile t - 1 used
-            jA = jB; jB = jC;
-            jC = issue_index(t + RING + 2);
+            issue_rows(t + RING - 1, staged_index(t + RING - 1));                    // refill the slot tile t - 1 used
             const unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
             mbar_wait(&bar_empty[st], ph ^ 1u);
             unsigned char* dst_hi = sm + C::stage0 + st * C::STAGE_BYTES;

@@ -20,7 +20,8 @@ constexpr int TG_THREADS = 128;
 constexpr int TG_KC = 32;                   // K columns per chunk (8 x 16 B)
 
 __global__ void __launch_bounds__(TG_THREADS)
-gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int tmem_cols, int relu) {
+gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int tmem_cols, int relu,
+                   int k_per_split) {
     extern __shared__ __align__(128) unsigned char tg_smem[];
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -30,6 +31,9 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     unsigned char* sB_lo = sB_hi + (size_t)N * TG_KC * 4;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.x * 128;
+    // split-K (gridDim.y > 1): this CTA contracts columns [k_begin, k_end) and writes its own [M,N] slab; the caller sums the slabs
+    const int k_begin = blockIdx.y * k_per_split, k_end = min(K, k_begin + k_per_split);
+    C += (size_t)blockIdx.y * M * N;
 
     if (warp == 0) tmem_alloc(&s_tmem, (uint32_t)tmem_cols);
     if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
@@ -40,7 +44,7 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     const uint32_t idesc = make_idesc_tf32(128, N, false, false);
 
     uint32_t phase = 0;
-    for (int k0 = 0; k0 < K; k0 += TG_KC) {
+    for (int k0 = k_begin; k0 < k_end; k0 += TG_KC) {
         // ---- stage the chunk (zero-filled past M, N, K)
         {
             const int r = tid, gm = m0 + r;
@@ -48,7 +52,7 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
             for (int c4 = 0; c4 < TG_KC / 4; ++c4) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int k = k0 + c4 * 4;
-                if (gm < M && k < K) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * K + k));
+                if (gm < M && k < k_end) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * K + k));
                 const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 const float4 l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
                 const uint32_t off = tile_off(r, c4 * 4, 128);
@@ -61,7 +65,7 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
             for (int c4 = 0; c4 < TG_KC / 4; ++c4) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int k = k0 + c4 * 4;
-                if (k < K) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)r * K + k));
+                if (k < k_end) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)r * K + k));
                 const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 const float4 l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
                 const uint32_t off = tile_off(r, c4 * 4, N);
@@ -80,7 +84,7 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
                 const uint64_t dal = make_desc(smem_u32(sA_lo) + a_off, 128 * 16, 128);
                 const uint64_t dbh = make_desc(smem_u32(sB_hi) + b_off, (uint32_t)N * 16, 128);
                 const uint64_t dbl = make_desc(smem_u32(sB_lo) + b_off, (uint32_t)N * 16, 128);
-                mma_tf32(tmem, dah, dbh, idesc, k0 > 0 || i > 0);
+                mma_tf32(tmem, dah, dbh, idesc, k0 > k_begin || i > 0);
                 mma_tf32(tmem, dal, dbh, idesc, true);
                 mma_tf32(tmem, dah, dbl, idesc, true);
             }
@@ -124,7 +128,23 @@ extern "C" int sgb_linear_tf32x3(const float* A, const float* B, float* C, int M
     while (cols < N) cols <<= 1;
     const size_t smem = (size_t)(2 * 128 + 2 * N) * TG_KC * 4;
     SGB_OPT_IN_SMEM(gemm_tf32x3_kernel);
-    gemm_tf32x3_kernel<<<sgb_div_up(M, 128), TG_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, cols, relu); SGB_COUNT_LAUNCH();
+    gemm_tf32x3_kernel<<<sgb_div_up(M, 128), TG_THREADS, smem, (cudaStream_t)stream>>>(A, B, C, M, N, K, cols, relu, K); SGB_COUNT_LAUNCH();
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+// Split-K variant for "tall" contractions (the weight gradient dW = dZ^T X of the GCN layer: M, N <= 256, K = number of
+// clusters): Cpart [ksplit, M, N], slab s = A[:, s*kps : (s+1)*kps] B[:, same]^T with kps = k_per_split (a multiple of 32);
+// the caller sums the slabs (fixed order -> deterministic).
+extern "C" int sgb_gemm_tf32x3_splitk(const float* A, const float* B, float* Cpart, int M, int N, int K, int k_per_split, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || k_per_split <= 0 || (k_per_split & 31)) return SGB_ERR_INVALID;
+    if (!A || !B || !Cpart) return SGB_ERR_INVALID;
+    if (N > 256 || (N & 15) || (K & 3)) return SGB_ERR_UNSUPPORTED;
+    int cols = 32;
+    while (cols < N) cols <<= 1;
+    const size_t smem = (size_t)(2 * 128 + 2 * N) * TG_KC * 4;
+    SGB_OPT_IN_SMEM(gemm_tf32x3_kernel);
+    dim3 grid(sgb_div_up(M, 128), sgb_div_up(K, k_per_split));
+    gemm_tf32x3_kernel<<<grid, TG_THREADS, smem, (cudaStream_t)stream>>>(A, B, Cpart, M, N, K, cols, 0, k_per_split); SGB_COUNT_LAUNCH();
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

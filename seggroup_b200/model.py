@@ -198,17 +198,24 @@ class SegModel(nn.Module):
     def _update_bn(self, res):
         """Running-statistics update of training-mode BatchNorm (momentum 0.1, unbiased variance), one update per scene in
         batch order; the buffers are never read (the reference never calls .eval()) but they are part of the checkpoint."""
-        mods = {"mlp_1.bn1": self.mlp_1.bn1, "mlp_2.bn1": self.mlp_2.bn1, "mlp_3.bn1": self.mlp_3.bn1, "mlp_3.bn2": self.mlp_3.bn2}
+        mods = {"mlp_1.bn1": self.mlp_1.bn1, "mlp_2.bn1": self.mlp_2.bn1, "mlp_3.bn1": self.mlp_3.bn1, "mlp_3.bn2": self.mlp_3.bn2,
+                "classifier.bn1": self.classifier.bn1}
         with torch.no_grad():
             for k, (mean, var, counts) in res.bn_stats_scenes.items():
                 bn = mods.get(k)
                 if bn is None or not bn.training:
                     continue
                 m = bn.momentum
-                for b, count in enumerate(counts):
+                if torch.is_tensor(counts):                            # classifier head: instance counts live on the device
+                    unbiased = var * (counts / (counts - 1).clamp(min=1)).unsqueeze(1)
+                    n = counts.numel()
+                else:
+                    unbiased = var * torch.tensor([c / max(c - 1, 1) for c in counts], dtype=var.dtype, device=var.device).unsqueeze(1)
+                    n = len(counts)
+                for b in range(n):
                     bn.running_mean.mul_(1 - m).add_(mean[b], alpha=m)
-                    bn.running_var.mul_(1 - m).add_(var[b] * (count / max(count - 1, 1)), alpha=m)
-                bn.num_batches_tracked += len(counts)
+                    bn.running_var.mul_(1 - m).add_(unbiased[b], alpha=m)
+                bn.num_batches_tracked += n
 
     # ---- label export (model.py:525-605): D2H on a side stream into pinned buffers, text formatting on writer threads
     def _pinned(self, shape):

@@ -414,6 +414,32 @@ def export_labels(unmap, seg_of_point, level: Level, want_seg=True, split=None):
     return seg, ins, sem
 
 
+def classifier_head_fwd(feat, g_off, gold, W1, gamma, beta, W2, b2, mask, drop_scale):
+    """-> dict(hpre [G,128], stats [B,256], logits [G,40], loss_raw [B,2])"""
+    _chk(feat, F32, "feat"); _chk(g_off, I32, "g_off"); _chk(gold, I32, "gold")
+    G, B = feat.shape[0], g_off.numel() - 1
+    dev = feat.device
+    o = dict(hpre=torch.empty(G, 128, dtype=F32, device=dev), stats=torch.empty(B, 256, dtype=F32, device=dev),
+             logits=torch.empty(G, 40, dtype=F32, device=dev), loss_raw=torch.empty(B, 2, dtype=F32, device=dev))
+    _lib.call("sgb_classifier_head_fwd", feat, G, g_off, B, gold, _chk(W1, F32, "W1"), _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta"),
+              _chk(W2, F32, "W2"), _chk(b2, F32, "b2"), mask, float(drop_scale), o["hpre"], o["stats"], o["logits"], o["loss_raw"], _stream())
+    return o
+
+
+def classifier_head_bwd(feat, g_off, gold, W1, gamma, beta, W2, mask, drop_scale, hpre, stats, logits, grad_loss_sum):
+    """-> (dfeat [G,256], dW1 [128,256], dgamma [128], dbeta [128], dW2 [40,128], db2 [40]); per-scene partials summed in scene order"""
+    G, B = feat.shape[0], g_off.numel() - 1
+    dev = feat.device
+    e = lambda *s: torch.empty(*s, dtype=F32, device=dev)
+    scratch, dfeat = e(G, 128), e(G, 256)
+    dW1p, dgp, dbp, dW2p, db2p = e(B, 128, 256), e(B, 128), e(B, 128), e(B, 40, 128), e(B, 40)
+    _lib.call("sgb_classifier_head_bwd", feat, G, g_off, B, gold, W1, gamma, beta, W2, mask, float(drop_scale), hpre, stats, logits,
+              _chk(grad_loss_sum, F32, "grad_loss_sum"), scratch, dfeat, dW1p, dgp, dbp, dW2p, db2p, _stream())
+    if B == 1:
+        return dfeat, dW1p[0], dgp[0], dbp[0], dW2p[0], db2p[0]
+    return dfeat, dW1p.sum(0), dgp.sum(0), dbp.sum(0), dW2p.sum(0), db2p.sum(0)
+
+
 _VALID_IDS = {}
 
 
@@ -445,6 +471,13 @@ def gemm_tf32x3(A, B, relu=False):
     N = B.shape[0]
     if B.shape[1] != K:
         raise ValueError("A [M,K] and B [N,K] must share K")
+    if not relu and M <= 256 and K >= 1024:
+        # tall contraction (weight gradient): one CTA per 128 rows would walk K alone -> split K over the grid, sum the slabs in order
+        kps = max(128, ((K // 96) + 31) // 32 * 32)
+        ns = (K + kps - 1) // kps
+        part = torch.empty(ns, M, N, dtype=F32, device=A.device)
+        _lib.call("sgb_gemm_tf32x3_splitk", A, B, part, M, N, K, kps, _stream())
+        return part.sum(0)
     C = torch.empty(M, N, dtype=F32, device=A.device)
     _lib.call("sgb_linear_tf32x3", A, B, C, M, N, K, int(bool(relu)), _stream())
     return C

@@ -157,6 +157,29 @@ class LinearReluFn(torch.autograd.Function):
         return dx, dW
 
 
+class ClassifierHeadFn(torch.autograd.Function):
+    """Classifier head + label-smoothed cross entropy (model.py:154-166, 902-932, util.py:12-29) for all scenes of a batch in one
+    launch (one CTA per scene: BatchNorm1d statistics are per scene), forward and backward.  Returns loss_raw [B,2], logits,
+    and the per-scene batch statistics (for the running-stat update of the module's BatchNorm1d)."""
+    @staticmethod
+    def forward(ctx, feat6, W1, gamma, beta, W2, b2, g_off, gold, mask, drop_scale):
+        feat6 = feat6.contiguous()
+        o = ops.classifier_head_fwd(feat6, g_off, gold, W1.contiguous(), gamma.contiguous(), beta.contiguous(), W2.contiguous(), b2.contiguous(),
+                                    mask, drop_scale)
+        ctx.save_for_backward(feat6, W1, gamma, beta, W2, g_off, gold, o["hpre"], o["stats"], o["logits"], mask if mask is not None else feat6.new_empty(0))
+        ctx.drop_scale, ctx.has_mask = drop_scale, mask is not None
+        ctx.mark_non_differentiable(o["logits"], o["stats"])
+        return o["loss_raw"], o["logits"], o["stats"]
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        feat6, W1, gamma, beta, W2, g_off, gold, hpre, stats, logits, mask = ctx.saved_tensors
+        gl = g_loss[:, 0].contiguous()
+        dfeat, dW1, dg, db, dW2, db2 = ops.classifier_head_bwd(feat6, g_off, gold, W1.contiguous(), gamma.contiguous(), beta.contiguous(), W2.contiguous(),
+                                                               mask if ctx.has_mask else None, ctx.drop_scale, hpre, stats, logits, gl)
+        return dfeat, dW1, dg, db, dW2, db2, None, None, None, None
+
+
 def _acc(total, part):
     return part if total is None else total + part
 
@@ -454,31 +477,35 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     off[1:] = torch.cumsum(torch.bincount(inv, minlength=uniq.numel()), 0)
     sem_gt = sem[order[off[:-1].long()].long()]                        # sem label of the first cluster of the group (model.py:916)
     Feat_6, _ = SegmentMaxFn.apply(Feat_5, off, order)
-    g_off = [0, int(uniq.numel())] if B == 1 else [0] + torch.cumsum(torch.bincount(uniq // kmul, minlength=B), 0).tolist()
-    masks = dropout_mask if isinstance(dropout_mask, (list, tuple)) else [dropout_mask] * B
-    losses, logits_all = [], []
-    for b, (g0, g1) in enumerate(_pairs(g_off)):
-        f6 = Feat_6[g0:g1]
-        if classifier is not None:
-            logits = classifier(f6)
-        else:
-            h = F.linear(f6, p["classifier.linear1.weight"])
-            h = F.batch_norm(h, None, None, p["classifier.bn1.weight"], p["classifier.bn1.bias"], True, 0.1, 1e-5)
-            h = F.leaky_relu(h, 0.2)
-            if masks[b] is None:
-                h = F.dropout(h, 0.5, True)
-            else:
-                h = h * masks[b].to(h.dtype) * 2.0
-            logits = F.linear(h, p["classifier.linear2.weight"], p["classifier.linear2.bias"])
-        eps, n_class = 0.2, logits.size(1)
-        one_hot = torch.zeros_like(logits).scatter(1, sem_gt[g0:g1].view(-1, 1), 1)
-        one_hot = one_hot * (1 - eps) + (1 - one_hot) * eps / (n_class - 1)
-        loss_sum = -(one_hot * F.log_softmax(logits, dim=1)).sum()
-        losses.append(torch.stack([loss_sum, torch.full((), float(g1 - g0), dtype=loss_sum.dtype, device=dev)]))
-        logits_all.append(logits)
-    res.loss_raw = torch.stack(losses)                                 # [B,2] = (sum, count) per scene (model.py:932 returns [1,2])
+    g_cnt = torch.bincount(uniq // kmul, minlength=B) if B > 1 else torch.full((1,), uniq.numel(), device=dev)
+    g_off_d = torch.zeros(B + 1, dtype=I32, device=dev)
+    g_off_d[1:] = torch.cumsum(g_cnt, 0)
+    n_groups = int(uniq.numel())
+    if n_groups < 2 * B and int(g_cnt.min()) < 2:                      # (host check only when it can fail)
+        raise ValueError("Expected more than 1 value per channel when training (a scene with a single instance group: "
+                         "BatchNorm1d of the classifier, model.py:157)")
+    # dropout (model.py:159): Bernoulli keep mask drawn with torch's generator, one launch for the whole batch
+    if classifier is not None:
+        cp = {"classifier." + k: v for k, v in classifier.named_parameters()}
+        drop_p = float(classifier.dp1.p) if classifier.training else 0.0
+    else:
+        cp, drop_p = p, 0.5
+    if isinstance(dropout_mask, (list, tuple)):
+        mask = torch.cat([m.to(torch.float32) for m in dropout_mask]).contiguous()
+        drop_scale = 2.0
+    elif dropout_mask is not None:
+        mask, drop_scale = dropout_mask.to(torch.float32).contiguous(), 2.0
+    elif drop_p > 0.0:
+        mask = (torch.rand(n_groups, 128, device=dev) >= drop_p).to(torch.float32)
+        drop_scale = 1.0 / (1.0 - drop_p)
+    else:
+        mask, drop_scale = None, 1.0
+    loss_raw, logits, cstats = ClassifierHeadFn.apply(Feat_6, cp["classifier.linear1.weight"], cp["classifier.bn1.weight"], cp["classifier.bn1.bias"],
+                                                      cp["classifier.linear2.weight"], cp["classifier.linear2.bias"], g_off_d, sem_gt.to(I32), mask, drop_scale)
+    res.loss_raw = loss_raw                                            # [B,2] = (sum, count) per scene (model.py:932 returns [1,2])
+    res.bn_stats_scenes["classifier.bn1"] = (cstats[:, :128], cstats[:, 128:], loss_raw[:, 1].detach())
     if keep_aux:
-        res.aux["logits"] = torch.cat(logits_all).detach()
+        res.aux["logits"] = logits.detach()
     return res
 
 

@@ -484,3 +484,45 @@ def test_evaluate_matches_oracle(case):
     for a, b in zip(out, ref):
         a = a.cpu().numpy().reshape(b.shape)
         assert np.allclose(a, b, rtol=1e-6, atol=0, equal_nan=True), (case, a, b)
+
+
+@pytest.mark.parametrize("counts,drop", [([41, 17, 2, 33], True), ([9], False), ([64, 64], True)])
+def test_classifier_head_forward_backward(counts, drop):
+    """a15: the fused classifier head + label-smoothed cross entropy (model.py:154-166, 902-932, util.py:12-29), one CTA per
+    scene, against torch fp64 evaluated per scene: loss (sum, count), logits, BatchNorm batch statistics and every gradient."""
+    import torch.nn.functional as F
+    from seggroup_b200.pipeline import ClassifierHeadFn
+    g = torch.Generator().manual_seed(sum(counts))
+    G = sum(counts)
+    feat = torch.randn(G, 256, generator=g)
+    W1 = torch.randn(128, 256, generator=g) / 16
+    gamma, beta = 0.5 + torch.rand(128, generator=g), 0.2 * torch.randn(128, generator=g)
+    W2, b2 = torch.randn(40, 128, generator=g) / 11, 0.1 * torch.randn(40, generator=g)
+    gold = torch.randint(0, 40, (G,), generator=g)
+    mask = (torch.rand(G, 128, generator=g) > 0.5).float() if drop else None
+    w = torch.randn(len(counts), generator=g)                         # upstream gradient of every scene's loss sum
+    off = [0] + list(np.cumsum(counts))
+    dv = [t.cuda().requires_grad_(True) for t in (feat, W1, gamma, beta, W2, b2)]
+    loss_raw, logits, stats = ClassifierHeadFn.apply(*dv, torch.tensor(off, dtype=torch.int32, device="cuda"), gold.int().cuda(),
+                                                     mask.cuda() if drop else None, 2.0 if drop else 1.0)
+    (loss_raw[:, 0] * w.cuda()).sum().backward()
+    rv = [t.double().requires_grad_(True) for t in (feat, W1, gamma, beta, W2, b2)]
+    total = 0
+    for b, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        h = F.linear(rv[0][lo:hi], rv[1])
+        assert torch.allclose(stats[b, :128].cpu().double(), h.mean(0).detach(), atol=1e-5)
+        assert torch.allclose(stats[b, 128:].cpu().double(), h.var(0, unbiased=False).detach(), rtol=1e-4, atol=1e-6)
+        h = F.leaky_relu(F.batch_norm(h, None, None, rv[2], rv[3], True, 0.1, 1e-5), 0.2)
+        if drop:
+            h = h * mask[lo:hi].double() * 2.0
+        lg = F.linear(h, rv[4], rv[5])
+        one_hot = torch.zeros_like(lg).scatter(1, gold[lo:hi].view(-1, 1), 1)
+        one_hot = one_hot * 0.8 + (1 - one_hot) * 0.2 / 39
+        ls = -(one_hot * F.log_softmax(lg, dim=1)).sum()
+        assert abs(float(loss_raw[b, 0]) - float(ls)) < 1e-5 * abs(float(ls)) and int(loss_raw[b, 1]) == hi - lo
+        assert float((logits[lo:hi].cpu().double() - lg.detach()).abs().max()) < 1e-4
+        total = total + ls * w[b].double()
+    total.backward()
+    for a, r, name in zip(dv, rv, ("feat", "W1", "gamma", "beta", "W2", "b2")):
+        err = float((a.grad.cpu().double() - r.grad).abs().max() / (r.grad.abs().max() + 1e-30))
+        assert err < 2e-5, (name, err)

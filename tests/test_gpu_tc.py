@@ -23,7 +23,18 @@ def test_gemm_tf32x3(M, N, K):
     assert _rel(C, ref) < 1e-4
 
 
-@pytest.mark.parametrize("S,C", [(351, 192), (1047, 256), (66, 192), (2, 256)])
+def test_gemm_tf32x3_split_k():
+    """tall contraction (the GCN weight gradient dW = dZ^T X with K = thousands of clusters): split-K slabs summed in order"""
+    from seggroup_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for M, N, K in [(192, 192, 8600), (256, 256, 5368), (256, 256, 1024), (192, 192, 1028)]:
+        A = torch.randn(M, K, generator=g)
+        B = torch.randn(N, K, generator=g) * 0.3
+        C = ops.gemm_tf32x3(A.cuda(), B.cuda())
+        assert _rel(C, A.double() @ B.double().t()) < 1e-5
+
+
+@pytest.mark.parametrize("S,C", [(351, 192), (1047, 256), (66, 192), (2, 256), (8599, 192)])
 def test_gcn_linear_relu_forward_backward(S, C):
     """relu(fc(x)) of the GCN layer (model.py:146-151) on tcgen05 with the ReLU fused into the epilogue, and its backward (two
     more GEMMs), against torch fp64."""

@@ -38,6 +38,20 @@ agg = {}
 for e in ev:
     a = agg.setdefault(e.name[:70], [0, 0.0]); a[0] += 1; a[1] += (e.device_time if hasattr(e, "device_time") else e.cuda_time)
 print("torch profiler: %d device activities, %.3f ms summed" % (len(ev), tot_k / 1e3))
+# idle gaps of the device between consecutive activities, attributed to the activity that FOLLOWS the gap
+evs = sorted(ev, key=lambda e: e.time_range.start)
+gaps = {}
+t_end = evs[0].time_range.end
+total_gap = 0.0
+for e in evs[1:]:
+    g = e.time_range.start - t_end
+    if g > 2.0:
+        a = gaps.setdefault(e.name[:60], [0, 0.0]); a[0] += 1; a[1] += g
+        total_gap += g
+    t_end = max(t_end, e.time_range.end)
+print("device idle gaps > 2 us: %.3f ms in total over a span of %.3f ms" % (total_gap / 1e3, (t_end - evs[0].time_range.start) / 1e3))
+for k, v in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+    print("  gap before %-60s n %4d  %8.3f ms" % (k, v[0], v[1] / 1e3))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("  %-70s n %4d  %9.3f ms" % (k, v[0], v[1] / 1e3))
 _lib.enable_profile()
