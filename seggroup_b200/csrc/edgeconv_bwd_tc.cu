@@ -5,21 +5,20 @@
 //     dv1[e, c] = (r[c] - sum_j Bm[c, j] h[e, j]) * lrelu'(v1[e, c]),      h[e, :] = lrelu(BN1(W1 e_e))
 // and the first-layer parameter gradients need   A0[c] = sum_e dv1[e, c],   T[c, t] = sum_e dv1[e, c] (e_e[t] - ebar[t])
 // (the dgamma sum follows from T:  sum_e dv1 zhat1 = invstd1[c] * W1[c, :] . T[c, :], because mean(W1 e) = W1 ebar).
-// The 64x64 mat-vec per edge (8.2 kFLOP x 3 M edges) is the same GEMM shape as the forward second layer, so this kernel is
-// the forward tcgen05 kernel (edgeconv_tc.cu) with Bm in place of W2:  D[64 channels, 160 edges] = Bm * H^T, kind::tf32 x 3.
-// Differences from the forward kernel:
-//   * the producers also leave, per edge, the sign bits of the 64 hidden activations (2 words) and the centred edge vector
-//     (18 floats) in the stage, for the epilogue;
-//   * the epilogue owns the stage until it is done with it (bar_empty is arrived by the epilogue warps, not by the MMA commit):
-//     thread = channel (lanes 0..15 of each warp hold the M = 64 accumulator rows), the partner lane 16 + l takes half of the
-//     18 columns of T for the same channel (dv1 by shuffle), accumulators fp32 per 8 tiles, fp64 across;
-//   * outputs: per-CTA partial sums part[cta][64][20] = (A0, sum dv1 zhat1, T[18]) in fp64, reduced in a fixed order.
-// Measured (profiles/r01i_ncu_full_train_150k.txt): 827 us at 150k points, l1tex 88 %, tensor pipe 16.5 %: the kernel is
-// shared-memory-bandwidth bound, and the largest consumer is the epilogue's broadcast reads of the centred edge vectors
-// (every warp re-reads the 72 bytes of every edge, two distinct addresses per wavefront).  Spreading the epilogue over eight
-// warps with pipelined TMEM loads did not help (0.93 -> 0.96 ms: same shared-memory traffic); the next step is to run
-// T = dv1^T (e - ebar) as a second tcgen05 GEMM over the edges (K = edges, as the forward Gram accumulator does), which needs
-// 80-edge tiles to fit the dv1 operand next to the H tiles.
+//
+// Round 2 design — BOTH contractions run on tcgen05 (kind::tf32 x 3, tc_common.cuh):
+//   (1) z = Bm h per edge:   D_z[64 channels, 80 edges] = Bm[64, 64] * H[80, 64]^T          (as the forward second layer)
+//   (2) T and A0:            D_T[64 channels, 24]      += dv1^T[64, 80 edges] * EC[24, 80 edges]^T, K = the edges of the tile,
+//       EC rows 0..17 = centred edge vector, row 18 = 1 for a real edge (-> A0), rows 19..23 = 0.
+// Round 1 accumulated (2) on the CUDA cores in the epilogue: 9 FMA + 3 shared-memory loads + a shuffle per edge and thread,
+// one warp per scheduler, latency bound (profiles/r02o: 400 instructions per point and warp); the shared-memory reads of the
+// centred vectors plus the producers' weight reads put the kernel at 88 % l1tex.  Now the epilogue only turns z into dv1
+// (20 values per point in registers -> hi / lo split -> 16-byte stores of 4 consecutive edges into a K-major operand tile) and
+// the tensor cores do the rest; D_T stays in TMEM for 32 tiles, is flushed to fp64 accumulators, and double buffered.
+// Producers: as the forward kernel (edgeconv_tc.cu) — first-layer weights in registers, cp.async gather ring 3 tiles ahead —
+// plus, per edge, the sign bits of the hidden activations (a byte per 4-channel chunk) and the transposed centred edge vector.
+// Pipelines (mbarriers): H stage full / empty (empty = tcgen05.commit after the T MMAs of the tile), z accumulators full /
+// empty (2 TMEM buffers), dv1 tile full / empty (1 buffer), T accumulator segment full / empty (2 TMEM buffers).
 #include "common.cuh"
 #include "bn_moments.cuh"
 #include "edgeconv_common.cuh"
@@ -33,37 +32,54 @@ using sgb_ec::KNN;
 using sgb_bn::lrelu;
 using sgb_bn::SLOPE;
 
-constexpr int EPI_WARPS = 4, PROD_WARPS = 10;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS;
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 480
-constexpr int PROD_THREADS = PROD_WARPS * 32;                  // 320
-constexpr int TE = 160;                                        // edges per tile
-constexpr int PTS = TE / KNN;                                  // 8 points per tile
-constexpr int PPE = PROD_THREADS / TE;                         // 2 producer threads per edge
-constexpr int CPT = 16 / PPE;                                  // 8 chunks of 4 hidden channels per producer thread
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 416
+constexpr int PROD_THREADS = PROD_WARPS * 32;                  // 256
+constexpr int TE = 80;                                         // edges per tile
+constexpr int PTS = TE / KNN;                                  // 4 points per tile
+constexpr int BLOCKS = TE / 8;                                 // 8-edge blocks per tile; a group of 4 producer warps takes every 2nd one
+constexpr int TN = 24;                                         // columns of the T accumulator: 18 + A0 + 5 zero
 constexpr int BM_BYTES = COUT * COUT * 4;
-constexpr int TILE_BYTES = TE * COUT * 4;                      // one K-major H tile (hi or lo)
-constexpr int DROW = 20;                                       // floats per edge row of the centred edge vectors
-constexpr int D_BYTES = TE * DROW * 4;
-constexpr int MASK_BYTES = TE * 2 * 4;
-constexpr int STAGE_BYTES = 2 * TILE_BYTES + D_BYTES + MASK_BYTES;        // 96,000: a multiple of 128
-constexpr int W1T_STRIDE = 80;
+constexpr int TILE_BYTES = TE * COUT * 4;                      // one K-major H tile (hi or lo); also one dv1^T tile [64 rows][80 edges]
+constexpr int EC_BYTES = TN * TE * 4;                          // one K-major EC tile [24 rows][80 edges] (hi or lo)
+constexpr int MASK_BYTES = TE * 16;                            // one byte per (edge, 4-channel chunk): sign bits of the hidden activations
+constexpr int HSTAGE_BYTES = 2 * TILE_BYTES;                   // H hi / lo: free again as soon as the z MMAs of the tile have completed
+constexpr int ESTAGE_BYTES = 2 * EC_BYTES + MASK_BYTES;        // EC hi / lo + sign bytes: live until the T MMAs of the tile have completed
+constexpr int ERING = 3;
+constexpr int DVH_BYTES = COUT * (TE / 2) * 4;                 // dv1^T of HALF a tile (2 points = 40 edges), hi or lo
+constexpr int RING = 3;                                        // tiles in flight in the gather ring
+constexpr int RAW_BYTES = TE * 48 + PTS * 48 + TE * 8;         // x_j rows, x_i rows, validity words, neighbour indices of a later tile
 constexpr int NACC = CIN + 2;
-constexpr int FLUSH_TILES = 8;
+constexpr int ACCN = 20;                                       // fp64 accumulator columns kept per channel (18 + A0 + pad)
+constexpr int FLUSH = 32;                                      // tiles per T segment (fp32 in TMEM), then fp64
 constexpr int TMEM_COLS = 512;
-constexpr int Z_COL = 256;
+constexpr int Z_COL = 256;                                     // z accumulators at columns 0 and 256
+constexpr int T_COL0 = 128, T_COLS = 64;                       // T accumulators at columns 128 and 192
 
 constexpr int off_bm_hi = 0;
 constexpr int off_bm_lo = off_bm_hi + BM_BYTES;
-constexpr int off_stage0 = off_bm_lo + BM_BYTES;
-constexpr int off_w1t = off_stage0 + 2 * STAGE_BYTES;
-constexpr int off_b1 = off_w1t + CIN * W1T_STRIDE * 4;
-constexpr int off_ebar = off_b1 + COUT * 4;
-constexpr int off_bars = off_ebar + 32 * 4;
-constexpr int off_tmem_slot = off_bars + 8 * 8;
+constexpr int off_h0 = off_bm_lo + BM_BYTES;                   // 2 H stages
+constexpr int off_e0 = off_h0 + 2 * HSTAGE_BYTES;              // 3 EC / mask stages
+constexpr int off_dv = off_e0 + ERING * ESTAGE_BYTES;          // [half][hi, lo]
+constexpr int off_raw0 = off_dv + 4 * DVH_BYTES;
+constexpr int off_acc = off_raw0 + RING * RAW_BYTES;           // fp64 accumulators [64 channels][ACCN]
+constexpr int off_ebar = off_acc + COUT * ACCN * 8;
+constexpr int off_bars = off_ebar + 32 * 4;                    // 19 mbarriers
+constexpr int off_tmem_slot = off_bars + 20 * 8;
 constexpr int SMEM_TOTAL = off_tmem_slot + 16;
-static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
+static_assert(HSTAGE_BYTES % 128 == 0 && ESTAGE_BYTES % 128 == 0 && DVH_BYTES % 128 == 0, "stage alignment");
 static_assert(SMEM_TOTAL + 128 <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ bool mbar_test(uint64_t* mbar, uint32_t parity) {       // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// byte offset of (row r, K index e) in a canonical no-swizzle K-major tile with R rows (tc_common.cuh tile_off with c = e)
+__device__ __forceinline__ uint32_t kmajor_off(int r, int e, int R) { return (uint32_t)((e >> 2) * (R * 16) + (r >> 3) * 128 + (r & 7) * 16 + (e & 3) * 4); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ W1,
@@ -72,12 +88,15 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + off_bars);         // [2] producers -> MMA
-    uint64_t* bar_empty = bar_full + 2;                                      // [2] epilogue -> producers (stage + TMEM buffer free)
-    uint64_t* bar_tfull = bar_full + 4;                                      // [2] MMA (commit) -> epilogue
-    uint64_t* bar_tempty = bar_full + 6;                                     // [2] epilogue -> MMA
+    uint64_t* bar_hempty = bar_full + 2;                                     // [2] MMA (commit after the z MMAs) -> producers: H tiles free
+    uint64_t* bar_tfull = bar_full + 4;                                      // [2] MMA (commit) -> epilogue: z ready
+    uint64_t* bar_tempty = bar_full + 6;                                     // [2] epilogue -> MMA: z buffer free
+    uint64_t* bar_dvfull = bar_full + 8;                                     // [2] epilogue -> MMA: half of the dv1 tile written
+    uint64_t* bar_dvempty = bar_full + 10;                                   // [2] MMA (commit) -> epilogue: that half consumed
+    uint64_t* bar_gfull = bar_full + 12;                                     // [2] MMA (commit) -> epilogue: T segment complete
+    uint64_t* bar_gempty = bar_full + 14;                                    // [2] epilogue -> MMA: T accumulator flushed
+    uint64_t* bar_eempty = bar_full + 16;                                    // [3] MMA (commit after the T MMAs) -> producers: EC / mask stage free
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + off_tmem_slot);
-    float* s_w1t = reinterpret_cast<float*>(sm + off_w1t);
-    float* s_b1 = reinterpret_cast<float*>(sm + off_b1);
     float* s_ebar = reinterpret_cast<float*>(sm + off_ebar);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -87,7 +106,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
     const long long g_begin = (long long)p_begin * KNN, g_end = (long long)p_end * KNN;
     const int ntiles = (int)((g_end - g_begin + TE - 1) / TE);
 
-    // ---- one-time setup: Bm (symmetric) -> K-major canonical tiles, hi / lo split
+    // ---- one-time setup: Bm (symmetric) -> K-major canonical tiles, hi / lo split; constant rows of the EC tiles; accumulators
     for (int i = tid; i < COUT * COUT; i += THREADS) {
         const int c = i / COUT, j = i % COUT;
         const float w = __ldg(coef + i);
@@ -96,17 +115,26 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         *reinterpret_cast<float*>(sm + off_bm_hi + off) = hi;
         *reinterpret_cast<float*>(sm + off_bm_lo + off) = tf32_hi(w - hi);
     }
-    for (int i = tid; i < COUT * CIN; i += THREADS) {
-        const int c = i / CIN, q = i % CIN;
-        s_w1t[q * W1T_STRIDE + (c >> 4) * 20 + (c & 15)] = __ldg(W1 + i) * stats1[128 + c];
+    for (int s2 = 0; s2 < ERING; ++s2) {                                      // rows 18..23 of the EC tiles of every stage: zero (row 18 is
+        unsigned char* ec = sm + off_e0 + s2 * ESTAGE_BYTES;                  // rewritten per edge by the producers, 19..23 stay zero)
+        for (int i = tid; i < 6 * TE; i += THREADS) {
+            const int r = 18 + i / TE, e = i % TE;
+            *reinterpret_cast<float*>(ec + kmajor_off(r, e, TN)) = 0.f;
+            *reinterpret_cast<float*>(ec + EC_BYTES + kmajor_off(r, e, TN)) = 0.f;
+        }
     }
-    for (int i = tid; i < COUT; i += THREADS) s_b1[i] = fmaf(-stats1[128 + i], stats1[i], stats1[192 + i]);
+    for (int i = tid; i < COUT * ACCN; i += THREADS) reinterpret_cast<double*>(sm + off_acc)[i] = 0.0;
     if (tid < CIN) s_ebar[tid] = (float)(mom1[tid] / M + (double)e0[tid]);
     if (tid == 0) {
         mbar_init(&bar_full[0], PROD_WARPS); mbar_init(&bar_full[1], PROD_WARPS);
-        mbar_init(&bar_empty[0], EPI_WARPS); mbar_init(&bar_empty[1], EPI_WARPS);
+        mbar_init(&bar_hempty[0], 1); mbar_init(&bar_hempty[1], 1);
         mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
         mbar_init(&bar_tempty[0], EPI_WARPS); mbar_init(&bar_tempty[1], EPI_WARPS);
+        mbar_init(&bar_dvfull[0], EPI_WARPS); mbar_init(&bar_dvfull[1], EPI_WARPS);
+        mbar_init(&bar_dvempty[0], 1); mbar_init(&bar_dvempty[1], 1);
+        mbar_init(&bar_eempty[0], 1); mbar_init(&bar_eempty[1], 1); mbar_init(&bar_eempty[2], 1);
+        mbar_init(&bar_gfull[0], 1); mbar_init(&bar_gfull[1], 1);
+        mbar_init(&bar_gempty[0], EPI_WARPS); mbar_init(&bar_gempty[1], EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -117,66 +145,105 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
     const uint32_t tmem = *tmem_slot;
 
     if (warp > MMA_WARP) {
-        // ================= producers (as the forward kernel) + sign bits and centred edge vectors for the epilogue
-        const int pw = warp - (MMA_WARP + 1);
-        const int er = pw * (32 / PPE) + lane / PPE;
-        const int part_id = lane % PPE;
-        float en[CIN];
-        int j_next = 0;
-        bool v_next = false;
-        auto issue_index = [&](int t) -> int {
-            const long long g = g_begin + (long long)t * TE + er;
-            return (t < ntiles && g < g_end) ? __ldg(knn + g) : -1;
+        // ================= producers (as the forward kernel) + sign bits and transposed centred edge vectors
+        const int pw = warp - (MMA_WARP + 1);           // 0..7
+        const int ptid = pw * 32 + lane;                // gather role: edge row `ptid` (< TE), point row `ptid` (< PTS)
+        const int grp = pw >> 2;
+        const int c4 = (lane >> 3) * 4 + (pw & 3);      // my chunk of the hidden vector: channels 4 c4 .. 4 c4 + 3
+        const int eb = lane & 7;
+        float2 w01[CIN], w23[CIN];
+        float4 bias;
+        {
+            float sc[4], bb[4];
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int c = 4 * c4 + s4;
+                sc[s4] = stats1[128 + c];
+                bb[s4] = fmaf(-stats1[128 + c], stats1[c], stats1[192 + c]);
+            }
+#pragma unroll
+            for (int q = 0; q < CIN; ++q) {
+                w01[q] = make_float2(__ldg(W1 + (4 * c4 + 0) * CIN + q) * sc[0], __ldg(W1 + (4 * c4 + 1) * CIN + q) * sc[1]);
+                w23[q] = make_float2(__ldg(W1 + (4 * c4 + 2) * CIN + q) * sc[2], __ldg(W1 + (4 * c4 + 3) * CIN + q) * sc[3]);
+            }
+            bias = make_float4(bb[0], bb[1], bb[2], bb[3]);
+        }
+        const bool gatherer = ptid < TE, pgatherer = ptid < PTS;
+        auto edge_in_range = [&](int t) -> bool {
+            const long long g = g_begin + (long long)t * TE + ptid;
+            return gatherer && t < ntiles && g < g_end;
         };
-        auto issue_rows = [&](int t, int j) {
-            const long long g = g_begin + (long long)t * TE + er;
-            v_next = j >= 0;
-            if (v_next) {
-                const float4* xi = reinterpret_cast<const float4*>(x12 + (size_t)(g / KNN) * 12);
-                const float4* xj = reinterpret_cast<const float4*>(x12 + (size_t)j * 12);
-                const float4 a0 = __ldg(xi), a1 = __ldg(xi + 1), a2 = __ldg(xi + 2);
-                const float4 b0 = __ldg(xj), b1 = __ldg(xj + 1), b2 = __ldg(xj + 2);
-                en[0] = b0.x - a0.x; en[1] = b0.y - a0.y; en[2] = b0.z - a0.z; en[3] = b0.w - a0.w;
-                en[4] = b1.x - a1.x; en[5] = b1.y - a1.y; en[6] = b1.z - a1.z; en[7] = b1.w - a1.w;
-                en[8] = b2.x - a2.x;
-                en[9] = a0.x; en[10] = a0.y; en[11] = a0.z; en[12] = a0.w;
-                en[13] = a1.x; en[14] = a1.y; en[15] = a1.z; en[16] = a1.w; en[17] = a2.x;
+        auto cp16 = [&](void* dst, const float* src, bool valid) {
+            const uint32_t n = valid ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+        };
+        auto issue_index_copy = [&](int t) {
+            if (edge_in_range(t)) {
+                unsigned char* slot = sm + off_raw0 + (t % RING) * RAW_BYTES + TE * 48 + PTS * 48 + TE * 4 + ptid * 4;
+                const int* src = knn + (g_begin + (long long)t * TE + ptid);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(slot)), "l"(src) : "memory");
             }
         };
-        issue_rows(0, issue_index(0));
-        j_next = issue_index(1);
+        auto issue_rows = [&](int t, int j) {
+            unsigned char* raw = sm + off_raw0 + (t % RING) * RAW_BYTES;
+            if (gatherer) {
+                const bool v = j >= 0;
+                const float* src = x12 + (size_t)(v ? j : 0) * 12;
+                unsigned char* dst = raw + ptid * 48;
+                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
+                *reinterpret_cast<uint32_t*>(raw + TE * 48 + PTS * 48 + ptid * 4) = v ? 1u : 0u;
+            }
+            if (pgatherer) {
+                const long long pt = g_begin / KNN + (long long)t * PTS + ptid;
+                const bool v = t < ntiles && pt < (long long)p_end;
+                const float* src = x12 + (size_t)(v ? pt : 0) * 12;
+                unsigned char* dst = raw + TE * 48 + ptid * 48;
+                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
+            }
+            issue_index_copy(t + RING - 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto staged_index = [&](int t) -> int {
+            if (!edge_in_range(t)) return -1;
+            return *reinterpret_cast<const volatile int*>(sm + off_raw0 + (t % RING) * RAW_BYTES + TE * 48 + PTS * 48 + TE * 4 + ptid * 4);
+        };
+#pragma unroll 1
+        for (int tt = 0; tt < RING - 1; ++tt) issue_rows(tt, edge_in_range(tt) ? __ldg(knn + (g_begin + (long long)tt * TE + ptid)) : -1);
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            float2 ee[CIN];
-            float ec[CIN];
-            const bool valid = v_next;
-#pragma unroll
-            for (int q = 0; q < CIN; ++q) { ee[q] = make_float2(en[q], en[q]); ec[q] = valid ? en[q] - s_ebar[q] : 0.f; }
-            issue_rows(t + 1, j_next);
-            j_next = issue_index(t + 2);
-            mbar_wait(&bar_empty[st], ph ^ 1u);
-            unsigned char* dst_hi = sm + off_stage0 + st * STAGE_BYTES;
+            asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory");
+            asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");
+            issue_rows(t + RING - 1, staged_index(t + RING - 1));
+            const unsigned char* raw = sm + off_raw0 + (t % RING) * RAW_BYTES;
+            mbar_wait(&bar_hempty[st], ph ^ 1u);
+            mbar_wait(&bar_eempty[t % ERING], ((uint32_t)(t / ERING) & 1u) ^ 1u);
+            unsigned char* dst_hi = sm + off_h0 + st * HSTAGE_BYTES;
             unsigned char* dst_lo = dst_hi + TILE_BYTES;
-            float* dst_d = reinterpret_cast<float*>(dst_lo + TILE_BYTES) + er * DROW;
-            uint32_t* dst_m = reinterpret_cast<uint32_t*>(dst_lo + TILE_BYTES + D_BYTES) + er * 2;
-            uint32_t bits = 0;
-#pragma unroll 2
-            for (int i4 = 0; i4 < CPT; ++i4) {
-                const int c4 = part_id * CPT + i4;
+            unsigned char* dst_ech = sm + off_e0 + (t % ERING) * ESTAGE_BYTES;
+            unsigned char* dst_ecl = dst_ech + EC_BYTES;
+            unsigned char* dst_mt = dst_ecl + EC_BYTES;
+#pragma unroll 1
+            for (int blk = grp; blk < BLOCKS; blk += 2) {
+                const int er = blk * 8 + eb;
+                const float4* rj = reinterpret_cast<const float4*>(raw + er * 48);
+                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + (er / KNN) * 48);
+                const float4 b0 = rj[0], b1 = rj[1], b2 = rj[2];
+                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
+                const float ev[CIN] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w, b1.x - a1.x, b1.y - a1.y, b1.z - a1.z, b1.w - a1.w, b2.x - a2.x,
+                                       a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+                const bool valid = *reinterpret_cast<const uint32_t*>(raw + TE * 48 + PTS * 48 + er * 4) != 0u;
+                float2 y01 = make_float2(bias.x, bias.y), y23 = make_float2(bias.z, bias.w);
+#pragma unroll
+                for (int q = 0; q < CIN; ++q) {
+                    const float2 ee = make_float2(ev[q], ev[q]);
+                    ffma2(y01, w01[q], ee);
+                    ffma2(y23, w23[q], ee);
+                }
+                uint32_t bits = 0;
                 float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
-                    const float4 b = *reinterpret_cast<const float4*>(s_b1 + c4 * 4);
-                    float2 y01 = make_float2(b.x, b.y), y23 = make_float2(b.z, b.w);
-                    const float* wrow = s_w1t + (c4 >> 2) * 20 + (c4 & 3) * 4;
-#pragma unroll
-                    for (int q = 0; q < CIN; ++q) {
-                        const float4 w = *reinterpret_cast<const float4*>(wrow + q * W1T_STRIDE);
-                        ffma2(y01, make_float2(w.x, w.y), ee[q]);
-                        ffma2(y23, make_float2(w.z, w.w), ee[q]);
-                    }
-                    bits |= (y01.x > 0.f ? 1u : 0u) << (4 * i4) | (y01.y > 0.f ? 2u : 0u) << (4 * i4) |
-                            (y23.x > 0.f ? 4u : 0u) << (4 * i4) | (y23.y > 0.f ? 8u : 0u) << (4 * i4);
+                    bits = (y01.x > 0.f ? 1u : 0u) | (y01.y > 0.f ? 2u : 0u) | (y23.x > 0.f ? 4u : 0u) | (y23.y > 0.f ? 8u : 0u);
                     y = make_float4(lrelu(y01.x), lrelu(y01.y), lrelu(y23.x), lrelu(y23.y));
                 }
                 const float4 hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
@@ -184,109 +251,183 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 const uint32_t off = (uint32_t)c4 * (TE * 16) + (uint32_t)(er >> 3) * 128 + (uint32_t)(er & 7) * 16;
                 *reinterpret_cast<float4*>(dst_hi + off) = hi;
                 *reinterpret_cast<float4*>(dst_lo + off) = lo;
-            }
-            dst_m[part_id] = bits;                      // sign bits of hidden channels 32 part_id .. 32 part_id + 31
-            if (part_id == 0) {                         // centred edge vector: [0..7] = t 0..7, [8..15] = t 8..15, [16], [17]
-                float4* d4 = reinterpret_cast<float4*>(dst_d);
-                d4[0] = make_float4(ec[0], ec[1], ec[2], ec[3]);
-                d4[1] = make_float4(ec[4], ec[5], ec[6], ec[7]);
-                d4[2] = make_float4(ec[8], ec[9], ec[10], ec[11]);
-                d4[3] = make_float4(ec[12], ec[13], ec[14], ec[15]);
-                d4[4] = make_float4(ec[16], ec[17], 0.f, 0.f);
+                dst_mt[er * 16 + c4] = (unsigned char)bits;     // sign bits of hidden channels 4 c4 .. 4 c4 + 3
+                // EC column of this edge (centred edge vector, then 1 for a real edge -> A0), spread over the 16 threads of the edge:
+                // thread c4 writes row c4, threads 0..2 also rows 16..18.  Values come straight from the gathered rows (same
+                // subtraction as ev[]), so no register array is indexed dynamically.
+                {
+                    const float* fj = reinterpret_cast<const float*>(rj);
+                    const float* fi = reinterpret_cast<const float*>(ri);
+                    auto ec_store = [&](int q) {
+                        float v = 0.f;
+                        if (valid) {
+                            if (q == CIN) v = 1.f;
+                            else {
+                                const float xi = fi[q < 9 ? q : q - 9];
+                                v = (q < 9 ? fj[q] - xi : xi) - s_ebar[q];
+                            }
+                        }
+                        const float vh = tf32_hi(v);
+                        const uint32_t o = kmajor_off(q, er, TN);
+                        *reinterpret_cast<float*>(dst_ech + o) = vh;
+                        *reinterpret_cast<float*>(dst_ecl + o) = tf32_hi(v - vh);
+                    };
+                    ec_store(c4);
+                    if (c4 < 3) ec_store(16 + c4);
+                }
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[st]);
         }
     } else if (warp == MMA_WARP) {
-        // ================= MMA issuer
-        const uint32_t idesc = make_idesc_tf32(64, TE, false, false);
-        const uint32_t a_hi = smem_u32(sm + off_bm_hi), a_lo = smem_u32(sm + off_bm_lo);
-        for (int t = 0; t < ntiles; ++t) {
-            const int st = t & 1;
-            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            mbar_wait(&bar_full[st], ph);
-            mbar_wait(&bar_tempty[st], ph ^ 1u);
-            fence_after_sync();
-            if (lane == 0) {
-                const uint32_t b_hi = smem_u32(sm + off_stage0 + st * STAGE_BYTES), b_lo = b_hi + TILE_BYTES;
-                const uint32_t d = tmem + (uint32_t)(st * Z_COL);
+        // ================= MMA issuer (one thread): an event loop over two independent streams of work — the z MMAs of the next
+        // tile whose H stage is full, and the T MMAs of the next half tile whose dv1 operand the epilogue has finished — so that
+        // neither waits for the other's inputs (non-blocking mbarrier tests)
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(64, TE, false, false);
+            const uint32_t idesc_t = make_idesc_tf32(64, TN, false, false);
+            const uint32_t a_hi = smem_u32(sm + off_bm_hi), a_lo = smem_u32(sm + off_bm_lo);
+            int nz = 0, nT = 0;                         // next tile for z, next HALF tile (2 u + h) for T
+            while (nT < 2 * ntiles) {
+                bool did = false;
+                if (nz < ntiles) {
+                    const int st = nz & 1;
+                    const uint32_t ph = (uint32_t)(nz >> 1) & 1u;
+                    if (mbar_test(&bar_full[st], ph) && mbar_test(&bar_tempty[st], ph ^ 1u)) {
+                        fence_after_sync();
+                        const uint32_t b_hi = smem_u32(sm + off_h0 + st * HSTAGE_BYTES), b_lo = b_hi + TILE_BYTES;
+                        const uint32_t d = tmem + (uint32_t)(st * Z_COL);
 #pragma unroll
-                for (int i = 0; i < COUT / 8; ++i) {
-                    const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
-                    const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
-                    const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
-                    mma_tf32(d, dah, dbh, idesc, i > 0);
-                    mma_tf32(d, dal, dbh, idesc, true);
-                    mma_tf32(d, dah, dbl, idesc, true);
+                        for (int i = 0; i < COUT / 8; ++i) {
+                            const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
+                            const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
+                            const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
+                            mma_tf32(d, dah, dbh, idesc, i > 0);
+                            mma_tf32(d, dal, dbh, idesc, true);
+                            mma_tf32(d, dah, dbl, idesc, true);
+                        }
+                        mma_commit(&bar_tfull[st]);
+                        mma_commit(&bar_hempty[st]);
+                        ++nz;
+                        did = true;
+                    }
                 }
-                mma_commit(&bar_tfull[st]);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ================= epilogue: channel c = 16 warp + (lane & 15); lane half h = lane >> 4 takes columns
-        //                   t = 8h .. 8h + 7 and 16 + h of T for that channel
-        const int c = warp * 16 + (lane & 15);
-        const int half = lane >> 4;
-        const float rc = __ldg(coef + COUT * COUT + c);
-        const uint32_t word = (uint32_t)(c >> 5), bit = (uint32_t)(c & 31);
-        float a0 = 0.f, tt[9];
-        double A0 = 0.0, TT[9];
+                {
+                    const int u = nT >> 1, h = nT & 1;
+                    const int seg = u / FLUSH, gb = seg & 1;
+                    bool ok = mbar_test(&bar_dvfull[h], (uint32_t)u & 1u);
+                    if (ok && h == 0 && u % FLUSH == 0) ok = mbar_test(&bar_gempty[gb], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
+                    if (ok) {
+                        fence_after_sync();
+                        const uint32_t ec_hi = smem_u32(sm + off_e0 + (u % ERING) * ESTAGE_BYTES), ec_lo = ec_hi + EC_BYTES;
+                        const uint32_t dvh = smem_u32(sm + off_dv + h * 2 * DVH_BYTES), dvl = dvh + DVH_BYTES;
+                        const uint32_t d = tmem + (uint32_t)(T_COL0 + gb * T_COLS);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { tt[i] = 0.f; TT[i] = 0.0; }
+                        for (int i = 0; i < TE / 16; ++i) {           // 8 edges (K) per instruction = 2 chunks of 4; 5 per half tile
+                            const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(h * (TE / 8) + 2 * i) * (TN * 16);
+                            const uint64_t dah = make_desc(dvh + ao, COUT * 16, 128), dal = make_desc(dvl + ao, COUT * 16, 128);
+                            const uint64_t dbh = make_desc(ec_hi + bo, TN * 16, 128), dbl = make_desc(ec_lo + bo, TN * 16, 128);
+                            mma_tf32(d, dah, dbh, idesc_t, (u % FLUSH) > 0 || h > 0 || i > 0);
+                            mma_tf32(d, dal, dbh, idesc_t, true);
+                            mma_tf32(d, dah, dbl, idesc_t, true);
+                        }
+                        mma_commit(&bar_dvempty[h]);
+                        if (h == 1) {
+                            mma_commit(&bar_eempty[u % ERING]);
+                            if ((u + 1) % FLUSH == 0 || u == ntiles - 1) mma_commit(&bar_gfull[gb]);
+                        }
+                        ++nT;
+                        did = true;
+                    }
+                }
+                if (!did) __nanosleep(32);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue: channel c = 16 warp + lane on lanes 0..15 (the rows of an M = 64 accumulator); z -> dv1 -> operand tile
+        const int c = warp * 16 + (lane & 15);
+        const bool owner = lane < 16;
+        const float rc = __ldg(coef + COUT * COUT + c);
+        const uint32_t mbyte = (uint32_t)(c >> 2), bit = (uint32_t)(c & 3);
+        double* acc = reinterpret_cast<double*>(sm + off_acc) + c * ACCN;
+        unsigned char* dv_row = sm + off_dv + (c >> 3) * 128 + (c & 7) * 16;          // my row in a [64][40] K-major half tile
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
             mbar_wait(&bar_tfull[st], ph);
             fence_after_sync();
-            const long long g0 = g_begin + (long long)t * TE;
-            const int npts = (int)min((long long)PTS, (g_end - g0) / KNN);
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * Z_COL);
-            const unsigned char* stage = sm + off_stage0 + st * STAGE_BYTES + 2 * TILE_BYTES;
-            const float* s_d = reinterpret_cast<const float*>(stage);
-            const uint32_t* s_m = reinterpret_cast<const uint32_t*>(stage + D_BYTES);
+            const unsigned char* s_m = sm + off_e0 + (t % ERING) * ESTAGE_BYTES + 2 * EC_BYTES;
 #pragma unroll 1
-            for (int pp = 0; pp < npts; ++pp) {
+            for (int pp = 0; pp < PTS; ++pp) {
+                const int h = pp >> 1;                                  // half of the dv1 tile this point belongs to
+                if ((pp & 1) == 0) mbar_wait(&bar_dvempty[h], ((uint32_t)t & 1u) ^ 1u);      // the T MMAs of tile t - 1 are done with this half
                 float v[16], u[4];
                 tmem_ld16(taddr + (uint32_t)(pp * KNN), v);
                 tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
+                float dv[KNN];
 #pragma unroll
                 for (int k = 0; k < KNN; ++k) {
                     const int e = pp * KNN + k;
                     const float z = k < 16 ? v[k] : u[k - 16];
-                    const bool posv = (s_m[e * 2 + word] >> bit) & 1u;
-                    float dv = (rc - z) * (posv ? 1.f : SLOPE);          // meaningful on lanes 0..15 (accumulator rows)
-                    dv = __shfl_sync(SGB_FULL_MASK, dv, lane & 15);
-                    a0 += dv;
-                    const float4 d0 = *reinterpret_cast<const float4*>(s_d + e * DROW + half * 8);
-                    const float4 d1 = *reinterpret_cast<const float4*>(s_d + e * DROW + half * 8 + 4);
-                    const float d2 = s_d[e * DROW + 16 + half];
-                    tt[0] = fmaf(dv, d0.x, tt[0]); tt[1] = fmaf(dv, d0.y, tt[1]); tt[2] = fmaf(dv, d0.z, tt[2]); tt[3] = fmaf(dv, d0.w, tt[3]);
-                    tt[4] = fmaf(dv, d1.x, tt[4]); tt[5] = fmaf(dv, d1.y, tt[5]); tt[6] = fmaf(dv, d1.z, tt[6]); tt[7] = fmaf(dv, d1.w, tt[7]);
-                    tt[8] = fmaf(dv, d2, tt[8]);
+                    const bool posv = (s_m[e * 16 + mbyte] >> bit) & 1u;
+                    dv[k] = (rc - z) * (posv ? 1.f : SLOPE);            // padding edges: their EC column is zero, so any finite value is inert
+                }
+                if (owner) {
+#pragma unroll
+                    for (int q = 0; q < KNN / 4; ++q) {                   // 4 consecutive edges = one 16-byte chunk of row c
+                        const float4 d4 = make_float4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
+                        const float4 hi = make_float4(tf32_hi(d4.x), tf32_hi(d4.y), tf32_hi(d4.z), tf32_hi(d4.w));
+                        const float4 lo = make_float4(tf32_hi(d4.x - hi.x), tf32_hi(d4.y - hi.y), tf32_hi(d4.z - hi.z), tf32_hi(d4.w - hi.w));
+                        const uint32_t o = (uint32_t)(h * 2 * DVH_BYTES) + (uint32_t)((pp & 1) * (KNN / 4) + q) * (COUT * 16);
+                        *reinterpret_cast<float4*>(dv_row + o) = hi;
+                        *reinterpret_cast<float4*>(dv_row + o + DVH_BYTES) = lo;
+                    }
+                }
+                if (pp & 1) {                                           // half complete: hand it to the tensor cores
+                    fence_async_smem();                                 // generic-proxy writes -> tcgen05.mma operand reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_dvfull[h]);
                 }
             }
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&bar_tempty[st]); mbar_arrive(&bar_empty[st]); }
-            if ((t % FLUSH_TILES) == FLUSH_TILES - 1 || t == ntiles - 1) {
-                A0 += (double)a0; a0 = 0.f;
+            if (lane == 0) mbar_arrive(&bar_tempty[st]);
+            if ((t + 1) % FLUSH == 0 || t == ntiles - 1) {
+                // flush the finished T segment into the fp64 accumulators (thread = accumulator row)
+                const int seg = t / FLUSH, gb = seg & 1;
+                mbar_wait(&bar_gfull[gb], (uint32_t)(seg >> 1) & 1u);
+                fence_after_sync();
+                const uint32_t gaddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(T_COL0 + gb * T_COLS);
+                float g16[16], g4a[4], g4b[4];
+                tmem_ld16(gaddr, g16);
+                tmem_ld4(gaddr + 16, g4a);
+                tmem_ld4(gaddr + 20, g4b);
+                if (owner) {
 #pragma unroll
-                for (int i = 0; i < 9; ++i) { TT[i] += (double)tt[i]; tt[i] = 0.f; }
+                    for (int q = 0; q < 16; ++q) acc[q] += (double)g16[q];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[16 + q] += (double)g4a[q];      // columns 20..23 are structurally zero
+                    (void)g4b;
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_gempty[gb]);
             }
         }
         // part[cta][c][0] = A0, [1] = sum dv1 zhat1 = invstd1 * W1[c,:].T[c,:], [2 + t] = T[c][t]
-        double* dst = part + ((size_t)blockIdx.x * COUT + c) * NACC;
-        double dot = 0.0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const int tcol = i < 8 ? half * 8 + i : 16 + half;
-            dst[2 + tcol] = TT[i];
-            dot += (double)__ldg(W1 + c * CIN + tcol) * TT[i];
+        if (owner) {
+            double* dst = part + ((size_t)blockIdx.x * COUT + c) * NACC;
+            double dot = 0.0;
+            for (int i = 0; i < CIN; ++i) {
+                dst[2 + i] = acc[i];
+                dot += (double)__ldg(W1 + c * CIN + i) * acc[i];
+            }
+            dst[0] = acc[CIN];
+            dst[1] = (double)stats1[64 + c] * dot;
         }
-        dot += __shfl_xor_sync(SGB_FULL_MASK, dot, 16);
-        if (half == 0) { dst[0] = A0; dst[1] = (double)stats1[64 + c] * dot; }
     }
     fence_before_sync();
     __syncthreads();
