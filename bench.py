@@ -380,6 +380,23 @@ def main():
         model.cache_scenes = True
         extra["e2e_first_epoch"] = {"value": pts_per_step * 2 / (ms_cold * 1e-3), "unit": UNIT, "ms_per_step": ms_cold / 2,
                                     "what": "same plugin call with the HBM scene cache off: adj / unmap / seg CSR read from the on-disk binary cache and uploaded every step"}
+        # ---- loader-fed step (N2): a background thread reads the tree (binary CSR cache), collates the 8 scenes into pinned
+        # block-diagonal host arrays and the step uploads them — nothing cached in HBM, every input crosses PCIe every step
+        from seggroup_b200.loader import SceneShardLoader
+        n_ld = max(3, args.steps)
+        ld = iter(SceneShardLoader(model.scene_list, data_root=model.data_root, batch_size=B, cache_dir=model.scene_cache_dir,
+                                   prefetch=2, epochs=n_ld + 2))
+        ld_bytes = []
+
+        def step_loader():
+            hb = next(ld)
+            ld_bytes.append(hb.nbytes)
+            return float(step_resident(hb.to_device(dev)).item())
+        step_loader(); step_loader()
+        ms_ld, _ = timed(step_loader, n_ld)
+        extra["e2e_shard_loader"] = {"value": pts_per_step * n_ld / (ms_ld * 1e-3), "unit": UNIT, "ms_per_step": ms_ld / n_ld, "h2d_bytes_per_step": int(ld_bytes[-1]),
+                                     "what": "training step fed by seggroup_b200.loader.SceneShardLoader (prefetch thread, binary CSR cache, pinned collated "
+                                             "batch, 7 H2D copies per step, loss read back); no label files"}
         # ---- BASELINE configs[3] unit: 1 scene per GPU per step (the reference's own batch size, train.py:92)
         one = pipeline.SceneDevice.from_host(scenes_host[0])
         for _ in range(2):

@@ -388,6 +388,27 @@ int sgb_kpconv_bwd(const float* g, const float* query_points, const float* suppo
                    int K, float KP_extent, int influence, int closest, float* gfeat, float* gK,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* N3  deformable KPConv: replaces kpconv/kernels/convolution_ops.py:371-493 `KPConv_deform_ops`.
+ * offsets [n,K,3]: per-query kernel-point displacements (the deformed kernel points are K_points + offsets[i]); modulations [n,K]
+ * or NULL.  A neighbour farther than KP_extent from EVERY deformed kernel point is dropped (the reference compacts the neighbour
+ * rows to the in-range ones, :426-445), 'constant' influence is the indicator d^2 < KP_extent^2, the per-kernel-point weighted
+ * features are scaled by the modulations (:485-486).  With offsets == NULL these ARE sgb_kpconv_fwd / sgb_kpconv_bwd.
+ * bwd additionally writes goffsets [n,K,3] and gmodulations [n,K] (overwritten). */
+int sgb_kpconv_deform_fwd(const float* query_points, const float* support_points, const int* neighbors, const float* features,
+                          const float* K_points, const float* offsets, const float* modulations, const float* K_values,
+                          int n, int n0, int W, int Cin, int Cout, int K, float KP_extent, int influence, int closest,
+                          float* out, void* stream);
+int sgb_kpconv_deform_bwd(const float* g, const float* query_points, const float* support_points, const int* neighbors,
+                          const float* features, const float* K_points, const float* offsets, const float* modulations,
+                          const float* K_values, int n, int n0, int W, int Cin, int Cout, int K, float KP_extent, int influence,
+                          int closest, float* gfeat, float* gK, float* goffsets, float* gmodulations,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* N3  'fitting' regulariser of the deformable layers (kpconv/models/KPFCNN_model.py:242-266): arg [n,K] = column of the neighbour row
+ * closest to every deformed kernel point (first minimum; shadow entries count as a point at 1000, convolution_ops.py:405). */
+int sgb_deform_closest_neighbor(const float* query_points, const float* support_points, const int* neighbors, const float* K_points,
+                                const float* offsets, int n, int n0, int W, int K, int* arg, void* stream);
+
 /* a20 on the tensor cores: same contract as sgb_kpconv_fwd, with the [n, K*Cin] x [K*Cin, Cout] contraction of
  * convolution_ops.py:240-247 on tcgen05 (kind::tf32, TF32 x 3 split: fp32-level accuracy, 1e-4 relative holds).
  * Shapes: Cin multiple of 32, Cout multiple of 16 and <= 256, W <= 64, K <= 32 (sgb_kpconv_tc_supported -> 1);

@@ -10,7 +10,8 @@ reference block names to the classes.  All point-sized work runs in the library 
     KPConv (gather + influence + K x Cin x Cout contraction)   sgb_kpconv_fwd / _bwd  (tcgen05 contraction)
     ind_max_pool / closest_pool                                sgb_ind_max_pool_* / sgb_closest_pool_*
 
-and the [n, Cin] x [Cin, Cout] unary convolutions + batch norm are library GEMMs / torch ops on the device.  There is no
+    unary convolutions [n, Cin] x [Cin, Cout]                  sgb_linear_tf32x3 (tcgen05, TF32 x 3), forward and backward
+and batch norm / LeakyReLU are elementwise torch ops on the device.  There is no
 CPU path (the operators reject non-CUDA tensors).  Kernel-point dispositions are an explicit input (`config.K_points`,
 [K,3] for unit K_radius; the reference regenerates them with an unseeded optimisation): they are scaled by
 K_radius = 1.5 * extent exactly as convolution_ops.py:124-131 does.
@@ -72,7 +73,7 @@ class UnaryBlock(nn.Module):
         self.bn = BatchNorm(fdim, config.use_batch_norm, config.batch_norm_momentum)
 
     def forward(self, layer_ind, inputs, features, radius, config, training=True):
-        return leaky_relu(self.bn(features @ self.w, training))
+        return leaky_relu(self.bn(KO.unary_convolution(features, self.w), training))
 
 
 class SimpleBlock(nn.Module):
@@ -116,20 +117,63 @@ class ResnetbBlock(nn.Module):
             self.shortcut_w = None
 
     def forward(self, layer_ind, inputs, features, radius, config, training=True):
-        x = leaky_relu(self.conv1_bn(features @ self.conv1_w, training))
+        x = leaky_relu(self.conv1_bn(KO.unary_convolution(features, self.conv1_w), training))
         if self.strided:
             q, s, idx = inputs['points'][layer_ind + 1], inputs['points'][layer_ind], inputs['pools'][layer_ind]
         else:
             q, s, idx = inputs['points'][layer_ind], inputs['points'][layer_ind], inputs['neighbors'][layer_ind]
         x = leaky_relu(self.conv2_bn(kp_conv(q, s, idx, x, self.conv2_w, radius, config), training))
-        x = self.conv3_bn(x @ self.conv3_w, training)
+        x = self.conv3_bn(KO.unary_convolution(x, self.conv3_w), training)
         shortcut = KO.ind_max_pool(features, inputs['pools'][layer_ind]) if self.strided else features
         if self.shortcut_w is not None:
-            shortcut = self.shortcut_bn(shortcut @ self.shortcut_w, training)
+            shortcut = self.shortcut_bn(KO.unary_convolution(shortcut, self.shortcut_w), training)
         return leaky_relu(x + shortcut)
 
 
 class ResnetbStridedBlock(ResnetbBlock):
+    strided = True
+
+
+class ResnetbDeformableBlock(ResnetbBlock):
+    """`resnetb_deformable_block` (393-440) / `resnetb_deformable_strided_block` (641-692): the bottleneck block whose middle
+    convolution is a deformable KPConv (convolution_ops.py:252-493).  Extra variables, as the reference creates them (zeros):
+    `conv2_offset_w` [K, fdim/2, 3K (+K if modulated)] and `conv2_offset_b`.  The offsets of the last forward are kept in
+    `self.last_offsets` (with the operands of the layer) for the 'fitting' regulariser, `offsets_loss()`."""
+
+    def __init__(self, in_dim, fdim, config):
+        super().__init__(in_dim, fdim, config)
+        K = config.num_kernel_points
+        odim = (4 if getattr(config, "modulated", False) else 3) * K
+        self.conv2_offset_w = nn.Parameter(torch.zeros(K, fdim // 2, odim))
+        self.conv2_offset_b = nn.Parameter(torch.zeros(odim))
+        self.last_offsets = None
+
+    def forward(self, layer_ind, inputs, features, radius, config, training=True):
+        x = leaky_relu(self.conv1_bn(KO.unary_convolution(features, self.conv1_w), training))
+        if self.strided:
+            q, s, idx = inputs['points'][layer_ind + 1], inputs['points'][layer_ind], inputs['pools'][layer_ind]
+        else:
+            q, s, idx = inputs['points'][layer_ind], inputs['points'][layer_ind], inputs['neighbors'][layer_ind]
+        extent = config.KP_extent * radius / config.density_parameter
+        K_points = config.K_points.to(features.device, torch.float32) * (1.5 * extent)
+        x, offsets = KO.KPConv_deformable(q, s, idx, x, self.conv2_w, self.conv2_offset_w, self.conv2_offset_b, fixed=config.fixed_kernel_points,
+                                          KP_extent=extent, KP_influence=config.KP_influence, aggregation_mode=config.convolution_mode,
+                                          modulated=getattr(config, "modulated", False), K_points=K_points)
+        self.last_offsets = (q, s, idx, K_points, offsets, extent)
+        x = leaky_relu(self.conv2_bn(x, training))
+        x = self.conv3_bn(KO.unary_convolution(x, self.conv3_w), training)
+        shortcut = KO.ind_max_pool(features, inputs['pools'][layer_ind]) if self.strided else features
+        if self.shortcut_w is not None:
+            shortcut = self.shortcut_bn(KO.unary_convolution(shortcut, self.shortcut_w), training)
+        return leaky_relu(x + shortcut)
+
+    def offsets_loss(self, loss_type="fitting"):
+        """KPFCNN_model.py:218-286 for this layer (multiply by config.offsets_decay and add to the training loss)."""
+        q, s, idx, K_points, offsets, extent = self.last_offsets
+        return KO.deformable_offsets_loss(q, s, idx, K_points, offsets, extent, loss_type)
+
+
+class ResnetbDeformableStridedBlock(ResnetbDeformableBlock):
     strided = True
 
 
@@ -155,12 +199,14 @@ class NearestUpsampleBlock(nn.Module):
 
 _BLOCKS = {
     'unary': UnaryBlock, 'simple': SimpleBlock, 'simple_strided': SimpleStridedBlock, 'resnetb': ResnetbBlock,
-    'resnetb_strided': ResnetbStridedBlock, 'max_pool': MaxPoolBlock, 'nearest_upsample': NearestUpsampleBlock,
+    'resnetb_strided': ResnetbStridedBlock, 'max_pool': MaxPoolBlock, 'max_pool_wide': MaxPoolBlock, 'nearest_upsample': NearestUpsampleBlock,
+    'resnetb_deformable': ResnetbDeformableBlock, 'resnetb_deformable_strided': ResnetbDeformableStridedBlock,
 }
 
 
 def get_block_ops(block_name):
-    """network_blocks.py:951-1015 for the rigid blocks; the deformable / inception variants are SURVEY.md 8f row N3."""
+    """network_blocks.py:951-1015 for the rigid blocks and the deformable bottleneck blocks of the ScanNet architecture
+    (training_Scannet.py:78-98); the inception / `_v2` development variants are not built."""
     if block_name not in _BLOCKS:
         raise ValueError('Unknown block name in the architecture definition : ' + block_name)
     return _BLOCKS[block_name]

@@ -96,6 +96,37 @@ def ordered_neighbors(queries, supports, radius):
     return batch_ordered_neighbors(queries, supports, None, None, radius)
 
 
+# ------------------------------------------------------------------------------------------------ unary convolution
+class _UnaryConvFn(torch.autograd.Function):
+    """`conv_ops.unary_convolution(features, w)` = features @ w (kpconv/kernels/convolution_ops.py:58-66, used by every unary /
+    resnetb block, network_blocks.py:176-188, 290-337) on the tcgen05 tensor cores (TF32 x 3: fp32-level accuracy), forward and
+    both backward products."""
+    @staticmethod
+    def forward(ctx, x, w):
+        from . import ops
+        ctx.save_for_backward(x, w)
+        return ops.linear_tf32x3(x, w.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        dx = ops.linear_tf32x3(g, w)                                   # [n,Cout] x [Cin,Cout]^T
+        n = x.shape[0]
+        pad = (-n) % 4
+        xt, gt = x.t(), g.t()
+        if pad:
+            xt, gt = torch.nn.functional.pad(xt, (0, pad)), torch.nn.functional.pad(gt, (0, pad))
+        dw = ops.linear_tf32x3(xt.contiguous(), gt.contiguous())      # [Cin,n] x [Cout,n]^T, split over n inside
+        return dx, dw
+
+
+def unary_convolution(features, w):
+    _chk(features, F32, "features")
+    return _UnaryConvFn.apply(features, w)
+
+
 # ------------------------------------------------------------------------------------------------ B4
 class _KPConvFn(torch.autograd.Function):
     @staticmethod
@@ -144,6 +175,107 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
     idx = _chk(idx.contiguous(), I32, "neighbors_indices")
     return _KPConvFn.apply(q, s, idx, features.contiguous(), _chk(K_points.contiguous(), F32, "K_points"), K_values.contiguous(),
                            KP_extent, _INFLUENCE[KP_influence], int(aggregation_mode == "closest"), bool(tensor_cores))
+
+
+# ------------------------------------------------------------------------------------------------ N3 deformable KPConv
+class _KPConvDeformFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, s, idx, feats, kpts, offsets, mods, kvals, extent, influence, closest):
+        n, n0 = q.shape[0], s.shape[0]
+        K, Cin, Cout = kvals.shape
+        out = torch.empty(n, Cout, dtype=F32, device=q.device)
+        _lib.call("sgb_kpconv_deform_fwd", q, s, idx, feats, kpts, offsets, mods, kvals, n, n0, idx.shape[1], Cin, Cout, K, float(extent),
+                  influence, closest, out, _stream())
+        ctx.save_for_backward(q, s, idx, feats, kpts, offsets, kvals, mods if mods is not None else q.new_empty(0))
+        ctx.cfg = (float(extent), influence, closest, mods is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, s, idx, feats, kpts, offsets, kvals, mods = ctx.saved_tensors
+        extent, influence, closest, has_mod = ctx.cfg
+        n, n0 = q.shape[0], s.shape[0]
+        K, Cin, Cout = kvals.shape
+        dev = q.device
+        gf = torch.zeros(n0, Cin, dtype=F32, device=dev)
+        gk = torch.zeros(K, Cin, Cout, dtype=F32, device=dev)
+        go = torch.zeros(n, K, 3, dtype=F32, device=dev)
+        gm = torch.zeros(n, K, dtype=F32, device=dev) if has_mod else None
+        ws = _ws(_lib.call("sgb_kpconv_bwd_ws_bytes", n, Cin, Cout, K), dev)
+        _lib.call("sgb_kpconv_deform_bwd", g.contiguous(), q, s, idx, feats, kpts, offsets, mods if has_mod else None, kvals, n, n0, idx.shape[1],
+                  Cin, Cout, K, extent, influence, closest, gf, gk, go, gm, ws, ws.numel(), _stream())
+        return None, None, None, gf, None, go, gm, gk, None, None, None
+
+
+def KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations, K_values, KP_extent,
+                      KP_influence, mode):
+    """kpconv/kernels/convolution_ops.py:371-493, same argument order; differentiable w.r.t. features, offsets, modulations, K_values."""
+    if KP_influence not in _INFLUENCE:
+        raise ValueError('Unknown influence function type (config.KP_influence)')
+    if mode not in ("sum", "closest"):
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    q = _chk(query_points.contiguous(), F32, "query_points"); s = _chk(support_points.contiguous(), F32, "support_points")
+    idx = neighbors_indices
+    if idx.dtype != I32:
+        idx = idx.to(I32)
+    idx = _chk(idx.contiguous(), I32, "neighbors_indices")
+    return _KPConvDeformFn.apply(q, s, idx, features.contiguous(), _chk(K_points.contiguous(), F32, "K_points"), offsets.contiguous(),
+                                 modulations.contiguous() if modulations is not None else None, K_values.contiguous(), KP_extent,
+                                 _INFLUENCE[KP_influence], int(mode == "closest"))
+
+
+def KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values, K_values0, b0, fixed='center', KP_extent=1.0,
+                      KP_influence='linear', aggregation_mode='sum', modulated=False, K_points=None):
+    """kpconv/kernels/convolution_ops.py:252-368: a rigid KPConv with its own weights K_values0 [K,Cin,3K (+K)] and bias b0 produces
+    the kernel-point offsets (in units of KP_extent) and, if `modulated`, 2*sigmoid modulations; the deformed convolution uses K_values.
+    K_values0 / b0 are the reference's `offset_conv_weights` / `offset_conv_bias` variables (created as zeros there, :321-322);
+    K_points is an explicit input as in `KPConv`.  Returns (features, offsets) — the offsets feed the 'fitting' regulariser."""
+    if K_points is None:
+        raise ValueError("K_points must be given: kernel-point dispositions are an input of the op (SURVEY.md 8c)")
+    n_kp = K_values.shape[0]
+    odim = K_values0.shape[2]
+    pad = (-odim) % 4                      # the kernels take output widths that are multiples of 4: 3K = 45 -> 48 zero columns, sliced off again
+    kv0 = torch.nn.functional.pad(K_values0, (0, pad)) if pad else K_values0
+    f0 = KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, kv0, KP_extent, KP_influence, aggregation_mode)
+    f0 = (f0[:, :odim] if pad else f0) + b0
+    if modulated:
+        offsets = f0[:, :3 * n_kp].reshape(-1, n_kp, 3)
+        modulations = 2 * torch.sigmoid(f0[:, 3 * n_kp:])
+    else:
+        offsets = f0.reshape(-1, n_kp, 3)
+        modulations = None
+    offsets = offsets * KP_extent
+    out = KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations, K_values, KP_extent,
+                            KP_influence, aggregation_mode)
+    return out, offsets
+
+
+def deformable_offsets_loss(query_points, support_points, neighbors_indices, K_points, offsets, KP_extent, loss_type="fitting"):
+    """The offset regulariser of ONE deformable layer, kpconv/models/KPFCNN_model.py:218-286 (before `offsets_decay`):
+    'fitting'   : mean over (query, kernel point) of the squared distance from the deformed kernel point to its closest neighbour,
+                  in units of KP_extent^2 (:249-266), plus the repulsive terms sum_i mean_n sum_{j != i} max(0, 1.5 - |kp_i - kp_j| / extent)^2
+                  with the other points held constant (:268-286);
+    'permissive': mean of max(0, |kp| / extent - 1) (:226-239).
+    The arg-min over the neighbour row is a kernel (sgb_deform_closest_neighbor); the differentiable part is elementwise torch."""
+    q = _chk(query_points.contiguous(), F32, "query_points"); s = _chk(support_points.contiguous(), F32, "support_points")
+    idx = neighbors_indices.to(I32).contiguous()
+    kp = _chk(K_points.contiguous(), F32, "K_points")
+    n, K = offsets.shape[0], kp.shape[0]
+    dkp = offsets + kp                                                                       # deformed_KP, convolution_ops.py:418
+    if loss_type == "permissive":
+        return torch.clamp(torch.linalg.norm(dkp / KP_extent, dim=2) - 1.0, min=0.0).mean()
+    if loss_type != "fitting":
+        raise ValueError('Unknown offset loss')
+    arg = torch.empty(n, K, dtype=I32, device=q.device)
+    _lib.call("sgb_deform_closest_neighbor", q, s, idx, kp, offsets.detach().contiguous(), n, s.shape[0], idx.shape[1], K, arg, _stream())
+    s_ext = torch.cat([s, torch.full((1, 3), 1000.0, dtype=F32, device=q.device)])
+    nb = torch.gather(idx.long().clamp(min=0, max=s.shape[0]), 1, arg.long())               # [n,K] support ids (shadow = n0)
+    rel = s_ext[nb] - q.unsqueeze(1)                                                         # [n,K,3]
+    fit = (((rel - dkp) ** 2).sum(2) / (KP_extent ** 2)).mean()
+    locs = dkp / KP_extent
+    dist = torch.sqrt(((locs.detach().unsqueeze(1) - locs.unsqueeze(2)) ** 2).sum(3) + torch.eye(K, device=q.device) * 1e30)   # [n,i,j], j held constant
+    rep = (torch.clamp(1.5 - dist, min=0.0) ** 2).sum(2).mean(0).sum()
+    return fit + rep
 
 
 def KPConv(query_points, support_points, neighbors_indices, features, K_values, fixed='center', KP_extent=1.0,

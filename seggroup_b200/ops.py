@@ -471,7 +471,7 @@ def gemm_tf32x3(A, B, relu=False):
     N = B.shape[0]
     if B.shape[1] != K:
         raise ValueError("A [M,K] and B [N,K] must share K")
-    if not relu and M <= 256 and K >= 1024:
+    if not relu and M <= 512 and K >= 1024:
         # tall contraction (weight gradient): one CTA per 128 rows would walk K alone -> split K over the grid, sum the slabs in order
         kps = max(128, ((K // 96) + 31) // 32 * 32)
         ns = (K + kps - 1) // kps
@@ -481,3 +481,23 @@ def gemm_tf32x3(A, B, relu=False):
     C = torch.empty(M, N, dtype=F32, device=A.device)
     _lib.call("sgb_linear_tf32x3", A, B, C, M, N, K, int(bool(relu)), _stream())
     return C
+
+
+def linear_tf32x3(x, Wt):
+    """y [n,Cout] = x [n,Cin] @ Wt [Cout,Cin]^T for any Cout / Cin: the tcgen05 GEMM takes N <= 256 (multiple of 16) and K % 4 == 0,
+    so wide outputs are produced in column panels of 256 and odd inner / outer sizes are zero-padded."""
+    n, cin = x.shape
+    cout = Wt.shape[0]
+    kp = (-cin) % 4
+    if kp:
+        x = torch.nn.functional.pad(x, (0, kp)); Wt = torch.nn.functional.pad(Wt, (0, kp))
+    x = x.contiguous()
+    outs = []
+    for c0 in range(0, cout, 256):
+        w = Wt[c0:c0 + 256]
+        npad = (-w.shape[0]) % 16
+        if npad:
+            w = torch.nn.functional.pad(w, (0, 0, 0, npad))
+        y = gemm_tf32x3(x, w.contiguous())
+        outs.append(y[:, :y.shape[1] - npad] if npad else y)
+    return outs[0] if len(outs) == 1 else torch.cat(outs, 1)

@@ -34,6 +34,8 @@ def test_block_registry_and_variable_shapes():
     assert shapes["shortcut_w"] == (64, 128)
     assert B.get_block_ops("resnetb")(128, 64, c).shortcut_w is None                  # in_dim == 2 fdim: identity shortcut
     assert B.get_block_ops("simple")(4, 32, c).w.shape == (15, 4, 32)
+    d = B.get_block_ops("resnetb_deformable_strided")(64, 64, c)                      # N3: offset convolution variables (zeros, as the reference)
+    assert tuple(d.conv2_offset_w.shape) == (15, 32, 45) and tuple(d.conv2_offset_b.shape) == (45,) and float(d.conv2_offset_w.abs().sum()) == 0
     bn = b.conv1_bn.bn
     assert bn.eps == 1e-6 and abs(bn.momentum - 0.01) < 1e-12                         # TF momentum 0.99
     c.use_batch_norm = False

@@ -119,3 +119,25 @@ def test_executor_fused_batch_matches_stream_executor():
     assert torch.isfinite(la) and torch.isfinite(lb)
     for k in ga:
         assert p[k].grad is not None and p[k].grad.shape == ga[k].shape
+
+
+def test_shard_loader_batch_runs_like_resident_batch(tmp_path):
+    """N2: a batch collated by the shard loader from the on-disk tree (pinned host arrays, ids already offset) gives the labels of
+    the same scenes uploaded one by one and concatenated on the device."""
+    import os
+    from seggroup_b200 import pipeline, synth
+    from seggroup_b200.loader import SceneShardLoader
+    scenes = [synth.make_scene(61 + i, 6000 + 250 * i, name="lg_%d" % i) for i in range(3)]
+    synth.write_scene_tree(str(tmp_path), scenes)
+    root = os.path.join(str(tmp_path), "dataset", "scannet")
+    names = open(os.path.join(root, "scannetv2_train.txt")).readlines()
+    hb = next(iter(SceneShardLoader(names, data_root=root, batch_size=3, cache_dir=os.path.join(str(tmp_path), "c"))))
+    assert hb.data.is_pinned()
+    p = _params(False)
+    with torch.no_grad():
+        a = pipeline.forward_scene(hb.to_device("cuda"), p, mode="ins_infer")
+        b = pipeline.forward_scene(pipeline.SceneDevice.concat([pipeline.SceneDevice.from_host(s) for s in scenes]), p, mode="ins_infer")
+    for k, v in b.labels.items():
+        assert torch.equal(a.labels[k], v), k
+    for x, y in zip(a.metrics_scenes, b.metrics_scenes):
+        assert all(torch.equal(u, w) for u, w in zip(x, y))

@@ -348,3 +348,131 @@ def test_kpconv_input_pipeline_matches_restatement():
     assert torch.equal(KI.get_batch_inds(cu(batches[0][3], torch.int32)).cpu(), torch.as_tensor(batches[0][4]))
     eq = KI.stack_batch_inds(torch.tensor([4, 4, 4], dtype=torch.int32, device="cuda")).cpu().numpy()
     assert np.array_equal(eq, K.stack_batch_inds([4, 4, 4])) and eq.shape == (3, 5)
+
+
+# ---- golden vectors minted by executing the unmodified reference on the TensorFlow stand-in (oracle/make_golden_kpconv.py) ----------
+def _golden():
+    import os
+    from oracle import make_golden_kpconv as M
+    g = M.geometry()
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return M, g, M.ops_inputs(g), np.load(os.path.join(gd, "kpconv_ref_ops.npz")), np.load(os.path.join(gd, "kpconv_ref_blocks.npz"))
+
+
+def _close(a, b, tol):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-12)
+
+
+def test_kpconv_ops_and_pools_match_reference_vectors():
+    """a20 / a21 against the reference itself (fixtures from the unmodified convolution_ops.py / network_blocks.py): KPConv_ops in the six
+    influence x aggregation modes (SIMT fp32 and tcgen05 paths), ind_max_pool, closest_pool — outputs and gradients, 1e-4 relative."""
+    from seggroup_b200.kpconv_ops import KPConv_ops, closest_pool, ind_max_pool
+    M, g, x, gold, _ = _golden()
+    for infl, mode in M.OPS_MODES:
+        for tc in (False, True):
+            f, kv = cu(x["feats"]).requires_grad_(True), cu(x["kv"]).requires_grad_(True)
+            y = KPConv_ops(cu(x["q"]), cu(x["s"]), cu(x["idx"]), f, cu(x["kp"]), kv, float(x["extent"]), infl, mode, tensor_cores=tc)
+            (y * cu(x["go"])).sum().backward()
+            tag = "ops/%s_%s/" % (infl, mode)
+            assert _close(y, gold[tag + "out"], 1e-4), (tag, tc)
+            assert _close(f.grad, gold[tag + "dfeats"], 1e-4) and _close(kv.grad, gold[tag + "dkv"], 1e-4), (tag, tc)
+    for name, fn, idx, src in (("ind_max_pool", ind_max_pool, x["idx"], x["feats"]), ("closest_pool", closest_pool, g["up0"], x["go"][:, :16])):
+        f = cu(np.ascontiguousarray(src)).requires_grad_(True)
+        y = fn(f, cu(idx))
+        (y * cu(gold[name + "/go"].astype(np.float32))).sum().backward()
+        assert _close(y, gold[name + "/out"], 1e-6) and _close(f.grad, gold[name + "/dx"], 1e-5), name
+
+
+def test_deformable_kpconv_matches_reference_vectors():
+    """N3: KPConv_deform_ops (explicit offsets, +- modulations; linear / gaussian / constant / closest) and KPConv_deformable (offset
+    convolution -> deformed convolution) against the fixtures minted from the unmodified convolution_ops.py:252-493: outputs and the
+    gradients w.r.t. features, K_values, offsets, modulations, offset-convolution weights and bias."""
+    from seggroup_b200.kpconv_ops import KPConv_deform_ops, KPConv_deformable
+    M, g, x, gold, _ = _golden()
+    for infl, mode, modulated in [("linear", "sum", False), ("linear", "sum", True), ("gaussian", "sum", False), ("constant", "sum", False),
+                                  ("linear", "closest", False)]:
+        f, kv = cu(x["feats"]).requires_grad_(True), cu(x["kv"]).requires_grad_(True)
+        off = cu(x["offsets"]).requires_grad_(True)
+        mod = cu(x["modulations"]).requires_grad_(True) if modulated else None
+        y = KPConv_deform_ops(cu(x["q"]), cu(x["s"]), cu(x["idx"]), f, cu(x["kp"]), off, mod, kv, float(x["extent"]), infl, mode)
+        (y * cu(x["go"])).sum().backward()
+        tag = "deform_ops/%s_%s_%d/" % (infl, mode, int(modulated))
+        assert _close(y, gold[tag + "out"], 1e-4), tag
+        assert _close(f.grad, gold[tag + "dfeats"], 1e-4) and _close(kv.grad, gold[tag + "dkv"], 1e-4), tag
+        assert _close(off.grad, gold[tag + "doffsets"], 2e-4) or np.abs(gold[tag + "doffsets"]).max() == 0, tag
+        if np.abs(gold[tag + "doffsets"]).max() == 0:
+            assert float(off.grad.abs().max()) == 0.0, tag
+        if modulated:
+            assert _close(mod.grad, gold[tag + "dmod"], 1e-4), tag
+    for modulated in (False, True):
+        f, kv = cu(x["feats"]).requires_grad_(True), cu(x["kv"]).requires_grad_(True)
+        kv0 = cu(x["kv0m" if modulated else "kv0"]).requires_grad_(True)
+        b0 = cu(x["b0m" if modulated else "b0"]).requires_grad_(True)
+        y, _ = KPConv_deformable(cu(x["q"]), cu(x["s"]), cu(x["idx"]), f, kv, kv0, b0, KP_extent=float(x["extent"]), KP_influence="linear",
+                                 aggregation_mode="sum", modulated=modulated, K_points=cu(x["kp"]))
+        (y * cu(x["go"])).sum().backward()
+        tag = "deformable/%d/" % int(modulated)
+        assert _close(y, gold[tag + "out"], 1e-4), tag
+        for a, k in ((f.grad, "dfeats"), (kv.grad, "dkv"), (kv0.grad, "dkv0"), (b0.grad, "db0")):
+            assert _close(a, gold[tag + k], 3e-4), (tag, k)
+
+
+def test_kpfcnn_blocks_match_reference_vectors():
+    """N1 / N3: every block of network_blocks.py that the ScanNet architecture uses (training_Scannet.py:78-98: simple, resnetb,
+    resnetb_strided, resnetb_deformable, resnetb_deformable_strided, nearest_upsample, unary; + simple_strided, max_pool) in training
+    mode against the fixtures minted from the unmodified reference blocks: output 1e-4, gradients 1e-3 of their largest entry."""
+    from test_kpconv_reference_pin import _restatement_params
+    from seggroup_b200 import kpconv_blocks as B
+    M, g, x, _, gold = _golden()
+    cfg = M.config(g["kp_unit"])
+    inputs = {"points": [cu(g["p0"]), cu(g["p1"])], "neighbors": [cu(g["nb0"]), cu(g["nb1"])], "pools": [cu(g["pool0"])], "upsamples": [cu(g["up0"])]}
+    for name in M.BLOCKS:
+        li, fdim, radius, feats, V = M.block_case(name, g)
+        blk = B.get_block_ops(name)(feats.shape[1], fdim, cfg).cuda()
+        P = _restatement_params(name, V)
+        named = dict(blk.named_parameters())
+        assert set(P) == set(named), (name, sorted(P), sorted(named))
+        with torch.no_grad():
+            for k, v in P.items():
+                named[k].copy_(cu(v))
+        f = cu(feats).requires_grad_(True)
+        y = blk(li, inputs, f, radius, cfg, True)
+        tag = "block/%s/" % name
+        (y * cu(gold[tag + "go"].astype(np.float32))).sum().backward()
+        assert _close(y, gold[tag + "out"], 1e-4), name
+        assert _close(f.grad, gold[tag + "dfeats"], 1e-3), name
+        inv = {v2: k2 for k2, v2 in zip(V.keys(), _restatement_params(name, {k: k for k in V}).keys())}
+        for k, prm in named.items():
+            assert prm.grad is not None, (name, k)
+            assert _close(prm.grad, gold[tag + "d/" + inv[k]], 1e-3), (name, k)
+
+
+def test_deformable_offsets_loss():
+    """KPFCNN_model.py:218-286 ('fitting' and 'permissive' offset regularisers of one layer) against a brute-force torch fp64 evaluation."""
+    from seggroup_b200.kpconv_ops import deformable_offsets_loss
+    M, g, x, _, _ = _golden()
+    q, s, idx, kp = x["q"], x["s"], x["idx"], x["kp"]
+    ext = float(x["extent"])
+    off = cu(x["offsets"]).requires_grad_(True)
+    loss = deformable_offsets_loss(cu(q), cu(s), cu(idx), cu(kp), off, ext, "fitting")
+    loss.backward()
+    o64 = torch.tensor(x["offsets"], dtype=torch.float64, requires_grad=True)
+    s_ext = torch.cat([torch.tensor(s, dtype=torch.float64), torch.full((1, 3), 1000.0, dtype=torch.float64)])
+    nbr = s_ext[torch.tensor(idx).long()] - torch.tensor(q, dtype=torch.float64).unsqueeze(1)                 # [n,W,3]
+    dkp = o64 + torch.tensor(kp, dtype=torch.float64)
+    d2 = ((nbr.unsqueeze(2) - dkp.unsqueeze(1)) ** 2).sum(3)                                                    # [n,W,K]
+    fit = (d2.min(1)[0] / ext ** 2).mean()
+    locs = dkp / ext
+    rep = 0
+    for i in range(15):
+        other = torch.cat([locs[:, :i], locs[:, i + 1:]], 1).detach()
+        dist = torch.sqrt(((other - locs[:, i:i + 1]) ** 2).sum(2))
+        rep = rep + (torch.clamp(1.5 - dist, min=0) ** 2).sum(1).mean()
+    ref = fit + rep
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref))
+    assert _close(off.grad, o64.grad.numpy(), 1e-3)
+    perm = deformable_offsets_loss(cu(q), cu(s), cu(idx), cu(kp), off.detach(), ext, "permissive")
+    assert abs(float(perm) - float(torch.clamp(torch.linalg.norm(locs.detach(), dim=2) - 1, min=0).mean())) < 1e-5
