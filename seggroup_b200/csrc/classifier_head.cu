@@ -13,6 +13,7 @@
 namespace {
 constexpr int CH_IN = 256, CH_HID = 128, CH_OUT = 40;
 constexpr int CH_THREADS = 256;                 // 2 row groups x 128 hidden columns
+constexpr int CH_WS = CH_HID + 1;               // row stride of the transposed W1 tile: odd -> conflict-free transposed stores
 constexpr float CH_SLOPE = 0.2f, CH_BN_EPS = 1e-5f, CH_SMOOTH = 0.2f;
 
 __device__ __forceinline__ float ch_lrelu(float v) { return v > 0.f ? v : CH_SLOPE * v; }
@@ -42,8 +43,8 @@ cls_head_fwd_kernel(const float* __restrict__ feat, const int* __restrict__ g_of
                     const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ mask, float drop_scale,
                     float* __restrict__ hpre, float* __restrict__ stats, float* __restrict__ logits, float* __restrict__ loss_raw) {
     extern __shared__ __align__(16) float ch_smem[];
-    float* s_w1t = ch_smem;                              // [256][128]: W1 transposed
-    float* s_row = s_w1t + CH_IN * CH_HID;               // [2][256]
+    float* s_w1t = ch_smem;                              // [256][CH_WS]: W1 transposed
+    float* s_row = s_w1t + CH_IN * CH_WS;                // [2][256]
     float* s_h = s_row + 2 * CH_IN;                      // [2][128]
     float* s_lg = s_h + 2 * CH_HID;                      // [2][40]
     float* s_red = s_lg + 2 * CH_OUT;                    // [2][128]
@@ -52,7 +53,7 @@ cls_head_fwd_kernel(const float* __restrict__ feat, const int* __restrict__ g_of
     __shared__ float s_loss[2];
     const int b = blockIdx.x, tid = threadIdx.x, grp = tid >> 7, j = tid & 127;
     const int g0 = g_off[b], g1 = g_off[b + 1], I = g1 - g0;
-    for (int i = tid; i < CH_IN * CH_HID; i += CH_THREADS) { const int jj = i / CH_IN, k = i % CH_IN; s_w1t[k * CH_HID + jj] = __ldg(W1 + i); }
+    for (int i = tid; i < CH_IN * CH_HID; i += CH_THREADS) { const int jj = i / CH_IN, k = i % CH_IN; s_w1t[k * CH_WS + jj] = __ldg(W1 + i); }   // coalesced reads, stride-129 stores
     if (tid < 2) s_loss[tid] = 0.f;
     __syncthreads();
     // ---- Linear1 + column sums
@@ -66,7 +67,7 @@ cls_head_fwd_kernel(const float* __restrict__ feat, const int* __restrict__ g_of
             float acc = 0.f;
             const float* x = s_row + grp * CH_IN;
 #pragma unroll 8
-            for (int k = 0; k < CH_IN; ++k) acc = fmaf(x[k], s_w1t[k * CH_HID + j], acc);
+            for (int k = 0; k < CH_IN; ++k) acc = fmaf(x[k], s_w1t[k * CH_WS + j], acc);
             hpre[(size_t)r * CH_HID + j] = acc;
             csum += acc;
         }
@@ -227,7 +228,7 @@ cls_head_bwd_kernel(const float* __restrict__ feat, const int* __restrict__ g_of
     for (int i = tid; i < CH_HID * CH_IN; i += CH_THREADS) dW1p[(size_t)b * CH_HID * CH_IN + i] = s_dw1[i];
 }
 
-constexpr size_t CH_FWD_SMEM = (size_t)(CH_IN * CH_HID + 2 * CH_IN + 2 * CH_HID + 2 * CH_OUT + 2 * CH_HID + 2 * CH_HID) * sizeof(float);
+constexpr size_t CH_FWD_SMEM = (size_t)(CH_IN * CH_WS + 2 * CH_IN + 2 * CH_HID + 2 * CH_OUT + 2 * CH_HID + 2 * CH_HID) * sizeof(float);
 constexpr size_t CH_BWD_SMEM = (size_t)(CH_HID * CH_IN + 2 * CH_IN + 2 * CH_HID + 2 * CH_OUT + 4 * CH_HID) * sizeof(float);
 }  // namespace
 

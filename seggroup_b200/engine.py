@@ -122,7 +122,7 @@ class SceneExecutor:
                 return pipeline.forward_scene(sc, params, mode=mode)
         return self._run(fn, scenes)
 
-    def train_batch(self, scenes, params, train_keys, upload=None, fused=None):
+    def train_batch(self, scenes, params, train_keys, upload=None, fused=None, classifier=None):
         """Forward + backward of every scene; accumulates d(mean_i loss_i)/d(param) into `param.grad` (fixed scene
         order) and returns the mean loss (0-dim device tensor).  params: dict name -> tensor; train_keys: names
         of the leaves that require grad.
@@ -134,7 +134,7 @@ class SceneExecutor:
         if self.fused if fused is None else fused:
             batch = scenes if isinstance(scenes, pipeline.SceneDevice) else pipeline.SceneDevice.concat(
                 [upload(s) if upload is not None else s for s in scenes])
-            r = pipeline.forward_scene(batch, params, mode="train")
+            r = pipeline.forward_scene(batch, params, mode="train", classifier=classifier)
             loss = (r.loss_raw[:, 0] / r.loss_raw[:, 1]).mean()                 # mean over scenes of loss_sum / loss_num (train.py:165-170 + DDP)
             grads = torch.autograd.grad(loss, leaves, allow_unused=True)
             for pp, g in zip(leaves, grads):
@@ -146,14 +146,15 @@ class SceneExecutor:
                     pp.grad.add_(g)
             self.last_result = r
             return loss.detach()
-        n = len(scenes)
+        # items may themselves be scene batches (lanes of several scenes each): the mean is over ALL scenes
+        n = sum(getattr(sc, "n_scenes", 1) for sc in scenes)
         main = torch.cuda.current_stream(self.device)
 
         def fn(sc, i):
             if upload is not None:
                 sc = upload(sc)
-            r = pipeline.forward_scene(sc, params, mode="train")
-            loss = r.loss_raw[0, 0] / r.loss_raw[0, 1] / n
+            r = pipeline.forward_scene(sc, params, mode="train", classifier=classifier)
+            loss = (r.loss_raw[:, 0] / r.loss_raw[:, 1]).sum() / n
             grads = torch.autograd.grad(loss, leaves, allow_unused=True)
             for g in grads:
                 if g is not None:
