@@ -209,7 +209,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config 3 / config 4 / first-epoch legs")
     ap.add_argument("--shard-scenes", type=int, default=1201, help="config 3: scenes of the whole job (len(scannetv2_train.txt))")
-    ap.add_argument("--lanes", type=int, default=2, help="scene batches in flight per GPU: the batch is split into this many block-diagonal "
+    ap.add_argument("--lanes", type=int, default=1, help="scene batches in flight per GPU: the batch is split into this many block-diagonal "
                     "sub-batches, each driven by its own host thread / CUDA stream (1 = one batch on the caller's stream)")
     ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "off"], help="clock sampler during the timed region")
     ap.add_argument("--gc", default="frozen", choices=["frozen", "default"],

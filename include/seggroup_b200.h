@@ -115,9 +115,11 @@ int sgb_cluster_cloud_transform(const float* data6, const int* cloud_idx, int S,
 
 /* a8  replaces seggroup/model.py:429-436 `combine_centralized_pointcloud`:
  * x9[p] = (data6[p], xyz[p] - mean xyz of p's cluster). */
+size_t sgb_centralize_ws_bytes(int N, int S);
 int sgb_centralize(const float* data6, int N, const int* order, const int* cl_off, int S, float* x9,
-                   void* sum_ws /* 24*S bytes of scratch, 8-byte aligned: 64-bit fixed-point coordinate sums per cluster */,
-                   void* stream);
+                   void* ws /* sgb_centralize_ws_bytes(N, S), 8-byte aligned: 64-bit fixed-point coordinate sums per cluster
+                               + the cluster id of every point (pass 1 scatters it, pass 2 streams in point order) */,
+                   size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a5/a6  structural-layer MLP on the 64-point segment clouds
@@ -387,6 +389,19 @@ int sgb_kpconv_bwd(const float* g, const float* query_points, const float* suppo
                    const float* features, const float* K_points, const float* K_values, int n, int n0, int W, int Cin, int Cout,
                    int K, float KP_extent, int influence, int closest, float* gfeat, float* gK,
                    void* ws, size_t ws_bytes, void* stream);
+
+/* the same gradients with both contractions on tcgen05 (TF32 x 3, fp32 accumulation in TMEM; kpconv_bwd_tc.cu):
+ *   dK = WF^T g            persistent CTAs accumulate [K*Cin, Cout] in TMEM over all their 64-query tiles, partial sums reduced in a
+ *                          fixed order (deterministic);
+ *   dfeat += h_k * (g K_values[k]^T)   per 128-query tile and kernel point, scattered with coalesced red.global.add.
+ * Gradient of kpconv/kernels/convolution_ops.py:240-247.  _supported: Cin in {32,64,128}, Cout a multiple of 32 up to 128, K <= 32,
+ * W <= 64 (else use sgb_kpconv_bwd).  features, g and gfeat must be 16-byte aligned. */
+int sgb_kpconv_bwd_tc_supported(int n, int W, int Cin, int Cout, int K, int n0);
+size_t sgb_kpconv_bwd_tc_ws_bytes(int n, int Cin, int Cout, int K);
+int sgb_kpconv_bwd_tc(const float* g, const float* query_points, const float* support_points, const int* neighbors,
+                      const float* features, const float* K_points, const float* K_values, int n, int n0, int W, int Cin, int Cout,
+                      int K, float KP_extent, int influence, int closest, float* gfeat, float* gK,
+                      void* ws, size_t ws_bytes, void* stream);
 
 /* N3  deformable KPConv: replaces kpconv/kernels/convolution_ops.py:371-493 `KPConv_deform_ops`.
  * offsets [n,K,3]: per-query kernel-point displacements (the deformed kernel points are K_points + offsets[i]); modulations [n,K]

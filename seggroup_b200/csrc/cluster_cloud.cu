@@ -169,15 +169,17 @@ __global__ void cluster_cloud_transform_kernel(const float* __restrict__ data6, 
 constexpr double FIX_SCALE = 68719476736.0;           // 2^36
 __global__ void __launch_bounds__(256)
 cluster_sum_kernel(const float* __restrict__ data6, int N, const int* __restrict__ order, const int* __restrict__ cl_off, int S,
-                   long long* __restrict__ sums /*[S,3], zeroed*/) {
+                   long long* __restrict__ sums /*[S,3], zeroed*/, int* __restrict__ pt_cluster /*[N]: cluster of every POINT*/) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int q0 = q - lane;
     if (q0 >= N) return;
     const bool valid = q < N;
     long long fx = 0, fy = 0, fz = 0;
+    int pid = 0;
     if (valid) {
-        const float2* p = reinterpret_cast<const float2*>(data6 + (size_t)__ldg(order + q) * 6);
+        pid = __ldg(order + q);
+        const float2* p = reinterpret_cast<const float2*>(data6 + (size_t)pid * 6);
         const float2 a = __ldg(p);
         const float z = __ldg(reinterpret_cast<const float*>(p + 1));
         fx = __double2ll_rn((double)a.x * FIX_SCALE); fy = __double2ll_rn((double)a.y * FIX_SCALE); fz = __double2ll_rn((double)z * FIX_SCALE);
@@ -185,6 +187,7 @@ cluster_sum_kernel(const float* __restrict__ data6, int N, const int* __restrict
     int c = sgb_upper_segment(cl_off, S, q0);         // one search per warp, then a short forward walk
     const int c_first_end = __ldg(cl_off + c + 1);
     if (c_first_end >= min(q0 + 32, N)) {             // the whole warp lies in one cluster (the common case)
+        if (valid) pt_cluster[pid] = c;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             fx += __shfl_xor_sync(SGB_FULL_MASK, fx, o); fy += __shfl_xor_sync(SGB_FULL_MASK, fy, o); fz += __shfl_xor_sync(SGB_FULL_MASK, fz, o);
@@ -193,35 +196,54 @@ cluster_sum_kernel(const float* __restrict__ data6, int N, const int* __restrict
                                 (unsigned long long)(lane == 0 ? fx : lane == 1 ? fy : fz));
     } else if (valid) {
         while (c + 1 < S && q >= __ldg(cl_off + c + 1)) ++c;
+        pt_cluster[pid] = c;
         atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)c * 3 + 0), (unsigned long long)fx);
         atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)c * 3 + 1), (unsigned long long)fy);
         atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)c * 3 + 2), (unsigned long long)fz);
     }
 }
 
-__global__ void centralize_kernel(const float* __restrict__ data6, int N, const int* __restrict__ order,
-                                  const int* __restrict__ cl_off, int S, const long long* __restrict__ sums,
-                                  float* __restrict__ x9) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= N) return;
-    const int pid = __ldg(order + q);
-    const float2* p = reinterpret_cast<const float2*>(data6 + (size_t)pid * 6);      // rows are 24 B: 8-byte aligned
-    float* o = x9 + (size_t)pid * 9;
-    const float2 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
-    const float x = a.x, y = a.y, z = b.x;
-    // cluster of position q: ONE binary search per warp (lane 0's position, broadcast), then a short forward walk — the
-    // per-thread search was 12 dependent loads per point and throttled the load/store unit (ncu: lg_throttle)
-    int c = 0;
-    {
-        const int q0 = q - (threadIdx.x & 31);
-        c = sgb_upper_segment(cl_off, S, q0);
-        while (c + 1 < S && q >= __ldg(cl_off + c + 1)) ++c;
+// Second pass in POINT order: every global access is a full-width coalesced vector access.  The first pass left the cluster of
+// every point in pt_cluster (one 4-byte scatter per point instead of the nine strided scalar stores per point that the
+// position-ordered version of this kernel issued: ncu showed it bound by the load/store unit, l1tex 64 %, DRAM 6.5 %).  A CTA
+// stages its CZ_PTS input rows (24 B each) through shared memory with 16-byte loads, every thread builds the 9-float row of
+// one point in shared memory, and the CTA streams the 36-byte rows out with 16-byte stores.  The means are looked up through
+// the cluster tables (24 B sums + two offsets per cluster: a few hundred KB, L1/L2 resident).
+constexpr int CZ_PTS = 256;
+__global__ void __launch_bounds__(CZ_PTS)
+centralize_kernel(const float* __restrict__ data6, int N, const int* __restrict__ pt_cluster, const int* __restrict__ cl_off, int S,
+                  const long long* __restrict__ sums, float* __restrict__ x9) {
+    __shared__ __align__(16) float s_in[CZ_PTS * 6];
+    __shared__ __align__(16) float s_out[CZ_PTS * 9];
+    const int p0 = blockIdx.x * CZ_PTS, t = threadIdx.x;
+    const int np = min(CZ_PTS, N - p0);
+    const float* src = data6 + (size_t)p0 * 6;                   // CZ_PTS * 24 B per CTA: 16-byte aligned when data6 is
+    const bool vec = ((reinterpret_cast<uintptr_t>(data6) | reinterpret_cast<uintptr_t>(x9)) & 15) == 0;
+    if (vec && np == CZ_PTS) {
+        for (int i = t; i < CZ_PTS * 6 / 4; i += CZ_PTS) reinterpret_cast<float4*>(s_in)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    } else {
+        for (int i = t; i < np * 6; i += CZ_PTS) s_in[i] = __ldg(src + i);
     }
-    o[0] = x; o[1] = y; o[2] = z; o[3] = b.y; o[4] = cc.x; o[5] = cc.y;
-    const double inv = 1.0 / (FIX_SCALE * (double)(__ldg(cl_off + c + 1) - __ldg(cl_off + c)));
-    o[6] = x - (float)((double)__ldg(sums + (size_t)c * 3) * inv);
-    o[7] = y - (float)((double)__ldg(sums + (size_t)c * 3 + 1) * inv);
-    o[8] = z - (float)((double)__ldg(sums + (size_t)c * 3 + 2) * inv);
+    int c = 0;
+    if (t < np) c = pt_cluster[p0 + t];
+    if ((unsigned)c >= (unsigned)S) c = 0;                      // a point outside every cluster (order is not a full permutation): row undefined, as before
+    __syncthreads();
+    if (t < np) {
+        const float x = s_in[t * 6], y = s_in[t * 6 + 1], z = s_in[t * 6 + 2];
+        const double inv = 1.0 / (FIX_SCALE * (double)(__ldg(cl_off + c + 1) - __ldg(cl_off + c)));
+        float* o = s_out + t * 9;                                // stride 9 words: odd -> conflict-free
+        o[0] = x; o[1] = y; o[2] = z; o[3] = s_in[t * 6 + 3]; o[4] = s_in[t * 6 + 4]; o[5] = s_in[t * 6 + 5];
+        o[6] = x - (float)((double)__ldg(sums + (size_t)c * 3) * inv);
+        o[7] = y - (float)((double)__ldg(sums + (size_t)c * 3 + 1) * inv);
+        o[8] = z - (float)((double)__ldg(sums + (size_t)c * 3 + 2) * inv);
+    }
+    __syncthreads();
+    float* dst = x9 + (size_t)p0 * 9;                            // CZ_PTS * 36 B per CTA: 16-byte aligned when x9 is
+    if (vec && np == CZ_PTS) {
+        for (int i = t; i < CZ_PTS * 9 / 4; i += CZ_PTS) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_out)[i];
+    } else {
+        for (int i = t; i < np * 9; i += CZ_PTS) dst[i] = s_out[i];
+    }
 }
 }  // namespace
 
@@ -249,16 +271,23 @@ extern "C" int sgb_cluster_cloud_transform(const float* data6, const int* cloud_
     return SGB_OK;
 }
 
+/* scratch of sgb_centralize: 24 B of fixed-point sums per cluster + the cluster id of every point */
+extern "C" size_t sgb_centralize_ws_bytes(int N, int S) {
+    return (((size_t)(S > 0 ? S : 0) * 24 + 15) & ~(size_t)15) + (size_t)(N > 0 ? N : 0) * 4;
+}
+
 extern "C" int sgb_centralize(const float* data6, int N, const int* order, const int* cl_off, int S, float* x9,
-                              void* sum_ws /*24*S bytes*/, void* stream) {
+                              void* ws, size_t ws_bytes, void* stream) {
     if (N < 0 || S < 0) return SGB_ERR_INVALID;
     if (N == 0 || S == 0) return SGB_OK;
-    if (!data6 || !order || !cl_off || !x9 || !sum_ws) return SGB_ERR_INVALID;
+    if (!data6 || !order || !cl_off || !x9 || !ws || ((uintptr_t)ws & 7)) return SGB_ERR_INVALID;
+    if (ws_bytes < sgb_centralize_ws_bytes(N, S)) return SGB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    long long* sums = (long long*)sum_ws;
+    long long* sums = (long long*)ws;
+    int* pt_cluster = (int*)((unsigned char*)ws + (((size_t)S * 24 + 15) & ~(size_t)15));
     SGB_CUDA(cudaMemsetAsync(sums, 0, (size_t)S * 3 * sizeof(long long), st));
-    { cluster_sum_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, sums); SGB_COUNT_LAUNCH(); }
-    { centralize_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, sums, x9); SGB_COUNT_LAUNCH(); }
+    { cluster_sum_kernel<<<sgb_div_up(N, 256), 256, 0, st>>>(data6, N, order, cl_off, S, sums, pt_cluster); SGB_COUNT_LAUNCH(); }
+    { centralize_kernel<<<sgb_div_up(N, CZ_PTS), CZ_PTS, 0, st>>>(data6, N, pt_cluster, cl_off, S, sums, x9); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

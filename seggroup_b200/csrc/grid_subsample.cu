@@ -170,17 +170,35 @@ __global__ void gs_flag_first(const int* __restrict__ slot_of, const int* __rest
     if (i < N) flag[i] = tfirst[slot_of[i]] == i ? 1 : 0;
 }
 // rank = exclusive scan of flag.  first points publish voxel id / count of their slot, and count voxels per batch
-__global__ void gs_number_voxels(const int* __restrict__ slot_of, const int* __restrict__ flag, const int* __restrict__ rank, int N,
-                                 const int* __restrict__ tcount, int* __restrict__ tvox, int* __restrict__ vcount, int* __restrict__ vfirst,
-                                 const int* __restrict__ boff, int B, int* __restrict__ out_batches, int* __restrict__ counts) {
+// The per-batch voxel counts are aggregated warp -> CTA -> one global atomic per (CTA, batch element): with one atomicAdd per
+// voxel every first point of a cloud hit the SAME address (B = 1: 358k serialised atomics, 240 us of a 400 us entry in ncu).
+__global__ void __launch_bounds__(256)
+gs_number_voxels(const int* __restrict__ slot_of, const int* __restrict__ flag, const int* __restrict__ rank, int N,
+                 const int* __restrict__ tcount, int* __restrict__ tvox, int* __restrict__ vcount, int* __restrict__ vfirst,
+                 const int* __restrict__ boff, int B, int* __restrict__ out_batches, int* __restrict__ counts) {
+    __shared__ int s_cnt, s_b0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) counts[0] = rank[N];
-    if (i >= N || !flag[i]) return;
-    const int v = rank[i], s = slot_of[i];
-    tvox[s] = v;
-    vcount[v] = tcount[s];
-    vfirst[v] = i;
-    if (out_batches) atomicAdd(out_batches + sgb_upper_segment(boff, B, i), 1);
+    const bool first = i < N && flag[i];
+    if (first) {
+        const int v = rank[i], s = slot_of[i];
+        tvox[s] = v;
+        vcount[v] = tcount[s];
+        vfirst[v] = i;
+    }
+    if (!out_batches) return;                                  // kernel-uniform
+    if (threadIdx.x == 0) { s_cnt = 0; s_b0 = sgb_upper_segment(boff, B, min(i, N - 1)); }
+    __syncthreads();
+    const int b0 = s_b0;
+    // points are grouped by batch element, so almost every CTA lies inside one element: its first points are counted in
+    // shared memory; the few threads of a CTA that straddles a boundary fall back to a global atomic
+    int b = -1;
+    if (first) b = (i >= __ldg(boff + b0) && i < __ldg(boff + b0 + 1)) ? b0 : sgb_upper_segment(boff, B, i);
+    const unsigned m = __ballot_sync(SGB_FULL_MASK, b == b0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
+    if (b >= 0 && b != b0) atomicAdd(out_batches + b, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(out_batches + b0, s_cnt);
 }
 __global__ void gs_bucket(const int* __restrict__ slot_of, const int* __restrict__ tvox, int N, const int* __restrict__ voff,
                           int* __restrict__ cursor, int* __restrict__ list) {

@@ -32,21 +32,6 @@ constexpr int MAXK = 32;
 constexpr uint32_t NB_MASK = 0x03ffffffu;             // neighbour id in the low 26 bits, closest kernel point above
 enum { INFL_LINEAR = 0, INFL_CONSTANT = 1, INFL_GAUSSIAN = 2 };
 
-// byte offset of (row r, column c) in a K-major SWIZZLE_128B fp32 tile with R rows: 32-column blocks of R x 128 B, atoms of
-// 8 rows x 128 B whose 16-byte chunks are XOR-ed with the row (tile base 1024-byte aligned)
-__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int c, int R) {
-    return (uint32_t)((c >> 5) * (R * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 31) >> 2) ^ (r & 7)) << 4) + (c & 3) * 4);
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 struct Args {
     const float* q; const float* s; const int* idx; const float* feat; const float* kpts; const unsigned char* bimg; float* out;
     int n, n0, W, Cin, Cout, K, tmem_cols;

@@ -125,6 +125,31 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// byte offset of (row r, column c) in a K-major SWIZZLE_128B fp32 tile with R rows: 32-column blocks of R x 128 B, atoms of
+// 8 rows x 128 B whose 16-byte chunks are XOR-ed with the row (tile base 1024-byte aligned)
+__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int c, int R) {
+    return (uint32_t)((c >> 5) * (R * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 31) >> 2) ^ (r & 7)) << 4) + (c & 3) * 4);
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // packed fp32x2 fused multiply-add (Blackwell FFMA2): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}, each lane IEEE fma.rn
 __device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
     unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);

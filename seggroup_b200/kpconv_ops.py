@@ -144,6 +144,7 @@ class _KPConvFn(torch.autograd.Function):
             _lib.call("sgb_kpconv_fwd", q, s, idx, feats, kpts, kvals, n, n0, W, Cin, Cout, K, float(extent), influence, closest, out, _stream())
         ctx.save_for_backward(q, s, idx, feats, kpts, kvals)
         ctx.cfg = (float(extent), influence, closest)
+        ctx.use_tc = bool(use_tc)
         return out
 
     @staticmethod
@@ -154,9 +155,16 @@ class _KPConvFn(torch.autograd.Function):
         K, Cin, Cout = kvals.shape
         gf = torch.zeros(n0, Cin, dtype=F32, device=q.device)
         gk = torch.zeros(K, Cin, Cout, dtype=F32, device=q.device)
-        ws = _ws(_lib.call("sgb_kpconv_bwd_ws_bytes", n, Cin, Cout, K), q.device)
-        _lib.call("sgb_kpconv_bwd", g.contiguous(), q, s, idx, feats, kpts, kvals, n, n0, idx.shape[1], Cin, Cout, K, extent, influence, closest,
-                  gf, gk, ws, ws.numel(), _stream())
+        W = idx.shape[1]
+        if ctx.use_tc and n > 0 and _lib.call("sgb_kpconv_bwd_tc_supported", n, W, Cin, Cout, K, n0):
+            # both contractions (dK = WF^T g, GW = g K^T) on tcgen05, TF32 x 3; other shapes take the SIMT kernel
+            ws = _ws(_lib.call("sgb_kpconv_bwd_tc_ws_bytes", n, Cin, Cout, K), q.device)
+            _lib.call("sgb_kpconv_bwd_tc", g.contiguous(), q, s, idx, feats, kpts, kvals, n, n0, W, Cin, Cout, K, extent, influence, closest,
+                      gf, gk, ws, ws.numel(), _stream())
+        else:
+            ws = _ws(_lib.call("sgb_kpconv_bwd_ws_bytes", n, Cin, Cout, K), q.device)
+            _lib.call("sgb_kpconv_bwd", g.contiguous(), q, s, idx, feats, kpts, kvals, n, n0, W, Cin, Cout, K, extent, influence, closest,
+                      gf, gk, ws, ws.numel(), _stream())
         return None, None, None, gf, None, gk, None, None, None, None
 
 

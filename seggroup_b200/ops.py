@@ -113,8 +113,8 @@ def centralize(data6, order, cl_off):
     N = data6.shape[0]
     S = cl_off.numel() - 1
     x9 = torch.empty(N, 9, dtype=F32, device=data6.device)
-    sums = torch.empty(S, 3, dtype=torch.int64, device=data6.device)      # scratch: fixed-point coordinate sums
-    _lib.call("sgb_centralize", data6, N, order, cl_off, S, x9, sums, _stream())
+    nb = _lib.call("sgb_centralize_ws_bytes", N, S)                        # fixed-point coordinate sums + cluster id per point
+    _lib.call("sgb_centralize", data6, N, order, cl_off, S, x9, _ws(nb, data6.device), nb, _stream())
     return x9
 
 

@@ -170,6 +170,76 @@ def test_kpconv_tensor_core_contraction(cin, cout, wcap, influence, mode):
     assert float((out - simt).abs().max()) < 5e-5 * scale
 
 
+@pytest.mark.parametrize("cin,cout,wcap", [(64, 64, 64), (64, 64, 20), (32, 32, 40), (128, 64, 64), (64, 128, 48), (128, 128, 64), (32, 96, 33)])
+@pytest.mark.parametrize("influence,mode", [("linear", "sum"), ("gaussian", "sum"), ("linear", "closest"), ("constant", "sum")])
+def test_kpconv_tensor_core_backward(cin, cout, wcap, influence, mode):
+    """sgb_kpconv_bwd_tc (dK = WF^T g and GW = g K^T on tcgen05, TF32 x 3; gradient of convolution_ops.py:240-247) against the
+    fp64 restatement (1e-4 relative, north_star bar) and the fp32 SIMT backward; dK must be bit-reproducible."""
+    from oracle import kpconv_oracle as K
+    from seggroup_b200 import _lib
+    from seggroup_b200.kpconv_ops import KPConv_ops, batch_ordered_neighbors
+    pts, lens = cloud(7, 5000)
+    sub, _ = K.batch_grid_subsampling(pts, lens, 0.05)
+    qs, _ = K.batch_grid_subsampling(pts, lens, 0.07)          # a query count that is neither a multiple of 64 nor of 128
+    S, Q = cu(sub), cu(qs)
+    radius, extent = 0.14, 0.055
+    nb = batch_ordered_neighbors(Q, S, None, None, radius)[:, :wcap].contiguous()
+    assert (nb == len(sub)).any(), "the case must hold shadow neighbours"
+    assert _lib.call("sgb_kpconv_bwd_tc_supported", len(qs), nb.shape[1], cin, cout, 15, len(sub)) == 1
+    g = torch.Generator().manual_seed(cin * 1000 + cout + wcap)
+    kp = (torch.rand(15, 3, generator=g) * 2 - 1) * 0.08
+    kp[0] = 0
+    feats = torch.randn(len(sub), cin, generator=g)
+    kv = torch.randn(15, cin, cout, generator=g) * (1.0 / np.sqrt(cin * 15))
+    go = torch.randn(len(qs), cout, generator=g)
+
+    def grads(tc):
+        fd = feats.cuda().requires_grad_(True); kd = kv.cuda().requires_grad_(True)
+        out = KPConv_ops(Q, S, nb, fd, kp.cuda(), kd, extent, influence, mode, tensor_cores=tc)
+        launches = _lib.launch_count()
+        (out * go.cuda()).sum().backward()
+        return fd.grad, kd.grad, _lib.launch_count() - launches
+    gf, gk, nl = grads(True)
+    assert nl == 4                                              # dK kernel + ordered reduce + K_values image + dfeat kernel: the tcgen05 path ran
+    gf2, gk2, _ = grads(True)
+    assert torch.equal(gk, gk2)                                 # deterministic weight gradient
+    sf, sk, _ = grads(False)
+    f64 = feats.double().requires_grad_(True); k64 = kv.double().requires_grad_(True)
+    ref = K.kpconv_ops(Q.cpu(), S.cpu(), nb.cpu(), f64, kp, k64, extent, influence, mode, dtype=torch.float64)
+    (ref * go.double()).sum().backward()
+    fs, ks = float(f64.grad.abs().max()), float(k64.grad.abs().max())
+    assert float((gf.cpu().double() - f64.grad).abs().max()) < 1e-4 * fs
+    assert float((gk.cpu().double() - k64.grad).abs().max()) < 1e-4 * ks
+    assert float((gf - sf).abs().max()) < 5e-5 * fs and float((gk - sk).abs().max()) < 5e-5 * ks
+    assert float((gf - gf2).abs().max()) < 1e-5 * fs            # scatter-add order only
+
+
+def test_kpconv_tensor_core_backward_small_and_unsupported():
+    from oracle import kpconv_oracle as K
+    from seggroup_b200 import _lib
+    from seggroup_b200.kpconv_ops import KPConv_ops
+    assert _lib.call("sgb_kpconv_bwd_tc_supported", 1000, 65, 64, 64, 15, 1000) == 0     # rows wider than 64 neighbours
+    assert _lib.call("sgb_kpconv_bwd_tc_supported", 1000, 40, 5, 64, 15, 1000) == 0      # first-layer Cin
+    assert _lib.call("sgb_kpconv_bwd_tc_supported", 1000, 40, 64, 256, 15, 1000) == 0    # Cout > 128: SIMT backward
+    g = torch.Generator().manual_seed(5)
+    for n, n0, W, K_ in [(1, 7, 3, 15), (37, 50, 9, 15), (129, 300, 32, 13), (5, 40, 0, 15), (300, 200, 40, 1)]:
+        q = torch.rand(n, 3, generator=g) * 0.2
+        s = torch.rand(n0, 3, generator=g) * 0.2
+        nb = torch.randint(0, n0 + 3, (n, W), generator=g).clamp(max=n0).to(torch.int32)   # id n0 = shadow neighbour
+        kp = (torch.rand(K_, 3, generator=g) * 2 - 1) * 0.06
+        feats = torch.randn(n0, 64, generator=g)
+        kv = torch.randn(K_, 64, 32, generator=g) * 0.05
+        go = torch.randn(n, 32, generator=g)
+        fd = feats.cuda().requires_grad_(True); kd = kv.cuda().requires_grad_(True)
+        out = KPConv_ops(q.cuda(), s.cuda(), nb.cuda(), fd, kp.cuda(), kd, 0.08, "linear", "sum")
+        (out * go.cuda()).sum().backward()
+        f64 = feats.double().requires_grad_(True); k64 = kv.double().requires_grad_(True)
+        ref = K.kpconv_ops(q, s, nb, f64, kp, k64, 0.08, "linear", "sum", dtype=torch.float64)
+        (ref * go.double()).sum().backward()
+        assert float((fd.grad.cpu().double() - f64.grad).abs().max()) <= 1e-4 * max(float(f64.grad.abs().max()), 1e-6)
+        assert float((kd.grad.cpu().double() - k64.grad).abs().max()) <= 1e-4 * max(float(k64.grad.abs().max()), 1e-6)
+
+
 def test_kpconv_tensor_core_small_and_unsupported():
     from oracle import kpconv_oracle as K
     from seggroup_b200 import _lib

@@ -227,6 +227,15 @@ def main():
                     fd.grad = None; kd.grad = None
                     out.backward(go, retain_graph=True)
                 ms, mn = T(bwd)
+                emit(rows, "kpconv_bwd %dx%d tcgen05 (a20: dK = WF^T g, GW = g K^T, scatter)" % (cin, cout), M, ms, mn, flops=2 * fl, width=Wc)
+                fs = feats.clone().requires_grad_(True)
+                ks = kv.clone().requires_grad_(True)
+                outs = KO.KPConv_ops(sub, sub, nbc, fs, kp, ks, extent, "linear", "sum", tensor_cores=False)
+
+                def bwd_simt():
+                    fs.grad = None; ks.grad = None
+                    outs.backward(go, retain_graph=True)
+                ms, mn = T(bwd_simt)
                 emit(rows, "kpconv_bwd %dx%d fp32 SIMT (a20)" % (cin, cout), M, ms, mn, flops=2 * fl, width=Wc)
         if want("kppool"):
             # a21: strided-block shortcut pooling on the same geometry: pool the dl=0.04 features onto a dl=0.08 subsample
