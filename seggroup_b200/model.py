@@ -164,6 +164,7 @@ class SegModel(nn.Module):
         self._scene_cache = {}
         self._pending = []
         self._pinned_pool = {}
+        self._bn_cache = {}            # constant weights of the closed-form running-statistics update
         self._path_locks = {}
         self._io_lock = threading.Lock()
         self._copy_stream = None
@@ -197,7 +198,10 @@ class SegModel(nn.Module):
 
     def _update_bn(self, res):
         """Running-statistics update of training-mode BatchNorm (momentum 0.1, unbiased variance), one update per scene in
-        batch order; the buffers are never read (the reference never calls .eval()) but they are part of the checkpoint."""
+        batch order; the buffers are never read (the reference never calls .eval()) but they are part of the checkpoint.
+        The n sequential updates  r <- (1 - m) r + m x_b  are applied in closed form,
+            r <- (1 - m)^n r + sum_b m (1 - m)^(n-1-b) x_b,
+        i.e. three small launches per buffer instead of 2 n (the step is host-bound between the clustering levels)."""
         mods = {"mlp_1.bn1": self.mlp_1.bn1, "mlp_2.bn1": self.mlp_2.bn1, "mlp_3.bn1": self.mlp_3.bn1, "mlp_3.bn2": self.mlp_3.bn2,
                 "classifier.bn1": self.classifier.bn1}
         with torch.no_grad():
@@ -206,15 +210,23 @@ class SegModel(nn.Module):
                 if bn is None or not bn.training:
                     continue
                 m = bn.momentum
+                dev = var.device
                 if torch.is_tensor(counts):                            # classifier head: instance counts live on the device
-                    unbiased = var * (counts / (counts - 1).clamp(min=1)).unsqueeze(1)
+                    corr = counts / (counts - 1).clamp(min=1)
                     n = counts.numel()
                 else:
-                    unbiased = var * torch.tensor([c / max(c - 1, 1) for c in counts], dtype=var.dtype, device=var.device).unsqueeze(1)
                     n = len(counts)
-                for b in range(n):
-                    bn.running_mean.mul_(1 - m).add_(mean[b], alpha=m)
-                    bn.running_var.mul_(1 - m).add_(unbiased[b], alpha=m)
+                    key = ("corr", tuple(counts), str(dev))
+                    corr = self._bn_cache.get(key)
+                    if corr is None:
+                        corr = self._bn_cache[key] = torch.tensor([c / max(c - 1, 1) for c in counts], dtype=var.dtype, device=dev)
+                key = ("w", n, float(m), str(dev))
+                w = self._bn_cache.get(key)
+                if w is None:
+                    w = self._bn_cache[key] = torch.tensor([m * (1.0 - m) ** (n - 1 - b) for b in range(n)], dtype=var.dtype, device=dev)
+                keep = (1.0 - m) ** n
+                bn.running_mean.mul_(keep).add_(w @ mean)
+                bn.running_var.mul_(keep).add_((w * corr) @ var)
                 bn.num_batches_tracked += n
 
     # ---- label export (model.py:525-605): D2H on a side stream into pinned buffers, text formatting on writer threads
