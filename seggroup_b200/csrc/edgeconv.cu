@@ -173,24 +173,32 @@ __global__ void pad_rows12_kernel(const float* __restrict__ x9, long long n12, f
 // pass B: out[p, c] = max_k of the edge MLP
 // ------------------------------------------------------------------------------------------------
 // Round 2: rows come from the 48-byte padded copy (three aligned 16-byte loads instead of nine scalar ones), BatchNorm-1 is folded
-// into the weights (a = lrelu((scale W) e + (beta - scale mean))), and the two channels of a lane advance with ONE packed FFMA2 per
-// input feature (weights as (w_c0, w_c0+1) pairs, the staged edge feature as the broadcast scalar operand): 18 instead of 36 FMA
-// issues per edge and lane.  Two points per warp iteration keep two independent accumulation chains in flight.
+// into the weights, and the two channels of a lane advance with ONE packed FFMA2 per input feature (weights as (w_c0, w_c0+1) pairs,
+// the staged edge feature as the broadcast scalar operand).  The edge vector is (x_j - x_i, x_i): its second half is the same for
+// the 20 edges of a point, so  y_k = [bias + Wc x_i] + Wd (x_j - x_i)  costs 9 FFMA2 per edge and lane plus 9 per point instead of
+// 18 per edge, and only the 9 differences are staged.  LeakyReLU is increasing, so max_k lrelu(y_k) = lrelu(max_k y_k): one
+// activation per point (first maximum kept, as torch.max).  Two points per warp iteration keep two independent chains in flight.
+constexpr int CD = 9;                     // difference features per edge
+constexpr int CDP = 12;                   // staged row: 9 differences + 3 pad (48 B, three 16-byte loads)
 __global__ void __launch_bounds__(WARPS * 32)
 forward_max_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ W1,
                    const float* __restrict__ stats1, float* __restrict__ out, unsigned char* __restrict__ argk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float (*s_e)[2][KNN][CINP] = reinterpret_cast<float (*)[2][KNN][CINP]>(smem_raw);      // [warp][point of the pair][edge][20]
+    float (*s_e)[2][KNN][CDP] = reinterpret_cast<float (*)[2][KNN][CDP]>(smem_raw);        // [warp][point of the pair][edge][12]
+    __shared__ __align__(16) float s_c[WARPS][2][CDP];                                      // centre rows x_i of the pair
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = lane * 2;
-    float2 w[CIN];
+    float2 wd[CD], wc[CD];
     const float sc0 = stats1[128 + c0], sc1 = stats1[128 + c0 + 1];
 #pragma unroll
-    for (int t = 0; t < CIN; ++t) w[t] = make_float2(__ldg(W1 + c0 * CIN + t) * sc0, __ldg(W1 + (c0 + 1) * CIN + t) * sc1);
+    for (int t = 0; t < CD; ++t) {
+        wd[t] = make_float2(__ldg(W1 + c0 * CIN + t) * sc0, __ldg(W1 + (c0 + 1) * CIN + t) * sc1);
+        wc[t] = make_float2(__ldg(W1 + c0 * CIN + CD + t) * sc0, __ldg(W1 + (c0 + 1) * CIN + CD + t) * sc1);
+    }
     const float2 bias = make_float2(fmaf(-sc0, stats1[c0], stats1[192 + c0]), fmaf(-sc1, stats1[c0 + 1], stats1[192 + c0 + 1]));
     for (int p0 = (blockIdx.x * WARPS + warp) * 2; p0 < N; p0 += gridDim.x * WARPS * 2) {
         __syncwarp();
-        // stage the 2 x 20 edge vectors: lane l < 20 fetches neighbour l of point p0, lanes 20..31 + a second pass neighbours of p0 + 1
+        // stage the 2 x 20 difference vectors: lane l < 20 fetches neighbour l of point p0, lanes 20..31 + a second pass neighbours of p0 + 1
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
             const int slot = pass * 32 + lane;                 // 0..39 used
@@ -205,44 +213,52 @@ forward_max_kernel(const float* __restrict__ x12, const int* __restrict__ knn, i
                     float4* d = reinterpret_cast<float4*>(&s_e[warp][pp][k][0]);
                     d[0] = make_float4(b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w);
                     d[1] = make_float4(b1.x - a1.x, b1.y - a1.y, b1.z - a1.z, b1.w - a1.w);
-                    d[2] = make_float4(b2.x - a2.x, a0.x, a0.y, a0.z);
-                    d[3] = make_float4(a0.w, a1.x, a1.y, a1.z);
-                    d[4] = make_float4(a1.w, a2.x, 0.f, 0.f);
+                    d[2] = make_float4(b2.x - a2.x, 0.f, 0.f, 0.f);
+                    if (k == 0) {
+                        float4* c = reinterpret_cast<float4*>(&s_c[warp][pp][0]);
+                        c[0] = a0; c[1] = a1; c[2] = a2;
+                    }
                 }
             }
         }
         __syncwarp();
+        float2 base[2] = {bias, bias};                       // bias + Wc x_i: once per point
+#pragma unroll
+        for (int t = 0; t < CD; ++t) {
+            const float e0 = s_c[warp][0][t], e1 = s_c[warp][1][t];
+            sgb_tc::ffma2(base[0], wc[t], make_float2(e0, e0));
+            sgb_tc::ffma2(base[1], wc[t], make_float2(e1, e1));
+        }
         float2 best[2] = {make_float2(-INFINITY, -INFINITY), make_float2(-INFINITY, -INFINITY)};
         int bk[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll 4
         for (int k = 0; k < KNN; ++k) {
-            float2 y[2] = {bias, bias};
+            float2 y[2] = {base[0], base[1]};
 #pragma unroll
-            for (int t4 = 0; t4 < CINP / 4; ++t4) {
+            for (int t4 = 0; t4 < CDP / 4; ++t4) {
                 const float4 v0 = *reinterpret_cast<const float4*>(&s_e[warp][0][k][t4 * 4]);
                 const float4 v1 = *reinterpret_cast<const float4*>(&s_e[warp][1][k][t4 * 4]);
                 const float e0[4] = {v0.x, v0.y, v0.z, v0.w}, e1[4] = {v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int t = t4 * 4 + u;
-                    if (t < CIN) {
-                        sgb_tc::ffma2(y[0], w[t], make_float2(e0[u], e0[u]));
-                        sgb_tc::ffma2(y[1], w[t], make_float2(e1[u], e1[u]));
+                    if (t < CD) {
+                        sgb_tc::ffma2(y[0], wd[t], make_float2(e0[u], e0[u]));
+                        sgb_tc::ffma2(y[1], wd[t], make_float2(e1[u], e1[u]));
                     }
                 }
             }
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
-                const float a0 = lrelu(y[pp].x), a1 = lrelu(y[pp].y);
-                if (a0 > best[pp].x) { best[pp].x = a0; bk[pp][0] = k; }
-                if (a1 > best[pp].y) { best[pp].y = a1; bk[pp][1] = k; }
+                if (y[pp].x > best[pp].x) { best[pp].x = y[pp].x; bk[pp][0] = k; }
+                if (y[pp].y > best[pp].y) { best[pp].y = y[pp].y; bk[pp][1] = k; }
             }
         }
 #pragma unroll
         for (int pp = 0; pp < 2; ++pp) {
             const int p = p0 + pp;
             if (p < N) {
-                *reinterpret_cast<float2*>(out + (size_t)p * COUT + c0) = best[pp];
+                *reinterpret_cast<float2*>(out + (size_t)p * COUT + c0) = make_float2(lrelu(best[pp].x), lrelu(best[pp].y));
                 if (argk) *reinterpret_cast<uchar2*>(argk + (size_t)p * COUT + c0) = make_uchar2((unsigned char)bk[pp][0], (unsigned char)bk[pp][1]);
             }
         }
@@ -309,7 +325,7 @@ extern "C" int sgb_edgeconv_fwd(const float* x9, const int* knn, int N, int two_
         return sgb_ec2_tc_forward(x12, knn, N, W1, stats1, W2, gamma2, beta2, out, argk, stats2, var2, mom2, w8 + off, st);
     }
     {                                      // single layer (MLP2): recompute the edge layer per neighbour, max over k
-        const size_t smB = sizeof(float) * WARPS * 2 * KNN * CINP;
+        const size_t smB = sizeof(float) * WARPS * 2 * KNN * CDP;
         SGB_OPT_IN_SMEM(forward_max_kernel);
         { forward_max_kernel<<<grid, WARPS * 32, smB, st>>>(x12, knn, N, W1, stats1, out, argk); SGB_COUNT_LAUNCH(); }
     }
