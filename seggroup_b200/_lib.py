@@ -12,7 +12,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "seggroup_b200.h")
-LIB_PATH = os.path.join(_HERE, "lib", "libseggroup_b200.so")
+LIB_PATH = os.environ.get("SGB_LIB_PATH") or os.path.join(_HERE, "lib", "libseggroup_b200.so")     # override: kernel experiments (tools/ablate.sh)
 
 _SCALARS = {"unsigned long long": ctypes.c_ulonglong, "unsigned": ctypes.c_uint, "int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t,
             "long long": ctypes.c_longlong}

@@ -24,6 +24,10 @@
 #include "edgeconv_common.cuh"
 #include "tc_common.cuh"
 
+#ifndef SGB_ABL
+#define SGB_ABL 0      // role-ablation timing experiments (tools/ablate.sh): results are WRONG for any value but 0
+#endif
+
 namespace sgb_ecbt {
 using namespace sgb_tc;
 using sgb_ec::CIN;
@@ -235,7 +239,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 const bool valid = *reinterpret_cast<const uint32_t*>(raw + TE * 48 + PTS * 48 + er * 4) != 0u;
                 float2 y01 = make_float2(bias.x, bias.y), y23 = make_float2(bias.z, bias.w);
 #pragma unroll
-                for (int q = 0; q < CIN; ++q) {
+                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CIN); ++q) {
                     const float2 ee = make_float2(ev[q], ev[q]);
                     ffma2(y01, w01[q], ee);
                     ffma2(y23, w23[q], ee);
@@ -272,8 +276,10 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                         *reinterpret_cast<float*>(dst_ech + o) = vh;
                         *reinterpret_cast<float*>(dst_ecl + o) = tf32_hi(v - vh);
                     };
-                    ec_store(c4);
-                    if (c4 < 3) ec_store(16 + c4);
+                    if (!(SGB_ABL & 16)) {
+                        ec_store(c4);
+                        if (c4 < 3) ec_store(16 + c4);
+                    }
                 }
             }
             fence_async_smem();
@@ -304,8 +310,10 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                             const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
                             const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
                             mma_tf32(d, dah, dbh, idesc, i > 0);
-                            mma_tf32(d, dal, dbh, idesc, true);
-                            mma_tf32(d, dah, dbl, idesc, true);
+                            if (!(SGB_ABL & 4)) {
+                                mma_tf32(d, dal, dbh, idesc, true);
+                                mma_tf32(d, dah, dbl, idesc, true);
+                            }
                         }
                         mma_commit(&bar_tfull[st]);
                         mma_commit(&bar_hempty[st]);
@@ -324,13 +332,15 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                         const uint32_t dvh = smem_u32(sm + off_dv + h * 2 * DVH_BYTES), dvl = dvh + DVH_BYTES;
                         const uint32_t d = tmem + (uint32_t)(T_COL0 + gb * T_COLS);
 #pragma unroll
-                        for (int i = 0; i < TE / 16; ++i) {           // 8 edges (K) per instruction = 2 chunks of 4; 5 per half tile
+                        for (int i = 0; i < ((SGB_ABL & 8) ? 1 : TE / 16); ++i) {           // 8 edges (K) per instruction = 2 chunks of 4; 5 per half tile
                             const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(h * (TE / 8) + 2 * i) * (TN * 16);
                             const uint64_t dah = make_desc(dvh + ao, COUT * 16, 128), dal = make_desc(dvl + ao, COUT * 16, 128);
                             const uint64_t dbh = make_desc(ec_hi + bo, TN * 16, 128), dbl = make_desc(ec_lo + bo, TN * 16, 128);
                             mma_tf32(d, dah, dbh, idesc_t, (u % FLUSH) > 0 || h > 0 || i > 0);
-                            mma_tf32(d, dal, dbh, idesc_t, true);
-                            mma_tf32(d, dah, dbl, idesc_t, true);
+                            if (!(SGB_ABL & 4)) {
+                                mma_tf32(d, dal, dbh, idesc_t, true);
+                                mma_tf32(d, dah, dbl, idesc_t, true);
+                            }
                         }
                         mma_commit(&bar_dvempty[h]);
                         if (h == 1) {
@@ -369,7 +379,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
                 float dv[KNN];
 #pragma unroll
-                for (int k = 0; k < KNN; ++k) {
+                for (int k = 0; k < ((SGB_ABL & 2) ? 1 : KNN); ++k) {
                     const int e = pp * KNN + k;
                     const float z = k < 16 ? v[k] : u[k - 16];
                     const bool posv = (s_m[e * 16 + mbyte] >> bit) & 1u;
@@ -377,7 +387,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 }
                 if (owner) {
 #pragma unroll
-                    for (int q = 0; q < KNN / 4; ++q) {                   // 4 consecutive edges = one 16-byte chunk of row c
+                    for (int q = 0; q < ((SGB_ABL & 2) ? 0 : KNN / 4); ++q) {                   // 4 consecutive edges = one 16-byte chunk of row c
                         const float4 d4 = make_float4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
                         const float4 hi = make_float4(tf32_hi(d4.x), tf32_hi(d4.y), tf32_hi(d4.z), tf32_hi(d4.w));
                         const float4 lo = make_float4(tf32_hi(d4.x - hi.x), tf32_hi(d4.y - hi.y), tf32_hi(d4.z - hi.z), tf32_hi(d4.w - hi.w));

@@ -41,6 +41,10 @@
 #include "edgeconv_common.cuh"
 #include "tc_common.cuh"
 
+#ifndef SGB_ABL
+#define SGB_ABL 0      // role-ablation timing experiments (tools/ablate.sh): results are WRONG for any value but 0
+#endif
+
 namespace sgb_ectc {
 using namespace sgb_tc;
 using sgb_ec::CIN;
@@ -247,7 +251,7 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                                        a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
                 float2 y01 = make_float2(bias.x, bias.y), y23 = make_float2(bias.z, bias.w);
 #pragma unroll
-                for (int q = 0; q < CIN; ++q) {
+                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CIN); ++q) {
                     const float2 ee = make_float2(ev[q], ev[q]);
                     ffma2(y01, w01[q], ee);
                     ffma2(y23, w23[q], ee);
@@ -259,7 +263,7 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                 const uint32_t off = (uint32_t)c4 * (TE * 16) + (uint32_t)(er >> 3) * 128 + (uint32_t)(er & 7) * 16;
                 *reinterpret_cast<float4*>(dst_hi + off) = hi;
                 *reinterpret_cast<float4*>(dst_lo + off) = lo;
-                if (GRAM) {                             // transposed copy: rows 0..63 lo, 64..127 hi
+                if (GRAM && !(SGB_ABL & 16)) {          // transposed copy: rows 0..63 lo, 64..127 hi
                     const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                     for (int s4 = 0; s4 < 4; ++s4) {
@@ -295,15 +299,17 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                     const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
                     const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
                     mma_tf32(d, dah, dbh, idesc, i > 0);
-                    mma_tf32(d, dal, dbh, idesc, true);
-                    mma_tf32(d, dah, dbl, idesc, true);
+                    if (!(SGB_ABL & 4)) {
+                        mma_tf32(d, dal, dbh, idesc, true);
+                        mma_tf32(d, dah, dbl, idesc, true);
+                    }
                 }
                 mma_commit(&bar_tfull[st]);
                 if (GRAM) {
                     const uint32_t ht = b_lo + C::TILE_BYTES;
                     const uint32_t dg = tmem + (uint32_t)(C::G_COL0 + gb * 128);
 #pragma unroll
-                    for (int s = 0; s < TE / 8; ++s) {              // 8 edges (K) per instruction
+                    for (int s = 0; s < ((SGB_ABL & 8) ? 1 : TE / 8); ++s) {              // 8 edges (K) per instruction
                         const uint32_t ko = (uint32_t)(s >> 1) * (GR * 64) + (uint32_t)(s & 1) * 32;
                         const uint64_t da = make_desc_sw(ht + ko, 16, 512, 4);
                         const uint64_t db = make_desc_sw(ht + ko + 8 * 512, 16, 512, 4);      // rows 64.. : hi, ones, zeros
@@ -336,7 +342,7 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
             // Warp-uniform fast paths for the usual cases (all scales positive / all negative).
             auto scan = [&](auto better) {
 #pragma unroll 1
-                for (int pp = 0; pp < npts; ++pp) {
+                for (int pp = 0; pp < ((SGB_ABL & 2) ? 1 : npts); ++pp) {
                     float v[16], u[4];
                     tmem_ld16(taddr + (uint32_t)(pp * KNN), v);
                     tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
