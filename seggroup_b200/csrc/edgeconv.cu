@@ -166,7 +166,7 @@ __global__ void pad_rows12_kernel(const float* __restrict__ x9, long long n12, f
     if (i >= n12) return;
     const long long p = i / 12;
     const int q = (int)(i % 12);
-    x12[i] = q < 9 ? __ldg(x9 + p * 9 + q) : 0.f;
+    x12[i] = q < 9 ? __ldg(x9 + p * 9 + q) : (q == 11 ? 1.f : 0.f);     // pad lane 11 = 1: "this row was gathered" flag of the tcgen05 producers (a zero-filled row has 0 there)
 }
 
 // ------------------------------------------------------------------------------------------------

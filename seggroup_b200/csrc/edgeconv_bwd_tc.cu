@@ -67,8 +67,9 @@ constexpr int off_h0 = off_bm_lo + BM_BYTES;                   // 2 H stages
 constexpr int off_e0 = off_h0 + 2 * HSTAGE_BYTES;              // 3 EC / mask stages
 constexpr int off_dv = off_e0 + ERING * ESTAGE_BYTES;          // [half][hi, lo]
 constexpr int off_raw0 = off_dv + 4 * DVH_BYTES;
-constexpr int off_acc = off_raw0 + RING * RAW_BYTES;           // fp64 accumulators [64 channels][ACCN]
-constexpr int off_ebar = off_acc + COUT * ACCN * 8;
+constexpr int off_wc = off_raw0 + RING * RAW_BYTES;            // centre-half first-layer weights [16 chunks][9] float4 (BN1 folded in)
+constexpr int off_ctr = off_wc + 16 * 9 * 16;                  // per producer warp: centre rows [PTS][4 parts] float4 of the current tile
+constexpr int off_ebar = off_ctr + PROD_WARPS * PTS * 4 * 16;
 constexpr int off_bars = off_ebar + 32 * 4;                    // 19 mbarriers
 constexpr int off_tmem_slot = off_bars + 20 * 8;
 constexpr int SMEM_TOTAL = off_tmem_slot + 16;
@@ -85,7 +86,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* mbar, uint32_t parity) {    
 // byte offset of (row r, K index e) in a canonical no-swizzle K-major tile with R rows (tc_common.cuh tile_off with c = e)
 __device__ __forceinline__ uint32_t kmajor_off(int r, int e, int R) { return (uint32_t)((e >> 2) * (R * 16) + (r >> 3) * 128 + (r & 7) * 16 + (e & 3) * 4); }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 1)      // 13 warps: one scheduler hosts 4 of them -> 128 registers per thread at most
 ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ W1,
                   const float* __restrict__ stats1, const double* __restrict__ mom1, const float* __restrict__ e0, double M,
                   const float* __restrict__ coef /*[64*64 Bm][64 r]*/, double* __restrict__ part /*[grid][64*NACC]*/) {
@@ -127,7 +128,13 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             *reinterpret_cast<float*>(ec + EC_BYTES + kmajor_off(r, e, TN)) = 0.f;
         }
     }
-    for (int i = tid; i < COUT * ACCN; i += THREADS) reinterpret_cast<double*>(sm + off_acc)[i] = 0.0;
+    for (int i = tid; i < 16 * 9; i += THREADS) {                             // centre half of the first layer: columns 9..17 of W1, BN1 scale folded in
+        const int ch = i / 9, q = i % 9;
+        float w[4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) w[s4] = __ldg(W1 + (4 * ch + s4) * CIN + 9 + q) * stats1[128 + 4 * ch + s4];
+        *reinterpret_cast<float4*>(sm + off_wc + i * 16) = make_float4(w[0], w[1], w[2], w[3]);
+    }
     if (tid < CIN) s_ebar[tid] = (float)(mom1[tid] / M + (double)e0[tid]);
     if (tid == 0) {
         mbar_init(&bar_full[0], PROD_WARPS); mbar_init(&bar_full[1], PROD_WARPS);
@@ -155,7 +162,11 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         const int grp = pw >> 2;
         const int c4 = (lane >> 3) * 4 + (pw & 3);      // my chunk of the hidden vector: channels 4 c4 .. 4 c4 + 3
         const int eb = lane & 7;
-        float2 w01[CIN], w23[CIN];
+        const int part = lane >> 3;
+        // as the forward kernel: only the 9 difference columns of the first layer are per-edge work (weights in registers); the centre
+        // half  bias + Wc x_i  is evaluated once per point and tile
+        constexpr int CD = 9;
+        float2 w01[CD], w23[CD];
         float4 bias;
         {
             float sc[4], bb[4];
@@ -166,12 +177,14 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 bb[s4] = fmaf(-stats1[128 + c], stats1[c], stats1[192 + c]);
             }
 #pragma unroll
-            for (int q = 0; q < CIN; ++q) {
+            for (int q = 0; q < CD; ++q) {
                 w01[q] = make_float2(__ldg(W1 + (4 * c4 + 0) * CIN + q) * sc[0], __ldg(W1 + (4 * c4 + 1) * CIN + q) * sc[1]);
                 w23[q] = make_float2(__ldg(W1 + (4 * c4 + 2) * CIN + q) * sc[2], __ldg(W1 + (4 * c4 + 3) * CIN + q) * sc[3]);
             }
             bias = make_float4(bb[0], bb[1], bb[2], bb[3]);
         }
+        const float4* wc = reinterpret_cast<const float4*>(sm + off_wc) + c4 * 9;
+        unsigned char* ctr = sm + off_ctr + pw * (PTS * 4 * 16);
         const bool gatherer = ptid < TE, pgatherer = ptid < PTS;
         auto edge_in_range = [&](int t) -> bool {
             const long long g = g_begin + (long long)t * TE + ptid;
@@ -194,8 +207,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 const bool v = j >= 0;
                 const float* src = x12 + (size_t)(v ? j : 0) * 12;
                 unsigned char* dst = raw + ptid * 48;
-                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
-                *reinterpret_cast<uint32_t*>(raw + TE * 48 + PTS * 48 + ptid * 4) = v ? 1u : 0u;
+                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);      // !v: zero fill -> pad lane 11 = 0 marks the edge invalid
             }
             if (pgatherer) {
                 const long long pt = g_begin / KNN + (long long)t * PTS + ptid;
@@ -220,6 +232,21 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");
             issue_rows(t + RING - 1, staged_index(t + RING - 1));
             const unsigned char* raw = sm + off_raw0 + (t % RING) * RAW_BYTES;
+            if (eb < PTS) {                              // lane (part, eb): centre row of point eb of the tile for my chunk c4
+                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + eb * 48);
+                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
+                const float xi[CD] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+                float2 c01 = make_float2(bias.x, bias.y), c23 = make_float2(bias.z, bias.w);
+#pragma unroll
+                for (int q = 0; q < CD; ++q) {
+                    const float4 w = wc[q];
+                    const float2 xx = make_float2(xi[q], xi[q]);
+                    ffma2(c01, make_float2(w.x, w.y), xx);
+                    ffma2(c23, make_float2(w.z, w.w), xx);
+                }
+                *reinterpret_cast<float4*>(ctr + (eb * 4 + part) * 16) = make_float4(c01.x, c01.y, c23.x, c23.y);
+            }
+            __syncwarp();
             mbar_wait(&bar_hempty[st], ph ^ 1u);
             mbar_wait(&bar_eempty[t % ERING], ((uint32_t)(t / ERING) & 1u) ^ 1u);
             unsigned char* dst_hi = sm + off_h0 + st * HSTAGE_BYTES;
@@ -227,19 +254,24 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             unsigned char* dst_ech = sm + off_e0 + (t % ERING) * ESTAGE_BYTES;
             unsigned char* dst_ecl = dst_ech + EC_BYTES;
             unsigned char* dst_mt = dst_ecl + EC_BYTES;
-#pragma unroll 1
-            for (int blk = grp; blk < BLOCKS; blk += 2) {
+            struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; };
+            auto load_blk = [&](int blk, Blk& B) {
                 const int er = blk * 8 + eb;
+                const int pt = (er * 205) >> 12;        // er / KNN, exact for er < 1039
                 const float4* rj = reinterpret_cast<const float4*>(raw + er * 48);
-                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + (er / KNN) * 48);
-                const float4 b0 = rj[0], b1 = rj[1], b2 = rj[2];
-                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
-                const float ev[CIN] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w, b1.x - a1.x, b1.y - a1.y, b1.z - a1.z, b1.w - a1.w, b2.x - a2.x,
-                                       a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
-                const bool valid = *reinterpret_cast<const uint32_t*>(raw + TE * 48 + PTS * 48 + er * 4) != 0u;
-                float2 y01 = make_float2(bias.x, bias.y), y23 = make_float2(bias.z, bias.w);
+                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + pt * 48);
+                B.b0 = rj[0]; B.b1 = rj[1]; B.b2 = rj[2];
+                B.a0 = ri[0]; B.a1 = ri[1]; B.a2 = ri[2];
+                B.cc = *reinterpret_cast<const float4*>(ctr + (pt * 4 + part) * 16);
+            };
+            auto finish_blk = [&](int blk, const Blk& B) {
+                const int er = blk * 8 + eb;
+                const float ev[CD] = {B.b0.x - B.a0.x, B.b0.y - B.a0.y, B.b0.z - B.a0.z, B.b0.w - B.a0.w, B.b1.x - B.a1.x, B.b1.y - B.a1.y,
+                                      B.b1.z - B.a1.z, B.b1.w - B.a1.w, B.b2.x - B.a2.x};
+                const bool valid = B.b2.w != 0.f;        // pad lane 11: 1 in a gathered row, 0 in a zero-filled one
+                float2 y01 = make_float2(B.cc.x, B.cc.y), y23 = make_float2(B.cc.z, B.cc.w);
 #pragma unroll
-                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CIN); ++q) {
+                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CD); ++q) {
                     const float2 ee = make_float2(ev[q], ev[q]);
                     ffma2(y01, w01[q], ee);
                     ffma2(y23, w23[q], ee);
@@ -257,11 +289,11 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 *reinterpret_cast<float4*>(dst_lo + off) = lo;
                 dst_mt[er * 16 + c4] = (unsigned char)bits;     // sign bits of hidden channels 4 c4 .. 4 c4 + 3
                 // EC column of this edge (centred edge vector, then 1 for a real edge -> A0), spread over the 16 threads of the edge:
-                // thread c4 writes row c4, threads 0..2 also rows 16..18.  Values come straight from the gathered rows (same
-                // subtraction as ev[]), so no register array is indexed dynamically.
-                {
-                    const float* fj = reinterpret_cast<const float*>(rj);
-                    const float* fi = reinterpret_cast<const float*>(ri);
+                // thread c4 writes row c4, threads 0..2 also rows 16..18.  Values come straight from the gathered rows in shared memory
+                // (same subtraction as ev[]), so no register array is indexed dynamically.
+                if (!(SGB_ABL & 16)) {
+                    const float* fj = reinterpret_cast<const float*>(raw + er * 48);
+                    const float* fi = reinterpret_cast<const float*>(raw + TE * 48 + ((er * 205) >> 12) * 48);
                     auto ec_store = [&](int q) {
                         float v = 0.f;
                         if (valid) {
@@ -276,12 +308,21 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                         *reinterpret_cast<float*>(dst_ech + o) = vh;
                         *reinterpret_cast<float*>(dst_ecl + o) = tf32_hi(v - vh);
                     };
-                    if (!(SGB_ABL & 16)) {
-                        ec_store(c4);
-                        if (c4 < 3) ec_store(16 + c4);
-                    }
+                    ec_store(c4);
+                    if (c4 < 3) ec_store(16 + c4);
                 }
+            };
+            Blk A, Bq;
+            int blk = grp;
+            load_blk(blk, A);
+#pragma unroll 1
+            for (; blk + 2 < BLOCKS; blk += 4) {
+                load_blk(blk + 2, Bq);
+                finish_blk(blk, A);
+                if (blk + 4 < BLOCKS) load_blk(blk + 4, A);
+                finish_blk(blk + 2, Bq);
             }
+            if (blk < BLOCKS) finish_blk(blk, A);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[st]);
@@ -290,7 +331,9 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         // ================= MMA issuer (one thread): an event loop over two independent streams of work — the z MMAs of the next
         // tile whose H stage is full, and the T MMAs of the next half tile whose dv1 operand the epilogue has finished — so that
         // neither waits for the other's inputs (non-blocking mbarrier tests)
-        if (lane == 0) {
+        // The whole warp walks the loop with warp-uniform control flow (barrier tests agreed on by vote) and ONE elected lane issues:
+        // under `if (lane == 0)` the compiler wrapped every tcgen05.mma / commit in its own ELECT + BRA.U.ANY loop.
+        {
             const uint32_t idesc = make_idesc_tf32(64, TE, false, false);
             const uint32_t idesc_t = make_idesc_tf32(64, TN, false, false);
             const uint32_t a_hi = smem_u32(sm + off_bm_hi), a_lo = smem_u32(sm + off_bm_lo);
@@ -300,23 +343,27 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 if (nz < ntiles) {
                     const int st = nz & 1;
                     const uint32_t ph = (uint32_t)(nz >> 1) & 1u;
-                    if (mbar_test(&bar_full[st], ph) && mbar_test(&bar_tempty[st], ph ^ 1u)) {
+                    const bool ok = mbar_test(&bar_full[st], ph) && mbar_test(&bar_tempty[st], ph ^ 1u);
+                    if (__all_sync(SGB_FULL_MASK, ok)) {
                         fence_after_sync();
-                        const uint32_t b_hi = smem_u32(sm + off_h0 + st * HSTAGE_BYTES), b_lo = b_hi + TILE_BYTES;
-                        const uint32_t d = tmem + (uint32_t)(st * Z_COL);
+                        if (elect_one_sync()) {
+                            const uint32_t b_hi = smem_u32(sm + off_h0 + st * HSTAGE_BYTES), b_lo = b_hi + TILE_BYTES;
+                            const uint32_t d = tmem + (uint32_t)(st * Z_COL);
 #pragma unroll
-                        for (int i = 0; i < COUT / 8; ++i) {
-                            const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
-                            const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
-                            const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
-                            mma_tf32(d, dah, dbh, idesc, i > 0);
-                            if (!(SGB_ABL & 4)) {
-                                mma_tf32(d, dal, dbh, idesc, true);
-                                mma_tf32(d, dah, dbl, idesc, true);
+                            for (int i = 0; i < COUT / 8; ++i) {
+                                const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
+                                const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
+                                const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
+                                mma_tf32(d, dah, dbh, idesc, i > 0);
+                                if (!(SGB_ABL & 4)) {
+                                    mma_tf32(d, dal, dbh, idesc, true);
+                                    mma_tf32(d, dah, dbl, idesc, true);
+                                }
                             }
+                            mma_commit(&bar_tfull[st]);
+                            mma_commit(&bar_hempty[st]);
                         }
-                        mma_commit(&bar_tfull[st]);
-                        mma_commit(&bar_hempty[st]);
+                        __syncwarp();
                         ++nz;
                         did = true;
                     }
@@ -326,27 +373,30 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                     const int seg = u / FLUSH, gb = seg & 1;
                     bool ok = mbar_test(&bar_dvfull[h], (uint32_t)u & 1u);
                     if (ok && h == 0 && u % FLUSH == 0) ok = mbar_test(&bar_gempty[gb], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
-                    if (ok) {
+                    if (__all_sync(SGB_FULL_MASK, ok)) {
                         fence_after_sync();
-                        const uint32_t ec_hi = smem_u32(sm + off_e0 + (u % ERING) * ESTAGE_BYTES), ec_lo = ec_hi + EC_BYTES;
-                        const uint32_t dvh = smem_u32(sm + off_dv + h * 2 * DVH_BYTES), dvl = dvh + DVH_BYTES;
-                        const uint32_t d = tmem + (uint32_t)(T_COL0 + gb * T_COLS);
+                        if (elect_one_sync()) {
+                            const uint32_t ec_hi = smem_u32(sm + off_e0 + (u % ERING) * ESTAGE_BYTES), ec_lo = ec_hi + EC_BYTES;
+                            const uint32_t dvh = smem_u32(sm + off_dv + h * 2 * DVH_BYTES), dvl = dvh + DVH_BYTES;
+                            const uint32_t d = tmem + (uint32_t)(T_COL0 + gb * T_COLS);
 #pragma unroll
-                        for (int i = 0; i < ((SGB_ABL & 8) ? 1 : TE / 16); ++i) {           // 8 edges (K) per instruction = 2 chunks of 4; 5 per half tile
-                            const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(h * (TE / 8) + 2 * i) * (TN * 16);
-                            const uint64_t dah = make_desc(dvh + ao, COUT * 16, 128), dal = make_desc(dvl + ao, COUT * 16, 128);
-                            const uint64_t dbh = make_desc(ec_hi + bo, TN * 16, 128), dbl = make_desc(ec_lo + bo, TN * 16, 128);
-                            mma_tf32(d, dah, dbh, idesc_t, (u % FLUSH) > 0 || h > 0 || i > 0);
-                            if (!(SGB_ABL & 4)) {
-                                mma_tf32(d, dal, dbh, idesc_t, true);
-                                mma_tf32(d, dah, dbl, idesc_t, true);
+                            for (int i = 0; i < ((SGB_ABL & 8) ? 1 : TE / 16); ++i) {           // 8 edges (K) per instruction = 2 chunks of 4; 5 per half tile
+                                const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(h * (TE / 8) + 2 * i) * (TN * 16);
+                                const uint64_t dah = make_desc(dvh + ao, COUT * 16, 128), dal = make_desc(dvl + ao, COUT * 16, 128);
+                                const uint64_t dbh = make_desc(ec_hi + bo, TN * 16, 128), dbl = make_desc(ec_lo + bo, TN * 16, 128);
+                                mma_tf32(d, dah, dbh, idesc_t, (u % FLUSH) > 0 || h > 0 || i > 0);
+                                if (!(SGB_ABL & 4)) {
+                                    mma_tf32(d, dal, dbh, idesc_t, true);
+                                    mma_tf32(d, dah, dbl, idesc_t, true);
+                                }
+                            }
+                            mma_commit(&bar_dvempty[h]);
+                            if (h == 1) {
+                                mma_commit(&bar_eempty[u % ERING]);
+                                if ((u + 1) % FLUSH == 0 || u == ntiles - 1) mma_commit(&bar_gfull[gb]);
                             }
                         }
-                        mma_commit(&bar_dvempty[h]);
-                        if (h == 1) {
-                            mma_commit(&bar_eempty[u % ERING]);
-                            if ((u + 1) % FLUSH == 0 || u == ntiles - 1) mma_commit(&bar_gfull[gb]);
-                        }
+                        __syncwarp();
                         ++nT;
                         did = true;
                     }
@@ -361,7 +411,17 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         const bool owner = lane < 16;
         const float rc = __ldg(coef + COUT * COUT + c);
         const uint32_t mbyte = (uint32_t)(c >> 2), bit = (uint32_t)(c & 3);
-        double* acc = reinterpret_cast<double*>(sm + off_acc) + c * ACCN;
+        // T / A0 accumulators of my channel across the CTA's segments: unevaluated fp32 pairs in registers (two-sum), converted to
+        // fp64 once at the end (round 2a kept fp64 accumulators in 10 KB of shared memory; DADD is slow on this part)
+        float acc_h[ACCN], acc_l[ACCN];
+#pragma unroll
+        for (int q = 0; q < ACCN; ++q) { acc_h[q] = 0.f; acc_l[q] = 0.f; }
+        auto two_sum = [](float& h, float& l, float x) {
+            const float s_ = h + x;
+            const float bb = s_ - h;
+            l += (h - (s_ - bb)) + (x - bb);
+            h = s_;
+        };
         unsigned char* dv_row = sm + off_dv + (c >> 3) * 128 + (c & 7) * 16;          // my row in a [64][40] K-major half tile
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
@@ -374,14 +434,16 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             for (int pp = 0; pp < PTS; ++pp) {
                 const int h = pp >> 1;                                  // half of the dv1 tile this point belongs to
                 if ((pp & 1) == 0) mbar_wait(&bar_dvempty[h], ((uint32_t)t & 1u) ^ 1u);      // the T MMAs of tile t - 1 are done with this half
-                float v[16], u[4];
-                tmem_ld16(taddr + (uint32_t)(pp * KNN), v);
-                tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
+                uint32_t v[16], u[4];
+                tmem_ld16_issue(taddr + (uint32_t)(pp * KNN), v);
+                tmem_ld4_issue(taddr + (uint32_t)(pp * KNN + 16), u);
+                tmem_ld_wait();
+                tmem_ld_pin20(v, u);
                 float dv[KNN];
 #pragma unroll
                 for (int k = 0; k < ((SGB_ABL & 2) ? 1 : KNN); ++k) {
                     const int e = pp * KNN + k;
-                    const float z = k < 16 ? v[k] : u[k - 16];
+                    const float z = __uint_as_float(k < 16 ? v[k] : u[k - 16]);
                     const bool posv = (s_m[e * 16 + mbyte] >> bit) & 1u;
                     dv[k] = (rc - z) * (posv ? 1.f : SLOPE);            // padding edges: their EC column is zero, so any finite value is inert
                 }
@@ -415,13 +477,11 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 tmem_ld16(gaddr, g16);
                 tmem_ld4(gaddr + 16, g4a);
                 tmem_ld4(gaddr + 20, g4b);
-                if (owner) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) acc[q] += (double)g16[q];
+                for (int q = 0; q < 16; ++q) two_sum(acc_h[q], acc_l[q], g16[q]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[16 + q] += (double)g4a[q];      // columns 20..23 are structurally zero
-                    (void)g4b;
-                }
+                for (int q = 0; q < 4; ++q) two_sum(acc_h[16 + q], acc_l[16 + q], g4a[q]);      // columns 20..23 are structurally zero
+                (void)g4b;
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_gempty[gb]);
@@ -431,11 +491,13 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         if (owner) {
             double* dst = part + ((size_t)blockIdx.x * COUT + c) * NACC;
             double dot = 0.0;
+#pragma unroll
             for (int i = 0; i < CIN; ++i) {
-                dst[2 + i] = acc[i];
-                dot += (double)__ldg(W1 + c * CIN + i) * acc[i];
+                const double a_i = (double)acc_h[i] + (double)acc_l[i];
+                dst[2 + i] = a_i;
+                dot += (double)__ldg(W1 + c * CIN + i) * a_i;
             }
-            dst[0] = acc[CIN];
+            dst[0] = (double)acc_h[CIN] + (double)acc_l[CIN];
             dst[1] = (double)stats1[64 + c] * dot;
         }
     }

@@ -80,7 +80,9 @@ template <bool GRAM> struct Cfg {
     static constexpr int raw0 = stage0 + 2 * STAGE_BYTES;
     static constexpr int bars = raw0 + RING * RAW_BYTES;           // 12 mbarriers
     static constexpr int tmem_slot = bars + 12 * 8;
-    static constexpr int total = tmem_slot + 16;
+    static constexpr int wc_tab = tmem_slot + 16;                  // centre-half first-layer weights [16 chunks][9] float4 (BN1 folded in)
+    static constexpr int ctr_buf = wc_tab + 16 * 9 * 16;           // per producer warp: centre rows [PTS][4 parts] float4 of the current tile
+    static constexpr int total = ctr_buf + PROD_WARPS * PTS * 4 * 16;
     static constexpr int Z_COL = 128 + (GRAM ? 0 : 128);           // TMEM column stride of the two z accumulators
     static constexpr int G_COL0 = 256;                             // TMEM columns of the two Gram accumulators (256, 384)
 };
@@ -98,7 +100,7 @@ __device__ __forceinline__ uint32_t ht_off(int r, int e) {
 }
 
 template <bool ARG, bool GRAM>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 1)      // 13 warps: one scheduler hosts 4 of them -> 16384 / (4 * 32) = 128 registers per thread at most
 ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ W1,
               const float* __restrict__ stats1, const float* __restrict__ W2, const float* __restrict__ gamma2,
               float* __restrict__ zsel, unsigned char* __restrict__ ksel, double* __restrict__ part /*[grid][128]*/,
@@ -131,6 +133,13 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
         const uint32_t off = tile_off(c, j, COUT);
         *reinterpret_cast<float*>(sm + C::w2_hi + off) = hi;
         *reinterpret_cast<float*>(sm + C::w2_lo + off) = tf32_hi(w - hi);
+    }
+    for (int i = tid; i < 16 * 9; i += THREADS) {                   // centre half of the first layer: columns 9..17 of W1, BN1 scale folded in
+        const int ch = i / 9, q = i % 9;
+        float w[4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) w[s4] = __ldg(W1 + (4 * ch + s4) * CIN + 9 + q) * stats1[128 + 4 * ch + s4];
+        *reinterpret_cast<float4*>(sm + C::wc_tab + i * 16) = make_float4(w[0], w[1], w[2], w[3]);
     }
     if (GRAM) {                                                     // extra rows of the transposed tiles: ones, then zeros
         for (int s = 0; s < 2; ++s) {
@@ -165,8 +174,12 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
         const int part = lane >> 3;                     // hidden channels 16 part .. 16 part + 15 (the Gram row mapping of ht_row)
         const int c4 = part * 4 + (pw & 3);             // my 16-byte chunk of the hidden vector: channels 4 c4 .. 4 c4 + 3, for the whole kernel
         const int eb = lane & 7;                        // my edge inside an 8-edge block
-        // first layer with the BatchNorm-1 affine folded in:  v1 = (scale1 W1) e + (beta1 - scale1 mean1), in registers
-        float2 w01[CIN], w23[CIN];
+        // first layer with the BatchNorm-1 affine folded in:  v1 = (scale1 W1) e + (beta1 - scale1 mean1).  The edge vector is
+        // (x_j - x_i, x_i): the centre half  bias + Wc x_i  is the same for the 20 edges of a point and is evaluated ONCE per point and
+        // tile (each warp for its own 4 chunks, below); only the 9 difference columns are per-edge work and only their weights
+        // (36 registers instead of 72) stay in registers for the whole kernel.
+        constexpr int CD = 9;
+        float2 w01[CD], w23[CD];
         float4 bias;
         {
             float sc[4], bb[4];
@@ -177,12 +190,14 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                 bb[s4] = fmaf(-stats1[128 + c], stats1[c], stats1[192 + c]);
             }
 #pragma unroll
-            for (int q = 0; q < CIN; ++q) {
+            for (int q = 0; q < CD; ++q) {
                 w01[q] = make_float2(__ldg(W1 + (4 * c4 + 0) * CIN + q) * sc[0], __ldg(W1 + (4 * c4 + 1) * CIN + q) * sc[1]);
                 w23[q] = make_float2(__ldg(W1 + (4 * c4 + 2) * CIN + q) * sc[2], __ldg(W1 + (4 * c4 + 3) * CIN + q) * sc[3]);
             }
             bias = make_float4(bb[0], bb[1], bb[2], bb[3]);
         }
+        const float4* wc = reinterpret_cast<const float4*>(sm + C::wc_tab) + c4 * 9;
+        unsigned char* ctr = sm + C::ctr_buf + pw * (C::PTS * 4 * 16);
         // gather pipeline: neighbour indices by LDG two iterations before they are needed, rows by cp.async RING - 1 tiles ahead
         constexpr int RING = C::RING;
         const bool gatherer = ptid < TE;                // fetches x_j of edge row `ptid`
@@ -210,8 +225,7 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                 const bool v = j >= 0;
                 const float* src = x12 + (size_t)(v ? j : 0) * 12;
                 unsigned char* dst = raw + ptid * 48;
-                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
-                *reinterpret_cast<uint32_t*>(raw + TE * 48 + C::PTS * 48 + ptid * 4) = v ? 1u : 0u;
+                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);      // !v: zero fill -> pad lane 11 = 0 marks the edge invalid
             }
             if (pgatherer) {
                 const long long pt = g_begin / KNN + (long long)t * C::PTS + ptid;
@@ -236,28 +250,50 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
             asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");         // everybody's have, and everybody is done with tile t - 1
             issue_rows(t + RING - 1, staged_index(t + RING - 1));                    // refill the slot tile t - 1 used
             const unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
+            if (eb < C::PTS) {                           // lane (part, eb): centre row of point eb of the tile for my chunk c4
+                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + eb * 48);
+                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
+                const float xi[CD] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+                float2 c01 = make_float2(bias.x, bias.y), c23 = make_float2(bias.z, bias.w);
+#pragma unroll
+                for (int q = 0; q < CD; ++q) {
+                    const float4 w = wc[q];
+                    const float2 xx = make_float2(xi[q], xi[q]);
+                    ffma2(c01, make_float2(w.x, w.y), xx);
+                    ffma2(c23, make_float2(w.z, w.w), xx);
+                }
+                *reinterpret_cast<float4*>(ctr + (eb * 4 + part) * 16) = make_float4(c01.x, c01.y, c23.x, c23.y);
+            }
+            __syncwarp();
             mbar_wait(&bar_empty[st], ph ^ 1u);
             unsigned char* dst_hi = sm + C::stage0 + st * C::STAGE_BYTES;
             unsigned char* dst_lo = dst_hi + C::TILE_BYTES;
             unsigned char* dst_t = dst_lo + C::TILE_BYTES;
-#pragma unroll 1
-            for (int blk = grp; blk < C::BLOCKS; blk += 2) {
+            // two 8-edge blocks in flight per thread: the shared-memory loads of the next block are issued before the arithmetic of the
+            // current one (ncu source view of the one-block loop: 22 % of the producers' samples waited on LDS, 24 % on dependent FMAs)
+            struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; };
+            auto load_blk = [&](int blk, Blk& B) {
                 const int er = blk * 8 + eb;            // edge row in the tile
+                const int pt = (er * 205) >> 12;        // er / KNN, exact for er < 1039
                 const float4* rj = reinterpret_cast<const float4*>(raw + er * 48);                       // 48-byte stride: conflict-free
-                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + (er / KNN) * 48);     // the edge's own point (broadcast)
-                const float4 b0 = rj[0], b1 = rj[1], b2 = rj[2];
-                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
-                const float ev[CIN] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w, b1.x - a1.x, b1.y - a1.y, b1.z - a1.z, b1.w - a1.w, b2.x - a2.x,
-                                       a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
-                float2 y01 = make_float2(bias.x, bias.y), y23 = make_float2(bias.z, bias.w);
+                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + pt * 48);             // the edge's own point (broadcast)
+                B.b0 = rj[0]; B.b1 = rj[1]; B.b2 = rj[2];
+                B.a0 = ri[0]; B.a1 = ri[1]; B.a2 = ri[2];
+                B.cc = *reinterpret_cast<const float4*>(ctr + (pt * 4 + part) * 16);
+            };
+            auto finish_blk = [&](int blk, const Blk& B) {
+                const int er = blk * 8 + eb;
+                const float ev[CD] = {B.b0.x - B.a0.x, B.b0.y - B.a0.y, B.b0.z - B.a0.z, B.b0.w - B.a0.w, B.b1.x - B.a1.x, B.b1.y - B.a1.y,
+                                      B.b1.z - B.a1.z, B.b1.w - B.a1.w, B.b2.x - B.a2.x};
+                float2 y01 = make_float2(B.cc.x, B.cc.y), y23 = make_float2(B.cc.z, B.cc.w);
 #pragma unroll
-                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CIN); ++q) {
+                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CD); ++q) {
                     const float2 ee = make_float2(ev[q], ev[q]);
                     ffma2(y01, w01[q], ee);
                     ffma2(y23, w23[q], ee);
                 }
-                const bool valid = *reinterpret_cast<const uint32_t*>(raw + TE * 48 + C::PTS * 48 + er * 4) != 0u;
-                const float4 y = valid ? make_float4(lrelu(y01.x), lrelu(y01.y), lrelu(y23.x), lrelu(y23.y)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float vm = B.b2.w;                 // 1 for a gathered row, 0 for a zero-filled one (edge outside the CTA's range)
+                const float4 y = make_float4(lrelu(y01.x) * vm, lrelu(y01.y) * vm, lrelu(y23.x) * vm, lrelu(y23.y) * vm);
                 const float4 hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
                 const float4 lo = make_float4(tf32_hi(y.x - hi.x), tf32_hi(y.y - hi.y), tf32_hi(y.z - hi.z), tf32_hi(y.w - hi.w));
                 const uint32_t off = (uint32_t)c4 * (TE * 16) + (uint32_t)(er >> 3) * 128 + (uint32_t)(er & 7) * 16;
@@ -272,7 +308,18 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                         *reinterpret_cast<float*>(dst_t + ht_off(64 + r, er)) = hv[s4];
                     }
                 }
+            };
+            Blk A, Bq;
+            int blk = grp;
+            load_blk(blk, A);
+#pragma unroll 1
+            for (; blk + 2 < C::BLOCKS; blk += 4) {
+                load_blk(blk + 2, Bq);
+                finish_blk(blk, A);
+                if (blk + 4 < C::BLOCKS) load_blk(blk + 4, A);
+                finish_blk(blk + 2, Bq);
             }
+            if (blk < C::BLOCKS) finish_blk(blk, A);    // odd number of blocks per warp (TE = 80)
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[st]);
@@ -290,7 +337,7 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
             mbar_wait(&bar_tempty[st], ph ^ 1u);
             if (GRAM && t % FLUSH == 0) mbar_wait(&bar_gempty[gb], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
             fence_after_sync();
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 const uint32_t b_hi = smem_u32(sm + C::stage0 + st * C::STAGE_BYTES), b_lo = b_hi + C::TILE_BYTES;
                 const uint32_t d = tmem + (uint32_t)(st * C::Z_COL);
 #pragma unroll
@@ -326,7 +373,15 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
         const int c = warp * 16 + (lane & 15);
         const bool owner = lane < 16;
         const bool up = __ldg(gamma2 + c) > 0.f;
-        double S1 = 0.0, S2 = 0.0;
+        // running sums over the CTA's tiles as unevaluated fp32 pairs (two-sum): FP64 adds cost ~100 cycles per warp on this part
+        // (ncu source view: 10 % of the epilogue's samples sat on the two DADDs per tile)
+        float S1h = 0.f, S1l = 0.f, S2h = 0.f, S2l = 0.f;
+        auto two_sum = [](float& h, float& l, float x) {
+            const float s_ = h + x;
+            const float bb = s_ - h;
+            l += (h - (s_ - bb)) + (x - bb);
+            h = s_;
+        };
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
@@ -336,36 +391,59 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
             const int npts = (int)min((long long)C::PTS, (g_end - g0) / KNN);
             const long long p0 = g0 / KNN;
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * C::Z_COL);
-            float s1 = 0.f, s2 = 0.f;
+            float ps[4] = {0.f, 0.f, 0.f, 0.f}, qs[4] = {0.f, 0.f, 0.f, 0.f};      // four independent chains each for sum z and sum z^2
             // BN2 + LeakyReLU is monotone per channel, increasing iff gamma2 > 0: only that extreme of the 20 pre-activations (and its
-            // neighbour slot) is kept — one candidate array instead of max AND min (round 1), half the compare/select work.
-            // Warp-uniform fast paths for the usual cases (all scales positive / all negative).
-            auto scan = [&](auto better) {
-#pragma unroll 1
-                for (int pp = 0; pp < ((SGB_ABL & 2) ? 1 : npts); ++pp) {
-                    float v[16], u[4];
-                    tmem_ld16(taddr + (uint32_t)(pp * KNN), v);
-                    tmem_ld4(taddr + (uint32_t)(pp * KNN + 16), u);
-                    float best = v[0];
-                    int kb = 0;
-                    s1 += v[0]; s2 = fmaf(v[0], v[0], s2);
+            // neighbour slot) is kept.  The extreme is found by a tournament (depth 5 instead of a chain of 19 compare / select pairs; the
+            // left operand wins ties, so the FIRST extreme is kept exactly as in a left-to-right scan); two points per iteration share
+            // one tcgen05.wait::ld.  Warp-uniform fast paths for the usual cases (all scales positive / all negative).
+            auto reduce_point = [&](const uint32_t (&ra)[16], const uint32_t (&rb)[4], int pp, auto better) {
+                float z[KNN];
 #pragma unroll
-                    for (int i = 1; i < KNN; ++i) {
-                        const float z = i < 16 ? v[i] : u[i - 16];
-                        s1 += z; s2 = fmaf(z, z, s2);
-                        if (better(z, best)) { best = z; if (ARG) kb = i; }
+                for (int i = 0; i < KNN; ++i) z[i] = __uint_as_float(i < 16 ? ra[i] : rb[i - 16]);
+#pragma unroll
+                for (int i = 0; i < KNN; ++i) { ps[i & 3] += z[i]; qs[i & 3] = fmaf(z[i], z[i], qs[i & 3]); }
+                float m[10];
+                int k[10];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) { const bool r = better(z[2 * j + 1], z[2 * j]); m[j] = r ? z[2 * j + 1] : z[2 * j]; k[j] = r ? 2 * j + 1 : 2 * j; }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { const bool r = better(m[2 * j + 1], m[2 * j]); m[j] = r ? m[2 * j + 1] : m[2 * j]; k[j] = r ? k[2 * j + 1] : k[2 * j]; }
+                { const bool r = better(m[1], m[0]); m[0] = r ? m[1] : m[0]; k[0] = r ? k[1] : k[0]; }
+                { const bool r = better(m[3], m[2]); m[2] = r ? m[3] : m[2]; k[2] = r ? k[3] : k[2]; }
+                { const bool r = better(m[2], m[0]); m[0] = r ? m[2] : m[0]; k[0] = r ? k[2] : k[0]; }
+                { const bool r = better(m[4], m[0]); m[0] = r ? m[4] : m[0]; k[0] = r ? k[4] : k[0]; }
+                if (owner) {
+                    const size_t o = (size_t)(p0 + pp) * COUT + c;
+                    zsel[o] = m[0];
+                    if (ARG) ksel[o] = (unsigned char)k[0];
+                }
+            };
+            auto scan = [&](auto better) {
+                const int nloop = (SGB_ABL & 2) ? 1 : npts;
+#pragma unroll 1
+                for (int pp = 0; pp < nloop; pp += 2) {
+                    uint32_t a16[16], a4[4], b16[16], b4[4];
+                    const bool two = pp + 1 < nloop;         // warp-uniform
+                    tmem_ld16_issue(taddr + (uint32_t)(pp * KNN), a16);
+                    tmem_ld4_issue(taddr + (uint32_t)(pp * KNN + 16), a4);
+                    if (two) {
+                        tmem_ld16_issue(taddr + (uint32_t)((pp + 1) * KNN), b16);
+                        tmem_ld4_issue(taddr + (uint32_t)((pp + 1) * KNN + 16), b4);
                     }
-                    if (owner) {
-                        const size_t o = (size_t)(p0 + pp) * COUT + c;
-                        zsel[o] = best;
-                        if (ARG) ksel[o] = (unsigned char)kb;
+                    tmem_ld_wait();
+                    tmem_ld_pin20(a16, a4);
+                    reduce_point(a16, a4, pp, better);
+                    if (two) {
+                        tmem_ld_pin20(b16, b4);
+                        reduce_point(b16, b4, pp + 1, better);
                     }
                 }
             };
             if (__all_sync(SGB_FULL_MASK, up)) scan([](float z, float b) { return z > b; });
             else if (__all_sync(SGB_FULL_MASK, !up)) scan([](float z, float b) { return z < b; });
             else scan([up](float z, float b) { return up ? z > b : z < b; });
-            S1 += (double)s1; S2 += (double)s2;
+            two_sum(S1h, S1l, (ps[0] + ps[1]) + (ps[2] + ps[3]));
+            two_sum(S2h, S2l, (qs[0] + qs[1]) + (qs[2] + qs[3]));
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[st]);
@@ -390,8 +468,8 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
             }
         }
         if (owner) {
-            part[(size_t)blockIdx.x * 128 + c] = S1;
-            part[(size_t)blockIdx.x * 128 + 64 + c] = S2;
+            part[(size_t)blockIdx.x * 128 + c] = (double)S1h + (double)S1l;
+            part[(size_t)blockIdx.x * 128 + 64 + c] = (double)S2h + (double)S2l;
         }
     }
     fence_before_sync();

@@ -143,7 +143,7 @@ kpconv_bwd_w_tc_kernel(Args a) {
 
     if (warp == PROD_WARPS) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = make_idesc_tf32(128, a.Cout, false, false);
             const uint32_t g_hi = smem_u32(sG), g_lo = g_hi + (uint32_t)G_TILE;
             int it = 0;
@@ -349,7 +349,7 @@ kpconv_bwd_f_tc_kernel(Args a) {
 
     if (warp == PROD_WARPS) {
         // ------------------------------------------------------------------ TMA + MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = make_idesc_tf32(FQ, CW, false, false);
             for (int c = 0; c < 2 && c < NC; ++c) {
                 mbar_expect_tx(&full_b[c], (uint32_t)B_STAGE);

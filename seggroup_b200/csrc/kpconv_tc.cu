@@ -90,7 +90,7 @@ kpconv_tc_fwd_kernel(Args a) {
 
     if (warp == PROD_WARPS) {
         // ------------------------------------------------------------------ TMA + MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = make_idesc_tf32(TQ, a.Cout, false, false);
             for (int c = 0; c < 2 && c < NC; ++c) {
                 mbar_expect_tx(&full_b[c], (uint32_t)B_STAGE);

@@ -62,6 +62,23 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
 }
 
+// One lane of a converged warp (cute::elect_one_sync).  Guarding the MMA issue with THIS predicate instead of `lane == 0` lets the
+// compiler treat the branch as warp-uniform: with `lane == 0` every tcgen05.mma / commit was wrapped in its own ELECT + BRA.U.ANY loop
+// (4 extra dependent instructions per MMA in SASS), which made the single issuing thread co-critical (ncu: 80 % busy).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, %2;\n\t"
+        "@px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, rx;\n\t"
+        "}\n"
+        : "+r"(laneid), "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 // all previously issued tcgen05.mma of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
@@ -123,6 +140,26 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Split issue / wait (several loads in flight behind ONE wait): the registers are passed through the wait statement so that no use
+// of them can be scheduled ahead of it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// compiler-level dependency of 20 loaded registers on the preceding wait (emits no instruction)
+__device__ __forceinline__ void tmem_ld_pin20(uint32_t (&a)[16], uint32_t (&b)[4]) {
+    asm volatile("" : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]),
+                      "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]) :: "memory");
 }
 
 // byte offset of (row r, column c) in a K-major SWIZZLE_128B fp32 tile with R rows: 32-column blocks of R x 128 B, atoms of

@@ -75,7 +75,7 @@ gemm_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
         }
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one_sync()) {
             fence_after_sync();
 #pragma unroll
             for (int i = 0; i < TG_KC / 8; ++i) {
