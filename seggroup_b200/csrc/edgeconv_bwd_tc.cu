@@ -255,14 +255,15 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             unsigned char* dst_ecl = dst_ech + EC_BYTES;
             unsigned char* dst_mt = dst_ecl + EC_BYTES;
             struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; };
+            const uint32_t raw_s = smem_u32(raw), ctr_s = smem_u32(ctr);
             auto load_blk = [&](int blk, Blk& B) {
                 const int er = blk * 8 + eb;
                 const int pt = (er * 205) >> 12;        // er / KNN, exact for er < 1039
-                const float4* rj = reinterpret_cast<const float4*>(raw + er * 48);
-                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + pt * 48);
-                B.b0 = rj[0]; B.b1 = rj[1]; B.b2 = rj[2];
-                B.a0 = ri[0]; B.a1 = ri[1]; B.a2 = ri[2];
-                B.cc = *reinterpret_cast<const float4*>(ctr + (pt * 4 + part) * 16);
+                const uint32_t rj = raw_s + (uint32_t)(er * 48);
+                const uint32_t ri = raw_s + (uint32_t)(TE * 48 + pt * 48);
+                B.b0 = lds128_ordered(rj); B.b1 = lds128_ordered(rj + 16); B.b2 = lds128_ordered(rj + 32);
+                B.a0 = lds128_ordered(ri); B.a1 = lds128_ordered(ri + 16); B.a2 = lds128_ordered(ri + 32);
+                B.cc = lds128_ordered(ctr_s + (uint32_t)((pt * 4 + part) * 16));
             };
             auto finish_blk = [&](int blk, const Blk& B) {
                 const int er = blk * 8 + eb;

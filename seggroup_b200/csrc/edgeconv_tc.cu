@@ -198,6 +198,13 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
         }
         const float4* wc = reinterpret_cast<const float4*>(sm + C::wc_tab) + c4 * 9;
         unsigned char* ctr = sm + C::ctr_buf + pw * (C::PTS * 4 * 16);
+        uint32_t ht_rb[4], ht_rx[4];                    // my 4 rows of the transposed tile: byte offset of the row, swizzle term
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int r = ht_row(part, (pw & 3) * 4 + s4);
+            ht_rb[s4] = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
+            ht_rx[s4] = (uint32_t)(((r >> 1) & 3) << 4);
+        }
         // gather pipeline: neighbour indices by LDG two iterations before they are needed, rows by cp.async RING - 1 tiles ahead
         constexpr int RING = C::RING;
         const bool gatherer = ptid < TE;                // fetches x_j of edge row `ptid`
@@ -272,14 +279,15 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
             // two 8-edge blocks in flight per thread: the shared-memory loads of the next block are issued before the arithmetic of the
             // current one (ncu source view of the one-block loop: 22 % of the producers' samples waited on LDS, 24 % on dependent FMAs)
             struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; };
+            const uint32_t raw_s = smem_u32(raw), ctr_s = smem_u32(ctr);
             auto load_blk = [&](int blk, Blk& B) {
                 const int er = blk * 8 + eb;            // edge row in the tile
                 const int pt = (er * 205) >> 12;        // er / KNN, exact for er < 1039
-                const float4* rj = reinterpret_cast<const float4*>(raw + er * 48);                       // 48-byte stride: conflict-free
-                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + pt * 48);             // the edge's own point (broadcast)
-                B.b0 = rj[0]; B.b1 = rj[1]; B.b2 = rj[2];
-                B.a0 = ri[0]; B.a1 = ri[1]; B.a2 = ri[2];
-                B.cc = *reinterpret_cast<const float4*>(ctr + (pt * 4 + part) * 16);
+                const uint32_t rj = raw_s + (uint32_t)(er * 48);                                          // 48-byte stride: conflict-free
+                const uint32_t ri = raw_s + (uint32_t)(TE * 48 + pt * 48);                                // the edge's own point (broadcast)
+                B.b0 = lds128_ordered(rj); B.b1 = lds128_ordered(rj + 16); B.b2 = lds128_ordered(rj + 32);
+                B.a0 = lds128_ordered(ri); B.a1 = lds128_ordered(ri + 16); B.a2 = lds128_ordered(ri + 32);
+                B.cc = lds128_ordered(ctr_s + (uint32_t)((pt * 4 + part) * 16));
             };
             auto finish_blk = [&](int blk, const Blk& B) {
                 const int er = blk * 8 + eb;
@@ -301,11 +309,12 @@ ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N,
                 *reinterpret_cast<float4*>(dst_lo + off) = lo;
                 if (GRAM && !(SGB_ABL & 16)) {          // transposed copy: rows 0..63 lo, 64..127 hi
                     const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+                    const uint32_t e1 = (uint32_t)((er >> 4) * (GR * 64) + (er & 3) * 4), eq = (uint32_t)(((er & 15) >> 2) << 4);
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4) {
-                        const int r = ht_row(part, (pw & 3) * 4 + s4);
-                        *reinterpret_cast<float*>(dst_t + ht_off(r, er)) = lv[s4];
-                        *reinterpret_cast<float*>(dst_t + ht_off(64 + r, er)) = hv[s4];
+                    for (int s4 = 0; s4 < 4; ++s4) {      // ht_off(r, er) with the row-dependent terms hoisted (ht_rb / ht_rx); row 64 + r = + 8 atoms
+                        const uint32_t o = ht_rb[s4] + e1 + (eq ^ ht_rx[s4]);
+                        *reinterpret_cast<float*>(dst_t + o) = lv[s4];
+                        *reinterpret_cast<float*>(dst_t + o + 8 * 512) = hv[s4];
                     }
                 }
             };

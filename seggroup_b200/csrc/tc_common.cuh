@@ -187,6 +187,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16-byte shared-memory load that the compiler may not move across other memory operations: keeps software-pipelined loads
+// (next block) AHEAD of the stores of the current block instead of being sunk next to their first use
+__device__ __forceinline__ float4 lds128_ordered(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // packed fp32x2 fused multiply-add (Blackwell FFMA2): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}, each lane IEEE fma.rn
 __device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
     unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);

@@ -83,11 +83,15 @@ _PARAM_KEYS = ["mlp_1.conv1.0.weight", "mlp_1.bn1.weight", "mlp_1.bn1.bias",
 _writer = None
 
 
+def _writer_threads():
+    return int(os.environ.get("SGB_EXPORT_THREADS", "0")) or max(2, min(32, (os.cpu_count() or 4) - 2))
+
+
 def _get_writer():
     global _writer
     if _writer is None:
         # text formatting of 14 files x 150k lines per scene is ~15 ms of host time per scene: a pool keeps up with batches
-        n = int(os.environ.get("SGB_EXPORT_THREADS", "0")) or max(2, min(32, (os.cpu_count() or 4) - 2))   # pure C inside, GIL released
+        n = _writer_threads()                                             # pure C inside, GIL released
         _writer = ThreadPoolExecutor(max_workers=n, thread_name_prefix="sgb-export")
         atexit.register(lambda: _writer.shutdown(wait=True))
     return _writer
@@ -205,6 +209,7 @@ class SegModel(nn.Module):
         mods = {"mlp_1.bn1": self.mlp_1.bn1, "mlp_2.bn1": self.mlp_2.bn1, "mlp_3.bn1": self.mlp_3.bn1, "mlp_3.bn2": self.mlp_3.bn2,
                 "classifier.bn1": self.classifier.bn1}
         with torch.no_grad():
+            bufs, upd, keeps, counters = [], [], [], []
             for k, (mean, var, counts) in res.bn_stats_scenes.items():
                 bn = mods.get(k)
                 if bn is None or not bn.training:
@@ -225,9 +230,14 @@ class SegModel(nn.Module):
                 if w is None:
                     w = self._bn_cache[key] = torch.tensor([m * (1.0 - m) ** (n - 1 - b) for b in range(n)], dtype=var.dtype, device=dev)
                 keep = (1.0 - m) ** n
-                bn.running_mean.mul_(keep).add_(w @ mean)
-                bn.running_var.mul_(keep).add_((w * corr) @ var)
-                bn.num_batches_tracked += n
+                bufs += [bn.running_mean, bn.running_var]
+                upd += [w @ mean, (w * corr) @ var]
+                keeps += [keep, keep]
+                counters.append((bn.num_batches_tracked, n))
+            if bufs:                                                   # all buffers of the model in two multi-tensor launches
+                torch._foreach_mul_(bufs, keeps)
+                torch._foreach_add_(bufs, upd)
+                torch._foreach_add_([c for c, _ in counters], [n for _, n in counters])
 
     # ---- label export (model.py:525-605): D2H on a side stream into pinned buffers, text formatting on writer threads
     def _pinned(self, shape):
@@ -269,15 +279,21 @@ class SegModel(nn.Module):
             done.record(self._copy_stream)
         self.d2h_bytes += stacked.numel() * 4
         raw_off = res.raw_off
-        n_tasks = len(keys) * len(output_roots)
-        state = {"left": n_tasks}
+        # one task per (scene, run of label files): about as many tasks as writer threads (submitting 112 single-file futures per
+        # 8-scene batch cost 1.5 ms of host time per step)
+        n_files, n_sc = len(keys), len(output_roots)
+        per_scene = max(1, min(n_files, _writer_threads() // max(1, n_sc)))
+        step = -(-n_files // per_scene)
+        tasks = [(b, i0, min(i0 + step, n_files)) for b in range(n_sc) for i0 in range(0, n_files, step)]
+        state = {"left": len(tasks)}
 
-        def write(i, b):
+        def write(b, i0, i1):
             done.synchronize()
             lo, hi = raw_off[b], raw_off[b + 1]
-            path = os.path.join(output_roots[b], keys[i] + ".txt")
-            with self._path_lock(path):                                     # two forwards of the same scene / epoch: never interleaved
-                _lib.call("sgb_write_labels_host", path.encode(), host[i, lo:hi].numpy(), hi - lo)
+            for i in range(i0, i1):
+                path = os.path.join(output_roots[b], keys[i] + ".txt")
+                with self._path_lock(path):                                 # two forwards of the same scene / epoch: never interleaved
+                    _lib.call("sgb_write_labels_host", path.encode(), host[i, lo:hi].numpy(), hi - lo)
             with self._io_lock:
                 state["left"] -= 1
                 if state["left"] == 0:
@@ -285,11 +301,10 @@ class SegModel(nn.Module):
 
         if self.async_export:
             w = _get_writer()
-            self._pending += [w.submit(write, i, b) for b in range(len(output_roots)) for i in range(len(keys))]
+            self._pending += [w.submit(write, *t) for t in tasks]
         else:
-            for b in range(len(output_roots)):
-                for i in range(len(keys)):
-                    write(i, b)
+            for t in tasks:
+                write(*t)
 
     def _path_lock(self, path):
         with self._io_lock:
