@@ -4,28 +4,80 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "../../include/seggroup_b200.h"
 
-// Two digits per step from a 200-byte table; a repeated value (labels come in runs: neighbouring raw vertices mostly share a
-// cluster) re-uses the previous line.  ~2 ns per line instead of ~9 for the division loop, which matters because the reference
-// writes 14 files x N_raw lines per scene per forward (112 files per 8-scene batch) and the writer threads must keep up.
-static const char kDigits[201] =
-    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869"
-    "707172737475767778798081828384858687888990919293949596979899";
+// Formatting is branch-free for 0 <= |v| < 10^8: both 4-digit halves come from a 40 KB table (zero padded), the digit count from
+// the bit length, and the line is assembled in two 64-bit registers (shift out the leading zeros, OR in '\n') and stored with two
+// 8-byte writes — no byte loop, no store-to-load forwarding through a scratch line; a repeated value
+// (labels come in runs: neighbouring raw vertices mostly share a cluster) re-uses the previous line.  2.3 ns per line on label
+// vectors with runs, 3-4 ns on random ones (the division loop it replaces: 11-17 ns, branch mispredictions) — which matters
+// because the reference writes 14 files x N_raw lines per scene per forward (112 files per 8-scene batch) and, with one process
+// per GPU, eight ranks share the host cores for it.
+static char kLut4[10000][4];
+static const unsigned kPow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+static struct LutInit {
+    LutInit() {
+        for (int v = 0; v < 10000; ++v) {
+            kLut4[v][0] = (char)('0' + v / 1000); kLut4[v][1] = (char)('0' + (v / 100) % 10);
+            kLut4[v][2] = (char)('0' + (v / 10) % 10); kLut4[v][3] = (char)('0' + v % 10);
+        }
+    }
+} kLutInit;
 
-static inline int format_line(long long v, char* out) {       // "%d\n" -> out, returns the length
-    char tmp[24];
-    int len = 0;
+struct Line { unsigned long long w0, w1; int len; };     // the characters of one line, little endian, in two registers
+
+static inline Line format_slow(long long v) {           // |v| >= 10^8: at most "-2147483648\n" = 12 characters
+    char tmp[16] = {0};
+    const int len = snprintf(tmp, sizeof(tmp), "%lld\n", v);
+    Line L;
+    memcpy(&L.w0, tmp, 8);
+    memcpy(&L.w1, tmp + 8, 8);
+    L.len = len;
+    return L;
+}
+
+static inline Line format_line(long long v) {           // "%d\n"
     const bool neg = v < 0;
-    unsigned long long u = neg ? (unsigned long long)(-v) : (unsigned long long)v;
-    while (u >= 100) { const unsigned r = (unsigned)(u % 100); u /= 100; tmp[len++] = kDigits[2 * r + 1]; tmp[len++] = kDigits[2 * r]; }
-    if (u >= 10) { tmp[len++] = kDigits[2 * u + 1]; tmp[len++] = kDigits[2 * u]; }
-    else tmp[len++] = (char)('0' + u);
-    int pos = 0;
-    if (neg) out[pos++] = '-';
-    while (len) out[pos++] = tmp[--len];
-    out[pos++] = '\n';
-    return pos;
+    const unsigned long long u64 = neg ? (unsigned long long)(-v) : (unsigned long long)v;
+    if (u64 >= 100000000ull) return format_slow(v);
+    const unsigned u = (unsigned)u64;
+    const unsigned hi = u / 10000u, lo = u - hi * 10000u;
+    unsigned d_hi, d_lo;
+    memcpy(&d_hi, kLut4[hi], 4);
+    memcpy(&d_lo, kLut4[lo], 4);
+    const unsigned long long D = (unsigned long long)d_hi | ((unsigned long long)d_lo << 32);      // 8 zero-padded digits, first digit in byte 0
+    const int t = ((32 - __builtin_clz(u | 1u)) * 1233) >> 12;            // floor(log10(u)) or one more
+    const int nd0 = t + 1 - (u < kPow10[t] ? 1 : 0);
+    const int nd = nd0 < 1 ? 1 : nd0;                                      // digits to print
+    Line L;
+    L.w0 = D >> (8 * (8 - nd));                                            // drop the leading zeros
+    L.w0 |= nd < 8 ? (0x0aull << ((8 * nd) & 63)) : 0ull;                  // '\n' after the last digit
+    L.w1 = nd < 8 ? 0ull : 0x0aull;
+    L.len = nd + 1;
+    if (neg) {
+        L.w1 = (L.w1 << 8) | (L.w0 >> 56);
+        L.w0 = (L.w0 << 8) | (unsigned long long)'-';
+        L.len += 1;
+    }
+    return L;
+}
+
+// Values in [-1, 2^20 - 2] (every label this path writes: class ids, instance ids, cluster root point ids of scenes below a million
+// points, -1 for "unlabeled") take one load from a table of complete lines: entry = the characters of "%d\n", left aligned in 8
+// bytes (at most "1048574\n"), the length is 8 - (leading zero bytes).  A label vector holds a few thousand DISTINCT values, so the
+// entries it touches stay in L1 / L2 whatever the order of the vertices (the synthetic scenes of the bench have no runs at all).
+static const unsigned kTab = 1u << 20;
+static unsigned long long* g_line_tab = nullptr;
+static std::once_flag g_line_once;
+static void build_line_tab() {
+    unsigned long long* t = (unsigned long long*)malloc((size_t)kTab * sizeof(unsigned long long));
+    if (!t) return;
+    for (unsigned i = 0; i < kTab; ++i) {
+        const Line L = format_line((long long)i - 1);
+        t[i] = L.w0;                                              // at most 8 characters: w1 is empty
+    }
+    g_line_tab = t;
 }
 
 extern "C" int sgb_write_labels_host(const char* path, const int* values, int n) {
@@ -34,17 +86,30 @@ extern "C" int sgb_write_labels_host(const char* path, const int* values, int n)
     if (!f) return SGB_ERR_INVALID;
     setvbuf(f, nullptr, _IONBF, 0);                               // our own 1 MB buffer below
     const size_t cap = 1 << 20;
-    char* buf = (char*)malloc(cap + 32);
+    char* buf = (char*)malloc(cap + 64);
     if (!buf) { fclose(f); return SGB_ERR_INVALID; }
     size_t pos = 0;
     bool ok = true;
-    char last[16] = {0};
-    int last_len = 0, last_val = 0;
+    std::call_once(g_line_once, build_line_tab);
+    const unsigned long long* tab = g_line_tab;
+    Line last = {0ull, 0ull, 0};                                  // kept in registers: no store -> load round trip per line
+    int last_val = 0;
     for (int i = 0; i < n; ++i) {
         const int v = values[i];
-        if (last_len == 0 || v != last_val) { last_len = format_line(v, last); last_val = v; }
-        memcpy(buf + pos, last, 16);                              // one unaligned 16-byte store; only last_len bytes count
-        pos += last_len;
+        if (last.len == 0 || v != last_val) {                     // a run re-uses the previous line
+            const unsigned idx = (unsigned)v + 1u;
+            if (tab && idx < kTab) {                              // the table path (see above)
+                const unsigned long long e = tab[idx];
+                last.w0 = e; last.w1 = 0ull;
+                last.len = 8 - (__builtin_clzll(e) >> 3);
+            } else {
+                last = format_line(v);
+            }
+            last_val = v;
+        }
+        memcpy(buf + pos, &last.w0, 8);                           // two 8-byte stores; only last.len bytes count
+        memcpy(buf + pos + 8, &last.w1, 8);
+        pos += (size_t)last.len;
         if (pos >= cap) { ok = ok && fwrite(buf, 1, pos, f) == pos; pos = 0; }
     }
     if (pos) ok = ok && fwrite(buf, 1, pos, f) == pos;

@@ -84,7 +84,14 @@ _writer = None
 
 
 def _writer_threads():
-    return int(os.environ.get("SGB_EXPORT_THREADS", "0")) or max(2, min(32, (os.cpu_count() or 4) - 2))
+    """Writer threads of THIS process: the host cores are shared by the ranks of the node (one process per GPU), and every rank also
+    needs a core for the thread that drives its step — 8 ranks x 30 writers on 32 cores starved the step threads (measured)."""
+    n = int(os.environ.get("SGB_EXPORT_THREADS", "0"))
+    if n > 0:
+        return n
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    cores = os.cpu_count() or 4
+    return max(2, min(32, (cores - ranks) // ranks))
 
 
 def _get_writer():
