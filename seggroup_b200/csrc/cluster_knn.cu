@@ -146,26 +146,33 @@ knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ c
     const float2 one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
     const float2 nx2 = make_float2(-me.x, -me.x), ny2 = make_float2(-me.y, -me.y), nz2 = make_float2(-me.z, -me.z);
 
-    float sc[K];
-    int ps[K];
+    // top K as 64-bit keys (monotone key of the score << 32 | ~member position): a larger key is a better candidate under the
+    // ranking (score desc, member position asc), so one unsigned 64-bit comparison (two ISETP) decides, ties included
+    uint32_t khi[K], klo[K];
+    const uint32_t kmin = sgb_float_key(-INFINITY);
 #pragma unroll
-    for (int t = 0; t < K; ++t) { sc[t] = -INFINITY; ps[t] = 0x7fffffff; }
+    for (int t = 0; t < K; ++t) { khi[t] = kmin; klo[t] = 0u; }            // klo 0 = position 0xffffffff: loses every tie
     float T = INFINITY;                             // stopping / rejection radius^2 = -score_k + 2 err
 
     auto consider = [&](int t) {                    // exact score of candidate t of the staged chunk; insertion into the top K
         const float4 cand = make_float4(s_x[w][t], s_y[w][t], s_z[w][t], s_w[w][t]);
-        const float s = score_ref(me.x, me.y, me.z, me.w, cand);
-        const int p = s_pos[w][t];
-        if (s > sc[K - 1] || (s == sc[K - 1] && p < ps[K - 1])) {
-            sc[K - 1] = s; ps[K - 1] = p;
+        const float s = score_ref(me.x, me.y, me.z, me.w, cand) + 0.f;       // + 0: -0.0 and +0.0 are one score
+        const uint32_t nh = sgb_float_key(s), nl = ~(uint32_t)s_pos[w][t];
+        const unsigned long long nk = ((unsigned long long)nh << 32) | nl;
+        auto key_at = [&](int q) { return ((unsigned long long)khi[q] << 32) | klo[q]; };
+        bool c_q = nk > key_at(K - 1);              // better than the current K-th?
+        if (c_q) {
+            // Shift-insertion, descending order: the entries the new key beats move down by one slot, the new key takes the first
+            // such slot.  Every step reads only OLD values (walking upwards from the bottom), so the K steps are independent
+            // (round 1 bubbled the new entry up through a chain of 19 dependent compare-and-swaps: ~150 instructions, serial).
 #pragma unroll
             for (int q = K - 1; q > 0; --q) {
-                if (sc[q] > sc[q - 1] || (sc[q] == sc[q - 1] && ps[q] < ps[q - 1])) {
-                    const float ts = sc[q]; sc[q] = sc[q - 1]; sc[q - 1] = ts;
-                    const int tp = ps[q]; ps[q] = ps[q - 1]; ps[q - 1] = tp;
-                }
+                const bool c_lo = nk > key_at(q - 1);                        // beats entry q - 1 as well?
+                if (c_q) { khi[q] = c_lo ? khi[q - 1] : nh; klo[q] = c_lo ? klo[q - 1] : nl; }
+                c_q = c_lo;
             }
-            T = -sc[K - 1] + err2;                  // +inf until K records have been seen
+            if (c_q) { khi[0] = nh; klo[0] = nl; }
+            T = -sgb_key_float(khi[K - 1]) + err2;  // +inf until K records have been seen
         }
     };
 
@@ -215,7 +222,7 @@ knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ c
     int L = i0, R = i0 + 32;                        // unprocessed records: (.., L) on the left, [R, ..) on the right
     bool flip = false;
     while (true) {
-        // per lane: is a side still able to contribute?  (ps[K-1] != sentinel <=> K records seen)
+        // per lane: is a side still able to contribute?
         bool open_l = false, open_r = false;
         if (searching) {
             if (L > lo) { const float d = cq - coord(rec[L - 1]); open_l = !(d * d * 0.999999f > T); }
@@ -238,7 +245,7 @@ knn_sweep_kernel(int N, const int* __restrict__ order, const int* __restrict__ c
         for (int t = 0; t < K; ++t) out[t] = (t < n) ? __ldg(order + lo + t) - base : 0;
     } else {
 #pragma unroll
-        for (int t = 0; t < K; ++t) out[t] = __ldg(order + ps[t]) - base;
+        for (int t = 0; t < K; ++t) out[t] = __ldg(order + (int)~klo[t]) - base;
     }
 }
 
