@@ -45,6 +45,24 @@ def test_host_label_writer(tmp_path):
     assert open(p).read() == "".join("%d\n" % x for x in v)
 
 
+def test_host_label_writer_every_path(tmp_path):
+    """All three formatting paths of sgb_write_labels_host against '%d\\n': the line table ([-1, 2^20 - 2]), the register-assembled
+    lines (|v| < 10^8, every digit count, negative values) and the snprintf path beyond; runs re-use the previous line."""
+    from seggroup_b200 import _lib
+    rng = np.random.default_rng(5)
+    edges = [0, -1, -2, 1, 9, 10, 99, 100, 999, 1000, 9999, 10000, 99999, 100000, 999999, 1000000, 1048573, 1048574, 1048575, 1048576,
+             9999999, 10000000, 99999999, 100000000, 999999999, 2147483647, -2147483648, -99999999, -100000000, -10000000, -9999999]
+    v = np.concatenate([np.arange(-300, 3000), np.array(edges), rng.integers(-2**31, 2**31 - 1, 20000), rng.integers(0, 10**8, 20000),
+                        rng.integers(-10**8, 0, 20000), rng.integers(1040000, 1060000, 5000), np.repeat(rng.integers(0, 3000, 500), 7)]).astype(np.int32)
+    p = str(tmp_path / "y.txt")
+    _lib.call("sgb_write_labels_host", p.encode(), v, len(v))
+    assert open(p).read() == "".join("%d\n" % x for x in v)
+    _lib.call("sgb_write_labels_host", p.encode(), v[:0], 0)             # empty vector -> empty file
+    assert open(p).read() == ""
+    with pytest.raises(_lib.SgbError):
+        _lib.call("sgb_write_labels_host", str(tmp_path / "no_such_dir" / "z.txt").encode(), v, len(v))
+
+
 def test_scene_file_loader_roundtrip(tmp_path, scene8k):
     from seggroup_b200 import synth
     from seggroup_b200.model import load_scene_files
