@@ -583,7 +583,7 @@ def forward(scene, params, mode="train", tie="torch", dropout_mask=None, want_gr
     logits = F.linear(h, p["classifier.linear2.weight"], p["classifier.linear2.bias"])
     loss_sum = smoothed_ce_sum(logits, torch.as_tensor(sem_gt, dtype=torch.long))
     out["logits"] = logits.detach().clone()
-    out["loss_raw"] = np.array([[float(loss_sum), float(len(groups))]], np.float32)
+    out["loss_raw"] = np.array([[float(loss_sum.detach()), float(len(groups))]], np.float32)
     if want_grads:
         (loss_sum / len(groups)).backward()
         out["grads"] = {k: (p[k].grad.clone() if p[k].grad is not None else None) for k in TRAINABLE}
