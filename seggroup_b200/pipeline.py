@@ -64,12 +64,25 @@ class SceneDevice:
             sg.append(sg[-1] + sc.seg_off.numel() - 1)
             rw.append(rw[-1] + (sc.unmap.numel() if sc.unmap is not None else sc.n_points))
         cat = torch.cat
-        seg_off = cat([scenes[0].seg_off[:1]] + [sc.seg_off[1:] + pt[i] for i, sc in enumerate(scenes)])
-        unmap = cat([(sc.unmap if sc.unmap is not None else torch.arange(sc.n_points, device=dev)) + pt[i] for i, sc in enumerate(scenes)])
+        # id arrays: one concatenation + ONE offset addition each (the offset of element e = first point of its scene, expanded from
+        # a [B] vector) instead of an addition per scene and array: ~20 launches instead of ~45 for 8 scenes
+        counts = [[sc.seg_off.numel() - 1 for sc in scenes], [sc.seg_members.numel() for sc in scenes], [sc.adj0.shape[0] for sc in scenes],
+                  [sc.unmap.numel() if sc.unmap is not None else sc.n_points for sc in scenes]]
+        meta = torch.tensor(counts + [pt[:-1]], dtype=torch.int64).to(dev, non_blocking=True)       # one small upload
+        base = meta[4]
+
+        def shifted(parts, row, width=1):
+            v = cat(parts)
+            off = torch.repeat_interleave(base, meta[row], output_size=sum(counts[row]))
+            return v.add_(off.to(v.dtype) if width == 1 else off.to(v.dtype).unsqueeze(1))
+
+        seg_off = cat([scenes[0].seg_off[:1], shifted([sc.seg_off[1:] for sc in scenes], 0)])
+        seg_members = shifted([sc.seg_members for sc in scenes], 1)
+        adj0 = shifted([sc.adj0 for sc in scenes], 2, width=2)
+        unmap = shifted([(sc.unmap if sc.unmap is not None else torch.arange(sc.n_points, device=dev)) for sc in scenes], 3)
         real = cat([sc.real_label for sc in scenes]) if all(sc.real_label is not None for sc in scenes) else None
         return SceneDevice(data=cat([sc.data for sc in scenes]), weak_label=cat([sc.weak_label for sc in scenes]), seg_off=seg_off,
-                           seg_members=cat([sc.seg_members + pt[i] for i, sc in enumerate(scenes)]),
-                           adj0=cat([sc.adj0 + pt[i] for i, sc in enumerate(scenes)]), unmap=unmap, real_label=real,
+                           seg_members=seg_members, adj0=adj0, unmap=unmap, real_label=real,
                            name="+".join(sc.name for sc in scenes), split=ops.SceneSplit(pt, sg, rw, dev))
 
     @staticmethod
@@ -180,8 +193,10 @@ class ClassifierHeadFn(torch.autograd.Function):
         return dfeat, dW1, dg, db, dW2, db2, None, None, None, None
 
 
-def _acc(total, part):
-    return part if total is None else total + part
+def _sum_scenes(parts):
+    """Sum of the per-scene parameter gradients of a batch in scene order: one stack + one reduction per parameter instead of a
+    chain of B - 1 additions (the step is host-bound between the clustering levels: 120 tiny launches per step otherwise)."""
+    return parts[0] if len(parts) == 1 else torch.stack(parts).sum(0)
 
 
 class Mlp1Fn(torch.autograd.Function):
@@ -210,11 +225,11 @@ class Mlp1Fn(torch.autograd.Function):
     def backward(ctx, g, *_):
         clouds, W, knn, arg_pt, stats, mom = ctx.saved_tensors
         g = g.contiguous()
-        gW = gg = gb = None
+        gW, gg, gb = [], [], []
         for b, (lo, hi) in enumerate(ctx.seg_ranges):       # fixed scene order -> deterministic sums
             w_, g_, b_ = ops.mlp1_bwd(g[lo:hi], clouds[lo:hi], knn[lo:hi], arg_pt[lo:hi], W, stats[b], mom[b])
-            gW, gg, gb = _acc(gW, w_), _acc(gg, g_), _acc(gb, b_)
-        return None, gW.view_as(W), gg, gb, None
+            gW.append(w_); gg.append(g_); gb.append(b_)
+        return None, _sum_scenes(gW).view_as(W), _sum_scenes(gg), _sum_scenes(gb), None
 
 
 class EdgeConvPoolFn(torch.autograd.Function):
@@ -262,7 +277,8 @@ class EdgeConvPoolFn(torch.autograd.Function):
             else:
                 r = ops.edgeconv_bwd(g[c0:c1], arg_b, argk[lo:hi], x9[lo:hi], knn[lo:hi], W1, stats1[b], mom1[b], ctr[b])
             for k, v in r.items():
-                acc[k] = _acc(acc.get(k), v)
+                acc.setdefault(k, []).append(v)
+        acc = {k: _sum_scenes(v) for k, v in acc.items()}
         if two:
             return (None, None, None, None, acc["gW1"].view_as(W1), acc["gg1"], acc["gb1"], acc["gW2"].view_as(W2), acc["gg2"], acc["gb2"], None, None)
         return (None, None, None, None, acc["gW1"].view_as(W1), acc["gg1"], acc["gb1"], None, None, None, None, None)

@@ -37,3 +37,22 @@ def test_running_statistics_closed_form_matches_sequential_updates(tmp_path, mon
             assert torch.allclose(bn.running_var, want[name][1], rtol=1e-5, atol=1e-6)
             assert int(bn.num_batches_tracked) == B
     assert int(model.mlp_3.bn1.num_batches_tracked) == 0
+
+
+def test_scene_batch_concat_offsets():
+    """SceneDevice.concat: ids of scene b are shifted by the first point of scene b (one expanded offset vector per array) — equal to
+    the per-scene formula, dtypes kept, inputs untouched."""
+    from seggroup_b200 import pipeline, synth
+    scs = [synth.make_scene(40 + i, 8000 + 500 * i) for i in range(3)]
+    sd = [pipeline.SceneDevice.from_host(s, device="cpu") for s in scs]
+    keep = [s.seg_members.clone() for s in sd]
+    b = pipeline.SceneDevice.concat(sd)
+    pt = [0]
+    for s in sd:
+        pt.append(pt[-1] + s.n_points)
+    assert torch.equal(b.seg_members, torch.cat([s.seg_members + pt[i] for i, s in enumerate(sd)])) and b.seg_members.dtype == torch.int32
+    assert torch.equal(b.adj0, torch.cat([s.adj0 + pt[i] for i, s in enumerate(sd)]))
+    assert torch.equal(b.unmap, torch.cat([s.unmap + pt[i] for i, s in enumerate(sd)])) and b.unmap.dtype == torch.int64
+    assert torch.equal(b.seg_off, torch.cat([sd[0].seg_off[:1]] + [s.seg_off[1:] + pt[i] for i, s in enumerate(sd)]))
+    assert b.split.pt_off == pt and b.n_scenes == 3
+    assert all(torch.equal(a, s.seg_members) for a, s in zip(keep, sd))
