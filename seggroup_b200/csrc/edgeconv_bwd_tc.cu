@@ -185,6 +185,9 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         }
         const float4* wc = reinterpret_cast<const float4*>(sm + off_wc) + c4 * 9;
         unsigned char* ctr = sm + off_ctr + pw * (PTS * 4 * 16);
+        // my EC rows: row c4 = (x_j[c4] - x_i[c4]) - ebar[c4] for c4 < 9, x_i[c4 - 9] - ebar[c4] otherwise; rows 16 + c4 for c4 < 3
+        const uint32_t ec_qj = (uint32_t)(c4 < 9 ? c4 : 0), ec_qi = (uint32_t)(c4 < 9 ? c4 : c4 - 9);
+        const float ebar0 = s_ebar[c4], ebar1 = c4 < 2 ? s_ebar[16 + c4] : 0.f;
         const bool gatherer = ptid < TE, pgatherer = ptid < PTS;
         auto edge_in_range = [&](int t) -> bool {
             const long long g = g_begin + (long long)t * TE + ptid;
@@ -254,7 +257,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             unsigned char* dst_ech = sm + off_e0 + (t % ERING) * ESTAGE_BYTES;
             unsigned char* dst_ecl = dst_ech + EC_BYTES;
             unsigned char* dst_mt = dst_ecl + EC_BYTES;
-            struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; };
+            struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; float ej, ei; };      // ej / ei: the entries of x_j / x_i my EC row is made of
             const uint32_t raw_s = smem_u32(raw), ctr_s = smem_u32(ctr);
             auto load_blk = [&](int blk, Blk& B) {
                 const int er = blk * 8 + eb;
@@ -264,6 +267,8 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 B.b0 = lds128_ordered(rj); B.b1 = lds128_ordered(rj + 16); B.b2 = lds128_ordered(rj + 32);
                 B.a0 = lds128_ordered(ri); B.a1 = lds128_ordered(ri + 16); B.a2 = lds128_ordered(ri + 32);
                 B.cc = lds128_ordered(ctr_s + (uint32_t)((pt * 4 + part) * 16));
+                B.ej = lds32_ordered(rj + ec_qj * 4);
+                B.ei = lds32_ordered(ri + ec_qi * 4);
             };
             auto finish_blk = [&](int blk, const Blk& B) {
                 const int er = blk * 8 + eb;
@@ -290,27 +295,27 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 *reinterpret_cast<float4*>(dst_lo + off) = lo;
                 dst_mt[er * 16 + c4] = (unsigned char)bits;     // sign bits of hidden channels 4 c4 .. 4 c4 + 3
                 // EC column of this edge (centred edge vector, then 1 for a real edge -> A0), spread over the 16 threads of the edge:
-                // thread c4 writes row c4, threads 0..2 also rows 16..18.  Values come straight from the gathered rows in shared memory
-                // (same subtraction as ev[]), so no register array is indexed dynamically.
+                // thread c4 writes row c4, threads 0..2 also rows 16..18.  The two entries row c4 is made of were fetched with the
+                // block's rows (load_blk), rows 16 / 17 are x_i[7] / x_i[8] (already in registers), the centres e-bar are per-thread
+                // constants: no shared-memory load sits between the arithmetic and these stores any more (ncu source view: 11 % of
+                // the producers' samples waited on them).
                 if (!(SGB_ABL & 16)) {
-                    const float* fj = reinterpret_cast<const float*>(raw + er * 48);
-                    const float* fi = reinterpret_cast<const float*>(raw + TE * 48 + ((er * 205) >> 12) * 48);
-                    auto ec_store = [&](int q) {
-                        float v = 0.f;
-                        if (valid) {
-                            if (q == CIN) v = 1.f;
-                            else {
-                                const float xi = fi[q < 9 ? q : q - 9];
-                                v = (q < 9 ? fj[q] - xi : xi) - s_ebar[q];
-                            }
-                        }
+                    const float vm = valid ? 1.f : 0.f;
+                    {
+                        const float v = ((c4 < 9 ? B.ej - B.ei : B.ei) - ebar0) * vm;
                         const float vh = tf32_hi(v);
-                        const uint32_t o = kmajor_off(q, er, TN);
+                        const uint32_t o = kmajor_off(c4, er, TN);
                         *reinterpret_cast<float*>(dst_ech + o) = vh;
                         *reinterpret_cast<float*>(dst_ecl + o) = tf32_hi(v - vh);
-                    };
-                    ec_store(c4);
-                    if (c4 < 3) ec_store(16 + c4);
+                    }
+                    if (c4 < 3) {
+                        const float x = c4 == 0 ? B.a1.w : B.a2.x;                     // x_i[7], x_i[8]
+                        const float v = (c4 == 2 ? 1.f : x - ebar1) * vm;
+                        const float vh = tf32_hi(v);
+                        const uint32_t o = kmajor_off(16 + c4, er, TN);
+                        *reinterpret_cast<float*>(dst_ech + o) = vh;
+                        *reinterpret_cast<float*>(dst_ecl + o) = tf32_hi(v - vh);
+                    }
                 }
             };
             Blk A, Bq;

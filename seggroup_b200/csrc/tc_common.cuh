@@ -195,6 +195,12 @@ __device__ __forceinline__ float4 lds128_ordered(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ float lds32_ordered(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // packed fp32x2 fused multiply-add (Blackwell FFMA2): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}, each lane IEEE fma.rn
 __device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
     unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);
