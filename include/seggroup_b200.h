@@ -72,6 +72,13 @@ int sgb_segment_pool_max_fwd(const float* feat, int n_rows, int C, const int* me
  * Deterministic when the segments are disjoint (every row has at most one owner), as in the model. */
 int sgb_segment_pool_max_bwd(const float* grad_out, const int* argmax, int S, int C,
                              float* grad_feat, void* stream);
+/* use_avg variant (seggroup/model.py:282-284, `torch.mean(Feat_old[indexs], dim=0)`; never enabled by the reference's callers):
+ * out[s,c] = mean over the rows of segment s (member-list order, fp32); an empty segment gives NaN as torch.mean does.
+ * Backward: grad_feat[row, c] += grad_out[s,c] / n_s for every row of segment s; grad_feat must be zero-filled (or hold a sum). */
+int sgb_segment_pool_mean_fwd(const float* feat, int n_rows, int C, const int* members, int n_members,
+                              const int* offsets, int S, float* out, void* stream);
+int sgb_segment_pool_mean_bwd(const float* grad_out, int S, int C, const int* members, int n_members,
+                              const int* offsets, float* grad_feat, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a5/a7  kNN inside clusters

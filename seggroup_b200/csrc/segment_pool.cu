@@ -345,3 +345,61 @@ extern "C" int sgb_segment_pool_max_bwd(const float* grad_out, const int* argmax
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// use_avg variant of aggregate_cluster_feature (seggroup/model.py:282-284): the mean over a segment's rows.  One warp per
+// segment, lanes over channels (coalesced row reads), rows added in member-list order in fp32 (torch.mean sums in another,
+// unspecified order: equal to ~1e-6 relative, not bitwise).  An empty segment gives NaN, as torch.mean of an empty slice.
+namespace {
+__global__ void __launch_bounds__(256)
+segment_mean_fwd_kernel(const float* __restrict__ feat, int C, const int* __restrict__ members, const int* __restrict__ offsets, int S,
+                        float* __restrict__ out) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= S) return;
+    const int lo = __ldg(offsets + s), hi = __ldg(offsets + s + 1);
+    const float inv = 1.f / (float)(hi - lo);          // 1 / 0 = inf -> 0 * inf = NaN below
+    for (int c = lane; c < C; c += 32) {
+        float acc = 0.f;
+        for (int q = lo; q < hi; ++q) {
+            const int r = members ? __ldg(members + q) : q;
+            acc += __ldg(feat + (size_t)r * C + c);
+        }
+        out[(size_t)s * C + c] = acc * inv;
+    }
+}
+__global__ void __launch_bounds__(256)
+segment_mean_bwd_kernel(const float* __restrict__ gout, int C, const int* __restrict__ members, const int* __restrict__ offsets, int S,
+                        float* __restrict__ gfeat) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= S) return;
+    const int lo = __ldg(offsets + s), hi = __ldg(offsets + s + 1);
+    if (hi <= lo) return;
+    const float inv = 1.f / (float)(hi - lo);
+    for (int c = lane; c < C; c += 32) {
+        const float g = __ldg(gout + (size_t)s * C + c) * inv;
+        for (int q = lo; q < hi; ++q) {
+            const int r = members ? __ldg(members + q) : q;
+            atomicAdd(gfeat + (size_t)r * C + c, g);      // one owner per row in the model -> deterministic there
+        }
+    }
+}
+}  // namespace
+
+extern "C" int sgb_segment_pool_mean_fwd(const float* feat, int n_rows, int C, const int* members, int n_members,
+                                         const int* offsets, int S, float* out, void* stream) {
+    if (S < 0 || C <= 0 || n_rows < 0 || n_members < 0) return SGB_ERR_INVALID;
+    if (S == 0) return SGB_OK;
+    if (!feat || !offsets || !out) return SGB_ERR_INVALID;
+    { segment_mean_fwd_kernel<<<sgb_div_up(S, 8), 256, 0, (cudaStream_t)stream>>>(feat, C, members, offsets, S, out); SGB_COUNT_LAUNCH(); }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+extern "C" int sgb_segment_pool_mean_bwd(const float* grad_out, int S, int C, const int* members, int n_members, const int* offsets,
+                                         float* grad_feat, void* stream) {
+    if (S < 0 || C <= 0 || n_members < 0) return SGB_ERR_INVALID;
+    if (S == 0) return SGB_OK;
+    if (!grad_out || !offsets || !grad_feat) return SGB_ERR_INVALID;
+    { segment_mean_bwd_kernel<<<sgb_div_up(S, 8), 256, 0, (cudaStream_t)stream>>>(grad_out, C, members, offsets, S, grad_feat); SGB_COUNT_LAUNCH(); }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}

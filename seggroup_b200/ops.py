@@ -67,6 +67,26 @@ def segment_pool_max_bwd(grad_out, argmax, n_rows):
     return g
 
 
+def segment_pool_mean(feat, offsets, members=None):
+    """use_avg variant of aggregate_cluster_feature (model.py:282-284): feat [R,C] f32 -> [S,C] row means of the segments."""
+    _chk(feat, F32, "feat"); _chk(offsets, I32, "offsets")
+    R, C = feat.shape
+    S = offsets.numel() - 1
+    M = R if members is None else _chk(members, I32, "members").numel()
+    out = torch.empty(S, C, dtype=F32, device=feat.device)
+    _lib.call("sgb_segment_pool_mean_fwd", feat, R, C, members, M, offsets, S, out, _stream())
+    return out
+
+
+def segment_pool_mean_bwd(grad_out, offsets, members, n_rows):
+    _chk(grad_out, F32, "grad_out"); _chk(offsets, I32, "offsets")
+    S, C = grad_out.shape
+    g = torch.zeros(n_rows, C, dtype=F32, device=grad_out.device)
+    M = n_rows if members is None else members.numel()
+    _lib.call("sgb_segment_pool_mean_bwd", grad_out, S, C, members, M, offsets, g, _stream())
+    return g
+
+
 def cluster_knn(xyz, order, cl_off, k=20, scene_pt_off=None):
     """xyz [N,>=3] f32 (row stride = xyz.stride(0)); order [N] i32; cl_off [S+1] i32 -> knn [N,k] i32.
     scene_pt_off [B+1] i32 (device, scene batch): ids are written relative to the first point of the query's scene."""

@@ -113,6 +113,29 @@ class SegmentMaxFn(torch.autograd.Function):
         return ops.segment_pool_max_bwd(g.contiguous(), arg, ctx.n_rows), None, None
 
 
+class SegmentMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, offsets, members):
+        feat = feat.contiguous()
+        ctx.save_for_backward(offsets, members if members is not None else offsets.new_empty(0))
+        ctx.n_rows, ctx.has_members = feat.shape[0], members is not None
+        return ops.segment_pool_mean(feat, offsets, members)
+
+    @staticmethod
+    def backward(ctx, g):
+        offsets, members = ctx.saved_tensors
+        return ops.segment_pool_mean_bwd(g.contiguous(), offsets, members if ctx.has_members else None, ctx.n_rows), None, None
+
+
+def aggregate_cluster_feature(Feat_old, offsets, members=None, use_avg=False):
+    """seggroup/model.py:278-288 on a CSR of the new clusters (offsets [S+1], members = old-cluster rows in member-list order):
+    [S,C] max features, or [S,2C] = (max, mean) with use_avg=True (a flag no caller of the reference sets)."""
+    f1, _ = SegmentMaxFn.apply(Feat_old, offsets, members)
+    if not use_avg:
+        return f1
+    return torch.cat([f1, SegmentMeanFn.apply(Feat_old, offsets, members)], dim=-1)
+
+
 class EdgeDistFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, adj, csr_off, csr_nbr, csr_eid):

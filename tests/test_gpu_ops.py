@@ -526,3 +526,36 @@ def test_classifier_head_forward_backward(counts, drop):
     for a, r, name in zip(dv, rv, ("feat", "W1", "gamma", "beta", "W2", "b2")):
         err = float((a.grad.cpu().double() - r.grad).abs().max() / (r.grad.abs().max() + 1e-30))
         assert err < 2e-5, (name, err)
+
+
+@pytest.mark.parametrize("C", [64, 192, 256])
+def test_aggregate_cluster_feature_use_avg(C):
+    """use_avg variant of aggregate_cluster_feature (model.py:278-288): (max, mean) per new cluster, forward and backward against
+    the reference's own loop over clusters evaluated with torch on the same device."""
+    from seggroup_b200 import pipeline
+    g = torch.Generator().manual_seed(3)
+    R, S = 700, 90
+    feat = torch.randn(R, C, generator=g).cuda().requires_grad_(True)
+    perm = torch.randperm(R, generator=g)
+    cuts = torch.sort(torch.randperm(R - 1, generator=g)[:S - 1] + 1).values
+    offsets = torch.cat([torch.zeros(1, dtype=torch.long), cuts, torch.tensor([R])]).to(torch.int32).cuda()
+    members = perm.to(torch.int32).cuda()
+    out = pipeline.aggregate_cluster_feature(feat, offsets, members, use_avg=True)
+    assert out.shape == (S, 2 * C)
+    w = torch.randn(S, 2 * C, generator=g).cuda()
+    (out * w).sum().backward()
+    got_grad = feat.grad.clone()
+    ref_feat = feat.detach().clone().requires_grad_(True)
+    rows = []
+    off = offsets.cpu().tolist()
+    for s in range(S):                                   # model.py:279-285
+        idx = members[off[s]:off[s + 1]].long()
+        f1 = torch.max(ref_feat[idx], dim=0, keepdim=True)[0]
+        f2 = torch.mean(ref_feat[idx], dim=0, keepdim=True)[0].unsqueeze(0)
+        rows.append(torch.cat([f1, f2], dim=-1))
+    ref = torch.cat(rows, dim=0)
+    (ref * w).sum().backward()
+    assert torch.equal(out[:, :C], ref[:, :C])
+    assert torch.allclose(out[:, C:], ref[:, C:], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got_grad, ref_feat.grad, rtol=1e-5, atol=1e-6)
+    assert torch.equal(pipeline.aggregate_cluster_feature(feat.detach(), offsets, members), ref[:, :C].detach())
