@@ -1,16 +1,17 @@
-"""Scene-parallel executor for one GPU: runs the scenes of a batch concurrently on separate CUDA streams.
+"""Scene executor for one GPU + the multi-GPU plumbing.
 
-A SegGroup scene is a chain of ~600 kernels of which many are latency bound (single-CTA sequential union
-replays, CSR builds over a few thousand rows) and a handful are wide (EdgeConv, kNN).  One scene therefore
-cannot fill 148 SMs; the unit of parallelism on a B200 is the scene (scenes are independent,
-BatchNorm statistics are per scene).  `SceneExecutor` keeps `n_streams` host threads, each bound to its own
-CUDA stream; every thread drives whole scenes through `pipeline.forward_scene` (+ `torch.autograd.grad`), so
-the narrow kernels of one scene overlap the wide kernels of the others and the host-side read-backs of one
-scene (cluster counts) do not idle the device.
+A SegGroup scene is a chain of ~600 kernels of which many are latency bound (single-CTA sequential union replays, CSR builds over
+a few thousand rows) and a handful are wide (EdgeConv, kNN).  One scene therefore cannot fill 148 SMs; the unit of parallelism
+on a B200 is the scene (scenes are independent, BatchNorm statistics are per scene).
 
-Gradient semantics of a training batch = the reference at `len(scenes)` ranks (train.py:165-170 + DDP
-average): mean over scenes of loss_sum / loss_num.  Per-scene gradients are summed in scene order on the
-caller's stream, so the result does not depend on thread scheduling.
+`SceneExecutor` (default `fused=True`): the scenes of a step are concatenated into ONE block-diagonal scene batch
+(`pipeline.SceneDevice.concat`) and driven by one forward / backward on the caller's stream — every graph / kNN / pooling / export
+launch serves all scenes, the order-dependent replays run one CTA per scene (round 2: 56 -> 25 ms per 8 x 150k step).
+`fused=False` is the round-1 executor: `n_streams` host threads, each bound to its own CUDA stream, every thread driving whole
+scenes (or sub-batches) so that the narrow kernels of one overlap the wide kernels of the others.
+
+Gradient semantics of a training batch = the reference at `len(scenes)` ranks (train.py:165-170 + DDP average): mean over scenes
+of loss_sum / loss_num, per-scene contributions summed in scene order (independent of thread scheduling).
 """
 from __future__ import annotations
 

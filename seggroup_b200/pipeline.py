@@ -1,13 +1,14 @@
 """Functional SegGroup forward (seggroup/model.py:684-932) on the CUDA kernels.
 
-`forward_scene(scene, params, mode)` runs one scene: graph init -> structural grouping layer ->
-two semantic grouping layers -> final clustering -> classifier, returning the loss tensors (train),
-the per-layer pseudo labels and the metrics.  Differentiable ops are `torch.autograd.Function`s whose
-forward AND backward are kernels of libseggroup_b200.so; torch itself is used for allocation, the tiny
-dense GEMMs of the GCN / classifier heads (plain library GEMMs) and elementwise glue on [S, C] tensors.
+`forward_scene(scene, params, mode)` runs one scene — or a scene batch (`SceneDevice.concat`: several scenes as ONE block-diagonal
+scene, every launch serving all of them, everything the reference defines per scene kept per scene) — through graph init ->
+structural grouping layer -> two semantic grouping layers -> final clustering -> classifier, returning the loss tensors (train),
+the per-layer pseudo labels and the metrics.  Differentiable ops are `torch.autograd.Function`s whose forward AND backward are
+kernels of libseggroup_b200.so (EdgeConv, pooling, edge distances, GCN aggregation, the GCN `fc` GEMMs on tcgen05, the classifier
+head + label-smoothed cross entropy); torch itself is used for allocation and elementwise glue on [S, C] tensors.
 
-Host synchronisation: one 4-byte read-back per clustering level (the cluster count fixes the shapes of
-everything downstream) and one per adjacency update — the reference does the whole grouping on the host.
+Host synchronisation: two 4-byte read-backs per clustering level (cluster count and edge count fix the shapes of everything
+downstream) — the reference does the whole grouping on the host.
 """
 from __future__ import annotations
 
