@@ -44,9 +44,105 @@ __device__ __forceinline__ int block_argmax(float v, int i, float* s_val, int* s
     return s_idx[0];
 }
 
+// Round 2b: clusters of at most FPSW_MAX members with P <= FPSW_P picks — every level-1 segment of the model (~150 points, P = 64)
+// — are sampled by ONE WARP each: 8 points per lane in registers (coordinates mirrored in shared memory for the broadcast of the
+// picked point), the arg-max of a pick is a 5-step shuffle reduction with the same first-maximum tie rule, no block barrier at all.
+// The block kernel below spent two __syncthreads and a shared-memory round trip per pick for ~150 points on 256 threads
+// (0.52 ms for the 8,571 segments of an 8-scene batch); it remains the path for large clusters (phase B: P = 1024).
+constexpr int FPSW_PPL = 8, FPSW_MAX = 32 * FPSW_PPL, FPSW_P = 64, FPSW_WARPS = 4;
+
+__global__ void __launch_bounds__(FPSW_WARPS * 32)
+cluster_cloud_indices_warp_kernel(const float* __restrict__ xyz, int stride, const int* __restrict__ order,
+                                  const int* __restrict__ cl_off, int S, int P, int* __restrict__ cloud_idx, int* __restrict__ status) {
+    __shared__ float s_x[FPSW_WARPS][FPSW_MAX], s_y[FPSW_WARPS][FPSW_MAX], s_z[FPSW_WARPS][FPSW_MAX];
+    __shared__ int s_choice[FPSW_WARPS][FPSW_P];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * FPSW_WARPS + w;
+    if (c >= S) return;
+    const int lo = __ldg(cl_off + c), n = __ldg(cl_off + c + 1) - lo;
+    if (n <= 0 || n > FPSW_MAX) return;                  // large clusters: cluster_cloud_indices_kernel
+    int* out = cloud_idx + (size_t)c * P;
+    const int rep = P / n, rem = P % n;
+    for (int i = lane; i < rep * n; i += 32) out[i] = __ldg(order + lo + (i % n));
+    if (rem == 0) return;
+    // member i = lane + 32 j lives in slot j of its lane
+    float px[FPSW_PPL], py[FPSW_PPL], pz[FPSW_PPL], pd[FPSW_PPL];
+#pragma unroll
+    for (int j = 0; j < FPSW_PPL; ++j) {
+        const int i = lane + 32 * j;
+        px[j] = py[j] = pz[j] = 0.f;
+        if (i < n) {
+            const float* p = xyz + (size_t)__ldg(order + lo + i) * stride;
+            px[j] = __ldg(p); py[j] = __ldg(p + 1); pz[j] = __ldg(p + 2);
+            s_x[w][i] = px[j]; s_y[w][i] = py[j]; s_z[w][i] = pz[j];
+        }
+    }
+    __syncwarp();
+    auto warp_argmax = [&](float v, int i) {             // ties -> lowest index; result in every lane
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(SGB_FULL_MASK, v, o);
+            const int oi = __shfl_xor_sync(SGB_FULL_MASK, i, o);
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+        return i;
+    };
+    // distances to member 0 -> first pick
+    float sx = s_x[w][0], sy = s_y[w][0], sz = s_z[w][0];
+    float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < FPSW_PPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < n) {
+            pd[j] = sq_dist_np(sx, sy, sz, px[j], py[j], pz[j]);
+            if (pd[j] > bv) { bv = pd[j]; bi = i; }
+        } else pd[j] = 0.f;
+    }
+    int sel = warp_argmax(bv, bi);
+    if (lane == 0) s_choice[w][0] = sel;
+    // skip_initial: restart the running minimum from the first pick
+    sx = s_x[w][sel]; sy = s_y[w][sel]; sz = s_z[w][sel];
+    bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < FPSW_PPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < n) {
+            pd[j] = sq_dist_np(sx, sy, sz, px[j], py[j], pz[j]);
+            if (pd[j] > bv) { bv = pd[j]; bi = i; }
+        }
+    }
+    for (int k = 1; k < rem; ++k) {
+        sel = warp_argmax(bv, bi);
+        if (lane == 0) s_choice[w][k] = sel;
+        sx = s_x[w][sel]; sy = s_y[w][sel]; sz = s_z[w][sel];
+        bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < FPSW_PPL; ++j) {
+            const int i = lane + 32 * j;
+            if (i < n) {
+                const float d = sq_dist_np(sx, sy, sz, px[j], py[j], pz[j]);
+                if (d < pd[j]) pd[j] = d;
+                if (pd[j] > bv) { bv = pd[j]; bi = i; }
+            }
+        }
+    }
+    __syncwarp();
+    // trailing picks equal to member 0 are replaced by the leading picks (model.py:407-412), as in the block kernel
+    if (lane == 0 && s_choice[w][rem - 1] == 0) {
+        int j = 1;
+        for (; j <= rem; ++j) if (s_choice[w][rem - j] != 0) break;
+        if (j > rem) j = rem;
+        const int invalid = j - 1;
+        if (invalid == 0) atomicOr(status, 1);
+        for (int t = 0; t < invalid; ++t) s_choice[w][rem - invalid + t] = (t < rem - invalid) ? s_choice[w][t] : 0;
+    }
+    __syncwarp();
+    for (int i = lane; i < rem; i += 32) out[rep * n + i] = __ldg(order + lo + s_choice[w][i]);
+}
+
 __global__ void __launch_bounds__(FPS_THREADS)
 cluster_cloud_indices_kernel(const float* __restrict__ xyz, int stride, const int* __restrict__ order,
-                             const int* __restrict__ cl_off, int P, int* __restrict__ cloud_idx,
+                             const int* __restrict__ cl_off, int P, int small_done, int* __restrict__ cloud_idx,
                              float4* __restrict__ scratch, int* __restrict__ status) {
     __shared__ float4 s_pts[FPS_SMEM_PTS];
     __shared__ float s_val[FPS_THREADS / 32];
@@ -56,6 +152,7 @@ cluster_cloud_indices_kernel(const float* __restrict__ xyz, int stride, const in
     const int lo = cl_off[c], n = cl_off[c + 1] - lo;
     int* out = cloud_idx + (size_t)c * P;
     if (n <= 0) return;
+    if (small_done && n <= FPSW_MAX) return;   // sampled by cluster_cloud_indices_warp_kernel
     const int rep = P / n, rem = P % n;
     for (int i = threadIdx.x; i < rep * n; i += FPS_THREADS) out[i] = __ldg(order + lo + (i % n));
     if (rem == 0) return;
@@ -256,8 +353,13 @@ extern "C" int sgb_cluster_cloud_indices(const float* xyz, int stride, int N, co
     if (!xyz || !order || !cl_off || !cloud_idx || !status || !ws) return SGB_ERR_INVALID;
     if (ws_bytes < sgb_cluster_cloud_ws_bytes(N)) return SGB_ERR_WORKSPACE;
     if ((size_t)P * sizeof(int) > 40 * 1024) return SGB_ERR_UNSUPPORTED;
+    const int small = P <= FPSW_P ? 1 : 0;
+    if (small) {
+        cluster_cloud_indices_warp_kernel<<<sgb_div_up(S, FPSW_WARPS), FPSW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            xyz, stride, order, cl_off, S, P, cloud_idx, status); SGB_COUNT_LAUNCH();
+    }
     { cluster_cloud_indices_kernel<<<S, FPS_THREADS, (size_t)P * sizeof(int), (cudaStream_t)stream>>>(
-        xyz, stride, order, cl_off, P, cloud_idx, (float4*)ws, status); SGB_COUNT_LAUNCH(); }
+        xyz, stride, order, cl_off, P, small, cloud_idx, (float4*)ws, status); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
