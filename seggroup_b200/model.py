@@ -344,8 +344,11 @@ class SegModel(nn.Module):
                     self._made_dirs.add(r)
         with torch.cuda.device(data.device):                    # kernels launch on the tensors' device, whatever the current one is
             engine.reserve_current_stream(device=data.device)  # once per stream: no cudaMalloc in later forwards
-            scenes = [self._scene(names[b], data[b], weak_label[b]) for b in range(B)]
-            sc = SceneDevice.concat(scenes)
+            # the loader's batch tensors ARE the concatenation of the scenes: one dtype conversion for the whole batch, no per-scene copies
+            data_f = data.contiguous().float()
+            weak_i = weak_label.to(torch.int32).contiguous()
+            scenes = [self._scene(names[b], data_f[b], weak_i[b]) for b in range(B)]
+            sc = SceneDevice.concat(scenes, data=data_f.view(-1, data_f.shape[-1]), weak_label=weak_i.view(-1, weak_i.shape[-1]))
             res = pipeline.forward_scene(sc, self._params(), mode=mode, classifier=self.classifier, sweep_cap=self.SWEEP_CAP)
             if res.status & 2:
                 import warnings

@@ -52,10 +52,12 @@ class SceneDevice:
         return self.split.pt_off, self.split.seg_off, self.split.raw_off
 
     @staticmethod
-    def concat(scenes):
+    def concat(scenes, data=None, weak_label=None):
         """Several resident scenes -> ONE block-diagonal scene batch (device-side concatenation, point / segment ids offset by
         the scene's base).  Scenes are independent in the reference (one scene per rank per step, train.py:92; BatchNorm
-        statistics, graphs and labels are per scene): a batch shares launches, not state."""
+        statistics, graphs and labels are per scene): a batch shares launches, not state.
+        data / weak_label: the already concatenated [sum N, 6] f32 / [sum N, 2] i32 rows of the scenes (a loader's batch tensor
+        viewed flat) — then the per-scene copies are not concatenated again."""
         if len(scenes) == 1:
             return scenes[0]
         dev = scenes[0].data.device
@@ -82,7 +84,8 @@ class SceneDevice:
         adj0 = shifted([sc.adj0 for sc in scenes], 2, width=2)
         unmap = shifted([(sc.unmap if sc.unmap is not None else torch.arange(sc.n_points, device=dev)) for sc in scenes], 3)
         real = cat([sc.real_label for sc in scenes]) if all(sc.real_label is not None for sc in scenes) else None
-        return SceneDevice(data=cat([sc.data for sc in scenes]), weak_label=cat([sc.weak_label for sc in scenes]), seg_off=seg_off,
+        return SceneDevice(data=cat([sc.data for sc in scenes]) if data is None else data,
+                           weak_label=cat([sc.weak_label for sc in scenes]) if weak_label is None else weak_label, seg_off=seg_off,
                            seg_members=seg_members, adj0=adj0, unmap=unmap, real_label=real,
                            name="+".join(sc.name for sc in scenes), split=ops.SceneSplit(pt, sg, rw, dev))
 
