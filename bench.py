@@ -453,7 +453,9 @@ def main():
         def step_loader():
             hb = next(ld)
             ld_bytes.append(hb.nbytes)
-            return float(step_resident(hb.to_device(dev)).item())
+            loss = float(step_resident(hb.to_device(dev)).item())
+            hb.recycle()                                    # the step has completed: the pinned buffers go back to the loader's pool
+            return loss
         step_loader(); step_loader()
         ms_ld, _ = timed(step_loader, n_ld)
         extra["e2e_shard_loader"] = {"value": pts_per_step * n_ld / (ms_ld * 1e-3), "unit": UNIT, "ms_per_step": ms_ld / n_ld, "h2d_bytes_per_step": int(ld_bytes[-1]),

@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from . import engine
-from .model import load_scene_files
+from . import scene_pack
 
 
 @dataclass
@@ -46,6 +46,13 @@ class HostBatch:
     seg_cnt_off: list
     raw_off: list
 
+    def recycle(self):
+        """Give the pinned buffers back to the loader's pool (call once the H2D copies of this batch have completed)."""
+        owned, self._owned = getattr(self, "_owned", []), []
+        with _pinned_lock:
+            for key, base in owned:
+                _pinned_pool.setdefault(key, []).append(base)
+
     @property
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.data, self.weak_label, self.seg_off, self.seg_members, self.adj0, self.unmap, self.real_label))
@@ -59,36 +66,70 @@ class HostBatch:
 
 
 def load_scene(name, data_root=os.path.join("dataset", "scannet"), label_style="manual", cache_dir=None):
-    """Everything one forward of one scene needs, as numpy arrays (file layout of SURVEY.md 9.1)."""
-    d = os.path.join(data_root, "data", "resampled", name)
-    data = torch.load(os.path.join(d, name + ".pcl.pth")).numpy().astype(np.float32, copy=False)
-    weak = torch.load(os.path.join(data_root, "label", "seg", label_style, "resampled", name, name + ".label.pth")).numpy().astype(np.int32)
-    adj, unmap, seg_off, seg_members = load_scene_files(name, data_root, cache_dir)
-    real = torch.load(os.path.join(data_root, "label", "real", "raw", name, name + ".label.pth")).numpy().astype(np.int64, copy=False)
-    return dict(data=data, weak=weak, adj=adj, unmap=unmap, seg_off=seg_off, seg_members=seg_members, real=real)
+    """Everything one forward of one scene needs, as numpy arrays (scene_pack.load_scene: one raw binary read per scene when
+    `cache_dir` is given, the reference's pickles + JSON otherwise)."""
+    return scene_pack.load_scene(name, data_root, label_style, cache_dir)
 
 
-def collate(scenes, names, index, pin=True):
-    """Block-diagonal concatenation of per-scene arrays into one set of (pinned) host tensors."""
+_pinned_pool = {}
+_pinned_lock = threading.Lock()
+
+
+def _pinned(tag, n_elems, dtype, cols, pin):
+    """[n, cols] host tensor; pinned buffers are drawn from a pool of capacity-rounded allocations (cudaHostAlloc of a few tens of
+    MB costs milliseconds, a batch needs seven of them): a HostBatch gives its buffers back with `recycle()`."""
+    if not pin:
+        return torch.empty((n_elems, cols) if cols > 1 else (n_elems,), dtype=dtype), None
+    cap = max(1, -(-n_elems // 65536)) * 65536
+    key = (tag, cap, cols, dtype)
+    with _pinned_lock:
+        pool = _pinned_pool.setdefault(key, [])
+        base = pool.pop() if pool else None
+    if base is None:
+        base = torch.empty((cap, cols) if cols > 1 else (cap,), dtype=dtype, pin_memory=True)
+    return base[:n_elems], (key, base)
+
+
+def collate(scenes, names, index, pin=True, pool=None):
+    """Block-diagonal concatenation of per-scene arrays into one set of (pinned) host tensors; ids are offset by the first point
+    of their scene while they are copied (no temporaries).  pool: optional executor — the per-scene copies (numpy, GIL released)
+    run on its threads."""
     pt, sg, rw, ed = [0], [0], [0], [0]
     for s in scenes:
         pt.append(pt[-1] + s["data"].shape[0]); sg.append(sg[-1] + len(s["seg_off"]) - 1)
         rw.append(rw[-1] + s["unmap"].shape[0]); ed.append(ed[-1] + s["adj"].shape[0])
     pin = pin and torch.cuda.is_available()
-    new = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)
-    hb = HostBatch(names=list(names), index=list(index), data=new((pt[-1], 6), torch.float32), weak_label=new((pt[-1], 2), torch.int32),
-                   seg_off=new((sg[-1] + 1,), torch.int32), seg_members=new((pt[-1],), torch.int32), adj0=new((ed[-1], 2), torch.int32),
-                   unmap=new((rw[-1],), torch.int64), real_label=new((rw[-1], 2), torch.int64), pt_off=pt, seg_cnt_off=sg, raw_off=rw)
-    hb.seg_off[0] = 0
-    for i, s in enumerate(scenes):
+    owned = []
+
+    def new(tag, n, dt, cols=1):
+        t, own = _pinned(tag, n, dt, cols, pin)
+        if own is not None:
+            owned.append(own)
+        return t
+    hb = HostBatch(names=list(names), index=list(index), data=new("data", pt[-1], torch.float32, 6), weak_label=new("weak", pt[-1], torch.int32, 2),
+                   seg_off=new("seg_off", sg[-1] + 1, torch.int32), seg_members=new("seg_members", pt[-1], torch.int32),
+                   adj0=new("adj", ed[-1], torch.int32, 2), unmap=new("unmap", rw[-1], torch.int64), real_label=new("real", rw[-1], torch.int64, 2),
+                   pt_off=pt, seg_cnt_off=sg, raw_off=rw)
+    hb._owned = owned
+    v = {k: getattr(hb, k).numpy() for k in ("data", "weak_label", "seg_off", "seg_members", "adj0", "unmap", "real_label")}
+    v["seg_off"][0] = 0
+
+    def copy_scene(i):
+        s = scenes[i]
         p0, p1 = pt[i], pt[i + 1]
-        hb.data[p0:p1] = torch.from_numpy(s["data"])
-        hb.weak_label[p0:p1] = torch.from_numpy(s["weak"])
-        hb.seg_members[p0:p1] = torch.from_numpy(s["seg_members"] + p0)
-        hb.seg_off[sg[i] + 1:sg[i + 1] + 1] = torch.from_numpy(s["seg_off"][1:] + p0)
-        hb.adj0[ed[i]:ed[i + 1]] = torch.from_numpy(s["adj"] + p0)
-        hb.unmap[rw[i]:rw[i + 1]] = torch.from_numpy(s["unmap"] + p0)
-        hb.real_label[rw[i]:rw[i + 1]] = torch.from_numpy(s["real"])
+        v["data"][p0:p1] = s["data"]
+        v["weak_label"][p0:p1] = s["weak"]
+        np.add(s["seg_members"], p0, out=v["seg_members"][p0:p1], casting="unsafe")
+        np.add(s["seg_off"][1:], p0, out=v["seg_off"][sg[i] + 1:sg[i + 1] + 1], casting="unsafe")
+        np.add(s["adj"], p0, out=v["adj0"][ed[i]:ed[i + 1]], casting="unsafe")
+        np.add(s["unmap"], p0, out=v["unmap"][rw[i]:rw[i + 1]], casting="unsafe")
+        v["real_label"][rw[i]:rw[i + 1]] = s["real"]
+
+    if pool is not None and len(scenes) > 1:
+        list(pool.map(copy_scene, range(len(scenes))))
+    else:
+        for i in range(len(scenes)):
+            copy_scene(i)
     return hb
 
 
@@ -101,6 +142,8 @@ class SceneShardLoader:
         self.data_root, self.label_style, self.cache_dir = data_root, label_style, cache_dir
         self.batch_size, self.pin, self.prefetch, self.epochs = int(batch_size), pin, int(prefetch), int(epochs)
         self.shard = engine.shard_scenes(len(self.names), rank, world, pad=pad)
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=max(1, min(4, self.batch_size)), thread_name_prefix="sgb-scene-read")
 
     def __len__(self):
         return self.epochs * ((len(self.shard) + self.batch_size - 1) // self.batch_size)
@@ -112,8 +155,9 @@ class SceneShardLoader:
 
     def _load(self, idx):
         names = [self.names[i] for i in idx]
-        scenes = [load_scene(n, self.data_root, self.label_style, self.cache_dir) for n in names]
-        return collate(scenes, names, idx, self.pin)
+        one = lambda n: load_scene(n, self.data_root, self.label_style, self.cache_dir)
+        scenes = list(self._pool.map(one, names)) if len(names) > 1 else [one(names[0])]       # file reads release the GIL
+        return collate(scenes, names, idx, self.pin, pool=self._pool)
 
     def __iter__(self):
         q = queue.Queue(maxsize=max(1, self.prefetch))

@@ -179,6 +179,8 @@ class SegModel(nn.Module):
         self._path_locks = {}
         self._io_lock = threading.Lock()
         self._copy_stream = None
+        self._read_pool = None
+        self._stage_pool, self._stage_busy = {}, []      # pinned staging buffers of the side packs: free / in flight (event, buffer)
         self._made_dirs = set()
         self.d2h_bytes = 0                     # label bytes copied to the host so far (bench bookkeeping)
         self.last_result = None
@@ -192,15 +194,71 @@ class SegModel(nn.Module):
         # named_parameters() de-duplicates the shared BN modules under their first name (mlp_k.bn1 / bn2)
         return {k: named[k] for k in _PARAM_KEYS}
 
-    def _scene(self, scene_name, data, weak_label):
+    def _side_host(self, scene_name):
+        """Host-side read of one scene's side files (model.py:696-699, 610-614).  With a cache directory: the scene's side pack
+        (one memory-mapped raw file instead of two pickles, a zip archive and, the first time, the JSON parse) copied into ONE
+        pinned staging buffer -> `_scene` uploads it with a single asynchronous copy and slices the arrays on the device (five
+        pageable, i.e. synchronous, copies per scene otherwise).  Without: numpy arrays + the real-label tensor."""
+        if self.scene_cache_dir:
+            from . import scene_pack
+            scene_pack.load_side(scene_name, self.data_root, self.scene_cache_dir)          # builds the pack if it is missing or stale
+            m = np.memmap(os.path.join(self.scene_cache_dir, scene_name + ".side.sgbpack"), dtype=np.uint8, mode="r")
+            pin = torch.cuda.is_available()
+            stage = self._stage_get(int(m.size), pin)
+            np.copyto(stage.numpy()[:m.size], m)
+            return ("pack", stage, int(m.size), scene_pack.pack_layout(stage.numpy()))
+        adj, unmap, seg_off, seg_members = load_scene_files(scene_name, self.data_root, None)
+        real = torch.load(os.path.join(self.data_root, 'label', 'real', 'raw', scene_name, scene_name + '.label.pth'))
+        return adj, unmap, seg_off, seg_members, real
+
+    def _stage_get(self, nbytes, pin):
+        """Pinned staging buffer of at least nbytes from the pool (capacity rounded to 1 MB); buffers come back through
+        `_stage_release` once the copy that reads them has completed."""
+        cap = -(-nbytes // (1 << 20)) * (1 << 20)
+        with self._io_lock:
+            done = [x for x in self._stage_busy if x[0].query()]
+            self._stage_busy = [x for x in self._stage_busy if not x[0].query()] if done else self._stage_busy
+            for _, buf in done:
+                self._stage_pool.setdefault(buf.numel(), []).append(buf)
+            pool = self._stage_pool.get(cap)
+            if pool:
+                return pool.pop()
+        return torch.empty(cap, dtype=torch.uint8, pin_memory=pin)
+
+    def _preload(self, names, dev):
+        """Scenes of a batch whose side files are not in HBM yet are read concurrently (file reads / unpickling release the GIL
+        for most of their time): a first-epoch batch of 8 scenes otherwise spends longer parsing on one thread than computing."""
+        todo = [n for n in dict.fromkeys(names) if not (self.cache_scenes and (n, dev) in self._scene_cache)]
+        if len(todo) < 2:
+            return {}
+        if self._read_pool is None:
+            self._read_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="sgb-side-read")
+        return dict(zip(todo, self._read_pool.map(self._side_host, todo)))
+
+    def _scene(self, scene_name, data, weak_label, host=None):
         dev = data.device
         key = (scene_name, dev)
         side = self._scene_cache.get(key) if self.cache_scenes else None
         if side is None:
-            adj, unmap, seg_off, seg_members = load_scene_files(scene_name, self.data_root, self.scene_cache_dir)
-            real = torch.load(os.path.join(self.data_root, 'label', 'real', 'raw', scene_name, scene_name + '.label.pth'))
-            t = lambda a: torch.as_tensor(a).to(dev, non_blocking=True)
-            side = dict(adj0=t(adj), unmap=t(unmap), seg_off=t(seg_off), seg_members=t(seg_members), real=real.to(dev))
+            host = host if host is not None else self._side_host(scene_name)
+            if isinstance(host[0], str):                                    # ("pack", staging buffer, bytes, layout)
+                _, stage, nbytes, lay = host
+                dbuf = stage[:nbytes].to(dev, non_blocking=True)              # one copy for the five arrays
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                with self._io_lock:
+                    self._stage_busy.append((ev, stage))
+                tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64, np.dtype(np.float32): torch.float32}
+
+                def view(key):
+                    off, r, cols, dt = lay[key]
+                    v = dbuf[off:off + r * cols * np.dtype(dt).itemsize].view(tdt[np.dtype(dt)])
+                    return v.view(r, cols) if cols > 1 else v
+                side = dict(adj0=view("adj"), unmap=view("unmap"), seg_off=view("seg_off"), seg_members=view("seg_members"), real=view("real"))
+            else:
+                adj, unmap, seg_off, seg_members, real = host
+                t = lambda a: torch.as_tensor(a).to(dev, non_blocking=True)
+                side = dict(adj0=t(adj), unmap=t(unmap), seg_off=t(seg_off), seg_members=t(seg_members), real=real.to(dev))
             if self.cache_scenes:
                 self._scene_cache[key] = side
         return SceneDevice(data=data.contiguous().float(), weak_label=weak_label.to(torch.int32).contiguous(),
@@ -347,7 +405,8 @@ class SegModel(nn.Module):
             # the loader's batch tensors ARE the concatenation of the scenes: one dtype conversion for the whole batch, no per-scene copies
             data_f = data.contiguous().float()
             weak_i = weak_label.to(torch.int32).contiguous()
-            scenes = [self._scene(names[b], data_f[b], weak_i[b]) for b in range(B)]
+            pre = self._preload(names, data.device)
+            scenes = [self._scene(names[b], data_f[b], weak_i[b], pre.get(names[b])) for b in range(B)]
             sc = SceneDevice.concat(scenes, data=data_f.view(-1, data_f.shape[-1]), weak_label=weak_i.view(-1, weak_i.shape[-1]))
             res = pipeline.forward_scene(sc, self._params(), mode=mode, classifier=self.classifier, sweep_cap=self.SWEEP_CAP)
             if res.status & 2:

@@ -53,3 +53,52 @@ def test_loader_surfaces_missing_files(tmp_path):
     from seggroup_b200.loader import SceneShardLoader
     with pytest.raises(Exception):
         list(SceneShardLoader(["nope\n"], data_root=str(tmp_path), batch_size=1))
+
+
+def test_scene_pack_round_trip_and_rebuild(tmp_path):
+    """seggroup_b200/scene_pack.py: a pack returns exactly what the reference's files parse to (dtypes as uploaded), is used while
+    it is newer than its sources, rebuilt when a source changes, and never trusted when it does not parse."""
+    import time
+    from seggroup_b200 import scene_pack, synth
+    sc = synth.make_scene(77, 7000, name="pk_0")
+    synth.write_scene_tree(str(tmp_path), [sc])
+    root = os.path.join(str(tmp_path), "dataset", "scannet")
+    cache = os.path.join(str(tmp_path), "packs")
+    ref = scene_pack.load_scene("pk_0", root, "manual", None)                 # parsed from the reference's files
+    first = scene_pack.load_scene("pk_0", root, "manual", cache)              # parsed + packed
+    p = scene_pack.pack_path(cache, "pk_0", "manual")
+    assert os.path.isfile(p)
+    t_built = os.path.getmtime(p)
+    got = scene_pack.load_scene("pk_0", root, "manual", cache)                # served from the pack
+    assert os.path.getmtime(p) == t_built
+    want = dict(data=(np.float32, sc.data), weak=(np.int32, sc.weak_label), seg_off=(np.int32, sc.seg_offsets), seg_members=(np.int32, sc.seg_members),
+                adj=(np.int32, sc.adj), unmap=(np.int64, sc.unmap), real=(np.int64, sc.real_label))
+    for k, (dt, val) in want.items():
+        for d in (ref, first, got):
+            assert d[k].dtype == dt and np.array_equal(d[k], val), k
+    src = scene_pack.source_paths("pk_0", root, "manual")[0]
+    os.utime(src, (time.time() + 5, time.time() + 5))                         # newer source -> rebuilt
+    scene_pack.load_scene("pk_0", root, "manual", cache)
+    assert os.path.getmtime(p) >= os.path.getmtime(src) - 5 and os.path.getmtime(p) != t_built or os.path.getmtime(p) > t_built
+    for junk in (b"short", b"SGBPACK1" + b"\\x00" * 100):                      # foreign / truncated file -> rebuilt, not trusted
+        with open(p, "wb") as f:
+            f.write(junk)
+        os.utime(p, (time.time() + 60, time.time() + 60))
+        again = scene_pack.load_scene("pk_0", root, "manual", cache)
+        assert np.array_equal(again["seg_members"], sc.seg_members) and np.array_equal(again["real"], sc.real_label)
+
+
+def test_side_pack_matches_the_side_files(tmp_path):
+    """scene_pack.load_side: what SegModel reads per scene (adj, unmap, seg CSR, real labels), packed without the point cloud."""
+    from seggroup_b200 import scene_pack, synth
+    from seggroup_b200.model import load_scene_files
+    sc = synth.make_scene(78, 6500, name="sd_0")
+    synth.write_scene_tree(str(tmp_path), [sc])
+    root = os.path.join(str(tmp_path), "dataset", "scannet")
+    cache = os.path.join(str(tmp_path), "packs")
+    adj, unmap, so, sm = load_scene_files("sd_0", root)
+    for _ in range(2):                                     # built, then served from the pack
+        d = scene_pack.load_side("sd_0", root, cache)
+        assert np.array_equal(d["adj"], adj) and np.array_equal(d["unmap"], unmap) and np.array_equal(d["seg_off"], so)
+        assert np.array_equal(d["seg_members"], sm) and np.array_equal(d["real"], sc.real_label) and d["data"].shape == (0, 6)
+    assert os.listdir(cache) == ["sd_0.side.sgbpack"]

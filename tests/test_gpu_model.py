@@ -158,3 +158,46 @@ def test_export_failure_is_raised(tree, scene8k):
         model(*_inputs(scene8k))
     with pytest.raises(SgbError):
         model.flush_exports()
+
+
+def test_side_pack_cold_path_equals_the_file_parse(tmp_path):
+    """SegModel with a cache directory and the HBM scene cache off (first epoch / inference: every scene is read at its forward): the
+    side files come from the scene packs, staged in pinned memory and uploaded with one copy per scene — outputs and the 14 label
+    files equal the plain parse of the reference's files, on the first call (pack built) and on the second (pack mapped)."""
+    from seggroup_b200 import synth
+    from seggroup_b200.model import SegModel
+    scenes = [synth.make_scene(61 + i, 6000 + 300 * i, name="pk_%d" % i) for i in range(3)]
+    synth.write_scene_tree(str(tmp_path), scenes)
+    old = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        outs, files = [], []
+        for exp, cache in (("plain", None), ("packed", str(tmp_path / "packs")), ("packed2", str(tmp_path / "packs"))):
+            torch.manual_seed(1)
+            model = SegModel(exp_name=exp, ins_infer=True).to("cuda")
+            with torch.no_grad():
+                model.mlp_1.bn1.weight.mul_(4.0)
+            model.epoch = "ins_infer"
+            model.cache_scenes = False
+            model.scene_cache_dir = cache
+            res = []
+            for b, s in enumerate(scenes):                  # one scene per call (sizes differ) ...
+                d = torch.from_numpy(s.data.copy()).unsqueeze(0).cuda()
+                w = torch.from_numpy(s.weak_label.copy()).unsqueeze(0).cuda()
+                res.append(model(d, w, torch.tensor([[b]]).cuda()))
+            model.flush_exports()
+            outs.append(res)
+            got = {}
+            for s in scenes:
+                root = os.path.join("results", exp, s.name, "ins_infer")
+                got[s.name] = {f: open(os.path.join(root, f), "rb").read() for f in sorted(os.listdir(root))}
+                assert len(got[s.name]) == 14
+            files.append(got)
+        assert sorted(os.listdir(tmp_path / "packs")) == ["pk_%d.side.sgbpack" % i for i in range(3)]
+        for other in (1, 2):
+            assert files[other] == files[0]
+            for a, b in zip(outs[0], outs[other]):
+                for x, y in zip(a, b):
+                    assert torch.equal(x, y)
+    finally:
+        os.chdir(old)
