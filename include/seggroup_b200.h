@@ -463,6 +463,26 @@ int sgb_closest_pool_bwd(const float* g, int n1, int d, const int* inds, int n2,
  * consumers read (kpconv/datasets/Scannet2.py:148-156).  `values` is a host pointer. */
 int sgb_write_labels_host(const char* path, const int* values, int n);
 
+/* ---------------------------------------------------------------------------------------------
+ * N1  batch normalisation (+ residual) + LeakyReLU of the KPFCNN blocks
+ * replaces kpconv/models/network_blocks.py:147-163 `batch_norm` (tf.layers.batch_normalization, epsilon 1e-6, batch statistics
+ * over the points of the stacked batch in training) + 166-173 `leaky_relu`, and the residual join of the bottleneck blocks
+ * (`leaky_relu(features + shortcut)`, 337, 581).
+ *
+ * y [n,d] = act(gamma * (x - mean) * invstd + beta + residual), act = LeakyReLU(slope) (slope = 1: identity).
+ * training != 0: batch statistics; stat [3][d] <- mean, invstd, biased variance; running_mean / running_var (optional) are
+ * updated as r <- (1 - momentum) r + momentum * batch value (unbiased variance).  training == 0: the running statistics.
+ * gamma / beta / residual may be NULL.  ws: sgb_bn_act_ws_bytes(n, d).
+ * Backward: dx, dres (gradient of the residual input, optional), dgamma, dbeta (optional) from dy, x, y, stat of the forward.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgb_bn_act_ws_bytes(int n, int d);
+int sgb_bn_act_fwd(const float* x, int n, int d, const float* gamma, const float* beta, const float* residual, float eps,
+                   float slope, int training, float momentum, float* running_mean, float* running_var, float* y, float* stat,
+                   void* ws, size_t ws_bytes, void* stream);
+int sgb_bn_act_bwd(const float* dy, const float* x, const float* y, int n, int d, const float* gamma, const float* stat,
+                   float slope, int training, float* dx, float* dres, float* dgamma, float* dbeta,
+                   void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,13 +43,17 @@ class BatchNorm(nn.Module):
         else:
             self.offset = nn.Parameter(torch.zeros(dim))
 
-    def forward(self, x, training=True):
+    def forward(self, x, training=True, slope=1.0, residual=None):
+        """slope-activation(batch_norm(x) + residual) in one library call (`sgb_bn_act_fwd/_bwd`); slope = 1: no activation.
+        Without batch norm (config.use_batch_norm = False) the reference adds a bias: plain torch, as rare as that setting."""
         if not self.use_batch_norm:
-            return x + self.offset
+            y = x + self.offset
+            if residual is not None:
+                y = y + residual
+            return y if slope == 1.0 else F.leaky_relu(y, slope)
         bn = self.bn
-        if training:
-            return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
-        return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, bn.momentum, bn.eps)
+        return KO.bn_act(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual=residual, eps=bn.eps, slope=slope,
+                         training=training, momentum=bn.momentum)
 
 
 def leaky_relu(features, alpha=0.2):
@@ -73,7 +77,7 @@ class UnaryBlock(nn.Module):
         self.bn = BatchNorm(fdim, config.use_batch_norm, config.batch_norm_momentum)
 
     def forward(self, layer_ind, inputs, features, radius, config, training=True):
-        return leaky_relu(self.bn(KO.unary_convolution(features, self.w), training))
+        return self.bn(KO.unary_convolution(features, self.w), training, slope=0.2)
 
 
 class SimpleBlock(nn.Module):
@@ -90,7 +94,7 @@ class SimpleBlock(nn.Module):
             q, s, idx = inputs['points'][layer_ind + 1], inputs['points'][layer_ind], inputs['pools'][layer_ind]
         else:
             q, s, idx = inputs['points'][layer_ind], inputs['points'][layer_ind], inputs['neighbors'][layer_ind]
-        return leaky_relu(self.bn(kp_conv(q, s, idx, features, self.w, radius, config), training))
+        return self.bn(kp_conv(q, s, idx, features, self.w, radius, config), training, slope=0.2)
 
 
 class SimpleStridedBlock(SimpleBlock):
@@ -117,17 +121,17 @@ class ResnetbBlock(nn.Module):
             self.shortcut_w = None
 
     def forward(self, layer_ind, inputs, features, radius, config, training=True):
-        x = leaky_relu(self.conv1_bn(KO.unary_convolution(features, self.conv1_w), training))
+        x = self.conv1_bn(KO.unary_convolution(features, self.conv1_w), training, slope=0.2)
         if self.strided:
             q, s, idx = inputs['points'][layer_ind + 1], inputs['points'][layer_ind], inputs['pools'][layer_ind]
         else:
             q, s, idx = inputs['points'][layer_ind], inputs['points'][layer_ind], inputs['neighbors'][layer_ind]
-        x = leaky_relu(self.conv2_bn(kp_conv(q, s, idx, x, self.conv2_w, radius, config), training))
-        x = self.conv3_bn(KO.unary_convolution(x, self.conv3_w), training)
+        x = self.conv2_bn(kp_conv(q, s, idx, x, self.conv2_w, radius, config), training, slope=0.2)
         shortcut = KO.ind_max_pool(features, inputs['pools'][layer_ind]) if self.strided else features
         if self.shortcut_w is not None:
             shortcut = self.shortcut_bn(KO.unary_convolution(shortcut, self.shortcut_w), training)
-        return leaky_relu(x + shortcut)
+        # leaky_relu(batch_norm(conv3) + shortcut): the residual join rides in the same kernel as the last normalisation
+        return self.conv3_bn(KO.unary_convolution(x, self.conv3_w), training, slope=0.2, residual=shortcut)
 
 
 class ResnetbStridedBlock(ResnetbBlock):
@@ -149,7 +153,7 @@ class ResnetbDeformableBlock(ResnetbBlock):
         self.last_offsets = None
 
     def forward(self, layer_ind, inputs, features, radius, config, training=True):
-        x = leaky_relu(self.conv1_bn(KO.unary_convolution(features, self.conv1_w), training))
+        x = self.conv1_bn(KO.unary_convolution(features, self.conv1_w), training, slope=0.2)
         if self.strided:
             q, s, idx = inputs['points'][layer_ind + 1], inputs['points'][layer_ind], inputs['pools'][layer_ind]
         else:
@@ -160,12 +164,12 @@ class ResnetbDeformableBlock(ResnetbBlock):
                                           KP_extent=extent, KP_influence=config.KP_influence, aggregation_mode=config.convolution_mode,
                                           modulated=getattr(config, "modulated", False), K_points=K_points)
         self.last_offsets = (q, s, idx, K_points, offsets, extent)
-        x = leaky_relu(self.conv2_bn(x, training))
-        x = self.conv3_bn(KO.unary_convolution(x, self.conv3_w), training)
+        x = self.conv2_bn(x, training, slope=0.2)
         shortcut = KO.ind_max_pool(features, inputs['pools'][layer_ind]) if self.strided else features
         if self.shortcut_w is not None:
             shortcut = self.shortcut_bn(KO.unary_convolution(shortcut, self.shortcut_w), training)
-        return leaky_relu(x + shortcut)
+        # leaky_relu(batch_norm(conv3) + shortcut): the residual join rides in the same kernel as the last normalisation
+        return self.conv3_bn(KO.unary_convolution(x, self.conv3_w), training, slope=0.2, residual=shortcut)
 
     def offsets_loss(self, loss_type="fitting"):
         """KPFCNN_model.py:218-286 for this layer (multiply by config.offsets_decay and add to the training loss)."""

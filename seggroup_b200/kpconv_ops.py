@@ -127,6 +127,49 @@ def unary_convolution(features, w):
     return _UnaryConvFn.apply(features, w)
 
 
+# ------------------------------------------------------------------------------------------------ N1: batch norm + LeakyReLU
+class _BnActFn(torch.autograd.Function):
+    """`leaky_relu(batch_norm(x) [+ residual])` of the KPFCNN blocks (kpconv/models/network_blocks.py:147-173, 337, 581) as library
+    kernels (`sgb_bn_act_fwd/_bwd`): column statistics in fp32 partials + fp64 reduction, one streaming apply pass; the backward
+    returns dx, d(residual), dgamma, dbeta."""
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, eps, slope, training, momentum):
+        from . import ops
+        x = _chk(x.contiguous(), F32, "x")
+        n, d = x.shape
+        y = torch.empty_like(x)
+        stat = torch.empty(3, d, dtype=F32, device=x.device)
+        res = residual.contiguous() if residual is not None else None
+        ws = ops._ws(_lib.call("sgb_bn_act_ws_bytes", n, d), x.device)
+        _lib.call("sgb_bn_act_fwd", x, n, d, gamma, beta, res, float(eps), float(slope), int(bool(training)), float(momentum),
+                  running_mean, running_var, y, stat, ws, ws.numel(), ops._stream())
+        ctx.save_for_backward(x, y, stat, gamma if gamma is not None else x.new_empty(0))
+        ctx.cfg = (float(slope), int(bool(training)), gamma is not None, beta is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        x, y, stat, gamma = ctx.saved_tensors
+        slope, training, has_g, has_b, has_r = ctx.cfg
+        n, d = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_r else None
+        dg = torch.empty(d, dtype=F32, device=x.device) if has_g else None
+        db = torch.empty(d, dtype=F32, device=x.device) if has_b else None
+        ws = ops._ws(_lib.call("sgb_bn_act_ws_bytes", n, d), x.device)
+        _lib.call("sgb_bn_act_bwd", dy, x, y, n, d, gamma if has_g else None, stat, slope, training, dx, dres, dg, db,
+                  ws, ws.numel(), ops._stream())
+        return dx, dg, db, dres, None, None, None, None, None, None
+
+
+def bn_act(x, gamma, beta, running_mean=None, running_var=None, residual=None, eps=1e-6, slope=0.2, training=True, momentum=0.01):
+    """act(batch_norm(x) + residual): x [n,d] f32 CUDA; slope = 1.0 for no activation.  In training the running statistics (if
+    given) are updated in place with torch's momentum rule; in evaluation they are required."""
+    return _BnActFn.apply(x, gamma, beta, residual, running_mean, running_var, eps, slope, training, momentum)
+
+
 # ------------------------------------------------------------------------------------------------ B4
 class _KPConvFn(torch.autograd.Function):
     @staticmethod

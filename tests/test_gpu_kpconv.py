@@ -356,13 +356,19 @@ def test_kpfcnn_rigid_blocks_forward_backward():
     import torch.nn.functional as F
     for b, (n, li, _, _, rad), fin in zip(blocks, arch, stage_in):
         masks = []
-        orig_lrelu = B.leaky_relu
-        B.leaky_relu = lambda f, alpha=0.2: (masks.append((f.detach() > 0).cpu()), F.leaky_relu(f, alpha))[1]
+        orig_fwd = B.BatchNorm.forward
+
+        def bn_fwd(self, x_, training=True, slope=1.0, residual=None):       # LeakyReLU is fused into the BN kernel: y > 0 <=> pre-activation > 0
+            y_ = orig_fwd(self, x_, training, slope, residual)
+            if slope != 1.0:
+                masks.append((y_.detach() > 0).cpu())
+            return y_
+        B.BatchNorm.forward = bn_fwd
         try:
             fd = fin.float().cuda().requires_grad_(True)
             out = b(li, inputs, fd, rad, cfg, True)
         finally:
-            B.leaky_relu = orig_lrelu
+            B.BatchNorm.forward = orig_fwd
         go = torch.randn(out.shape, generator=g)
         (out * go.cuda()).sum().backward()
         f64 = fin.float().double().requires_grad_(True)
@@ -546,3 +552,39 @@ def test_deformable_offsets_loss():
     assert _close(off.grad, o64.grad.numpy(), 1e-3)
     perm = deformable_offsets_loss(cu(q), cu(s), cu(idx), cu(kp), off.detach(), ext, "permissive")
     assert abs(float(perm) - float(torch.clamp(torch.linalg.norm(locs.detach(), dim=2) - 1, min=0).mean())) < 1e-5
+
+
+@pytest.mark.parametrize("n,d", [(1, 64), (300, 32), (5000, 128), (1237, 72)])
+@pytest.mark.parametrize("slope,use_res", [(0.2, False), (1.0, False), (0.2, True)])
+def test_bn_act_matches_torch(n, d, slope, use_res):
+    """sgb_bn_act_fwd/_bwd (N1: batch_norm + leaky_relu of network_blocks.py:147-173, residual join of 337 / 581) against
+    F.batch_norm + F.leaky_relu evaluated in fp64: outputs, running statistics, and the gradients w.r.t. x, the residual, gamma, beta;
+    training and evaluation mode."""
+    import torch.nn.functional as F
+    from seggroup_b200 import kpconv_ops as KO
+    g = torch.Generator().manual_seed(n * 7 + d)
+    x = (torch.randn(n, d, generator=g) * 1.7 + 0.8).cuda().requires_grad_(True)
+    res = torch.randn(n, d, generator=g).cuda().requires_grad_(True) if use_res else None
+    gamma = (torch.rand(d, generator=g) + 0.5).cuda().requires_grad_(True)
+    beta = torch.randn(d, generator=g).cuda().requires_grad_(True)
+    w = torch.randn(n, d, generator=g).cuda()
+    for training in ((True, False) if n > 1 else (False,)):
+        rm, rv = torch.randn(d, generator=g).cuda() * 0.1, (torch.rand(d, generator=g) + 0.5).cuda()
+        rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+        for t in (x, gamma, beta) + ((res,) if use_res else ()):
+            t.grad = None
+        y = KO.bn_act(x, gamma, beta, rm, rv, residual=res, eps=1e-6, slope=slope, training=training, momentum=0.01)
+        (y * w).sum().backward()
+        got = [y.detach().clone(), x.grad.clone(), gamma.grad.clone(), beta.grad.clone()] + ([res.grad.clone()] if use_res else [])
+        xd, gd, bd = x.detach().double().requires_grad_(True), gamma.detach().double().requires_grad_(True), beta.detach().double().requires_grad_(True)
+        rd = res.detach().double().requires_grad_(True) if use_res else None
+        z = F.batch_norm(xd, rm_ref, rv_ref, gd, bd, training, 0.01, 1e-6)
+        if use_res:
+            z = z + rd
+        yr = F.leaky_relu(z, slope) if slope != 1.0 else z
+        (yr * w.double()).sum().backward()
+        ref = [yr.detach(), xd.grad, gd.grad, bd.grad] + ([rd.grad] if use_res else [])
+        # the derivative of LeakyReLU jumps at 0: exclude nothing, fp32 pre-activations within 1e-6 of zero do not occur with these draws
+        for a, b in zip(got, ref):
+            assert torch.allclose(a.double(), b, rtol=2e-4, atol=2e-4 * float(b.abs().max())), (n, d, slope, use_res, training)
+        assert torch.allclose(rm.double(), rm_ref, rtol=1e-5, atol=1e-6) and torch.allclose(rv.double(), rv_ref, rtol=1e-5, atol=1e-6)
