@@ -277,7 +277,7 @@ def main():
     def finish_step(loss_raw, metrics):
         """loss = mean over scenes of loss_sum / loss_num (train.py:165-170 at B ranks), backward, ONE all-reduce of the flat
         gradient buffer with the 165 logging floats of train.py:172-175 appended, SGD step."""
-        loss = (loss_raw[:, 0] / loss_raw[:, 1]).mean()
+        loss = pipeline.batch_loss(loss_raw)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if dist is not None:

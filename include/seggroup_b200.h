@@ -321,6 +321,15 @@ int sgb_classifier_head_bwd(const float* feat, int G, const int* g_off, int n_sc
                             const float* grad_loss_sum, float* scratch, float* dfeat, float* dW1_part, float* dgamma_part,
                             float* dbeta_part, float* dW2_part, float* db2_part, void* stream);
 
+/* a15  per-instance grouping of the final clusters, replaces seggroup/model.py:902-916 (`np.unique` of the clusters' weak instance
+ * labels, the `torch.cat` of each group's clusters in ascending id order, the semantic label of the group's first cluster).
+ * cl_ins / cl_sem [S] weak labels of the clusters (-1 = none: forms a group of its own, as np.unique does), scene_cl_off
+ * [n_scenes+1] (device) cluster range of every scene (NULL with n_scenes = 1).  One launch, no host synchronisation.
+ * out: order [S] cluster ids sorted by (scene, label, id); off [S+1] group offsets into `order` (G + 1 entries used);
+ * gold [S] semantic label per group (G used); g_off [n_scenes+1] group range per scene; counts [2] = (G, min groups per scene). */
+int sgb_classifier_groups(const int* cl_ins, const int* cl_sem, const int* scene_cl_off, int n_scenes, int S,
+                          int* order, int* off, int* gold, int* g_off, int* counts, void* stream);
+
 /* a16  replaces seggroup/model.py:525-605 `export_{segment,instance,semantic}_label` up to the text
  * formatting: per raw vertex r (p = unmap[r], int64 as stored in unmap.pth; NULL = identity):
  * seg = root point id of p's cluster, ins/sem = weak label + 1 or -1. */
@@ -340,6 +349,11 @@ size_t sgb_evaluate_ws_bytes(void);
 int sgb_evaluate(const long long* real_label, const int* sem_pred, const int* ins_pred, int n,
                  const int* sem_valid_ids, int n_sem_valid, const int* ins_valid_ids, int n_ins_valid,
                  float* out, int* status, void* ws, size_t ws_bytes, void* stream);
+/* scene batch: raw_off [n_scenes+1] HOST array, raw-vertex range of every scene inside real_label / sem_pred / ins_pred;
+ * out [n_scenes,164]; the scenes are evaluated one after the other on `stream` with the same workspace. */
+int sgb_evaluate_scenes(const long long* real_label, const int* sem_pred, const int* ins_pred, const int* raw_off, int n_scenes,
+                        const int* sem_valid_ids, int n_sem_valid, const int* ins_valid_ids, int n_ins_valid,
+                        float* out, int* status, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a18  grid subsampling (boundaries B2 / B3)

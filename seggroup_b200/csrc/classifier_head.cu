@@ -228,6 +228,82 @@ cls_head_bwd_kernel(const float* __restrict__ feat, const int* __restrict__ g_of
     for (int i = tid; i < CH_HID * CH_IN; i += CH_THREADS) dW1p[(size_t)b * CH_HID * CH_IN + i] = s_dw1[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Per-instance grouping of the final clusters (model.py:902-916): per scene `np.unique` of the clusters' weak instance labels
+// (ascending), the clusters of a label in ascending id order, the semantic label of the FIRST cluster of each group.  The eager
+// form (unique / argsort / bincount / cumsum / repeat_interleave on ~300 rows) is ~35 framework launches and four blocking
+// read-backs per step with the device idle in between (profiles/r03d_timeline_8x150k_train.txt: 1.25 ms per 8-scene step for
+// microseconds of work).  Here: ONE single-CTA launch — the scenes one after the other, rank of a cluster = number of clusters
+// of its scene with a smaller (label, id) key (O(n^2) comparisons on n <= a few thousand rows), group heads by a block scan over
+// the sorted order — and one 8-byte read-back (group count: it sizes the classifier's tensors).
+// out: order [S] cluster ids sorted by (scene, label, id); off [G+1] positions of the group heads in `order` (off[G] = S);
+//      gold [G] semantic weak label of the first cluster of the group; g_off [n_scenes+1] group range of every scene;
+//      counts [2] = (G, smallest number of groups of a scene).
+// ---------------------------------------------------------------------------------------------
+constexpr int CG_THREADS = 1024;
+
+__global__ void __launch_bounds__(CG_THREADS)
+cls_groups_kernel(const int* __restrict__ cl_ins, const int* __restrict__ cl_sem, const int* __restrict__ scene_cl_off, int n_scenes, int S,
+                  int* order, int* off, int* gold, int* g_off, int* counts) {
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    int gbase = 0, min_groups = 0x7fffffff;
+    if (tid == 0) g_off[0] = 0;
+    for (int b = 0; b < n_scenes; ++b) {
+        const int c0 = scene_cl_off ? __ldg(scene_cl_off + b) : 0;
+        const int c1 = scene_cl_off ? __ldg(scene_cl_off + b + 1) : S;
+        const int n = c1 - c0;
+        for (int i = tid; i < n; i += CG_THREADS) {          // rank by (label, id): a stable sort of the scene's clusters by label
+            const int ki = __ldg(cl_ins + c0 + i);
+            int r = 0;
+            for (int j = 0; j < n; ++j) {
+                const int kj = __ldg(cl_ins + c0 + j);
+                r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+            }
+            order[c0 + r] = c0 + i;
+        }
+        __syncthreads();
+        const int before = gbase;
+        for (int p0 = 0; p0 < n; p0 += CG_THREADS) {         // group heads in sorted order, scanned in chunks of one CTA
+            const int p = p0 + tid;
+            int flag = 0, cl = 0;
+            if (p < n) {
+                cl = order[c0 + p];
+                flag = (p == 0 || __ldg(cl_ins + order[c0 + p - 1]) != __ldg(cl_ins + cl)) ? 1 : 0;
+            }
+            int inc = flag;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(SGB_FULL_MASK, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) s_warp[wp] = inc;
+            __syncthreads();
+            if (wp == 0) {
+                const int v = s_warp[lane];
+                int iv = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(SGB_FULL_MASK, iv, o); if (lane >= o) iv += u; }
+                s_warp[lane] = iv - v;
+                if (lane == 31) s_warp[32] = iv;
+            }
+            __syncthreads();
+            if (flag) {
+                const int g = gbase + s_warp[wp] + inc - 1;
+                off[g] = c0 + p;
+                gold[g] = __ldg(cl_sem + cl);
+            }
+            gbase += s_warp[32];
+            __syncthreads();                                 // s_warp is rewritten by the next chunk
+        }
+        min_groups = min(min_groups, gbase - before);
+        if (tid == 0) g_off[b + 1] = gbase;
+    }
+    if (tid == 0) {
+        off[gbase] = S;
+        counts[0] = gbase;
+        counts[1] = n_scenes > 0 ? min_groups : 0;
+    }
+}
+
 constexpr size_t CH_FWD_SMEM = (size_t)(CH_IN * CH_WS + 2 * CH_IN + 2 * CH_HID + 2 * CH_OUT + 2 * CH_HID + 2 * CH_HID) * sizeof(float);
 constexpr size_t CH_BWD_SMEM = (size_t)(CH_HID * CH_IN + 2 * CH_IN + 2 * CH_HID + 2 * CH_OUT + 4 * CH_HID) * sizeof(float);
 }  // namespace
@@ -256,6 +332,15 @@ extern "C" int sgb_classifier_head_bwd(const float* feat, int G, const int* g_of
     { cls_head_bwd_kernel<<<n_scenes, CH_THREADS, CH_BWD_SMEM, (cudaStream_t)stream>>>(feat, g_off, gold, W1, gamma, beta, W2, mask, drop_scale,
                                                                                      hpre, stats, logits, grad_loss_sum, scratch, dfeat, dW1_part,
                                                                                      dgamma_part, dbeta_part, dW2_part, db2_part); SGB_COUNT_LAUNCH(); }
+    SGB_CHECK_LAUNCH();
+    return SGB_OK;
+}
+
+extern "C" int sgb_classifier_groups(const int* cl_ins, const int* cl_sem, const int* scene_cl_off, int n_scenes, int S,
+                                     int* order, int* off, int* gold, int* g_off, int* counts, void* stream) {
+    if (S <= 0 || n_scenes < 1 || !cl_ins || !cl_sem || !order || !off || !gold || !g_off || !counts) return SGB_ERR_INVALID;
+    if (n_scenes > 1 && !scene_cl_off) return SGB_ERR_INVALID;
+    { cls_groups_kernel<<<1, CG_THREADS, 0, (cudaStream_t)stream>>>(cl_ins, cl_sem, scene_cl_off, n_scenes, S, order, off, gold, g_off, counts); SGB_COUNT_LAUNCH(); }
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }

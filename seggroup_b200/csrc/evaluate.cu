@@ -141,3 +141,19 @@ extern "C" int sgb_evaluate(const long long* real_label, const int* sem_pred, co
     SGB_CHECK_LAUNCH();
     return SGB_OK;
 }
+
+// scene batch: the scenes of a batch one after the other on the same stream and workspace (stream order keeps them apart), driven
+// from C: one library call per step instead of one per scene (the per-scene calls left the device idle for ~15 us each,
+// profiles/r03d_timeline_8x150k_train.txt).  raw_off [n_scenes+1]: HOST array, raw-vertex range of every scene; out [n_scenes,164].
+extern "C" int sgb_evaluate_scenes(const long long* real_label, const int* sem_pred, const int* ins_pred, const int* raw_off, int n_scenes,
+                                   const int* sem_valid_ids, int n_sem_valid, const int* ins_valid_ids, int n_ins_valid,
+                                   float* out, int* status, void* ws, size_t ws_bytes, void* stream) {
+    if (n_scenes < 1 || !raw_off || !real_label || !sem_pred || !ins_pred || !out) return SGB_ERR_INVALID;
+    for (int b = 0; b < n_scenes; ++b) {
+        const int lo = raw_off[b], hi = raw_off[b + 1];
+        const int rc = sgb_evaluate(real_label + 2 * (size_t)lo, sem_pred + lo, ins_pred + lo, hi - lo, sem_valid_ids, n_sem_valid,
+                                    ins_valid_ids, n_ins_valid, out + (size_t)b * 164, status, ws, ws_bytes, stream);
+        if (rc != SGB_OK) return rc;
+    }
+    return SGB_OK;
+}

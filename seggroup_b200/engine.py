@@ -136,7 +136,7 @@ class SceneExecutor:
             batch = scenes if isinstance(scenes, pipeline.SceneDevice) else pipeline.SceneDevice.concat(
                 [upload(s) if upload is not None else s for s in scenes])
             r = pipeline.forward_scene(batch, params, mode="train", classifier=classifier)
-            loss = (r.loss_raw[:, 0] / r.loss_raw[:, 1]).mean()                 # mean over scenes of loss_sum / loss_num (train.py:165-170 + DDP)
+            loss = pipeline.batch_loss(r.loss_raw)                 # mean over scenes of loss_sum / loss_num (train.py:165-170 + DDP)
             grads = torch.autograd.grad(loss, leaves, allow_unused=True)
             for pp, g in zip(leaves, grads):
                 if g is None:
@@ -155,7 +155,7 @@ class SceneExecutor:
             if upload is not None:
                 sc = upload(sc)
             r = pipeline.forward_scene(sc, params, mode="train", classifier=classifier)
-            loss = (r.loss_raw[:, 0] / r.loss_raw[:, 1]).sum() / n
+            loss = pipeline.batch_loss(r.loss_raw, n)
             grads = torch.autograd.grad(loss, leaves, allow_unused=True)
             for g in grads:
                 if g is not None:

@@ -434,6 +434,20 @@ def export_labels(unmap, seg_of_point, level: Level, want_seg=True, split=None):
     return seg, ins, sem
 
 
+def classifier_groups(cl_ins, cl_sem, d_scene_cl_off=None, n_scenes=1):
+    """Per-instance grouping of the final clusters (model.py:902-916) in one launch + one 8-byte read-back.
+    -> (order [S] i32, off [G+1] i32, gold [G] i32, g_off [n_scenes+1] i32, G, min groups per scene)"""
+    _chk(cl_ins, I32, "cl_ins"); _chk(cl_sem, I32, "cl_sem")
+    S = cl_ins.numel()
+    buf = torch.empty(3 * S + 1 + n_scenes + 1 + 2, dtype=I32, device=cl_ins.device)
+    order, off, gold = buf[:S], buf[S:2 * S + 1], buf[2 * S + 1:3 * S + 1]
+    g_off, counts = buf[3 * S + 1:3 * S + 2 + n_scenes], buf[3 * S + 2 + n_scenes:]
+    _lib.call("sgb_classifier_groups", cl_ins, cl_sem, d_scene_cl_off if n_scenes > 1 else None, int(n_scenes), S, order, off, gold, g_off,
+              counts, _stream())
+    G, gmin = counts.tolist()                           # the one host sync: G sizes the classifier's tensors
+    return order, off[:G + 1], gold[:G], g_off, G, gmin
+
+
 def classifier_head_fwd(feat, g_off, gold, W1, gamma, beta, W2, b2, mask, drop_scale):
     """-> dict(hpre [G,128], stats [B,256], logits [G,40], loss_raw [B,2])"""
     _chk(feat, F32, "feat"); _chk(g_off, I32, "g_off"); _chk(gold, I32, "gold")
@@ -477,6 +491,26 @@ def evaluate(real_label, sem_pred, ins_pred, sem_valid, ins_valid, status=None):
     ws = _ws(_lib.call("sgb_evaluate_ws_bytes"), sem_pred.device)
     _lib.call("sgb_evaluate", real_label, sem_pred, ins_pred, n, ids[0], len(ids[0]), ids[1], len(ids[1]), out, status, ws, ws.numel(),
               _stream())
+    return out
+
+
+def evaluate_scenes(real_label, sem_pred, ins_pred, raw_off, sem_valid, ins_valid, status=None):
+    """sgb_evaluate for every scene of a batch in ONE library call; raw_off: host list of n_scenes + 1 raw-vertex offsets.
+    -> out [n_scenes,164] f32"""
+    import numpy as np
+    _chk(real_label, torch.int64, "real_label"); _chk(sem_pred, I32, "sem_pred"); _chk(ins_pred, I32, "ins_pred")
+    key = (tuple(sem_valid), tuple(ins_valid))
+    ids = _VALID_IDS.get(key)
+    if ids is None:
+        ids = _VALID_IDS[key] = (np.ascontiguousarray(sem_valid, np.int32), np.ascontiguousarray(ins_valid, np.int32))
+    B = len(raw_off) - 1
+    off = np.ascontiguousarray(raw_off, np.int32)
+    if off[-1] > sem_pred.numel() or off[-1] > real_label.shape[0]:
+        raise ValueError("raw_off exceeds the label vectors")
+    out = torch.empty(B, 164, dtype=F32, device=sem_pred.device)
+    ws = _ws(_lib.call("sgb_evaluate_ws_bytes"), sem_pred.device)
+    _lib.call("sgb_evaluate_scenes", real_label, sem_pred, ins_pred, off, B, ids[0], len(ids[0]), ids[1], len(ids[1]), out, status, ws,
+              ws.numel(), _stream())
     return out
 
 

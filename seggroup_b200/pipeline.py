@@ -395,8 +395,8 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     def put_metrics(sem_key, ins_key):
         if sc.real_label is None or not export:
             return
-        for lo, hi in _pairs(raw_off):
-            res.metrics_scenes.append(evaluate(sc.real_label[lo:hi], res.labels[sem_key][lo:hi], res.labels[ins_key][lo:hi], status))
+        o = ops.evaluate_scenes(sc.real_label, res.labels[sem_key], res.labels[ins_key], raw_off, SEM_VALID, INS_VALID, status)
+        res.metrics_scenes += [(r[:80].view(1, 2, 40), r[80:160].view(1, 2, 40), r[160:164]) for r in o]
         res.metrics = res.metrics_scenes[0]
 
     def put_bn(prefix, mean, var, counts):
@@ -506,25 +506,9 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
         return res
 
     # ---- classifier (model.py:902-932): per-instance max, MLP head, label-smoothed CE (sum) — per scene
-    ins, sem = L5.cl_ins.long(), L5.cl_sem.long()
-    if B == 1:
-        key = ins + 1
-        kmul = None
-    else:
-        kmul = int(ins.max().item()) + 2
-        scene_of_cl = torch.repeat_interleave(torch.arange(B, device=dev), torch.tensor([b - a for a, b in _pairs(L5.scene_cl_off)], device=dev))
-        key = scene_of_cl * kmul + ins + 1
-    uniq, inv = torch.unique(key, return_inverse=True)                 # ascending: per scene ascending weak ins label (np.unique, model.py:905)
-    order = torch.argsort(inv, stable=True).to(I32)                    # clusters of a group in ascending order
-    off = torch.zeros(uniq.numel() + 1, dtype=I32, device=dev)
-    off[1:] = torch.cumsum(torch.bincount(inv, minlength=uniq.numel()), 0)
-    sem_gt = sem[order[off[:-1].long()].long()]                        # sem label of the first cluster of the group (model.py:916)
+    order, off, sem_gt, g_off_d, n_groups, g_min = ops.classifier_groups(L5.cl_ins, L5.cl_sem, L5.d_scene_cl_off, B)
     Feat_6, _ = SegmentMaxFn.apply(Feat_5, off, order)
-    g_cnt = torch.bincount(uniq // kmul, minlength=B) if B > 1 else torch.full((1,), uniq.numel(), device=dev)
-    g_off_d = torch.zeros(B + 1, dtype=I32, device=dev)
-    g_off_d[1:] = torch.cumsum(g_cnt, 0)
-    n_groups = int(uniq.numel())
-    if n_groups < 2 * B and int(g_cnt.min()) < 2:                      # (host check only when it can fail)
+    if g_min < 2:
         raise ValueError("Expected more than 1 value per channel when training (a scene with a single instance group: "
                          "BatchNorm1d of the classifier, model.py:157)")
     # dropout (model.py:159): Bernoulli keep mask drawn with torch's generator, one launch for the whole batch
@@ -544,12 +528,22 @@ def forward_scene(sc: SceneDevice, p: dict, mode: str = "train", keep_aux: bool 
     else:
         mask, drop_scale = None, 1.0
     loss_raw, logits, cstats = ClassifierHeadFn.apply(Feat_6, cp["classifier.linear1.weight"], cp["classifier.bn1.weight"], cp["classifier.bn1.bias"],
-                                                      cp["classifier.linear2.weight"], cp["classifier.linear2.bias"], g_off_d, sem_gt.to(I32), mask, drop_scale)
+                                                      cp["classifier.linear2.weight"], cp["classifier.linear2.bias"], g_off_d, sem_gt, mask, drop_scale)
     res.loss_raw = loss_raw                                            # [B,2] = (sum, count) per scene (model.py:932 returns [1,2])
     res.bn_stats_scenes["classifier.bn1"] = (cstats[:, :128], cstats[:, 128:], loss_raw[:, 1].detach())
     if keep_aux:
         res.aux["logits"] = logits.detach()
     return res
+
+
+def batch_loss(loss_raw, n_scenes=None):
+    """mean over the scenes of loss_sum / loss_num (train.py:165-170 on one scene per rank + DDP's gradient average) from the
+    [B,2] tensor the classifier head returns.  The instance count is a constant of the step: dividing by the detached column keeps
+    the backward graph to one multiplication (the plain `(l[:,0] / l[:,1]).mean()` differentiates the count column as well: seven
+    more launches on a host-bound stretch of the step)."""
+    n = loss_raw.shape[0] if n_scenes is None else n_scenes
+    w = torch.reciprocal(loss_raw[:, 1].detach() * float(n))
+    return (loss_raw[:, 0] * w).sum()
 
 
 def _phase_b(sc, uf, sos, status, Lo, Feat, split, sweep_cap=64):

@@ -486,6 +486,51 @@ def test_evaluate_matches_oracle(case):
         assert np.allclose(a, b, rtol=1e-6, atol=0, equal_nan=True), (case, a, b)
 
 
+@pytest.mark.parametrize("sizes,n_labels", [([37], 9), ([40, 3, 1500, 212], 30), ([5, 5], 1), ([2500, 1200, 7], 400)])
+def test_classifier_groups_match_numpy_unique(sizes, n_labels):
+    """sgb_classifier_groups (a15 grouping) against the reference formulation model.py:902-916 per scene: np.unique of the
+    clusters' weak instance labels, np.where order inside a group, semantic label of the group's first cluster.  Bit-exact."""
+    from seggroup_b200 import ops
+    rng = np.random.default_rng(sum(sizes) + n_labels)
+    ins = np.concatenate([rng.integers(-1, n_labels, n) for n in sizes]).astype(np.int32)
+    sem = rng.integers(-1, 40, ins.size).astype(np.int32)
+    cl_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    B = len(sizes)
+    order, off, gold, g_off, G, gmin = ops.classifier_groups(dev(ins), dev(sem), dev(cl_off) if B > 1 else None, B)
+    r_order, r_off, r_gold, r_goff = [], [0], [], [0]
+    for b in range(B):
+        lo, hi = cl_off[b], cl_off[b + 1]
+        ins_list = ins[lo:hi]
+        for v in np.unique(ins_list):
+            idx = np.where(ins_list == v)[0]
+            r_order += list(lo + idx)
+            r_off.append(len(r_order))
+            r_gold.append(sem[lo + idx[0]])
+        r_goff.append(len(r_gold))
+    assert G == len(r_gold) and gmin == min(b - a for a, b in zip(r_goff[:-1], r_goff[1:]))
+    assert np.array_equal(order.cpu().numpy(), np.asarray(r_order))
+    assert np.array_equal(off.cpu().numpy(), np.asarray(r_off))
+    assert np.array_equal(gold.cpu().numpy(), np.asarray(r_gold))
+    assert np.array_equal(g_off.cpu().numpy(), np.asarray(r_goff))
+
+
+def test_evaluate_scenes_equals_per_scene_calls():
+    """sgb_evaluate_scenes (one library call per batch) returns, per scene, exactly what sgb_evaluate returns on the scene's slice."""
+    from seggroup_b200 import ops, pipeline
+    rng = np.random.default_rng(5)
+    sizes = [30000, 1, 45001, 777]
+    off = [0] + list(np.cumsum(sizes))
+    n = off[-1]
+    real = np.stack([rng.integers(0, 41, n), rng.integers(1, 60, n)], 1).astype(np.int64)
+    ins_pred = rng.integers(-1, 60, n).astype(np.int32)
+    sem_pred = np.where(ins_pred >= 0, 1 + ins_pred % 40, -1).astype(np.int32)
+    d_real, d_sem, d_ins = dev(real), dev(sem_pred), dev(ins_pred)
+    out = ops.evaluate_scenes(d_real, d_sem, d_ins, off, pipeline.SEM_VALID, pipeline.INS_VALID)
+    for b, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        one = ops.evaluate(d_real[lo:hi].contiguous(), d_sem[lo:hi].contiguous(), d_ins[lo:hi].contiguous(), pipeline.SEM_VALID, pipeline.INS_VALID)
+        assert np.array_equal(out[b].cpu().numpy(), one.cpu().numpy(), equal_nan=True), b
+
+
 @pytest.mark.parametrize("counts,drop", [([41, 17, 2, 33], True), ([9], False), ([64, 64], True)])
 def test_classifier_head_forward_backward(counts, drop):
     """a15: the fused classifier head + label-smoothed cross entropy (model.py:154-166, 902-932, util.py:12-29), one CTA per

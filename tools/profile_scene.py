@@ -19,7 +19,7 @@ def step():
     with torch.set_grad_enabled(mode == "train"):
         r = pipeline.forward_scene(sc, p, mode=mode)
         if mode == "train":
-            (r.loss_raw[:, 0].sum() / r.loss_raw[:, 1].sum()).backward()
+            pipeline.batch_loss(r.loss_raw).backward()
     return r
 for _ in range(2): r = step()
 torch.cuda.synchronize()
@@ -52,6 +52,15 @@ for e in evs[1:]:
 print("device idle gaps > 2 us: %.3f ms in total over a span of %.3f ms" % (total_gap / 1e3, (t_end - evs[0].time_range.start) / 1e3))
 for k, v in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
     print("  gap before %-60s n %4d  %8.3f ms" % (k, v[0], v[1] / 1e3))
+if os.environ.get("SGB_TIMELINE"):          # ordered list of the idle gaps: what ran before, what ran after
+    t_end, prev = evs[0].time_range.end, evs[0].name
+    t0 = evs[0].time_range.start
+    for e in evs[1:]:
+        g = e.time_range.start - t_end
+        if g > 4.0:
+            print("  t=%8.3f ms gap %7.1f us  after %-42s before %s" % ((e.time_range.start - t0) / 1e3, g, prev[:42], e.name[:60]))
+        if e.time_range.end >= t_end:
+            t_end, prev = e.time_range.end, e.name
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("  %-70s n %4d  %9.3f ms" % (k, v[0], v[1] / 1e3))
 _lib.enable_profile()
