@@ -162,6 +162,11 @@ __device__ __forceinline__ void tmem_ld_pin20(uint32_t (&a)[16], uint32_t (&b)[4
                       "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]) :: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_pin16(uint32_t (&a)[16]) {
+    asm volatile("" : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]),
+                      "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]) :: "memory");
+}
+
 // byte offset of (row r, column c) in a K-major SWIZZLE_128B fp32 tile with R rows: 32-column blocks of R x 128 B, atoms of
 // 8 rows x 128 B whose 16-byte chunks are XOR-ed with the row (tile base 1024-byte aligned)
 __host__ __device__ __forceinline__ uint32_t sw128_off(int r, int c, int R) {
