@@ -185,7 +185,7 @@ def ncu_record(kernel_substr):
     """Per-launch metrics of a kernel from the committed `ncu --set full` summary of THIS round (tools/ncu_summary.py --json),
     or None: nothing is typed in by hand."""
     for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
-        if name.startswith("r02") and name.endswith("_ncu.json"):
+        if name[:3] in ("r02", "r03") and name.endswith("_ncu.json"):
             try:
                 rows = json.load(open(os.path.join(ROOT, "profiles", name)))
             except Exception:
@@ -515,11 +515,11 @@ def main():
         flops = 2.0 * N * 20 * (18 * 64 + 64 * 64)
         achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        ncu = ncu_record("ec2_tc_kernel<1, 1>") or ncu_record("ec2_tc_kernel<true, true>")
+        ncu = ncu_record("ec2_tc1_kernel<1, 1>") or ncu_record("ec2_tc1_kernel<true, true>")
         traffic = None
         if ncu and ncu.get("dram_bytes") is not None:
             traffic = ncu["dram_bytes"] * (N / float(ncu.get("points", 150000)))
-        roofline = {"bound": "tensor", "kernel": "sgb_edgeconv_fwd two_layer (gram1_pt_kernel + ec2_tc_kernel<ARG,GRAM> [tcgen05 kind::tf32 x3] + ec2_apply_kernel), one launch per scene",
+        roofline = {"bound": "tensor", "kernel": "sgb_edgeconv_fwd two_layer (gram1_pt_kernel + ec2_tc1_kernel<ARG,GRAM> [both layers on tcgen05, kind::tf32 x3] + ec2_apply_kernel), one launch per scene",
                     "achieved": achieved, "peak": peak_tf, "peak_kind": peak_kind + " bf16 dense, sustained (tf32 runs at half of it, the x3 split costs 3 MMAs)",
                     "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None, "traffic": traffic, "ms_per_launch": k_ms,
                     "algorithmic_flops_per_launch": flops, "launches_timed": k_n,

@@ -343,6 +343,23 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             const uint32_t idesc = make_idesc_tf32(64, TE, false, false);
             const uint32_t idesc_t = make_idesc_tf32(64, TN, false, false);
             const uint32_t a_hi = smem_u32(sm + off_bm_hi), a_lo = smem_u32(sm + off_bm_lo);
+            // Descriptors are loop-invariant up to the start-address field: bases once, a K step = an add of (bytes >> 4) to the low word
+            // (shared-memory addresses < 256 KB: the 14-bit field cannot carry).  The issuing thread is ONE instruction stream; at 40 tensor
+            // cycles per instruction (N = 80) the descriptor arithmetic between two tcgen05.mma was the pacing item of the kernel.
+            auto adv = [](uint64_t dsc, uint32_t bytes) -> uint64_t { return dsc + (uint64_t)(bytes >> 4); };
+            const uint64_t dBh = make_desc(a_hi, COUT * 16, 128), dBl = make_desc(a_lo, COUT * 16, 128);
+            uint64_t dHh[2], dHl[2], dDh[2], dDl[2], dEh[ERING], dEl[ERING];
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+                const uint32_t hh = smem_u32(sm + off_h0 + b2 * HSTAGE_BYTES), dv = smem_u32(sm + off_dv + b2 * 2 * DVH_BYTES);
+                dHh[b2] = make_desc(hh, TE * 16, 128); dHl[b2] = make_desc(hh + TILE_BYTES, TE * 16, 128);
+                dDh[b2] = make_desc(dv, COUT * 16, 128); dDl[b2] = make_desc(dv + DVH_BYTES, COUT * 16, 128);
+            }
+#pragma unroll
+            for (int b3 = 0; b3 < ERING; ++b3) {
+                const uint32_t ec = smem_u32(sm + off_e0 + b3 * ESTAGE_BYTES);
+                dEh[b3] = make_desc(ec, TN * 16, 128); dEl[b3] = make_desc(ec + EC_BYTES, TN * 16, 128);
+            }
             int nz = 0, nT = 0;                         // next tile for z, next HALF tile (2 u + h) for T
             while (nT < 2 * ntiles) {
                 bool did = false;
@@ -352,14 +369,13 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                     const bool ok = mbar_test(&bar_full[st], ph) && mbar_test(&bar_tempty[st], ph ^ 1u);
                     if (__all_sync(SGB_FULL_MASK, ok)) {
                         fence_after_sync();
+                        const uint64_t hh = st ? dHh[1] : dHh[0], hl = st ? dHl[1] : dHl[0];
+                        const uint32_t d = tmem + (uint32_t)(st * Z_COL);
                         if (elect_one_sync()) {
-                            const uint32_t b_hi = smem_u32(sm + off_h0 + st * HSTAGE_BYTES), b_lo = b_hi + TILE_BYTES;
-                            const uint32_t d = tmem + (uint32_t)(st * Z_COL);
 #pragma unroll
                             for (int i = 0; i < COUT / 8; ++i) {
-                                const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
-                                const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
-                                const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
+                                const uint64_t dah = adv(dBh, 2 * i * (COUT * 16)), dal = adv(dBl, 2 * i * (COUT * 16));
+                                const uint64_t dbh = adv(hh, 2 * i * (TE * 16)), dbl = adv(hl, 2 * i * (TE * 16));
                                 mma_tf32(d, dah, dbh, idesc, i > 0);
                                 if (!(SGB_ABL & 4)) {
                                     mma_tf32(d, dal, dbh, idesc, true);
@@ -381,15 +397,16 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                     if (ok && h == 0 && u % FLUSH == 0) ok = mbar_test(&bar_gempty[gb], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
                     if (__all_sync(SGB_FULL_MASK, ok)) {
                         fence_after_sync();
+                        const int er = u % ERING;
+                        const uint64_t eh0 = er == 0 ? dEh[0] : (er == 1 ? dEh[1] : dEh[2]), el0 = er == 0 ? dEl[0] : (er == 1 ? dEl[1] : dEl[2]);
+                        const uint64_t eh = adv(eh0, (uint32_t)(h * (TE / 8)) * (TN * 16)), el = adv(el0, (uint32_t)(h * (TE / 8)) * (TN * 16));
+                        const uint64_t vh = h ? dDh[1] : dDh[0], vl = h ? dDl[1] : dDl[0];
+                        const uint32_t d = tmem + (uint32_t)(T_COL0 + gb * T_COLS);
                         if (elect_one_sync()) {
-                            const uint32_t ec_hi = smem_u32(sm + off_e0 + (u % ERING) * ESTAGE_BYTES), ec_lo = ec_hi + EC_BYTES;
-                            const uint32_t dvh = smem_u32(sm + off_dv + h * 2 * DVH_BYTES), dvl = dvh + DVH_BYTES;
-                            const uint32_t d = tmem + (uint32_t)(T_COL0 + gb * T_COLS);
 #pragma unroll
                             for (int i = 0; i < ((SGB_ABL & 8) ? 1 : TE / 16); ++i) {           // 8 edges (K) per instruction = 2 chunks of 4; 5 per half tile
-                                const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(h * (TE / 8) + 2 * i) * (TN * 16);
-                                const uint64_t dah = make_desc(dvh + ao, COUT * 16, 128), dal = make_desc(dvl + ao, COUT * 16, 128);
-                                const uint64_t dbh = make_desc(ec_hi + bo, TN * 16, 128), dbl = make_desc(ec_lo + bo, TN * 16, 128);
+                                const uint64_t dah = adv(vh, 2 * i * (COUT * 16)), dal = adv(vl, 2 * i * (COUT * 16));
+                                const uint64_t dbh = adv(eh, 2 * i * (TN * 16)), dbl = adv(el, 2 * i * (TN * 16));
                                 mma_tf32(d, dah, dbh, idesc_t, (u % FLUSH) > 0 || h > 0 || i > 0);
                                 if (!(SGB_ABL & 4)) {
                                     mma_tf32(d, dal, dbh, idesc_t, true);

@@ -1,50 +1,61 @@
-// a9 on the tensor cores: second EdgeConv layer of MLP3 (seggroup/model.py:121-138) as a warp-specialised tcgen05 kernel.
+// a9 on the tensor cores: BOTH EdgeConv layers of MLP3 (seggroup/model.py:121-138) in one warp-specialised tcgen05 kernel.
 //
 //   z[c, e] = sum_j W2[c, j] h[e, j],   h[e, :] = lrelu(BN1(W1 e_e)),   e = (x_j - x_i, x_i),  j in knn(i)
 //
-// The 64x64 contraction per edge (8.2 kFLOP x 3 M edges per scene) is the one GEMM-shaped piece of SegModel.  It runs as
-// D[64 channels, TE edges] += W2[64, 64] * H[TE, 64]^T with kind::tf32 and the TF32 x 3 split of tc_common.cuh, so the
-// features keep fp32-level accuracy (the merge decisions downstream are discrete).  Orientation: channels on the TMEM
-// lanes, edges on the TMEM columns, so that one epilogue thread owns one channel and both reductions over edges are
-// thread-local:
-//   * BatchNorm-2 batch statistics  sum z, sum z^2  (fp32 per tile, fp64 across tiles, fixed order);
-//   * max / min over the 20 neighbours of a point.  BN (per-channel affine) followed by LeakyReLU is monotone, so
-//         max_k lrelu(BN2(z_k)) = lrelu(BN2(max_k z_k))  if gamma2 >= 0,   lrelu(BN2(min_k z_k))  otherwise,
-//     which removes the separate statistics pass of the SIMT path: ONE pass over the edges produces the statistics and
-//     the (max, min, arg) candidates; a light second kernel applies BN2 + LeakyReLU per point.
-// GRAM variant (training): the backward pass needs the second moments of the hidden activations, sum_e h h^T and sum_e h
-// (analytic BatchNorm backward, edgeconv_bwd.cu).  They are an edge contraction, i.e. the edges must lie along K.
-// kind::tf32 only walks MN-major operands in one swizzle mode that no K-major layout shares (measured with a one-instruction descriptor probe during bring-up, round 1), so the
-// producers store h a second time, transposed ([hidden row][edges], K-major SWIZZLE_64B), and a second accumulator
-//   G[128, 80] += [H_lo^T ; H_hi^T] (K = edges) x [H_hi^T ; 1 ; 0]^T
-// collects lo*hi (rows 0..63), hi*hi (rows 64..127) and the column of ones gives sum h; hi*lo follows by symmetry.
-// G is flushed to global fp32 slots every FLUSH tiles and summed in fp64 in a fixed order (TMEM accumulates in fp32).
+// Per tile of TE edges (TE / 20 points) three products run on the tensor cores, all kind::tf32 with the TF32 x 3 split of tc_common.cuh
+// (fp32-level accuracy: the merge decisions downstream are discrete):
+//   (1) first layer    D1[128 edge rows, 64 channels] = E[128, 24] * W1s[64, 24]^T      (K = 9 differences + 9 centre + 1 + 5 zero)
+//       E = (x_j - x_i, x_i, valid, 0...) is assembled by ONE thread per edge (hi / lo split, five 16-byte stores; K = 20..23 is one
+//       shared chunk of zeros reached through the descriptor's leading-dimension offset); W1s = (scale1 W1 | beta1 - scale1 mean1 | 0):
+//       the constant-1 column carries the folded BatchNorm-1 bias, an all-zero row (edge outside the CTA's range) gives h = lrelu(0) = 0.
+//       Round 2 had this layer on the CUDA cores: 16 producer threads per edge, each re-reading the edge's two raw rows, ~1,700
+//       instructions per edge against ~350 now.
+//   (2) second layer   D[64 channels, TE edges] += W2[64, 64] * H[TE, 64]^T.  The edges of D1 lie on the TMEM LANES, so a producer thread
+//       owns one edge row: tcgen05.ld of 32 of its 64 pre-activations (two warps per TMEM quadrant, one per channel half), LeakyReLU,
+//       hi / lo split, 16-byte stores into the K-major H tile (consecutive lanes = consecutive rows: conflict-free).  W2 (hi | lo) is the
+//       A operand and lives in TMEM for the whole kernel (written once as W2 * I by the tensor core itself, so it has the layout of an
+//       M = 64 accumulator by construction).  Orientation: channels on the TMEM lanes, edges on the columns, so that one epilogue thread owns
+//       one channel and both reductions over edges are thread-local:
+//         * BatchNorm-2 batch statistics  sum z, sum z^2  (fp32 per tile, two-sum pairs across tiles, fixed order);
+//         * max / min over the 20 neighbours of a point.  BN (per-channel affine) followed by LeakyReLU is monotone, so
+//               max_k lrelu(BN2(z_k)) = lrelu(BN2(max_k z_k))  if gamma2 >= 0,   lrelu(BN2(min_k z_k))  otherwise:
+//           ONE pass over the edges produces the statistics and the (extreme, arg) candidates; a light second kernel applies BN2 + LeakyReLU.
+//       An M = 64 accumulator keeps its rows on lanes 0..15 of each TMEM quadrant: the .16x32bx2 load shape gives the upper half-warp
+//       the NEXT point (20 columns further) of the same channels, so every lane of the epilogue works.
+//   (3) GRAM variant (training): the backward pass needs the second moments of the hidden activations, sum_e h h^T and sum_e h
+//       (analytic BatchNorm backward, edgeconv_bwd.cu) — an edge contraction, i.e. the edges must lie along K.  kind::tf32 only walks
+//       MN-major operands in one swizzle mode that no K-major layout shares (descriptor probe, round 1), so the producers store h a
+//       second time, transposed ([hidden row][edges], K-major SWIZZLE_64B, 32 consecutive edges of one row per store), and
+//           G[128, 80] += [H_lo^T ; H_hi^T] (K = edges) x [H_hi^T ; 1 ; 0]^T
+//       collects lo*hi (rows 0..63), hi*hi (rows 64..127); the column of ones gives sum h; hi*lo follows by symmetry.  G is flushed to
+//       global fp32 slots every FLUSH tiles and summed in fp64 in a fixed order (TMEM accumulates in fp32).
 //
 // Warp roles (416 threads, 1 CTA / SM, persistent over a contiguous range of points):
-//   warps 0-3   epilogue: tcgen05.ld of their TMEM sub-partition (an M = 64 accumulator keeps rows 16q..16q+15 on lanes
-//               32q..32q+15), statistics + max/min over 20 consecutive columns, stores of the per-point candidates;
-//   warp  4     TMEM allocation + the single MMA-issuing thread + tcgen05.commit;
-//   warps 5-12  producers.  (a) gather: thread g < TE copies the (48-byte padded) row x_j of edge g, thread p < TE / 20 the row x_i of
-//               point p, into a shared ring RING - 1 tiles ahead with cp.async (neighbour indices by LDG two tiles before that):
-//               the random row gathers cost ~1 us of latency against ~0.5 us per tile, so one tile of register look-ahead (round
-//               1) left the producers waiting on the scoreboard; (b) first layer: a thread owns ONE
-//               16-byte chunk of the hidden vector (4 channels) for the whole kernel, so its 72 first-layer weights (BN1
-//               folded in) live in REGISTERS — round 1 re-read them from shared memory for every edge, 72 LDS.128 per thread
-//               and tile, which was the largest consumer of a shared-memory-bound kernel (l1tex 93 %, tensor pipe 22 %) — and
-//               walks the tile in blocks of 8 edges (lane & 7 = edge, lane >> 3 = which of the warp's 4 chunks): 5 broadcast
-//               LDS.128 of the two rows (9 subtractions rebuild the edge vector), 36 packed FFMA2, LeakyReLU, hi/lo split, 16-byte stores into the canonical
-//               no-swizzle K-major tile (+ the 4-byte transposed stores of the Gram variant), fence.proxy.async, mbarrier arrive.
-// Pipelines: shared-memory tiles full/empty (2 stages), the gather ring (producer-internal: cp.async groups + one named barrier
-// per tile) and TMEM accumulators full/empty (2 buffers).
+//   warps 0-3   epilogue (one per TMEM quadrant);
+//   warp  4     TMEM allocation + the single MMA-issuing thread.  Its descriptors are loop-invariant up to the start-address field (a K
+//               step is one add to the low word); per iteration it issues  MMA1(t), Gram(t - 1), MMA2(t - 1);
+//   warps 5-12  producers: (a) gather — thread g < TE copies the (48-byte padded) row x_j of edge g, thread p < TE / 20 the row x_i of
+//               point p, into a shared ring RING - 1 tiles ahead with cp.async (neighbour indices travel through the ring as well);
+//               (b) E(t); (c) H(t - 1) from D1, so that the first-layer MMA of tile t overlaps the second half of the step.
+// Pipelines (mbarriers): E tiles and D1 accumulators (2 each), H stages (2), z accumulators (2), the transposed tile (1: the Gram MMAs
+// are issued first), the Gram accumulator (1).  Tiles: 120 edges (rows 120..127 of the M = 128 operand are whatever follows in shared
+// memory — their D1 rows are never read) without the Gram, 80 edges with it (shared-memory budget of the transposed tile).
+//
+// Measured (profiles/r03*): tcgen05.mma runs at N / 2 cycles per instruction for M = 64 and at the shared-memory fetch time
+// (32 M + 32 N bytes at 128 B / cycle) for M = 128, dependent or not, A from shared memory or TMEM (tools/ubench/mma_rate.cu):
+// 15.6 tensor cycles per edge without the Gram, 23.9 with it.  Cycle counters around every wait (-DSGB_ROLE_CLOCKS): the issuing
+// thread is busy 84-88 % of the kernel, the producers 65-90 %, the epilogue ~45 %.
 #include "common.cuh"
 #include "bn_moments.cuh"
 #include "edgeconv_common.cuh"
 #include "tc_common.cuh"
 
-#ifndef SGB_ABL
-#define SGB_ABL 0      // role-ablation timing experiments (tools/ablate.sh): results are WRONG for any value but 0
+#ifdef SGB_ROLE_CLOCKS
+#include <cstdio>
+#define WAITC(i, x) do { const long long t0_ = clock64(); x; wc[i] += clock64() - t0_; } while (0)
+#else
+#define WAITC(i, x) x
 #endif
-
 namespace sgb_ectc {
 using namespace sgb_tc;
 using sgb_ec::CIN;
@@ -52,457 +63,24 @@ using sgb_ec::COUT;
 using sgb_ec::KNN;
 using sgb_bn::lrelu;
 
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
-constexpr int MMA_WARP = EPI_WARPS;           // warp 4
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 416
+constexpr int PROD_WARPS = 8;
 constexpr int PROD_THREADS = PROD_WARPS * 32; // 256
-// raw gather ring: per tile the 48-byte rows x_j of its TE edges, the rows x_i of its TE / 20 points and a validity word per edge,
-// filled by cp.async several tiles ahead (no registers held across the latency of the random row gathers)
+#ifndef SGB_EPI1
+#define SGB_EPI1 4
+#endif
+constexpr int EPI1 = SGB_EPI1, NH1 = EPI1 / 4, MMA1W = EPI1;         // epilogue warps (NH1 per TMEM quadrant), the issuing warp follows, then the producers
+constexpr int THREADS1 = (EPI1 + 1 + PROD_WARPS) * 32;         // 416
 constexpr int W2_BYTES = COUT * COUT * 4;     // 16 KB
 constexpr int TMEM_COLS = 512;
 constexpr int FLUSH = 32;                     // tiles per Gram segment
 constexpr int GN = 80;                        // Gram accumulator columns: 64 hidden + ones + 15 zero rows
 constexpr int GR = 144;                       // rows of the transposed tile: 64 lo + 64 hi + 16 extra
 
-template <bool GRAM> struct Cfg {
-    static constexpr int TE = GRAM ? 80 : 160;                     // edges per tile (TMEM columns per z accumulator)
-    static constexpr int PTS = TE / KNN;                           // points per tile
-    static constexpr int BLOCKS = TE / 8;                          // 8-edge blocks per tile; a group of 4 producer warps takes every 2nd one
-    static constexpr int TILE_BYTES = TE * COUT * 4;               // one K-major H tile (hi or lo)
-    static constexpr int HT_BYTES = GRAM ? GR * TE * 4 : 0;        // transposed tile (lo, hi, extra rows)
-    static constexpr int STAGE_BYTES = 2 * TILE_BYTES + HT_BYTES;  // multiple of 1024 in both variants
-    // offsets into the dynamic shared memory block (1024-byte aligned base)
-    static constexpr int w2_hi = 0;
-    static constexpr int w2_lo = w2_hi + W2_BYTES;
-    static constexpr int stage0 = w2_lo + W2_BYTES;
-    static constexpr int RING = GRAM ? 4 : 3;                      // tiles in flight in the gather ring
-    static constexpr int RAW_BYTES = TE * 48 + PTS * 48 + TE * 8;  // x_j rows, x_i rows, validity words, neighbour indices of a LATER tile
-    static constexpr int raw0 = stage0 + 2 * STAGE_BYTES;
-    static constexpr int bars = raw0 + RING * RAW_BYTES;           // 12 mbarriers
-    static constexpr int tmem_slot = bars + 12 * 8;
-    static constexpr int wc_tab = tmem_slot + 16;                  // centre-half first-layer weights [16 chunks][9] float4 (BN1 folded in)
-    static constexpr int ctr_buf = wc_tab + 16 * 9 * 16;           // per producer warp: centre rows [PTS][4 parts] float4 of the current tile
-    static constexpr int total = ctr_buf + PROD_WARPS * PTS * 4 * 16;
-    static constexpr int Z_COL = 128 + (GRAM ? 0 : 128);           // TMEM column stride of the two z accumulators
-    static constexpr int G_COL0 = 256;                             // TMEM columns of the two Gram accumulators (256, 384)
-};
-static_assert(Cfg<true>::STAGE_BYTES % 1024 == 0 && Cfg<false>::STAGE_BYTES % 1024 == 0, "stage alignment");
-static_assert((2 * Cfg<true>::TILE_BYTES) % 1024 == 0, "transposed tile alignment");
-static_assert(Cfg<true>::total + 1024 <= 227 * 1024 && Cfg<false>::total + 1024 <= 227 * 1024, "shared memory budget");
-
-// row of the transposed tile that holds hidden channel (part p, local index i): chosen so that the four parts of a warp hit
-// distinct (row parity, swizzle class) pairs -> conflict-free 4-byte stores
-__host__ __device__ constexpr int ht_row(int p, int i) { return 8 * (i >> 1) + ((p & 1) + 4 * (p >> 1)) + 2 * (i & 1); }
-
 // byte offset of (row r, edge e) in the transposed K-major SWIZZLE_64B tile (atoms of 8 rows x 16 edges, 512 B)
 __device__ __forceinline__ uint32_t ht_off(int r, int e) {
     return (uint32_t)((e >> 4) * (GR * 64) + (r >> 3) * 512 + (r & 7) * 64 + ((((e & 15) >> 2) ^ ((r >> 1) & 3)) << 4) + (e & 3) * 4);
 }
 
-template <bool ARG, bool GRAM>
-__global__ void __launch_bounds__(THREADS, 1)      // 13 warps: one scheduler hosts 4 of them -> 16384 / (4 * 32) = 128 registers per thread at most
-ec2_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ W1,
-              const float* __restrict__ stats1, const float* __restrict__ W2, const float* __restrict__ gamma2,
-              float* __restrict__ zsel, unsigned char* __restrict__ ksel, double* __restrict__ part /*[grid][128]*/,
-              float* __restrict__ gslots /*[grid][nflush][128*GN]*/, int nflush) {
-    using C = Cfg<GRAM>;
-    constexpr int TE = C::TE;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // keeps the shared address space
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + C::bars);          // [2] producers -> MMA
-    uint64_t* bar_empty = bar_full + 2;                                      // [2] MMA (commit) -> producers
-    uint64_t* bar_tfull = bar_full + 4;                                      // [2] MMA (commit) -> epilogue
-    uint64_t* bar_tempty = bar_full + 6;                                     // [2] epilogue -> MMA
-    uint64_t* bar_gfull = bar_full + 8;                                      // [2] MMA (commit) -> epilogue: Gram segment complete
-    uint64_t* bar_gempty = bar_full + 10;                                    // [2] epilogue -> MMA: Gram accumulator flushed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::tmem_slot);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // contiguous, balanced range of points for this CTA
-    const int per = N / gridDim.x, rem = N % gridDim.x;
-    const int p_begin = blockIdx.x * per + min((int)blockIdx.x, rem);
-    const int p_end = p_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
-    const long long g_begin = (long long)p_begin * KNN, g_end = (long long)p_end * KNN;
-    const int ntiles = (int)((g_end - g_begin + TE - 1) / TE);
-
-    // ---- one-time setup
-    for (int i = tid; i < COUT * COUT; i += THREADS) {              // W2 [c][j] -> K-major canonical tile (rows = c, K = j)
-        const int c = i / COUT, j = i % COUT;
-        const float w = __ldg(W2 + i);
-        const float hi = tf32_hi(w);
-        const uint32_t off = tile_off(c, j, COUT);
-        *reinterpret_cast<float*>(sm + C::w2_hi + off) = hi;
-        *reinterpret_cast<float*>(sm + C::w2_lo + off) = tf32_hi(w - hi);
-    }
-    for (int i = tid; i < 16 * 9; i += THREADS) {                   // centre half of the first layer: columns 9..17 of W1, BN1 scale folded in
-        const int ch = i / 9, q = i % 9;
-        float w[4];
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) w[s4] = __ldg(W1 + (4 * ch + s4) * CIN + 9 + q) * stats1[128 + 4 * ch + s4];
-        *reinterpret_cast<float4*>(sm + C::wc_tab + i * 16) = make_float4(w[0], w[1], w[2], w[3]);
-    }
-    if (GRAM) {                                                     // extra rows of the transposed tiles: ones, then zeros
-        for (int s = 0; s < 2; ++s) {
-            unsigned char* ht = sm + C::stage0 + s * C::STAGE_BYTES + 2 * C::TILE_BYTES;
-            for (int i = tid; i < 16 * TE; i += THREADS) {
-                const int r = 128 + i / TE, e = i % TE;
-                *reinterpret_cast<float*>(ht + ht_off(r, e)) = (r == 128) ? 1.f : 0.f;
-            }
-        }
-    }
-    if (tid == 0) {
-        mbar_init(&bar_full[0], PROD_WARPS); mbar_init(&bar_full[1], PROD_WARPS);
-        mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
-        mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
-        mbar_init(&bar_tempty[0], EPI_WARPS); mbar_init(&bar_tempty[1], EPI_WARPS);
-        mbar_init(&bar_gfull[0], 1); mbar_init(&bar_gfull[1], 1);
-        mbar_init(&bar_gempty[0], EPI_WARPS); mbar_init(&bar_gempty[1], EPI_WARPS);
-        mbar_fence_init();
-    }
-    if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp > MMA_WARP) {
-        // ================= producers
-        const int pw = warp - (MMA_WARP + 1);           // 0..7
-        const int ptid = pw * 32 + lane;                // 0..255: gather role = edge row `ptid` of the tile (if < TE)
-        const int grp = pw >> 2;                        // which half of the 8-edge blocks this warp computes
-        const int part = lane >> 3;                     // hidden channels 16 part .. 16 part + 15 (the Gram row mapping of ht_row)
-        const int c4 = part * 4 + (pw & 3);             // my 16-byte chunk of the hidden vector: channels 4 c4 .. 4 c4 + 3, for the whole kernel
-        const int eb = lane & 7;                        // my edge inside an 8-edge block
-        // first layer with the BatchNorm-1 affine folded in:  v1 = (scale1 W1) e + (beta1 - scale1 mean1).  The edge vector is
-        // (x_j - x_i, x_i): the centre half  bias + Wc x_i  is the same for the 20 edges of a point and is evaluated ONCE per point and
-        // tile (each warp for its own 4 chunks, below); only the 9 difference columns are per-edge work and only their weights
-        // (36 registers instead of 72) stay in registers for the whole kernel.
-        constexpr int CD = 9;
-        float2 w01[CD], w23[CD];
-        float4 bias;
-        {
-            float sc[4], bb[4];
-#pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                const int c = 4 * c4 + s4;
-                sc[s4] = stats1[128 + c];
-                bb[s4] = fmaf(-stats1[128 + c], stats1[c], stats1[192 + c]);
-            }
-#pragma unroll
-            for (int q = 0; q < CD; ++q) {
-                w01[q] = make_float2(__ldg(W1 + (4 * c4 + 0) * CIN + q) * sc[0], __ldg(W1 + (4 * c4 + 1) * CIN + q) * sc[1]);
-                w23[q] = make_float2(__ldg(W1 + (4 * c4 + 2) * CIN + q) * sc[2], __ldg(W1 + (4 * c4 + 3) * CIN + q) * sc[3]);
-            }
-            bias = make_float4(bb[0], bb[1], bb[2], bb[3]);
-        }
-        const float4* wc = reinterpret_cast<const float4*>(sm + C::wc_tab) + c4 * 9;
-        unsigned char* ctr = sm + C::ctr_buf + pw * (C::PTS * 4 * 16);
-        uint32_t ht_rb[4], ht_rx[4];                    // my 4 rows of the transposed tile: byte offset of the row, swizzle term
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-            const int r = ht_row(part, (pw & 3) * 4 + s4);
-            ht_rb[s4] = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
-            ht_rx[s4] = (uint32_t)(((r >> 1) & 3) << 4);
-        }
-        // gather pipeline: neighbour indices by LDG two iterations before they are needed, rows by cp.async RING - 1 tiles ahead
-        constexpr int RING = C::RING;
-        const bool gatherer = ptid < TE;                // fetches x_j of edge row `ptid`
-        const bool pgatherer = ptid < C::PTS;           // fetches x_i of point `ptid` of the tile
-        // Neighbour indices travel through shared memory as well (4-byte cp.async, RING - 1 tiles before the rows that need them):
-        // held in rotating registers, the first register move after the LDG waits for it, i.e. one tile of look-ahead at best.
-        auto edge_in_range = [&](int t) -> bool {
-            const long long g = g_begin + (long long)t * TE + ptid;
-            return gatherer && t < ntiles && g < g_end;
-        };
-        auto cp16 = [&](void* dst, const float* src, bool valid) {       // 16-byte async copy, zero fill when !valid
-            const uint32_t n = valid ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
-        };
-        auto issue_index_copy = [&](int t) {            // index of my edge of tile t -> index slot t % RING
-            if (edge_in_range(t)) {
-                unsigned char* slot = sm + C::raw0 + (t % RING) * C::RAW_BYTES + TE * 48 + C::PTS * 48 + TE * 4 + ptid * 4;
-                const int* src = knn + (g_begin + (long long)t * TE + ptid);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(slot)), "l"(src) : "memory");
-            }
-        };
-        auto issue_rows = [&](int t, int j) {           // j < 0: edge out of range.  Every thread commits one (possibly empty) group per call
-            unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
-            if (gatherer) {
-                const bool v = j >= 0;
-                const float* src = x12 + (size_t)(v ? j : 0) * 12;
-                unsigned char* dst = raw + ptid * 48;
-                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);      // !v: zero fill -> pad lane 11 = 0 marks the edge invalid
-            }
-            if (pgatherer) {
-                const long long pt = g_begin / KNN + (long long)t * C::PTS + ptid;
-                const bool v = t < ntiles && pt < (long long)p_end;
-                const float* src = x12 + (size_t)(v ? pt : 0) * 12;
-                unsigned char* dst = raw + TE * 48 + ptid * 48;
-                cp16(dst, src, v); cp16(dst + 16, src + 4, v); cp16(dst + 32, src + 8, v);
-            }
-            issue_index_copy(t + RING - 1);             // lands before rows(t + RING - 1) are issued (same group as rows(t))
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto staged_index = [&](int t) -> int {         // read back my own copy (complete: its group has been waited for)
-            if (!edge_in_range(t)) return -1;
-            return *reinterpret_cast<const volatile int*>(sm + C::raw0 + (t % RING) * C::RAW_BYTES + TE * 48 + C::PTS * 48 + TE * 4 + ptid * 4);
-        };
-#pragma unroll 1
-        for (int tt = 0; tt < RING - 1; ++tt) issue_rows(tt, edge_in_range(tt) ? __ldg(knn + (g_begin + (long long)tt * TE + ptid)) : -1);
-        for (int t = 0; t < ntiles; ++t) {
-            const int st = t & 1;
-            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory");     // my copies for tile t (and the indices of tile t + RING - 1) have landed
-            asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");         // everybody's have, and everybody is done with tile t - 1
-            issue_rows(t + RING - 1, staged_index(t + RING - 1));                    // refill the slot tile t - 1 used
-            const unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
-            if (eb < C::PTS) {                           // lane (part, eb): centre row of point eb of the tile for my chunk c4
-                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + eb * 48);
-                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
-                const float xi[CD] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
-                float2 c01 = make_float2(bias.x, bias.y), c23 = make_float2(bias.z, bias.w);
-#pragma unroll
-                for (int q = 0; q < CD; ++q) {
-                    const float4 w = wc[q];
-                    const float2 xx = make_float2(xi[q], xi[q]);
-                    ffma2(c01, make_float2(w.x, w.y), xx);
-                    ffma2(c23, make_float2(w.z, w.w), xx);
-                }
-                *reinterpret_cast<float4*>(ctr + (eb * 4 + part) * 16) = make_float4(c01.x, c01.y, c23.x, c23.y);
-            }
-            __syncwarp();
-            mbar_wait(&bar_empty[st], ph ^ 1u);
-            unsigned char* dst_hi = sm + C::stage0 + st * C::STAGE_BYTES;
-            unsigned char* dst_lo = dst_hi + C::TILE_BYTES;
-            unsigned char* dst_t = dst_lo + C::TILE_BYTES;
-            // two 8-edge blocks in flight per thread: the shared-memory loads of the next block are issued before the arithmetic of the
-            // current one (ncu source view of the one-block loop: 22 % of the producers' samples waited on LDS, 24 % on dependent FMAs)
-            struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; };
-            const uint32_t raw_s = smem_u32(raw), ctr_s = smem_u32(ctr);
-            auto load_blk = [&](int blk, Blk& B) {
-                const int er = blk * 8 + eb;            // edge row in the tile
-                const int pt = (er * 205) >> 12;        // er / KNN, exact for er < 1039
-                const uint32_t rj = raw_s + (uint32_t)(er * 48);                                          // 48-byte stride: conflict-free
-                const uint32_t ri = raw_s + (uint32_t)(TE * 48 + pt * 48);                                // the edge's own point (broadcast)
-                B.b0 = lds128_ordered(rj); B.b1 = lds128_ordered(rj + 16); B.b2 = lds128_ordered(rj + 32);
-                B.a0 = lds128_ordered(ri); B.a1 = lds128_ordered(ri + 16); B.a2 = lds128_ordered(ri + 32);
-                B.cc = lds128_ordered(ctr_s + (uint32_t)((pt * 4 + part) * 16));
-            };
-            auto finish_blk = [&](int blk, const Blk& B) {
-                const int er = blk * 8 + eb;
-                const float ev[CD] = {B.b0.x - B.a0.x, B.b0.y - B.a0.y, B.b0.z - B.a0.z, B.b0.w - B.a0.w, B.b1.x - B.a1.x, B.b1.y - B.a1.y,
-                                      B.b1.z - B.a1.z, B.b1.w - B.a1.w, B.b2.x - B.a2.x};
-                float2 y01 = make_float2(B.cc.x, B.cc.y), y23 = make_float2(B.cc.z, B.cc.w);
-#pragma unroll
-                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CD); ++q) {
-                    const float2 ee = make_float2(ev[q], ev[q]);
-                    ffma2(y01, w01[q], ee);
-                    ffma2(y23, w23[q], ee);
-                }
-                const float vm = B.b2.w;                 // 1 for a gathered row, 0 for a zero-filled one (edge outside the CTA's range)
-                const float4 y = make_float4(lrelu(y01.x) * vm, lrelu(y01.y) * vm, lrelu(y23.x) * vm, lrelu(y23.y) * vm);
-                const float4 hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
-                const float4 lo = make_float4(tf32_hi(y.x - hi.x), tf32_hi(y.y - hi.y), tf32_hi(y.z - hi.z), tf32_hi(y.w - hi.w));
-                const uint32_t off = (uint32_t)c4 * (TE * 16) + (uint32_t)(er >> 3) * 128 + (uint32_t)(er & 7) * 16;
-                *reinterpret_cast<float4*>(dst_hi + off) = hi;
-                *reinterpret_cast<float4*>(dst_lo + off) = lo;
-                if (GRAM && !(SGB_ABL & 16)) {          // transposed copy: rows 0..63 lo, 64..127 hi
-                    const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
-                    const uint32_t e1 = (uint32_t)((er >> 4) * (GR * 64) + (er & 3) * 4), eq = (uint32_t)(((er & 15) >> 2) << 4);
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4) {      // ht_off(r, er) with the row-dependent terms hoisted (ht_rb / ht_rx); row 64 + r = + 8 atoms
-                        const uint32_t o = ht_rb[s4] + e1 + (eq ^ ht_rx[s4]);
-                        *reinterpret_cast<float*>(dst_t + o) = lv[s4];
-                        *reinterpret_cast<float*>(dst_t + o + 8 * 512) = hv[s4];
-                    }
-                }
-            };
-            Blk A, Bq;
-            int blk = grp;
-            load_blk(blk, A);
-#pragma unroll 1
-            for (; blk + 2 < C::BLOCKS; blk += 4) {
-                load_blk(blk + 2, Bq);
-                finish_blk(blk, A);
-                if (blk + 4 < C::BLOCKS) load_blk(blk + 4, A);
-                finish_blk(blk + 2, Bq);
-            }
-            if (blk < C::BLOCKS) finish_blk(blk, A);    // odd number of blocks per warp (TE = 80)
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[st]);
-        }
-    } else if (warp == MMA_WARP) {
-        // ================= MMA issuer
-        const uint32_t idesc = make_idesc_tf32(64, TE, false, false);
-        const uint32_t idesc_g = make_idesc_tf32(128, GN, false, false);
-        const uint32_t a_hi = smem_u32(sm + C::w2_hi), a_lo = smem_u32(sm + C::w2_lo);
-        for (int t = 0; t < ntiles; ++t) {
-            const int st = t & 1;
-            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            const int seg = t / FLUSH, gb = seg & 1;
-            mbar_wait(&bar_full[st], ph);
-            mbar_wait(&bar_tempty[st], ph ^ 1u);
-            if (GRAM && t % FLUSH == 0) mbar_wait(&bar_gempty[gb], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
-            fence_after_sync();
-            if (elect_one_sync()) {
-                const uint32_t b_hi = smem_u32(sm + C::stage0 + st * C::STAGE_BYTES), b_lo = b_hi + C::TILE_BYTES;
-                const uint32_t d = tmem + (uint32_t)(st * C::Z_COL);
-#pragma unroll
-                for (int i = 0; i < COUT / 8; ++i) {
-                    const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
-                    const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
-                    const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
-                    mma_tf32(d, dah, dbh, idesc, i > 0);
-                    if (!(SGB_ABL & 4)) {
-                        mma_tf32(d, dal, dbh, idesc, true);
-                        mma_tf32(d, dah, dbl, idesc, true);
-                    }
-                }
-                mma_commit(&bar_tfull[st]);
-                if (GRAM) {
-                    const uint32_t ht = b_lo + C::TILE_BYTES;
-                    const uint32_t dg = tmem + (uint32_t)(C::G_COL0 + gb * 128);
-#pragma unroll
-                    for (int s = 0; s < ((SGB_ABL & 8) ? 1 : TE / 8); ++s) {              // 8 edges (K) per instruction
-                        const uint32_t ko = (uint32_t)(s >> 1) * (GR * 64) + (uint32_t)(s & 1) * 32;
-                        const uint64_t da = make_desc_sw(ht + ko, 16, 512, 4);
-                        const uint64_t db = make_desc_sw(ht + ko + 8 * 512, 16, 512, 4);      // rows 64.. : hi, ones, zeros
-                        mma_tf32(dg, da, db, idesc_g, (t % FLUSH) > 0 || s > 0);
-                    }
-                    if ((t + 1) % FLUSH == 0 || t == ntiles - 1) mma_commit(&bar_gfull[gb]);
-                }
-                mma_commit(&bar_empty[st]);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ================= epilogue: warp q owns channels 16q + lane (lanes 0..15); one point = 20 consecutive columns
-        const int c = warp * 16 + (lane & 15);
-        const bool owner = lane < 16;
-        const bool up = __ldg(gamma2 + c) > 0.f;
-        // running sums over the CTA's tiles as unevaluated fp32 pairs (two-sum): FP64 adds cost ~100 cycles per warp on this part
-        // (ncu source view: 10 % of the epilogue's samples sat on the two DADDs per tile)
-        float S1h = 0.f, S1l = 0.f, S2h = 0.f, S2l = 0.f;
-        auto two_sum = [](float& h, float& l, float x) {
-            const float s_ = h + x;
-            const float bb = s_ - h;
-            l += (h - (s_ - bb)) + (x - bb);
-            h = s_;
-        };
-        for (int t = 0; t < ntiles; ++t) {
-            const int st = t & 1;
-            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            mbar_wait(&bar_tfull[st], ph);
-            fence_after_sync();
-            const long long g0 = g_begin + (long long)t * TE;
-            const int npts = (int)min((long long)C::PTS, (g_end - g0) / KNN);
-            const long long p0 = g0 / KNN;
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * C::Z_COL);
-            float ps[4] = {0.f, 0.f, 0.f, 0.f}, qs[4] = {0.f, 0.f, 0.f, 0.f};      // four independent chains each for sum z and sum z^2
-            // BN2 + LeakyReLU is monotone per channel, increasing iff gamma2 > 0: only that extreme of the 20 pre-activations (and its
-            // neighbour slot) is kept.  The extreme is found by a tournament (depth 5 instead of a chain of 19 compare / select pairs; the
-            // left operand wins ties, so the FIRST extreme is kept exactly as in a left-to-right scan); two points per iteration share
-            // one tcgen05.wait::ld.  Warp-uniform fast paths for the usual cases (all scales positive / all negative).
-            auto reduce_point = [&](const uint32_t (&ra)[16], const uint32_t (&rb)[4], int pp, auto better) {
-                float z[KNN];
-#pragma unroll
-                for (int i = 0; i < KNN; ++i) z[i] = __uint_as_float(i < 16 ? ra[i] : rb[i - 16]);
-#pragma unroll
-                for (int i = 0; i < KNN; ++i) { ps[i & 3] += z[i]; qs[i & 3] = fmaf(z[i], z[i], qs[i & 3]); }
-                float m[10];
-                int k[10];
-#pragma unroll
-                for (int j = 0; j < 10; ++j) { const bool r = better(z[2 * j + 1], z[2 * j]); m[j] = r ? z[2 * j + 1] : z[2 * j]; k[j] = r ? 2 * j + 1 : 2 * j; }
-#pragma unroll
-                for (int j = 0; j < 5; ++j) { const bool r = better(m[2 * j + 1], m[2 * j]); m[j] = r ? m[2 * j + 1] : m[2 * j]; k[j] = r ? k[2 * j + 1] : k[2 * j]; }
-                { const bool r = better(m[1], m[0]); m[0] = r ? m[1] : m[0]; k[0] = r ? k[1] : k[0]; }
-                { const bool r = better(m[3], m[2]); m[2] = r ? m[3] : m[2]; k[2] = r ? k[3] : k[2]; }
-                { const bool r = better(m[2], m[0]); m[0] = r ? m[2] : m[0]; k[0] = r ? k[2] : k[0]; }
-                { const bool r = better(m[4], m[0]); m[0] = r ? m[4] : m[0]; k[0] = r ? k[4] : k[0]; }
-                if (owner) {
-                    const size_t o = (size_t)(p0 + pp) * COUT + c;
-                    zsel[o] = m[0];
-                    if (ARG) ksel[o] = (unsigned char)k[0];
-                }
-            };
-            auto scan = [&](auto better) {
-                const int nloop = (SGB_ABL & 2) ? 1 : npts;
-#pragma unroll 1
-                for (int pp = 0; pp < nloop; pp += 2) {
-                    uint32_t a16[16], a4[4], b16[16], b4[4];
-                    const bool two = pp + 1 < nloop;         // warp-uniform
-                    tmem_ld16_issue(taddr + (uint32_t)(pp * KNN), a16);
-                    tmem_ld4_issue(taddr + (uint32_t)(pp * KNN + 16), a4);
-                    if (two) {
-                        tmem_ld16_issue(taddr + (uint32_t)((pp + 1) * KNN), b16);
-                        tmem_ld4_issue(taddr + (uint32_t)((pp + 1) * KNN + 16), b4);
-                    }
-                    tmem_ld_wait();
-                    tmem_ld_pin20(a16, a4);
-                    reduce_point(a16, a4, pp, better);
-                    if (two) {
-                        tmem_ld_pin20(b16, b4);
-                        reduce_point(b16, b4, pp + 1, better);
-                    }
-                }
-            };
-            if (__all_sync(SGB_FULL_MASK, up)) scan([](float z, float b) { return z > b; });
-            else if (__all_sync(SGB_FULL_MASK, !up)) scan([](float z, float b) { return z < b; });
-            else scan([up](float z, float b) { return up ? z > b : z < b; });
-            two_sum(S1h, S1l, (ps[0] + ps[1]) + (ps[2] + ps[3]));
-            two_sum(S2h, S2l, (qs[0] + qs[1]) + (qs[2] + qs[3]));
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[st]);
-            if (GRAM && ((t + 1) % FLUSH == 0 || t == ntiles - 1)) {
-                // flush the finished Gram segment: thread = accumulator row (all 128 lanes hold data for M = 128)
-                const int seg = t / FLUSH, gb = seg & 1;
-                mbar_wait(&bar_gfull[gb], (uint32_t)(seg >> 1) & 1u);
-                fence_after_sync();
-                float* dst = gslots + ((size_t)blockIdx.x * nflush + seg) * (128 * GN) + (size_t)(warp * 32 + lane) * GN;
-                const uint32_t gaddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::G_COL0 + gb * 128);
-#pragma unroll 1
-                for (int c0 = 0; c0 < GN; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(gaddr + (uint32_t)c0, v);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<float4*>(dst + c0 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                }
-                fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_gempty[gb]);
-            }
-        }
-        if (owner) {
-            part[(size_t)blockIdx.x * 128 + c] = (double)S1h + (double)S1l;
-            part[(size_t)blockIdx.x * 128 + 64 + c] = (double)S2h + (double)S2l;
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
-}
-
-// =================================================================================================================================
-// Round 3: BOTH layers on the tensor cores.
-//
-// The kernel above left the first layer (18 -> 64, BN1 folded in) on the CUDA cores: 16 producer threads per edge, each re-reading
-// the edge's two raw rows and spending ~110 instructions on 4 hidden channels (~1,700 per edge), which made the producers the critical
-// role of a kernel whose tensor pipe sat at 37-39 %.  Here the first layer is one more small GEMM per tile,
-//     D1[128 edge rows, 64 channels] = E[128, 24] * W1s[64, 24]^T          (kind::tf32 x 3, K = 9 differences + 9 centre + 1 + 5 zero)
-// with E = (x_j - x_i, x_i, valid, 0...) assembled by ONE thread per edge (hi / lo split, six 16-byte stores) and
-// W1s = (scale1 W1 | beta1 - scale1 mean1 | 0): the constant-1 column carries the folded BatchNorm-1 bias, an all-zero row (edge
-// outside the CTA's range) gives h = lrelu(0) = 0.  The edges lie on the TMEM LANES of D1, so a producer thread then owns one edge
-// row: tcgen05.ld of 32 of its 64 pre-activations (two warps per TMEM quadrant, one per channel half), LeakyReLU, hi / lo split and
-// 16-byte stores into the K-major H tile (consecutive lanes = consecutive rows: conflict-free) — ~250 instructions per edge and
-// channel half instead of ~1,700.  In the Gram variant the transposed copy is 32 consecutive edges of one channel row per store.
-// Roles and pipelines otherwise as above; per tile the producers run  [E(t)] -> [H(t-1)]  so that the first-layer MMA of tile t
-// overlaps the second half of the step, and the MMA warp issues  MMA1(t), Gram(t-1), MMA2(t-1).
-// Tiles: 120 edges (6 points; rows 120..127 of the M = 128 operand are whatever follows in shared memory — their D1 rows are never
-// read) without the Gram, 80 edges (4 points) with it (the transposed tile is single-buffered: the Gram MMAs are issued first).
 template <bool GRAM> struct Cfg1 {
     static constexpr int TE = GRAM ? 80 : 120;
     static constexpr int PTS = TE / KNN;
@@ -510,7 +88,8 @@ template <bool GRAM> struct Cfg1 {
     static constexpr int TILE_BYTES = TE * COUT * 4;               // one K-major H tile (hi or lo)
     static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
     static constexpr int HT_BYTES = GRAM ? GR * TE * 4 : 0;        // transposed tile (lo, hi, ones / zero rows), one buffer
-    static constexpr int E_BYTES = TE * KE * 4;                    // one K-major E tile (hi or lo), one buffer
+    static constexpr int E_BYTES = TE * 20 * 4;                    // one K-major E tile (hi or lo): chunks 0..4; the zero chunk (K = 20..23) is shared
+    static constexpr int EZ_BYTES = 128 * 16;                      // the shared zero chunk, M = 128 rows
     static constexpr int W1_BYTES = COUT * KE * 4;
     static constexpr int w2_hi = 0;
     static constexpr int w2_lo = w2_hi + W2_BYTES;
@@ -518,25 +97,26 @@ template <bool GRAM> struct Cfg1 {
     static constexpr int w1_lo = w1_hi + W1_BYTES;
     static constexpr int stage0 = w1_lo + W1_BYTES;
     static constexpr int ht0 = stage0 + 2 * STAGE_BYTES;
-    static constexpr int e_hi = ht0 + HT_BYTES;
-    static constexpr int e_lo = e_hi + E_BYTES;
+    static constexpr int e0 = ht0 + HT_BYTES;                      // E tiles: [buffer 0: hi, lo][buffer 1: hi, lo][zero chunk]
+    static constexpr int ezero = e0 + 4 * E_BYTES;
     static constexpr int RING = GRAM ? 4 : 3;
     static constexpr int RAW_BYTES = TE * 48 + PTS * 48 + TE * 8;
-    static constexpr int raw0 = e_lo + E_BYTES;                    // the M = 128 read of the last E chunk runs (128 - TE) * 16 bytes into the ring
-    static constexpr int bars = raw0 + RING * RAW_BYTES;           // 17 mbarriers
-    static constexpr int tmem_slot = bars + 20 * 8;
+    static constexpr int raw0 = ezero + EZ_BYTES;                  // (the M = 128 read of chunk 4 runs (128 - TE) * 16 bytes into whatever follows the tile)
+    static constexpr int bars = raw0 + RING * RAW_BYTES;           // 21 mbarriers
+    static constexpr int tmem_slot = bars + 22 * 8;
     static constexpr int total = tmem_slot + 16;
     static constexpr int Z_COL = GRAM ? 80 : 128;                  // TMEM: z accumulators at 0 and Z_COL
-    static constexpr int D1_COL = GRAM ? 160 : 256;                //       first-layer accumulator (64 columns)
-    static constexpr int G_COL0 = 256;                             //       Gram accumulators at 256 and 384
+    static constexpr int D1_COL = GRAM ? 160 : 256;                //       first-layer accumulators (2 x 64 columns)
+    static constexpr int G_COL0 = 288;                             //       Gram accumulator (80 columns, one buffer)
+    static constexpr int W_COL = GRAM ? 368 : 384;                 //       W2 hi | lo as the A operand of the second layer (2 x 64 columns)
 };
 static_assert(Cfg1<true>::ht0 % 1024 == 0 && Cfg1<true>::stage0 % 1024 == 0, "swizzled tile alignment");
 static_assert(Cfg1<true>::bars % 8 == 0 && Cfg1<false>::bars % 8 == 0, "barrier alignment");
 static_assert(Cfg1<true>::total + 1024 <= 227 * 1024 && Cfg1<false>::total + 1024 <= 227 * 1024, "shared memory budget");
-static_assert((128 - Cfg1<true>::TE) * 16 <= Cfg1<true>::RING * Cfg1<true>::RAW_BYTES, "E overrun stays inside the block");
+static_assert(Cfg1<true>::e0 % 16 == 0 && Cfg1<false>::e0 % 16 == 0 && Cfg1<true>::E_BYTES % 16 == 0 && Cfg1<false>::E_BYTES % 16 == 0, "descriptor alignment");
 
 template <bool ARG, bool GRAM>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS1, 1)     // 13 warps: one scheduler hosts 4 of them -> 128 registers per thread at most
 ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N, const float* __restrict__ W1,
                const float* __restrict__ stats1, const float* __restrict__ W2, const float* __restrict__ gamma2,
                float* __restrict__ zsel, unsigned char* __restrict__ ksel, double* __restrict__ part /*[grid][128]*/,
@@ -551,13 +131,16 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
     uint64_t* bar_tempty = bar_full + 6;                                     // [2] epilogue -> MMA
     uint64_t* bar_gfull = bar_full + 8;                                      // [2] MMA (commit) -> epilogue: Gram segment complete
     uint64_t* bar_gempty = bar_full + 10;                                    // [2] epilogue -> MMA: Gram accumulator flushed
-    uint64_t* bar_efull = bar_full + 12;                                     // producers -> MMA: E tile written
-    uint64_t* bar_eempty = bar_full + 13;                                    // MMA (commit after the first-layer MMAs) -> producers
-    uint64_t* bar_d1full = bar_full + 14;                                    // MMA (same commit) -> producers: D1 complete
-    uint64_t* bar_d1empty = bar_full + 15;                                   // producers -> MMA: D1 read into registers
-    uint64_t* bar_htempty = bar_full + 16;                                   // MMA (commit after the Gram MMAs) -> producers: transposed tile free
+    uint64_t* bar_efull = bar_full + 12;                                     // [2] producers -> MMA: E tile written
+    uint64_t* bar_eempty = bar_full + 14;                                    // [2] MMA (commit after the first-layer MMAs) -> producers
+    uint64_t* bar_d1full = bar_full + 16;                                    // [2] MMA (same commit) -> producers: D1 complete
+    uint64_t* bar_d1empty = bar_full + 18;                                   // [2] producers -> MMA: D1 read into registers
+    uint64_t* bar_htempty = bar_full + 20;                                   // MMA (commit after the Gram MMAs) -> producers: transposed tile free
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::tmem_slot);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SGB_ROLE_CLOCKS
+    long long wc[32]; for (int i = 0; i < 32; ++i) wc[i] = 0; const long long tstart = clock64();
+#endif
 
     const int per = N / gridDim.x, rem = N % gridDim.x;
     const int p_begin = blockIdx.x * per + min((int)blockIdx.x, rem);
@@ -566,7 +149,7 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
     const int ntiles = (int)((g_end - g_begin + TE - 1) / TE);
 
     // ---- one-time setup
-    for (int i = tid; i < COUT * COUT; i += THREADS) {              // W2 [c][j] -> K-major canonical tile (rows = c, K = j)
+    for (int i = tid; i < COUT * COUT; i += THREADS1) {              // W2 [c][j] -> K-major canonical tile (rows = c, K = j)
         const int c = i / COUT, j = i % COUT;
         const float w = __ldg(W2 + i);
         const float hi = tf32_hi(w);
@@ -574,7 +157,7 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
         *reinterpret_cast<float*>(sm + C::w2_hi + off) = hi;
         *reinterpret_cast<float*>(sm + C::w2_lo + off) = tf32_hi(w - hi);
     }
-    for (int i = tid; i < COUT * C::KE; i += THREADS) {             // W1s [c][k]: BN1 scale folded in, column 18 = folded bias
+    for (int i = tid; i < COUT * C::KE; i += THREADS1) {             // W1s [c][k]: BN1 scale folded in, column 18 = folded bias
         const int c = i / C::KE, k = i % C::KE;
         const float sc = stats1[128 + c];
         float w = 0.f;
@@ -585,13 +168,15 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
         *reinterpret_cast<float*>(sm + C::w1_hi + off) = hi;
         *reinterpret_cast<float*>(sm + C::w1_lo + off) = tf32_hi(w - hi);
     }
-    for (int i = tid; i < TE; i += THREADS) {                       // chunk 5 of the E tiles (K = 20..23): zero, never rewritten
-        *reinterpret_cast<float4*>(sm + C::e_hi + 5 * (TE * 16) + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sm + C::e_lo + 5 * (TE * 16) + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 128; i += THREADS1)                       // K = 20..23 of every E tile: one shared chunk of zeros
+        *reinterpret_cast<float4*>(sm + C::ezero + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < COUT * COUT; i += THREADS1) {             // identity (aliases H stage 0 until the first tile): W2 reaches TMEM as W2 * I
+        const int n = i / COUT, j = i % COUT;
+        *reinterpret_cast<float*>(sm + C::stage0 + tile_off(n, j, COUT)) = (n == j) ? 1.f : 0.f;
     }
     if (GRAM) {                                                     // extra rows of the transposed tile: ones, then zeros
         unsigned char* ht = sm + C::ht0;
-        for (int i = tid; i < 16 * TE; i += THREADS) {
+        for (int i = tid; i < 16 * TE; i += THREADS1) {
             const int r = 128 + i / TE, e = i % TE;
             *reinterpret_cast<float*>(ht + ht_off(r, e)) = (r == 128) ? 1.f : 0.f;
         }
@@ -600,24 +185,26 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
         mbar_init(&bar_full[0], PROD_WARPS); mbar_init(&bar_full[1], PROD_WARPS);
         mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
         mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
-        mbar_init(&bar_tempty[0], EPI_WARPS); mbar_init(&bar_tempty[1], EPI_WARPS);
+        mbar_init(&bar_tempty[0], EPI1); mbar_init(&bar_tempty[1], EPI1);
         mbar_init(&bar_gfull[0], 1); mbar_init(&bar_gfull[1], 1);
-        mbar_init(&bar_gempty[0], EPI_WARPS); mbar_init(&bar_gempty[1], EPI_WARPS);
-        mbar_init(bar_efull, PROD_WARPS); mbar_init(bar_eempty, 1);
-        mbar_init(bar_d1full, 1); mbar_init(bar_d1empty, PROD_WARPS);
+        mbar_init(&bar_gempty[0], EPI1); mbar_init(&bar_gempty[1], EPI1);
+        for (int b2 = 0; b2 < 2; ++b2) {
+            mbar_init(&bar_efull[b2], PROD_WARPS); mbar_init(&bar_eempty[b2], 1);
+            mbar_init(&bar_d1full[b2], 1); mbar_init(&bar_d1empty[b2], PROD_WARPS);
+        }
         mbar_init(bar_htempty, 1);
         mbar_fence_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == MMA1W) tmem_alloc(tmem_slot, TMEM_COLS);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp > MMA_WARP) {
+    if (warp > MMA1W) {
         // ================= producers
-        const int pw = warp - (MMA_WARP + 1);           // 0..7
+        const int pw = warp - (MMA1W + 1);              // 0..7
         const int ptid = pw * 32 + lane;                // gather / E role: edge row `ptid` of the tile (if < TE)
         const int quad = warp & 3;                      // the TMEM lanes this warp may read: 32 quad .. 32 quad + 31
         const int chh = pw >> 2;                        // H role: channels 32 chh .. 32 chh + 31 of edge row 32 quad + lane
@@ -673,11 +260,14 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
         for (int t = 0; t <= ntiles; ++t) {
             if (t < ntiles) {
                 // ---- E(t): the edge vectors of tile t as the A operand of the first layer
-                asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory");     // my copies for tile t (and the indices of tile t + RING - 1) have landed
-                asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");         // everybody's have, and everybody is done with tile t - 1
+                WAITC(30, asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory"));
+                WAITC(31, asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory"));
                 issue_rows(t + RING - 1, staged_index(t + RING - 1));                    // refill the slot tile t - 1 used
-                mbar_wait(bar_eempty, ((uint32_t)t & 1u) ^ 1u);
+                const int eb = t & 1;
+                WAITC(0, mbar_wait(&bar_eempty[eb], (((uint32_t)t >> 1) & 1u) ^ 1u));
                 if (gatherer) {
+                    unsigned char* e_hi = sm + C::e0 + eb * (2 * C::E_BYTES);
+                    unsigned char* e_lo = e_hi + C::E_BYTES;
                     const unsigned char* raw = sm + C::raw0 + (t % RING) * C::RAW_BYTES;
                     const int pt = (ptid * 205) >> 12;      // ptid / KNN
                     const float4* rj = reinterpret_cast<const float4*>(raw + ptid * 48);
@@ -696,36 +286,39 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
                         const float4 y = make_float4(ch[q].x * one, ch[q].y * one, ch[q].z * one, ch[q].w * one);
                         float4 hi, lo;
                         split4(y, hi, lo);
-                        *reinterpret_cast<float4*>(sm + C::e_hi + q * (TE * 16) + ptid * 16) = hi;
-                        *reinterpret_cast<float4*>(sm + C::e_lo + q * (TE * 16) + ptid * 16) = lo;
+                        *reinterpret_cast<float4*>(e_hi + q * (TE * 16) + ptid * 16) = hi;
+                        *reinterpret_cast<float4*>(e_lo + q * (TE * 16) + ptid * 16) = lo;
                     }
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_efull);
+                if (lane == 0) mbar_arrive(&bar_efull[eb]);
             }
             if (t >= 1) {
                 // ---- H(u): hidden activations of tile u = t - 1 from the first-layer accumulator
                 const int u = t - 1, su = u & 1;
-                mbar_wait(bar_d1full, (uint32_t)u & 1u);
+                WAITC(1, mbar_wait(&bar_d1full[su], ((uint32_t)u >> 1) & 1u));
                 fence_after_sync();
                 uint32_t va[16], vb[16];
-                tmem_ld16_issue(d1addr, va);
-                tmem_ld16_issue(d1addr + 16u, vb);
+                tmem_ld16_issue(d1addr + (uint32_t)(su * 64), va);
+                tmem_ld16_issue(d1addr + (uint32_t)(su * 64 + 16), vb);
                 tmem_ld_wait();
                 tmem_ld_pin16(va);
                 tmem_ld_pin16(vb);
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_d1empty);
-                mbar_wait(&bar_empty[su], (((uint32_t)(u >> 1)) & 1u) ^ 1u);
+                if (lane == 0) mbar_arrive(&bar_d1empty[su]);
+                WAITC(2, mbar_wait(&bar_empty[su], (((uint32_t)(u >> 1)) & 1u) ^ 1u));
                 unsigned char* dst_hi = sm + C::stage0 + su * C::STAGE_BYTES;
                 unsigned char* dst_lo = dst_hi + C::TILE_BYTES;
                 const bool rowv = hrow < TE;
-                if (GRAM) mbar_wait(bar_htempty, ((uint32_t)u & 1u) ^ 1u);      // the Gram MMAs of tile u - 1 were issued before its second layer
+                if (GRAM) WAITC(3, mbar_wait(bar_htempty, ((uint32_t)u & 1u) ^ 1u));      // the Gram MMAs of tile u - 1 were issued before its second layer
                 // transposed copy of the Gram variant: rows 0..63 lo, 64..127 hi (row = channel), 32 consecutive edges of one row per store
                 unsigned char* dst_t = sm + C::ht0 + (uint32_t)chh * (4 * 512);
                 const uint32_t e1 = (uint32_t)((hrow >> 4) * (GR * 64) + (hrow & 3) * 4), eq = (uint32_t)(((hrow & 15) >> 2) << 4);
+                unsigned char* htb[4];                  // the four swizzle classes of a row: everything else is an immediate offset
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) htb[k4] = dst_t + e1 + (eq ^ (uint32_t)(k4 << 4));
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
                     float y[4];
@@ -740,14 +333,15 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
                         const uint32_t off = (uint32_t)(8 * chh + i4) * (TE * 16) + (uint32_t)hrow * 16;
                         *reinterpret_cast<float4*>(dst_hi + off) = hi;
                         *reinterpret_cast<float4*>(dst_lo + off) = lo;
-                        if (GRAM) {
+                        if (GRAM) {                         // (the warp's two halves write neighbouring 16-edge atoms, 9216 bytes apart: a 2-way bank
+                            // conflict per store; swapping channel pairs in the upper half removes it but costs a select per store and measured slower)
                             const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                             for (int s4 = 0; s4 < 4; ++s4) {
                                 const int ci = 4 * i4 + s4;                  // channel 32 chh + ci = row of the transposed tile
-                                const uint32_t o = (uint32_t)((ci >> 3) * 512 + (ci & 7) * 64) + e1 + (eq ^ (uint32_t)(((ci >> 1) & 3) << 4));
-                                *reinterpret_cast<float*>(dst_t + o) = lv[s4];
-                                *reinterpret_cast<float*>(dst_t + o + 8 * 512) = hv[s4];
+                                unsigned char* q = htb[(ci >> 1) & 3] + ((ci >> 3) * 512 + (ci & 7) * 64);
+                                *reinterpret_cast<float*>(q) = lv[s4];
+                                *reinterpret_cast<float*>(q + 8 * 512) = hv[s4];
                             }
                         }
                     }
@@ -758,67 +352,96 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == MMA_WARP) {
+    } else if (warp == MMA1W) {
         // ================= MMA issuer
         const uint32_t idesc1 = make_idesc_tf32(128, COUT, false, false);
         const uint32_t idesc = make_idesc_tf32(64, TE, false, false);
         const uint32_t idesc_g = make_idesc_tf32(128, GN, false, false);
         const uint32_t a_hi = smem_u32(sm + C::w2_hi), a_lo = smem_u32(sm + C::w2_lo);
         const uint32_t w1h = smem_u32(sm + C::w1_hi), w1l = smem_u32(sm + C::w1_lo);
-        const uint32_t eh = smem_u32(sm + C::e_hi), el = smem_u32(sm + C::e_lo);
+        const uint32_t ez = smem_u32(sm + C::ezero);
+        // W2 (hi, lo) into TMEM in the layout of an M = 64 accumulator: D = W2 * I (exact: tf32 values times one).  The tensor pipe runs in
+        // issue order, so every later MMA — and the first write into H stage 0, which waits for the first-layer MMA of tile 0 — comes after.
+        if (elect_one_sync()) {
+            const uint32_t idw = make_idesc_tf32(64, COUT, false, false);
+            const uint32_t idn = smem_u32(sm + C::stage0);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                for (int i = 0; i < COUT / 8; ++i) {
+                    const uint32_t o = (uint32_t)(2 * i) * (COUT * 16);
+                    mma_tf32(tmem + (uint32_t)(C::W_COL + h2 * 64), make_desc((h2 ? a_lo : a_hi) + o, COUT * 16, 128), make_desc(idn + o, COUT * 16, 128), idw, i > 0);
+                }
+        }
+        __syncwarp();
+        // Descriptors are loop-invariant up to the start-address field: bases are built once, a K step is an add of (bytes >> 4) to the low
+        // word (smem addresses < 256 KB: the 14-bit field cannot carry).  The issuing thread is a single instruction stream that shares
+        // its scheduler with three busy warps; at ~60 tensor cycles per instruction every ALU operation between two tcgen05.mma counts.
+        auto adv = [](uint64_t dsc, uint32_t bytes) -> uint64_t { return dsc + (uint64_t)(bytes >> 4); };
+        const uint64_t dW1h = make_desc(w1h, COUT * 16, 128), dW1l = make_desc(w1l, COUT * 16, 128);
+        uint64_t dEh[2], dEl[2], dEh2[2], dEl2[2], dHh[2], dHl[2];
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+            const uint32_t eh = smem_u32(sm + C::e0 + b2 * (2 * C::E_BYTES)), el = eh + C::E_BYTES;
+            dEh[b2] = make_desc(eh, TE * 16, 128);
+            dEl[b2] = make_desc(el, TE * 16, 128);
+            dEh2[b2] = make_desc(eh + 4 * (TE * 16), ez - (eh + 4 * (TE * 16)), 128);      // K chunk 4 paired with the shared zero chunk
+            dEl2[b2] = make_desc(el + 4 * (TE * 16), ez - (el + 4 * (TE * 16)), 128);
+            const uint32_t hh = smem_u32(sm + C::stage0 + b2 * C::STAGE_BYTES);
+            dHh[b2] = make_desc(hh, TE * 16, 128);
+            dHl[b2] = make_desc(hh + C::TILE_BYTES, TE * 16, 128);
+        }
+        const uint64_t dGa = make_desc_sw(smem_u32(sm + C::ht0), 16, 512, 4), dGb = make_desc_sw(smem_u32(sm + C::ht0) + 8 * 512, 16, 512, 4);
         for (int t = 0; t <= ntiles; ++t) {
             if (t < ntiles) {
-                mbar_wait(bar_efull, (uint32_t)t & 1u);
-                mbar_wait(bar_d1empty, ((uint32_t)t & 1u) ^ 1u);
+                const int eb = t & 1;
+                const uint32_t ph1 = ((uint32_t)t >> 1) & 1u;
+                WAITC(4, mbar_wait(&bar_efull[eb], ph1));
+                WAITC(5, mbar_wait(&bar_d1empty[eb], ph1 ^ 1u));
                 fence_after_sync();
+                const uint64_t eh = eb ? dEh[1] : dEh[0], el = eb ? dEl[1] : dEl[0], eh2 = eb ? dEh2[1] : dEh2[0], el2 = eb ? dEl2[1] : dEl2[0];
+                const uint32_t d1 = tmem + (uint32_t)(C::D1_COL + eb * 64);
                 if (elect_one_sync()) {
-                    const uint32_t d1 = tmem + (uint32_t)C::D1_COL;
 #pragma unroll
                     for (int i = 0; i < C::KE / 8; ++i) {
-                        const uint32_t ao = (uint32_t)(2 * i) * (TE * 16), bo = (uint32_t)(2 * i) * (COUT * 16);
-                        const uint64_t dah = make_desc(eh + ao, TE * 16, 128), dal = make_desc(el + ao, TE * 16, 128);
-                        const uint64_t dbh = make_desc(w1h + bo, COUT * 16, 128), dbl = make_desc(w1l + bo, COUT * 16, 128);
+                        const uint64_t dah = i < 2 ? adv(eh, 2 * i * (TE * 16)) : eh2, dal = i < 2 ? adv(el, 2 * i * (TE * 16)) : el2;
+                        const uint64_t dbh = adv(dW1h, 2 * i * (COUT * 16)), dbl = adv(dW1l, 2 * i * (COUT * 16));
                         mma_tf32(d1, dah, dbh, idesc1, i > 0);
                         mma_tf32(d1, dal, dbh, idesc1, true);
                         mma_tf32(d1, dah, dbl, idesc1, true);
                     }
-                    mma_commit(bar_d1full);
-                    mma_commit(bar_eempty);
+                    mma_commit(&bar_d1full[eb]);
+                    mma_commit(&bar_eempty[eb]);
                 }
                 __syncwarp();
             }
             if (t >= 1) {
                 const int u = t - 1, st = u & 1;
                 const uint32_t ph = (uint32_t)(u >> 1) & 1u;
-                const int seg = u / FLUSH, gb = seg & 1;
-                mbar_wait(&bar_full[st], ph);
-                mbar_wait(&bar_tempty[st], ph ^ 1u);
-                if (GRAM && u % FLUSH == 0) mbar_wait(&bar_gempty[gb], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
+                const int seg = u / FLUSH;
+                WAITC(6, mbar_wait(&bar_full[st], ph));
+                WAITC(7, mbar_wait(&bar_tempty[st], ph ^ 1u));
+                if (GRAM && u % FLUSH == 0) WAITC(8, mbar_wait(&bar_gempty[0], ((uint32_t)seg & 1u) ^ 1u));
                 fence_after_sync();
+                const uint64_t hh = st ? dHh[1] : dHh[0], hl = st ? dHl[1] : dHl[0];
+                const uint32_t d = tmem + (uint32_t)(st * C::Z_COL), wb = tmem + (uint32_t)C::W_COL, dg = tmem + (uint32_t)C::G_COL0;
+                const bool gacc = (u % FLUSH) > 0, glast = (u + 1) % FLUSH == 0 || u == ntiles - 1;
                 if (elect_one_sync()) {
-                    const uint32_t b_hi = smem_u32(sm + C::stage0 + st * C::STAGE_BYTES), b_lo = b_hi + C::TILE_BYTES;
                     if (GRAM) {                         // first: the transposed tile has ONE buffer and is free again as soon as these complete
-                        const uint32_t ht = smem_u32(sm + C::ht0);
-                        const uint32_t dg = tmem + (uint32_t)(C::G_COL0 + gb * 128);
 #pragma unroll
-                        for (int s = 0; s < TE / 8; ++s) {                               // 8 edges (K) per instruction
-                            const uint32_t ko = (uint32_t)(s >> 1) * (GR * 64) + (uint32_t)(s & 1) * 32;
-                            const uint64_t da = make_desc_sw(ht + ko, 16, 512, 4);
-                            const uint64_t db = make_desc_sw(ht + ko + 8 * 512, 16, 512, 4);      // rows 64.. : hi, ones, zeros
-                            mma_tf32(dg, da, db, idesc_g, (u % FLUSH) > 0 || s > 0);
+                        for (int s2 = 0; s2 < TE / 8; ++s2) {                              // 8 edges (K) per instruction
+                            const uint32_t ko = (uint32_t)(s2 >> 1) * (GR * 64) + (uint32_t)(s2 & 1) * 32;
+                            mma_tf32(dg, adv(dGa, ko), adv(dGb, ko), idesc_g, gacc || s2 > 0);
                         }
                         mma_commit(bar_htempty);
-                        if ((u + 1) % FLUSH == 0 || u == ntiles - 1) mma_commit(&bar_gfull[gb]);
+                        if (glast) mma_commit(&bar_gfull[0]);
                     }
-                    const uint32_t d = tmem + (uint32_t)(st * C::Z_COL);
 #pragma unroll
-                    for (int i = 0; i < COUT / 8; ++i) {
-                        const uint32_t ao = (uint32_t)(2 * i) * (COUT * 16), bo = (uint32_t)(2 * i) * (TE * 16);
-                        const uint64_t dah = make_desc(a_hi + ao, COUT * 16, 128), dal = make_desc(a_lo + ao, COUT * 16, 128);
-                        const uint64_t dbh = make_desc(b_hi + bo, TE * 16, 128), dbl = make_desc(b_lo + bo, TE * 16, 128);
-                        mma_tf32(d, dah, dbh, idesc, i > 0);
-                        mma_tf32(d, dal, dbh, idesc, true);
-                        mma_tf32(d, dah, dbl, idesc, true);
+                    for (int i = 0; i < COUT / 8; ++i) {                                   // A = W2 from TMEM: 8 columns (K) per instruction
+                        const uint64_t dbh = adv(hh, 2 * i * (TE * 16)), dbl = adv(hl, 2 * i * (TE * 16));
+                        mma_tf32_ts(d, wb + (uint32_t)(8 * i), dbh, idesc, i > 0);
+                        mma_tf32_ts(d, wb + (uint32_t)(64 + 8 * i), dbh, idesc, true);
+                        mma_tf32_ts(d, wb + (uint32_t)(8 * i), dbl, idesc, true);
                     }
                     mma_commit(&bar_tfull[st]);
                     mma_commit(&bar_empty[st]);
@@ -827,9 +450,12 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
             }
         }
     } else {
-        // ================= epilogue: warp q owns channels 16q + lane (lanes 0..15); one point = 20 consecutive columns
-        const int c = warp * 16 + (lane & 15);
-        const bool owner = lane < 16;
+        // ================= epilogue: the two warps of TMEM quadrant q own channels 16q + lane (lanes 0..15) and split the points of a
+        // tile between them; one point = 20 consecutive columns
+        const int quad = warp & 3, half = warp >> 2;
+        const int c = quad * 16 + (lane & 15);
+        const int hp = lane >> 4;                       // an M = 64 accumulator keeps its rows on lanes 0..15 of the quadrant: the .16x32bx2 loads give
+                                                        // the upper half-warp the NEXT point (20 columns further) of the same 16 channels
         const bool up = __ldg(gamma2 + c) > 0.f;
         float S1h = 0.f, S1l = 0.f, S2h = 0.f, S2l = 0.f;      // running sums as unevaluated fp32 pairs (two-sum)
         auto two_sum = [](float& h, float& l, float x) {
@@ -841,12 +467,13 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            mbar_wait(&bar_tfull[st], ph);
+            WAITC(9, mbar_wait(&bar_tfull[st], ph));
             fence_after_sync();
             const long long g0 = g_begin + (long long)t * TE;
             const int npts = (int)min((long long)C::PTS, (g_end - g0) / KNN);
             const long long p0 = g0 / KNN;
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * C::Z_COL);
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * C::Z_COL);
+            const int pbeg = min(npts, half * (C::PTS / NH1)), pend = half == NH1 - 1 ? npts : min(npts, (half + 1) * (C::PTS / NH1));
             float ps[4] = {0.f, 0.f, 0.f, 0.f}, qs[4] = {0.f, 0.f, 0.f, 0.f};
             // BN2 + LeakyReLU is monotone per channel, increasing iff gamma2 > 0: only that extreme of the 20 pre-activations (and its
             // neighbour slot) is kept, found by a tournament (the left operand wins ties: the FIRST extreme, as in a left-to-right scan)
@@ -866,29 +493,29 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
                 { const bool r = better(m[3], m[2]); m[2] = r ? m[3] : m[2]; k[2] = r ? k[3] : k[2]; }
                 { const bool r = better(m[2], m[0]); m[0] = r ? m[2] : m[0]; k[0] = r ? k[2] : k[0]; }
                 { const bool r = better(m[4], m[0]); m[0] = r ? m[4] : m[0]; k[0] = r ? k[4] : k[0]; }
-                if (owner) {
-                    const size_t o = (size_t)(p0 + pp) * COUT + c;
+                if (pp + hp < pend) {
+                    const size_t o = (size_t)(p0 + pp + hp) * COUT + c;
                     zsel[o] = m[0];
                     if (ARG) ksel[o] = (unsigned char)k[0];
                 }
             };
-            auto scan = [&](auto better) {
+            auto scan = [&](auto better) {              // a pair of points per load, two pairs per wait; columns past the last point hold z = 0 (h = 0)
 #pragma unroll 1
-                for (int pp = 0; pp < npts; pp += 2) {
+                for (int pp = pbeg; pp < pend; pp += 4) {
                     uint32_t a16[16], a4[4], b16[16], b4[4];
-                    const bool two = pp + 1 < npts;         // warp-uniform
-                    tmem_ld16_issue(taddr + (uint32_t)(pp * KNN), a16);
-                    tmem_ld4_issue(taddr + (uint32_t)(pp * KNN + 16), a4);
+                    const bool two = pp + 2 < pend;         // warp-uniform
+                    tmem_ld16_halves_issue<KNN>(taddr + (uint32_t)(pp * KNN), a16);
+                    tmem_ld4_halves_issue<KNN>(taddr + (uint32_t)(pp * KNN + 16), a4);
                     if (two) {
-                        tmem_ld16_issue(taddr + (uint32_t)((pp + 1) * KNN), b16);
-                        tmem_ld4_issue(taddr + (uint32_t)((pp + 1) * KNN + 16), b4);
+                        tmem_ld16_halves_issue<KNN>(taddr + (uint32_t)((pp + 2) * KNN), b16);
+                        tmem_ld4_halves_issue<KNN>(taddr + (uint32_t)((pp + 2) * KNN + 16), b4);
                     }
                     tmem_ld_wait();
                     tmem_ld_pin20(a16, a4);
                     reduce_point(a16, a4, pp, better);
                     if (two) {
                         tmem_ld_pin20(b16, b4);
-                        reduce_point(b16, b4, pp + 1, better);
+                        reduce_point(b16, b4, pp + 2, better);
                     }
                 }
             };
@@ -902,13 +529,13 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
             if (lane == 0) mbar_arrive(&bar_tempty[st]);
             if (GRAM && ((t + 1) % FLUSH == 0 || t == ntiles - 1)) {
                 // flush the finished Gram segment: thread = accumulator row (all 128 lanes hold data for M = 128)
-                const int seg = t / FLUSH, gb = seg & 1;
-                mbar_wait(&bar_gfull[gb], (uint32_t)(seg >> 1) & 1u);
+                const int seg = t / FLUSH;
+                WAITC(10, mbar_wait(&bar_gfull[0], (uint32_t)seg & 1u));
                 fence_after_sync();
-                float* dst = gslots + ((size_t)blockIdx.x * nflush + seg) * (128 * GN) + (size_t)(warp * 32 + lane) * GN;
-                const uint32_t gaddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::G_COL0 + gb * 128);
+                float* dst = gslots + ((size_t)blockIdx.x * nflush + seg) * (128 * GN) + (size_t)(quad * 32 + lane) * GN;
+                const uint32_t gaddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)C::G_COL0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < GN; c0 += 16) {
+                for (int c0 = 16 * half; c0 < GN; c0 += 16 * NH1) {       // the quadrant's two warps take alternate 16-column groups
                     float v[16];
                     tmem_ld16(gaddr + (uint32_t)c0, v);
 #pragma unroll
@@ -917,20 +544,27 @@ ec2_tc1_kernel(const float* __restrict__ x12, const int* __restrict__ knn, int N
                 }
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_gempty[gb]);
+                if (lane == 0) mbar_arrive(&bar_gempty[0]);
             }
         }
-        if (owner) {
-            part[(size_t)blockIdx.x * 128 + c] = (double)S1h + (double)S1l;
-            part[(size_t)blockIdx.x * 128 + 64 + c] = (double)S2h + (double)S2l;
+        double s1 = (double)S1h + (double)S1l, s2 = (double)S2h + (double)S2l;
+        s1 += __shfl_xor_sync(SGB_FULL_MASK, s1, 16);
+        s2 += __shfl_xor_sync(SGB_FULL_MASK, s2, 16);
+        if (hp == 0) {
+            part[((size_t)blockIdx.x * NH1 + half) * 128 + c] = s1;
+            part[((size_t)blockIdx.x * NH1 + half) * 128 + 64 + c] = s2;
         }
     }
+#ifdef SGB_ROLE_CLOCKS
+    if (blockIdx.x == 3 && lane == 0) { const long long tot = clock64() - tstart; for (int i = 0; i < 32; ++i) if (wc[i]) printf("warp %2d wait %2d : %6.1f%%  (total %lld clk, %d tiles)\n", warp, i, 100.0 * wc[i] / tot, tot, ntiles); }
+#endif
     fence_before_sync();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+    if (warp == MMA1W) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// mom2 from the reduced Gram accumulator of ec2_tc1_kernel (row of the transposed tile = hidden channel)
+// mom2 [64*64 + 64] (sum h h^T, sum h) from the reduced Gram accumulator R [128][GN]: rows 0..63 = lo*(hi | 1), rows 64..127 = hi*(hi | 1),
+// row of the transposed tile = hidden channel
 __global__ void __launch_bounds__(64)
 mom2_from_gram1_kernel(const double* __restrict__ R, double* __restrict__ mom2) {
     const int j = threadIdx.x;
@@ -952,23 +586,6 @@ bn2_from_sums_kernel(const double* __restrict__ sums, double M, const float* __r
     stats[128 + c] = (float)((double)gamma[c] * invstd);
     stats[192 + c] = beta[c];
     if (var_out) var_out[c] = (float)var;
-}
-
-// mom2 [64*64 + 64] (sum h h^T, sum h) from the reduced Gram accumulator R [128][GN]:
-// rows 0..63 = lo*(hi | 1), rows 64..127 = hi*(hi | 1), both in transposed-tile row order -> un-permute
-__global__ void __launch_bounds__(64)
-mom2_from_gram_kernel(const double* __restrict__ R, double* __restrict__ mom2) {
-    __shared__ int s_row[COUT];                         // hidden channel -> row of the transposed tile
-    const int j = threadIdx.x;
-    s_row[j] = ht_row(j >> 4, j & 15);
-    __syncthreads();
-    const int rj = s_row[j];
-    for (int i = 0; i < COUT; ++i) {
-        const int ri = s_row[i];
-        // hi_j.hi_i + lo_j.hi_i + hi_j.lo_i
-        mom2[j * COUT + i] = R[(64 + rj) * GN + ri] + R[rj * GN + ri] + R[ri * GN + rj];
-    }
-    mom2[COUT * COUT + j] = R[(64 + rj) * GN + 64] + R[rj * GN + 64];
 }
 
 // out[p, c] = lrelu(BN2(z*)), z* = the extreme the forward kernel kept for the sign of the BN scale; argk = its neighbour slot
@@ -1000,21 +617,21 @@ inline int tc_grid(int N, int TE) {
 }
 inline int tc_nflush(int N, int grid) {                 // Gram segments per CTA (the largest CTA range)
     const long long pts = (N + grid - 1) / grid;
-    const int tiles = sgb_div_up(pts * KNN, Cfg<true>::TE);
+    const int tiles = sgb_div_up(pts * KNN, Cfg1<true>::TE);
     return sgb_div_up(tiles > 0 ? tiles : 1, FLUSH);
 }
 }  // namespace sgb_ectc
 
-// workspace: partial sums [148][128] f64, reduced sums [128] f64, reduced Gram [128*GN] f64, zsel [N,64] f32, ksel [N,64] u8,
+// workspace: partial sums [2 * 148][128] f64, reduced sums [128] f64, reduced Gram [128*GN] f64, zsel [N,64] f32, ksel [N,64] u8,
 // Gram slots [148][nflush][128*GN] f32
 size_t sgb_ec2_tc_ws_bytes(int N) {
     using namespace sgb_ectc;
     const int nf = tc_nflush(N, 148) + 1;
-    return (size_t)(148 + 1) * 128 * 8 + (size_t)128 * GN * 8 + (size_t)N * 64 * (4 + 1) +
+    return (size_t)(2 * 148 + 1) * 128 * 8 + (size_t)128 * GN * 8 + (size_t)N * 64 * (4 + 1) +
            (size_t)148 * nf * 128 * GN * 4 + 1024;
 }
 
-// second layer of MLP3 on the tensor cores: stats2/var2 and out/argk as sgb_edgeconv_fwd produces them; mom2 (optional)
+// both layers of MLP3 on the tensor cores: stats2/var2 and out/argk as sgb_edgeconv_fwd produces them; mom2 (optional)
 // = second moments of the hidden activations for the backward pass
 int sgb_ec2_tc_forward(const float* x12 /*[N,12]: 48-byte padded rows*/, const int* knn, int N, const float* W1, const float* stats1, const float* W2,
                        const float* gamma2, const float* beta2, float* out, unsigned char* argk, float* stats2, float* var2,
@@ -1022,54 +639,31 @@ int sgb_ec2_tc_forward(const float* x12 /*[N,12]: 48-byte padded rows*/, const i
     using namespace sgb_ectc;
     unsigned char* w8 = (unsigned char*)ws;
     double* part = (double*)w8;
-    double* sums = part + 148 * 128;
+    double* sums = part + 2 * 148 * 128;
     double* gred = sums + 128;
     float* zsel = (float*)(gred + 128 * GN);
     unsigned char* ksel = (unsigned char*)(zsel + (size_t)N * 64);
     float* gslots = (float*)(((uintptr_t)(ksel + (size_t)N * 64) + 255) & ~(uintptr_t)255);
     const bool gram = mom2 != nullptr;
-    static const bool old_path = getenv("SGB_EC2_OLD") != nullptr;      // bring-up switch: the round-2 kernel (first layer on the CUDA cores)
-    int grid;
-    if (!old_path) {
-        grid = tc_grid(N, gram ? Cfg1<true>::TE : Cfg1<false>::TE);
-        const int nflush = gram ? tc_nflush(N, grid) : 0;
-        if (gram) {
-            const size_t smem = Cfg1<true>::total + 1024;
-            SGB_CUDA(cudaMemsetAsync(gslots, 0, (size_t)grid * nflush * 128 * GN * 4, st));
-            SGB_OPT_IN_SMEM((ec2_tc1_kernel<true, true>));
-            { ec2_tc1_kernel<true, true><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, gslots, nflush); SGB_COUNT_LAUNCH(); }
-            sgb_bn::reduce_partials(gslots, grid * nflush, 128 * GN, gred, st);
-            { mom2_from_gram1_kernel<<<1, 64, 0, st>>>(gred, mom2); SGB_COUNT_LAUNCH(); }
-        } else if (argk) {
-            const size_t smem = Cfg1<false>::total + 1024;
-            SGB_OPT_IN_SMEM((ec2_tc1_kernel<true, false>));
-            { ec2_tc1_kernel<true, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
-        } else {
-            const size_t smem = Cfg1<false>::total + 1024;
-            SGB_OPT_IN_SMEM((ec2_tc1_kernel<false, false>));
-            { ec2_tc1_kernel<false, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
-        }
-    } else {
-    grid = tc_grid(N, gram ? Cfg<true>::TE : Cfg<false>::TE);
+    const int grid = tc_grid(N, gram ? Cfg1<true>::TE : Cfg1<false>::TE);
     const int nflush = gram ? tc_nflush(N, grid) : 0;
     if (gram) {
-        const size_t smem = Cfg<true>::total + 1024;
+        const size_t smem = Cfg1<true>::total + 1024;
         SGB_CUDA(cudaMemsetAsync(gslots, 0, (size_t)grid * nflush * 128 * GN * 4, st));
-        SGB_OPT_IN_SMEM(ec2_tc_kernel<true, true>);
-        { ec2_tc_kernel<true, true><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, gslots, nflush); SGB_COUNT_LAUNCH(); }
+        SGB_OPT_IN_SMEM((ec2_tc1_kernel<true, true>));
+        { ec2_tc1_kernel<true, true><<<grid, THREADS1, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, gslots, nflush); SGB_COUNT_LAUNCH(); }
         sgb_bn::reduce_partials(gslots, grid * nflush, 128 * GN, gred, st);
-        { mom2_from_gram_kernel<<<1, 64, 0, st>>>(gred, mom2); SGB_COUNT_LAUNCH(); }
+        { mom2_from_gram1_kernel<<<1, 64, 0, st>>>(gred, mom2); SGB_COUNT_LAUNCH(); }
     } else if (argk) {
-        const size_t smem = Cfg<false>::total + 1024;
-        SGB_OPT_IN_SMEM(ec2_tc_kernel<true, false>);
-        { ec2_tc_kernel<true, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
+        const size_t smem = Cfg1<false>::total + 1024;
+        SGB_OPT_IN_SMEM((ec2_tc1_kernel<true, false>));
+        { ec2_tc1_kernel<true, false><<<grid, THREADS1, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
     } else {
-        const size_t smem = Cfg<false>::total + 1024;
-        SGB_OPT_IN_SMEM(ec2_tc_kernel<false, false>);
-        { ec2_tc_kernel<false, false><<<grid, THREADS, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
+        const size_t smem = Cfg1<false>::total + 1024;
+        SGB_OPT_IN_SMEM((ec2_tc1_kernel<false, false>));
+        { ec2_tc1_kernel<false, false><<<grid, THREADS1, smem, st>>>(x12, knn, N, W1, stats1, W2, gamma2, zsel, ksel, part, nullptr, 0); SGB_COUNT_LAUNCH(); }
     }
-    }
-    sgb_bn::reduce_partials(part, grid, 128, sums, st);
+    sgb_bn::reduce_partials(part, NH1 * grid, 128, sums, st);
     { bn2_from_sums_kernel<<<1, 64, 0, st>>>(sums, (double)N * KNN, gamma2, beta2, stats2, var2); SGB_COUNT_LAUNCH(); }
     const long long total = (long long)N * 64;
     { ec2_apply_kernel<<<sgb_div_up(total / 4, 256), 256, 0, st>>>(zsel, ksel, stats2, total, out, argk); SGB_COUNT_LAUNCH(); }

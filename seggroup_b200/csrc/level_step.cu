@@ -69,8 +69,12 @@ extern "C" int sgb_level_step_scenes(int mode, const int* adj_old, int A_old, co
                                      cl_ins, cl_sem, cl_rootpt, counts_dev, scene_seg_off, n_scenes, batch ? scene_cl_off_new : nullptr,
                                      ws, ws_bytes, stream))) return rc;
     // sgb_level_build leaves counts_dev[0] = clusters and counts_dev[2] = clusters without a label
-    SGB_CUDA(cudaMemcpyAsync(counts_host, counts_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (batch) SGB_CUDA(cudaMemcpyAsync(counts_host + 4, scene_cl_off_new, (size_t)(n_scenes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (batch && scene_cl_off_new == counts_dev + 4) {         // the caller laid the scene offsets out behind the counters: one copy
+        SGB_CUDA(cudaMemcpyAsync(counts_host, counts_dev, (size_t)(4 + n_scenes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    } else {
+        SGB_CUDA(cudaMemcpyAsync(counts_host, counts_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (batch) SGB_CUDA(cudaMemcpyAsync(counts_host + 4, scene_cl_off_new, (size_t)(n_scenes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     SGB_CUDA(cudaStreamSynchronize(st));
     const int S_new = counts_host[0];
     if (S_new <= 0) return SGB_ERR_INVALID;

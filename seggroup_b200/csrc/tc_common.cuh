@@ -62,6 +62,20 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
 }
 
+// A operand read from tensor memory (rows on the lanes in the layout of an accumulator of the same M, K along the columns: 8 columns per
+// kind::tf32 instruction), B from shared memory.  Constant A operands (weight tiles) are parked in TMEM once per CTA and stop costing
+// shared-memory bandwidth on every instruction.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
+}
+
 // One lane of a converged warp (cute::elect_one_sync).  Guarding the MMA issue with THIS predicate instead of `lane == 0` lets the
 // compiler treat the branch as warp-uniform: with `lane == 0` every tcgen05.mma / commit was wrapped in its own ELECT + BRA.U.ANY loop
 // (4 extra dependent instructions per MMA in SASS), which made the single issuing thread co-critical (ncu: 80 % busy).
@@ -154,6 +168,22 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
 __device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+// M = 64 accumulators keep their 64 rows on lanes 0..15 of each TMEM quadrant.  The .16x32bx2 shape reads those 16 lanes twice: threads
+// 0..15 get columns [col, col + n), threads 16..31 the SAME lanes at columns [col + SPLIT, col + SPLIT + n) — so the upper half-warp works
+// on a second group of columns instead of idling.
+template <int SPLIT>
+__device__ __forceinline__ void tmem_ld16_halves_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x32bx2.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16], %17;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr), "n"(SPLIT) : "memory");
+}
+template <int SPLIT>
+__device__ __forceinline__ void tmem_ld4_halves_issue(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x4.b32 {%0, %1, %2, %3}, [%4], %5;\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr), "n"(SPLIT) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // compiler-level dependency of 20 loaded registers on the preceding wait (emits no instruction)

@@ -265,15 +265,16 @@ def level_step(mode, uf, seg_off, seg_members, seg_of_pos, status, old=None, dis
         edges = old.adj
     E = edges.shape[0]
     B = split.n if split is not None and split.n > 1 else 1
+    # counts (4 ints) directly followed by the scenes' new cluster offsets: the library reads both back with ONE copy
     sizes = [S1, S1, S1 + 1, S1, S1 + 1, N, S1, S1, S1, max(S_old, 1), S1 + 1, max(S_old, 1), 2 * max(E, 1), S1 + 1,
-             2 * max(E, 1), 2 * max(E, 1), 4 + B + 1, B + 1]
+             2 * max(E, 1), 2 * max(E, 1), 4, B + 1]
     buf = torch.empty(sum(sizes), dtype=I32, device=dev)
     parts, o = [], 0
     for n in sizes:
         parts.append(buf[o:o + n]); o += n
     (roots, seg2cl, cl_seg_off, cl_seg_list, cl_pt_off, order, cl_ins, cl_sem, cl_rootpt, o2n, ch_off, ch_list, adj_new, csr_off,
      csr_nbr, csr_eid, counts, scl) = parts
-    host = np.zeros(4 + B + 1, np.int32)
+    host = _pinned_counts(4 + B + 1)           # page-locked: the two read-backs per level are plain DMA + one stream sync each
     ws = _ws(_lib.call("sgb_level_step_ws_bytes", S1, S_old), dev)
     oc = old.csr if (old is not None and mode == 1) else (None, None, None)
     common = (int(mode), old.adj if old is not None else None, old.adj.shape[0] if old is not None else 0,
@@ -287,9 +288,10 @@ def level_step(mode, uf, seg_off, seg_members, seg_of_pos, status, old=None, dis
         max_cl_old = max(b - a for a, b in zip(old.scene_cl_off[:-1], old.scene_cl_off[1:])) if old is not None else 0
         _lib.call("sgb_level_step_scenes", *common, split.d_seg_off, old.d_scene_cl_off if old is not None else None, scl, B,
                   split.max_segs, max_cl_old, ws, ws.numel(), _stream())
-    S, A = int(host[0]), int(host[1])
+    hv = host.tolist()
+    S, A = hv[0], hv[1]
     L = Level()
-    L.scene_cl_off = [int(v) for v in host[4:4 + B + 1]] if B > 1 else [0, S]
+    L.scene_cl_off = hv[4:4 + B + 1] if B > 1 else [0, S]
     L.d_scene_cl_off = scl if B > 1 else None
     L.S, L.counts = S, counts
     L.roots, L.cl_seg_off, L.cl_pt_off = roots[:S], cl_seg_off[:S + 1], cl_pt_off[:S + 1]
@@ -298,8 +300,21 @@ def level_step(mode, uf, seg_off, seg_members, seg_of_pos, status, old=None, dis
     L.adj = adj_new[:2 * A].view(A, 2)
     L.csr = (csr_off[:S + 1], csr_nbr[:max(2 * A, 1)], csr_eid[:max(2 * A, 1)])
     L.o2n, L.ch_off, L.ch_list = (o2n[:S_old], ch_off[:S + 1], ch_list[:S_old]) if old is not None else (None, None, None)
-    L.n_unlabeled, L.status = int(host[2]), int(host[3])
+    L.n_unlabeled, L.status = hv[2], hv[3]
     return L
+
+
+_pinned = {}
+
+
+def _pinned_counts(n):
+    """Per-thread page-locked int32 scratch for the level counters (level_step consumes it before it returns)."""
+    import threading
+    key = (threading.get_ident(), n)
+    t = _pinned.get(key)
+    if t is None:
+        t = _pinned[key] = torch.zeros(n, dtype=I32).pin_memory()
+    return t
 
 
 def level_build(uf, seg_off, seg_members, seg_of_pos):

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Role-ablation builds of the two tcgen05 EdgeConv kernels (timing experiments only: every variant but 0 computes garbage).
+# Role-ablation builds of the tcgen05 EdgeConv backward kernel (timing experiments only: every variant but 0 computes garbage; the
+# forward kernel of round 2, which had the same switches, was replaced in round 3 — its timings are in profiles/r02z_ablate_ec2.txt).
 #   bash tools/ablate.sh build "1 2 4 8 16"   (here: cross-compile lib/abl/libsgb_abl_<n>.so)
 #   bash tools/ablate.sh run   "1 2 4 8 16" <tag>  (on the GPU box)
 set -e
@@ -8,9 +9,9 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 case $1 in
 build) mkdir -p $L/abl
   for n in $2; do
-    for f in edgeconv_tc edgeconv_bwd_tc; do nvcc $FLAGS -DSGB_ABL=$n -c $C/$f.cu -o $L/abl/${f}_$n.o & done; wait
-    objs=$(ls $L/*.o | grep -v -e /edgeconv_tc.o -e /edgeconv_bwd_tc.o)
-    nvcc -shared -o $L/abl/libsgb_abl_$n.so $objs $L/abl/edgeconv_tc_$n.o $L/abl/edgeconv_bwd_tc_$n.o -gencode arch=compute_100a,code=sm_100a -lcudart
+    for f in edgeconv_bwd_tc; do nvcc $FLAGS -DSGB_ABL=$n -c $C/$f.cu -o $L/abl/${f}_$n.o & done; wait
+    objs=$(ls $L/*.o | grep -v -e /edgeconv_bwd_tc.o)
+    nvcc -shared -o $L/abl/libsgb_abl_$n.so $objs $L/abl/edgeconv_bwd_tc_$n.o -gencode arch=compute_100a,code=sm_100a -lcudart
     rm $L/abl/*_$n.o
   done ;;
 run) for n in 0 $2; do
