@@ -28,6 +28,12 @@
 #define SGB_ABL 0      // role-ablation timing experiments (tools/ablate.sh): results are WRONG for any value but 0
 #endif
 
+#ifdef SGB_ROLE_CLOCKS
+#include <cstdio>
+#define WAITC(i, x) do { const long long t0_ = clock64(); x; wclk[i] += clock64() - t0_; } while (0)
+#else
+#define WAITC(i, x) x
+#endif
 namespace sgb_ecbt {
 using namespace sgb_tc;
 using sgb_ec::CIN;
@@ -42,7 +48,7 @@ constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;     // 416
 constexpr int PROD_THREADS = PROD_WARPS * 32;                  // 256
 constexpr int TE = 80;                                         // edges per tile
 constexpr int PTS = TE / KNN;                                  // 4 points per tile
-constexpr int BLOCKS = TE / 8;                                 // 8-edge blocks per tile; a group of 4 producer warps takes every 2nd one
+
 constexpr int TN = 24;                                         // columns of the T accumulator: 18 + A0 + 5 zero
 constexpr int BM_BYTES = COUT * COUT * 4;
 constexpr int TILE_BYTES = TE * COUT * 4;                      // one K-major H tile (hi or lo); also one dv1^T tile [64 rows][80 edges]
@@ -58,23 +64,34 @@ constexpr int NACC = CIN + 2;
 constexpr int ACCN = 20;                                       // fp64 accumulator columns kept per channel (18 + A0 + pad)
 constexpr int FLUSH = 32;                                      // tiles per T segment (fp32 in TMEM), then fp64
 constexpr int TMEM_COLS = 512;
-constexpr int Z_COL = 256;                                     // z accumulators at columns 0 and 256
-constexpr int T_COL0 = 128, T_COLS = 64;                       // T accumulators at columns 128 and 192
+constexpr int Z_COL = 80;                                      // TMEM: z accumulators at columns 0 and 80
+constexpr int T_COL0 = 160, T_COLS = 32;                       //       T accumulators at 160 and 192 (24 columns used)
+constexpr int D1_COL = 224;                                    //       first-layer accumulators at 224 and 288 (64 columns each)
+constexpr int BM_COL = 352;                                    //       Bm hi | lo as the A operand of the z MMAs (2 x 64 columns)
+constexpr int KE = 24;                                         // K of the first layer: 9 differences + 9 centre + 1 + 5 zero
+constexpr int E_BYTES = TE * 20 * 4;                           // one K-major E tile (hi or lo): K chunks 0..4; K = 20..23 is one shared chunk of zeros
+constexpr int EZ_BYTES = 128 * 16;
+constexpr int W1_BYTES = COUT * KE * 4;
 
-constexpr int off_bm_hi = 0;
+constexpr int off_w1_hi = 0;                                   // W1s = (scale1 W1 | folded BN1 bias | 0), hi / lo
+constexpr int off_w1_lo = off_w1_hi + W1_BYTES;
+constexpr int off_h0 = off_w1_lo + W1_BYTES;                   // 2 H stages
+constexpr int off_bm_hi = off_h0;                              // setup only (aliases the H stages): Bm hi / lo and the identity that moves them to TMEM
 constexpr int off_bm_lo = off_bm_hi + BM_BYTES;
-constexpr int off_h0 = off_bm_lo + BM_BYTES;                   // 2 H stages
+constexpr int off_ident = off_bm_lo + BM_BYTES;
 constexpr int off_e0 = off_h0 + 2 * HSTAGE_BYTES;              // 3 EC / mask stages
 constexpr int off_dv = off_e0 + ERING * ESTAGE_BYTES;          // [half][hi, lo]
-constexpr int off_raw0 = off_dv + 4 * DVH_BYTES;
-constexpr int off_wc = off_raw0 + RING * RAW_BYTES;            // centre-half first-layer weights [16 chunks][9] float4 (BN1 folded in)
-constexpr int off_ctr = off_wc + 16 * 9 * 16;                  // per producer warp: centre rows [PTS][4 parts] float4 of the current tile
-constexpr int off_ebar = off_ctr + PROD_WARPS * PTS * 4 * 16;
-constexpr int off_bars = off_ebar + 32 * 4;                    // 19 mbarriers
-constexpr int off_tmem_slot = off_bars + 20 * 8;
+constexpr int off_et0 = off_dv + 4 * DVH_BYTES;                // E tiles: [buffer 0: hi, lo][buffer 1: hi, lo][zero chunk]
+constexpr int off_ezero = off_et0 + 4 * E_BYTES;
+constexpr int off_raw0 = off_ezero + EZ_BYTES;                 // (the M = 128 read of K chunk 4 runs 48 rows into whatever follows the tile)
+constexpr int off_ebar = off_raw0 + RING * RAW_BYTES;
+constexpr int off_bars = off_ebar + 32 * 4;                    // 27 mbarriers
+constexpr int off_tmem_slot = off_bars + 28 * 8;
 constexpr int SMEM_TOTAL = off_tmem_slot + 16;
 static_assert(HSTAGE_BYTES % 128 == 0 && ESTAGE_BYTES % 128 == 0 && DVH_BYTES % 128 == 0, "stage alignment");
 static_assert(SMEM_TOTAL + 128 <= 227 * 1024, "shared memory budget");
+static_assert(3 * BM_BYTES <= 2 * HSTAGE_BYTES, "setup tiles fit into the H stages");
+static_assert(off_et0 % 16 == 0 && E_BYTES % 16 == 0 && off_bars % 8 == 0, "alignment");
 
 __device__ __forceinline__ bool mbar_test(uint64_t* mbar, uint32_t parity) {       // non-blocking
     uint32_t ok;
@@ -101,9 +118,16 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
     uint64_t* bar_gfull = bar_full + 12;                                     // [2] MMA (commit) -> epilogue: T segment complete
     uint64_t* bar_gempty = bar_full + 14;                                    // [2] epilogue -> MMA: T accumulator flushed
     uint64_t* bar_eempty = bar_full + 16;                                    // [3] MMA (commit after the T MMAs) -> producers: EC / mask stage free
+    uint64_t* bar_xfull = bar_full + 19;                                     // [2] producers -> MMA: E tile written
+    uint64_t* bar_xempty = bar_full + 21;                                    // [2] MMA (commit after the first-layer MMAs) -> producers
+    uint64_t* bar_d1full = bar_full + 23;                                    // [2] MMA (same commit) -> producers: D1 complete
+    uint64_t* bar_d1empty = bar_full + 25;                                   // [2] producers -> MMA: D1 read into registers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + off_tmem_slot);
     float* s_ebar = reinterpret_cast<float*>(sm + off_ebar);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SGB_ROLE_CLOCKS
+    long long wclk[32]; for (int i = 0; i < 32; ++i) wclk[i] = 0; const long long tstart = clock64();
+#endif
 
     const int per = N / gridDim.x, rem = N % gridDim.x;
     const int p_begin = blockIdx.x * per + min((int)blockIdx.x, rem);
@@ -128,13 +152,22 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             *reinterpret_cast<float*>(ec + EC_BYTES + kmajor_off(r, e, TN)) = 0.f;
         }
     }
-    for (int i = tid; i < 16 * 9; i += THREADS) {                             // centre half of the first layer: columns 9..17 of W1, BN1 scale folded in
-        const int ch = i / 9, q = i % 9;
-        float w[4];
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) w[s4] = __ldg(W1 + (4 * ch + s4) * CIN + 9 + q) * stats1[128 + 4 * ch + s4];
-        *reinterpret_cast<float4*>(sm + off_wc + i * 16) = make_float4(w[0], w[1], w[2], w[3]);
+    for (int i = tid; i < COUT * COUT; i += THREADS) {                        // identity: Bm reaches TMEM as Bm * I (edgeconv_tc.cu)
+        const int n = i / COUT, j = i % COUT;
+        *reinterpret_cast<float*>(sm + off_ident + tile_off(n, j, COUT)) = (n == j) ? 1.f : 0.f;
     }
+    for (int i = tid; i < COUT * KE; i += THREADS) {                          // W1s [c][k]: BN1 scale folded in, column 18 = folded bias
+        const int c = i / KE, k = i % KE;
+        const float sc = stats1[128 + c];
+        float w = 0.f;
+        if (k < CIN) w = __ldg(W1 + c * CIN + k) * sc;
+        else if (k == CIN) w = fmaf(-sc, stats1[c], stats1[192 + c]);
+        const float hi = tf32_hi(w);
+        const uint32_t off = tile_off(c, k, COUT);
+        *reinterpret_cast<float*>(sm + off_w1_hi + off) = hi;
+        *reinterpret_cast<float*>(sm + off_w1_lo + off) = tf32_hi(w - hi);
+    }
+    for (int i = tid; i < 128; i += THREADS) *reinterpret_cast<float4*>(sm + off_ezero + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < CIN) s_ebar[tid] = (float)(mom1[tid] / M + (double)e0[tid]);
     if (tid == 0) {
         mbar_init(&bar_full[0], PROD_WARPS); mbar_init(&bar_full[1], PROD_WARPS);
@@ -146,6 +179,10 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         mbar_init(&bar_eempty[0], 1); mbar_init(&bar_eempty[1], 1); mbar_init(&bar_eempty[2], 1);
         mbar_init(&bar_gfull[0], 1); mbar_init(&bar_gfull[1], 1);
         mbar_init(&bar_gempty[0], EPI_WARPS); mbar_init(&bar_gempty[1], EPI_WARPS);
+        for (int b2 = 0; b2 < 2; ++b2) {
+            mbar_init(&bar_xfull[b2], PROD_WARPS); mbar_init(&bar_xempty[b2], 1);
+            mbar_init(&bar_d1full[b2], 1); mbar_init(&bar_d1empty[b2], PROD_WARPS);
+        }
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -156,38 +193,17 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
     const uint32_t tmem = *tmem_slot;
 
     if (warp > MMA_WARP) {
-        // ================= producers (as the forward kernel) + sign bits and transposed centred edge vectors
+        // ================= producers, as ec2_tc1_kernel (edgeconv_tc.cu): the first layer runs on the tensor cores,
+        //     D1[128 edge rows, 64 channels] = E[128, 24] * W1s[64, 24]^T,   E = (x_j - x_i, x_i, valid, 0...),
+        // and a producer thread owns one edge ROW of D1: sign bits, LeakyReLU, hi / lo split, 16-byte stores into the K-major H tile.
+        // Per tile:  [gather ring] -> E(t) (one thread per edge) and EC(t) (one thread per (row, 4 edges)) -> H(t - 1), mask(t - 1).
+        // Round 2 evaluated the first layer on the CUDA cores, 16 threads per edge: the producers were busy 96 % of the kernel
+        // (cycle counters around every wait, -DSGB_ROLE_CLOCKS) with everybody else waiting for them.
         const int pw = warp - (MMA_WARP + 1);           // 0..7
-        const int ptid = pw * 32 + lane;                // gather role: edge row `ptid` (< TE), point row `ptid` (< PTS)
-        const int grp = pw >> 2;
-        const int c4 = (lane >> 3) * 4 + (pw & 3);      // my chunk of the hidden vector: channels 4 c4 .. 4 c4 + 3
-        const int eb = lane & 7;
-        const int part = lane >> 3;
-        // as the forward kernel: only the 9 difference columns of the first layer are per-edge work (weights in registers); the centre
-        // half  bias + Wc x_i  is evaluated once per point and tile
-        constexpr int CD = 9;
-        float2 w01[CD], w23[CD];
-        float4 bias;
-        {
-            float sc[4], bb[4];
-#pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                const int c = 4 * c4 + s4;
-                sc[s4] = stats1[128 + c];
-                bb[s4] = fmaf(-stats1[128 + c], stats1[c], stats1[192 + c]);
-            }
-#pragma unroll
-            for (int q = 0; q < CD; ++q) {
-                w01[q] = make_float2(__ldg(W1 + (4 * c4 + 0) * CIN + q) * sc[0], __ldg(W1 + (4 * c4 + 1) * CIN + q) * sc[1]);
-                w23[q] = make_float2(__ldg(W1 + (4 * c4 + 2) * CIN + q) * sc[2], __ldg(W1 + (4 * c4 + 3) * CIN + q) * sc[3]);
-            }
-            bias = make_float4(bb[0], bb[1], bb[2], bb[3]);
-        }
-        const float4* wc = reinterpret_cast<const float4*>(sm + off_wc) + c4 * 9;
-        unsigned char* ctr = sm + off_ctr + pw * (PTS * 4 * 16);
-        // my EC rows: row c4 = (x_j[c4] - x_i[c4]) - ebar[c4] for c4 < 9, x_i[c4 - 9] - ebar[c4] otherwise; rows 16 + c4 for c4 < 3
-        const uint32_t ec_qj = (uint32_t)(c4 < 9 ? c4 : 0), ec_qi = (uint32_t)(c4 < 9 ? c4 : c4 - 9);
-        const float ebar0 = s_ebar[c4], ebar1 = c4 < 2 ? s_ebar[16 + c4] : 0.f;
+        const int ptid = pw * 32 + lane;                // gather / E role: edge row `ptid` (< TE), point row `ptid` (< PTS)
+        const int quad = warp & 3;                      // the TMEM lanes this warp may read: 32 quad .. 32 quad + 31
+        const int chh = pw >> 2;                        // H role: channels 32 chh .. 32 chh + 31 of edge row 32 quad + lane
+        const int hrow = quad * 32 + lane;
         const bool gatherer = ptid < TE, pgatherer = ptid < PTS;
         auto edge_in_range = [&](int t) -> bool {
             const long long g = g_begin + (long long)t * TE + ptid;
@@ -226,113 +242,128 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             if (!edge_in_range(t)) return -1;
             return *reinterpret_cast<const volatile int*>(sm + off_raw0 + (t % RING) * RAW_BYTES + TE * 48 + PTS * 48 + TE * 4 + ptid * 4);
         };
+        auto split4 = [](const float4 y, float4& hi, float4& lo) {
+            hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
+            lo = make_float4(tf32_hi(y.x - hi.x), tf32_hi(y.y - hi.y), tf32_hi(y.z - hi.z), tf32_hi(y.w - hi.w));
+        };
+        const uint32_t d1addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL + 32 * chh);
 #pragma unroll 1
         for (int tt = 0; tt < RING - 1; ++tt) issue_rows(tt, edge_in_range(tt) ? __ldg(knn + (g_begin + (long long)tt * TE + ptid)) : -1);
-        for (int t = 0; t < ntiles; ++t) {
-            const int st = t & 1;
-            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory");
-            asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory");
-            issue_rows(t + RING - 1, staged_index(t + RING - 1));
-            const unsigned char* raw = sm + off_raw0 + (t % RING) * RAW_BYTES;
-            if (eb < PTS) {                              // lane (part, eb): centre row of point eb of the tile for my chunk c4
-                const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + eb * 48);
-                const float4 a0 = ri[0], a1 = ri[1], a2 = ri[2];
-                const float xi[CD] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
-                float2 c01 = make_float2(bias.x, bias.y), c23 = make_float2(bias.z, bias.w);
-#pragma unroll
-                for (int q = 0; q < CD; ++q) {
-                    const float4 w = wc[q];
-                    const float2 xx = make_float2(xi[q], xi[q]);
-                    ffma2(c01, make_float2(w.x, w.y), xx);
-                    ffma2(c23, make_float2(w.z, w.w), xx);
-                }
-                *reinterpret_cast<float4*>(ctr + (eb * 4 + part) * 16) = make_float4(c01.x, c01.y, c23.x, c23.y);
-            }
-            __syncwarp();
-            mbar_wait(&bar_hempty[st], ph ^ 1u);
-            mbar_wait(&bar_eempty[t % ERING], ((uint32_t)(t / ERING) & 1u) ^ 1u);
-            unsigned char* dst_hi = sm + off_h0 + st * HSTAGE_BYTES;
-            unsigned char* dst_lo = dst_hi + TILE_BYTES;
-            unsigned char* dst_ech = sm + off_e0 + (t % ERING) * ESTAGE_BYTES;
-            unsigned char* dst_ecl = dst_ech + EC_BYTES;
-            unsigned char* dst_mt = dst_ecl + EC_BYTES;
-            struct Blk { float4 b0, b1, b2, a0, a1, a2, cc; float ej, ei; };      // ej / ei: the entries of x_j / x_i my EC row is made of
-            const uint32_t raw_s = smem_u32(raw), ctr_s = smem_u32(ctr);
-            auto load_blk = [&](int blk, Blk& B) {
-                const int er = blk * 8 + eb;
-                const int pt = (er * 205) >> 12;        // er / KNN, exact for er < 1039
-                const uint32_t rj = raw_s + (uint32_t)(er * 48);
-                const uint32_t ri = raw_s + (uint32_t)(TE * 48 + pt * 48);
-                B.b0 = lds128_ordered(rj); B.b1 = lds128_ordered(rj + 16); B.b2 = lds128_ordered(rj + 32);
-                B.a0 = lds128_ordered(ri); B.a1 = lds128_ordered(ri + 16); B.a2 = lds128_ordered(ri + 32);
-                B.cc = lds128_ordered(ctr_s + (uint32_t)((pt * 4 + part) * 16));
-                B.ej = lds32_ordered(rj + ec_qj * 4);
-                B.ei = lds32_ordered(ri + ec_qi * 4);
-            };
-            auto finish_blk = [&](int blk, const Blk& B) {
-                const int er = blk * 8 + eb;
-                const float ev[CD] = {B.b0.x - B.a0.x, B.b0.y - B.a0.y, B.b0.z - B.a0.z, B.b0.w - B.a0.w, B.b1.x - B.a1.x, B.b1.y - B.a1.y,
-                                      B.b1.z - B.a1.z, B.b1.w - B.a1.w, B.b2.x - B.a2.x};
-                const bool valid = B.b2.w != 0.f;        // pad lane 11: 1 in a gathered row, 0 in a zero-filled one
-                float2 y01 = make_float2(B.cc.x, B.cc.y), y23 = make_float2(B.cc.z, B.cc.w);
-#pragma unroll
-                for (int q = 0; q < ((SGB_ABL & 1) ? 1 : CD); ++q) {
-                    const float2 ee = make_float2(ev[q], ev[q]);
-                    ffma2(y01, w01[q], ee);
-                    ffma2(y23, w23[q], ee);
-                }
-                uint32_t bits = 0;
-                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    bits = (y01.x > 0.f ? 1u : 0u) | (y01.y > 0.f ? 2u : 0u) | (y23.x > 0.f ? 4u : 0u) | (y23.y > 0.f ? 8u : 0u);
-                    y = make_float4(lrelu(y01.x), lrelu(y01.y), lrelu(y23.x), lrelu(y23.y));
-                }
-                const float4 hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
-                const float4 lo = make_float4(tf32_hi(y.x - hi.x), tf32_hi(y.y - hi.y), tf32_hi(y.z - hi.z), tf32_hi(y.w - hi.w));
-                const uint32_t off = (uint32_t)c4 * (TE * 16) + (uint32_t)(er >> 3) * 128 + (uint32_t)(er & 7) * 16;
-                *reinterpret_cast<float4*>(dst_hi + off) = hi;
-                *reinterpret_cast<float4*>(dst_lo + off) = lo;
-                dst_mt[er * 16 + c4] = (unsigned char)bits;     // sign bits of hidden channels 4 c4 .. 4 c4 + 3
-                // EC column of this edge (centred edge vector, then 1 for a real edge -> A0), spread over the 16 threads of the edge:
-                // thread c4 writes row c4, threads 0..2 also rows 16..18.  The two entries row c4 is made of were fetched with the
-                // block's rows (load_blk), rows 16 / 17 are x_i[7] / x_i[8] (already in registers), the centres e-bar are per-thread
-                // constants: no shared-memory load sits between the arithmetic and these stores any more (ncu source view: 11 % of
-                // the producers' samples waited on them).
-                if (!(SGB_ABL & 16)) {
-                    const float vm = valid ? 1.f : 0.f;
-                    {
-                        const float v = ((c4 < 9 ? B.ej - B.ei : B.ei) - ebar0) * vm;
-                        const float vh = tf32_hi(v);
-                        const uint32_t o = kmajor_off(c4, er, TN);
-                        *reinterpret_cast<float*>(dst_ech + o) = vh;
-                        *reinterpret_cast<float*>(dst_ecl + o) = tf32_hi(v - vh);
-                    }
-                    if (c4 < 3) {
-                        const float x = c4 == 0 ? B.a1.w : B.a2.x;                     // x_i[7], x_i[8]
-                        const float v = (c4 == 2 ? 1.f : x - ebar1) * vm;
-                        const float vh = tf32_hi(v);
-                        const uint32_t o = kmajor_off(16 + c4, er, TN);
-                        *reinterpret_cast<float*>(dst_ech + o) = vh;
-                        *reinterpret_cast<float*>(dst_ecl + o) = tf32_hi(v - vh);
-                    }
-                }
-            };
-            Blk A, Bq;
-            int blk = grp;
-            load_blk(blk, A);
 #pragma unroll 1
-            for (; blk + 2 < BLOCKS; blk += 4) {
-                load_blk(blk + 2, Bq);
-                finish_blk(blk, A);
-                if (blk + 4 < BLOCKS) load_blk(blk + 4, A);
-                finish_blk(blk + 2, Bq);
+        for (int t = 0; t <= ntiles; ++t) {
+            if (t < ntiles) {
+                WAITC(30, asm volatile("cp.async.wait_group %0;" :: "n"(RING - 2) : "memory"));
+                WAITC(31, asm volatile("bar.sync 1, %0;" :: "n"(PROD_THREADS) : "memory"));
+                issue_rows(t + RING - 1, staged_index(t + RING - 1));
+                const unsigned char* raw = sm + off_raw0 + (t % RING) * RAW_BYTES;
+                // ---- E(t): the edge vectors of tile t as the A operand of the first layer
+                const int xb = t & 1;
+                WAITC(0, mbar_wait(&bar_xempty[xb], (((uint32_t)t >> 1) & 1u) ^ 1u));
+                if (gatherer) {
+                    unsigned char* e_hi = sm + off_et0 + xb * (2 * E_BYTES);
+                    unsigned char* e_lo = e_hi + E_BYTES;
+                    const int pt = (ptid * 205) >> 12;      // ptid / KNN
+                    const float4* rj = reinterpret_cast<const float4*>(raw + ptid * 48);
+                    const float4* ri = reinterpret_cast<const float4*>(raw + TE * 48 + pt * 48);
+                    const float4 b0 = rj[0], b1 = rj[1], b2 = rj[2], a0 = ri[0], a1 = ri[1], a2 = ri[2];
+                    const float one = b2.w != 0.f ? 1.f : 0.f;      // 1 for a gathered row, 0 for a zero-filled one (edge outside the CTA's range)
+                    float4 ch[5];
+                    ch[0] = make_float4(b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w);
+                    ch[1] = make_float4(b1.x - a1.x, b1.y - a1.y, b1.z - a1.z, b1.w - a1.w);
+                    ch[2] = make_float4(b2.x - a2.x, a0.x, a0.y, a0.z);
+                    ch[3] = make_float4(a0.w, a1.x, a1.y, a1.z);
+                    ch[4] = make_float4(a1.w, a2.x, 1.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const float4 y = make_float4(ch[q].x * one, ch[q].y * one, ch[q].z * one, ch[q].w * one);
+                        float4 hi, lo;
+                        split4(y, hi, lo);
+                        *reinterpret_cast<float4*>(e_hi + q * (TE * 16) + ptid * 16) = hi;
+                        *reinterpret_cast<float4*>(e_lo + q * (TE * 16) + ptid * 16) = lo;
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_xfull[xb]);
             }
-            if (blk < BLOCKS) finish_blk(blk, A);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[st]);
+            if (t >= 1) {
+                // ---- H(u), mask(u): hidden activations and their sign bits of tile u = t - 1 from the first-layer accumulator
+                const int u = t - 1, su = u & 1;
+                WAITC(2, mbar_wait(&bar_d1full[su], ((uint32_t)u >> 1) & 1u));
+                fence_after_sync();
+                uint32_t va[16], vb[16];
+                tmem_ld16_issue(d1addr + (uint32_t)(su * 64), va);
+                tmem_ld16_issue(d1addr + (uint32_t)(su * 64 + 16), vb);
+                tmem_ld_wait();
+                tmem_ld_pin16(va);
+                tmem_ld_pin16(vb);
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_d1empty[su]);
+                WAITC(3, mbar_wait(&bar_hempty[su], (((uint32_t)(u >> 1)) & 1u) ^ 1u));
+                unsigned char* dst_hi = sm + off_h0 + su * HSTAGE_BYTES;
+                unsigned char* dst_lo = dst_hi + TILE_BYTES;
+                unsigned char* dst_mt = sm + off_e0 + (u % ERING) * ESTAGE_BYTES + 2 * EC_BYTES;      // this stage was acquired with EC(u)
+                const bool rowv = hrow < TE;
+                uint32_t mlo = 0, mhi = 0;              // sign bits: one byte per 4-channel chunk (a zero row — edge out of range — gives 0 and h = 0)
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    float y[4];
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        const int i = 4 * i4 + s4;
+                        const float pre = __uint_as_float(i < 16 ? va[i] : vb[i - 16]);
+                        bits |= pre > 0.f ? (1u << s4) : 0u;
+                        y[s4] = lrelu(pre);
+                    }
+                    if (i4 < 4) mlo |= bits << (8 * i4); else mhi |= bits << (8 * (i4 - 4));
+                    float4 hi, lo;
+                    split4(make_float4(y[0], y[1], y[2], y[3]), hi, lo);
+                    if (rowv) {
+                        const uint32_t off = (uint32_t)(8 * chh + i4) * (TE * 16) + (uint32_t)hrow * 16;
+                        *reinterpret_cast<float4*>(dst_hi + off) = hi;
+                        *reinterpret_cast<float4*>(dst_lo + off) = lo;
+                    }
+                }
+                if (rowv) *reinterpret_cast<uint2*>(dst_mt + hrow * 16 + 8 * chh) = make_uint2(mlo, mhi);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[su]);
+            }
+            if (t < ntiles) {
+                // ---- EC(t), LAST (its stage is freed by the T MMAs of tile t - 3: waiting here does not hold back H(t - 1)): the centred edge vectors with the edges along K, [24 rows][80 edges]: one work item = (row r < 19, 4 consecutive
+                // edges — one point, one 16-byte chunk), consecutive lanes = consecutive rows (conflict-free loads and stores)
+                const unsigned char* raw = sm + off_raw0 + (t % RING) * RAW_BYTES;
+                WAITC(1, mbar_wait(&bar_eempty[t % ERING], ((uint32_t)(t / ERING) & 1u) ^ 1u));
+                {
+                    unsigned char* dst_ech = sm + off_e0 + (t % ERING) * ESTAGE_BYTES;
+                    unsigned char* dst_ecl = dst_ech + EC_BYTES;
+#pragma unroll 1
+                    for (int it = ptid; it < 19 * (TE / 4); it += PROD_THREADS) {
+                        const int g = it / 19, r = it - g * 19;
+                        const int e0i = 4 * g, pt = g / (KNN / 4);
+                        const float* rj = reinterpret_cast<const float*>(raw + e0i * 48);
+                        const float* ri = reinterpret_cast<const float*>(raw + TE * 48 + pt * 48);
+                        const float eb_ = r < CIN ? s_ebar[r] : 0.f;
+                        const float xi = r < CIN ? ri[r < 9 ? r : r - 9] : 0.f;
+                        float v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float vm = rj[q * 12 + 11] != 0.f ? 1.f : 0.f;
+                            const float ev = r < 9 ? rj[q * 12 + r] - xi : (r < CIN ? xi : 1.f);
+                            v[q] = (ev - eb_) * vm;
+                        }
+                        float4 hi, lo;
+                        split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+                        const uint32_t o = (uint32_t)g * (TN * 16) + (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16;
+                        *reinterpret_cast<float4*>(dst_ech + o) = hi;
+                        *reinterpret_cast<float4*>(dst_ecl + o) = lo;
+                    }
+                }
+            }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer (one thread): an event loop over two independent streams of work — the z MMAs of the next
         // tile whose H stage is full, and the T MMAs of the next half tile whose dv1 operand the epilogue has finished — so that
@@ -347,7 +378,32 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             // (shared-memory addresses < 256 KB: the 14-bit field cannot carry).  The issuing thread is ONE instruction stream; at 40 tensor
             // cycles per instruction (N = 80) the descriptor arithmetic between two tcgen05.mma was the pacing item of the kernel.
             auto adv = [](uint64_t dsc, uint32_t bytes) -> uint64_t { return dsc + (uint64_t)(bytes >> 4); };
-            const uint64_t dBh = make_desc(a_hi, COUT * 16, 128), dBl = make_desc(a_lo, COUT * 16, 128);
+            // Bm (hi, lo) into TMEM in the layout of an M = 64 accumulator: D = Bm * I (exact).  The tensor pipe runs in issue order, so every
+            // later MMA — and the first write into H stage 0, which waits for the first-layer MMA of tile 0 — comes after these.
+            if (elect_one_sync()) {
+                const uint32_t idw = make_idesc_tf32(64, COUT, false, false);
+                const uint32_t idn = smem_u32(sm + off_ident);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                    for (int i = 0; i < COUT / 8; ++i) {
+                        const uint32_t o = (uint32_t)(2 * i) * (COUT * 16);
+                        mma_tf32(tmem + (uint32_t)(BM_COL + h2 * 64), make_desc((h2 ? a_lo : a_hi) + o, COUT * 16, 128), make_desc(idn + o, COUT * 16, 128), idw, i > 0);
+                    }
+            }
+            __syncwarp();
+            const uint32_t idesc1 = make_idesc_tf32(128, COUT, false, false);
+            const uint32_t ez = smem_u32(sm + off_ezero);
+            const uint64_t dW1h = make_desc(smem_u32(sm + off_w1_hi), COUT * 16, 128), dW1l = make_desc(smem_u32(sm + off_w1_lo), COUT * 16, 128);
+            uint64_t dXh[2], dXl[2], dXh2[2], dXl2[2];
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+                const uint32_t eh = smem_u32(sm + off_et0 + b2 * (2 * E_BYTES)), el = eh + E_BYTES;
+                dXh[b2] = make_desc(eh, TE * 16, 128);
+                dXl[b2] = make_desc(el, TE * 16, 128);
+                dXh2[b2] = make_desc(eh + 4 * (TE * 16), ez - (eh + 4 * (TE * 16)), 128);      // K chunk 4 paired with the shared zero chunk
+                dXl2[b2] = make_desc(el + 4 * (TE * 16), ez - (el + 4 * (TE * 16)), 128);
+            }
             uint64_t dHh[2], dHl[2], dDh[2], dDl[2], dEh[ERING], dEl[ERING];
 #pragma unroll
             for (int b2 = 0; b2 < 2; ++b2) {
@@ -360,26 +416,52 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                 const uint32_t ec = smem_u32(sm + off_e0 + b3 * ESTAGE_BYTES);
                 dEh[b3] = make_desc(ec, TN * 16, 128); dEl[b3] = make_desc(ec + EC_BYTES, TN * 16, 128);
             }
-            int nz = 0, nT = 0;                         // next tile for z, next HALF tile (2 u + h) for T
+            int n1 = 0, nz = 0, nT = 0;                 // next tile for the first layer, for z, next HALF tile (2 u + h) for T
             while (nT < 2 * ntiles) {
                 bool did = false;
+                if (n1 < ntiles) {
+                    const int xb = n1 & 1;
+                    const uint32_t ph1 = ((uint32_t)n1 >> 1) & 1u;
+                    const bool ok = mbar_test(&bar_xfull[xb], ph1) && mbar_test(&bar_d1empty[xb], ph1 ^ 1u);
+                    if (__all_sync(SGB_FULL_MASK, ok)) {
+                        fence_after_sync();
+                        const uint64_t eh = xb ? dXh[1] : dXh[0], el = xb ? dXl[1] : dXl[0], eh2 = xb ? dXh2[1] : dXh2[0], el2 = xb ? dXl2[1] : dXl2[0];
+                        const uint32_t d1 = tmem + (uint32_t)(D1_COL + xb * 64);
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int i = 0; i < KE / 8; ++i) {
+                                const uint64_t dah = i < 2 ? adv(eh, 2 * i * (TE * 16)) : eh2, dal = i < 2 ? adv(el, 2 * i * (TE * 16)) : el2;
+                                const uint64_t dbh = adv(dW1h, 2 * i * (COUT * 16)), dbl = adv(dW1l, 2 * i * (COUT * 16));
+                                mma_tf32(d1, dah, dbh, idesc1, i > 0);
+                                mma_tf32(d1, dal, dbh, idesc1, true);
+                                mma_tf32(d1, dah, dbl, idesc1, true);
+                            }
+                            mma_commit(&bar_d1full[xb]);
+                            mma_commit(&bar_xempty[xb]);
+                        }
+                        __syncwarp();
+                        ++n1;
+                        did = true;
+                    }
+                }
                 if (nz < ntiles) {
+                    // (issuing the 24 z instructions in 4 groups with the other streams polled in between measured SLOWER, 0.72 -> 0.88 ms per
+                    // entry at 150k points, as did a round-robin of the three products in the forward kernel: batches stay whole)
                     const int st = nz & 1;
                     const uint32_t ph = (uint32_t)(nz >> 1) & 1u;
                     const bool ok = mbar_test(&bar_full[st], ph) && mbar_test(&bar_tempty[st], ph ^ 1u);
                     if (__all_sync(SGB_FULL_MASK, ok)) {
                         fence_after_sync();
                         const uint64_t hh = st ? dHh[1] : dHh[0], hl = st ? dHl[1] : dHl[0];
-                        const uint32_t d = tmem + (uint32_t)(st * Z_COL);
+                        const uint32_t d = tmem + (uint32_t)(st * Z_COL), wb = tmem + (uint32_t)BM_COL;
                         if (elect_one_sync()) {
 #pragma unroll
-                            for (int i = 0; i < COUT / 8; ++i) {
-                                const uint64_t dah = adv(dBh, 2 * i * (COUT * 16)), dal = adv(dBl, 2 * i * (COUT * 16));
+                            for (int i = 0; i < COUT / 8; ++i) {                           // A = Bm from TMEM: 8 columns (K) per instruction
                                 const uint64_t dbh = adv(hh, 2 * i * (TE * 16)), dbl = adv(hl, 2 * i * (TE * 16));
-                                mma_tf32(d, dah, dbh, idesc, i > 0);
+                                mma_tf32_ts(d, wb + (uint32_t)(8 * i), dbh, idesc, i > 0);
                                 if (!(SGB_ABL & 4)) {
-                                    mma_tf32(d, dal, dbh, idesc, true);
-                                    mma_tf32(d, dah, dbl, idesc, true);
+                                    mma_tf32_ts(d, wb + (uint32_t)(64 + 8 * i), dbh, idesc, true);
+                                    mma_tf32_ts(d, wb + (uint32_t)(8 * i), dbl, idesc, true);
                                 }
                             }
                             mma_commit(&bar_tfull[st]);
@@ -424,7 +506,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                         did = true;
                     }
                 }
-                if (!did) __nanosleep(32);
+                if (!did) { WAITC(29, __nanosleep(32)); }
             }
         }
         __syncwarp();
@@ -434,6 +516,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         const bool owner = lane < 16;
         const float rc = __ldg(coef + COUT * COUT + c);
         const uint32_t mbyte = (uint32_t)(c >> 2), bit = (uint32_t)(c & 3);
+        const int hp = lane >> 4;
         // T / A0 accumulators of my channel across the CTA's segments: unevaluated fp32 pairs in registers (two-sum), converted to
         // fp64 once at the end (round 2a kept fp64 accumulators in 10 KB of shared memory; DADD is slow on this part)
         float acc_h[ACCN], acc_l[ACCN];
@@ -449,17 +532,19 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
         for (int t = 0; t < ntiles; ++t) {
             const int st = t & 1;
             const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-            mbar_wait(&bar_tfull[st], ph);
+            WAITC(2, mbar_wait(&bar_tfull[st], ph));
             fence_after_sync();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * Z_COL);
             const unsigned char* s_m = sm + off_e0 + (t % ERING) * ESTAGE_BYTES + 2 * EC_BYTES;
+            // An M = 64 accumulator keeps its rows on lanes 0..15 of the quadrant: the .16x32bx2 loads hand the upper half-warp the SECOND
+            // point of a pair (20 columns further) of the same 16 channels, so one pass of the loop body turns a whole half tile into dv1.
 #pragma unroll 1
-            for (int pp = 0; pp < PTS; ++pp) {
-                const int h = pp >> 1;                                  // half of the dv1 tile this point belongs to
-                if ((pp & 1) == 0) mbar_wait(&bar_dvempty[h], ((uint32_t)t & 1u) ^ 1u);      // the T MMAs of tile t - 1 are done with this half
+            for (int h = 0; h < PTS / 2; ++h) {                         // half of the dv1 tile = points 2 h (lanes 0..15) and 2 h + 1 (lanes 16..31)
+                WAITC(3, mbar_wait(&bar_dvempty[h], ((uint32_t)t & 1u) ^ 1u));      // the T MMAs of tile t - 1 are done with this half
+                const int pp = 2 * h + hp;
                 uint32_t v[16], u[4];
-                tmem_ld16_issue(taddr + (uint32_t)(pp * KNN), v);
-                tmem_ld4_issue(taddr + (uint32_t)(pp * KNN + 16), u);
+                tmem_ld16_halves_issue<KNN>(taddr + (uint32_t)(2 * h * KNN), v);
+                tmem_ld4_halves_issue<KNN>(taddr + (uint32_t)(2 * h * KNN + 16), u);
                 tmem_ld_wait();
                 tmem_ld_pin20(v, u);
                 float dv[KNN];
@@ -470,22 +555,18 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
                     const bool posv = (s_m[e * 16 + mbyte] >> bit) & 1u;
                     dv[k] = (rc - z) * (posv ? 1.f : SLOPE);            // padding edges: their EC column is zero, so any finite value is inert
                 }
-                if (owner) {
 #pragma unroll
-                    for (int q = 0; q < ((SGB_ABL & 2) ? 0 : KNN / 4); ++q) {                   // 4 consecutive edges = one 16-byte chunk of row c
-                        const float4 d4 = make_float4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
-                        const float4 hi = make_float4(tf32_hi(d4.x), tf32_hi(d4.y), tf32_hi(d4.z), tf32_hi(d4.w));
-                        const float4 lo = make_float4(tf32_hi(d4.x - hi.x), tf32_hi(d4.y - hi.y), tf32_hi(d4.z - hi.z), tf32_hi(d4.w - hi.w));
-                        const uint32_t o = (uint32_t)(h * 2 * DVH_BYTES) + (uint32_t)((pp & 1) * (KNN / 4) + q) * (COUT * 16);
-                        *reinterpret_cast<float4*>(dv_row + o) = hi;
-                        *reinterpret_cast<float4*>(dv_row + o + DVH_BYTES) = lo;
-                    }
+                for (int q = 0; q < ((SGB_ABL & 2) ? 0 : KNN / 4); ++q) {                   // 4 consecutive edges = one 16-byte chunk of row c
+                    const float4 d4 = make_float4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
+                    const float4 hi = make_float4(tf32_hi(d4.x), tf32_hi(d4.y), tf32_hi(d4.z), tf32_hi(d4.w));
+                    const float4 lo = make_float4(tf32_hi(d4.x - hi.x), tf32_hi(d4.y - hi.y), tf32_hi(d4.z - hi.z), tf32_hi(d4.w - hi.w));
+                    const uint32_t o = (uint32_t)(h * 2 * DVH_BYTES) + (uint32_t)(hp * (KNN / 4) + q) * (COUT * 16);
+                    *reinterpret_cast<float4*>(dv_row + o) = hi;
+                    *reinterpret_cast<float4*>(dv_row + o + DVH_BYTES) = lo;
                 }
-                if (pp & 1) {                                           // half complete: hand it to the tensor cores
-                    fence_async_smem();                                 // generic-proxy writes -> tcgen05.mma operand reads
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_dvfull[h]);
-                }
+                fence_async_smem();                                     // generic-proxy writes -> tcgen05.mma operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_dvfull[h]);              // half complete: hand it to the tensor cores
             }
             fence_before_sync();
             __syncwarp();
@@ -493,7 +574,7 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             if ((t + 1) % FLUSH == 0 || t == ntiles - 1) {
                 // flush the finished T segment into the fp64 accumulators (thread = accumulator row)
                 const int seg = t / FLUSH, gb = seg & 1;
-                mbar_wait(&bar_gfull[gb], (uint32_t)(seg >> 1) & 1u);
+                WAITC(4, mbar_wait(&bar_gfull[gb], (uint32_t)(seg >> 1) & 1u));
                 fence_after_sync();
                 const uint32_t gaddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(T_COL0 + gb * T_COLS);
                 float g16[16], g4a[4], g4b[4];
@@ -524,6 +605,9 @@ ec2_bwd_tc_kernel(const float* __restrict__ x12, const int* __restrict__ knn, in
             dst[1] = (double)stats1[64 + c] * dot;
         }
     }
+#ifdef SGB_ROLE_CLOCKS
+    if (blockIdx.x == 3 && lane == 0) { const long long tot = clock64() - tstart; for (int i = 0; i < 32; ++i) if (wclk[i]) printf("bwd warp %2d wait %2d : %6.1f%%  (total %lld clk, %d tiles)\n", warp, i, 100.0 * wclk[i] / tot, tot, ntiles); }
+#endif
     fence_before_sync();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
