@@ -21,6 +21,11 @@ def step():
         if mode == "train":
             pipeline.batch_loss(r.loss_raw).backward()
     return r
+if os.environ.get("SGB_PROFILE_FAST"):       # under `ncu --set full` (tools/gpu_final.sh): one warm-up step, one step to capture, nothing else
+    r = step(); torch.cuda.synchronize()
+    r = step(); torch.cuda.synchronize()
+    print("levels", [L.S for L in r.levels])
+    sys.exit(0)
 for _ in range(2): r = step()
 torch.cuda.synchronize()
 t = time.time()
@@ -40,6 +45,8 @@ for e in ev:
 print("torch profiler: %d device activities, %.3f ms summed" % (len(ev), tot_k / 1e3))
 # idle gaps of the device between consecutive activities, attributed to the activity that FOLLOWS the gap
 evs = sorted(ev, key=lambda e: e.time_range.start)
+if not evs:                                   # another profiler owns the device (ncu): no activity records
+    sys.exit(0)
 gaps = {}
 t_end = evs[0].time_range.end
 total_gap = 0.0
