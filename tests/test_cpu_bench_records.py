@@ -23,7 +23,7 @@ def test_roofline_record_is_the_current_forward_kernel():
     b = _bench()
     rec = b.ncu_record("ec2_tc1_kernel<1, 1>") or b.ncu_record("ec2_tc1_kernel<true, true>")
     assert rec is not None, "no committed ncu summary names the dominant kernel: roofline.traffic would be null"
-    assert rec["source"].startswith("profiles/r03") and rec["dram_bytes"] > 0 and rec["points"] == 150000
+    assert rec["source"] >= "profiles/r03" and rec["dram_bytes"] > 0 and rec["points"] == 150000      # this round's capture or a later one
     # algorithmic bytes of the kernel (436 B per point) against the measured DRAM traffic: no wasted re-reads
     assert rec["dram_bytes"] < 1.1 * 436 * rec["points"]
     for key in ("ec2_bwd_tc_kernel", "segment_pool_staged_kernel", "knn_sweep_kernel", "centralize_kernel", "export_labels_kernel"):
