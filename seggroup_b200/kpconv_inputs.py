@@ -24,8 +24,11 @@ I32 = torch.int32
 
 def get_batch_inds(stacks_len):
     """common.py:386-430: [3, 2, 5] -> [0, 0, 0, 1, 1, 2, 2, 2, 2, 2] (int32, device of stacks_len)."""
-    n = stacks_len.numel()
-    return torch.repeat_interleave(torch.arange(n, dtype=I32, device=stacks_len.device), stacks_len.long())
+    # element e belongs to the batch entry whose end is the first one > e: a parallel binary search (torch.repeat_interleave builds the
+    # same vector with one thread block — 300 us per million points, profiles/r03z_launches_bench.md)
+    ends = torch.cumsum(stacks_len.long(), 0)
+    total = int(ends[-1]) if ends.numel() else 0
+    return torch.bucketize(torch.arange(total, device=stacks_len.device), ends, right=True).to(I32)
 
 
 def stack_batch_inds(stacks_len):

@@ -71,12 +71,17 @@ class SceneDevice:
         # a [B] vector) instead of an addition per scene and array: ~20 launches instead of ~45 for 8 scenes
         counts = [[sc.seg_off.numel() - 1 for sc in scenes], [sc.seg_members.numel() for sc in scenes], [sc.adj0.shape[0] for sc in scenes],
                   [sc.unmap.numel() if sc.unmap is not None else sc.n_points for sc in scenes]]
-        meta = torch.tensor(counts + [pt[:-1]], dtype=torch.int64).to(dev, non_blocking=True)       # one small upload
+        ends = [np.cumsum(c).tolist() for c in counts]
+        meta = torch.tensor(ends + [pt[:-1]], dtype=torch.int64).to(dev, non_blocking=True)         # one small upload
         base = meta[4]
 
         def shifted(parts, row, width=1):
+            # scene of element e = number of scene ends <= e (a binary search per element over B boundaries: fully parallel).
+            # torch.repeat_interleave(base, counts) builds the same vector with ONE thread block: 150-300 us per 1.2 M-element id array
+            # (`compute_cuda_kernel<long>`, 1.8 % of the device time in profiles/r03z_launches_bench.md).
             v = cat(parts)
-            off = torch.repeat_interleave(base, meta[row], output_size=sum(counts[row]))
+            n = v.shape[0]
+            off = base[torch.bucketize(_arange(n, dev), meta[row], right=True)]
             return v.add_(off.to(v.dtype) if width == 1 else off.to(v.dtype).unsqueeze(1))
 
         seg_off = cat([scenes[0].seg_off[:1], shifted([sc.seg_off[1:] for sc in scenes], 0)])
@@ -97,6 +102,17 @@ class SceneDevice:
                            seg_off=t(scene.seg_offsets, I32), seg_members=t(scene.seg_members, I32),
                            adj0=t(scene.adj, I32), unmap=t(scene.unmap, torch.int64),
                            real_label=t(scene.real_label, torch.int64), name=scene.name)
+
+
+_arange_cache = {}
+
+
+def _arange(n, dev):
+    """[0, n) int64 on `dev`, cached by the largest size asked for (batch assembly asks for the same few sizes every step)."""
+    t = _arange_cache.get(str(dev))
+    if t is None or t.numel() < n:
+        t = _arange_cache[str(dev)] = torch.arange(n, dtype=torch.int64, device=dev)
+    return t[:n]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -56,3 +56,14 @@ def test_scene_batch_concat_offsets():
     assert torch.equal(b.seg_off, torch.cat([sd[0].seg_off[:1]] + [s.seg_off[1:] + pt[i] for i, s in enumerate(sd)]))
     assert b.split.pt_off == pt and b.n_scenes == 3
     assert all(torch.equal(a, s.seg_members) for a, s in zip(keep, sd))
+
+
+def test_batch_index_vectors_without_repeat_interleave():
+    """kpconv_inputs.get_batch_inds (common.py:386-430) and the offset vectors of SceneDevice.concat come from a parallel binary search
+    over the batch boundaries; equal to torch.repeat_interleave, empty batch entries included."""
+    from seggroup_b200.kpconv_inputs import get_batch_inds
+    for lens in ([3, 2, 5], [0, 4, 0, 0, 7, 1], [5], [0], [1, 1, 1, 1]):
+        t = torch.tensor(lens, dtype=torch.int32)
+        ref = torch.repeat_interleave(torch.arange(len(lens), dtype=torch.int32), t.long())
+        got = get_batch_inds(t)
+        assert torch.equal(ref, got) and got.dtype == torch.int32, lens
